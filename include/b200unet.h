@@ -1,0 +1,217 @@
+/*
+ * b200unet.h — C ABI of libb200unet.so: the sm_100a (B200) kernels behind the U-Net hot path of
+ * a-green-hand-jack/mdeical_image_segmentation (2D/3D encoder-decoder forward + backward, Dice/IoU
+ * losses and metrics).
+ *
+ * The reference has no FFI of its own: every entry point below replaces a stock-PyTorch call site
+ * of the reference (cited per function as file:line relative to the reference root). Host code
+ * (mdeical_image_segmentation_b200/_lib.py) binds these with ctypes; see INTEGRATION.md.
+ *
+ * Conventions
+ *   - activations are channels-last bf16: (N, D, H, W, C) with D = 1 for 2D; a tensor may be a
+ *     channel slice of a wider buffer, described by (ctot = channel stride, coff = first channel);
+ *   - parameters and their gradients are fp32 in the reference's own layouts (OIDHW, IODHW);
+ *   - every buffer is caller-owned device memory; nothing is allocated, freed or retained;
+ *   - all work is enqueued on the caller's stream, asynchronously, with no device sync;
+ *   - return 0 on success, negative b200 error codes or a positive cudaError_t; no exceptions.
+ */
+#ifndef B200UNET_H
+#define B200UNET_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* b200_stream_t; /* cudaStream_t */
+
+#define B200_IMPL_AUTO 0
+#define B200_IMPL_TCGEN05 1
+#define B200_IMPL_DIRECT 2
+
+int b200_version(void);
+const char* b200_strerror(int code);
+/* last tcgen05/direct decision taken by a conv-like entry point on this thread (1 or 2) */
+int b200_last_impl(void);
+
+/* ---- 3x3 / 3x3x3 / 1x1 "same" convolution ------------------------------------------------------
+ * replaces nn.Conv2d  model/unet2d/layers.py:20,122,125 and nn.Conv3d/2d
+ * model/unet3d/buildingblocks.py:63-70 (and their autograd backward). */
+typedef struct b200_conv_desc {
+  int32_t n, d, h, w;          /* positions; d = 1 for 2D                                  */
+  int32_t c_in, c_out;
+  int32_t kd, kh, kw;          /* each 1 or 3; zero padding k/2, stride 1, dilation 1      */
+  int32_t in_ctot, in_coff;    /* layout of x / dx                                        */
+  int32_t out_ctot, out_coff;  /* layout of y / dy                                        */
+  int32_t relu;                /* fwd epilogue: y = max(conv + bias, 0)                   */
+  int32_t impl;                /* B200_IMPL_*                                             */
+} b200_conv_desc;
+
+/* w: fp32 (c_out, c_in, kd, kh, kw)  ->  wp_fwd bf16 [tap][c_out][c_in],
+ * wp_bwd bf16 [flipped tap][c_in][c_out]  (either output may be NULL). */
+int b200_conv_repack_weight(const b200_conv_desc* desc, const float* w, void* wp_fwd, void* wp_bwd,
+                            b200_stream_t stream);
+int b200_conv_fwd(const b200_conv_desc* desc, const void* x, const void* wp_fwd, const float* bias,
+                  void* y, b200_stream_t stream);
+/* dx = conv_transpose(dy); if relu_mask != NULL (same layout as dx) dx is zeroed where mask <= 0 */
+int b200_conv_bwd_data(const b200_conv_desc* desc, const void* dy, const void* wp_bwd,
+                       const void* relu_mask, void* dx, b200_stream_t stream);
+/* dw fp32 (c_out, c_in, kd, kh, kw) is ACCUMULATED into (caller zeroes it) */
+int b200_conv_bwd_weight(const b200_conv_desc* desc, const void* x, const void* dy, float* dw,
+                         b200_stream_t stream);
+
+/* ---- ConvTranspose2d(kernel 2, stride 2) -------------------------------------------------------
+ * replaces nn.ConvTranspose2d  model/unet2d/layers.py:165. x: (n,1,h,w,c_in) -> y: (n,1,2h,2w,c_out) */
+typedef struct b200_convt_desc {
+  int32_t n, h, w;
+  int32_t c_in, c_out;
+  int32_t in_ctot, in_coff;
+  int32_t out_ctot, out_coff;
+  int32_t impl;
+} b200_convt_desc;
+/* w fp32 (c_in, c_out, 2, 2) -> wp_fwd bf16 [4*c_out][c_in] (row = (i*2+j)*c_out + co),
+ * wp_bwd bf16 [4][c_in][c_out] */
+int b200_convt2x2_repack_weight(const b200_convt_desc* desc, const float* w, void* wp_fwd,
+                                void* wp_bwd, b200_stream_t stream);
+int b200_convt2x2_fwd(const b200_convt_desc* desc, const void* x, const void* wp_fwd,
+                      const float* bias, void* y, b200_stream_t stream);
+int b200_convt2x2_bwd_data(const b200_convt_desc* desc, const void* dy, const void* wp_bwd,
+                           const void* relu_mask, void* dx, b200_stream_t stream);
+int b200_convt2x2_bwd_weight(const b200_convt_desc* desc, const void* x, const void* dy, float* dw,
+                             b200_stream_t stream);
+
+/* ---- ConvTranspose(kernel 3, stride 2, padding 1, no bias) + nearest resize to 2x ----------------
+ * replaces TransposeConvUpsampling.Upsample.forward  model/unet3d/buildingblocks.py:699-703
+ * (conv_transposed then F.interpolate(size=2*in)). x: (n,d,h,w,c_in) -> y: (n,od,oh,ow,c_out)
+ * where each o* is the skip's size (2*in here); d = od = 1 for the 2D variant. */
+typedef struct b200_deconv_desc {
+  int32_t n, d, h, w;
+  int32_t od, oh, ow;
+  int32_t c_in, c_out;
+  int32_t in_ctot, in_coff;
+  int32_t out_ctot, out_coff;
+} b200_deconv_desc;
+/* w fp32 (c_in, c_out, kd, 3, 3) -> wp bf16 [tap][c_in][c_out] */
+int b200_deconv3s2_repack_weight(const b200_deconv_desc* desc, const float* w, void* wp,
+                                 b200_stream_t stream);
+int b200_deconv3s2_fwd(const b200_deconv_desc* desc, const void* x, const void* wp, void* y,
+                       b200_stream_t stream);
+int b200_deconv3s2_bwd_data(const b200_deconv_desc* desc, const void* dy, const void* wp, void* dx,
+                            b200_stream_t stream);
+int b200_deconv3s2_bwd_weight(const b200_deconv_desc* desc, const void* x, const void* dy,
+                              float* dw, b200_stream_t stream);
+
+/* ---- memory-bound tensor ops -------------------------------------------------------------------
+ * A "view" is a channels-last bf16 tensor slice. */
+typedef struct b200_view {
+  void* ptr;      /* base of the wider buffer */
+  int32_t ctot;   /* channel stride           */
+  int32_t coff;   /* first channel            */
+} b200_view;
+
+/* MaxPool(kernel 2, stride 2, floor) — nn.MaxPool2d layers.py:147; nn.MaxPool3d/2d
+ * buildingblocks.py:409-413. pool_d = 1 keeps D (2D pooling). */
+int b200_maxpool2_fwd(int32_t n, int32_t d, int32_t h, int32_t w, int32_t c, int32_t pool_d,
+                      b200_view x, b200_view y, b200_stream_t stream);
+/* dx fully written; ties go to the first maximum in (d,h,w) scan order, as ATen does */
+int b200_maxpool2_bwd(int32_t n, int32_t d, int32_t h, int32_t w, int32_t c, int32_t pool_d,
+                      b200_view x, b200_view dy, b200_view dx, b200_stream_t stream);
+/* F.interpolate(mode='nearest') buildingblocks.py:671-673: src = floor(dst * in / out) */
+int b200_upsample_nearest_fwd(int32_t n, int32_t id, int32_t ih, int32_t iw, int32_t od,
+                              int32_t oh, int32_t ow, int32_t c, b200_view x, b200_view y,
+                              b200_stream_t stream);
+int b200_upsample_nearest_bwd(int32_t n, int32_t id, int32_t ih, int32_t iw, int32_t od,
+                              int32_t oh, int32_t ow, int32_t c, b200_view dy, b200_view dx,
+                              b200_stream_t stream);
+/* torch.cat halves — layers.py:188, buildingblocks.py:547: copy c channels of npos positions */
+int b200_copy_channels(int64_t npos, int32_t c, b200_view src, b200_view dst, b200_stream_t stream);
+/* dz = dy * (a > 0) (ReLU backward), optionally db[c] += sum_pos dz (conv bias gradient) */
+int b200_relu_bwd(int64_t npos, int32_t c, b200_view dy, b200_view a, b200_view dz, float* db,
+                  b200_stream_t stream);
+/* db[c] += sum_pos dy */
+int b200_bias_grad(int64_t npos, int32_t c, b200_view dy, float* db, b200_stream_t stream);
+/* layout / precision boundary: fp32 NC(spatial) <-> bf16 channels-last */
+int b200_nchw_f32_to_cl_bf16(int32_t n, int32_t c, int64_t spatial, const float* src, b200_view dst,
+                             b200_stream_t stream);
+int b200_cl_bf16_to_nchw_f32(int32_t n, int32_t c, int64_t spatial, b200_view src, float* dst,
+                             b200_stream_t stream);
+
+/* ---- GroupNorm (nn.GroupNorm, buildingblocks.py:73-92), eps 1e-5, affine per channel ------------ */
+/* stats: fp32 [n][groups][2] = (mean, rstd) over (c/groups x spatial);
+ * sums: fp64 [n][2][c] scratch, zeroed by the caller */
+int b200_gn_stats(int32_t n, int64_t spatial, int32_t c, int32_t groups, float eps, b200_view x,
+                  double* sums, float* stats, b200_stream_t stream);
+int b200_gn_apply(int32_t n, int64_t spatial, int32_t c, int32_t groups, b200_view x,
+                  const float* stats, const float* gamma, const float* beta, int32_t relu,
+                  b200_view y, b200_stream_t stream);
+/* dgamma/dbeta fp32 [c] accumulated into (either may be NULL);
+ * scratch fp32 [n][2][c] + [n][groups][2], zeroed by the caller */
+int b200_gn_bwd(int32_t n, int64_t spatial, int32_t c, int32_t groups, b200_view x,
+                const float* stats, const float* gamma, b200_view dy, b200_view dx, float* dgamma,
+                float* dbeta, float* scratch, b200_stream_t stream);
+
+/* ---- BatchNorm (nn.BatchNorm2d/3d, layers.py:21, buildingblocks.py:93-103) ---------------------- */
+/* sums: fp64 [2][c] = (sum x, sum x^2) accumulated into (caller zeroes) */
+int b200_bn_stats(int64_t npos, int32_t c, b200_view x, double* sums, b200_stream_t stream);
+/* y = (x - mean) * rstd * gamma + beta, optional ReLU; mean/rstd fp32 [c] */
+int b200_bn_apply(int64_t npos, int32_t c, b200_view x, const float* mean, const float* rstd,
+                  const float* gamma, const float* beta, int32_t relu, b200_view y,
+                  b200_stream_t stream);
+/* pass 1: red fp32 [2][c] += (sum dz, sum dz * xhat) with dz = dy * (y > 0 if relu_out given) */
+int b200_bn_bwd_reduce(int64_t npos, int32_t c, b200_view x, b200_view dy, b200_view relu_out,
+                       const float* mean, const float* rstd, float* red, b200_stream_t stream);
+/* pass 2: dx = gamma * rstd * (dz - red0/M - xhat * red1/M) */
+int b200_bn_bwd_apply(int64_t npos, int32_t c, b200_view x, b200_view dy, b200_view relu_out,
+                      const float* mean, const float* rstd, const float* gamma, const float* red,
+                      b200_view dx, b200_stream_t stream);
+
+/* ---- 1x1 head (nn.Conv2d(64,C,1) unet.py:89; nn.Conv3d(f0,C,1) model.py:110-113) ---------------- */
+/* logits fp32 (n, c_out, spatial) = x (n, spatial, c_in) . w^T + b;  w fp32 [c_out][c_in] */
+int b200_head_fwd(int32_t n, int64_t spatial, int32_t c_in, int32_t c_out, b200_view x,
+                  const float* w, const float* b, float* logits, b200_stream_t stream);
+/* dx bf16, dw fp32 [c_out][c_in] and db fp32 [c_out] accumulated into */
+int b200_head_bwd(int32_t n, int64_t spatial, int32_t c_in, int32_t c_out, b200_view x,
+                  const float* w, const float* dlogits, b200_view dx, float* dw, float* db,
+                  b200_stream_t stream);
+
+/* ---- losses ------------------------------------------------------------------------------------
+ * One pass over fp32 logits (n, c, spatial) and a same-shape fp32 target produces the per-channel
+ * sums every loss of the path needs:  sums[c][6] (fp64) =
+ *   { sum p*t, sum p*p, sum t*t, sum p, sum t, sum bce(x,t) }  with p = sigmoid(x).
+ * Serves compute_per_channel_dice / DiceLoss / BCEDiceLoss (model/unet3d/losses.py:7-33,119-129,
+ * 167-178), nn.BCEWithLogitsLoss (model/unet2d/unet.py:1184-1188), IoULoss / F1Loss
+ * (model/unet2d/loss.py:32-57) and DiceCoefficient (model/unet3d/metrics.py:15-29).
+ * normalization: 0 = sigmoid, 1 = none (input already a probability; bce column is then 0). */
+int b200_seg_sums(int32_t n, int32_t c, int64_t spatial, const float* logits, const float* target,
+                  int32_t normalization, double* sums, b200_stream_t stream);
+/* dlogits = ka*(p - t) + p*(1-p) * (k1[c]*t + k2[c]*p + k3[c]);  coef fp32 [c][4] = (ka,k1,k2,k3),
+ * all read from device memory so no host sync is needed. */
+int b200_seg_loss_bwd(int32_t n, int32_t c, int64_t spatial, const float* logits,
+                      const float* target, const float* coef, float* dlogits, b200_stream_t stream);
+/* nn.CrossEntropyLoss() (unet.py:1185): nll_sum (fp64 [1]) += sum_pos -log softmax(x)[label] */
+int b200_ce_fwd(int32_t n, int32_t c, int64_t spatial, const float* logits, const int64_t* labels,
+                double* nll_sum, b200_stream_t stream);
+/* dlogits = scale[0] * (softmax(x) - onehot(label)) */
+int b200_ce_bwd(int32_t n, int32_t c, int64_t spatial, const float* logits, const int64_t* labels,
+                const float* scale, float* dlogits, b200_stream_t stream);
+
+/* ---- metrics -----------------------------------------------------------------------------------
+ * trainer/metrcis.py:61-109,153-168: p = 1/(1+exp(-x)+1e-6); psum (fp64 [1]) += sum p */
+int b200_metric_prob_sum(int64_t numel, const float* logits, double* psum, b200_stream_t stream);
+/* counts fp64 [n][3] += per-sample { |P & L|, |P|, |L| } with P = p > thr[0], L = label > thr[0].
+ * mode 0: p = 1/(1+exp(-x)+1e-6) (compute_metrics); mode 1: p = sigmoid(x) (iou_score);
+ * mode 2: p = x (already a probability map: compute_iou/compute_dice, MeanIoU C=1).
+ * thr is read from device memory. */
+int b200_metric_counts(int32_t n, int64_t per_sample, const float* logits, const float* labels,
+                       const float* thr, int32_t mode, double* counts, b200_stream_t stream);
+/* MeanIoU multi-class (model/unet3d/metrics.py:45-104): one-hot argmax over c of x (n,c,spatial)
+ * against target (n,c,spatial); counts fp64 [n][c][2] += { |P & T|, |P | T| } */
+int b200_metric_argmax_counts(int32_t n, int32_t c, int64_t spatial, const float* x,
+                              const float* target, double* counts, b200_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200UNET_H */

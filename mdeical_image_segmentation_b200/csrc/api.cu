@@ -1,0 +1,287 @@
+// extern "C" entry points for the convolution family: weight repacking and the dispatch between the
+// tcgen05 implicit-GEMM kernels (conv_tc.cu) and the CUDA-core kernels (conv_direct.cu).
+#include "../../include/b200unet.h"
+#include "conv_tc.cuh"
+
+namespace b200 {
+int direct_gemm_conv(const TcGemmProblem& p, cudaStream_t stream);
+int direct_wgrad(const TcWgradProblem& p, cudaStream_t stream);
+struct DeconvArgs {
+  const bf16* x; int n, d, h, w, c_in, in_ctot, in_coff;
+  bf16* y; int od, oh, ow, c_out, out_ctot, out_coff;
+  const bf16* wp;
+  int kd;
+};
+int deconv_fwd(const DeconvArgs& a, cudaStream_t s);
+int deconv_bwd_data(const DeconvArgs& a, cudaStream_t s);
+int deconv_bwd_weight(const DeconvArgs& a, float* dw, cudaStream_t s);
+
+static thread_local int g_last_impl = 0;
+
+// w (c_out, c_in, taps) fp32 -> fwd [tap][c_out][c_in], bwd [ntaps-1-tap][c_in][c_out]
+__global__ void conv_repack_kernel(int c_out, int c_in, int ntaps, const float* w, bf16* fwd, bf16* bwd) {
+  const long total = (long)c_out * c_in * ntaps;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int tap = (int)(i % ntaps);
+    const int ci = (int)((i / ntaps) % c_in);
+    const int co = (int)(i / ((long)ntaps * c_in));
+    const bf16 v = __float2bfloat16(w[i]);
+    if (fwd) fwd[((long)tap * c_out + co) * c_in + ci] = v;
+    if (bwd) bwd[((long)(ntaps - 1 - tap) * c_in + ci) * c_out + co] = v;
+  }
+}
+// w (c_in, c_out, 2, 2) fp32 -> fwd [(ij)*c_out + co][c_in], bwd [ij][c_in][c_out]
+__global__ void convt_repack_kernel(int c_in, int c_out, const float* w, bf16* fwd, bf16* bwd) {
+  const long total = (long)c_in * c_out * 4;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int ij = (int)(i % 4);
+    const int co = (int)((i / 4) % c_out);
+    const int ci = (int)(i / (4L * c_out));
+    const bf16 v = __float2bfloat16(w[i]);
+    if (fwd) fwd[((long)ij * c_out + co) * c_in + ci] = v;
+    if (bwd) bwd[((long)ij * c_in + ci) * c_out + co] = v;
+  }
+}
+// w (c_in, c_out, taps) fp32 -> [tap][c_in][c_out]
+__global__ void deconv_repack_kernel(int c_in, int c_out, int ntaps, const float* w, bf16* wp) {
+  const long total = (long)c_in * c_out * ntaps;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int tap = (int)(i % ntaps);
+    const int co = (int)((i / ntaps) % c_out);
+    const int ci = (int)(i / ((long)ntaps * c_out));
+    wp[((long)tap * c_in + ci) * c_out + co] = __float2bfloat16(w[i]);
+  }
+}
+
+static int check_conv(const b200_conv_desc* d) {
+  if (!d) return B200_ERR_BAD_ARG;
+  if (d->n <= 0 || d->d <= 0 || d->h <= 0 || d->w <= 0 || d->c_in <= 0 || d->c_out <= 0)
+    return B200_ERR_BAD_ARG;
+  const int ks[3] = {d->kd, d->kh, d->kw};
+  for (int k : ks)
+    if (k != 1 && k != 3) return B200_ERR_UNSUPPORTED;
+  if (d->in_coff < 0 || d->in_coff + d->c_in > d->in_ctot) return B200_ERR_BAD_ARG;
+  if (d->out_coff < 0 || d->out_coff + d->c_out > d->out_ctot) return B200_ERR_BAD_ARG;
+  return B200_OK;
+}
+static unsigned grid_for(long total) {
+  long b = (total + 255) / 256;
+  return (unsigned)(b > 148L * 8 ? 148L * 8 : (b < 1 ? 1 : b));
+}
+
+static int run_gemm(const TcGemmProblem& p, int impl, cudaStream_t s) {
+  const bool tc_ok = tc_gemm_supported(p);
+  if (impl == B200_IMPL_TCGEN05 && !tc_ok) return B200_ERR_UNSUPPORTED;
+  if (impl == B200_IMPL_DIRECT || !tc_ok) {
+    g_last_impl = B200_IMPL_DIRECT;
+    return direct_gemm_conv(p, s);
+  }
+  g_last_impl = B200_IMPL_TCGEN05;
+  return tc_gemm_conv(p, s);
+}
+static int run_wgrad(const TcWgradProblem& p, int impl, cudaStream_t s) {
+  const bool tc_ok = tc_wgrad_supported(p);
+  if (impl == B200_IMPL_TCGEN05 && !tc_ok) return B200_ERR_UNSUPPORTED;
+  if (impl == B200_IMPL_DIRECT || !tc_ok) {
+    g_last_impl = B200_IMPL_DIRECT;
+    return direct_wgrad(p, s);
+  }
+  g_last_impl = B200_IMPL_TCGEN05;
+  return tc_wgrad(p, s);
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" {
+
+int b200_version(void) { return 100; }
+
+const char* b200_strerror(int code) {
+  switch (code) {
+    case B200_OK: return "success";
+    case B200_ERR_BAD_ARG: return "b200: bad argument";
+    case B200_ERR_UNSUPPORTED: return "b200: unsupported shape, alignment or kernel size";
+    case B200_ERR_WORKSPACE: return "b200: workspace too small";
+    case B200_ERR_ARCH: return "b200: device is not sm_100";
+    case B200_ERR_DRIVER: return "b200: cuTensorMapEncodeTiled unavailable or failed";
+    default: break;
+  }
+  if (code > 0) return cudaGetErrorString((cudaError_t)code);
+  return "b200: unknown error";
+}
+
+int b200_last_impl(void) { return g_last_impl; }
+
+int b200_conv_repack_weight(const b200_conv_desc* d, const float* w, void* wp_fwd, void* wp_bwd,
+                            b200_stream_t stream) {
+  int rc = check_conv(d);
+  if (rc) return rc;
+  const int ntaps = d->kd * d->kh * d->kw;
+  const long total = (long)d->c_out * d->c_in * ntaps;
+  conv_repack_kernel<<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(d->c_out, d->c_in, ntaps, w,
+                                                                        (bf16*)wp_fwd, (bf16*)wp_bwd);
+  B200_LAUNCH_CHECK();
+  return B200_OK;
+}
+
+int b200_conv_fwd(const b200_conv_desc* d, const void* x, const void* wp_fwd, const float* bias,
+                  void* y, b200_stream_t stream) {
+  int rc = check_conv(d);
+  if (rc) return rc;
+  TcGemmProblem p{};
+  p.a = ActView{(const bf16*)x, d->n, d->d, d->h, d->w, d->c_in, d->in_ctot, d->in_coff};
+  p.wp = (const bf16*)wp_fwd;
+  p.ncols = d->c_out; p.kdim = d->c_in;
+  p.kd = d->kd; p.kh = d->kh; p.kw = d->kw;
+  p.tap_mode = TC_TAP_SHIFT; p.out_mode = TC_OUT_CONV;
+  p.pn = d->n; p.pd = d->d; p.ph = d->h; p.pw = d->w;
+  p.out = (bf16*)y; p.out_ctot = d->out_ctot; p.out_coff = d->out_coff;
+  p.bias = bias; p.relu = d->relu;
+  return run_gemm(p, d->impl, (cudaStream_t)stream);
+}
+
+int b200_conv_bwd_data(const b200_conv_desc* d, const void* dy, const void* wp_bwd,
+                       const void* relu_mask, void* dx, b200_stream_t stream) {
+  int rc = check_conv(d);
+  if (rc) return rc;
+  TcGemmProblem p{};
+  p.a = ActView{(const bf16*)dy, d->n, d->d, d->h, d->w, d->c_out, d->out_ctot, d->out_coff};
+  p.wp = (const bf16*)wp_bwd;
+  p.ncols = d->c_in; p.kdim = d->c_out;
+  p.kd = d->kd; p.kh = d->kh; p.kw = d->kw;
+  p.tap_mode = TC_TAP_SHIFT; p.out_mode = TC_OUT_CONV;
+  p.pn = d->n; p.pd = d->d; p.ph = d->h; p.pw = d->w;
+  p.out = (bf16*)dx; p.out_ctot = d->in_ctot; p.out_coff = d->in_coff;
+  p.mask = (const bf16*)relu_mask; p.mask_ctot = d->in_ctot; p.mask_coff = d->in_coff;
+  return run_gemm(p, d->impl, (cudaStream_t)stream);
+}
+
+int b200_conv_bwd_weight(const b200_conv_desc* d, const void* x, const void* dy, float* dw,
+                         b200_stream_t stream) {
+  int rc = check_conv(d);
+  if (rc) return rc;
+  TcWgradProblem p{};
+  p.mop = ActView{(const bf16*)dy, d->n, d->d, d->h, d->w, d->c_out, d->out_ctot, d->out_coff};
+  p.nop = ActView{(const bf16*)x, d->n, d->d, d->h, d->w, d->c_in, d->in_ctot, d->in_coff};
+  p.kd = d->kd; p.kh = d->kh; p.kw = d->kw;
+  p.tap_mode = TC_TAP_SHIFT;
+  p.pn = d->n; p.pd = d->d; p.ph = d->h; p.pw = d->w;
+  p.dw = dw;
+  const int ntaps = d->kd * d->kh * d->kw;
+  p.s_m = (long)d->c_in * ntaps; p.s_n = ntaps;
+  return run_wgrad(p, d->impl, (cudaStream_t)stream);
+}
+
+// ---- ConvTranspose2d k2 s2
+static int check_convt(const b200_convt_desc* d) {
+  if (!d || d->n <= 0 || d->h <= 0 || d->w <= 0 || d->c_in <= 0 || d->c_out <= 0) return B200_ERR_BAD_ARG;
+  if (d->in_coff < 0 || d->in_coff + d->c_in > d->in_ctot) return B200_ERR_BAD_ARG;
+  if (d->out_coff < 0 || d->out_coff + d->c_out > d->out_ctot) return B200_ERR_BAD_ARG;
+  return B200_OK;
+}
+int b200_convt2x2_repack_weight(const b200_convt_desc* d, const float* w, void* wp_fwd, void* wp_bwd,
+                                b200_stream_t stream) {
+  int rc = check_convt(d);
+  if (rc) return rc;
+  convt_repack_kernel<<<grid_for((long)d->c_in * d->c_out * 4), 256, 0, (cudaStream_t)stream>>>(
+      d->c_in, d->c_out, w, (bf16*)wp_fwd, (bf16*)wp_bwd);
+  B200_LAUNCH_CHECK();
+  return B200_OK;
+}
+int b200_convt2x2_fwd(const b200_convt_desc* d, const void* x, const void* wp_fwd, const float* bias,
+                      void* y, b200_stream_t stream) {
+  int rc = check_convt(d);
+  if (rc) return rc;
+  TcGemmProblem p{};
+  p.a = ActView{(const bf16*)x, d->n, 1, d->h, d->w, d->c_in, d->in_ctot, d->in_coff};
+  p.wp = (const bf16*)wp_fwd;
+  p.ncols = 4 * d->c_out; p.kdim = d->c_in;
+  p.kd = p.kh = p.kw = 1;
+  p.tap_mode = TC_TAP_SHIFT; p.out_mode = TC_OUT_K2S2_SCATTER;
+  p.pn = d->n; p.pd = 1; p.ph = d->h; p.pw = d->w;
+  p.out = (bf16*)y; p.out_ctot = d->out_ctot; p.out_coff = d->out_coff; p.cout_t = d->c_out;
+  p.bias = bias;
+  return run_gemm(p, d->impl, (cudaStream_t)stream);
+}
+int b200_convt2x2_bwd_data(const b200_convt_desc* d, const void* dy, const void* wp_bwd,
+                           const void* relu_mask, void* dx, b200_stream_t stream) {
+  int rc = check_convt(d);
+  if (rc) return rc;
+  TcGemmProblem p{};
+  p.a = ActView{(const bf16*)dy, d->n, 1, 2 * d->h, 2 * d->w, d->c_out, d->out_ctot, d->out_coff};
+  p.wp = (const bf16*)wp_bwd;
+  p.ncols = d->c_in; p.kdim = d->c_out;
+  p.kd = 1; p.kh = 2; p.kw = 2;
+  p.tap_mode = TC_TAP_K2S2; p.out_mode = TC_OUT_CONV;
+  p.pn = d->n; p.pd = 1; p.ph = d->h; p.pw = d->w;
+  p.out = (bf16*)dx; p.out_ctot = d->in_ctot; p.out_coff = d->in_coff;
+  p.mask = (const bf16*)relu_mask; p.mask_ctot = d->in_ctot; p.mask_coff = d->in_coff;
+  return run_gemm(p, d->impl, (cudaStream_t)stream);
+}
+int b200_convt2x2_bwd_weight(const b200_convt_desc* d, const void* x, const void* dy, float* dw,
+                             b200_stream_t stream) {
+  int rc = check_convt(d);
+  if (rc) return rc;
+  TcWgradProblem p{};
+  p.mop = ActView{(const bf16*)x, d->n, 1, d->h, d->w, d->c_in, d->in_ctot, d->in_coff};
+  p.nop = ActView{(const bf16*)dy, d->n, 1, 2 * d->h, 2 * d->w, d->c_out, d->out_ctot, d->out_coff};
+  p.kd = 1; p.kh = 2; p.kw = 2;
+  p.tap_mode = TC_TAP_K2S2;
+  p.pn = d->n; p.pd = 1; p.ph = d->h; p.pw = d->w;
+  p.dw = dw;
+  p.s_m = (long)d->c_out * 4; p.s_n = 4;  // dw (c_in, c_out, 2, 2)
+  return run_wgrad(p, d->impl, (cudaStream_t)stream);
+}
+
+// ---- ConvTranspose k3 s2 p1
+static int check_deconv(const b200_deconv_desc* d) {
+  if (!d || d->n <= 0 || d->d <= 0 || d->h <= 0 || d->w <= 0 || d->c_in <= 0 || d->c_out <= 0)
+    return B200_ERR_BAD_ARG;
+  if (d->oh != 2 * d->h - 1 || d->ow != 2 * d->w - 1) return B200_ERR_BAD_ARG;
+  if (!((d->d == 1 && d->od == 1) || d->od == 2 * d->d - 1)) return B200_ERR_BAD_ARG;
+  if (d->in_coff < 0 || d->in_coff + d->c_in > d->in_ctot) return B200_ERR_BAD_ARG;
+  if (d->out_coff < 0 || d->out_coff + d->c_out > d->out_ctot) return B200_ERR_BAD_ARG;
+  return B200_OK;
+}
+static DeconvArgs mk_deconv(const b200_deconv_desc* d, const void* x, const void* y, const void* wp) {
+  DeconvArgs a;
+  a.x = (const bf16*)x; a.n = d->n; a.d = d->d; a.h = d->h; a.w = d->w; a.c_in = d->c_in;
+  a.in_ctot = d->in_ctot; a.in_coff = d->in_coff;
+  a.y = (bf16*)const_cast<void*>(y); a.od = d->od; a.oh = d->oh; a.ow = d->ow; a.c_out = d->c_out;
+  a.out_ctot = d->out_ctot; a.out_coff = d->out_coff;
+  a.wp = (const bf16*)wp;
+  a.kd = (d->d == 1 && d->od == 1) ? 1 : 3;
+  return a;
+}
+int b200_deconv3s2_repack_weight(const b200_deconv_desc* d, const float* w, void* wp,
+                                 b200_stream_t stream) {
+  int rc = check_deconv(d);
+  if (rc) return rc;
+  const int ntaps = ((d->d == 1 && d->od == 1) ? 1 : 3) * 9;
+  deconv_repack_kernel<<<grid_for((long)d->c_in * d->c_out * ntaps), 256, 0, (cudaStream_t)stream>>>(
+      d->c_in, d->c_out, ntaps, w, (bf16*)wp);
+  B200_LAUNCH_CHECK();
+  return B200_OK;
+}
+int b200_deconv3s2_fwd(const b200_deconv_desc* d, const void* x, const void* wp, void* y,
+                       b200_stream_t stream) {
+  int rc = check_deconv(d);
+  if (rc) return rc;
+  return deconv_fwd(mk_deconv(d, x, y, wp), (cudaStream_t)stream);
+}
+int b200_deconv3s2_bwd_data(const b200_deconv_desc* d, const void* dy, const void* wp, void* dx,
+                            b200_stream_t stream) {
+  int rc = check_deconv(d);
+  if (rc) return rc;
+  return deconv_bwd_data(mk_deconv(d, dx, dy, wp), (cudaStream_t)stream);
+}
+int b200_deconv3s2_bwd_weight(const b200_deconv_desc* d, const void* x, const void* dy, float* dw,
+                              b200_stream_t stream) {
+  int rc = check_deconv(d);
+  if (rc) return rc;
+  return deconv_bwd_weight(mk_deconv(d, x, dy, nullptr), dw, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,560 @@
+// tcgen05 / TMEM / TMA implicit-GEMM kernels for the U-Net convolutions (sm_100a only).
+//
+// Data layout in HBM: activations are channels-last bf16 (N, D, H, W, C); one 128-row GEMM tile is
+// a TD x TH x TW box of positions, fetched by ONE TMA tile-mode load per (tap, 64-channel chunk):
+// the box start is shifted by the tap offset and the hardware zero-fills everything that falls
+// outside the tensor, which is exactly the conv's zero padding. The box lands in shared memory as
+// 128 rows x 128 B with the 128-byte swizzle, i.e. the canonical K-major UMMA operand.
+// Weights are pre-packed [tap][n][k] bf16 so a (tap, k-chunk, n-tile) slab is one 3-D TMA box.
+//
+// Kernel anatomy (one CTA per SM, persistent over tiles):
+//   warp 0 lane 0 : TMA producer      (full/empty mbarrier ring of `stages` slots)
+//   warp 1 lane 0 : tcgen05.mma issuer (accumulators double-buffered in TMEM)
+//   warp 2        : TMEM allocator
+//   warps 4..7    : epilogue: tcgen05.ld -> bias / ReLU / mask -> bf16 -> global (concat slice)
+#include "conv_tc.cuh"
+
+#include "tmap.cuh"
+
+namespace b200 {
+
+static const int kSmemBudget = 227 * 1024;
+static const int kTileRows = 128;
+static const int kABytes = kTileRows * 128;  // 128 rows x 64 bf16
+
+struct TileGeom {
+  int tdl, thl, twl;
+  int tiles_d, tiles_h, tiles_w;
+  int m_tiles;
+};
+
+// pick a power-of-two TD x TH x TW = 128 box minimising padded work, then halo surface
+static TileGeom pick_tile(int pn, int pd, int ph, int pw, bool force_td1) {
+  TileGeom best{};
+  double best_cost = 1e300;
+  for (int tdl = 0; tdl <= 7; ++tdl)
+    for (int thl = 0; tdl + thl <= 7; ++thl) {
+      int twl = 7 - tdl - thl;
+      int td = 1 << tdl, th = 1 << thl, tw = 1 << twl;
+      if (force_td1 && td != 1) continue;
+      if (td > 2 * pd && td > 1) continue;
+      long nd = (pd + td - 1) / td, nh = (ph + th - 1) / th, nw = (pw + tw - 1) / tw;
+      double padded = (double)nd * td * nh * th * nw * tw;
+      double halo = (double)(td + 2) * (th + 2) * (tw + 2) / 128.0;  // L2 re-read factor proxy
+      double cost = padded * (1.0 + 0.02 * halo) + (tw < 4 ? padded * 0.05 : 0.0);
+      if (cost < best_cost) {
+        best_cost = cost;
+        best.tdl = tdl;
+        best.thl = thl;
+        best.twl = twl;
+        best.tiles_d = (int)nd;
+        best.tiles_h = (int)nh;
+        best.tiles_w = (int)nw;
+        best.m_tiles = (int)(pn * nd * nh * nw);
+      }
+    }
+  return best;
+}
+
+static int make_act_tmap(CUtensorMap* tm, const ActView& v, int tap_mode, const TileGeom& g) {
+  uint64_t dims[5], str[5];
+  uint32_t box[5];
+  const bf16* base = v.ptr + v.coff;
+  if (tap_mode == TC_TAP_SHIFT) {
+    dims[0] = v.c; dims[1] = v.w; dims[2] = v.h; dims[3] = v.d; dims[4] = v.n;
+    str[0] = 1; str[1] = v.ctot; str[2] = (uint64_t)v.w * v.ctot;
+    str[3] = (uint64_t)v.h * v.w * v.ctot; str[4] = (uint64_t)v.d * v.h * v.w * v.ctot;
+    box[0] = 64; box[1] = 1u << g.twl; box[2] = 1u << g.thl; box[3] = 1u << g.tdl; box[4] = 1;
+  } else {
+    // (N, 1, 2H, 2W, C) seen as (C, j, W, i, N*H)
+    int H = v.h / 2, W = v.w / 2;
+    dims[0] = v.c; dims[1] = 2; dims[2] = W; dims[3] = 2; dims[4] = (uint64_t)v.n * H;
+    str[0] = 1; str[1] = v.ctot; str[2] = 2ull * v.ctot; str[3] = (uint64_t)v.w * v.ctot;
+    str[4] = 2ull * v.w * v.ctot;
+    box[0] = 64; box[1] = 1; box[2] = 1u << g.twl; box[3] = 1; box[4] = 1u << g.thl;
+  }
+  return make_tmap_bf16(tm, base, 5, dims, str, box);
+}
+
+struct TileCoord {
+  int n, d0, h0, w0;
+};
+__device__ __forceinline__ TileCoord decode_tile(int mt, int tiles_d, int tiles_h, int tiles_w,
+                                                 int tdl, int thl, int twl) {
+  TileCoord t;
+  int tw = mt % tiles_w; mt /= tiles_w;
+  int th = mt % tiles_h; mt /= tiles_h;
+  int td = mt % tiles_d; mt /= tiles_d;
+  t.n = mt; t.d0 = td << tdl; t.h0 = th << thl; t.w0 = tw << twl;
+  return t;
+}
+
+// ===================================================================== forward / dgrad GEMM
+struct GemmArgs {
+  int pn, pd, ph, pw;
+  int tdl, thl, twl, tiles_d, tiles_h, tiles_w;
+  int m_tiles, n_tiles, total;
+  int ntaps, kh, kw, pad_d, pad_h, pad_w;
+  int tap_mode, out_mode;
+  int kchunks, kdim, BN, stages;
+  bf16* out;
+  int out_ctot, out_coff;
+  int cout_t;
+  const float* bias;
+  int relu;
+  const bf16* mask;
+  int mask_ctot, mask_coff;
+};
+
+__global__ void __launch_bounds__(256, 1)
+    tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                   const GemmArgs p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t sraw = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (sraw & 1023u)) & 1023u);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem);
+  uint64_t* empty = full + 16;
+  uint64_t* tfull = empty + 16;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  uint8_t* tiles = smem + 1024;
+  const int stage_bytes = kABytes + p.BN * 128;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tfull[a], 1);
+      mbar_init(&tempty[a], 128);
+    }
+    fence_barrier_init();
+  }
+  uint32_t tmem_cols = 32;
+  while (tmem_cols < (uint32_t)(2 * p.BN)) tmem_cols <<= 1;
+  if (warp == 2) tmem_alloc(tmem_slot, tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int num_kb = p.ntaps * p.kchunks;
+
+  if (warp == 0 && lane == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int work = blockIdx.x; work < p.total; work += gridDim.x) {
+      const int mt = work / p.n_tiles, nt = work - mt * p.n_tiles;
+      const TileCoord tc = decode_tile(mt, p.tiles_d, p.tiles_h, p.tiles_w, p.tdl, p.thl, p.twl);
+      for (int tap = 0; tap < p.ntaps; ++tap) {
+        const int kwi = tap % p.kw, khi = (tap / p.kw) % p.kh, kdi = tap / (p.kw * p.kh);
+        for (int kc = 0; kc < p.kchunks; ++kc) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          uint8_t* sA = tiles + (size_t)stage * stage_bytes;
+          uint8_t* sB = sA + kABytes;
+          mbar_arrive_expect_tx(&full[stage], (uint32_t)stage_bytes);
+          if (p.tap_mode == TC_TAP_SHIFT)
+            tma_load_5d(sA, &tmA, &full[stage], kc * 64, tc.w0 + kwi - p.pad_w,
+                        tc.h0 + khi - p.pad_h, tc.d0 + kdi - p.pad_d, tc.n);
+          else
+            tma_load_5d(sA, &tmA, &full[stage], kc * 64, kwi, tc.w0, khi, tc.n * p.ph + tc.h0);
+          tma_load_3d(sB, &tmB, &full[stage], kc * 64, nt * p.BN, tap);
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ------------------------------------------------------------------ MMA issuer
+    const uint32_t idesc = make_idesc_bf16(128, p.BN, 0, 0);
+    int stage = 0;
+    uint32_t phase = 0, acc = 0, acc_phase = 0;
+    for (int work = blockIdx.x; work < p.total; work += gridDim.x) {
+      mbar_wait(&tempty[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + acc * (uint32_t)p.BN;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int kc = kb % p.kchunks;
+        int nk = (p.kdim - kc * 64 + 15) >> 4;
+        nk = nk > 4 ? 4 : nk;
+        mbar_wait(&full[stage], phase);
+        tc_fence_after();
+        const uint32_t aaddr = smem_u32(tiles + (size_t)stage * stage_bytes);
+        const uint32_t baddr = aaddr + kABytes;
+        for (int k = 0; k < nk; ++k) {
+          const uint64_t da = make_smem_desc_sw128(aaddr + k * 32, 16, 1024);
+          const uint64_t db = make_smem_desc_sw128(baddr + k * 32, 16, 1024);
+          umma_bf16(tmem_d, da, db, idesc, (kb | k) != 0);
+        }
+        umma_commit(&empty[stage]);
+        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+      }
+      umma_commit(&tfull[acc]);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------------ epilogue
+    const int q = warp - 4;
+    const int row = q * 32 + lane;
+    uint32_t acc = 0, acc_phase = 0;
+    for (int work = blockIdx.x; work < p.total; work += gridDim.x) {
+      const int mt = work / p.n_tiles, nt = work - mt * p.n_tiles;
+      const TileCoord tc = decode_tile(mt, p.tiles_d, p.tiles_h, p.tiles_w, p.tdl, p.thl, p.twl);
+      const int wx = tc.w0 + (row & ((1 << p.twl) - 1));
+      const int hy = tc.h0 + ((row >> p.twl) & ((1 << p.thl) - 1));
+      const int dz = tc.d0 + (row >> (p.twl + p.thl));
+      const bool valid = (wx < p.pw) && (hy < p.ph) && (dz < p.pd);
+      long opos;
+      int ocol0 = nt * p.BN;
+      if (p.out_mode == TC_OUT_CONV) {
+        opos = (((long)tc.n * p.pd + dz) * p.ph + hy) * p.pw + wx;
+      } else {
+        const int ij = ocol0 / p.cout_t;
+        ocol0 -= ij * p.cout_t;
+        opos = ((long)tc.n * (2 * p.ph) + (2 * hy + (ij >> 1))) * (2 * p.pw) + (2 * wx + (ij & 1));
+      }
+      bf16* orow = p.out + opos * p.out_ctot + p.out_coff + ocol0;
+      const bf16* mrow = p.mask ? p.mask + opos * p.mask_ctot + p.mask_coff + ocol0 : nullptr;
+      const float* brow = p.bias ? p.bias + ocol0 : nullptr;
+
+      mbar_wait(&tfull[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * (uint32_t)p.BN;
+      for (int c0 = 0; c0 < p.BN; c0 += 16) {
+        uint32_t v[16];
+        tmem_ld16(taddr + c0, v);
+        tmem_ld_wait();
+        if (valid) {
+          float f[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
+          if (brow) {
+#pragma unroll
+            for (int j = 0; j < 16; j += 4) {
+              const float4 b4 = __ldg(reinterpret_cast<const float4*>(brow + c0 + j));
+              f[j] += b4.x; f[j + 1] += b4.y; f[j + 2] += b4.z; f[j + 3] += b4.w;
+            }
+          }
+          if (p.relu) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
+          }
+          if (mrow) {
+            const uint4 m0 = *reinterpret_cast<const uint4*>(mrow + c0);
+            const uint4 m1 = *reinterpret_cast<const uint4*>(mrow + c0 + 8);
+            const uint32_t mw[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float2 mv = unpack_bf16x2(mw[j]);
+              if (!(mv.x > 0.f)) f[2 * j] = 0.f;
+              if (!(mv.y > 0.f)) f[2 * j + 1] = 0.f;
+            }
+          }
+          uint4 o0, o1;
+          o0.x = pack_bf16x2(f[0], f[1]);   o0.y = pack_bf16x2(f[2], f[3]);
+          o0.z = pack_bf16x2(f[4], f[5]);   o0.w = pack_bf16x2(f[6], f[7]);
+          o1.x = pack_bf16x2(f[8], f[9]);   o1.y = pack_bf16x2(f[10], f[11]);
+          o1.z = pack_bf16x2(f[12], f[13]); o1.w = pack_bf16x2(f[14], f[15]);
+          *reinterpret_cast<uint4*>(orow + c0) = o0;
+          *reinterpret_cast<uint4*>(orow + c0 + 8) = o1;
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&tempty[acc]);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, tmem_cols);
+}
+
+static int sm_count() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+static int pick_bn(int ncols, int limit) {
+  for (int bn = limit; bn >= 16; bn -= 16)
+    if (ncols % bn == 0) return bn;
+  return 0;
+}
+
+bool tc_gemm_supported(const TcGemmProblem& p) {
+  if (p.kdim < 16 || p.kdim % 8) return false;
+  if (p.a.ctot % 8 || p.a.coff % 8) return false;
+  if (p.out_ctot % 8 || p.out_coff % 8) return false;
+  if (p.mask && (p.mask_ctot % 8 || p.mask_coff % 8)) return false;
+  if (p.ncols % 16) return false;
+  if (p.out_mode == TC_OUT_K2S2_SCATTER) {
+    if (p.cout_t % 16 || pick_bn(p.cout_t, 256) == 0) return false;
+  }
+  if (p.tap_mode == TC_TAP_K2S2 && (p.pd != 1 || p.a.h != 2 * p.ph || p.a.w != 2 * p.pw))
+    return false;
+  return true;
+}
+
+int tc_gemm_conv(const TcGemmProblem& p, cudaStream_t stream) {
+  if (!tc_gemm_supported(p)) return B200_ERR_UNSUPPORTED;
+  GemmArgs a{};
+  a.pn = p.pn; a.pd = p.pd; a.ph = p.ph; a.pw = p.pw;
+  const TileGeom g = pick_tile(p.pn, p.pd, p.ph, p.pw, p.tap_mode == TC_TAP_K2S2 || p.pd == 1);
+  a.tdl = g.tdl; a.thl = g.thl; a.twl = g.twl;
+  a.tiles_d = g.tiles_d; a.tiles_h = g.tiles_h; a.tiles_w = g.tiles_w;
+  a.m_tiles = g.m_tiles;
+  a.BN = p.out_mode == TC_OUT_K2S2_SCATTER ? pick_bn(p.cout_t, 256) : pick_bn(p.ncols, 256);
+  a.n_tiles = p.ncols / a.BN;
+  a.total = a.m_tiles * a.n_tiles;
+  a.ntaps = p.kd * p.kh * p.kw; a.kh = p.kh; a.kw = p.kw;
+  a.pad_d = p.kd / 2; a.pad_h = p.kh / 2; a.pad_w = p.kw / 2;
+  a.tap_mode = p.tap_mode; a.out_mode = p.out_mode;
+  a.kdim = p.kdim; a.kchunks = (p.kdim + 63) / 64;
+  const int stage_bytes = kABytes + a.BN * 128;
+  a.stages = (kSmemBudget - 2048) / stage_bytes;
+  if (a.stages > 12) a.stages = 12;
+  if (a.stages < 2) return B200_ERR_UNSUPPORTED;
+  a.out = p.out; a.out_ctot = p.out_ctot; a.out_coff = p.out_coff; a.cout_t = p.cout_t;
+  a.bias = p.bias; a.relu = p.relu;
+  a.mask = p.mask; a.mask_ctot = p.mask_ctot; a.mask_coff = p.mask_coff;
+
+  CUtensorMap tmA, tmB;
+  int rc = make_act_tmap(&tmA, p.a, p.tap_mode, g);
+  if (rc) return rc;
+  {
+    uint64_t dims[3] = {(uint64_t)p.kdim, (uint64_t)p.ncols, (uint64_t)a.ntaps};
+    uint64_t str[3] = {1, (uint64_t)p.kdim, (uint64_t)p.kdim * p.ncols};
+    uint32_t box[3] = {64, (uint32_t)a.BN, 1};
+    rc = make_tmap_bf16(&tmB, p.wp, 3, dims, str, box);
+    if (rc) return rc;
+  }
+  const int smem = a.stages * stage_bytes + 2048;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         kSmemBudget);
+    if (e != cudaSuccess) return (int)e;
+    attr_set = true;
+  }
+  int grid = a.total < sm_count() ? a.total : sm_count();
+  tc_gemm_kernel<<<grid, 256, smem, stream>>>(tmA, tmB, a);
+  B200_LAUNCH_CHECK();
+  return B200_OK;
+}
+
+// ===================================================================== weight gradient
+// Both operands are MN-major: a [128 positions x 64 channels] TMA box is read by the tensor core
+// with the positions as the reduction (K) dimension, 16 positions per tcgen05.mma.
+struct WgradArgs {
+  int pn, pd, ph, pw;
+  int tdl, thl, twl, tiles_d, tiles_h, tiles_w, m_tiles;
+  int ntaps, kh, kw, pad_d, pad_h, pad_w, tap_mode;
+  int M, mblk, nblk, T, tap_groups, splits, tiles_per_split;
+  int cm, cn;  // channel counts of the M / N operands
+  int stages;
+  float* dw;
+  long s_m, s_n;
+};
+
+__global__ void __launch_bounds__(256, 1)
+    tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmM, const __grid_constant__ CUtensorMap tmN,
+                    const WgradArgs p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t sraw = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (sraw & 1023u)) & 1023u);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem);
+  uint64_t* empty = full + 16;
+  uint64_t* tfull = empty + 16;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tfull + 2);
+  uint8_t* tiles = smem + 1024;
+  const int mboxes = p.M / 64;
+  const int stage_bytes = (mboxes + p.T) * kABytes;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmM);
+    tma_prefetch_desc(&tmN);
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(&tfull[0], 1);
+    fence_barrier_init();
+  }
+  uint32_t tmem_cols = 32;
+  while (tmem_cols < (uint32_t)(p.T * 64)) tmem_cols <<= 1;
+  if (warp == 2) tmem_alloc(tmem_slot, tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // work decode: blockIdx.x -> (split, tap group, n block, m block)
+  int w = blockIdx.x;
+  const int mb = w % p.mblk; w /= p.mblk;
+  const int nb = w % p.nblk; w /= p.nblk;
+  const int tg = w % p.tap_groups; w /= p.tap_groups;
+  const int split = w;
+  const int mt_begin = split * p.tiles_per_split;
+  int mt_end = mt_begin + p.tiles_per_split;
+  if (mt_end > p.m_tiles) mt_end = p.m_tiles;
+  const int tap0 = tg * p.T;
+
+  if (warp == 0 && lane == 0) {
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int mt = mt_begin; mt < mt_end; ++mt) {
+      const TileCoord tc = decode_tile(mt, p.tiles_d, p.tiles_h, p.tiles_w, p.tdl, p.thl, p.twl);
+      mbar_wait(&empty[stage], phase ^ 1);
+      uint8_t* sM = tiles + (size_t)stage * stage_bytes;
+      uint8_t* sN = sM + mboxes * kABytes;
+      mbar_arrive_expect_tx(&full[stage], (uint32_t)stage_bytes);
+      for (int b = 0; b < mboxes; ++b) {
+        const int c0 = mb * p.M + b * 64;
+        if (p.tap_mode == TC_TAP_SHIFT)
+          tma_load_5d(sM + b * kABytes, &tmM, &full[stage], c0, tc.w0, tc.h0, tc.d0, tc.n);
+        else  // convT 2x2: the M operand is x, a plain (N,1,H,W,C) tensor
+          tma_load_5d(sM + b * kABytes, &tmM, &full[stage], c0, tc.w0, tc.h0, 0, tc.n);
+      }
+      for (int t = 0; t < p.T; ++t) {
+        const int tap = tap0 + t;
+        const int kwi = tap % p.kw, khi = (tap / p.kw) % p.kh, kdi = tap / (p.kw * p.kh);
+        if (p.tap_mode == TC_TAP_SHIFT)
+          tma_load_5d(sN + t * kABytes, &tmN, &full[stage], nb * 64, tc.w0 + kwi - p.pad_w,
+                      tc.h0 + khi - p.pad_h, tc.d0 + kdi - p.pad_d, tc.n);
+        else
+          tma_load_5d(sN + t * kABytes, &tmN, &full[stage], nb * 64, kwi, tc.w0, khi,
+                      tc.n * p.ph + tc.h0);
+      }
+      if (++stage == p.stages) { stage = 0; phase ^= 1; }
+    }
+  } else if (warp == 1 && lane == 0) {
+    const uint32_t idesc = make_idesc_bf16(p.M, 64, 1, 1);
+    int stage = 0;
+    uint32_t phase = 0;
+    bool first = true;
+    for (int mt = mt_begin; mt < mt_end; ++mt) {
+      mbar_wait(&full[stage], phase);
+      tc_fence_after();
+      const uint32_t maddr = smem_u32(tiles + (size_t)stage * stage_bytes);
+      const uint32_t naddr = maddr + mboxes * kABytes;
+      for (int t = 0; t < p.T; ++t) {
+        for (int k = 0; k < 8; ++k) {  // 16 positions (= 2 KB of rows) per MMA
+          const uint64_t da = make_smem_desc_sw128(maddr + k * 2048, kABytes, 1024);
+          const uint64_t db = make_smem_desc_sw128(naddr + t * kABytes + k * 2048, kABytes, 1024);
+          umma_bf16(tmem_base + t * 64, da, db, idesc, !(first && k == 0));
+        }
+      }
+      first = false;
+      umma_commit(&empty[stage]);
+      if (++stage == p.stages) { stage = 0; phase ^= 1; }
+    }
+    umma_commit(&tfull[0]);
+  } else if (warp >= 4) {
+    const int q = warp - 4;
+    int m_local;
+    bool lane_ok = true;
+    if (p.M == 128) {
+      m_local = q * 32 + lane;
+    } else {  // M = 64: row m lives in TMEM lane (m % 16) + 32 * (m / 16)
+      m_local = q * 16 + (lane & 15);
+      lane_ok = lane < 16;
+    }
+    const int m = mb * p.M + m_local;
+    const bool m_ok = lane_ok && m < p.cm && mt_end > mt_begin;
+    mbar_wait(&tfull[0], 0);
+    tc_fence_after();
+    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+    for (int t = 0; t < p.T; ++t) {
+      const int tap = tap0 + t;
+      for (int c0 = 0; c0 < 64; c0 += 16) {
+        uint32_t v[16];
+        tmem_ld16(taddr + t * 64 + c0, v);
+        tmem_ld_wait();
+        if (m_ok) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int n = nb * 64 + c0 + j;
+            if (n < p.cn) atomicAdd(p.dw + (long)m * p.s_m + (long)n * p.s_n + tap, __uint_as_float(v[j]));
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, tmem_cols);
+}
+
+bool tc_wgrad_supported(const TcWgradProblem& p) {
+  if (p.mop.c < 16 || p.nop.c < 16 || p.mop.c % 8 || p.nop.c % 8) return false;
+  if (p.mop.ctot % 8 || p.mop.coff % 8 || p.nop.ctot % 8 || p.nop.coff % 8) return false;
+  if (p.tap_mode == TC_TAP_K2S2 && p.pd != 1) return false;
+  return true;
+}
+
+int tc_wgrad(const TcWgradProblem& p, cudaStream_t stream) {
+  if (!tc_wgrad_supported(p)) return B200_ERR_UNSUPPORTED;
+  WgradArgs a{};
+  a.pn = p.pn; a.pd = p.pd; a.ph = p.ph; a.pw = p.pw;
+  const TileGeom g = pick_tile(p.pn, p.pd, p.ph, p.pw, p.tap_mode == TC_TAP_K2S2 || p.pd == 1);
+  a.tdl = g.tdl; a.thl = g.thl; a.twl = g.twl;
+  a.tiles_d = g.tiles_d; a.tiles_h = g.tiles_h; a.tiles_w = g.tiles_w; a.m_tiles = g.m_tiles;
+  a.ntaps = p.kd * p.kh * p.kw; a.kh = p.kh; a.kw = p.kw;
+  a.pad_d = p.kd / 2; a.pad_h = p.kh / 2; a.pad_w = p.kw / 2;
+  a.tap_mode = p.tap_mode;
+  a.cm = p.mop.c; a.cn = p.nop.c;
+  a.M = a.cm > 64 ? 128 : 64;
+  a.mblk = (a.cm + a.M - 1) / a.M;
+  a.nblk = (a.cn + 63) / 64;
+  a.T = (a.ntaps % 3 == 0) ? 3 : (a.ntaps % 4 == 0 ? 4 : 1);
+  a.tap_groups = a.ntaps / a.T;
+  const int stage_bytes = (a.M / 64 + a.T) * kABytes;
+  a.stages = (kSmemBudget - 2048) / stage_bytes;
+  if (a.stages > 8) a.stages = 8;
+  if (a.stages < 2) return B200_ERR_UNSUPPORTED;
+  const long base_ctas = (long)a.mblk * a.nblk * a.tap_groups;
+  long want = (3L * sm_count() + base_ctas - 1) / base_ctas;  // ~3 waves of CTAs
+  if (want < 1) want = 1;
+  if (want > a.m_tiles) want = a.m_tiles;
+  a.tiles_per_split = (int)((a.m_tiles + want - 1) / want);
+  a.splits = (a.m_tiles + a.tiles_per_split - 1) / a.tiles_per_split;
+  a.dw = p.dw; a.s_m = p.s_m; a.s_n = p.s_n;
+
+  CUtensorMap tmM, tmN;
+  int rc;
+  if (p.tap_mode == TC_TAP_SHIFT) {
+    rc = make_act_tmap(&tmM, p.mop, TC_TAP_SHIFT, g);
+    if (rc) return rc;
+    rc = make_act_tmap(&tmN, p.nop, TC_TAP_SHIFT, g);
+  } else {
+    rc = make_act_tmap(&tmM, p.mop, TC_TAP_SHIFT, g);
+    if (rc) return rc;
+    rc = make_act_tmap(&tmN, p.nop, TC_TAP_K2S2, g);
+  }
+  if (rc) return rc;
+  const int smem = a.stages * stage_bytes + 2048;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(tc_wgrad_kernel,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
+    if (e != cudaSuccess) return (int)e;
+    attr_set = true;
+  }
+  const long grid = base_ctas * a.splits;
+  tc_wgrad_kernel<<<(unsigned)grid, 256, smem, stream>>>(tmM, tmN, a);
+  B200_LAUNCH_CHECK();
+  return B200_OK;
+}
+
+}  // namespace b200

@@ -1,0 +1,55 @@
+// Internal interface of the tcgen05 implicit-GEMM kernels (conv_tc.cu).
+#pragma once
+#include "common.cuh"
+
+namespace b200 {
+
+// Activation operand of an implicit GEMM: channels-last bf16 (N, D, H, W, C) slice.
+struct ActView {
+  const bf16* ptr;
+  int n, d, h, w, c;
+  int ctot, coff;
+};
+
+enum { TC_OUT_CONV = 0, TC_OUT_K2S2_SCATTER = 1 };
+// how taps address the tap-dependent operand:
+//   TC_TAP_SHIFT : taps shift the tile by (kd-1, kh-1, kw-1) with zero padding (3x3x3 conv)
+//   TC_TAP_K2S2  : operand is (N, 1, 2H, 2W, C); tap (i, j) selects positions (2h+i, 2w+j)
+enum { TC_TAP_SHIFT = 0, TC_TAP_K2S2 = 1 };
+
+// Forward / data-gradient implicit GEMM over position tiles of 128 rows:
+//   out[pos][n] = sum_{tap, k} A[pos (+) tap][k] * Wp[tap][n][k]   (+ bias, ReLU, mask)
+struct TcGemmProblem {
+  ActView a;              // A operand (x for fwd, dy for dgrad); for TC_TAP_K2S2 h,w are 2H,2W
+  const bf16* wp;         // [ntaps][ncols][kdim] bf16, K contiguous
+  int ncols, kdim;        // GEMM N and per-tap K
+  int kd, kh, kw;         // taps per axis (TC_TAP_K2S2: 1,2,2)
+  int tap_mode;           // TC_TAP_*
+  int out_mode;           // TC_OUT_*
+  int pn, pd, ph, pw;     // position grid the 128-row tiles enumerate
+  bf16* out;
+  int out_ctot, out_coff;
+  int cout_t;             // TC_OUT_K2S2_SCATTER: channels per (i,j) block (ncols = 4 * cout_t)
+  const float* bias;      // per output channel or NULL
+  int relu;
+  const bf16* mask;       // optional: out = 0 where mask <= 0; same geometry as out
+  int mask_ctot, mask_coff;
+};
+int tc_gemm_conv(const TcGemmProblem& p, cudaStream_t stream);
+bool tc_gemm_supported(const TcGemmProblem& p);
+
+// Weight-gradient implicit GEMM (reduction over positions):
+//   dw[m*s_m + n*s_n + tap] += sum_pos Mop[pos][m] * Nop[pos (+) tap][n]
+struct TcWgradProblem {
+  ActView mop;            // un-shifted operand (dy for conv, x for convT 2x2)
+  ActView nop;            // tap-addressed operand (x for conv, dy for convT 2x2)
+  int kd, kh, kw;
+  int tap_mode;
+  int pn, pd, ph, pw;     // position grid
+  float* dw;
+  long s_m, s_n;
+};
+int tc_wgrad(const TcWgradProblem& p, cudaStream_t stream);
+bool tc_wgrad_supported(const TcWgradProblem& p);
+
+}  // namespace b200

@@ -1,0 +1,399 @@
+// 1x1 segmentation head, the loss reductions (Dice / BCE / IoU / F1 / cross-entropy) and the
+// evaluation-metric reductions. All HBM-bound: one pass over the logits + target, fp32 math,
+// fp64 block-level accumulation (one atomic per block and quantity).
+#include "common.cuh"
+#include "../../include/b200unet.h"
+
+namespace b200 {
+
+struct View {
+  bf16* p;
+  int ctot, coff;
+  __device__ __forceinline__ bf16* at(long pos, int c) const { return p + pos * ctot + coff + c; }
+};
+static inline View mk(const b200_view& v) { return View{(bf16*)v.ptr, v.ctot, v.coff}; }
+
+__device__ __forceinline__ double block_sum_d(double v, double* sh) {
+  v = warp_sum_d(v);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  __syncthreads();
+  if (lane == 0) sh[warp] = v;
+  __syncthreads();
+  double r = 0;
+  if (warp == 0) {
+    r = lane < (blockDim.x >> 5) ? sh[lane] : 0.0;
+    r = warp_sum_d(r);
+  }
+  return r;  // valid in thread 0
+}
+
+// ------------------------------------------------------------------------------------ head
+#define HEAD_MAX_CO 8
+__global__ void __launch_bounds__(256)
+    head_fwd_kernel(int n, long spatial, int c_in, int c_out, View x, const float* w, const float* b,
+                    float* logits) {
+  extern __shared__ float sw[];  // [c_out][c_in] + [c_out]
+  for (int i = threadIdx.x; i < c_out * c_in; i += blockDim.x) sw[i] = w[i];
+  for (int i = threadIdx.x; i < c_out; i += blockDim.x) sw[c_out * c_in + i] = b ? b[i] : 0.f;
+  __syncthreads();
+  const long total = (long)n * spatial;
+  for (long pos = (long)blockIdx.x * blockDim.x + threadIdx.x; pos < total; pos += (long)gridDim.x * blockDim.x) {
+    const long bi = pos / spatial, s = pos % spatial;
+    for (int co0 = 0; co0 < c_out; co0 += HEAD_MAX_CO) {
+      float acc[HEAD_MAX_CO];
+#pragma unroll
+      for (int j = 0; j < HEAD_MAX_CO; ++j) acc[j] = (co0 + j < c_out) ? sw[c_out * c_in + co0 + j] : 0.f;
+      const bf16* xr = x.at(pos, 0);
+      for (int ci = 0; ci < c_in; ++ci) {
+        const float xv = __bfloat162float(xr[ci]);
+#pragma unroll
+        for (int j = 0; j < HEAD_MAX_CO; ++j)
+          if (co0 + j < c_out) acc[j] = fmaf(xv, sw[(co0 + j) * c_in + ci], acc[j]);
+      }
+#pragma unroll
+      for (int j = 0; j < HEAD_MAX_CO; ++j)
+        if (co0 + j < c_out) logits[(bi * c_out + co0 + j) * spatial + s] = acc[j];
+    }
+  }
+}
+// dx[pos][ci] = sum_co dlogits[n][co][pos] * w[co][ci]
+__global__ void __launch_bounds__(256)
+    head_bwd_data_kernel(int n, long spatial, int c_in, int c_out, const float* w,
+                         const float* dlogits, View dx) {
+  extern __shared__ float sw[];
+  for (int i = threadIdx.x; i < c_out * c_in; i += blockDim.x) sw[i] = w[i];
+  __syncthreads();
+  const int cv = (c_in + 7) / 8;
+  const long total = (long)n * spatial * cv;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const long pos = i / cv;
+    const int ci0 = (int)(i % cv) * 8;
+    const long bi = pos / spatial, s = pos % spatial;
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int co = 0; co < c_out; ++co) {
+      const float g = dlogits[(bi * c_out + co) * spatial + s];
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (ci0 + j < c_in) acc[j] = fmaf(g, sw[co * c_in + ci0 + j], acc[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      if (ci0 + j < c_in) *dx.at(pos, ci0 + j) = __float2bfloat16(acc[j]);
+  }
+}
+// dw[co][ci] += sum_pos dlogits[co][pos] * x[pos][ci];  db[co] += sum_pos dlogits[co][pos]
+// block: 256 threads = c_in lanes x rows; each thread keeps c_out accumulators (c_out <= 8 per pass)
+__global__ void __launch_bounds__(256)
+    head_bwd_weight_kernel(int n, long spatial, int c_in, int c_out, long chunk, View x,
+                           const float* dlogits, float* dw, float* db) {
+  __shared__ float sred[256];
+  const int lanes = c_in < 256 ? c_in : 256;
+  const int rows = 256 / lanes;
+  const int ci = threadIdx.x % lanes, row = threadIdx.x / lanes;
+  const long total = (long)n * spatial;
+  const long pbeg = (long)blockIdx.x * chunk;
+  const long pend = pbeg + chunk < total ? pbeg + chunk : total;
+  for (int cib = 0; cib < c_in; cib += lanes) {
+    const int c = cib + ci;
+    for (int co = 0; co < c_out; ++co) {
+      float acc = 0.f, accb = 0.f;
+      if (row < rows && c < c_in) {
+        for (long pos = pbeg + row; pos < pend; pos += rows) {
+          const long bi = pos / spatial, s = pos % spatial;
+          const float g = dlogits[(bi * c_out + co) * spatial + s];
+          acc = fmaf(g, __bfloat162float(*x.at(pos, c)), acc);
+          accb += g;
+        }
+      }
+      __syncthreads();
+      sred[threadIdx.x] = acc;
+      __syncthreads();
+      if (row == 0 && c < c_in) {
+        float s = 0.f;
+        for (int r = 0; r < rows; ++r) s += sred[r * lanes + ci];
+        atomicAdd(dw + (long)co * c_in + c, s);
+      }
+      if (cib == 0 && db) {
+        __syncthreads();
+        sred[threadIdx.x] = (ci == 0 && row < rows) ? accb : 0.f;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+          float s = 0.f;
+          for (int r = 0; r < rows; ++r) s += sred[r * lanes];
+          atomicAdd(db + co, s);
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------ seg sums
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + __expf(-x)); }
+// numerically stable BCE-with-logits: max(x,0) - x*t + log(1 + exp(-|x|))
+__device__ __forceinline__ float bce_logits(float x, float t) {
+  return fmaxf(x, 0.f) - x * t + log1pf(__expf(-fabsf(x)));
+}
+
+__global__ void __launch_bounds__(256)
+    seg_sums_kernel(int c, long spatial, long chunk, const float* logits, const float* target,
+                    int normalization, double* sums) {
+  __shared__ double sh[8];
+  const int row = blockIdx.y;  // n * c + channel
+  const int ch = row % c;
+  const float* xr = logits + (long)row * spatial;
+  const float* tr = target + (long)row * spatial;
+  const long pbeg = (long)blockIdx.x * chunk;
+  const long pend = pbeg + chunk < spatial ? pbeg + chunk : spatial;
+  float a[6] = {0, 0, 0, 0, 0, 0};
+  for (long i = pbeg + threadIdx.x; i < pend; i += blockDim.x) {
+    const float x = xr[i], t = tr[i];
+    const float p = normalization == 0 ? 1.f / (1.f + expf(-x)) : x;
+    a[0] += p * t; a[1] += p * p; a[2] += t * t; a[3] += p; a[4] += t;
+    if (normalization == 0) a[5] += bce_logits(x, t);
+  }
+  for (int k = 0; k < 6; ++k) {
+    const double r = block_sum_d((double)a[k], sh);
+    if (threadIdx.x == 0) atomicAdd(&sums[ch * 6 + k], r);
+  }
+}
+__global__ void seg_loss_bwd_kernel(int c, long spatial, long total, const float* logits,
+                                    const float* target, const float* coef, float* dlogits) {
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int ch = (int)((i / spatial) % c);
+    const float x = logits[i], t = target[i];
+    const float p = 1.f / (1.f + expf(-x));
+    const float* k = coef + ch * 4;
+    dlogits[i] = k[0] * (p - t) + p * (1.f - p) * (k[1] * t + k[2] * p + k[3]);
+  }
+}
+
+// ------------------------------------------------------------------------------------ cross entropy
+__global__ void __launch_bounds__(256)
+    ce_fwd_kernel(int n, int c, long spatial, const float* logits, const int64_t* labels,
+                  double* nll_sum) {
+  __shared__ double sh[8];
+  const long total = (long)n * spatial;
+  float acc = 0.f;
+  for (long pos = (long)blockIdx.x * blockDim.x + threadIdx.x; pos < total; pos += (long)gridDim.x * blockDim.x) {
+    const long b = pos / spatial, s = pos % spatial;
+    const float* xr = logits + b * c * spatial + s;
+    float m = -INFINITY;
+    for (int k = 0; k < c; ++k) m = fmaxf(m, xr[(long)k * spatial]);
+    float se = 0.f;
+    for (int k = 0; k < c; ++k) se += expf(xr[(long)k * spatial] - m);
+    const int lab = (int)labels[pos];
+    acc += (m + logf(se)) - xr[(long)lab * spatial];
+  }
+  const double r = block_sum_d((double)acc, sh);
+  if (threadIdx.x == 0) atomicAdd(nll_sum, r);
+}
+__global__ void ce_bwd_kernel(int n, int c, long spatial, const float* logits, const int64_t* labels,
+                              const float* scale, float* dlogits) {
+  const long total = (long)n * spatial;
+  const float sc = scale[0];
+  for (long pos = (long)blockIdx.x * blockDim.x + threadIdx.x; pos < total; pos += (long)gridDim.x * blockDim.x) {
+    const long b = pos / spatial, s = pos % spatial;
+    const float* xr = logits + b * c * spatial + s;
+    float* gr = dlogits + b * c * spatial + s;
+    float m = -INFINITY;
+    for (int k = 0; k < c; ++k) m = fmaxf(m, xr[(long)k * spatial]);
+    float se = 0.f;
+    for (int k = 0; k < c; ++k) se += expf(xr[(long)k * spatial] - m);
+    const float inv = 1.f / se;
+    const int lab = (int)labels[pos];
+    for (int k = 0; k < c; ++k)
+      gr[(long)k * spatial] = sc * (expf(xr[(long)k * spatial] - m) * inv - (k == lab ? 1.f : 0.f));
+  }
+}
+
+// ------------------------------------------------------------------------------------ metrics
+__device__ __forceinline__ float metric_prob(float x, int mode) {
+  if (mode == 0) return 1.f / (1.f + expf(-x) + 1e-6f);
+  if (mode == 1) return 1.f / (1.f + expf(-x));
+  return x;
+}
+__global__ void __launch_bounds__(256) metric_prob_sum_kernel(long numel, const float* logits, double* psum) {
+  __shared__ double sh[8];
+  float acc = 0.f;
+  double dacc = 0.0;
+  int cnt = 0;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < numel; i += (long)gridDim.x * blockDim.x) {
+    acc += metric_prob(logits[i], 0);
+    if (++cnt == 256) { dacc += acc; acc = 0.f; cnt = 0; }
+  }
+  dacc += acc;
+  const double r = block_sum_d(dacc, sh);
+  if (threadIdx.x == 0) atomicAdd(psum, r);
+}
+__global__ void __launch_bounds__(256)
+    metric_counts_kernel(long per_sample, long chunk, const float* logits, const float* labels,
+                         const float* thr, int mode, double* counts) {
+  __shared__ double sh[8];
+  const int b = blockIdx.y;
+  const float th = thr[0];
+  const float* xr = logits + (long)b * per_sample;
+  const float* lr = labels + (long)b * per_sample;
+  const long pbeg = (long)blockIdx.x * chunk;
+  const long pend = pbeg + chunk < per_sample ? pbeg + chunk : per_sample;
+  unsigned ci = 0, cp = 0, cl = 0;
+  for (long i = pbeg + threadIdx.x; i < pend; i += blockDim.x) {
+    const bool P = metric_prob(xr[i], mode) > th;
+    const bool L = lr[i] > th;
+    ci += (P && L); cp += P; cl += L;
+  }
+  const double r0 = block_sum_d((double)ci, sh);
+  if (threadIdx.x == 0) atomicAdd(&counts[b * 3 + 0], r0);
+  const double r1 = block_sum_d((double)cp, sh);
+  if (threadIdx.x == 0) atomicAdd(&counts[b * 3 + 1], r1);
+  const double r2 = block_sum_d((double)cl, sh);
+  if (threadIdx.x == 0) atomicAdd(&counts[b * 3 + 2], r2);
+}
+#define ARGMAX_MAX_C 16
+__global__ void __launch_bounds__(256)
+    metric_argmax_counts_kernel(int c, long spatial, long chunk, const float* x, const float* target,
+                                double* counts) {
+  __shared__ double sh[8];
+  const int b = blockIdx.y;
+  const float* xr = x + (long)b * c * spatial;
+  const float* tr = target + (long)b * c * spatial;
+  const long pbeg = (long)blockIdx.x * chunk;
+  const long pend = pbeg + chunk < spatial ? pbeg + chunk : spatial;
+  unsigned inter[ARGMAX_MAX_C], uni[ARGMAX_MAX_C];
+#pragma unroll
+  for (int k = 0; k < ARGMAX_MAX_C; ++k) inter[k] = uni[k] = 0;
+  for (long i = pbeg + threadIdx.x; i < pend; i += blockDim.x) {
+    int am = 0;
+    float m = xr[i];
+    for (int k = 1; k < c; ++k) {
+      const float v = xr[(long)k * spatial + i];
+      if (v > m) { m = v; am = k; }
+    }
+#pragma unroll
+    for (int k = 0; k < ARGMAX_MAX_C; ++k) {
+      if (k < c) {
+        const bool P = (k == am);
+        const bool T = ((unsigned char)tr[(long)k * spatial + i]) != 0;  // `.byte()` of the reference
+        inter[k] += (P && T); uni[k] += (P || T);
+      }
+    }
+  }
+  for (int k = 0; k < c; ++k) {
+    const double r0 = block_sum_d((double)inter[k], sh);
+    if (threadIdx.x == 0) atomicAdd(&counts[((long)b * c + k) * 2], r0);
+    const double r1 = block_sum_d((double)uni[k], sh);
+    if (threadIdx.x == 0) atomicAdd(&counts[((long)b * c + k) * 2 + 1], r1);
+  }
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+static inline unsigned grid1d(long total) {
+  long b = (total + 255) / 256;
+  return (unsigned)(b < 148L * 16 ? (b < 1 ? 1 : b) : 148L * 16);
+}
+static inline long pick_chunk(long per_row, long rows) {
+  long want = 148L * 8 / (rows > 0 ? rows : 1);
+  if (want < 1) want = 1;
+  long chunk = (per_row + want - 1) / want;
+  if (chunk < 1024) chunk = 1024;
+  return chunk;
+}
+
+extern "C" {
+
+int b200_head_fwd(int32_t n, int64_t spatial, int32_t c_in, int32_t c_out, b200_view x,
+                  const float* w, const float* b, float* logits, b200_stream_t stream) {
+  const long total = (long)n * spatial;
+  if (total <= 0) return B200_OK;
+  const size_t smem = ((size_t)c_out * c_in + c_out) * sizeof(float);
+  if (smem > 48 * 1024) return B200_ERR_UNSUPPORTED;
+  head_fwd_kernel<<<grid1d(total), 256, smem, (cudaStream_t)stream>>>(n, (long)spatial, c_in, c_out, mk(x), w, b, logits);
+  B200_LAUNCH_CHECK();
+  return B200_OK;
+}
+int b200_head_bwd(int32_t n, int64_t spatial, int32_t c_in, int32_t c_out, b200_view x,
+                  const float* w, const float* dlogits, b200_view dx, float* dw, float* db,
+                  b200_stream_t stream) {
+  const long total = (long)n * spatial;
+  if (total <= 0) return B200_OK;
+  const size_t smem = (size_t)c_out * c_in * sizeof(float);
+  if (smem > 48 * 1024) return B200_ERR_UNSUPPORTED;
+  if (dx.ptr) {
+    head_bwd_data_kernel<<<grid1d(total * ((c_in + 7) / 8)), 256, smem, (cudaStream_t)stream>>>(
+        n, (long)spatial, c_in, c_out, w, dlogits, mk(dx));
+    B200_LAUNCH_CHECK();
+  }
+  if (dw) {
+    long chunk = (total + 148L * 4 - 1) / (148L * 4);
+    if (chunk < 64) chunk = 64;
+    head_bwd_weight_kernel<<<(unsigned)((total + chunk - 1) / chunk), 256, 0, (cudaStream_t)stream>>>(
+        n, (long)spatial, c_in, c_out, chunk, mk(x), dlogits, dw, db);
+    B200_LAUNCH_CHECK();
+  }
+  return B200_OK;
+}
+
+int b200_seg_sums(int32_t n, int32_t c, int64_t spatial, const float* logits, const float* target,
+                  int32_t normalization, double* sums, b200_stream_t stream) {
+  if ((long)n * c * spatial <= 0) return B200_OK;
+  if ((long)n * c > 65535) return B200_ERR_UNSUPPORTED;
+  const long chunk = pick_chunk(spatial, (long)n * c);
+  dim3 grid((unsigned)((spatial + chunk - 1) / chunk), (unsigned)(n * c));
+  seg_sums_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(c, (long)spatial, chunk, logits, target, normalization, sums);
+  B200_LAUNCH_CHECK();
+  return B200_OK;
+}
+int b200_seg_loss_bwd(int32_t n, int32_t c, int64_t spatial, const float* logits,
+                      const float* target, const float* coef, float* dlogits, b200_stream_t stream) {
+  const long total = (long)n * c * spatial;
+  if (total <= 0) return B200_OK;
+  seg_loss_bwd_kernel<<<grid1d(total), 256, 0, (cudaStream_t)stream>>>(c, (long)spatial, total, logits, target, coef, dlogits);
+  B200_LAUNCH_CHECK();
+  return B200_OK;
+}
+int b200_ce_fwd(int32_t n, int32_t c, int64_t spatial, const float* logits, const int64_t* labels,
+                double* nll_sum, b200_stream_t stream) {
+  const long total = (long)n * spatial;
+  if (total <= 0) return B200_OK;
+  ce_fwd_kernel<<<grid1d(total), 256, 0, (cudaStream_t)stream>>>(n, c, (long)spatial, logits, labels, nll_sum);
+  B200_LAUNCH_CHECK();
+  return B200_OK;
+}
+int b200_ce_bwd(int32_t n, int32_t c, int64_t spatial, const float* logits, const int64_t* labels,
+                const float* scale, float* dlogits, b200_stream_t stream) {
+  const long total = (long)n * spatial;
+  if (total <= 0) return B200_OK;
+  ce_bwd_kernel<<<grid1d(total), 256, 0, (cudaStream_t)stream>>>(n, c, (long)spatial, logits, labels, scale, dlogits);
+  B200_LAUNCH_CHECK();
+  return B200_OK;
+}
+int b200_metric_prob_sum(int64_t numel, const float* logits, double* psum, b200_stream_t stream) {
+  if (numel <= 0) return B200_OK;
+  metric_prob_sum_kernel<<<grid1d(numel), 256, 0, (cudaStream_t)stream>>>((long)numel, logits, psum);
+  B200_LAUNCH_CHECK();
+  return B200_OK;
+}
+int b200_metric_counts(int32_t n, int64_t per_sample, const float* logits, const float* labels,
+                       const float* thr, int32_t mode, double* counts, b200_stream_t stream) {
+  if ((long)n * per_sample <= 0) return B200_OK;
+  if (n > 65535) return B200_ERR_UNSUPPORTED;
+  const long chunk = pick_chunk(per_sample, n);
+  dim3 grid((unsigned)((per_sample + chunk - 1) / chunk), (unsigned)n);
+  metric_counts_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((long)per_sample, chunk, logits, labels, thr, mode, counts);
+  B200_LAUNCH_CHECK();
+  return B200_OK;
+}
+int b200_metric_argmax_counts(int32_t n, int32_t c, int64_t spatial, const float* x,
+                              const float* target, double* counts, b200_stream_t stream) {
+  if ((long)n * spatial <= 0) return B200_OK;
+  if (c > ARGMAX_MAX_C || n > 65535) return B200_ERR_UNSUPPORTED;
+  const long chunk = pick_chunk(spatial, n);
+  dim3 grid((unsigned)((spatial + chunk - 1) / chunk), (unsigned)n);
+  metric_argmax_counts_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(c, (long)spatial, chunk, x, target, counts);
+  B200_LAUNCH_CHECK();
+  return B200_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,701 @@
+// HBM-bound kernels of the U-Net path: max-pool, nearest up-sampling, concat copies, ReLU backward,
+// bias gradients, GroupNorm, BatchNorm and the fp32 NCHW <-> bf16 channels-last boundary.
+// All of them stream channels-last bf16 with 128-bit accesses (8 channels per thread) and reduce
+// with warp shuffles + one atomic per block.
+#include "common.cuh"
+#include "../../include/b200unet.h"
+
+namespace b200 {
+
+template <int V>
+struct Vec;
+template <>
+struct Vec<8> {
+  static __device__ __forceinline__ void load(const bf16* p, float* f) {
+    const uint4 u = *reinterpret_cast<const uint4*>(p);
+    const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z),
+                 d = unpack_bf16x2(u.w);
+    f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
+  }
+  static __device__ __forceinline__ void store(bf16* p, const float* f) {
+    uint4 u;
+    u.x = pack_bf16x2(f[0], f[1]); u.y = pack_bf16x2(f[2], f[3]);
+    u.z = pack_bf16x2(f[4], f[5]); u.w = pack_bf16x2(f[6], f[7]);
+    *reinterpret_cast<uint4*>(p) = u;
+  }
+};
+template <>
+struct Vec<1> {
+  static __device__ __forceinline__ void load(const bf16* p, float* f) { f[0] = __bfloat162float(*p); }
+  static __device__ __forceinline__ void store(bf16* p, const float* f) { *p = __float2bfloat16(f[0]); }
+};
+
+struct View {
+  bf16* p;
+  int ctot, coff;
+  __device__ __forceinline__ bf16* at(long pos, int c) const { return p + pos * ctot + coff + c; }
+};
+static inline View mk(const b200_view& v) { return View{(bf16*)v.ptr, v.ctot, v.coff}; }
+static inline bool vec8(int c, const b200_view& a) {
+  return c % 8 == 0 && a.ctot % 8 == 0 && a.coff % 8 == 0 && ((uintptr_t)a.ptr % 16) == 0;
+}
+static inline unsigned blocks_for(long total, int threads) {
+  return (unsigned)((total + threads - 1) / threads);
+}
+
+// ------------------------------------------------------------------------------------ max-pool
+template <int V>
+__global__ void maxpool_fwd_kernel(int n, int d, int h, int w, int c, int pd, View x, View y) {
+  const int od = d / pd, oh = h / 2, ow = w / 2, cv = c / V;
+  const long total = (long)n * od * oh * ow * cv;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    long r = i;
+    const int ch = (int)(r % cv) * V; r /= cv;
+    const int xw = (int)(r % ow); r /= ow;
+    const int xh = (int)(r % oh); r /= oh;
+    const int xd = (int)(r % od); r /= od;
+    const int b = (int)r;
+    float m[V];
+    bool first = true;
+    for (int a = 0; a < pd; ++a)
+      for (int e = 0; e < 2; ++e)
+        for (int g = 0; g < 2; ++g) {
+          float f[V];
+          const long pos = (((long)b * d + xd * pd + a) * h + xh * 2 + e) * w + xw * 2 + g;
+          Vec<V>::load(x.at(pos, ch), f);
+#pragma unroll
+          for (int j = 0; j < V; ++j) m[j] = first ? f[j] : fmaxf(m[j], f[j]);
+          first = false;
+        }
+    const long opos = (((long)b * od + xd) * oh + xh) * ow + xw;
+    Vec<V>::store(y.at(opos, ch), m);
+  }
+}
+
+// one thread per INPUT position: recompute the window arg-max (first maximum in d,h,w scan order)
+template <int V>
+__global__ void maxpool_bwd_kernel(int n, int d, int h, int w, int c, int pd, View x, View dy, View dx) {
+  const int od = d / pd, oh = h / 2, ow = w / 2, cv = c / V;
+  const long total = (long)n * d * h * w * cv;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    long r = i;
+    const int ch = (int)(r % cv) * V; r /= cv;
+    const int xw = (int)(r % w); r /= w;
+    const int xh = (int)(r % h); r /= h;
+    const int xd = (int)(r % d); r /= d;
+    const int b = (int)r;
+    const long ipos = (((long)b * d + xd) * h + xh) * w + xw;
+    float out[V];
+#pragma unroll
+    for (int j = 0; j < V; ++j) out[j] = 0.f;
+    const int pw_ = xw >> 1, ph_ = xh >> 1, pdd = xd / pd;
+    if (pw_ < ow && ph_ < oh && pdd < od) {
+      const int self = ((xd - pdd * pd) * 2 + (xh & 1)) * 2 + (xw & 1);
+      float m[V];
+      int arg[V];
+      int k = 0;
+      for (int a = 0; a < pd; ++a)
+        for (int e = 0; e < 2; ++e)
+          for (int g = 0; g < 2; ++g, ++k) {
+            float f[V];
+            const long pos = (((long)b * d + pdd * pd + a) * h + ph_ * 2 + e) * w + pw_ * 2 + g;
+            Vec<V>::load(x.at(pos, ch), f);
+#pragma unroll
+            for (int j = 0; j < V; ++j)
+              if (k == 0 || f[j] > m[j]) { m[j] = f[j]; arg[j] = k; }
+          }
+      float g_[V];
+      const long opos = (((long)b * od + pdd) * oh + ph_) * ow + pw_;
+      Vec<V>::load(dy.at(opos, ch), g_);
+#pragma unroll
+      for (int j = 0; j < V; ++j) out[j] = (arg[j] == self) ? g_[j] : 0.f;
+    }
+    Vec<V>::store(dx.at(ipos, ch), out);
+  }
+}
+
+// ------------------------------------------------------------------------------------ nearest
+__device__ __forceinline__ int nearest_src(int dst, float scale, int in) {
+  const int s = (int)floorf(dst * scale);
+  return s < in - 1 ? s : in - 1;
+}
+template <int V>
+__global__ void upsample_fwd_kernel(int n, int id, int ih, int iw, int od, int oh, int ow, int c,
+                                    View x, View y) {
+  const int cv = c / V;
+  const float sd = (float)id / od, sh = (float)ih / oh, sw = (float)iw / ow;
+  const long total = (long)n * od * oh * ow * cv;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    long r = i;
+    const int ch = (int)(r % cv) * V; r /= cv;
+    const int xw = (int)(r % ow); r /= ow;
+    const int xh = (int)(r % oh); r /= oh;
+    const int xd = (int)(r % od); r /= od;
+    const int b = (int)r;
+    const long ipos = (((long)b * id + nearest_src(xd, sd, id)) * ih + nearest_src(xh, sh, ih)) * iw +
+                      nearest_src(xw, sw, iw);
+    float f[V];
+    Vec<V>::load(x.at(ipos, ch), f);
+    Vec<V>::store(y.at((((long)b * od + xd) * oh + xh) * ow + xw, ch), f);
+  }
+}
+// children of source index s along one axis: [lo, hi)
+__device__ __forceinline__ void children(int s, float scale, int in, int out, int& lo, int& hi) {
+  int o = (int)floorf(s / scale) - 2;
+  if (o < 0) o = 0;
+  while (o < out && nearest_src(o, scale, in) < s) ++o;
+  lo = o;
+  while (o < out && nearest_src(o, scale, in) == s) ++o;
+  hi = o;
+}
+template <int V>
+__global__ void upsample_bwd_kernel(int n, int id, int ih, int iw, int od, int oh, int ow, int c,
+                                    View dy, View dx) {
+  const int cv = c / V;
+  const float sd = (float)id / od, sh = (float)ih / oh, sw = (float)iw / ow;
+  const long total = (long)n * id * ih * iw * cv;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    long r = i;
+    const int ch = (int)(r % cv) * V; r /= cv;
+    const int xw = (int)(r % iw); r /= iw;
+    const int xh = (int)(r % ih); r /= ih;
+    const int xd = (int)(r % id); r /= id;
+    const int b = (int)r;
+    int d0, d1, h0, h1, w0, w1;
+    children(xd, sd, id, od, d0, d1);
+    children(xh, sh, ih, oh, h0, h1);
+    children(xw, sw, iw, ow, w0, w1);
+    float acc[V];
+#pragma unroll
+    for (int j = 0; j < V; ++j) acc[j] = 0.f;
+    for (int a = d0; a < d1; ++a)
+      for (int e = h0; e < h1; ++e)
+        for (int g = w0; g < w1; ++g) {
+          float f[V];
+          Vec<V>::load(dy.at((((long)b * od + a) * oh + e) * ow + g, ch), f);
+#pragma unroll
+          for (int j = 0; j < V; ++j) acc[j] += f[j];
+        }
+    Vec<V>::store(dx.at((((long)b * id + xd) * ih + xh) * iw + xw, ch), acc);
+  }
+}
+
+// ------------------------------------------------------------------------------------ copies
+template <int V>
+__global__ void copy_kernel(long npos, int c, View src, View dst) {
+  const int cv = c / V;
+  const long total = npos * cv;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const long pos = i / cv;
+    const int ch = (int)(i % cv) * V;
+    if (V == 8)
+      *reinterpret_cast<uint4*>(dst.at(pos, ch)) = *reinterpret_cast<const uint4*>(src.at(pos, ch));
+    else
+      *dst.at(pos, ch) = *src.at(pos, ch);
+  }
+}
+
+// ------------------------------------------------------------------------------------ column sums
+// Generic "elementwise + per-channel reduction" skeleton. blockDim = 256; thread t owns channel
+// vector (t % cvb) of the block's channel window and walks positions with stride rows = 256 / cvb.
+template <int V, int NRED, bool DO_RED, class OutT, class F>
+__device__ __forceinline__ void column_pass(long npos, int c, long chunk, F f, OutT* red_out[NRED]) {
+  const int cv = c / V;
+  const int cvb = cv < 256 ? cv : 256;  // channel vectors per block window
+  const int rows = 256 / cvb;
+  const int t_cv = threadIdx.x % cvb, t_row = threadIdx.x / cvb;
+  const int windows = (cv + cvb - 1) / cvb;
+  const int win = blockIdx.y % windows;
+  const int my_cv = win * cvb + t_cv;
+  float acc[NRED][V];
+#pragma unroll
+  for (int k = 0; k < NRED; ++k)
+#pragma unroll
+    for (int j = 0; j < V; ++j) acc[k][j] = 0.f;
+  const long pbeg = (long)blockIdx.x * chunk;
+  const long pend = pbeg + chunk < npos ? pbeg + chunk : npos;
+  if (t_row < rows && my_cv < cv)
+    for (long pos = pbeg + t_row; pos < pend; pos += rows) f(pos, my_cv * V, acc);
+  if (!DO_RED) return;
+  __shared__ float sred[256 * 8];
+  for (int k = 0; k < NRED; ++k) {
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < V; ++j) sred[threadIdx.x * V + j] = acc[k][j];
+    __syncthreads();
+    if (t_row == 0 && my_cv < cv) {
+#pragma unroll
+      for (int j = 0; j < V; ++j) {
+        float s = 0.f;
+        for (int r = 0; r < rows; ++r) s += sred[(r * cvb + t_cv) * V + j];
+        atomicAdd(red_out[k] + my_cv * V + j, (OutT)s);
+      }
+    }
+  }
+}
+static inline void column_grid(long npos, int c, int V, dim3& grid, long& chunk) {
+  const int cv = c / V;
+  const int cvb = cv < 256 ? cv : 256;
+  const int windows = (cv + cvb - 1) / cvb;
+  long want = 148L * 8 / windows;
+  if (want < 1) want = 1;
+  chunk = (npos + want - 1) / want;
+  const int rows = 256 / cvb;
+  if (chunk < 4L * rows) chunk = 4L * rows;
+  grid = dim3((unsigned)((npos + chunk - 1) / chunk), (unsigned)windows);
+}
+
+template <int V, bool MASK, bool BIAS>
+__global__ void __launch_bounds__(256)
+    relu_bwd_kernel(long npos, int c, long chunk, View dy, View a, View dz, float* db) {
+  float* outs[1] = {db};
+  auto f = [&](long pos, int ch, float(*acc)[V]) {
+    float g[V];
+    Vec<V>::load(dy.at(pos, ch), g);
+    if (MASK) {
+      float av[V];
+      Vec<V>::load(a.at(pos, ch), av);
+#pragma unroll
+      for (int j = 0; j < V; ++j)
+        if (!(av[j] > 0.f)) g[j] = 0.f;
+      Vec<V>::store(dz.at(pos, ch), g);
+    }
+    if (BIAS) {
+#pragma unroll
+      for (int j = 0; j < V; ++j) acc[0][j] += g[j];
+    }
+  };
+  column_pass<V, 1, BIAS, float>(npos, c, chunk, f, outs);
+}
+
+// ------------------------------------------------------------------------------------ layout
+__global__ void nchw_to_cl_kernel(int n, int c, long spatial, const float* src, View dst) {
+  const long total = (long)n * spatial;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const long b = i / spatial, s = i % spatial;
+    for (int ch = 0; ch < c; ++ch)
+      *dst.at(i, ch) = __float2bfloat16(src[(b * c + ch) * spatial + s]);
+  }
+}
+__global__ void cl_to_nchw_kernel(int n, int c, long spatial, View src, float* dst) {
+  const long total = (long)n * spatial;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const long b = i / spatial, s = i % spatial;
+    for (int ch = 0; ch < c; ++ch)
+      dst[(b * c + ch) * spatial + s] = __bfloat162float(*src.at(i, ch));
+  }
+}
+
+// ------------------------------------------------------------------------------------ GroupNorm
+// sums: double [n][2][c] per-sample per-channel (sum x, sum x^2); finalize folds channels -> groups
+template <int V>
+__global__ void __launch_bounds__(256)
+    gn_sums_kernel(long spatial, int c, long chunk, View x, double* sums) {
+  const int b = blockIdx.z;
+  double* outs[2] = {sums + (long)b * c * 2, sums + (long)b * c * 2 + c};
+  auto f = [&](long pos, int ch, float(*acc)[V]) {
+    float xv[V];
+    Vec<V>::load(x.at((long)b * spatial + pos, ch), xv);
+#pragma unroll
+    for (int j = 0; j < V; ++j) { acc[0][j] += xv[j]; acc[1][j] += xv[j] * xv[j]; }
+  };
+  column_pass<V, 2, true, double>(spatial, c, chunk, f, outs);
+}
+__global__ void gn_finalize_kernel(int n, int c, int groups, double count, float eps,
+                                   const double* sums, float* stats) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * groups) return;
+  const int b = i / groups, g = i % groups, cpg = c / groups;
+  double s1 = 0, s2 = 0;
+  for (int ch = g * cpg; ch < (g + 1) * cpg; ++ch) {
+    s1 += sums[(long)b * c * 2 + ch];
+    s2 += sums[(long)b * c * 2 + c + ch];
+  }
+  const double mean = s1 / count;
+  double var = s2 / count - mean * mean;
+  if (var < 0) var = 0;
+  stats[2 * i] = (float)mean;
+  stats[2 * i + 1] = (float)(1.0 / sqrt(var + (double)eps));
+}
+template <int V>
+__global__ void gn_apply_kernel(int n, long spatial, int c, int groups, View x, const float* stats,
+                                const float* gamma, const float* beta, int relu, View y) {
+  const int cv = c / V, cpg = c / groups;
+  const long total = (long)n * spatial * cv;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const long pos = i / cv;
+    const int ch = (int)(i % cv) * V;
+    const int b = (int)(pos / spatial);
+    float f[V];
+    Vec<V>::load(x.at(pos, ch), f);
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+      const int g = (ch + j) / cpg;
+      const float mean = stats[(b * groups + g) * 2], rstd = stats[(b * groups + g) * 2 + 1];
+      float v = (f[j] - mean) * rstd * gamma[ch + j] + beta[ch + j];
+      f[j] = relu ? fmaxf(v, 0.f) : v;
+    }
+    Vec<V>::store(y.at(pos, ch), f);
+  }
+}
+// per-sample per-channel sums: s[n][c][2] = (sum dy, sum dy * xhat)
+template <int V>
+__global__ void __launch_bounds__(256)
+    gn_bwd_reduce_kernel(long spatial, int c, int groups, long chunk, View x, View dy,
+                         const float* stats, float* s) {
+  const int b = blockIdx.z;
+  const int cpg = c / groups;
+  float* outs[2] = {s + (long)b * c * 2, s + (long)b * c * 2 + c};
+  auto f = [&](long pos, int ch, float(*acc)[V]) {
+    float xv[V], g[V];
+    const long gp = (long)b * spatial + pos;
+    Vec<V>::load(x.at(gp, ch), xv);
+    Vec<V>::load(dy.at(gp, ch), g);
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+      const int gi = (ch + j) / cpg;
+      const float mean = stats[(b * groups + gi) * 2], rstd = stats[(b * groups + gi) * 2 + 1];
+      acc[0][j] += g[j];
+      acc[1][j] += g[j] * (xv[j] - mean) * rstd;
+    }
+  };
+  column_pass<V, 2, true, float>(spatial, c, chunk, f, outs);
+}
+// gsum[n][g][2] = (sum_c gamma*s1, sum_c gamma*s2); dgamma += sum_n s2; dbeta += sum_n s1
+__global__ void gn_bwd_finalize_kernel(int n, int c, int groups, const float* gamma, const float* s,
+                                       float* gsum, float* dgamma, float* dbeta) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int cpg = c / groups;
+  if (i < n * groups) {
+    const int b = i / groups, g = i % groups;
+    float a = 0.f, bb = 0.f;
+    for (int ch = g * cpg; ch < (g + 1) * cpg; ++ch) {
+      a += gamma[ch] * s[(long)b * c * 2 + ch];
+      bb += gamma[ch] * s[(long)b * c * 2 + c + ch];
+    }
+    gsum[2 * i] = a;
+    gsum[2 * i + 1] = bb;
+  }
+  if (i < c) {
+    float a = 0.f, bb = 0.f;
+    for (int b = 0; b < n; ++b) {
+      a += s[(long)b * c * 2 + i];
+      bb += s[(long)b * c * 2 + c + i];
+    }
+    if (dbeta) atomicAdd(dbeta + i, a);
+    if (dgamma) atomicAdd(dgamma + i, bb);
+  }
+}
+template <int V>
+__global__ void gn_bwd_apply_kernel(int n, long spatial, int c, int groups, View x, View dy,
+                                    const float* stats, const float* gamma, const float* gsum,
+                                    View dx) {
+  const int cv = c / V, cpg = c / groups;
+  const float inv_m = 1.f / ((float)cpg * (float)spatial);
+  const long total = (long)n * spatial * cv;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const long pos = i / cv;
+    const int ch = (int)(i % cv) * V;
+    const int b = (int)(pos / spatial);
+    float xv[V], g[V];
+    Vec<V>::load(x.at(pos, ch), xv);
+    Vec<V>::load(dy.at(pos, ch), g);
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+      const int gi = b * groups + (ch + j) / cpg;
+      const float mean = stats[gi * 2], rstd = stats[gi * 2 + 1];
+      const float xhat = (xv[j] - mean) * rstd;
+      g[j] = rstd * (g[j] * gamma[ch + j] - (gsum[gi * 2] + xhat * gsum[gi * 2 + 1]) * inv_m);
+    }
+    Vec<V>::store(dx.at(pos, ch), g);
+  }
+}
+
+// ------------------------------------------------------------------------------------ BatchNorm
+template <int V>
+__global__ void __launch_bounds__(256)
+    bn_stats_kernel(long npos, int c, long chunk, View x, double* sums) {
+  double* outs[2] = {sums, sums + c};
+  auto f = [&](long pos, int ch, float(*acc)[V]) {
+    float xv[V];
+    Vec<V>::load(x.at(pos, ch), xv);
+#pragma unroll
+    for (int j = 0; j < V; ++j) { acc[0][j] += xv[j]; acc[1][j] += xv[j] * xv[j]; }
+  };
+  column_pass<V, 2, true, double>(npos, c, chunk, f, outs);
+}
+template <int V>
+__global__ void bn_apply_kernel(long npos, int c, View x, const float* mean, const float* rstd,
+                                const float* gamma, const float* beta, int relu, View y) {
+  const int cv = c / V;
+  const long total = npos * cv;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const long pos = i / cv;
+    const int ch = (int)(i % cv) * V;
+    float f[V];
+    Vec<V>::load(x.at(pos, ch), f);
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+      const float v = (f[j] - mean[ch + j]) * rstd[ch + j] * gamma[ch + j] + beta[ch + j];
+      f[j] = relu ? fmaxf(v, 0.f) : v;
+    }
+    Vec<V>::store(y.at(pos, ch), f);
+  }
+}
+template <int V>
+__global__ void __launch_bounds__(256)
+    bn_bwd_reduce_kernel(long npos, int c, long chunk, View x, View dy, View ro, const float* mean,
+                         const float* rstd, float* red) {
+  float* outs[2] = {red, red + c};
+  auto f = [&](long pos, int ch, float(*acc)[V]) {
+    float xv[V], g[V];
+    Vec<V>::load(x.at(pos, ch), xv);
+    Vec<V>::load(dy.at(pos, ch), g);
+    if (ro.p) {
+      float o[V];
+      Vec<V>::load(ro.at(pos, ch), o);
+#pragma unroll
+      for (int j = 0; j < V; ++j)
+        if (!(o[j] > 0.f)) g[j] = 0.f;
+    }
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+      acc[0][j] += g[j];
+      acc[1][j] += g[j] * (xv[j] - mean[ch + j]) * rstd[ch + j];
+    }
+  };
+  column_pass<V, 2, true, float>(npos, c, chunk, f, outs);
+}
+template <int V>
+__global__ void bn_bwd_apply_kernel(long npos, int c, View x, View dy, View ro, const float* mean,
+                                    const float* rstd, const float* gamma, const float* red,
+                                    View dx) {
+  const int cv = c / V;
+  const float inv_m = 1.f / (float)npos;
+  const long total = npos * cv;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const long pos = i / cv;
+    const int ch = (int)(i % cv) * V;
+    float xv[V], g[V];
+    Vec<V>::load(x.at(pos, ch), xv);
+    Vec<V>::load(dy.at(pos, ch), g);
+    if (ro.p) {
+      float o[V];
+      Vec<V>::load(ro.at(pos, ch), o);
+#pragma unroll
+      for (int j = 0; j < V; ++j)
+        if (!(o[j] > 0.f)) g[j] = 0.f;
+    }
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+      const float xhat = (xv[j] - mean[ch + j]) * rstd[ch + j];
+      g[j] = gamma[ch + j] * rstd[ch + j] * (g[j] - red[ch + j] * inv_m - xhat * red[c + ch + j] * inv_m);
+    }
+    Vec<V>::store(dx.at(pos, ch), g);
+  }
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+#define GRID1D(total) (blocks_for((total), 256) < 148u * 16u ? blocks_for((total), 256) : 148u * 16u)
+#define DISPATCH_V(cond, KERNEL, GRID, ...)                                  \
+  do {                                                                       \
+    if (cond)                                                                \
+      KERNEL<8><<<GRID, 256, 0, (cudaStream_t)stream>>>(__VA_ARGS__);        \
+    else                                                                     \
+      KERNEL<1><<<GRID, 256, 0, (cudaStream_t)stream>>>(__VA_ARGS__);        \
+    B200_LAUNCH_CHECK();                                                     \
+  } while (0)
+
+extern "C" {
+
+int b200_maxpool2_fwd(int32_t n, int32_t d, int32_t h, int32_t w, int32_t c, int32_t pool_d,
+                      b200_view x, b200_view y, b200_stream_t stream) {
+  if (pool_d != 1 && pool_d != 2) return B200_ERR_BAD_ARG;
+  const long total = (long)n * (d / pool_d) * (h / 2) * (w / 2) * c;
+  if (total <= 0) return B200_OK;
+  const bool v = vec8(c, x) && vec8(c, y);
+  DISPATCH_V(v, maxpool_fwd_kernel, GRID1D(total / (v ? 8 : 1)), n, d, h, w, c, pool_d, mk(x), mk(y));
+  return B200_OK;
+}
+int b200_maxpool2_bwd(int32_t n, int32_t d, int32_t h, int32_t w, int32_t c, int32_t pool_d,
+                      b200_view x, b200_view dy, b200_view dx, b200_stream_t stream) {
+  if (pool_d != 1 && pool_d != 2) return B200_ERR_BAD_ARG;
+  const long total = (long)n * d * h * w * c;
+  if (total <= 0) return B200_OK;
+  const bool v = vec8(c, x) && vec8(c, dy) && vec8(c, dx);
+  DISPATCH_V(v, maxpool_bwd_kernel, GRID1D(total / (v ? 8 : 1)), n, d, h, w, c, pool_d, mk(x), mk(dy),
+             mk(dx));
+  return B200_OK;
+}
+int b200_upsample_nearest_fwd(int32_t n, int32_t id, int32_t ih, int32_t iw, int32_t od, int32_t oh,
+                              int32_t ow, int32_t c, b200_view x, b200_view y, b200_stream_t stream) {
+  const long total = (long)n * od * oh * ow * c;
+  if (total <= 0) return B200_OK;
+  const bool v = vec8(c, x) && vec8(c, y);
+  DISPATCH_V(v, upsample_fwd_kernel, GRID1D(total / (v ? 8 : 1)), n, id, ih, iw, od, oh, ow, c, mk(x),
+             mk(y));
+  return B200_OK;
+}
+int b200_upsample_nearest_bwd(int32_t n, int32_t id, int32_t ih, int32_t iw, int32_t od, int32_t oh,
+                              int32_t ow, int32_t c, b200_view dy, b200_view dx,
+                              b200_stream_t stream) {
+  const long total = (long)n * id * ih * iw * c;
+  if (total <= 0) return B200_OK;
+  const bool v = vec8(c, dy) && vec8(c, dx);
+  DISPATCH_V(v, upsample_bwd_kernel, GRID1D(total / (v ? 8 : 1)), n, id, ih, iw, od, oh, ow, c, mk(dy),
+             mk(dx));
+  return B200_OK;
+}
+int b200_copy_channels(int64_t npos, int32_t c, b200_view src, b200_view dst, b200_stream_t stream) {
+  const long total = (long)npos * c;
+  if (total <= 0) return B200_OK;
+  const bool v = vec8(c, src) && vec8(c, dst);
+  DISPATCH_V(v, copy_kernel, GRID1D(total / (v ? 8 : 1)), (long)npos, c, mk(src), mk(dst));
+  return B200_OK;
+}
+
+int b200_relu_bwd(int64_t npos, int32_t c, b200_view dy, b200_view a, b200_view dz, float* db,
+                  b200_stream_t stream) {
+  if (npos <= 0) return B200_OK;
+  const bool v = vec8(c, dy) && vec8(c, a) && vec8(c, dz);
+  dim3 grid;
+  long chunk;
+  column_grid(npos, c, v ? 8 : 1, grid, chunk);
+  if (v) {
+    if (db) relu_bwd_kernel<8, true, true><<<grid, 256, 0, (cudaStream_t)stream>>>(npos, c, chunk, mk(dy), mk(a), mk(dz), db);
+    else relu_bwd_kernel<8, true, false><<<grid, 256, 0, (cudaStream_t)stream>>>(npos, c, chunk, mk(dy), mk(a), mk(dz), db);
+  } else {
+    if (db) relu_bwd_kernel<1, true, true><<<grid, 256, 0, (cudaStream_t)stream>>>(npos, c, chunk, mk(dy), mk(a), mk(dz), db);
+    else relu_bwd_kernel<1, true, false><<<grid, 256, 0, (cudaStream_t)stream>>>(npos, c, chunk, mk(dy), mk(a), mk(dz), db);
+  }
+  B200_LAUNCH_CHECK();
+  return B200_OK;
+}
+int b200_bias_grad(int64_t npos, int32_t c, b200_view dy, float* db, b200_stream_t stream) {
+  if (npos <= 0 || !db) return B200_OK;
+  const bool v = vec8(c, dy);
+  dim3 grid;
+  long chunk;
+  column_grid(npos, c, v ? 8 : 1, grid, chunk);
+  if (v) relu_bwd_kernel<8, false, true><<<grid, 256, 0, (cudaStream_t)stream>>>(npos, c, chunk, mk(dy), mk(dy), mk(dy), db);
+  else relu_bwd_kernel<1, false, true><<<grid, 256, 0, (cudaStream_t)stream>>>(npos, c, chunk, mk(dy), mk(dy), mk(dy), db);
+  B200_LAUNCH_CHECK();
+  return B200_OK;
+}
+
+int b200_nchw_f32_to_cl_bf16(int32_t n, int32_t c, int64_t spatial, const float* src, b200_view dst,
+                             b200_stream_t stream) {
+  const long total = (long)n * spatial;
+  if (total <= 0) return B200_OK;
+  nchw_to_cl_kernel<<<GRID1D(total), 256, 0, (cudaStream_t)stream>>>(n, c, (long)spatial, src, mk(dst));
+  B200_LAUNCH_CHECK();
+  return B200_OK;
+}
+int b200_cl_bf16_to_nchw_f32(int32_t n, int32_t c, int64_t spatial, b200_view src, float* dst,
+                             b200_stream_t stream) {
+  const long total = (long)n * spatial;
+  if (total <= 0) return B200_OK;
+  cl_to_nchw_kernel<<<GRID1D(total), 256, 0, (cudaStream_t)stream>>>(n, c, (long)spatial, mk(src), dst);
+  B200_LAUNCH_CHECK();
+  return B200_OK;
+}
+
+int b200_gn_stats(int32_t n, int64_t spatial, int32_t c, int32_t groups, float eps, b200_view x,
+                  double* sums, float* stats, b200_stream_t stream) {
+  if (groups <= 0 || c % groups) return B200_ERR_BAD_ARG;
+  if ((long)n * spatial <= 0) return B200_OK;
+  const bool v = vec8(c, x);
+  dim3 grid;
+  long chunk;
+  column_grid(spatial, c, v ? 8 : 1, grid, chunk);
+  grid.z = n;
+  if (v) gn_sums_kernel<8><<<grid, 256, 0, (cudaStream_t)stream>>>((long)spatial, c, chunk, mk(x), sums);
+  else gn_sums_kernel<1><<<grid, 256, 0, (cudaStream_t)stream>>>((long)spatial, c, chunk, mk(x), sums);
+  B200_LAUNCH_CHECK();
+  gn_finalize_kernel<<<(n * groups + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
+      n, c, groups, (double)(c / groups) * (double)spatial, eps, sums, stats);
+  B200_LAUNCH_CHECK();
+  return B200_OK;
+}
+int b200_gn_apply(int32_t n, int64_t spatial, int32_t c, int32_t groups, b200_view x,
+                  const float* stats, const float* gamma, const float* beta, int32_t relu,
+                  b200_view y, b200_stream_t stream) {
+  const long total = (long)n * spatial * c;
+  if (total <= 0) return B200_OK;
+  const bool v = vec8(c, x) && vec8(c, y);
+  DISPATCH_V(v, gn_apply_kernel, GRID1D(total / (v ? 8 : 1)), n, (long)spatial, c, groups, mk(x), stats,
+             gamma, beta, relu, mk(y));
+  return B200_OK;
+}
+int b200_gn_bwd(int32_t n, int64_t spatial, int32_t c, int32_t groups, b200_view x,
+                const float* stats, const float* gamma, b200_view dy, b200_view dx, float* dgamma,
+                float* dbeta, float* scratch, b200_stream_t stream) {
+  if (groups <= 0 || c % groups) return B200_ERR_BAD_ARG;
+  const long total = (long)n * spatial * c;
+  if (total <= 0) return B200_OK;
+  const bool v = vec8(c, x) && vec8(c, dy) && vec8(c, dx);
+  float* s = scratch;                    // [n][2][c]
+  float* gsum = scratch + (long)n * c * 2;  // [n][groups][2]
+  dim3 grid;
+  long chunk;
+  column_grid(spatial, c, v ? 8 : 1, grid, chunk);
+  grid.z = n;
+  if (v) gn_bwd_reduce_kernel<8><<<grid, 256, 0, (cudaStream_t)stream>>>((long)spatial, c, groups, chunk, mk(x), mk(dy), stats, s);
+  else gn_bwd_reduce_kernel<1><<<grid, 256, 0, (cudaStream_t)stream>>>((long)spatial, c, groups, chunk, mk(x), mk(dy), stats, s);
+  B200_LAUNCH_CHECK();
+  const int work = n * groups > c ? n * groups : c;
+  gn_bwd_finalize_kernel<<<(work + 127) / 128, 128, 0, (cudaStream_t)stream>>>(n, c, groups, gamma, s, gsum, dgamma, dbeta);
+  B200_LAUNCH_CHECK();
+  DISPATCH_V(v, gn_bwd_apply_kernel, GRID1D(total / (v ? 8 : 1)), n, (long)spatial, c, groups, mk(x),
+             mk(dy), stats, gamma, gsum, mk(dx));
+  return B200_OK;
+}
+
+int b200_bn_stats(int64_t npos, int32_t c, b200_view x, double* sums, b200_stream_t stream) {
+  if (npos <= 0) return B200_OK;
+  const bool v = vec8(c, x);
+  dim3 grid;
+  long chunk;
+  column_grid(npos, c, v ? 8 : 1, grid, chunk);
+  if (v) bn_stats_kernel<8><<<grid, 256, 0, (cudaStream_t)stream>>>((long)npos, c, chunk, mk(x), sums);
+  else bn_stats_kernel<1><<<grid, 256, 0, (cudaStream_t)stream>>>((long)npos, c, chunk, mk(x), sums);
+  B200_LAUNCH_CHECK();
+  return B200_OK;
+}
+int b200_bn_apply(int64_t npos, int32_t c, b200_view x, const float* mean, const float* rstd,
+                  const float* gamma, const float* beta, int32_t relu, b200_view y,
+                  b200_stream_t stream) {
+  const long total = (long)npos * c;
+  if (total <= 0) return B200_OK;
+  const bool v = vec8(c, x) && vec8(c, y);
+  DISPATCH_V(v, bn_apply_kernel, GRID1D(total / (v ? 8 : 1)), (long)npos, c, mk(x), mean, rstd, gamma,
+             beta, relu, mk(y));
+  return B200_OK;
+}
+int b200_bn_bwd_reduce(int64_t npos, int32_t c, b200_view x, b200_view dy, b200_view relu_out,
+                       const float* mean, const float* rstd, float* red, b200_stream_t stream) {
+  if (npos <= 0) return B200_OK;
+  const bool v = vec8(c, x) && vec8(c, dy) && (!relu_out.ptr || vec8(c, relu_out));
+  dim3 grid;
+  long chunk;
+  column_grid(npos, c, v ? 8 : 1, grid, chunk);
+  if (v) bn_bwd_reduce_kernel<8><<<grid, 256, 0, (cudaStream_t)stream>>>((long)npos, c, chunk, mk(x), mk(dy), mk(relu_out), mean, rstd, red);
+  else bn_bwd_reduce_kernel<1><<<grid, 256, 0, (cudaStream_t)stream>>>((long)npos, c, chunk, mk(x), mk(dy), mk(relu_out), mean, rstd, red);
+  B200_LAUNCH_CHECK();
+  return B200_OK;
+}
+int b200_bn_bwd_apply(int64_t npos, int32_t c, b200_view x, b200_view dy, b200_view relu_out,
+                      const float* mean, const float* rstd, const float* gamma, const float* red,
+                      b200_view dx, b200_stream_t stream) {
+  const long total = (long)npos * c;
+  if (total <= 0) return B200_OK;
+  const bool v = vec8(c, x) && vec8(c, dy) && vec8(c, dx) && (!relu_out.ptr || vec8(c, relu_out));
+  DISPATCH_V(v, bn_bwd_apply_kernel, GRID1D(total / (v ? 8 : 1)), (long)npos, c, mk(x), mk(dy),
+             mk(relu_out), mean, rstd, gamma, red, mk(dx));
+  return B200_OK;
+}
+
+}  // extern "C"

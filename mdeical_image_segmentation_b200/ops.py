@@ -1,0 +1,463 @@
+"""Raw (non-autograd) host wrappers over the C ABI.
+
+Activations live in HBM as channels-last bf16 ``(N, D, H, W, Ctot)`` buffers (``D == 1`` for 2D);
+a :class:`CL` names a channel slice ``[coff, coff + c)`` of such a buffer, which is how producers
+write straight into their half of a skip-concat buffer.  PyTorch is used only for device memory and
+the current stream.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import ConvDesc, ConvTDesc, DeconvDesc, View, call
+
+bf16 = torch.bfloat16
+
+
+def _stream() -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t: Optional[torch.Tensor]) -> C.c_void_p:
+    return C.c_void_p(0 if t is None else t.data_ptr())
+
+
+def require_cuda(t: torch.Tensor) -> None:
+    if not t.is_cuda:
+        raise RuntimeError("mdeical_image_segmentation_b200 runs on sm_100a CUDA tensors only "
+                           "(no CPU fallback): move the model and inputs to a B200 device")
+
+
+class CL:
+    """Channel slice of a channels-last bf16 buffer of shape (N, D, H, W, Ctot)."""
+    __slots__ = ("buf", "c", "coff")
+
+    def __init__(self, buf: torch.Tensor, c: Optional[int] = None, coff: int = 0):
+        assert buf.dim() == 5 and buf.dtype == bf16 and buf.is_contiguous(), (buf.shape, buf.dtype)
+        self.buf = buf
+        self.coff = coff
+        self.c = buf.shape[4] - coff if c is None else c
+        assert 0 <= coff and coff + self.c <= buf.shape[4]
+
+    @staticmethod
+    def empty(n, d, h, w, c, device) -> "CL":
+        return CL(torch.empty((n, d, h, w, c), dtype=bf16, device=device))
+
+    @property
+    def n(self): return self.buf.shape[0]
+    @property
+    def d(self): return self.buf.shape[1]
+    @property
+    def h(self): return self.buf.shape[2]
+    @property
+    def w(self): return self.buf.shape[3]
+    @property
+    def ctot(self): return self.buf.shape[4]
+    @property
+    def spatial(self): return self.d * self.h * self.w
+    @property
+    def npos(self): return self.n * self.spatial
+    @property
+    def dims(self) -> Tuple[int, int, int, int]: return (self.n, self.d, self.h, self.w)
+    @property
+    def device(self): return self.buf.device
+
+    def view(self) -> View:
+        return View(self.buf.data_ptr(), self.ctot, self.coff)
+
+    def dense(self) -> torch.Tensor:
+        return self.buf[..., self.coff:self.coff + self.c]
+
+    def slice(self, coff: int, c: int) -> "CL":
+        return CL(self.buf, c, self.coff + coff)
+
+    def is_full(self) -> bool:
+        return self.coff == 0 and self.c == self.ctot
+
+    def to_nchw(self) -> torch.Tensor:
+        """fp32 (N, C, [D,] H, W) copy — test / debugging helper."""
+        t = self.dense().float().permute(0, 4, 1, 2, 3).contiguous()
+        return t
+
+    def new_like(self, c: Optional[int] = None) -> "CL":
+        return CL.empty(self.n, self.d, self.h, self.w, self.c if c is None else c, self.device)
+
+
+_NULL_VIEW = View(0, 0, 0)
+
+
+# ------------------------------------------------------------------------------------- convolution
+def conv_desc(x: CL, c_out: int, k: Tuple[int, int, int], out_ctot: int, out_coff: int,
+              relu: bool = False, impl: int = 0) -> ConvDesc:
+    return ConvDesc(x.n, x.d, x.h, x.w, x.c, c_out, k[0], k[1], k[2], x.ctot, x.coff,
+                    out_ctot, out_coff, int(relu), impl)
+
+
+def conv_repack_weight(w: torch.Tensor, need_bwd: bool = True):
+    """w fp32 (c_out, c_in, [kd,] kh, kw) -> (wp_fwd [tap][c_out][c_in], wp_bwd [tap'][c_in][c_out])."""
+    require_cuda(w)
+    c_out, c_in = w.shape[0], w.shape[1]
+    k = tuple(w.shape[2:])
+    k = (1,) * (3 - len(k)) + k
+    ntaps = k[0] * k[1] * k[2]
+    w = w.detach().contiguous().float()
+    fwd = torch.empty((ntaps, c_out, c_in), dtype=bf16, device=w.device)
+    bwd = torch.empty((ntaps, c_in, c_out), dtype=bf16, device=w.device) if need_bwd else None
+    d = ConvDesc(1, 1, 1, 1, c_in, c_out, k[0], k[1], k[2], c_in, 0, c_out, 0, 0, 0)
+    call("b200_conv_repack_weight", C.byref(d), _p(w), _p(fwd), _p(bwd), _stream())
+    return fwd, bwd, k
+
+
+def conv_fwd(x: CL, wp_fwd: torch.Tensor, k, bias: Optional[torch.Tensor], relu: bool,
+             out: Optional[CL] = None, impl: int = 0) -> CL:
+    c_out = wp_fwd.shape[1]
+    if out is None:
+        out = CL.empty(x.n, x.d, x.h, x.w, c_out, x.device)
+    assert out.c == c_out and out.dims == x.dims and wp_fwd.shape[2] == x.c
+    d = conv_desc(x, c_out, k, out.ctot, out.coff, relu, impl)
+    call("b200_conv_fwd", C.byref(d), _p(x.buf), _p(wp_fwd), _p(bias), _p(out.buf), _stream())
+    return out
+
+
+def conv_bwd_data(dy: CL, wp_bwd: torch.Tensor, k, mask: Optional[CL] = None,
+                  out: Optional[CL] = None, impl: int = 0) -> CL:
+    c_in, c_out = wp_bwd.shape[1], wp_bwd.shape[2]
+    assert dy.c == c_out
+    if out is None:
+        out = CL.empty(dy.n, dy.d, dy.h, dy.w, c_in, dy.device)
+    if mask is not None:
+        assert mask.ctot == out.ctot and mask.coff == out.coff and mask.dims == out.dims
+    d = ConvDesc(dy.n, dy.d, dy.h, dy.w, c_in, c_out, k[0], k[1], k[2], out.ctot, out.coff,
+                 dy.ctot, dy.coff, 0, impl)
+    call("b200_conv_bwd_data", C.byref(d), _p(dy.buf), _p(wp_bwd),
+         _p(None if mask is None else mask.buf), _p(out.buf), _stream())
+    return out
+
+
+def conv_bwd_weight(x: CL, dy: CL, k, w_shape, impl: int = 0) -> torch.Tensor:
+    dw = torch.zeros(w_shape, dtype=torch.float32, device=x.device)
+    d = ConvDesc(x.n, x.d, x.h, x.w, x.c, dy.c, k[0], k[1], k[2], x.ctot, x.coff,
+                 dy.ctot, dy.coff, 0, impl)
+    call("b200_conv_bwd_weight", C.byref(d), _p(x.buf), _p(dy.buf), _p(dw), _stream())
+    return dw
+
+
+# ------------------------------------------------------------------------------------- convT 2x2 s2
+def convt_repack_weight(w: torch.Tensor):
+    require_cuda(w)
+    c_in, c_out = w.shape[0], w.shape[1]
+    w = w.detach().contiguous().float()
+    fwd = torch.empty((1, 4 * c_out, c_in), dtype=bf16, device=w.device)
+    bwd = torch.empty((4, c_in, c_out), dtype=bf16, device=w.device)
+    d = ConvTDesc(1, 1, 1, c_in, c_out, c_in, 0, c_out, 0, 0)
+    call("b200_convt2x2_repack_weight", C.byref(d), _p(w), _p(fwd), _p(bwd), _stream())
+    return fwd, bwd
+
+
+def convt_fwd(x: CL, wp_fwd, bias, out: Optional[CL] = None, impl: int = 0) -> CL:
+    assert x.d == 1
+    c_out = wp_fwd.shape[1] // 4
+    if out is None:
+        out = CL.empty(x.n, 1, 2 * x.h, 2 * x.w, c_out, x.device)
+    assert out.c == c_out and out.h == 2 * x.h and out.w == 2 * x.w
+    d = ConvTDesc(x.n, x.h, x.w, x.c, c_out, x.ctot, x.coff, out.ctot, out.coff, impl)
+    call("b200_convt2x2_fwd", C.byref(d), _p(x.buf), _p(wp_fwd), _p(bias), _p(out.buf), _stream())
+    return out
+
+
+def convt_bwd_data(dy: CL, wp_bwd, mask: Optional[CL] = None, out: Optional[CL] = None,
+                   impl: int = 0) -> CL:
+    c_in, c_out = wp_bwd.shape[1], wp_bwd.shape[2]
+    assert dy.c == c_out and dy.d == 1
+    h, w = dy.h // 2, dy.w // 2
+    if out is None:
+        out = CL.empty(dy.n, 1, h, w, c_in, dy.device)
+    d = ConvTDesc(dy.n, h, w, c_in, c_out, out.ctot, out.coff, dy.ctot, dy.coff, impl)
+    call("b200_convt2x2_bwd_data", C.byref(d), _p(dy.buf), _p(wp_bwd),
+         _p(None if mask is None else mask.buf), _p(out.buf), _stream())
+    return out
+
+
+def convt_bwd_weight(x: CL, dy: CL, impl: int = 0) -> torch.Tensor:
+    dw = torch.zeros((x.c, dy.c, 2, 2), dtype=torch.float32, device=x.device)
+    d = ConvTDesc(x.n, x.h, x.w, x.c, dy.c, x.ctot, x.coff, dy.ctot, dy.coff, impl)
+    call("b200_convt2x2_bwd_weight", C.byref(d), _p(x.buf), _p(dy.buf), _p(dw), _stream())
+    return dw
+
+
+# ------------------------------------------------------------------------------------- deconv k3 s2 p1
+def deconv_repack_weight(w: torch.Tensor):
+    require_cuda(w)
+    c_in, c_out = w.shape[0], w.shape[1]
+    k = tuple(w.shape[2:])
+    ntaps = 1
+    for v in k:
+        ntaps *= v
+    w = w.detach().contiguous().float()
+    wp = torch.empty((ntaps, c_in, c_out), dtype=bf16, device=w.device)
+    is3d = len(k) == 3
+    d = DeconvDesc(1, 2 if is3d else 1, 2, 2, 3 if is3d else 1, 3, 3, c_in, c_out, c_in, 0, c_out, 0)
+    call("b200_deconv3s2_repack_weight", C.byref(d), _p(w), _p(wp), _stream())
+    return wp
+
+
+def _deconv_desc(x: CL, y: CL) -> DeconvDesc:
+    return DeconvDesc(x.n, x.d, x.h, x.w, y.d, y.h, y.w, x.c, y.c, x.ctot, x.coff, y.ctot, y.coff)
+
+
+def deconv_out_dims(x: CL):
+    return (1 if x.d == 1 else 2 * x.d - 1, 2 * x.h - 1, 2 * x.w - 1)
+
+
+def deconv_fwd(x: CL, wp, is3d: bool) -> CL:
+    od = 2 * x.d - 1 if is3d else 1
+    y = CL.empty(x.n, od, 2 * x.h - 1, 2 * x.w - 1, wp.shape[2], x.device)
+    call("b200_deconv3s2_fwd", C.byref(_deconv_desc(x, y)), _p(x.buf), _p(wp), _p(y.buf), _stream())
+    return y
+
+
+def deconv_bwd_data(dy: CL, wp, x_dims, is3d: bool) -> CL:
+    n, d, h, w = x_dims
+    dx = CL.empty(n, d, h, w, wp.shape[1], dy.device)
+    call("b200_deconv3s2_bwd_data", C.byref(_deconv_desc(dx, dy)), _p(dy.buf), _p(wp), _p(dx.buf),
+         _stream())
+    return dx
+
+
+def deconv_bwd_weight(x: CL, dy: CL, w_shape) -> torch.Tensor:
+    dw = torch.zeros(w_shape, dtype=torch.float32, device=x.device)
+    call("b200_deconv3s2_bwd_weight", C.byref(_deconv_desc(x, dy)), _p(x.buf), _p(dy.buf), _p(dw),
+         _stream())
+    return dw
+
+
+# ------------------------------------------------------------------------------------- memory-bound ops
+def maxpool_fwd(x: CL, pool_d: int, out: Optional[CL] = None) -> CL:
+    if out is None:
+        out = CL.empty(x.n, x.d // pool_d, x.h // 2, x.w // 2, x.c, x.device)
+    call("b200_maxpool2_fwd", x.n, x.d, x.h, x.w, x.c, pool_d, x.view(), out.view(), _stream())
+    return out
+
+
+def maxpool_bwd(x: CL, dy: CL, pool_d: int, out: Optional[CL] = None) -> CL:
+    if out is None:
+        out = x.new_like()
+    call("b200_maxpool2_bwd", x.n, x.d, x.h, x.w, x.c, pool_d, x.view(), dy.view(), out.view(),
+         _stream())
+    return out
+
+
+def upsample_nearest_fwd(x: CL, size, out: Optional[CL] = None) -> CL:
+    od, oh, ow = size
+    if out is None:
+        out = CL.empty(x.n, od, oh, ow, x.c, x.device)
+    call("b200_upsample_nearest_fwd", x.n, x.d, x.h, x.w, od, oh, ow, x.c, x.view(), out.view(),
+         _stream())
+    return out
+
+
+def upsample_nearest_bwd(dy: CL, in_size, out: Optional[CL] = None) -> CL:
+    idd, ih, iw = in_size
+    if out is None:
+        out = CL.empty(dy.n, idd, ih, iw, dy.c, dy.device)
+    call("b200_upsample_nearest_bwd", dy.n, idd, ih, iw, dy.d, dy.h, dy.w, dy.c, dy.view(),
+         out.view(), _stream())
+    return out
+
+
+def copy_channels(src: CL, dst: CL) -> CL:
+    assert src.c == dst.c and src.dims == dst.dims
+    call("b200_copy_channels", src.npos, src.c, src.view(), dst.view(), _stream())
+    return dst
+
+
+def relu_bwd(dy: CL, a: CL, bias_grad: bool, out: Optional[CL] = None):
+    if out is None:
+        out = dy.new_like()
+    db = torch.zeros(dy.c, dtype=torch.float32, device=dy.device) if bias_grad else None
+    call("b200_relu_bwd", dy.npos, dy.c, dy.view(), a.view(), out.view(), _p(db), _stream())
+    return out, db
+
+
+def bias_grad(dy: CL) -> torch.Tensor:
+    db = torch.zeros(dy.c, dtype=torch.float32, device=dy.device)
+    call("b200_bias_grad", dy.npos, dy.c, dy.view(), _p(db), _stream())
+    return db
+
+
+def from_nchw(x: torch.Tensor, out: Optional[CL] = None) -> CL:
+    """fp32 (N, C, [D,] H, W) -> channels-last bf16."""
+    require_cuda(x)
+    x = x.contiguous().float()
+    n, c = x.shape[0], x.shape[1]
+    sp = tuple(x.shape[2:])
+    d, h, w = ((1,) + sp) if len(sp) == 2 else sp
+    if out is None:
+        out = CL.empty(n, d, h, w, c, x.device)
+    call("b200_nchw_f32_to_cl_bf16", n, c, d * h * w, _p(x), out.view(), _stream())
+    return out
+
+
+def to_nchw(x: CL, is3d: bool) -> torch.Tensor:
+    shape = (x.n, x.c, x.d, x.h, x.w) if is3d else (x.n, x.c, x.h, x.w)
+    out = torch.empty(shape, dtype=torch.float32, device=x.device)
+    call("b200_cl_bf16_to_nchw_f32", x.n, x.c, x.spatial, x.view(), _p(out), _stream())
+    return out
+
+
+# ------------------------------------------------------------------------------------- norms
+def gn_stats(x: CL, groups: int, eps: float) -> torch.Tensor:
+    sums = torch.zeros((x.n, 2, x.c), dtype=torch.float64, device=x.device)
+    stats = torch.empty((x.n, groups, 2), dtype=torch.float32, device=x.device)
+    call("b200_gn_stats", x.n, x.spatial, x.c, groups, eps, x.view(), _p(sums), _p(stats), _stream())
+    return stats
+
+
+def gn_apply(x: CL, groups, stats, gamma, beta, relu: bool, out: Optional[CL] = None) -> CL:
+    if out is None:
+        out = x.new_like()
+    call("b200_gn_apply", x.n, x.spatial, x.c, groups, x.view(), _p(stats), _p(gamma), _p(beta),
+         int(relu), out.view(), _stream())
+    return out
+
+
+def gn_bwd(x: CL, groups, stats, gamma, dy: CL, out: Optional[CL] = None):
+    if out is None:
+        out = x.new_like()
+    dgamma = torch.zeros(x.c, dtype=torch.float32, device=x.device)
+    dbeta = torch.zeros(x.c, dtype=torch.float32, device=x.device)
+    scratch = torch.zeros(x.n * x.c * 2 + x.n * groups * 2, dtype=torch.float32, device=x.device)
+    call("b200_gn_bwd", x.n, x.spatial, x.c, groups, x.view(), _p(stats), _p(gamma), dy.view(),
+         out.view(), _p(dgamma), _p(dbeta), _p(scratch), _stream())
+    return out, dgamma, dbeta
+
+
+def bn_stats(x: CL) -> torch.Tensor:
+    sums = torch.zeros((2, x.c), dtype=torch.float64, device=x.device)
+    call("b200_bn_stats", x.npos, x.c, x.view(), _p(sums), _stream())
+    return sums
+
+
+def bn_apply(x: CL, mean, rstd, gamma, beta, relu: bool, out: Optional[CL] = None) -> CL:
+    if out is None:
+        out = x.new_like()
+    call("b200_bn_apply", x.npos, x.c, x.view(), _p(mean), _p(rstd), _p(gamma), _p(beta), int(relu),
+         out.view(), _stream())
+    return out
+
+
+def bn_bwd(x: CL, dy: CL, relu_out: Optional[CL], mean, rstd, gamma, out: Optional[CL] = None):
+    if out is None:
+        out = x.new_like()
+    red = torch.zeros((2, x.c), dtype=torch.float32, device=x.device)
+    rv = _NULL_VIEW if relu_out is None else relu_out.view()
+    call("b200_bn_bwd_reduce", x.npos, x.c, x.view(), dy.view(), rv, _p(mean), _p(rstd), _p(red),
+         _stream())
+    call("b200_bn_bwd_apply", x.npos, x.c, x.view(), dy.view(), rv, _p(mean), _p(rstd), _p(gamma),
+         _p(red), out.view(), _stream())
+    # dbeta = sum dz, dgamma = sum dz * xhat
+    return out, red[1].clone(), red[0].clone()
+
+
+# ------------------------------------------------------------------------------------- head + losses
+def head_fwd(x: CL, w: torch.Tensor, b: Optional[torch.Tensor], is3d: bool) -> torch.Tensor:
+    c_out = w.shape[0]
+    shape = (x.n, c_out, x.d, x.h, x.w) if is3d else (x.n, c_out, x.h, x.w)
+    logits = torch.empty(shape, dtype=torch.float32, device=x.device)
+    w2 = w.detach().reshape(c_out, -1).contiguous().float()
+    call("b200_head_fwd", x.n, x.spatial, x.c, c_out, x.view(), _p(w2), _p(b), _p(logits), _stream())
+    return logits
+
+
+def head_bwd(x: CL, w: torch.Tensor, dlogits: torch.Tensor, need_dx: bool = True):
+    c_out = w.shape[0]
+    w2 = w.detach().reshape(c_out, -1).contiguous().float()
+    dlogits = dlogits.contiguous().float()
+    dx = x.new_like() if need_dx else None
+    dw = torch.zeros((c_out, x.c), dtype=torch.float32, device=x.device)
+    db = torch.zeros(c_out, dtype=torch.float32, device=x.device)
+    call("b200_head_bwd", x.n, x.spatial, x.c, c_out, x.view(), _p(w2), _p(dlogits),
+         _NULL_VIEW if dx is None else dx.view(), _p(dw), _p(db), _stream())
+    return dx, dw.reshape(w.shape), db
+
+
+def seg_sums(logits: torch.Tensor, target: torch.Tensor, normalization: int = 0) -> torch.Tensor:
+    """(C, 6) fp64: sum p*t, p*p, t*t, p, t, bce over batch and space, per channel."""
+    require_cuda(logits)
+    n, c = logits.shape[0], logits.shape[1]
+    spatial = logits[0, 0].numel()
+    logits = logits.contiguous().float()
+    target = target.contiguous().float()
+    sums = torch.zeros((c, 6), dtype=torch.float64, device=logits.device)
+    call("b200_seg_sums", n, c, spatial, _p(logits), _p(target), normalization, _p(sums), _stream())
+    return sums
+
+
+def seg_loss_bwd(logits: torch.Tensor, target: torch.Tensor, coef: torch.Tensor) -> torch.Tensor:
+    n, c = logits.shape[0], logits.shape[1]
+    spatial = logits[0, 0].numel()
+    logits = logits.contiguous().float()
+    target = target.contiguous().float()
+    coef = coef.contiguous().float()
+    out = torch.empty_like(logits)
+    call("b200_seg_loss_bwd", n, c, spatial, _p(logits), _p(target), _p(coef), _p(out), _stream())
+    return out
+
+
+def ce_fwd(logits: torch.Tensor, labels: torch.Tensor) -> torch.Tensor:
+    require_cuda(logits)
+    n, c = logits.shape[0], logits.shape[1]
+    spatial = logits[0, 0].numel()
+    logits = logits.contiguous().float()
+    labels = labels.contiguous().long()
+    s = torch.zeros(1, dtype=torch.float64, device=logits.device)
+    call("b200_ce_fwd", n, c, spatial, _p(logits), _p(labels), _p(s), _stream())
+    return s
+
+
+def ce_bwd(logits: torch.Tensor, labels: torch.Tensor, scale: torch.Tensor) -> torch.Tensor:
+    n, c = logits.shape[0], logits.shape[1]
+    spatial = logits[0, 0].numel()
+    logits = logits.contiguous().float()
+    labels = labels.contiguous().long()
+    out = torch.empty_like(logits)
+    call("b200_ce_bwd", n, c, spatial, _p(logits), _p(labels), _p(scale.contiguous().float()),
+         _p(out), _stream())
+    return out
+
+
+# ------------------------------------------------------------------------------------- metrics
+def metric_prob_sum(logits: torch.Tensor) -> torch.Tensor:
+    require_cuda(logits)
+    logits = logits.contiguous().float()
+    s = torch.zeros(1, dtype=torch.float64, device=logits.device)
+    call("b200_metric_prob_sum", logits.numel(), _p(logits), _p(s), _stream())
+    return s
+
+
+def metric_counts(logits: torch.Tensor, labels: torch.Tensor, thr: torch.Tensor, mode: int):
+    """(N, 3) fp64 per-sample {|P&L|, |P|, |L|}."""
+    require_cuda(logits)
+    n = logits.shape[0]
+    logits = logits.contiguous().float()
+    labels = labels.contiguous().float()
+    per = logits[0].numel()
+    counts = torch.zeros((n, 3), dtype=torch.float64, device=logits.device)
+    call("b200_metric_counts", n, per, _p(logits), _p(labels), _p(thr.contiguous().float()), mode,
+         _p(counts), _stream())
+    return counts
+
+
+def metric_argmax_counts(x: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
+    require_cuda(x)
+    n, c = x.shape[0], x.shape[1]
+    spatial = x[0, 0].numel()
+    x = x.contiguous().float()
+    target = target.contiguous().float()
+    counts = torch.zeros((n, c, 2), dtype=torch.float64, device=x.device)
+    call("b200_metric_argmax_counts", n, c, spatial, _p(x), _p(target), _p(counts), _stream())
+    return counts
