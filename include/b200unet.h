@@ -82,10 +82,10 @@ int b200_convt2x2_bwd_data(const b200_convt_desc* desc, const void* dy, const vo
 int b200_convt2x2_bwd_weight(const b200_convt_desc* desc, const void* x, const void* dy, float* dw,
                              b200_stream_t stream);
 
-/* ---- ConvTranspose(kernel 3, stride 2, padding 1, no bias) + nearest resize to 2x ----------------
- * replaces TransposeConvUpsampling.Upsample.forward  model/unet3d/buildingblocks.py:699-703
- * (conv_transposed then F.interpolate(size=2*in)). x: (n,d,h,w,c_in) -> y: (n,od,oh,ow,c_out)
- * where each o* is the skip's size (2*in here); d = od = 1 for the 2D variant. */
+/* ---- ConvTranspose(kernel 3, stride 2, padding 1, no bias) -------------------------------------
+ * replaces the conv_transposed of TransposeConvUpsampling  model/unet3d/buildingblocks.py:699-717;
+ * the F.interpolate(size=skip) that follows it (:703) is b200_upsample_nearest_*.
+ * x: (n,d,h,w,c_in) -> y: (n,od,oh,ow,c_out) with o* = 2*in - 1; d = od = 1 for the 2D variant. */
 typedef struct b200_deconv_desc {
   int32_t n, d, h, w;
   int32_t od, oh, ow;
@@ -115,9 +115,10 @@ typedef struct b200_view {
  * buildingblocks.py:409-413. pool_d = 1 keeps D (2D pooling). */
 int b200_maxpool2_fwd(int32_t n, int32_t d, int32_t h, int32_t w, int32_t c, int32_t pool_d,
                       b200_view x, b200_view y, b200_stream_t stream);
-/* dx fully written; ties go to the first maximum in (d,h,w) scan order, as ATen does */
+/* dx fully written; ties go to the first maximum in (d,h,w) scan order, as ATen does.
+ * add (ptr may be NULL): a second gradient of x's shape summed in (the skip branch of the U). */
 int b200_maxpool2_bwd(int32_t n, int32_t d, int32_t h, int32_t w, int32_t c, int32_t pool_d,
-                      b200_view x, b200_view dy, b200_view dx, b200_stream_t stream);
+                      b200_view x, b200_view dy, b200_view add, b200_view dx, b200_stream_t stream);
 /* F.interpolate(mode='nearest') buildingblocks.py:671-673: src = floor(dst * in / out) */
 int b200_upsample_nearest_fwd(int32_t n, int32_t id, int32_t ih, int32_t iw, int32_t od,
                               int32_t oh, int32_t ow, int32_t c, b200_view x, b200_view y,
@@ -186,10 +187,12 @@ int b200_head_bwd(int32_t n, int64_t spatial, int32_t c_in, int32_t c_out, b200_
  * normalization: 0 = sigmoid, 1 = none (input already a probability; bce column is then 0). */
 int b200_seg_sums(int32_t n, int32_t c, int64_t spatial, const float* logits, const float* target,
                   int32_t normalization, double* sums, b200_stream_t stream);
-/* dlogits = ka*(p - t) + p*(1-p) * (k1[c]*t + k2[c]*p + k3[c]);  coef fp32 [c][4] = (ka,k1,k2,k3),
- * all read from device memory so no host sync is needed. */
+/* normalization 0: dlogits = ka*(p - t) + p*(1-p) * (k1[c]*t + k2[c]*p + k3[c]);
+ * normalization 1: dlogits = k1[c]*t + k2[c]*x + k3[c].  coef fp32 [c][4] = (ka,k1,k2,k3) are
+ * d(loss)/d(sums) read from device memory, so no host sync is needed. */
 int b200_seg_loss_bwd(int32_t n, int32_t c, int64_t spatial, const float* logits,
-                      const float* target, const float* coef, float* dlogits, b200_stream_t stream);
+                      const float* target, const float* coef, int32_t normalization, float* dlogits,
+                      b200_stream_t stream);
 /* nn.CrossEntropyLoss() (unet.py:1185): nll_sum (fp64 [1]) += sum_pos -log softmax(x)[label] */
 int b200_ce_fwd(int32_t n, int32_t c, int64_t spatial, const float* logits, const int64_t* labels,
                 double* nll_sum, b200_stream_t stream);

@@ -1,0 +1,19 @@
+"""B200-native (sm_100a) implementation of the U-Net hot path of
+a-green-hand-jack/mdeical_image_segmentation: drop-in ``nn.Module`` classes, losses and metrics whose
+arithmetic runs in hand-written CUDA (tcgen05/TMEM/TMA implicit-GEMM convolutions + HBM-bound fused
+kernels) behind a C ABI (``include/b200unet.h``).  There is no CPU / PyTorch-eager fallback."""
+from . import _lib, metrics  # noqa: F401
+from .losses import (BCEDiceLoss, BCEWithLogitsLoss, CrossEntropyLoss, DiceLoss, F1Loss, IoULoss,
+                     compute_per_channel_dice, get_loss_criterion)
+from .unet2d import (CropAndConcat, DoubleConvolution, DownSample, UNet, UpSample, unetConv2)
+from .unet3d import (AbstractUNet, Decoder, DoubleConv, Encoder, SingleConv, UNet2D, UNet3D,
+                     create_conv, number_of_features_per_level)
+
+try:
+    from .unet2d import UNetConfig, UNetModel, UNetModelOutput
+    from .unet3d import (UNet3DForMedicalSegmentation, UNet3DForMedicalSegmentationConfig,
+                         UNet3DForMedicalSegmentationOutput)
+except ImportError:  # transformers missing
+    pass
+
+__version__ = "0.1.0"

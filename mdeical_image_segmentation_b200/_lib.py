@@ -56,7 +56,7 @@ SIGNATURES = {
     "b200_deconv3s2_bwd_data": [_PD, _P, _P, _P, _P],
     "b200_deconv3s2_bwd_weight": [_PD, _P, _P, _P, _P],
     "b200_maxpool2_fwd": [_I, _I, _I, _I, _I, _I, View, View, _P],
-    "b200_maxpool2_bwd": [_I, _I, _I, _I, _I, _I, View, View, View, _P],
+    "b200_maxpool2_bwd": [_I, _I, _I, _I, _I, _I, View, View, View, View, _P],
     "b200_upsample_nearest_fwd": [_I, _I, _I, _I, _I, _I, _I, _I, View, View, _P],
     "b200_upsample_nearest_bwd": [_I, _I, _I, _I, _I, _I, _I, _I, View, View, _P],
     "b200_copy_channels": [_L, _I, View, View, _P],
@@ -74,7 +74,7 @@ SIGNATURES = {
     "b200_head_fwd": [_I, _L, _I, _I, View, _P, _P, _P, _P],
     "b200_head_bwd": [_I, _L, _I, _I, View, _P, _P, View, _P, _P, _P],
     "b200_seg_sums": [_I, _I, _L, _P, _P, _I, _P, _P],
-    "b200_seg_loss_bwd": [_I, _I, _L, _P, _P, _P, _P, _P],
+    "b200_seg_loss_bwd": [_I, _I, _L, _P, _P, _P, _I, _P, _P],
     "b200_ce_fwd": [_I, _I, _L, _P, _P, _P, _P],
     "b200_ce_bwd": [_I, _I, _L, _P, _P, _P, _P, _P],
     "b200_metric_prob_sum": [_L, _P, _P, _P],

@@ -157,13 +157,18 @@ __global__ void __launch_bounds__(256)
   }
 }
 __global__ void seg_loss_bwd_kernel(int c, long spatial, long total, const float* logits,
-                                    const float* target, const float* coef, float* dlogits) {
+                                    const float* target, const float* coef, int normalization,
+                                    float* dlogits) {
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
     const int ch = (int)((i / spatial) % c);
     const float x = logits[i], t = target[i];
-    const float p = 1.f / (1.f + expf(-x));
     const float* k = coef + ch * 4;
-    dlogits[i] = k[0] * (p - t) + p * (1.f - p) * (k[1] * t + k[2] * p + k[3]);
+    if (normalization == 0) {
+      const float p = 1.f / (1.f + expf(-x));
+      dlogits[i] = k[0] * (p - t) + p * (1.f - p) * (k[1] * t + k[2] * p + k[3]);
+    } else {
+      dlogits[i] = k[1] * t + k[2] * x + k[3];
+    }
   }
 }
 
@@ -346,10 +351,11 @@ int b200_seg_sums(int32_t n, int32_t c, int64_t spatial, const float* logits, co
   return B200_OK;
 }
 int b200_seg_loss_bwd(int32_t n, int32_t c, int64_t spatial, const float* logits,
-                      const float* target, const float* coef, float* dlogits, b200_stream_t stream) {
+                      const float* target, const float* coef, int32_t normalization, float* dlogits,
+                      b200_stream_t stream) {
   const long total = (long)n * c * spatial;
   if (total <= 0) return B200_OK;
-  seg_loss_bwd_kernel<<<grid1d(total), 256, 0, (cudaStream_t)stream>>>(c, (long)spatial, total, logits, target, coef, dlogits);
+  seg_loss_bwd_kernel<<<grid1d(total), 256, 0, (cudaStream_t)stream>>>(c, (long)spatial, total, logits, target, coef, normalization, dlogits);
   B200_LAUNCH_CHECK();
   return B200_OK;
 }

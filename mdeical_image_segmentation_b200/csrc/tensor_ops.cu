@@ -74,7 +74,7 @@ __global__ void maxpool_fwd_kernel(int n, int d, int h, int w, int c, int pd, Vi
 
 // one thread per INPUT position: recompute the window arg-max (first maximum in d,h,w scan order)
 template <int V>
-__global__ void maxpool_bwd_kernel(int n, int d, int h, int w, int c, int pd, View x, View dy, View dx) {
+__global__ void maxpool_bwd_kernel(int n, int d, int h, int w, int c, int pd, View x, View dy, View add, View dx) {
   const int od = d / pd, oh = h / 2, ow = w / 2, cv = c / V;
   const long total = (long)n * d * h * w * cv;
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
@@ -88,6 +88,7 @@ __global__ void maxpool_bwd_kernel(int n, int d, int h, int w, int c, int pd, Vi
     float out[V];
 #pragma unroll
     for (int j = 0; j < V; ++j) out[j] = 0.f;
+    if (add.p) Vec<V>::load(add.at(ipos, ch), out);
     const int pw_ = xw >> 1, ph_ = xh >> 1, pdd = xd / pd;
     if (pw_ < ow && ph_ < oh && pdd < od) {
       const int self = ((xd - pdd * pd) * 2 + (xh & 1)) * 2 + (xw & 1);
@@ -108,7 +109,7 @@ __global__ void maxpool_bwd_kernel(int n, int d, int h, int w, int c, int pd, Vi
       const long opos = (((long)b * od + pdd) * oh + ph_) * ow + pw_;
       Vec<V>::load(dy.at(opos, ch), g_);
 #pragma unroll
-      for (int j = 0; j < V; ++j) out[j] = (arg[j] == self) ? g_[j] : 0.f;
+      for (int j = 0; j < V; ++j) out[j] += (arg[j] == self) ? g_[j] : 0.f;
     }
     Vec<V>::store(dx.at(ipos, ch), out);
   }
@@ -521,13 +522,13 @@ int b200_maxpool2_fwd(int32_t n, int32_t d, int32_t h, int32_t w, int32_t c, int
   return B200_OK;
 }
 int b200_maxpool2_bwd(int32_t n, int32_t d, int32_t h, int32_t w, int32_t c, int32_t pool_d,
-                      b200_view x, b200_view dy, b200_view dx, b200_stream_t stream) {
+                      b200_view x, b200_view dy, b200_view add, b200_view dx, b200_stream_t stream) {
   if (pool_d != 1 && pool_d != 2) return B200_ERR_BAD_ARG;
   const long total = (long)n * d * h * w * c;
   if (total <= 0) return B200_OK;
-  const bool v = vec8(c, x) && vec8(c, dy) && vec8(c, dx);
+  const bool v = vec8(c, x) && vec8(c, dy) && vec8(c, dx) && (!add.ptr || vec8(c, add));
   DISPATCH_V(v, maxpool_bwd_kernel, GRID1D(total / (v ? 8 : 1)), n, d, h, w, c, pool_d, mk(x), mk(dy),
-             mk(dx));
+             mk(add), mk(dx));
   return B200_OK;
 }
 int b200_upsample_nearest_fwd(int32_t n, int32_t id, int32_t ih, int32_t iw, int32_t od, int32_t oh,

@@ -1,0 +1,431 @@
+"""Whole-network forward / backward executors for the 2D and 3D U-Nets.
+
+The reference runs one stock ``nn.Module`` per op and lets autograd record ~100 nodes
+(model/unet2d/unet.py:95-128, model/unet3d/model.py:125-151).  Here the module tree is only the
+parameter container: each network is ONE ``torch.autograd.Function`` whose forward walks the tree,
+launches the sm_100a kernels on channels-last bf16 buffers and keeps an explicit tape, and whose
+backward replays the tape in reverse.  That gives the executor what autograd cannot express:
+
+* skip-concat fusion — encoder outputs and up-sampled tensors are written by their producers
+  directly into the two channel halves of one pre-allocated concat buffer (no ``torch.cat`` pass);
+  in backward the skip half of the concat gradient is summed into the max-pool backward;
+* conv epilogues carry bias + ReLU; norm kernels carry the ReLU that follows them;
+* gradients of the fp32 master parameters come back in the reference's own layouts.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Tuple
+
+import torch
+from torch import nn
+
+from . import ops
+from .ops import CL
+
+Grads = Dict[nn.Parameter, torch.Tensor]
+IMPL = 0  # B200_IMPL_AUTO; tests flip it to cross-check the tcgen05 and direct kernels
+
+
+def _acc(grads: Grads, p: Optional[nn.Parameter], g: torch.Tensor) -> None:
+    if p is None or not p.requires_grad:
+        return
+    g = g.reshape(p.shape)
+    grads[p] = g if p not in grads else grads[p] + g
+
+
+# ===================================================================================== SingleConv
+SUPPORTED_LETTERS = set("cgbr")
+
+
+class LayerSpec:
+    """One conv layer in the reference's ``layer_order`` mini-language (buildingblocks.py:14-113):
+    ``conv`` plus optional ``groupnorm`` / ``batchnorm`` modules, applied in ``order``."""
+
+    def __init__(self, order: str, conv: nn.Module, groupnorm: Optional[nn.GroupNorm] = None,
+                 batchnorm: Optional[nn.Module] = None):
+        bad = set(order) - SUPPORTED_LETTERS
+        if bad:
+            raise NotImplementedError(
+                f"layer_order letters {sorted(bad)} (LeakyReLU/ELU/dropout) are outside the B200 hot path")
+        self.order, self.conv, self.groupnorm, self.batchnorm = order, conv, groupnorm, batchnorm
+
+
+def _bn_moments(bn: nn.Module, x: CL, training: bool):
+    """mean / rstd for BatchNorm; in training also updates the running statistics the way
+    nn.BatchNorm does (momentum 0.1, unbiased running variance)."""
+    if training or bn.running_mean is None:
+        sums = ops.bn_stats(x)
+        m = float(x.npos)
+        mean = sums[0] / m
+        var = (sums[1] / m - mean * mean).clamp_(min=0.0)
+        if training and bn.running_mean is not None:
+            with torch.no_grad():
+                mom = bn.momentum if bn.momentum is not None else 0.1
+                unbiased = var * (m / max(m - 1.0, 1.0))
+                bn.running_mean.mul_(1 - mom).add_(mean.to(bn.running_mean.dtype), alpha=mom)
+                bn.running_var.mul_(1 - mom).add_(unbiased.to(bn.running_var.dtype), alpha=mom)
+                bn.num_batches_tracked += 1
+        rstd = torch.rsqrt(var + bn.eps)
+        return mean.float().contiguous(), rstd.float().contiguous()
+    mean = bn.running_mean.float().contiguous()
+    rstd = torch.rsqrt(bn.running_var.float() + bn.eps).contiguous()
+    return mean, rstd
+
+
+def single_conv_fwd(x: CL, spec: LayerSpec, training: bool, tape: Optional[list],
+                    out: Optional[CL] = None) -> CL:
+    """Runs one layer; ``out`` (optional) is the destination slice of its final result."""
+    letters = spec.order
+    cur = x
+    i = 0
+    while i < len(letters):
+        ch = letters[i]
+        fuse_relu = ch in "cgb" and i + 1 < len(letters) and letters[i + 1] == "r"
+        nxt = i + (2 if fuse_relu else 1)
+        dst = out if nxt >= len(letters) else None
+        if ch == "c":
+            conv = spec.conv
+            wp_fwd, wp_bwd, k = ops.conv_repack_weight(conv.weight, need_bwd=tape is not None)
+            bias = None if conv.bias is None else conv.bias.detach().float().contiguous()
+            y = ops.conv_fwd(cur, wp_fwd, k, bias, fuse_relu, out=dst, impl=IMPL)
+            if tape is not None:
+                tape.append(("conv", cur, conv, wp_bwd, k, y if fuse_relu else None))
+            cur = y
+        elif ch == "g":
+            gn = spec.groupnorm
+            stats = ops.gn_stats(cur, gn.num_groups, gn.eps)
+            gamma = gn.weight.detach().float().contiguous()
+            beta = gn.bias.detach().float().contiguous()
+            y = ops.gn_apply(cur, gn.num_groups, stats, gamma, beta, fuse_relu, out=dst)
+            if tape is not None:
+                tape.append(("gn", cur, gn, stats, gamma, y if fuse_relu else None))
+            cur = y
+        elif ch == "b":
+            bn = spec.batchnorm
+            mean, rstd = _bn_moments(bn, cur, training)
+            gamma = bn.weight.detach().float().contiguous()
+            beta = bn.bias.detach().float().contiguous()
+            y = ops.bn_apply(cur, mean, rstd, gamma, beta, fuse_relu, out=dst)
+            if tape is not None:
+                tape.append(("bn", cur, bn, mean, rstd, gamma, y if fuse_relu else None, training))
+            cur = y
+        elif ch == "r":  # a ReLU that could not be fused into its producer (first letter never is)
+            raise NotImplementedError(f"unfusable ReLU position in layer_order {letters!r}")
+        i = nxt
+    if out is not None and cur is not out:
+        ops.copy_channels(cur, out)
+        cur = out
+    return cur
+
+
+def single_conv_bwd(dy: CL, recs: list, grads: Grads, need_dx: bool = True) -> Optional[CL]:
+    """Backward of one layer: consumes the layer's tape records (in reverse); dy may be clobbered."""
+    for idx in range(len(recs) - 1, -1, -1):
+        rec = recs[idx]
+        kind = rec[0]
+        last = idx == 0
+        if kind == "conv":
+            _, x_in, conv, wp_bwd, k, y_relu = rec
+            has_bias = conv.bias is not None and conv.bias.requires_grad
+            if y_relu is not None:
+                dy, db = ops.relu_bwd(dy, y_relu, has_bias, out=dy)
+            else:
+                db = ops.bias_grad(dy) if has_bias else None
+            if has_bias:
+                _acc(grads, conv.bias, db)
+            if conv.weight.requires_grad:
+                _acc(grads, conv.weight, ops.conv_bwd_weight(x_in, dy, k, tuple(conv.weight.shape),
+                                                            impl=IMPL))
+            if last and not need_dx:
+                return None
+            dy = ops.conv_bwd_data(dy, wp_bwd, k, impl=IMPL)
+        elif kind == "gn":
+            _, x_in, gn, stats, gamma, y_relu = rec
+            if y_relu is not None:
+                dy, _ = ops.relu_bwd(dy, y_relu, False, out=dy)
+            dx, dgamma, dbeta = ops.gn_bwd(x_in, gn.num_groups, stats, gamma, dy)
+            _acc(grads, gn.weight, dgamma)
+            _acc(grads, gn.bias, dbeta)
+            dy = dx
+        elif kind == "bn":
+            _, x_in, bn, mean, rstd, gamma, y_relu, was_training = rec
+            # eval-mode BN (frozen statistics) is a per-channel affine map: no mean/variance terms
+            dx, dgamma, dbeta = ops.bn_bwd(x_in, dy, y_relu, mean, rstd, gamma, frozen=not was_training)
+            _acc(grads, bn.weight, dgamma)
+            _acc(grads, bn.bias, dbeta)
+            dy = dx
+    return dy
+
+
+def block_fwd(x: CL, specs: List[LayerSpec], training: bool, tape: Optional[list],
+              out: Optional[CL] = None) -> CL:
+    """A DoubleConv / DoubleConvolution / unetConv2: consecutive layers, last one writes ``out``."""
+    for j, spec in enumerate(specs):
+        sub = [] if tape is not None else None
+        x = single_conv_fwd(x, spec, training, sub, out=out if j == len(specs) - 1 else None)
+        if tape is not None:
+            tape.append(sub)
+    return x
+
+
+def block_bwd(dy: CL, tape: list, nlayers: int, grads: Grads, need_dx: bool = True) -> Optional[CL]:
+    for j in range(nlayers):
+        recs = tape.pop()
+        dy = single_conv_bwd(dy, recs, grads, need_dx=need_dx or j < nlayers - 1)
+    return dy
+
+
+# ===================================================================================== 2D U-Net
+def unet2d_specs(block) -> List[LayerSpec]:
+    """DoubleConvolution (model/unet2d/layers.py:103-133): conv+ReLU twice, bias, no norm."""
+    return [LayerSpec("cr", block.first), LayerSpec("cr", block.second)]
+
+
+def _crop_offsets(sh: int, sw: int, h: int, w: int) -> Tuple[int, int]:
+    return int(round((sh - h) / 2.0)), int(round((sw - w) / 2.0))
+
+
+def unet2d_forward(net, images: torch.Tensor, training: bool, tape: Optional[list]) -> CL:
+    """model/unet2d/unet.py:95-128 up to (excluding) the 1x1 head; returns the 64-channel feature map.
+
+    Concat order is [up-sampled, skip] (layers.py:188): the ConvTranspose epilogue scatters into
+    channels [0, C) and the encoder's second conv writes channels [C, 2C) of the same buffer."""
+    x = ops.from_nchw(images)
+    n_lvl = len(net.down_conv)
+    skips: List[CL] = []
+    for i in range(n_lvl):
+        c = net.down_conv[i].second.out_channels
+        if x.h % 2 == 0 and x.w % 2 == 0 and _fits_after(x.h, x.w, n_lvl - i):
+            cat = CL.empty(x.n, 1, x.h, x.w, 2 * c, x.device)
+            dst = cat.slice(c, c)
+        else:  # odd sizes need the centre crop of CropAndConcat: keep the skip in its own buffer
+            dst = None
+        x = block_fwd(x, unet2d_specs(net.down_conv[i]), training, tape, out=dst)
+        skips.append(x)
+        x = ops.maxpool_fwd(x, 1)
+    x = block_fwd(x, unet2d_specs(net.middle_conv), training, tape)
+    for i in range(n_lvl):
+        skip = skips[n_lvl - 1 - i]
+        up = net.up_sample[i].up
+        wp_fwd, wp_bwd = ops.convt_repack_weight(up.weight)
+        bias = None if up.bias is None else up.bias.detach().float().contiguous()
+        c = up.out_channels
+        if skip.ctot == 2 * c and skip.coff == c and (skip.h, skip.w) == (2 * x.h, 2 * x.w):
+            cat = CL(skip.buf)
+            crop = None
+        else:
+            cat = CL.empty(x.n, 1, 2 * x.h, 2 * x.w, c + skip.c, x.device)
+            top, left = _crop_offsets(skip.h, skip.w, 2 * x.h, 2 * x.w)
+            cropped = skip.dense()[:, :, top:top + 2 * x.h, left:left + 2 * x.w, :]
+            cat.buf[..., c:] = cropped
+            crop = (top, left)
+        ops.convt_fwd(x, wp_fwd, bias, out=cat.slice(0, c), impl=IMPL)
+        if tape is not None:
+            tape.append(("up", x, up, wp_bwd, c, crop, skip))
+        x = block_fwd(cat, unet2d_specs(net.up_conv[i]), training, tape)
+    if tape is not None:
+        tape.append(("skips", skips))
+    return x
+
+
+def _fits_after(h: int, w: int, levels_left: int) -> bool:
+    """True when every remaining pool halves exactly, so centre-crop is the identity."""
+    for _ in range(levels_left):
+        if h % 2 or w % 2:
+            return False
+        h //= 2
+        w //= 2
+    return True
+
+
+def unet2d_backward(net, tape: list, dfeat: CL, grads: Grads) -> None:
+    n_lvl = len(net.down_conv)
+    _, skips = tape.pop()
+    dskips: List[Optional[CL]] = [None] * n_lvl
+    d = dfeat
+    for i in range(n_lvl - 1, -1, -1):
+        dcat = block_bwd(d, tape, 2, grads)
+        _, x_in, up, wp_bwd, c, crop, skip = tape.pop()
+        d_up = dcat.slice(0, c)
+        if crop is None:
+            dskips[n_lvl - 1 - i] = dcat.slice(c, skip.c)
+        else:
+            full = torch.zeros_like(skip.dense(), memory_format=torch.contiguous_format)
+            top, left = crop
+            full[:, :, top:top + dcat.h, left:left + dcat.w, :] = dcat.dense()[..., c:]
+            dskips[n_lvl - 1 - i] = CL(full.contiguous())
+        if up.bias is not None:
+            _acc(grads, up.bias, ops.bias_grad(d_up))
+        _acc(grads, up.weight, ops.convt_bwd_weight(x_in, d_up, impl=IMPL))
+        d = ops.convt_bwd_data(d_up, wp_bwd, impl=IMPL)
+    d = block_bwd(d, tape, 2, grads)
+    for i in range(n_lvl - 1, -1, -1):
+        d = ops.maxpool_bwd(skips[i], d, 1, add=dskips[i])
+        d = block_bwd(d, tape, 2, grads, need_dx=i > 0)
+
+
+# ===================================================================================== 3D family
+def single_conv_spec(sc, order: str) -> LayerSpec:
+    """SingleConv (model/unet3d/buildingblocks.py:116-159): children 'conv', 'groupnorm', 'batchnorm'."""
+    return LayerSpec(order, sc.conv, getattr(sc, "groupnorm", None), getattr(sc, "batchnorm", None))
+
+
+def double_conv_specs(dc, order: str) -> List[LayerSpec]:
+    return [single_conv_spec(dc.SingleConv1, order), single_conv_spec(dc.SingleConv2, order)]
+
+
+def unet3d_forward(net, x_in: torch.Tensor, training: bool, tape: Optional[list]) -> CL:
+    """model/unet3d/model.py:125-143 up to the 1x1 head. Concat order is (skip, up-sampled)
+    (buildingblocks.py:547): skip channels [0, Cs), up-sampled [Cs, Cs + Cx)."""
+    is3d = net.is3d
+    order = net.layer_order
+    x = ops.from_nchw(x_in)
+    n_enc = len(net.encoders)
+    skips: List[CL] = []
+    for i, enc in enumerate(net.encoders):
+        if enc.pooling is not None:
+            pooled = ops.maxpool_fwd(x, 2 if is3d else 1)
+            if tape is not None:
+                tape.append(("pool", x))
+            x = pooled
+        cs = enc.basic_module.SingleConv2.conv.out_channels
+        dst = None
+        if i < n_enc - 1:
+            cx = _decoder_up_channels(net, n_enc - 2 - i)
+            cat = CL.empty(x.n, x.d, x.h, x.w, cs + cx, x.device)
+            dst = cat.slice(0, cs)
+        x = block_fwd(x, double_conv_specs(enc.basic_module, order), training, tape, out=dst)
+        skips.append(x)
+    for j, dec in enumerate(net.decoders):
+        skip = skips[n_enc - 2 - j]
+        cat = CL(skip.buf)
+        cx = cat.ctot - skip.c
+        size = (skip.d, skip.h, skip.w)
+        up_dst = cat.slice(skip.c, cx)
+        ct = getattr(getattr(dec.upsampling, "upsample", None), "conv_transposed", None)
+        if ct is not None:
+            wp = ops.deconv_repack_weight(ct.weight)
+            y = ops.deconv_fwd(x, wp, is3d)
+            ops.upsample_nearest_fwd(y, size, out=up_dst)
+            if tape is not None:
+                tape.append(("deconv", x, ct, wp, (y.d, y.h, y.w), skip.c, cx))
+        else:
+            ops.upsample_nearest_fwd(x, size, out=up_dst)
+            if tape is not None:
+                tape.append(("nearest", (x.d, x.h, x.w), skip.c, cx))
+        x = block_fwd(cat, double_conv_specs(dec.basic_module, order), training, tape)
+    if tape is not None:
+        tape.append(("skips", skips))
+    return x
+
+
+def _decoder_up_channels(net, j: int) -> int:
+    """Channels of the up-sampled tensor entering decoder j's concat."""
+    dec = net.decoders[j]
+    ct = getattr(getattr(dec.upsampling, "upsample", None), "conv_transposed", None)
+    if ct is not None:
+        return ct.out_channels
+    c_in = dec.basic_module.SingleConv1.conv.in_channels
+    skip_c = net.encoders[len(net.encoders) - 2 - j].basic_module.SingleConv2.conv.out_channels
+    return c_in - skip_c
+
+
+def unet3d_backward(net, tape: list, dfeat: CL, grads: Grads) -> None:
+    is3d = net.is3d
+    n_enc = len(net.encoders)
+    _, skips = tape.pop()
+    dskips: List[Optional[CL]] = [None] * n_enc
+    d = dfeat
+    for j in range(len(net.decoders) - 1, -1, -1):
+        dcat = block_bwd(d, tape, 2, grads)
+        rec = tape.pop()
+        if rec[0] == "deconv":
+            _, x_in, ct, wp, ct_size, cs, cx = rec
+            d_ct = ops.upsample_nearest_bwd(dcat.slice(cs, cx), ct_size)
+            _acc(grads, ct.weight, ops.deconv_bwd_weight(x_in, d_ct, tuple(ct.weight.shape)))
+            d = ops.deconv_bwd_data(d_ct, wp, x_in.dims, is3d)
+        else:
+            _, in_size, cs, cx = rec
+            d = ops.upsample_nearest_bwd(dcat.slice(cs, cx), in_size)
+        dskips[n_enc - 2 - j] = dcat.slice(0, cs)
+    for i in range(n_enc - 1, -1, -1):
+        d = block_bwd(d, tape, 2, grads, need_dx=i > 0)
+        if i > 0:
+            _, pre = tape.pop()
+            # the skip half of the concat gradient joins the gradient routed back through the pool
+            d = ops.maxpool_bwd(pre, d, 2 if is3d else 1, add=dskips[i - 1])
+
+
+# ===================================================================================== autograd glue
+class _NetFunction(torch.autograd.Function):
+    """One autograd node for a whole encoder-decoder + 1x1 head; returns fp32 logits (N, C, ...)."""
+
+    @staticmethod
+    def forward(ctx, net, kind: str, images: torch.Tensor, *params):
+        ops.require_cuda(images)
+        training = net.training
+        need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in params)
+        tape: Optional[list] = [] if need_grad else None
+        with torch.no_grad():
+            if kind == "unet2d":
+                feat = unet2d_forward(net, images, training, tape)
+            else:
+                feat = unet3d_forward(net, images, training, tape)
+            head = net.final_conv
+            bias = None if head.bias is None else head.bias.detach().float().contiguous()
+            logits = ops.head_fwd(feat, head.weight, bias, images.dim() == 5)
+        ctx.net, ctx.kind, ctx.tape, ctx.feat = net, kind, tape, feat if need_grad else None
+        ctx.params = params
+        return logits
+
+    @staticmethod
+    def backward(ctx, dlogits):
+        net, tape = ctx.net, ctx.tape
+        if tape is None:
+            raise RuntimeError("backward through a forward that ran without grad")
+        grads: Grads = {}
+        head = net.final_conv
+        dfeat, dw, db = ops.head_bwd(ctx.feat, head.weight, dlogits)
+        _acc(grads, head.weight, dw)
+        if head.bias is not None:
+            _acc(grads, head.bias, db)
+        if ctx.kind == "unet2d":
+            unet2d_backward(net, tape, dfeat, grads)
+        else:
+            unet3d_backward(net, tape, dfeat, grads)
+        ctx.tape = ctx.feat = None
+        out = tuple(grads.get(p) if p.requires_grad else None for p in ctx.params)
+        return (None, None, None) + out
+
+
+def run_network(net, kind: str, images: torch.Tensor) -> torch.Tensor:
+    params = tuple(net.parameters())
+    return _NetFunction.apply(net, kind, images, *params)
+
+
+class _BlockFunction(torch.autograd.Function):
+    """Stand-alone use of a block module (DoubleConvolution, DoubleConv, unetConv2, SingleConv) on an
+    fp32 NCHW tensor: same kernels, with the layout conversion at both ends."""
+
+    @staticmethod
+    def forward(ctx, mod, specs, x: torch.Tensor, *params):
+        ops.require_cuda(x)
+        need_grad = torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in params))
+        tape = [] if need_grad else None
+        with torch.no_grad():
+            y = block_fwd(ops.from_nchw(x), specs, mod.training, tape)
+            out = ops.to_nchw(y, x.dim() == 5)
+        ctx.tape, ctx.n, ctx.params, ctx.x_grad = tape, len(specs), params, x.requires_grad
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        grads: Grads = {}
+        dy = ops.from_nchw(dout)
+        dx = block_bwd(dy, ctx.tape, ctx.n, grads, need_dx=ctx.x_grad)
+        gx = ops.to_nchw(dx, dout.dim() == 5) if ctx.x_grad else None
+        return (None, None, gx) + tuple(grads.get(p) if p.requires_grad else None for p in ctx.params)
+
+
+def run_block(mod, specs: List[LayerSpec], x: torch.Tensor) -> torch.Tensor:
+    return _BlockFunction.apply(mod, specs, x, *tuple(mod.parameters()))

@@ -87,7 +87,6 @@ class CL:
         return CL.empty(self.n, self.d, self.h, self.w, self.c if c is None else c, self.device)
 
 
-_NULL_VIEW = View(0, 0, 0)
 
 
 # ------------------------------------------------------------------------------------- convolution
@@ -235,6 +234,9 @@ def deconv_bwd_weight(x: CL, dy: CL, w_shape) -> torch.Tensor:
     return dw
 
 
+_NULL_VIEW = View(0, 0, 0)
+
+
 # ------------------------------------------------------------------------------------- memory-bound ops
 def maxpool_fwd(x: CL, pool_d: int, out: Optional[CL] = None) -> CL:
     if out is None:
@@ -243,11 +245,12 @@ def maxpool_fwd(x: CL, pool_d: int, out: Optional[CL] = None) -> CL:
     return out
 
 
-def maxpool_bwd(x: CL, dy: CL, pool_d: int, out: Optional[CL] = None) -> CL:
+def maxpool_bwd(x: CL, dy: CL, pool_d: int, add: Optional[CL] = None,
+                out: Optional[CL] = None) -> CL:
     if out is None:
         out = x.new_like()
-    call("b200_maxpool2_bwd", x.n, x.d, x.h, x.w, x.c, pool_d, x.view(), dy.view(), out.view(),
-         _stream())
+    call("b200_maxpool2_bwd", x.n, x.d, x.h, x.w, x.c, pool_d, x.view(), dy.view(),
+         _NULL_VIEW if add is None else add.view(), out.view(), _stream())
     return out
 
 
@@ -350,15 +353,18 @@ def bn_apply(x: CL, mean, rstd, gamma, beta, relu: bool, out: Optional[CL] = Non
     return out
 
 
-def bn_bwd(x: CL, dy: CL, relu_out: Optional[CL], mean, rstd, gamma, out: Optional[CL] = None):
+def bn_bwd(x: CL, dy: CL, relu_out: Optional[CL], mean, rstd, gamma, out: Optional[CL] = None,
+           frozen: bool = False):
     if out is None:
         out = x.new_like()
     red = torch.zeros((2, x.c), dtype=torch.float32, device=x.device)
     rv = _NULL_VIEW if relu_out is None else relu_out.view()
     call("b200_bn_bwd_reduce", x.npos, x.c, x.view(), dy.view(), rv, _p(mean), _p(rstd), _p(red),
          _stream())
+    # frozen statistics (eval-mode BN): the batch-mean / batch-variance terms vanish
+    red_apply = torch.zeros_like(red) if frozen else red
     call("b200_bn_bwd_apply", x.npos, x.c, x.view(), dy.view(), rv, _p(mean), _p(rstd), _p(gamma),
-         _p(red), out.view(), _stream())
+         _p(red_apply), out.view(), _stream())
     # dbeta = sum dz, dgamma = sum dz * xhat
     return out, red[1].clone(), red[0].clone()
 
@@ -397,14 +403,16 @@ def seg_sums(logits: torch.Tensor, target: torch.Tensor, normalization: int = 0)
     return sums
 
 
-def seg_loss_bwd(logits: torch.Tensor, target: torch.Tensor, coef: torch.Tensor) -> torch.Tensor:
+def seg_loss_bwd(logits: torch.Tensor, target: torch.Tensor, coef: torch.Tensor,
+                 normalization: int = 0) -> torch.Tensor:
     n, c = logits.shape[0], logits.shape[1]
     spatial = logits[0, 0].numel()
     logits = logits.contiguous().float()
     target = target.contiguous().float()
     coef = coef.contiguous().float()
     out = torch.empty_like(logits)
-    call("b200_seg_loss_bwd", n, c, spatial, _p(logits), _p(target), _p(coef), _p(out), _stream())
+    call("b200_seg_loss_bwd", n, c, spatial, _p(logits), _p(target), _p(coef), normalization,
+         _p(out), _stream())
     return out
 
 

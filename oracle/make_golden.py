@@ -1,0 +1,220 @@
+"""Generates tests/golden/*.npz by running the UNMODIFIED reference (imported from /root/reference via
+oracle/ref_loader.py) on seeded inputs.  Run inside the build container:
+
+    python -m oracle.make_golden
+
+The fixtures pin the oracle (tests/test_oracle_golden.py); they are small on purpose: the full-width
+2D ``UNet`` (31 M parameters) is stored as its init seed, not its weights — the reference, the oracle
+and the product modules all create their ``nn.Conv2d`` children in the same order, so
+``torch.manual_seed(seed)`` reproduces the same ``state_dict`` (checked here).
+TEST INFRASTRUCTURE (see oracle/__init__).
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE))
+from oracle import ref_loader  # noqa: E402
+
+OUT = os.path.join(os.path.dirname(HERE), "tests", "golden")
+
+
+def _np(t):
+    return t.detach().cpu().numpy()
+
+
+def blob_target(shape, seed, q=0.7):
+    """Coherent binary blobs: box-blurred noise thresholded at its q-quantile."""
+    g = torch.Generator().manual_seed(seed)
+    noise = torch.randn(shape, generator=g)
+    nd = len(shape) - 2
+    pool = torch.nn.functional.avg_pool3d if nd == 3 else torch.nn.functional.avg_pool2d
+    blur = pool(noise, 5, stride=1, padding=2)
+    thr = torch.quantile(blur.flatten(), q)
+    return (blur > thr).float()
+
+
+def gen_unet2d(ns):
+    for name, cin, cout in (("unet2d_1_1", 1, 1), ("unet2d_3_4", 3, 4)):
+        torch.manual_seed(0)
+        net = ns.U2.UNet(cin, cout)
+        g = torch.Generator().manual_seed(1234)
+        x = torch.randn((2, cin, 32, 32), generator=g)
+        if cout == 1:
+            y = (torch.rand((2, 1, 32, 32), generator=g) > 0.7).float()
+            crit = torch.nn.BCEWithLogitsLoss()
+        else:
+            y = torch.randint(0, cout, (2, 32, 32), generator=g)
+            crit = torch.nn.CrossEntropyLoss()
+        logits = net(x)
+        loss = crit(logits, y)
+        loss.backward()
+        grads = {k: p.grad for k, p in net.named_parameters()}
+        keep = ["final_conv.weight", "final_conv.bias", "down_conv.0.first.weight",
+                "down_conv.0.first.bias", "up_sample.3.up.bias", "up_sample.0.up.bias"]
+        out = dict(seed=0, x=_np(x), y=_np(y), logits=_np(logits), loss=_np(loss),
+                   grad_names=np.array(sorted(grads)),
+                   grad_l2=np.array([grads[k].norm().item() for k in sorted(grads)]),
+                   grad_sum=np.array([grads[k].double().sum().item() for k in sorted(grads)]))
+        for k in keep:
+            out["grad__" + k] = _np(grads[k])
+        np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
+        print(name, "loss", loss.item())
+
+
+def gen_unet3d(ns):
+    cfgs = [
+        ("unet3d_gcr_nearest", dict(layer_order="gcr", upsample="default"), True),
+        ("unet3d_cbr_deconv", dict(layer_order="cbr", upsample="deconv"), True),
+        ("unet3d_cr_nearest", dict(layer_order="cr", upsample="default"), True),
+        ("unet2d3_gcr_nearest", dict(layer_order="gcr", upsample="default"), False),
+        ("unet2d3_cbr_deconv", dict(layer_order="cbr", upsample="deconv"), False),
+    ]
+    for name, kw, is3d in cfgs:
+        torch.manual_seed(0)
+        cls = ns.M3.UNet3D if is3d else ns.M3.UNet2D
+        cin, cout = (2, 2)
+        net = cls(cin, cout, f_maps=[8, 16, 32], num_groups=4, **kw)
+        net.train()
+        shape = (2, cin, 16, 16, 16) if is3d else (2, cin, 32, 32)
+        g = torch.Generator().manual_seed(77)
+        x = torch.randn(shape, generator=g)
+        t = blob_target((2, cout) + shape[2:], 5)
+        sd0 = {k: v.clone() for k, v in net.state_dict().items()}
+        logits = net(x)
+        loss = ns.L3.BCEDiceLoss(1.0, 1.0)(logits, t)
+        loss.backward()
+        out = dict(x=_np(x), t=_np(t), logits=_np(logits), loss=_np(loss), is3d=is3d,
+                   layer_order=kw["layer_order"], upsample=kw["upsample"])
+        for k, v in sd0.items():
+            out["sd__" + k] = _np(v)
+        for k, p in net.named_parameters():
+            out["grad__" + k] = _np(p.grad)
+        for k, v in net.state_dict().items():
+            if "running_" in k:
+                out["after__" + k] = _np(v)
+        net.eval()
+        with torch.no_grad():
+            out["logits_eval"] = _np(net(x))
+        np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
+        print(name, "loss", loss.item())
+
+
+def gen_blocks(ns):
+    torch.manual_seed(3)
+    blk = ns.L2.unetConv2(3, 8, True)
+    blk.train()
+    g = torch.Generator().manual_seed(9)
+    x = torch.randn((2, 3, 16, 16), generator=g, requires_grad=True)
+    sd0 = {k: v.clone() for k, v in blk.state_dict().items()}
+    y = blk(x)
+    y.square().sum().backward()
+    out = dict(x=_np(x), y=_np(y), dx=_np(x.grad))
+    for k, v in sd0.items():
+        out["sd__" + k] = _np(v)
+    for k, p in blk.named_parameters():
+        out["grad__" + k] = _np(p.grad)
+    np.savez_compressed(os.path.join(OUT, "unetconv2_bn.npz"), **out)
+    print("unetconv2 ok")
+
+
+def gen_losses_metrics(ns):
+    g = torch.Generator().manual_seed(11)
+    out = {}
+    # 3D dice-family losses on (N, C, D, H, W)
+    x = torch.randn((2, 3, 6, 8, 10), generator=g, requires_grad=True)
+    t = (torch.rand((2, 3, 6, 8, 10), generator=g) > 0.6).float()
+    for nm, crit in (("dice_sigmoid", ns.L3.DiceLoss()),
+                     ("dice_softmax", ns.L3.DiceLoss(normalization="softmax")),
+                     ("dice_weighted", ns.L3.DiceLoss(weight=torch.tensor([0.2, 0.3, 0.5]))),
+                     ("bce_dice", ns.L3.BCEDiceLoss(1.0, 1.0)),
+                     ("bce_dice_a", ns.L3.BCEDiceLoss(0.3, 0.7))):
+        x.grad = None
+        l = crit(x, t)
+        l.backward()
+        out[nm + "_loss"] = _np(l)
+        out[nm + "_grad"] = _np(x.grad)
+    out["x3"], out["t3"] = _np(x), _np(t)
+    out["dice_zero_target_loss"] = _np(ns.L3.DiceLoss()(x.detach(), torch.zeros_like(t)))
+    out["per_channel_dice"] = _np(ns.L3.compute_per_channel_dice(torch.sigmoid(x.detach()), t))
+    # 2D losses
+    x2 = torch.randn((4, 1, 24, 24), generator=g, requires_grad=True)
+    t2 = (torch.rand((4, 1, 24, 24), generator=g) > 0.7).float()
+    for nm, crit in (("iou", ns.LOSS2.IoULoss()), ("f1", ns.LOSS2.F1Loss()),
+                     ("bce", torch.nn.BCEWithLogitsLoss())):
+        x2.grad = None
+        l = crit(x2, t2)
+        l.backward()
+        out[nm + "_loss"] = _np(l)
+        out[nm + "_grad"] = _np(x2.grad)
+    out["x2"], out["t2"] = _np(x2), _np(t2)
+    xc = torch.randn((2, 4, 12, 12), generator=g, requires_grad=True)
+    yc = torch.randint(0, 4, (2, 12, 12), generator=g)
+    l = torch.nn.CrossEntropyLoss()(xc, yc)
+    l.backward()
+    out["ce_x"], out["ce_y"], out["ce_loss"], out["ce_grad"] = _np(xc), _np(yc), _np(l), _np(xc.grad)
+    # trainer/metrcis.py
+    MX = ns.MX
+    MX.plot_first_element = lambda *a, **k: None        # the matplotlib side effect is not on the path
+    logits = _np(x2)
+    labels = _np(t2)
+    m = MX.compute_metrics((logits, labels)) if False else None
+    from types import SimpleNamespace
+    m = MX.compute_metrics(SimpleNamespace(predictions=logits, label_ids=labels))
+    out["cm_iou"], out["cm_dice"] = np.float64(m["iou"]), np.float64(m["dice"])
+    probs = 1 / (1 + np.exp(-logits[:, 0]))
+    out["ci_05"] = np.float64(MX.compute_iou(probs, labels[:, 0], 0.5))
+    out["cd_05"] = np.float64(MX.compute_dice(probs, labels[:, 0], 0.5))
+    out["ci_empty"] = np.float64(MX.compute_iou(np.zeros_like(probs), np.zeros_like(probs), 0.5))
+    out["cd_empty"] = np.float64(MX.compute_dice(np.zeros_like(probs), np.zeros_like(probs), 0.5))
+    iou, dice = MX.iou_score(x2.detach(), t2)
+    out["iou_score"], out["iou_score_dice"] = np.float64(iou), np.float64(dice)
+    out["dice_coef"] = np.float64(MX.dice_coef(x2.detach(), t2))
+    # model/unet3d/metrics.py
+    p5 = torch.softmax(x.detach(), dim=1)
+    oh = torch.nn.functional.one_hot(torch.randint(0, 3, (2, 6, 8, 10), generator=g), 3)
+    oh = oh.permute(0, 4, 1, 2, 3).float()
+    out["oh5"] = _np(oh)
+    out["miou_multi"] = _np(ns.MET3.MeanIoU()(p5, oh.clone()))
+    p1 = torch.sigmoid(x.detach()[:, :1])
+    out["miou_single"] = _np(ns.MET3.MeanIoU()(p1, t[:, :1].clone()))
+    out["dice_coeff"] = _np(ns.MET3.DiceCoefficient()(p5, oh))
+    np.savez_compressed(os.path.join(OUT, "losses_metrics.npz"), **out)
+    print("losses/metrics ok")
+
+
+def check_seed_init(ns):
+    """The 2D fixture stores a seed instead of 124 MB of weights: prove the three constructors agree."""
+    import mdeical_image_segmentation_b200 as B
+    torch.manual_seed(0)
+    a = ns.U2.UNet(3, 4).state_dict()
+    torch.manual_seed(0)
+    b = B.UNet(3, 4).state_dict()
+    assert list(a) == list(b)
+    assert all(torch.equal(a[k], b[k]) for k in a)
+    torch.manual_seed(0)
+    a = ns.M3.UNet3D(1, 1, f_maps=16, layer_order="cbr", upsample="deconv").state_dict()
+    torch.manual_seed(0)
+    b = B.UNet3D(1, 1, f_maps=16, layer_order="cbr", upsample="deconv").state_dict()
+    assert list(a) == list(b) and all(torch.equal(a[k], b[k]) for k in a)
+    print("seeded init identical: reference vs product modules")
+
+
+def main():
+    torch.set_num_threads(8)
+    os.makedirs(OUT, exist_ok=True)
+    ns = ref_loader.load()
+    check_seed_init(ns)
+    gen_unet2d(ns)
+    gen_unet3d(ns)
+    gen_blocks(ns)
+    gen_losses_metrics(ns)
+
+
+if __name__ == "__main__":
+    main()

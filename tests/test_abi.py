@@ -1,0 +1,70 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads without a GPU or libcuda, exports
+every symbol include/b200unet.h declares, and the ctypes binding covers exactly that set."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+from conftest import ROOT
+from mdeical_image_segmentation_b200 import _lib
+
+HEADER = os.path.join(ROOT, "include", "b200unet.h")
+
+
+def header_symbols():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(b200_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_builds_and_loads():
+    _lib.build()
+    lib = _lib.lib()
+    assert lib.b200_version() >= 100
+    assert b"unsupported" in lib.b200_strerror(-2)
+
+
+def test_every_declared_symbol_is_exported_and_bound():
+    syms = header_symbols()
+    assert len(syms) >= 40
+    raw = ctypes.CDLL(str(_lib.LIB_PATH))
+    for s in syms:
+        assert hasattr(raw, s), f"{s} declared in b200unet.h but not exported"
+    assert sorted(_lib.ALL_SYMBOLS) == syms, set(_lib.ALL_SYMBOLS) ^ set(syms)
+
+
+def test_bad_arguments_return_error_codes_not_exceptions():
+    lib = _lib.lib()
+    d = _lib.ConvDesc(1, 1, 4, 4, 8, 8, 5, 5, 5, 8, 0, 8, 0, 0, 0)   # 5x5x5 kernel: unsupported
+    assert lib.b200_conv_fwd(ctypes.byref(d), None, None, None, None, None) == -2
+    d = _lib.ConvDesc(0, 1, 4, 4, 8, 8, 3, 3, 3, 8, 0, 8, 0, 0, 0)   # empty batch: bad arg
+    assert lib.b200_conv_fwd(ctypes.byref(d), None, None, None, None, None) == -1
+    d = _lib.ConvDesc(1, 1, 4, 4, 8, 8, 1, 3, 3, 8, 4, 8, 0, 0, 0)   # slice overruns its buffer
+    assert lib.b200_conv_fwd(ctypes.byref(d), None, None, None, None, None) == -1
+
+
+def test_no_cpu_fallback():
+    import mdeical_image_segmentation_b200 as B
+    net = B.UNet(1, 1)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        net(torch.zeros(1, 1, 16, 16))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        B.DiceLoss()(torch.zeros(1, 1, 4, 4, 4), torch.zeros(1, 1, 4, 4, 4))
+
+
+def test_state_dict_layouts_are_the_reference_ones():
+    import mdeical_image_segmentation_b200 as B
+    from conftest import load_golden
+    fix = load_golden("unet3d_cbr_deconv")
+    want = sorted(k[4:] for k in fix if k.startswith("sd__"))
+    net = B.UNet3D(2, 2, f_maps=[8, 16, 32], num_groups=4, layer_order="cbr", upsample="deconv")
+    assert sorted(net.state_dict()) == want
+    fix = load_golden("unet3d_gcr_nearest")
+    want = sorted(k[4:] for k in fix if k.startswith("sd__"))
+    net = B.UNet3D(2, 2, f_maps=[8, 16, 32], num_groups=4)
+    assert sorted(net.state_dict()) == want
+    sd2 = B.UNetModel(B.UNetConfig(3, 4)).state_dict()
+    assert len(sd2) == 46 and "unet.up_sample.3.up.weight" in sd2 and "unet.final_conv.bias" in sd2
+    assert tuple(sd2["unet.up_sample.0.up.weight"].shape) == (1024, 512, 2, 2)

@@ -1,0 +1,354 @@
+"""GPU parity tests (run on the B200 box): the CUDA path, called through the C ABI, against the CPU
+oracle and the reference's golden vectors.
+
+Tolerances (BASELINE.json north_star): logits and gradients within 2e-2 relative (bf16 storage, fp32
+accumulate), masks agreeing on >= 99.9 % of voxels, Dice/IoU within 1e-3 — asserted on briefly
+trained weights with signal-bearing inputs, where an ideal bf16 pipeline can meet them;
+random-init fixtures are held to the looser bound stated at each assert.
+"""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import load_golden, rel_l2, sd_from
+from oracle import metrics as OM
+from oracle import unet as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def B():
+    import mdeical_image_segmentation_b200 as B
+    return B
+
+
+def _grads(net):
+    return {k: p.grad.detach().cpu() for k, p in net.named_parameters() if p.grad is not None}
+
+
+def _global_rel(ga, gb, keys):
+    a = torch.cat([ga[k].flatten().double() for k in keys])
+    b = torch.cat([gb[k].flatten().double() for k in keys])
+    return ((a - b).norm() / b.norm()).item()
+
+
+# ----------------------------------------------------------------------------------- golden: 2D
+@pytest.mark.parametrize("name,cin,cout", [("unet2d_1_1", 1, 1), ("unet2d_3_4", 3, 4)])
+def test_unet2d_vs_reference_golden(B, name, cin, cout):
+    fix = load_golden(name)
+    torch.manual_seed(int(fix["seed"]))
+    model = B.UNetModel(B.UNetConfig(cin, cout)).cuda()
+    # seeded init is consumed by UNet's convs first (same order as the reference)
+    x = torch.from_numpy(fix["x"]).cuda()
+    y = torch.from_numpy(fix["y"]).cuda()
+    out = model(images=x, labels=y)
+    # random init + noise input, fp32 reference: bf16 pipeline measured ~2e-3; bound 1e-2
+    assert rel_l2(out.logits.cpu(), fix["logits"]) < 1e-2
+    assert abs(out.loss.item() - float(fix["loss"])) < 1e-3
+    out.loss.backward()
+    g = {k[len("unet."):]: v for k, v in _grads(model).items()}
+    names = [str(s) for s in fix["grad_names"]]
+    l2 = np.array([g[k].norm().item() for k in names])
+    ref = fix["grad_l2"]
+    # per-tensor gradient norms: within 5 % or an absolute floor tied to the global norm
+    floor = 2e-3 * np.linalg.norm(ref)
+    assert np.all(np.abs(l2 - ref) < 0.05 * ref + floor), np.abs(l2 - ref) / (ref + floor)
+    for k, v in fix.items():
+        if k.startswith("grad__"):
+            assert rel_l2(g[k[6:]], v) < 5e-2, (k, rel_l2(g[k[6:]], v))
+
+
+# ----------------------------------------------------------------------------------- golden: 3D family
+@pytest.mark.parametrize("name", ["unet3d_gcr_nearest", "unet3d_cbr_deconv", "unet3d_cr_nearest",
+                                  "unet2d3_gcr_nearest", "unet2d3_cbr_deconv"])
+def test_unet3d_family_vs_reference_golden(B, name):
+    fix = load_golden(name)
+    is3d = bool(fix["is3d"])
+    cls = B.UNet3D if is3d else B.UNet2D
+    net = cls(2, 2, f_maps=[8, 16, 32], num_groups=4, layer_order=str(fix["layer_order"]),
+              upsample=str(fix["upsample"]))
+    net.load_state_dict(sd_from(fix), strict=True)
+    net = net.cuda().train()
+    x, t = torch.from_numpy(fix["x"]).cuda(), torch.from_numpy(fix["t"]).cuda()
+    logits = net(x)
+    # random init + noise: an ideal bf16 pipeline sits at 4-7e-2 here; bound 1e-1
+    assert rel_l2(logits.cpu(), fix["logits"]) < 1e-1
+    loss = B.BCEDiceLoss(1.0, 1.0)(logits, t)
+    assert abs(loss.item() - float(fix["loss"])) < 2e-2
+    loss.backward()
+    g = _grads(net)
+    ref = {k[6:]: torch.from_numpy(v) for k, v in fix.items() if k.startswith("grad__")}
+    assert set(g) == set(ref)
+    assert _global_rel(g, ref, sorted(ref)) < 0.35          # random-init gradients: 19-29 %
+    for k, v in fix.items():
+        if k.startswith("after__"):                          # BatchNorm running statistics
+            assert rel_l2(net.state_dict()[k[7:]].cpu(), v) < 2e-2, k
+    net.eval()
+    with torch.no_grad():
+        ev = net(x)
+    assert rel_l2(ev.cpu(), fix["logits_eval"]) < 1e-1
+
+
+def test_unetconv2_block_vs_reference_golden(B):
+    fix = load_golden("unetconv2_bn")
+    blk = B.unetConv2(3, 8, True)
+    blk.load_state_dict(sd_from(fix))
+    blk = blk.cuda().train()
+    x = torch.from_numpy(fix["x"]).cuda().requires_grad_(True)
+    y = blk(x)
+    assert rel_l2(y.cpu(), fix["y"]) < 1e-2
+    y.square().sum().backward()
+    assert rel_l2(x.grad.cpu(), fix["dx"]) < 3e-2
+    for k, v in fix.items():
+        if k.startswith("grad__"):
+            assert rel_l2(dict(blk.named_parameters())[k[6:]].grad.cpu(), v) < 3e-2, k
+
+
+# ----------------------------------------------------------------------------------- trained fixtures
+def _blob_task(shape, seed):
+    g = torch.Generator().manual_seed(seed)
+    noise = torch.randn(shape, generator=g)
+    pool = F.avg_pool3d if len(shape) == 5 else F.avg_pool2d
+    blur = pool(noise, 5, stride=1, padding=2)
+    mask = (blur > torch.quantile(blur.flatten(), 0.7)).float()
+    x = 0.5 * torch.randn(shape, generator=g) + mask
+    return x, mask
+
+
+def _train_oracle(sd, fwd, loss_fn, shape, steps, lr=1e-3):
+    params = [v for k, v in sd.items() if v.is_floating_point() and "running" not in k]
+    for p in params:
+        p.requires_grad_(True)
+    opt = torch.optim.Adam(params, lr=lr)
+    for s in range(steps):
+        x, m = _blob_task(shape, 100 + s)
+        opt.zero_grad()
+        loss_fn(fwd(sd, x), m).backward()
+        opt.step()
+    return sd
+
+
+@pytest.mark.parametrize("order,upsample", [("gcr", "default"), ("cbr", "deconv")])
+def test_unet3d_trained_parity(B, order, upsample):
+    torch.manual_seed(0)
+    torch.set_num_threads(max(1, min(8, torch.get_num_threads())))
+    net = B.UNet3D(1, 1, f_maps=[16, 32, 64], layer_order=order, upsample=upsample)
+    sd = {k: v.clone() for k, v in net.state_dict().items()}
+    kw = dict(num_levels=3, layer_order=order, num_groups=8, upsample=upsample, is3d=True)
+    shape = (2, 1, 32, 32, 32)
+    fwd = lambda s, x: O.unet3d_forward(s, x, training=True, **kw)  # noqa: E731
+    sd = _train_oracle(sd, fwd, O.bce_dice_loss, shape, steps=40)
+    x, m = _blob_task(shape, 999)
+    for v in sd.values():
+        if v.grad is not None:
+            v.grad = None
+    sd_eval = {k: v.detach().clone() for k, v in sd.items()}
+    ref_logits = fwd(sd, x)
+    ref_loss = O.bce_dice_loss(ref_logits, m)
+    ref_loss.backward()
+    ref_g = {k: v.grad for k, v in sd.items() if v.requires_grad and v.grad is not None}
+
+    net.load_state_dict(sd_eval)
+    net = net.cuda().train()
+    logits = net(x.cuda())
+    loss = B.BCEDiceLoss(1.0, 1.0)(logits, m.cuda())
+    loss.backward()
+    lg = logits.detach().cpu()
+    assert rel_l2(lg, ref_logits.detach()) < 2e-2
+    assert (lg - ref_logits.detach()).abs().max() / ref_logits.detach().abs().max() < 2e-2
+    agree = ((lg > 0) == (ref_logits.detach() > 0)).float().mean().item()
+    assert agree >= 0.999, agree
+    assert abs(loss.item() - ref_loss.item()) < 1e-3
+    # Dice / IoU metrics within 1e-3
+    d_ref = O.dice_coefficient(torch.sigmoid(ref_logits.detach()), m).item()
+    d_dev = B.metrics.DiceCoefficient()(torch.sigmoid(logits.detach()), m.cuda()).item()
+    assert abs(d_ref - d_dev) < 1e-3
+    i_ref = O.mean_iou(torch.sigmoid(ref_logits.detach()), m).item()
+    i_dev = B.metrics.MeanIoU()(torch.sigmoid(logits.detach()), m.cuda()).item()
+    assert abs(i_ref - i_dev) < 1e-3
+    g = _grads(net)
+    keys = sorted(ref_g)
+    # headline: concatenated parameter gradient within 2e-2 of the fp32 oracle
+    assert _global_rel(g, ref_g, keys) < 2e-2, _global_rel(g, ref_g, keys)
+    gnorm = torch.cat([ref_g[k].flatten() for k in keys]).norm().item()
+    for k in keys:  # per tensor: 1e-1 relative with an absolute floor tied to the global norm
+        err = (g[k] - ref_g[k]).norm().item()
+        assert err < 0.1 * ref_g[k].norm().item() + 5e-3 * gnorm, (k, err, ref_g[k].norm().item())
+
+
+def test_unet2d_trained_parity(B):
+    torch.manual_seed(0)
+    model = B.UNetModel(B.UNetConfig(1, 1))
+    sd = {k[len("unet."):]: v.clone() for k, v in model.state_dict().items()}
+    shape = (2, 1, 32, 32)
+    bce = lambda lo, m: F.binary_cross_entropy_with_logits(lo, m)  # noqa: E731
+    sd = _train_oracle(sd, O.unet2d_forward, bce, shape, steps=12, lr=2e-4)
+    x, m = _blob_task((2, 1, 64, 64), 999)
+    for v in sd.values():
+        v.grad = None
+    ref_logits = O.unet2d_forward(sd, x)
+    ref_loss = bce(ref_logits, m)
+    ref_loss.backward()
+    ref_g = {k: v.grad for k, v in sd.items()}
+    model.load_state_dict({"unet." + k: v.detach() for k, v in sd.items()})
+    model = model.cuda().train()
+    out = model(images=x.cuda(), labels=m.cuda())
+    out.loss.backward()
+    lg = out.logits.detach().cpu()
+    assert rel_l2(lg, ref_logits.detach()) < 2e-2
+    agree = ((lg > 0) == (ref_logits.detach() > 0)).float().mean().item()
+    assert agree >= 0.999, agree
+    assert abs(out.loss.item() - ref_loss.item()) < 1e-3
+    g = {k[len("unet."):]: v for k, v in _grads(model).items()}
+    assert _global_rel(g, ref_g, sorted(ref_g)) < 2e-2
+    # metrics through the reference-facing API (numpy in, floats out)
+    mm = B.metrics.compute_metrics((lg.numpy(), m.numpy()))
+    rr = OM.compute_metrics(ref_logits.detach().numpy(), m.numpy())
+    assert abs(mm["iou"] - rr["iou"]) < 1e-3 and abs(mm["dice"] - rr["dice"]) < 1e-3
+
+
+# ----------------------------------------------------------------------------------- losses / metrics
+def test_losses_vs_reference_golden(B):
+    f = load_golden("losses_metrics")
+    t = torch.from_numpy(f["t3"]).cuda()
+    cases = {
+        "dice_sigmoid": B.DiceLoss(),
+        "dice_softmax": B.DiceLoss(normalization="softmax"),
+        "dice_weighted": B.DiceLoss(weight=torch.tensor([0.2, 0.3, 0.5])).cuda(),
+        "bce_dice": B.BCEDiceLoss(1.0, 1.0),
+        "bce_dice_a": B.BCEDiceLoss(0.3, 0.7),
+    }
+    for nm, crit in cases.items():
+        x = torch.from_numpy(f["x3"]).cuda().requires_grad_(True)
+        l = crit(x, t)
+        l.backward()
+        assert abs(l.item() - float(f[nm + "_loss"])) < 1e-5, nm          # fp32 inputs: float round-off
+        assert rel_l2(x.grad.cpu(), f[nm + "_grad"]) < 1e-4, nm
+    x = torch.from_numpy(f["x3"]).cuda()
+    assert abs(B.DiceLoss()(x, torch.zeros_like(t)).item() - float(f["dice_zero_target_loss"])) < 1e-5
+    pcd = B.compute_per_channel_dice(torch.sigmoid(x), t).cpu().numpy()
+    np.testing.assert_allclose(pcd, f["per_channel_dice"], rtol=1e-5)
+    t2 = torch.from_numpy(f["t2"]).cuda()
+    for nm, crit in {"iou": B.IoULoss(), "f1": B.F1Loss(), "bce": B.BCEWithLogitsLoss()}.items():
+        x2 = torch.from_numpy(f["x2"]).cuda().requires_grad_(True)
+        l = crit(x2, t2)
+        l.backward()
+        assert abs(l.item() - float(f[nm + "_loss"])) < 1e-5, nm
+        assert rel_l2(x2.grad.cpu(), f[nm + "_grad"]) < 1e-4, nm
+    xc = torch.from_numpy(f["ce_x"]).cuda().requires_grad_(True)
+    l = B.CrossEntropyLoss()(xc, torch.from_numpy(f["ce_y"]).cuda())
+    l.backward()
+    assert abs(l.item() - float(f["ce_loss"])) < 1e-5
+    assert rel_l2(xc.grad.cpu(), f["ce_grad"]) < 1e-4
+
+
+def test_metrics_vs_reference_golden(B):
+    f = load_golden("losses_metrics")
+    M = B.metrics
+    logits, labels = f["x2"], f["t2"]
+    m = M.compute_metrics((logits, labels))
+    assert abs(m["iou"] - float(f["cm_iou"])) < 1e-6 and abs(m["dice"] - float(f["cm_dice"])) < 1e-6
+    probs = 1 / (1 + np.exp(-logits[:, 0]))
+    assert abs(M.compute_iou(probs, labels[:, 0]) - float(f["ci_05"])) < 1e-6
+    assert abs(M.compute_dice(probs, labels[:, 0]) - float(f["cd_05"])) < 1e-6
+    z = np.zeros_like(probs)
+    assert M.compute_iou(z, z) == 0.0 and abs(M.compute_dice(z, z) - 0.5) < 1e-6
+    iou, dice = M.iou_score(torch.from_numpy(logits), torch.from_numpy(labels))
+    assert abs(iou - float(f["iou_score"])) < 1e-6 and abs(dice - float(f["iou_score_dice"])) < 1e-6
+    assert abs(M.dice_coef(torch.from_numpy(logits), torch.from_numpy(labels)) - float(f["dice_coef"])) < 1e-5
+    x3, t3, oh = (torch.from_numpy(f[k]).cuda() for k in ("x3", "t3", "oh5"))
+    p5 = torch.softmax(x3, dim=1)
+    assert abs(M.MeanIoU()(p5, oh).item() - float(f["miou_multi"])) < 1e-6
+    assert abs(M.MeanIoU()(torch.sigmoid(x3[:, :1]), t3[:, :1]).item() - float(f["miou_single"])) < 1e-6
+    assert abs(M.DiceCoefficient()(p5, oh).item() - float(f["dice_coeff"])) < 1e-5
+
+
+# ----------------------------------------------------------------------------------- kernels, edge cases
+def test_tcgen05_and_direct_kernels_agree(B):
+    """Same GEMM problem through the tensor-core and the CUDA-core kernel: identical up to fp32
+    summation order (both round the result to bf16 once)."""
+    from mdeical_image_segmentation_b200 import ops
+    from mdeical_image_segmentation_b200.ops import CL
+    g = torch.Generator().manual_seed(0)
+    for (n, d, h, w, cin, cout) in [(1, 1, 19, 23, 64, 64), (1, 6, 9, 10, 32, 48), (2, 4, 4, 4, 128, 256)]:
+        x = CL(torch.randn((n, d, h, w, cin), generator=g).to(torch.bfloat16).cuda())
+        dy = CL(torch.randn((n, d, h, w, cout), generator=g).to(torch.bfloat16).cuda())
+        ks = (3, 3, 3) if d > 1 else (3, 3)
+        wt = (torch.randn((cout, cin) + ks, generator=g) / (cin * 9) ** 0.5).cuda()
+        fwd, bwd, k = ops.conv_repack_weight(wt)
+        y1 = ops.conv_fwd(x, fwd, k, None, True, impl=1).dense().float()
+        y2 = ops.conv_fwd(x, fwd, k, None, True, impl=2).dense().float()
+        assert rel_l2(y1.cpu(), y2.cpu()) < 3e-3
+        d1 = ops.conv_bwd_data(dy, bwd, k, impl=1).dense().float()
+        d2 = ops.conv_bwd_data(dy, bwd, k, impl=2).dense().float()
+        assert rel_l2(d1.cpu(), d2.cpu()) < 3e-3
+        w1 = ops.conv_bwd_weight(x, dy, k, wt.shape, impl=1)
+        w2 = ops.conv_bwd_weight(x, dy, k, wt.shape, impl=2)
+        assert rel_l2(w1.cpu(), w2.cpu()) < 1e-4
+
+
+def test_maxpool_tie_routing_and_odd_sizes(B):
+    """Post-ReLU all-zero windows: the gradient goes to the FIRST element in (d,h,w) order, as ATen."""
+    from mdeical_image_segmentation_b200 import ops
+    g = torch.Generator().manual_seed(3)
+    x = torch.relu(torch.randn((2, 8, 5, 7, 9), generator=g) - 0.8)     # many zero windows, odd dims
+    x = x.to(torch.bfloat16).float()
+    xr = x.clone().requires_grad_(True)
+    y = F.max_pool3d(xr, 2)
+    gy = torch.randn(y.shape, generator=g).to(torch.bfloat16).float()
+    y.backward(gy)
+    xc = ops.from_nchw(x.cuda())
+    yc = ops.maxpool_fwd(xc, 2)
+    assert torch.equal(ops.to_nchw(yc, True).cpu(), y.detach())
+    dx = ops.maxpool_bwd(xc, ops.from_nchw(gy.cuda()), 2)
+    assert torch.equal(ops.to_nchw(dx, True).cpu(), xr.grad)
+
+
+def test_nearest_resize_index_map(B):
+    """F7: ConvTranspose output 2n-1 resized to 2n reads ct[max(i-1, 0)]; plus exact 2x."""
+    from mdeical_image_segmentation_b200 import ops
+    for (isz, osz) in [((3, 5, 7), (4, 6, 8)), ((4, 4, 4), (8, 8, 8)), ((15, 15, 15), (16, 16, 16))]:
+        x = torch.arange(2 * 8 * isz[0] * isz[1] * isz[2], dtype=torch.float32).reshape((2, 8) + isz) % 251
+        ref = F.interpolate(x, size=osz)
+        out = ops.to_nchw(ops.upsample_nearest_fwd(ops.from_nchw(x.cuda()), osz), True).cpu()
+        assert torch.equal(out, ref)
+        xr = x.clone().requires_grad_(True)
+        gy = (torch.arange(ref.numel(), dtype=torch.float32).reshape(ref.shape) % 7) - 3
+        F.interpolate(xr, size=osz).backward(gy)
+        dx = ops.to_nchw(ops.upsample_nearest_bwd(ops.from_nchw(gy.cuda()), isz), True).cpu()
+        assert torch.equal(dx, xr.grad)
+
+
+def test_size_independent_properties_at_headline_size(B):
+    """Linearity of the conv kernels and loss identities at a BASELINE-scale layer (128^3, 64 ch)."""
+    from mdeical_image_segmentation_b200 import ops
+    from mdeical_image_segmentation_b200.ops import CL
+    torch.manual_seed(0)
+    x = CL((torch.randn((1, 64, 128, 128, 32), device="cuda") * 0.5).to(torch.bfloat16))
+    wt = torch.randn((32, 32, 3, 3, 3), device="cuda") * 0.03
+    fwd, bwd, k = ops.conv_repack_weight(wt)
+    y = ops.conv_fwd(x, fwd, k, None, False).dense().float()
+    x2 = CL((x.dense().float() * 2).to(torch.bfloat16).contiguous())
+    y2 = ops.conv_fwd(x2, fwd, k, None, False).dense().float()
+    assert rel_l2((y2 / 2).cpu(), y.cpu()) < 4e-3                       # conv(2x) = 2 conv(x)
+    # <conv(x), dy> == <x, dgrad(dy)> == <w, wgrad(x, dy)>  (adjoint identities)
+    dy = CL((torch.randn_like(y) * 0.1).to(torch.bfloat16))
+    dx = ops.conv_bwd_data(dy, bwd, k).dense().float()
+    dw = ops.conv_bwd_weight(x, dy, k, wt.shape)
+    lhs = (y.double() * dy.dense().double()).sum().item()
+    mid = (x.dense().double() * dx.double()).sum().item()
+    rhs = (wt.to(torch.bfloat16).double() * dw.double()).sum().item()
+    assert abs(lhs - mid) < 2e-2 * abs(lhs) and abs(lhs - rhs) < 2e-2 * abs(lhs), (lhs, mid, rhs)
+    m = (torch.rand((2, 1, 128, 128, 128), device="cuda") > 0.7).float()
+    big = torch.where(m > 0, 30.0, -30.0)
+    assert B.DiceLoss()(big, m).item() < 1e-5
+    assert abs(B.metrics.MeanIoU()(m.clone(), m.clone()).item() - 1.0) < 1e-6
+
+
+def test_empty_batch_is_a_noop(B):
+    from mdeical_image_segmentation_b200 import ops
+    x = ops.CL(torch.empty((0, 1, 8, 8, 16), dtype=torch.bfloat16, device="cuda"))
+    y = ops.maxpool_fwd(x, 1)
+    assert y.n == 0

@@ -1,0 +1,147 @@
+"""Pins the CPU oracle (oracle/) against the golden vectors produced by the reference itself
+(oracle/make_golden.py).  fp32 on both sides: agreement to float round-off."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden, rel_l2, sd_from
+from oracle import metrics as OM
+from oracle import unet as O
+
+TOL = 2e-5
+
+
+def _seeded_unet2d_sd(cin, cout, seed):
+    # the 2D fixture stores the init seed: rebuild the weights with the product module's constructor
+    # (parameter-creation order identical to the reference; checked by make_golden.check_seed_init)
+    from mdeical_image_segmentation_b200.unet2d import UNet
+    torch.manual_seed(seed)
+    return {k: v.clone().requires_grad_(v.is_floating_point()) for k, v in UNet(cin, cout).state_dict().items()}
+
+
+@pytest.mark.parametrize("name,cin,cout", [("unet2d_1_1", 1, 1), ("unet2d_3_4", 3, 4)])
+def test_unet2d_matches_reference(name, cin, cout):
+    fix = load_golden(name)
+    sd = _seeded_unet2d_sd(cin, cout, int(fix["seed"]))
+    x = torch.from_numpy(fix["x"])
+    y = torch.from_numpy(fix["y"])
+    logits = O.unet2d_forward(sd, x)
+    assert rel_l2(logits, fix["logits"]) < TOL
+    loss = O.unet_model_loss(logits, y, cout)
+    assert abs(loss.item() - float(fix["loss"])) < 1e-5
+    loss.backward()
+    names = [str(s) for s in fix["grad_names"]]
+    l2 = np.array([sd[k].grad.norm().item() for k in names])
+    np.testing.assert_allclose(l2, fix["grad_l2"], rtol=2e-3, atol=1e-7)
+    for k, v in fix.items():
+        if k.startswith("grad__"):
+            assert rel_l2(sd[k[6:]].grad, v) < 1e-3, k
+
+
+@pytest.mark.parametrize("name", ["unet3d_gcr_nearest", "unet3d_cbr_deconv", "unet3d_cr_nearest",
+                                  "unet2d3_gcr_nearest", "unet2d3_cbr_deconv"])
+def test_unet3d_family_matches_reference(name):
+    fix = load_golden(name)
+    sd = sd_from(fix)
+    for v in sd.values():
+        if v.is_floating_point() and v.dim() > 0:
+            v.requires_grad_(True)
+    # running stats / counters are buffers
+    for k in sd:
+        if "running_" in k or "num_batches" in k:
+            sd[k] = sd[k].detach()
+    kw = dict(num_levels=3, layer_order=str(fix["layer_order"]), num_groups=4,
+              upsample=str(fix["upsample"]), is3d=bool(fix["is3d"]))
+    x, t = torch.from_numpy(fix["x"]), torch.from_numpy(fix["t"])
+    logits = O.unet3d_forward(sd, x, training=True, **kw)
+    assert rel_l2(logits, fix["logits"]) < TOL
+    loss = O.bce_dice_loss(logits, t)
+    assert abs(loss.item() - float(fix["loss"])) < 1e-5
+    loss.backward()
+    for k, v in fix.items():
+        if k.startswith("grad__"):
+            g = sd[k[6:]].grad
+            err = (g - torch.from_numpy(v)).norm().item()
+            assert err < 1e-3 * (np.linalg.norm(v) + 1e-4), (k, err)
+        if k.startswith("after__"):
+            assert rel_l2(sd[k[7:]], v) < 1e-5, k
+    with torch.no_grad():
+        ev = O.unet3d_forward(sd, x, training=False, **kw)
+    assert rel_l2(ev, fix["logits_eval"]) < TOL
+
+
+def test_unetconv2_block():
+    fix = load_golden("unetconv2_bn")
+    sd = sd_from(fix)
+    x = torch.from_numpy(fix["x"]).requires_grad_(True)
+    for k, v in sd.items():
+        if v.is_floating_point() and "running" not in k:
+            v.requires_grad_(True)
+    y = O.unet_conv2(sd, "", x, n=2, training=True)
+    assert rel_l2(y, fix["y"]) < TOL
+    y.square().sum().backward()
+    assert rel_l2(x.grad, fix["dx"]) < 1e-4
+
+
+def test_losses():
+    f = load_golden("losses_metrics")
+    t = torch.from_numpy(f["t3"])
+    cases = {
+        "dice_sigmoid": lambda x: O.dice_loss(x, t),
+        "dice_softmax": lambda x: O.dice_loss(x, t, normalization="softmax"),
+        "dice_weighted": lambda x: O.dice_loss(x, t, weight=torch.tensor([0.2, 0.3, 0.5])),
+        "bce_dice": lambda x: O.bce_dice_loss(x, t),
+        "bce_dice_a": lambda x: O.bce_dice_loss(x, t, 0.3, 0.7),
+    }
+    for nm, fn in cases.items():
+        x = torch.from_numpy(f["x3"]).requires_grad_(True)
+        l = fn(x)
+        l.backward()
+        assert abs(l.item() - float(f[nm + "_loss"])) < 1e-6, nm
+        assert rel_l2(x.grad, f[nm + "_grad"]) < 1e-5, nm
+    x = torch.from_numpy(f["x3"])
+    assert abs(O.dice_loss(x, torch.zeros_like(t)).item() - float(f["dice_zero_target_loss"])) < 1e-6
+    np.testing.assert_allclose(O.per_channel_dice(torch.sigmoid(x), t).numpy(), f["per_channel_dice"], rtol=1e-6)
+    t2 = torch.from_numpy(f["t2"])
+    for nm, fn in {"iou": O.iou_loss, "f1": O.f1_loss,
+                   "bce": lambda a, b: O.unet_model_loss(a, b, 1)}.items():
+        x2 = torch.from_numpy(f["x2"]).requires_grad_(True)
+        l = fn(x2, t2)
+        l.backward()
+        assert abs(l.item() - float(f[nm + "_loss"])) < 1e-6, nm
+        assert rel_l2(x2.grad, f[nm + "_grad"]) < 1e-5, nm
+    xc = torch.from_numpy(f["ce_x"]).requires_grad_(True)
+    l = O.unet_model_loss(xc, torch.from_numpy(f["ce_y"]), 4)
+    l.backward()
+    assert abs(l.item() - float(f["ce_loss"])) < 1e-6
+    assert rel_l2(xc.grad, f["ce_grad"]) < 1e-5
+
+
+def test_metrics():
+    f = load_golden("losses_metrics")
+    logits, labels = f["x2"], f["t2"]
+    m = OM.compute_metrics(logits, labels)
+    assert abs(m["iou"] - float(f["cm_iou"])) < 1e-7 and abs(m["dice"] - float(f["cm_dice"])) < 1e-7
+    probs = 1 / (1 + np.exp(-logits[:, 0]))
+    assert abs(OM.compute_iou(probs, labels[:, 0]) - float(f["ci_05"])) < 1e-7
+    assert abs(OM.compute_dice(probs, labels[:, 0]) - float(f["cd_05"])) < 1e-7
+    z = np.zeros_like(probs)
+    assert OM.compute_iou(z, z) == float(f["ci_empty"]) == 0.0
+    assert abs(OM.compute_dice(z, z) - float(f["cd_empty"])) < 1e-9       # (0 + e) / (e + e) = 0.5
+    iou, dice = OM.iou_score(logits, labels)
+    assert abs(iou - float(f["iou_score"])) < 1e-9 and abs(dice - float(f["iou_score_dice"])) < 1e-9
+    assert abs(OM.dice_coef(logits, labels) - float(f["dice_coef"])) < 1e-6
+    x3, t3, oh = torch.from_numpy(f["x3"]), torch.from_numpy(f["t3"]), torch.from_numpy(f["oh5"])
+    p5 = torch.softmax(x3, dim=1)
+    assert abs(O.mean_iou(p5, oh).item() - float(f["miou_multi"])) < 1e-6
+    assert abs(O.mean_iou(torch.sigmoid(x3[:, :1]), t3[:, :1]).item() - float(f["miou_single"])) < 1e-6
+    assert abs(O.dice_coefficient(p5, oh).item() - float(f["dice_coeff"])) < 1e-6
+
+
+def test_analytic_known_answers():
+    m = torch.zeros(1, 1, 4, 4, 4)
+    m[0, 0, 1:3] = 1
+    big = torch.where(m > 0, torch.tensor(30.0), torch.tensor(-30.0))
+    assert O.dice_loss(big, m).item() < 1e-6                      # identical masks -> dice 1
+    assert abs(O.mean_iou(m.clone(), m.clone()).item() - 1.0) < 1e-7
+    assert abs(O.dice_loss(-big, m).item() - 1.0) < 1e-6          # disjoint masks -> dice 0
