@@ -1,0 +1,421 @@
+#!/usr/bin/env python
+"""Headline benchmark: U-Net training throughput on B200 (imgs/s for 2D, vols/s for 3D).
+
+    python bench.py --gpus N --steps K --warmup W [--workload cfg2|cfg3|cfg3p|cfg1] [--impl reference]
+
+A step = forward + loss + backward + optimizer step on one per-GPU batch of synthetic data (random-init
+weights of the named architecture).  One JSON line on rank 0 (see the keys at the bottom).  For N > 1
+the driver launches this file under torch.distributed.run; ranks shard by batch (weak scaling) and the
+gradient all-reduce overlaps backward (mdeical_image_segmentation_b200/parallel.py).
+
+`--impl reference` times the reference's CPU implementation of the same path: /root/reference is a
+pure-Python project that cannot travel to the GPU box, so the arm runs the oracle port (oracle/unet.py,
+a functional restatement pinned to the reference by tests/golden) on all host threads.
+"""
+from __future__ import annotations
+
+import argparse
+import contextlib
+import json
+import os
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+# conv + transposed-conv FLOPs per sample, train = 3 x fwd - fwd(first conv)  
+WORKLOADS = {
+    "cfg1": dict(kind="2d", cin=1, cout=1, size=(256, 256), batch=4, train_tf=0.2885, unit="imgs/s",
+                 desc="UNet(1,1) 256x256 binary seg, batch 4, BCE + IoU/Dice metrics"),
+    "cfg2": dict(kind="2d", cin=3, cout=4, size=(512, 512), batch=64, train_tf=1.1554, unit="imgs/s",
+                 desc="UNet(3,4) 512x512 4-class, batch 64 per GPU, CrossEntropy + AdamW"),
+    "cfg3": dict(kind="3d", cin=1, cout=1, size=(128, 128, 128), batch=2, train_tf=11.358, unit="vols/s",
+                 order="gcr", upsample="default",
+                 desc="UNet3D(1,1) gcr+nearest 128^3, batch 2 per GPU, BCEDice + Adam"),
+    "cfg3p": dict(kind="3d", cin=1, cout=1, size=(128, 128, 128), batch=2, train_tf=9.532, unit="vols/s",
+                  order="cbr", upsample="deconv",
+                  desc="UNet3D(1,1) cbr+deconv 128^3, batch 2 per GPU, BCEDice + Adam"),
+}
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return dict(hbm=p["hbm_gbs"], tf_burst=p["bf16_tflops"], tf_sustained=p["bf16_tflops_sustained"],
+                    source="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, source="fallback")
+
+
+# --------------------------------------------------------------------------------------- data
+def make_batch(w, batch, seed, device="cpu", pin=False):
+    g = torch.Generator().manual_seed(seed)
+    if w["kind"] == "2d":
+        x = torch.randn((batch, w["cin"]) + w["size"], generator=g)
+        if w["cout"] > 1:
+            y = torch.randint(0, w["cout"], (batch,) + w["size"], generator=g)
+        else:
+            y = (torch.rand((batch, 1) + w["size"], generator=g) > 0.7).float()
+    else:
+        x = torch.randn((batch, w["cin"]) + w["size"], generator=g)
+        y = (torch.rand((batch, w["cout"]) + w["size"], generator=g) > 0.7).float()
+    if pin:
+        x, y = x.pin_memory(), y.pin_memory()
+    return x.to(device), y.to(device)
+
+
+# --------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._t = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _run(self):
+        nv = self.nv
+        names = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40,
+                 "sw_thermal_slowdown": 0x20, "hw_power_brake": 0x80, "sync_boost": 0x10,
+                 "applications_clocks": 0x2}
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                for k, bit in names.items():
+                    if mask & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def __enter__(self):
+        if self.nv is not None:
+            self._t = threading.Thread(target=self._run, daemon=True)
+            self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        if self._t is not None:
+            self._t.join()
+
+    def summary(self):
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons)}
+
+
+# --------------------------------------------------------------------------------------- B200 arm
+def build_model(w, device):
+    import mdeical_image_segmentation_b200 as B
+    torch.manual_seed(0)
+    if w["kind"] == "2d":
+        model = B.UNetModel(B.UNetConfig(w["cin"], w["cout"])).to(device).train()
+        opt = torch.optim.AdamW(model.parameters(), lr=1e-4, weight_decay=1e-3, fused=True)
+
+        def step_fn(x, y):
+            return model(images=x, labels=y).loss
+    else:
+        net = B.UNet3D(w["cin"], w["cout"], layer_order=w["order"], upsample=w["upsample"]).to(device).train()
+        crit = B.BCEDiceLoss(1.0, 1.0)
+        model = net
+        opt = torch.optim.Adam(model.parameters(), lr=1e-4, fused=True)
+
+        def step_fn(x, y):
+            return crit(net(x), y)
+    return model, opt, step_fn
+
+
+def conv_flops(name, args):
+    """Algorithmic FLOPs of one C-ABI conv-family call, from its descriptor."""
+    d = args[0]._obj if hasattr(args[0], "_obj") else None
+    if d is None:
+        return 0.0
+    if name.startswith("b200_convt2x2"):
+        return 2.0 * d.n * d.h * d.w * d.c_in * d.c_out * 4
+    if name.startswith("b200_conv_"):
+        return 2.0 * d.n * d.d * d.h * d.w * d.c_in * d.c_out * d.kd * d.kh * d.kw
+    if name.startswith("b200_deconv3s2"):
+        return 2.0 * d.n * d.d * d.h * d.w * d.c_in * d.c_out * (27 if d.d > 1 else 9)
+    return 0.0
+
+
+class KernelProfiler:
+    """Per-call CUDA-event timing on the launching stream for one instrumented step."""
+
+    def __init__(self):
+        self.records = []
+
+    @contextlib.contextmanager
+    def hook(self, name, args):
+        from mdeical_image_segmentation_b200 import _lib
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        yield
+        e1.record()
+        impl = _lib.lib().b200_last_impl() if ("conv" in name and "repack" not in name) else 0
+        self.records.append((name, impl, conv_flops(name, args), e0, e1))
+
+    def summarize(self):
+        torch.cuda.synchronize()
+        fam = {}
+        for name, impl, fl, e0, e1 in self.records:
+            ms = e0.elapsed_time(e1)
+            if "repack" in name:
+                key = "repack"
+            elif name in ("b200_conv_fwd", "b200_conv_bwd_data", "b200_convt2x2_fwd", "b200_convt2x2_bwd_data"):
+                key = "tc_gemm_kernel" if impl == 1 else "direct_gemm_kernel"
+            elif name in ("b200_conv_bwd_weight", "b200_convt2x2_bwd_weight"):
+                key = "tc_wgrad_kernel" if impl == 1 else "direct_wgrad_kernel"
+            elif name.startswith("b200_deconv3s2"):
+                key = "deconv_direct"
+            else:
+                key = name.replace("b200_", "")
+            f = fam.setdefault(key, dict(ms=0.0, flops=0.0, launches=0))
+            f["ms"] += ms
+            f["flops"] += fl
+            f["launches"] += 1
+        return fam
+
+
+def run_b200(args, w):
+    import torch.distributed as dist
+    from mdeical_image_segmentation_b200 import _lib
+    from mdeical_image_segmentation_b200.parallel import DataParallelUNet
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    batch = args.batch or w["batch"]
+    model, opt, step_fn = build_model(w, device)
+    if world > 1:
+        DataParallelUNet(model)
+
+    x, y = make_batch(w, batch, 1234 + rank, device)
+
+    def one_step(xb, yb):
+        opt.zero_grad(set_to_none=True)
+        loss = step_fn(xb, yb)
+        loss.backward()
+        opt.step()
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing
+    for _ in range(args.warmup):
+        one_step(x, y)
+    barrier()
+    _lib.launch_count = 0
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clocks:
+        e0.record()
+        for _ in range(args.steps):
+            loss = one_step(x, y)
+        e1.record()
+        barrier()
+    launches = _lib.launch_count
+    ms = torch.tensor([e0.elapsed_time(e1)], device=device)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_step = ms.item() / args.steps
+    value = world * batch / (ms_step / 1e3)
+    final_loss = float(loss.item())
+
+    # ---- end to end: pinned host batch -> H2D every step (prefetched on a copy stream), loss -> host
+    e2e = None
+    if not args.no_e2e:
+        host = [make_batch(w, batch, 99 + rank + i, "cpu", pin=True) for i in range(2)]
+        copy_stream = torch.cuda.Stream(device=device)
+        h2d = sum(t.numel() * t.element_size() for t in host[0])
+
+        def fetch(i):
+            with torch.cuda.stream(copy_stream):
+                xb = host[i % 2][0].to(device, non_blocking=True)
+                yb = host[i % 2][1].to(device, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(copy_stream)
+            return xb, yb, ev
+
+        def e2e_loop(n):
+            nxt = fetch(0)
+            for i in range(n):
+                xb, yb, ev = nxt
+                torch.cuda.current_stream().wait_event(ev)
+                if i + 1 < n:
+                    nxt = fetch(i + 1)
+                l = one_step(xb, yb)
+                xb.record_stream(torch.cuda.current_stream())
+                yb.record_stream(torch.cuda.current_stream())
+                l.item()                                   # D2H read of the step's result
+
+        e2e_loop(max(1, min(args.warmup, 2)))
+        barrier()
+        t0 = time.perf_counter()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        e2e_loop(args.steps)
+        s1.record()
+        barrier()
+        wall_ms = (time.perf_counter() - t0) * 1e3
+        ems = torch.tensor([max(s0.elapsed_time(s1), wall_ms)], device=device)
+        if world > 1:
+            dist.all_reduce(ems, op=dist.ReduceOp.MAX)
+        e2e = {"value": world * batch / (ems.item() / args.steps / 1e3), "unit": w["unit"],
+               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4}
+
+    # ---- roofline: one instrumented step with per-call CUDA events on the launching stream
+    pk = peaks()
+    roofline, breakdown = None, None
+    if rank == 0:
+        prof = KernelProfiler()
+        _lib.profile_hook = prof.hook
+        one_step(x, y)
+        _lib.profile_hook = None
+        fam = prof.summarize()
+        total_ms = sum(f["ms"] for f in fam.values())
+        breakdown = {k: {"ms": round(f["ms"], 3), "share": round(f["ms"] / total_ms, 4),
+                         "launches": f["launches"],
+                         **({"tflops": round(f["flops"] / f["ms"] / 1e9, 1)} if f["flops"] else {})}
+                     for k, f in sorted(fam.items(), key=lambda kv: -kv[1]["ms"])}
+        top = max(fam.items(), key=lambda kv: kv[1]["ms"])
+        if top[1]["flops"] > 0:
+            ach = top[1]["flops"] / top[1]["ms"] / 1e9
+            roofline = {"kernel": top[0], "bound": "tensor", "achieved": round(ach, 1),
+                        "peak": pk["tf_sustained"], "unit": "TFLOP/s",
+                        "frac": round(ach / pk["tf_sustained"], 4), "traffic": None,
+                        "peak_source": pk["source"] + " (sustained cuBLAS bf16)",
+                        "avg_launch_ms": round(top[1]["ms"] / top[1]["launches"], 4)}
+        step_tf = w["train_tf"] * batch
+        breakdown["_step"] = {"algorithmic_tflop_per_step": round(step_tf, 2),
+                              "step_tflops": round(step_tf / (ms_step / 1e3), 1),
+                              "frac_of_sustained_peak": round(step_tf / (ms_step / 1e3) / pk["tf_sustained"], 4)}
+
+    # ---- reference CPU baseline (oracle port) on a bounded sample, rank 0 at N = 1 only
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu = run_cpu_sample(w, steps=1, warmup=0)
+
+    if rank == 0:
+        out = {
+            "metric": "train " + w["unit"], "value": round(value, 3), "unit": w["unit"], "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_step, 3),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+            "data": "synthetic",
+            "config": {"workload": f"{args.workload}: {w['desc']}", "per_gpu_batch": batch,
+                       "global_batch": batch * world, "parallelism": f"dp{world}",
+                       "l2": "per-step inputs + activations far exceed the 126 MB L2 (no flush needed)"},
+            "e2e": e2e, "gpu_launches": launches, "clocks": clocks.summary(),
+            "roofline": roofline, "cpu_baseline": cpu, "breakdown": breakdown,
+            "final_loss": final_loss,
+        }
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# --------------------------------------------------------------------------------------- CPU arm
+def run_cpu_sample(w, steps, warmup, batch=None):
+    """Reference path on host cores via the oracle port: fwd + loss + bwd + optimizer on a bounded
+    sample (2D: one 512^2 image per step; 3D: one 64^3 crop per step, throughput scaled by voxels)."""
+    from oracle import unet as O
+    import mdeical_image_segmentation_b200 as B
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    torch.manual_seed(0)
+    if w["kind"] == "2d":
+        b = batch or 1
+        sd = {k: v.clone().requires_grad_(True) for k, v in B.UNet(w["cin"], w["cout"]).state_dict().items()}
+        x, y = make_batch(w, b, 7)
+        fwd = lambda: O.unet_model_loss(O.unet2d_forward(sd, x), y, w["cout"])  # noqa: E731
+        scale, sample = 1.0, f"{b} image(s) of {w['size'][0]}x{w['size'][1]} per step"
+        opt = torch.optim.AdamW(sd.values(), lr=1e-4, weight_decay=1e-3)
+    else:
+        b = batch or 1
+        net = B.UNet3D(w["cin"], w["cout"], layer_order=w["order"], upsample=w["upsample"])
+        sd = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and "running" not in k else v.clone())
+              for k, v in net.state_dict().items()}
+        crop = dict(w, size=(64, 64, 64))
+        x, y = make_batch(crop, b, 7)
+        fwd = lambda: O.bce_dice_loss(O.unet3d_forward(sd, x, layer_order=w["order"], upsample=w["upsample"],  # noqa: E731
+                                                      training=True), y)
+        scale = 64.0 ** 3 / (w["size"][0] * w["size"][1] * w["size"][2])
+        sample = f"{b} crop(s) of 64^3 per step, scaled by voxel count to {w['size'][0]}^3 volumes"
+        opt = torch.optim.Adam([v for v in sd.values() if v.requires_grad], lr=1e-4)
+
+    def step():
+        opt.zero_grad()
+        l = fwd()
+        l.backward()
+        opt.step()
+
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = (time.perf_counter() - t0) / steps
+    return {"value": round(b * scale / dt, 5), "unit": w["unit"], "cores": cores, "kind": "port",
+            "sample": sample, "s_per_step": round(dt, 3)}
+
+
+def run_reference(args, w):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps = max(1, min(args.steps, 8))
+    cpu = run_cpu_sample(w, steps=steps, warmup=min(args.warmup, 1))
+    out = {"impl": "reference", "metric": "train " + w["unit"], "value": cpu["value"], "unit": w["unit"],
+           "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": steps, "warmup": min(args.warmup, 1),
+           "ms_per_step": cpu["s_per_step"] * 1e3, "higher_is_better": True, "scaling": "weak",
+           "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": {"workload": f"{args.workload}: {w['desc']}", "note": "CPU oracle port of the reference path"},
+           "cpu_baseline": cpu, "gpu_launches": 0,
+           "e2e": {"value": cpu["value"], "unit": w["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=0)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    w = WORKLOADS[args.workload]
+    if args.gpus > 1 and "WORLD_SIZE" not in os.environ and args.impl == "b200":
+        # convenience: re-launch under torch.distributed.run, one rank per GPU
+        os.execvp(sys.executable, [sys.executable, "-m", "torch.distributed.run", "--nnodes=1",
+                                   f"--nproc-per-node={args.gpus}", "--master-addr", "127.0.0.1",
+                                   "--master-port", "29531", os.path.abspath(__file__)] + sys.argv[1:])
+    if args.impl == "reference":
+        run_reference(args, w)
+    else:
+        run_b200(args, w)
+
+
+if __name__ == "__main__":
+    main()

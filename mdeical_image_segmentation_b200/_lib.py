@@ -131,5 +131,18 @@ def check(rc: int, what: str = "") -> None:
         raise RuntimeError(f"{what or 'b200 call'} failed ({rc}): {strerror(rc)}")
 
 
+# kernels launched per successful C-ABI call (for bench.py's `gpu_launches` accounting)
+LAUNCHES_PER_CALL = {"b200_gn_stats": 2, "b200_gn_bwd": 3, "b200_head_bwd": 2}
+launch_count = 0
+# optional profiler hook: fn(name, args) -> context manager, installed by bench.py for per-kernel timing
+profile_hook = None
+
+
 def call(name: str, *args) -> None:
-    check(getattr(lib(), name)(*args), name)
+    global launch_count
+    if profile_hook is not None:
+        with profile_hook(name, args):
+            check(getattr(lib(), name)(*args), name)
+    else:
+        check(getattr(lib(), name)(*args), name)
+    launch_count += LAUNCHES_PER_CALL.get(name, 1)

@@ -26,11 +26,18 @@ Grads = Dict[nn.Parameter, torch.Tensor]
 IMPL = 0  # B200_IMPL_AUTO; tests flip it to cross-check the tcgen05 and direct kernels
 
 
+_REDUCER = None  # parallel.GradReducer of the network whose backward is running (data parallel)
+
+
 def _acc(grads: Grads, p: Optional[nn.Parameter], g: torch.Tensor) -> None:
+    """Record the (final) gradient of a parameter; under data parallelism hand it to the bucketed
+    all-reduce immediately so the transfer overlaps the rest of the backward pass."""
     if p is None or not p.requires_grad:
         return
     g = g.reshape(p.shape)
-    grads[p] = g if p not in grads else grads[p] + g
+    if p in grads:
+        raise RuntimeError("a parameter received two gradients: weight sharing is not supported")
+    grads[p] = _REDUCER.on_grad(p, g) if _REDUCER is not None else g
 
 
 # ===================================================================================== SingleConv
@@ -364,7 +371,7 @@ class _NetFunction(torch.autograd.Function):
     def forward(ctx, net, kind: str, images: torch.Tensor, *params):
         ops.require_cuda(images)
         training = net.training
-        need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in params)
+        need_grad = any(ctx.needs_input_grad)
         tape: Optional[list] = [] if need_grad else None
         with torch.no_grad():
             if kind == "unet2d":
@@ -383,16 +390,23 @@ class _NetFunction(torch.autograd.Function):
         net, tape = ctx.net, ctx.tape
         if tape is None:
             raise RuntimeError("backward through a forward that ran without grad")
+        global _REDUCER
         grads: Grads = {}
         head = net.final_conv
-        dfeat, dw, db = ops.head_bwd(ctx.feat, head.weight, dlogits)
-        _acc(grads, head.weight, dw)
-        if head.bias is not None:
-            _acc(grads, head.bias, db)
-        if ctx.kind == "unet2d":
-            unet2d_backward(net, tape, dfeat, grads)
-        else:
-            unet3d_backward(net, tape, dfeat, grads)
+        _REDUCER = getattr(net, "_b200_reducer", None)
+        try:
+            dfeat, dw, db = ops.head_bwd(ctx.feat, head.weight, dlogits)
+            _acc(grads, head.weight, dw)
+            if head.bias is not None:
+                _acc(grads, head.bias, db)
+            if ctx.kind == "unet2d":
+                unet2d_backward(net, tape, dfeat, grads)
+            else:
+                unet3d_backward(net, tape, dfeat, grads)
+            if _REDUCER is not None:
+                _REDUCER.finish()
+        finally:
+            _REDUCER = None
         ctx.tape = ctx.feat = None
         out = tuple(grads.get(p) if p.requires_grad else None for p in ctx.params)
         return (None, None, None) + out
@@ -410,12 +424,12 @@ class _BlockFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, mod, specs, x: torch.Tensor, *params):
         ops.require_cuda(x)
-        need_grad = torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in params))
+        need_grad = any(ctx.needs_input_grad)
         tape = [] if need_grad else None
         with torch.no_grad():
             y = block_fwd(ops.from_nchw(x), specs, mod.training, tape)
             out = ops.to_nchw(y, x.dim() == 5)
-        ctx.tape, ctx.n, ctx.params, ctx.x_grad = tape, len(specs), params, x.requires_grad
+        ctx.tape, ctx.n, ctx.params, ctx.x_grad = tape, len(specs), params, ctx.needs_input_grad[2]
         return out
 
     @staticmethod
