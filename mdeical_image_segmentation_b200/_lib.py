@@ -132,7 +132,7 @@ def check(rc: int, what: str = "") -> None:
 
 
 # kernels launched per successful C-ABI call (for bench.py's `gpu_launches` accounting)
-LAUNCHES_PER_CALL = {"b200_gn_stats": 2, "b200_gn_bwd": 3, "b200_head_bwd": 2}
+LAUNCHES_PER_CALL = {"b200_gn_stats": 2, "b200_gn_bwd": 3}
 launch_count = 0
 # optional profiler hook: fn(name, args) -> context manager, installed by bench.py for per-kernel timing
 profile_hook = None

@@ -28,7 +28,14 @@ __device__ __forceinline__ double block_sum_d(double v, double* sh) {
 }
 
 // ------------------------------------------------------------------------------------ head
+// 8 threads per position, each owning 8 consecutive input channels (one 16-byte load); a warp
+// therefore streams 512 contiguous bytes of x per pass.  c_in is processed in passes of 64.
 #define HEAD_MAX_CO 8
+__device__ __forceinline__ void ld8(const bf16* p, float* f) {
+  const uint4 u = *reinterpret_cast<const uint4*>(p);
+  const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+  f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
+}
 __global__ void __launch_bounds__(256)
     head_fwd_kernel(int n, long spatial, int c_in, int c_out, View x, const float* w, const float* b,
                     float* logits) {
@@ -37,90 +44,114 @@ __global__ void __launch_bounds__(256)
   for (int i = threadIdx.x; i < c_out; i += blockDim.x) sw[c_out * c_in + i] = b ? b[i] : 0.f;
   __syncthreads();
   const long total = (long)n * spatial;
-  for (long pos = (long)blockIdx.x * blockDim.x + threadIdx.x; pos < total; pos += (long)gridDim.x * blockDim.x) {
-    const long bi = pos / spatial, s = pos % spatial;
-    for (int co0 = 0; co0 < c_out; co0 += HEAD_MAX_CO) {
-      float acc[HEAD_MAX_CO];
+  const int oct = threadIdx.x & 7;
+  // warp-uniform trip count (4 positions per warp per pass) so the full-mask shuffles are safe
+  const int sub = (threadIdx.x & 31) >> 3;
+  for (long p0 = (((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 4; p0 < total;
+       p0 += (((long)gridDim.x * blockDim.x) >> 5) * 4) {
+    const long pos = p0 + sub;
+    const bool valid = pos < total;
+    float acc[HEAD_MAX_CO];
 #pragma unroll
-      for (int j = 0; j < HEAD_MAX_CO; ++j) acc[j] = (co0 + j < c_out) ? sw[c_out * c_in + co0 + j] : 0.f;
-      const bf16* xr = x.at(pos, 0);
-      for (int ci = 0; ci < c_in; ++ci) {
-        const float xv = __bfloat162float(xr[ci]);
+    for (int j = 0; j < HEAD_MAX_CO; ++j) acc[j] = 0.f;
+    for (int c0 = oct * 8; valid && c0 < c_in; c0 += 64) {
+      float f[8];
+      ld8(x.at(pos, c0), f);
 #pragma unroll
-        for (int j = 0; j < HEAD_MAX_CO; ++j)
-          if (co0 + j < c_out) acc[j] = fmaf(xv, sw[(co0 + j) * c_in + ci], acc[j]);
-      }
+      for (int j = 0; j < HEAD_MAX_CO; ++j) {
+        if (j < c_out) {
+          const float* wr = sw + j * c_in + c0;
 #pragma unroll
-      for (int j = 0; j < HEAD_MAX_CO; ++j)
-        if (co0 + j < c_out) logits[(bi * c_out + co0 + j) * spatial + s] = acc[j];
-    }
-  }
-}
-// dx[pos][ci] = sum_co dlogits[n][co][pos] * w[co][ci]
-__global__ void __launch_bounds__(256)
-    head_bwd_data_kernel(int n, long spatial, int c_in, int c_out, const float* w,
-                         const float* dlogits, View dx) {
-  extern __shared__ float sw[];
-  for (int i = threadIdx.x; i < c_out * c_in; i += blockDim.x) sw[i] = w[i];
-  __syncthreads();
-  const int cv = (c_in + 7) / 8;
-  const long total = (long)n * spatial * cv;
-  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
-    const long pos = i / cv;
-    const int ci0 = (int)(i % cv) * 8;
-    const long bi = pos / spatial, s = pos % spatial;
-    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    for (int co = 0; co < c_out; ++co) {
-      const float g = dlogits[(bi * c_out + co) * spatial + s];
-#pragma unroll
-      for (int j = 0; j < 8; ++j)
-        if (ci0 + j < c_in) acc[j] = fmaf(g, sw[co * c_in + ci0 + j], acc[j]);
-    }
-#pragma unroll
-    for (int j = 0; j < 8; ++j)
-      if (ci0 + j < c_in) *dx.at(pos, ci0 + j) = __float2bfloat16(acc[j]);
-  }
-}
-// dw[co][ci] += sum_pos dlogits[co][pos] * x[pos][ci];  db[co] += sum_pos dlogits[co][pos]
-// block: 256 threads = c_in lanes x rows; each thread keeps c_out accumulators (c_out <= 8 per pass)
-__global__ void __launch_bounds__(256)
-    head_bwd_weight_kernel(int n, long spatial, int c_in, int c_out, long chunk, View x,
-                           const float* dlogits, float* dw, float* db) {
-  __shared__ float sred[256];
-  const int lanes = c_in < 256 ? c_in : 256;
-  const int rows = 256 / lanes;
-  const int ci = threadIdx.x % lanes, row = threadIdx.x / lanes;
-  const long total = (long)n * spatial;
-  const long pbeg = (long)blockIdx.x * chunk;
-  const long pend = pbeg + chunk < total ? pbeg + chunk : total;
-  for (int cib = 0; cib < c_in; cib += lanes) {
-    const int c = cib + ci;
-    for (int co = 0; co < c_out; ++co) {
-      float acc = 0.f, accb = 0.f;
-      if (row < rows && c < c_in) {
-        for (long pos = pbeg + row; pos < pend; pos += rows) {
-          const long bi = pos / spatial, s = pos % spatial;
-          const float g = dlogits[(bi * c_out + co) * spatial + s];
-          acc = fmaf(g, __bfloat162float(*x.at(pos, c)), acc);
-          accb += g;
+          for (int k = 0; k < 8; ++k) acc[j] = fmaf(f[k], wr[k], acc[j]);
         }
       }
-      __syncthreads();
-      sred[threadIdx.x] = acc;
-      __syncthreads();
-      if (row == 0 && c < c_in) {
-        float s = 0.f;
-        for (int r = 0; r < rows; ++r) s += sred[r * lanes + ci];
-        atomicAdd(dw + (long)co * c_in + c, s);
+    }
+#pragma unroll
+    for (int j = 0; j < HEAD_MAX_CO; ++j) {
+      acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], 1);
+      acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], 2);
+      acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], 4);
+    }
+    if (valid && oct < c_out) {
+      const long bi = pos / spatial, sp = pos % spatial;
+      float v = 0.f;
+#pragma unroll
+      for (int j = 0; j < HEAD_MAX_CO; ++j)
+        if (j == oct) v = acc[j];
+      logits[(bi * c_out + oct) * spatial + sp] = v + sw[c_out * c_in + oct];
+    }
+  }
+}
+// One pass over x and dlogits: dx[pos][ci] = sum_co g[co] w[co][ci] (bf16 store) and
+// dw[co][ci] += sum_pos g[co] x[pos][ci], db[co] += sum_pos g[co].
+__global__ void __launch_bounds__(256)
+    head_bwd_kernel(int n, long spatial, int c_in, int c_out, long chunk, View x, const float* w,
+                    const float* dlogits, View dx, float* dw, float* db) {
+  extern __shared__ float sw[];       // [c_out][c_in] weights, then [32][c_out][8] reduction scratch
+  float* sred = sw + c_out * c_in;
+  for (int i = threadIdx.x; i < c_out * c_in; i += blockDim.x) sw[i] = w[i];
+  __syncthreads();
+  const long total = (long)n * spatial;
+  const int oct = threadIdx.x & 7, prow = threadIdx.x >> 3;  // 32 positions per block pass
+  const long pbeg = (long)blockIdx.x * chunk;
+  const long pend = pbeg + chunk < total ? pbeg + chunk : total;
+  for (int cb = 0; cb < c_in; cb += 64) {
+    const int c0 = cb + oct * 8;
+    float aw[HEAD_MAX_CO][8];
+    float ab[HEAD_MAX_CO];
+#pragma unroll
+    for (int j = 0; j < HEAD_MAX_CO; ++j) {
+      ab[j] = 0.f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) aw[j][k] = 0.f;
+    }
+    if (c0 < c_in) {
+      for (long pos = pbeg + prow; pos < pend; pos += 32) {
+        const long bi = pos / spatial, sp = pos % spatial;
+        float f[8], o[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        ld8(x.at(pos, c0), f);
+#pragma unroll
+        for (int j = 0; j < HEAD_MAX_CO; ++j) {
+          if (j < c_out) {
+            const float g = dlogits[(bi * c_out + j) * spatial + sp];
+            const float* wr = sw + j * c_in + c0;
+            ab[j] += g;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              aw[j][k] = fmaf(g, f[k], aw[j][k]);
+              o[k] = fmaf(g, wr[k], o[k]);
+            }
+          }
+        }
+        if (dx.p) {
+          uint4 u;
+          u.x = pack_bf16x2(o[0], o[1]); u.y = pack_bf16x2(o[2], o[3]);
+          u.z = pack_bf16x2(o[4], o[5]); u.w = pack_bf16x2(o[6], o[7]);
+          *reinterpret_cast<uint4*>(dx.at(pos, c0)) = u;
+        }
       }
-      if (cib == 0 && db) {
+    }
+    // reduce the 32 position-rows of the block, one output channel at a time
+    for (int j = 0; j < c_out; ++j) {
+      __syncthreads();
+#pragma unroll
+      for (int k = 0; k < 8; ++k) sred[(prow * 8 + oct) * 8 + k] = aw[j][k];
+      __syncthreads();
+      if (threadIdx.x < 64) {
+        const int o8 = threadIdx.x >> 3, k = threadIdx.x & 7;
+        float s = 0.f;
+        for (int r = 0; r < 32; ++r) s += sred[(r * 8 + o8) * 8 + k];
+        const int c = cb + o8 * 8 + k;
+        if (c < c_in && dw) atomicAdd(dw + (long)j * c_in + c, s);
+      }
+      if (cb == 0 && db) {
         __syncthreads();
-        sred[threadIdx.x] = (ci == 0 && row < rows) ? accb : 0.f;
+        sred[threadIdx.x] = oct == 0 ? ab[j] : 0.f;
         __syncthreads();
         if (threadIdx.x == 0) {
           float s = 0.f;
-          for (int r = 0; r < rows; ++r) s += sred[r * lanes];
-          atomicAdd(db + co, s);
+          for (int r = 0; r < 256; r += 8) s += sred[r];
+          atomicAdd(db + j, s);
         }
       }
     }
@@ -313,8 +344,9 @@ int b200_head_fwd(int32_t n, int64_t spatial, int32_t c_in, int32_t c_out, b200_
   const long total = (long)n * spatial;
   if (total <= 0) return B200_OK;
   const size_t smem = ((size_t)c_out * c_in + c_out) * sizeof(float);
-  if (smem > 48 * 1024) return B200_ERR_UNSUPPORTED;
-  head_fwd_kernel<<<grid1d(total), 256, smem, (cudaStream_t)stream>>>(n, (long)spatial, c_in, c_out, mk(x), w, b, logits);
+  if (smem > 48 * 1024 || c_out > HEAD_MAX_CO || c_in % 8 || x.ctot % 8 || x.coff % 8)
+    return B200_ERR_UNSUPPORTED;
+  head_fwd_kernel<<<grid1d(total * 8), 256, smem, (cudaStream_t)stream>>>(n, (long)spatial, c_in, c_out, mk(x), w, b, logits);
   B200_LAUNCH_CHECK();
   return B200_OK;
 }
@@ -323,20 +355,15 @@ int b200_head_bwd(int32_t n, int64_t spatial, int32_t c_in, int32_t c_out, b200_
                   b200_stream_t stream) {
   const long total = (long)n * spatial;
   if (total <= 0) return B200_OK;
-  const size_t smem = (size_t)c_out * c_in * sizeof(float);
-  if (smem > 48 * 1024) return B200_ERR_UNSUPPORTED;
-  if (dx.ptr) {
-    head_bwd_data_kernel<<<grid1d(total * ((c_in + 7) / 8)), 256, smem, (cudaStream_t)stream>>>(
-        n, (long)spatial, c_in, c_out, w, dlogits, mk(dx));
-    B200_LAUNCH_CHECK();
-  }
-  if (dw) {
-    long chunk = (total + 148L * 4 - 1) / (148L * 4);
-    if (chunk < 64) chunk = 64;
-    head_bwd_weight_kernel<<<(unsigned)((total + chunk - 1) / chunk), 256, 0, (cudaStream_t)stream>>>(
-        n, (long)spatial, c_in, c_out, chunk, mk(x), dlogits, dw, db);
-    B200_LAUNCH_CHECK();
-  }
+  const size_t smem = ((size_t)c_out * c_in + 2048) * sizeof(float);
+  if (smem > 48 * 1024 || c_out > HEAD_MAX_CO || c_in % 8 || x.ctot % 8 || x.coff % 8 ||
+      (dx.ptr && (dx.ctot % 8 || dx.coff % 8)))
+    return B200_ERR_UNSUPPORTED;
+  long chunk = (total + 148L * 8 - 1) / (148L * 8);
+  if (chunk < 256) chunk = 256;
+  head_bwd_kernel<<<(unsigned)((total + chunk - 1) / chunk), 256, smem, (cudaStream_t)stream>>>(
+      n, (long)spatial, c_in, c_out, chunk, mk(x), w, dlogits, mk(dx), dw, db);
+  B200_LAUNCH_CHECK();
   return B200_OK;
 }
 

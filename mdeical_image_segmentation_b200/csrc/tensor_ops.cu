@@ -72,28 +72,26 @@ __global__ void maxpool_fwd_kernel(int n, int d, int h, int w, int c, int pd, Vi
   }
 }
 
-// one thread per INPUT position: recompute the window arg-max (first maximum in d,h,w scan order)
+// one thread per pooling WINDOW (including the partial windows an odd edge leaves over): reads the
+// window once, routes dy to the first maximum in (d,h,w) scan order and writes every dx of the window
 template <int V>
 __global__ void maxpool_bwd_kernel(int n, int d, int h, int w, int c, int pd, View x, View dy, View add, View dx) {
   const int od = d / pd, oh = h / 2, ow = w / 2, cv = c / V;
-  const long total = (long)n * d * h * w * cv;
+  const int wd = (d + pd - 1) / pd, wh = (h + 1) / 2, ww = (w + 1) / 2;
+  const long total = (long)n * wd * wh * ww * cv;
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
     long r = i;
     const int ch = (int)(r % cv) * V; r /= cv;
-    const int xw = (int)(r % w); r /= w;
-    const int xh = (int)(r % h); r /= h;
-    const int xd = (int)(r % d); r /= d;
+    const int pw_ = (int)(r % ww); r /= ww;
+    const int ph_ = (int)(r % wh); r /= wh;
+    const int pdd = (int)(r % wd); r /= wd;
     const int b = (int)r;
-    const long ipos = (((long)b * d + xd) * h + xh) * w + xw;
-    float out[V];
+    const bool pooled = pw_ < ow && ph_ < oh && pdd < od;
+    float m[V];
+    int arg[V];
 #pragma unroll
-    for (int j = 0; j < V; ++j) out[j] = 0.f;
-    if (add.p) Vec<V>::load(add.at(ipos, ch), out);
-    const int pw_ = xw >> 1, ph_ = xh >> 1, pdd = xd / pd;
-    if (pw_ < ow && ph_ < oh && pdd < od) {
-      const int self = ((xd - pdd * pd) * 2 + (xh & 1)) * 2 + (xw & 1);
-      float m[V];
-      int arg[V];
+    for (int j = 0; j < V; ++j) { m[j] = 0.f; arg[j] = -1; }
+    if (pooled) {
       int k = 0;
       for (int a = 0; a < pd; ++a)
         for (int e = 0; e < 2; ++e)
@@ -105,13 +103,26 @@ __global__ void maxpool_bwd_kernel(int n, int d, int h, int w, int c, int pd, Vi
             for (int j = 0; j < V; ++j)
               if (k == 0 || f[j] > m[j]) { m[j] = f[j]; arg[j] = k; }
           }
-      float g_[V];
-      const long opos = (((long)b * od + pdd) * oh + ph_) * ow + pw_;
-      Vec<V>::load(dy.at(opos, ch), g_);
-#pragma unroll
-      for (int j = 0; j < V; ++j) out[j] += (arg[j] == self) ? g_[j] : 0.f;
     }
-    Vec<V>::store(dx.at(ipos, ch), out);
+    float g_[V];
+#pragma unroll
+    for (int j = 0; j < V; ++j) g_[j] = 0.f;
+    if (pooled) Vec<V>::load(dy.at((((long)b * od + pdd) * oh + ph_) * ow + pw_, ch), g_);
+    int k = 0;
+    for (int a = 0; a < pd; ++a)
+      for (int e = 0; e < 2; ++e)
+        for (int g = 0; g < 2; ++g, ++k) {
+          const int xd = pdd * pd + a, xh = ph_ * 2 + e, xw = pw_ * 2 + g;
+          if (xd >= d || xh >= h || xw >= w) continue;
+          const long pos = (((long)b * d + xd) * h + xh) * w + xw;
+          float out[V];
+#pragma unroll
+          for (int j = 0; j < V; ++j) out[j] = 0.f;
+          if (add.p) Vec<V>::load(add.at(pos, ch), out);
+#pragma unroll
+          for (int j = 0; j < V; ++j) out[j] += (arg[j] == k) ? g_[j] : 0.f;
+          Vec<V>::store(dx.at(pos, ch), out);
+        }
   }
 }
 
@@ -524,8 +535,8 @@ int b200_maxpool2_fwd(int32_t n, int32_t d, int32_t h, int32_t w, int32_t c, int
 int b200_maxpool2_bwd(int32_t n, int32_t d, int32_t h, int32_t w, int32_t c, int32_t pool_d,
                       b200_view x, b200_view dy, b200_view add, b200_view dx, b200_stream_t stream) {
   if (pool_d != 1 && pool_d != 2) return B200_ERR_BAD_ARG;
-  const long total = (long)n * d * h * w * c;
-  if (total <= 0) return B200_OK;
+  if ((long)n * d * h * w * c <= 0) return B200_OK;
+  const long total = (long)n * ((d + pool_d - 1) / pool_d) * ((h + 1) / 2) * ((w + 1) / 2) * c;
   const bool v = vec8(c, x) && vec8(c, dy) && vec8(c, dx) && (!add.ptr || vec8(c, add));
   DISPATCH_V(v, maxpool_bwd_kernel, GRID1D(total / (v ? 8 : 1)), n, d, h, w, c, pool_d, mk(x), mk(dy),
              mk(add), mk(dx));

@@ -92,17 +92,24 @@ def single_conv_fwd(x: CL, spec: LayerSpec, training: bool, tape: Optional[list]
         dst = out if nxt >= len(letters) else None
         if ch == "c":
             conv = spec.conv
-            wp_fwd, wp_bwd, k = ops.conv_repack_weight(conv.weight, need_bwd=tape is not None)
+            w = conv.weight.detach()
+            xin = cur
+            if cur.zpad:  # narrow network input stored zero-padded: pad the filter's c_in to match
+                xin = cur.widened()
+                w = torch.nn.functional.pad(w, (0, 0) * (w.dim() - 2) + (0, cur.zpad))
+            wp_fwd, wp_bwd, k = ops.conv_repack_weight(w, need_bwd=tape is not None)
             bias = None if conv.bias is None else conv.bias.detach().float().contiguous()
-            y = ops.conv_fwd(cur, wp_fwd, k, bias, fuse_relu, out=dst, impl=IMPL)
+            y = ops.conv_fwd(xin, wp_fwd, k, bias, fuse_relu, out=dst, impl=IMPL)
             if tape is not None:
-                tape.append(("conv", cur, conv, wp_bwd, k, y if fuse_relu else None))
+                tape.append(("conv", xin, conv, wp_bwd, k, y if fuse_relu else None, cur.zpad))
             cur = y
         elif ch == "g":
             gn = spec.groupnorm
             stats = ops.gn_stats(cur, gn.num_groups, gn.eps)
             gamma = gn.weight.detach().float().contiguous()
             beta = gn.bias.detach().float().contiguous()
+            if dst is None and cur.zpad:
+                dst = cur.new_like_padded()
             y = ops.gn_apply(cur, gn.num_groups, stats, gamma, beta, fuse_relu, out=dst)
             if tape is not None:
                 tape.append(("gn", cur, gn, stats, gamma, y if fuse_relu else None))
@@ -112,6 +119,8 @@ def single_conv_fwd(x: CL, spec: LayerSpec, training: bool, tape: Optional[list]
             mean, rstd = _bn_moments(bn, cur, training)
             gamma = bn.weight.detach().float().contiguous()
             beta = bn.bias.detach().float().contiguous()
+            if dst is None and cur.zpad:
+                dst = cur.new_like_padded()
             y = ops.bn_apply(cur, mean, rstd, gamma, beta, fuse_relu, out=dst)
             if tape is not None:
                 tape.append(("bn", cur, bn, mean, rstd, gamma, y if fuse_relu else None, training))
@@ -132,7 +141,7 @@ def single_conv_bwd(dy: CL, recs: list, grads: Grads, need_dx: bool = True) -> O
         kind = rec[0]
         last = idx == 0
         if kind == "conv":
-            _, x_in, conv, wp_bwd, k, y_relu = rec
+            _, x_in, conv, wp_bwd, k, y_relu, zpad = rec
             has_bias = conv.bias is not None and conv.bias.requires_grad
             if y_relu is not None:
                 dy, db = ops.relu_bwd(dy, y_relu, has_bias, out=dy)
@@ -141,11 +150,17 @@ def single_conv_bwd(dy: CL, recs: list, grads: Grads, need_dx: bool = True) -> O
             if has_bias:
                 _acc(grads, conv.bias, db)
             if conv.weight.requires_grad:
-                _acc(grads, conv.weight, ops.conv_bwd_weight(x_in, dy, k, tuple(conv.weight.shape),
-                                                            impl=IMPL))
+                wshape = list(conv.weight.shape)
+                wshape[1] += zpad
+                dw = ops.conv_bwd_weight(x_in, dy, k, tuple(wshape), impl=IMPL)
+                if zpad:
+                    dw = dw[:, :conv.weight.shape[1]].contiguous()
+                _acc(grads, conv.weight, dw)
             if last and not need_dx:
                 return None
             dy = ops.conv_bwd_data(dy, wp_bwd, k, impl=IMPL)
+            if zpad:  # gradient w.r.t. the padding channels is meaningless: expose the real slice
+                dy = CL(dy.buf, dy.c - zpad, 0, zpad)
         elif kind == "gn":
             _, x_in, gn, stats, gamma, y_relu = rec
             if y_relu is not None:
@@ -197,7 +212,7 @@ def unet2d_forward(net, images: torch.Tensor, training: bool, tape: Optional[lis
 
     Concat order is [up-sampled, skip] (layers.py:188): the ConvTranspose epilogue scatters into
     channels [0, C) and the encoder's second conv writes channels [C, 2C) of the same buffer."""
-    x = ops.from_nchw(images)
+    x = ops.from_nchw(images, pad=True)
     n_lvl = len(net.down_conv)
     skips: List[CL] = []
     for i in range(n_lvl):
@@ -286,7 +301,7 @@ def unet3d_forward(net, x_in: torch.Tensor, training: bool, tape: Optional[list]
     (buildingblocks.py:547): skip channels [0, Cs), up-sampled [Cs, Cs + Cx)."""
     is3d = net.is3d
     order = net.layer_order
-    x = ops.from_nchw(x_in)
+    x = ops.from_nchw(x_in, pad=True)
     n_enc = len(net.encoders)
     skips: List[CL] = []
     for i, enc in enumerate(net.encoders):

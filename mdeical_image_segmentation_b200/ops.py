@@ -34,14 +34,17 @@ def require_cuda(t: torch.Tensor) -> None:
 
 class CL:
     """Channel slice of a channels-last bf16 buffer of shape (N, D, H, W, Ctot)."""
-    __slots__ = ("buf", "c", "coff")
+    __slots__ = ("buf", "c", "coff", "zpad")
 
-    def __init__(self, buf: torch.Tensor, c: Optional[int] = None, coff: int = 0):
+    def __init__(self, buf: torch.Tensor, c: Optional[int] = None, coff: int = 0, zpad: int = 0):
         assert buf.dim() == 5 and buf.dtype == bf16 and buf.is_contiguous(), (buf.shape, buf.dtype)
         self.buf = buf
         self.coff = coff
         self.c = buf.shape[4] - coff if c is None else c
-        assert 0 <= coff and coff + self.c <= buf.shape[4]
+        # zpad: number of all-zero channels that follow the slice in the buffer.  Narrow network
+        # inputs (1..4 channels) are stored padded to 16 so the first conv runs on the tensor cores.
+        self.zpad = zpad
+        assert 0 <= coff and coff + self.c + zpad <= buf.shape[4]
 
     @staticmethod
     def empty(n, d, h, w, c, device) -> "CL":
@@ -85,6 +88,18 @@ class CL:
 
     def new_like(self, c: Optional[int] = None) -> "CL":
         return CL.empty(self.n, self.d, self.h, self.w, self.c if c is None else c, self.device)
+
+    def new_like_padded(self) -> "CL":
+        """Same logical channels and the same zero padding after them."""
+        if not self.zpad:
+            return self.new_like()
+        buf = torch.zeros((self.n, self.d, self.h, self.w, self.c + self.zpad), dtype=bf16,
+                          device=self.device)
+        return CL(buf, self.c, 0, self.zpad)
+
+    def widened(self) -> "CL":
+        """The slice together with its zero padding, as one wider operand."""
+        return CL(self.buf, self.c + self.zpad, self.coff) if self.zpad else self
 
 
 
@@ -292,15 +307,21 @@ def bias_grad(dy: CL) -> torch.Tensor:
     return db
 
 
-def from_nchw(x: torch.Tensor, out: Optional[CL] = None) -> CL:
-    """fp32 (N, C, [D,] H, W) -> channels-last bf16."""
+PAD_C = 16  # narrow inputs are zero-padded to this many channels (one UMMA K step)
+
+
+def from_nchw(x: torch.Tensor, out: Optional[CL] = None, pad: bool = False) -> CL:
+    """fp32 (N, C, [D,] H, W) -> channels-last bf16 (optionally zero-padded to PAD_C channels)."""
     require_cuda(x)
     x = x.contiguous().float()
     n, c = x.shape[0], x.shape[1]
     sp = tuple(x.shape[2:])
     d, h, w = ((1,) + sp) if len(sp) == 2 else sp
     if out is None:
-        out = CL.empty(n, d, h, w, c, x.device)
+        if pad and c < PAD_C:
+            out = CL(torch.zeros((n, d, h, w, PAD_C), dtype=bf16, device=x.device), c, 0, PAD_C - c)
+        else:
+            out = CL.empty(n, d, h, w, c, x.device)
     call("b200_nchw_f32_to_cl_bf16", n, c, d * h * w, _p(x), out.view(), _stream())
     return out
 
