@@ -35,6 +35,9 @@ int b200_version(void);
 const char* b200_strerror(int code);
 /* last tcgen05/direct decision taken by a conv-like entry point on this thread (1 or 2) */
 int b200_last_impl(void);
+/* tuning / A-B knobs (process-wide): key 0 = halo-reuse fwd/dgrad kernel,
+ * key 1 = halo-reuse weight-gradient kernel; value 1 = on (default), 0 = off */
+int b200_set_tuning(int key, int value);
 
 /* ---- 3x3 / 3x3x3 / 1x1 "same" convolution ------------------------------------------------------
  * replaces nn.Conv2d  model/unet2d/layers.py:20,122,125 and nn.Conv3d/2d

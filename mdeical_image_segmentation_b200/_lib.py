@@ -85,6 +85,7 @@ _SPECIAL = {
     "b200_version": ([], C.c_int),
     "b200_strerror": ([C.c_int], C.c_char_p),
     "b200_last_impl": ([], C.c_int),
+    "b200_set_tuning": ([C.c_int, C.c_int], C.c_int),
 }
 ALL_SYMBOLS = sorted(list(SIGNATURES) + list(_SPECIAL))
 

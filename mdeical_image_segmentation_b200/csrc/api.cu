@@ -4,6 +4,8 @@
 #include "conv_tc.cuh"
 
 namespace b200 {
+extern int g_halo_mode;
+extern int g_wgrad_halo_mode;
 int direct_gemm_conv(const TcGemmProblem& p, cudaStream_t stream);
 int direct_wgrad(const TcWgradProblem& p, cudaStream_t stream);
 struct DeconvArgs {
@@ -113,6 +115,12 @@ const char* b200_strerror(int code) {
 }
 
 int b200_last_impl(void) { return g_last_impl; }
+
+int b200_set_tuning(int key, int value) {
+  if (key == 0) { b200::g_halo_mode = value; return B200_OK; }
+  if (key == 1) { b200::g_wgrad_halo_mode = value; return B200_OK; }
+  return B200_ERR_BAD_ARG;
+}
 
 int b200_conv_repack_weight(const b200_conv_desc* d, const float* w, void* wp_fwd, void* wp_bwd,
                             b200_stream_t stream) {

@@ -274,6 +274,204 @@ __global__ void __launch_bounds__(256, 1)
   if (warp == 2) tmem_dealloc(tmem_base, tmem_cols);
 }
 
+// ===================================================================== halo-reuse forward / dgrad
+// For 3x3(x3) convolutions on planes of at least 16 x 8 positions the per-tap TMA loads above re-read
+// every activation 9 (27) times from L2.  This variant fetches ONE halo box per 64-channel chunk —
+// (TW+2) x (TH+2) x kd input positions for a 1 x 16 x 8 output tile — and feeds all taps from it:
+// the UMMA A descriptor of tap (kd,kh,kw) simply starts at halo row ((kd*18 + kh)*10 + kw) with an
+// 8-row-group stride (SBO) of 10 rows = 1280 B.  Measured on B200 (tools/desc_probe.cu,
+// profiles/r01_desc_probe_kmajor.log): SWIZZLE_128B operands may start at any 128-byte row and use
+// any SBO that is a multiple of 128 B, because the XOR pattern follows absolute shared-memory address
+// bits — exactly how TMA wrote the box.  L2->SM traffic for A drops 6.3x (3D) / 6.4x (2D).
+static const int kHaloW = 10, kHaloH = 18;
+static const int kHaloPlaneBytes = kHaloW * kHaloH * 128;  // 23040
+
+struct HaloArgs {
+  int pn, pd, ph, pw;
+  int tiles_h, tiles_w, m_tiles, n_tiles, total;
+  int kd;                // 1 or 3 depth taps (kh = kw = 3)
+  int kchunks, kdim, BN;
+  int a_stage_bytes, a_stages, b_slots;
+  bf16* out;
+  int out_ctot, out_coff;
+  const float* bias;
+  int relu;
+  const bf16* mask;
+  int mask_ctot, mask_coff;
+};
+
+__global__ void __launch_bounds__(256, 1)
+    tc_gemm_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                        const HaloArgs p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t sraw = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (sraw & 1023u)) & 1023u);
+  uint64_t* afull = reinterpret_cast<uint64_t*>(smem);
+  uint64_t* aempty = afull + 4;
+  uint64_t* bfull = aempty + 4;
+  uint64_t* bempty = bfull + 16;
+  uint64_t* tfull = bempty + 16;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  uint8_t* sA = smem + 1024;
+  uint8_t* sB = sA + (size_t)p.a_stages * p.a_stage_bytes;
+  const int b_bytes = p.BN * 128;
+  const int ntaps = p.kd * 9;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < p.a_stages; ++s) { mbar_init(&afull[s], 1); mbar_init(&aempty[s], 1); }
+    for (int s = 0; s < p.b_slots; ++s) { mbar_init(&bfull[s], 1); mbar_init(&bempty[s], 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 128); }
+    fence_barrier_init();
+  }
+  uint32_t tmem_cols = 32;
+  while (tmem_cols < (uint32_t)(2 * p.BN)) tmem_cols <<= 1;
+  if (warp == 2) tmem_alloc(tmem_slot, tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0 && lane == 0) {
+    // ---------------------------------------------------------------- A (halo) producer
+    int stage = 0;
+    uint32_t phase = 0;
+    const uint32_t halo_bytes = (uint32_t)(kHaloPlaneBytes * p.kd);
+    for (int work = blockIdx.x; work < p.total; work += gridDim.x) {
+      const int mt = work / p.n_tiles;
+      const TileCoord tc = decode_tile(mt, p.pd, p.tiles_h, p.tiles_w, 0, 4, 3);
+      for (int kc = 0; kc < p.kchunks; ++kc) {
+        mbar_wait(&aempty[stage], phase ^ 1);
+        mbar_arrive_expect_tx(&afull[stage], halo_bytes);
+        tma_load_5d(sA + (size_t)stage * p.a_stage_bytes, &tmA, &afull[stage], kc * 64, tc.w0 - 1,
+                    tc.h0 - 1, tc.d0 - (p.kd >> 1), tc.n);
+        if (++stage == p.a_stages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 3 && lane == 0) {
+    // ---------------------------------------------------------------- B (weights) producer
+    int slot = 0;
+    uint32_t phase = 0;
+    for (int work = blockIdx.x; work < p.total; work += gridDim.x) {
+      const int nt = work % p.n_tiles;
+      for (int kc = 0; kc < p.kchunks; ++kc)
+        for (int tap = 0; tap < ntaps; ++tap) {
+          mbar_wait(&bempty[slot], phase ^ 1);
+          mbar_arrive_expect_tx(&bfull[slot], (uint32_t)b_bytes);
+          tma_load_3d(sB + (size_t)slot * b_bytes, &tmB, &bfull[slot], kc * 64, nt * p.BN, tap);
+          if (++slot == p.b_slots) { slot = 0; phase ^= 1; }
+        }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ---------------------------------------------------------------- MMA issuer
+    const uint32_t idesc = make_idesc_bf16(128, p.BN, 0, 0);
+    int stage = 0, slot = 0;
+    uint32_t aphase = 0, bphase = 0, acc = 0, acc_phase = 0;
+    for (int work = blockIdx.x; work < p.total; work += gridDim.x) {
+      mbar_wait(&tempty[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + acc * (uint32_t)p.BN;
+      for (int kc = 0; kc < p.kchunks; ++kc) {
+        int nk = (p.kdim - kc * 64 + 15) >> 4;
+        nk = nk > 4 ? 4 : nk;
+        mbar_wait(&afull[stage], aphase);
+        tc_fence_after();
+        const uint32_t abase = smem_u32(sA + (size_t)stage * p.a_stage_bytes);
+        int tap = 0;
+        for (int kdi = 0; kdi < p.kd; ++kdi)
+          for (int khi = 0; khi < 3; ++khi)
+            for (int kwi = 0; kwi < 3; ++kwi, ++tap) {
+              mbar_wait(&bfull[slot], bphase);
+              tc_fence_after();
+              const uint32_t aaddr = abase + (uint32_t)(((kdi * kHaloH + khi) * kHaloW + kwi) * 128);
+              const uint32_t baddr = smem_u32(sB + (size_t)slot * b_bytes);
+              for (int k = 0; k < nk; ++k) {
+                const uint64_t da = make_smem_desc_sw128(aaddr + k * 32, 16, kHaloW * 128);
+                const uint64_t db = make_smem_desc_sw128(baddr + k * 32, 16, 1024);
+                umma_bf16(tmem_d, da, db, idesc, (kc | tap | k) != 0);
+              }
+              umma_commit(&bempty[slot]);
+              if (++slot == p.b_slots) { slot = 0; bphase ^= 1; }
+            }
+        umma_commit(&aempty[stage]);
+        if (++stage == p.a_stages) { stage = 0; aphase ^= 1; }
+      }
+      umma_commit(&tfull[acc]);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  } else if (warp >= 4) {
+    // ---------------------------------------------------------------- epilogue
+    const int q = warp - 4;
+    const int row = q * 32 + lane;
+    uint32_t acc = 0, acc_phase = 0;
+    for (int work = blockIdx.x; work < p.total; work += gridDim.x) {
+      const int mt = work / p.n_tiles, nt = work - mt * p.n_tiles;
+      const TileCoord tc = decode_tile(mt, p.pd, p.tiles_h, p.tiles_w, 0, 4, 3);
+      const int wx = tc.w0 + (row & 7);
+      const int hy = tc.h0 + (row >> 3);
+      const bool valid = (wx < p.pw) && (hy < p.ph);
+      const long opos = (((long)tc.n * p.pd + tc.d0) * p.ph + hy) * p.pw + wx;
+      const int ocol0 = nt * p.BN;
+      bf16* orow = p.out + opos * p.out_ctot + p.out_coff + ocol0;
+      const bf16* mrow = p.mask ? p.mask + opos * p.mask_ctot + p.mask_coff + ocol0 : nullptr;
+      const float* brow = p.bias ? p.bias + ocol0 : nullptr;
+      mbar_wait(&tfull[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * (uint32_t)p.BN;
+      for (int c0 = 0; c0 < p.BN; c0 += 16) {
+        uint32_t v[16];
+        tmem_ld16(taddr + c0, v);
+        tmem_ld_wait();
+        if (valid) {
+          float f[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
+          if (brow) {
+#pragma unroll
+            for (int j = 0; j < 16; j += 4) {
+              const float4 b4 = __ldg(reinterpret_cast<const float4*>(brow + c0 + j));
+              f[j] += b4.x; f[j + 1] += b4.y; f[j + 2] += b4.z; f[j + 3] += b4.w;
+            }
+          }
+          if (p.relu) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
+          }
+          if (mrow) {
+            const uint4 m0 = *reinterpret_cast<const uint4*>(mrow + c0);
+            const uint4 m1 = *reinterpret_cast<const uint4*>(mrow + c0 + 8);
+            const uint32_t mw[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float2 mv = unpack_bf16x2(mw[j]);
+              if (!(mv.x > 0.f)) f[2 * j] = 0.f;
+              if (!(mv.y > 0.f)) f[2 * j + 1] = 0.f;
+            }
+          }
+          uint4 o0, o1;
+          o0.x = pack_bf16x2(f[0], f[1]);   o0.y = pack_bf16x2(f[2], f[3]);
+          o0.z = pack_bf16x2(f[4], f[5]);   o0.w = pack_bf16x2(f[6], f[7]);
+          o1.x = pack_bf16x2(f[8], f[9]);   o1.y = pack_bf16x2(f[10], f[11]);
+          o1.z = pack_bf16x2(f[12], f[13]); o1.w = pack_bf16x2(f[14], f[15]);
+          *reinterpret_cast<uint4*>(orow + c0) = o0;
+          *reinterpret_cast<uint4*>(orow + c0 + 8) = o1;
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&tempty[acc]);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, tmem_cols);
+}
+
 static int sm_count() {
   static int n = 0;
   if (!n) {
@@ -305,8 +503,75 @@ bool tc_gemm_supported(const TcGemmProblem& p) {
   return true;
 }
 
+static int pick_bn(int ncols, int limit);
+static int sm_count();
+int g_halo_mode = 1;  // 0 disables the halo-reuse kernel (A/B testing from the bench tools)
+
+static bool halo_eligible(const TcGemmProblem& p) {
+  return g_halo_mode && p.tap_mode == TC_TAP_SHIFT && p.out_mode == TC_OUT_CONV && p.kh == 3 &&
+         p.kw == 3 && (p.kd == 3 || p.kd == 1) && p.ph >= 12 && p.pw >= 8;
+}
+
+static int tc_gemm_halo(const TcGemmProblem& p, cudaStream_t stream) {
+  HaloArgs a{};
+  a.pn = p.pn; a.pd = p.pd; a.ph = p.ph; a.pw = p.pw;
+  a.tiles_h = (p.ph + 15) / 16; a.tiles_w = (p.pw + 7) / 8;
+  a.m_tiles = p.pn * p.pd * a.tiles_h * a.tiles_w;
+  a.BN = pick_bn(p.ncols, 256);
+  a.n_tiles = p.ncols / a.BN;
+  a.total = a.m_tiles * a.n_tiles;
+  a.kd = p.kd;
+  a.kdim = p.kdim; a.kchunks = (p.kdim + 63) / 64;
+  a.a_stage_bytes = ((kHaloPlaneBytes * p.kd) + 1023) / 1024 * 1024;
+  a.a_stages = 2;
+  const int b_bytes = a.BN * 128;
+  int rem = kSmemBudget - 2048 - a.a_stages * a.a_stage_bytes;
+  if (p.kd == 1 && rem - 4 * b_bytes >= 2 * a.a_stage_bytes) {  // 2D: cheap stages, go deeper
+    a.a_stages = 4;
+    rem = kSmemBudget - 2048 - a.a_stages * a.a_stage_bytes;
+  }
+  a.b_slots = rem / b_bytes;
+  if (a.b_slots > 12) a.b_slots = 12;
+  if (a.b_slots < 2) return B200_ERR_UNSUPPORTED;
+  a.out = p.out; a.out_ctot = p.out_ctot; a.out_coff = p.out_coff;
+  a.bias = p.bias; a.relu = p.relu;
+  a.mask = p.mask; a.mask_ctot = p.mask_ctot; a.mask_coff = p.mask_coff;
+
+  CUtensorMap tmA, tmB;
+  {
+    const ActView& v = p.a;
+    uint64_t dims[5] = {(uint64_t)v.c, (uint64_t)v.w, (uint64_t)v.h, (uint64_t)v.d, (uint64_t)v.n};
+    uint64_t str[5] = {1, (uint64_t)v.ctot, (uint64_t)v.w * v.ctot, (uint64_t)v.h * v.w * v.ctot,
+                       (uint64_t)v.d * v.h * v.w * v.ctot};
+    uint32_t box[5] = {64, (uint32_t)kHaloW, (uint32_t)kHaloH, (uint32_t)p.kd, 1};
+    int rc = make_tmap_bf16(&tmA, v.ptr + v.coff, 5, dims, str, box);
+    if (rc) return rc;
+  }
+  {
+    const int ntaps = p.kd * 9;
+    uint64_t dims[3] = {(uint64_t)p.kdim, (uint64_t)p.ncols, (uint64_t)ntaps};
+    uint64_t str[3] = {1, (uint64_t)p.kdim, (uint64_t)p.kdim * p.ncols};
+    uint32_t box[3] = {64, (uint32_t)a.BN, 1};
+    int rc = make_tmap_bf16(&tmB, p.wp, 3, dims, str, box);
+    if (rc) return rc;
+  }
+  const int smem = a.a_stages * a.a_stage_bytes + a.b_slots * b_bytes + 2048;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(tc_gemm_halo_kernel,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
+    if (e != cudaSuccess) return (int)e;
+    attr_set = true;
+  }
+  const int grid = a.total < sm_count() ? a.total : sm_count();
+  tc_gemm_halo_kernel<<<grid, 256, smem, stream>>>(tmA, tmB, a);
+  B200_LAUNCH_CHECK();
+  return B200_OK;
+}
+
 int tc_gemm_conv(const TcGemmProblem& p, cudaStream_t stream) {
   if (!tc_gemm_supported(p)) return B200_ERR_UNSUPPORTED;
+  if (halo_eligible(p)) return tc_gemm_halo(p, stream);
   GemmArgs a{};
   a.pn = p.pn; a.pd = p.pd; a.ph = p.ph; a.pw = p.pw;
   const TileGeom g = pick_tile(p.pn, p.pd, p.ph, p.pw, p.tap_mode == TC_TAP_K2S2 || p.pd == 1);
@@ -496,6 +761,195 @@ __global__ void __launch_bounds__(256, 1)
   if (warp == 2) tmem_dealloc(tmem_base, tmem_cols);
 }
 
+// ===================================================================== halo-reuse weight gradient
+// dw[co][ci][tap] += sum_pos dy[pos][co] * x[pos + tap][ci] for the 9 taps of one depth plane, from ONE
+// x halo box (18 x 10 positions x 64 channels) and ONE dy tile (16 x 8 positions x <=64 channels) per
+// 128-position reduction block.  The shifted operand sits on the MMA's M side: M = 128 rows are TWO
+// taps x 64 input channels — the descriptor's leading byte offset (LBO) is simply the byte distance
+// between the two taps' first halo rows — so narrow layers still issue full-rate M = 128 MMAs.
+// Tap pairs (0,1)(2,3)(4,5)(6,7)(7,8); tap 7's duplicate is dropped in the epilogue.
+// MN-major operands with arbitrary row starts / SBO = 1280 B verified on B200
+// (tools/desc_probe_mn.cu, profiles/r01_desc_probe_mnmajor.log).
+struct WgradHaloArgs {
+  int pn, pd, ph, pw;
+  int tiles_h, tiles_w, m_tiles;
+  int kd;                       // depth taps (1 or 3); blockIdx decodes (split, kd, co blk, ci blk)
+  int ciblk, coblk, splits, tiles_per_split;
+  int cin, cout, N;             // N = co tile (multiple of 16, <= 64)
+  int stages;
+  float* dw;
+  long s_co, s_ci;
+};
+
+__global__ void __launch_bounds__(256, 1)
+    tc_wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmDY,
+                         const WgradHaloArgs p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t sraw = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (sraw & 1023u)) & 1023u);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem);
+  uint64_t* empty = full + 16;
+  uint64_t* tfull = empty + 16;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tfull + 2);
+  uint8_t* tiles = smem + 1024;
+  const int x_bytes = 23552;                 // 180 rows x 128 B, padded to 1024
+  const int stage_bytes = x_bytes + kABytes;  // + dy tile (128 rows x 128 B)
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmX);
+    tma_prefetch_desc(&tmDY);
+    for (int s = 0; s < p.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    mbar_init(&tfull[0], 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  int w = blockIdx.x;
+  const int cib = w % p.ciblk; w /= p.ciblk;
+  const int cob = w % p.coblk; w /= p.coblk;
+  const int kdi = w % p.kd; w /= p.kd;
+  const int split = w;
+  const int mt_begin = split * p.tiles_per_split;
+  int mt_end = mt_begin + p.tiles_per_split;
+  if (mt_end > p.m_tiles) mt_end = p.m_tiles;
+
+  if (warp == 0 && lane == 0) {
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int mt = mt_begin; mt < mt_end; ++mt) {
+      const TileCoord tc = decode_tile(mt, p.pd, p.tiles_h, p.tiles_w, 0, 4, 3);
+      mbar_wait(&empty[stage], phase ^ 1);
+      uint8_t* sX = tiles + (size_t)stage * stage_bytes;
+      uint8_t* sY = sX + x_bytes;
+      mbar_arrive_expect_tx(&full[stage], (uint32_t)(kHaloPlaneBytes + kABytes));
+      tma_load_5d(sX, &tmX, &full[stage], cib * 64, tc.w0 - 1, tc.h0 - 1, tc.d0 + kdi - (p.kd >> 1), tc.n);
+      tma_load_5d(sY, &tmDY, &full[stage], cob * 64, tc.w0, tc.h0, tc.d0, tc.n);
+      if (++stage == p.stages) { stage = 0; phase ^= 1; }
+    }
+  } else if (warp == 1 && lane == 0) {
+    const uint32_t idesc = make_idesc_bf16(128, p.N, 1, 1);
+    int stage = 0;
+    uint32_t phase = 0;
+    bool first = true;
+    for (int mt = mt_begin; mt < mt_end; ++mt) {
+      mbar_wait(&full[stage], phase);
+      tc_fence_after();
+      const uint32_t xaddr = smem_u32(tiles + (size_t)stage * stage_bytes);
+      const uint32_t yaddr = xaddr + x_bytes;
+      for (int g = 0; g < 5; ++g) {
+        const int ta = g < 4 ? 2 * g : 7, tb = ta + 1;
+        const int ra = (ta / 3) * kHaloW + (ta % 3), rb = (tb / 3) * kHaloW + (tb % 3);
+        for (int j = 0; j < 8; ++j) {  // 16 positions = 2 W-rows of the tile per MMA
+          const uint64_t da = make_smem_desc_sw128(xaddr + (uint32_t)((ra + j * 2 * kHaloW) * 128),
+                                                   (uint32_t)((rb - ra) * 128), kHaloW * 128);
+          const uint64_t db = make_smem_desc_sw128(yaddr + j * 2048, kABytes, 1024);
+          umma_bf16(tmem_base + g * 64, da, db, idesc, !(first && j == 0));
+        }
+      }
+      first = false;
+      umma_commit(&empty[stage]);
+      if (++stage == p.stages) { stage = 0; phase ^= 1; }
+    }
+    umma_commit(&tfull[0]);
+  } else if (warp >= 4) {
+    const int q = warp - 4;
+    const int m = q * 32 + lane;           // 0..127: (tap half, ci)
+    const int half = m >> 6;
+    const int ci = cib * 64 + (m & 63);
+    mbar_wait(&tfull[0], 0);
+    tc_fence_after();
+    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+    for (int g = 0; g < 5; ++g) {
+      const int ta = g < 4 ? 2 * g : 7;
+      const int tap = ta + half;
+      const bool dup = (g == 4 && half == 0);  // tap 7 was already produced by group 3
+      const bool ok = !dup && ci < p.cin && mt_end > mt_begin;
+      const long base = (long)ci * p.s_ci + (kdi * 9 + tap);
+      for (int c0 = 0; c0 < p.N; c0 += 16) {
+        uint32_t v[16];
+        tmem_ld16(taddr + g * 64 + c0, v);
+        tmem_ld_wait();
+        if (ok) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int co = cob * 64 + c0 + j;
+            if (co < p.cout) atomicAdd(p.dw + (long)co * p.s_co + base, __uint_as_float(v[j]));
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, 512);
+}
+
+int g_wgrad_halo_mode = 1;
+
+static bool wgrad_halo_eligible(const TcWgradProblem& p) {
+  return g_wgrad_halo_mode && p.tap_mode == TC_TAP_SHIFT && p.kh == 3 && p.kw == 3 &&
+         (p.kd == 3 || p.kd == 1) && p.ph >= 12 && p.pw >= 8;
+}
+
+static int tc_wgrad_halo(const TcWgradProblem& p, cudaStream_t stream) {
+  // conv: mop = dy (c_out), nop = x (c_in); dw index = co * s_m + ci * s_n + tap
+  WgradHaloArgs a{};
+  a.pn = p.pn; a.pd = p.pd; a.ph = p.ph; a.pw = p.pw;
+  a.tiles_h = (p.ph + 15) / 16; a.tiles_w = (p.pw + 7) / 8;
+  a.m_tiles = p.pn * p.pd * a.tiles_h * a.tiles_w;
+  a.kd = p.kd;
+  a.cin = p.nop.c; a.cout = p.mop.c;
+  a.ciblk = (a.cin + 63) / 64; a.coblk = (a.cout + 63) / 64;
+  a.N = a.cout >= 64 ? 64 : ((a.cout + 15) / 16) * 16;
+  const int stage_bytes = 23552 + kABytes;
+  a.stages = (kSmemBudget - 2048) / stage_bytes;
+  if (a.stages > 6) a.stages = 6;
+  const long base_ctas = (long)a.ciblk * a.coblk * a.kd;
+  long want = (2L * sm_count() + base_ctas - 1) / base_ctas;
+  if (want < 1) want = 1;
+  if (want > a.m_tiles) want = a.m_tiles;
+  a.tiles_per_split = (int)((a.m_tiles + want - 1) / want);
+  a.splits = (a.m_tiles + a.tiles_per_split - 1) / a.tiles_per_split;
+  a.dw = p.dw; a.s_co = p.s_m; a.s_ci = p.s_n;
+
+  CUtensorMap tmX, tmDY;
+  {
+    const ActView& v = p.nop;
+    uint64_t dims[5] = {(uint64_t)v.c, (uint64_t)v.w, (uint64_t)v.h, (uint64_t)v.d, (uint64_t)v.n};
+    uint64_t str[5] = {1, (uint64_t)v.ctot, (uint64_t)v.w * v.ctot, (uint64_t)v.h * v.w * v.ctot,
+                       (uint64_t)v.d * v.h * v.w * v.ctot};
+    uint32_t box[5] = {64, (uint32_t)kHaloW, (uint32_t)kHaloH, 1, 1};
+    int rc = make_tmap_bf16(&tmX, v.ptr + v.coff, 5, dims, str, box);
+    if (rc) return rc;
+  }
+  {
+    const ActView& v = p.mop;
+    uint64_t dims[5] = {(uint64_t)v.c, (uint64_t)v.w, (uint64_t)v.h, (uint64_t)v.d, (uint64_t)v.n};
+    uint64_t str[5] = {1, (uint64_t)v.ctot, (uint64_t)v.w * v.ctot, (uint64_t)v.h * v.w * v.ctot,
+                       (uint64_t)v.d * v.h * v.w * v.ctot};
+    uint32_t box[5] = {64, 8, 16, 1, 1};
+    int rc = make_tmap_bf16(&tmDY, v.ptr + v.coff, 5, dims, str, box);
+    if (rc) return rc;
+  }
+  const int smem = a.stages * stage_bytes + 2048;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(tc_wgrad_halo_kernel,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
+    if (e != cudaSuccess) return (int)e;
+    attr_set = true;
+  }
+  const long grid = base_ctas * a.splits;
+  tc_wgrad_halo_kernel<<<(unsigned)grid, 256, smem, stream>>>(tmX, tmDY, a);
+  B200_LAUNCH_CHECK();
+  return B200_OK;
+}
+
 bool tc_wgrad_supported(const TcWgradProblem& p) {
   if (p.mop.c < 16 || p.nop.c < 16 || p.mop.c % 8 || p.nop.c % 8) return false;
   if (p.mop.ctot % 8 || p.mop.coff % 8 || p.nop.ctot % 8 || p.nop.coff % 8) return false;
@@ -505,6 +959,7 @@ bool tc_wgrad_supported(const TcWgradProblem& p) {
 
 int tc_wgrad(const TcWgradProblem& p, cudaStream_t stream) {
   if (!tc_wgrad_supported(p)) return B200_ERR_UNSUPPORTED;
+  if (wgrad_halo_eligible(p)) return tc_wgrad_halo(p, stream);
   WgradArgs a{};
   a.pn = p.pn; a.pd = p.pd; a.ph = p.ph; a.pw = p.pw;
   const TileGeom g = pick_tile(p.pn, p.pd, p.ph, p.pw, p.tap_mode == TC_TAP_K2S2 || p.pd == 1);

@@ -182,10 +182,30 @@ def group_perf():
         flops = 2.0 * n * d * h * w * cin * cout * (27 if is3d else 9)
         out = CL.empty(n, d, h, w, cout, dev)
         dx = CL.empty(n, d, h, w, cin, dev)
+        from mdeical_image_segmentation_b200 import _lib
+        def _nohalo(f):
+            def g():
+                _lib.lib().b200_set_tuning(0, 0)
+                try:
+                    return f()
+                finally:
+                    _lib.lib().b200_set_tuning(0, 1)
+            return g
+        def _nohalo_w(f):
+            def g():
+                _lib.lib().b200_set_tuning(1, 0)
+                try:
+                    return f()
+                finally:
+                    _lib.lib().b200_set_tuning(1, 1)
+            return g
         for label, fn in [
             ("fwd", lambda: ops.conv_fwd(x, fwd, k, None, True, out=out, impl=1)),
+            ("fwd-nohalo", _nohalo(lambda: ops.conv_fwd(x, fwd, k, None, True, out=out, impl=1))),
             ("dgrad", lambda: ops.conv_bwd_data(dy, bwd, k, out=dx, impl=1)),
+            ("dgrad-nohalo", _nohalo(lambda: ops.conv_bwd_data(dy, bwd, k, out=dx, impl=1))),
             ("wgrad", lambda: ops.conv_bwd_weight(x, dy, k, wt.shape, impl=1)),
+            ("wgrad-nohalo", _nohalo_w(lambda: ops.conv_bwd_weight(x, dy, k, wt.shape, impl=1))),
         ]:
             try:
                 for _ in range(2):
