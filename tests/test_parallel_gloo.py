@@ -1,0 +1,65 @@
+"""Host-side logic of the data-parallel path on CPU: two gloo ranks feed different gradients through
+GradReducer in backward order; every rank must end with the cross-rank mean, bucket by bucket."""
+import os
+import socket
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+from torch import nn
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from mdeical_image_segmentation_b200.parallel import DataParallelUNet, GradReducer, allreduce_mean_
+    torch.manual_seed(100 + rank)                      # different init per rank: broadcast must fix it
+    net = nn.Sequential(nn.Conv2d(3, 8, 3), nn.Conv2d(8, 8, 3), nn.Conv2d(8, 2, 1))
+    net.final_conv = net[2]
+    dp = DataParallelUNet(net, bucket_mb=0.001)        # ~260 floats per bucket -> several buckets
+    ref0 = [p.detach().clone() for p in net.parameters()]
+    red: GradReducer = dp.reducer
+    params = list(net.parameters())
+    g = torch.Generator().manual_seed(7 + rank)
+    grads = {p: torch.randn(p.shape, generator=g) for p in params}
+    out = {}
+    for p in reversed(params):                         # backward order: head first
+        out[p] = red.on_grad(p, grads[p])
+    slots = red.finish()
+    res = [slots[p].clone() for p in params]
+    loss = allreduce_mean_(torch.tensor([float(rank)]))
+    q.put((rank, [t.numpy() for t in ref0], [g_.numpy() for g_ in grads.values()],
+           [t.numpy() for t in res], red.launched_buckets, loss.item()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_bucketed_allreduce_two_ranks():
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = sorted([q.get(timeout=120) for _ in range(world)], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    (_, w0, g0, r0, nb0, l0), (_, w1, g1, r1, nb1, l1) = got
+    for a, b in zip(w0, w1):                           # parameters broadcast from rank 0
+        assert (a == b).all()
+    assert nb0 == nb1 and nb0 >= 2                     # more than one bucket was exercised
+    for ga, gb, ra, rb in zip(g0, g1, r0, r1):
+        mean = (ga + gb) / 2
+        assert abs(ra - mean).max() < 1e-6 and abs(rb - mean).max() < 1e-6
+    assert l0 == l1 == 0.5
