@@ -143,7 +143,7 @@ __global__ void __launch_bounds__(256, 1)
   const uint32_t tmem_base = *tmem_slot;
   const int num_kb = p.ntaps * p.kchunks;
 
-  if (warp == 0 && lane == 0) {
+  if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
     int stage = 0;
     uint32_t phase = 0;
@@ -154,20 +154,23 @@ __global__ void __launch_bounds__(256, 1)
         const int kwi = tap % p.kw, khi = (tap / p.kw) % p.kh, kdi = tap / (p.kw * p.kh);
         for (int kc = 0; kc < p.kchunks; ++kc) {
           mbar_wait(&empty[stage], phase ^ 1);
-          uint8_t* sA = tiles + (size_t)stage * stage_bytes;
-          uint8_t* sB = sA + kABytes;
-          mbar_arrive_expect_tx(&full[stage], (uint32_t)stage_bytes);
-          if (p.tap_mode == TC_TAP_SHIFT)
-            tma_load_5d(sA, &tmA, &full[stage], kc * 64, tc.w0 + kwi - p.pad_w,
-                        tc.h0 + khi - p.pad_h, tc.d0 + kdi - p.pad_d, tc.n);
-          else
-            tma_load_5d(sA, &tmA, &full[stage], kc * 64, kwi, tc.w0, khi, tc.n * p.ph + tc.h0);
-          tma_load_3d(sB, &tmB, &full[stage], kc * 64, nt * p.BN, tap);
+          if (elect_one()) {
+            uint8_t* sA = tiles + (size_t)stage * stage_bytes;
+            uint8_t* sB = sA + kABytes;
+            mbar_arrive_expect_tx(&full[stage], (uint32_t)stage_bytes);
+            if (p.tap_mode == TC_TAP_SHIFT)
+              tma_load_5d(sA, &tmA, &full[stage], kc * 64, tc.w0 + kwi - p.pad_w,
+                          tc.h0 + khi - p.pad_h, tc.d0 + kdi - p.pad_d, tc.n);
+            else
+              tma_load_5d(sA, &tmA, &full[stage], kc * 64, kwi, tc.w0, khi, tc.n * p.ph + tc.h0);
+            tma_load_3d(sB, &tmB, &full[stage], kc * 64, nt * p.BN, tap);
+          }
+          __syncwarp();
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
       }
     }
-  } else if (warp == 1 && lane == 0) {
+  } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
     const uint32_t idesc = make_idesc_bf16(128, p.BN, 0, 0);
     int stage = 0;
@@ -183,16 +186,18 @@ __global__ void __launch_bounds__(256, 1)
         mbar_wait(&full[stage], phase);
         tc_fence_after();
         const uint32_t aaddr = smem_u32(tiles + (size_t)stage * stage_bytes);
-        const uint32_t baddr = aaddr + kABytes;
-        for (int k = 0; k < nk; ++k) {
-          const uint64_t da = make_smem_desc_sw128(aaddr + k * 32, 16, 1024);
-          const uint64_t db = make_smem_desc_sw128(baddr + k * 32, 16, 1024);
-          umma_bf16(tmem_d, da, db, idesc, (kb | k) != 0);
+        if (elect_one()) {
+          const uint64_t da = make_smem_desc_sw128(aaddr, 16, 1024);
+          const uint64_t db = make_smem_desc_sw128(aaddr + kABytes, 16, 1024);
+#pragma unroll 4
+          for (int k = 0; k < nk; ++k)
+            umma_bf16(tmem_d, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+          umma_commit(&empty[stage]);
+          if (kb == num_kb - 1) umma_commit(&tfull[acc]);
         }
-        umma_commit(&empty[stage]);
+        __syncwarp();
         if (++stage == p.stages) { stage = 0; phase ^= 1; }
       }
-      umma_commit(&tfull[acc]);
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
@@ -292,6 +297,7 @@ struct HaloArgs {
   int kd;                // 1 or 3 depth taps (kh = kw = 3)
   int kchunks, kdim, BN;
   int a_stage_bytes, a_stages, b_slots;
+  int G;                 // taps per weight slot (3 = one kw row per TMA box, or 1)
   bf16* out;
   int out_ctot, out_coff;
   const float* bias;
@@ -315,7 +321,8 @@ __global__ void __launch_bounds__(256, 1)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
   uint8_t* sA = smem + 1024;
   uint8_t* sB = sA + (size_t)p.a_stages * p.a_stage_bytes;
-  const int b_bytes = p.BN * 128;
+  const int tap_bytes = p.BN * 128;
+  const int b_bytes = tap_bytes * p.G;
   const int ntaps = p.kd * 9;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -335,7 +342,7 @@ __global__ void __launch_bounds__(256, 1)
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 0 && lane == 0) {
+  if (warp == 0) {
     // ---------------------------------------------------------------- A (halo) producer
     int stage = 0;
     uint32_t phase = 0;
@@ -345,27 +352,33 @@ __global__ void __launch_bounds__(256, 1)
       const TileCoord tc = decode_tile(mt, p.pd, p.tiles_h, p.tiles_w, 0, 4, 3);
       for (int kc = 0; kc < p.kchunks; ++kc) {
         mbar_wait(&aempty[stage], phase ^ 1);
-        mbar_arrive_expect_tx(&afull[stage], halo_bytes);
-        tma_load_5d(sA + (size_t)stage * p.a_stage_bytes, &tmA, &afull[stage], kc * 64, tc.w0 - 1,
-                    tc.h0 - 1, tc.d0 - (p.kd >> 1), tc.n);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&afull[stage], halo_bytes);
+          tma_load_5d(sA + (size_t)stage * p.a_stage_bytes, &tmA, &afull[stage], kc * 64, tc.w0 - 1,
+                      tc.h0 - 1, tc.d0 - (p.kd >> 1), tc.n);
+        }
+        __syncwarp();
         if (++stage == p.a_stages) { stage = 0; phase ^= 1; }
       }
     }
-  } else if (warp == 3 && lane == 0) {
+  } else if (warp == 3) {
     // ---------------------------------------------------------------- B (weights) producer
     int slot = 0;
     uint32_t phase = 0;
     for (int work = blockIdx.x; work < p.total; work += gridDim.x) {
       const int nt = work % p.n_tiles;
       for (int kc = 0; kc < p.kchunks; ++kc)
-        for (int tap = 0; tap < ntaps; ++tap) {
+        for (int tap = 0; tap < ntaps; tap += p.G) {
           mbar_wait(&bempty[slot], phase ^ 1);
-          mbar_arrive_expect_tx(&bfull[slot], (uint32_t)b_bytes);
-          tma_load_3d(sB + (size_t)slot * b_bytes, &tmB, &bfull[slot], kc * 64, nt * p.BN, tap);
+          if (elect_one()) {
+            mbar_arrive_expect_tx(&bfull[slot], (uint32_t)b_bytes);
+            tma_load_3d(sB + (size_t)slot * b_bytes, &tmB, &bfull[slot], kc * 64, nt * p.BN, tap);
+          }
+          __syncwarp();
           if (++slot == p.b_slots) { slot = 0; phase ^= 1; }
         }
     }
-  } else if (warp == 1 && lane == 0) {
+  } else if (warp == 1) {
     // ---------------------------------------------------------------- MMA issuer
     const uint32_t idesc = make_idesc_bf16(128, p.BN, 0, 0);
     int stage = 0, slot = 0;
@@ -379,27 +392,41 @@ __global__ void __launch_bounds__(256, 1)
         nk = nk > 4 ? 4 : nk;
         mbar_wait(&afull[stage], aphase);
         tc_fence_after();
-        const uint32_t abase = smem_u32(sA + (size_t)stage * p.a_stage_bytes);
+        // descriptors differ only in their 14-bit start-address field: build once, then add
+        const uint64_t da0 = make_smem_desc_sw128(smem_u32(sA + (size_t)stage * p.a_stage_bytes), 16,
+                                                  kHaloW * 128);
         int tap = 0;
         for (int kdi = 0; kdi < p.kd; ++kdi)
-          for (int khi = 0; khi < 3; ++khi)
+          for (int khi = 0; khi < 3; ++khi) {
+            const uint64_t da_row = da0 + (uint64_t)(((kdi * kHaloH + khi) * kHaloW * 128) >> 4);
             for (int kwi = 0; kwi < 3; ++kwi, ++tap) {
-              mbar_wait(&bfull[slot], bphase);
-              tc_fence_after();
-              const uint32_t aaddr = abase + (uint32_t)(((kdi * kHaloH + khi) * kHaloW + kwi) * 128);
-              const uint32_t baddr = smem_u32(sB + (size_t)slot * b_bytes);
-              for (int k = 0; k < nk; ++k) {
-                const uint64_t da = make_smem_desc_sw128(aaddr + k * 32, 16, kHaloW * 128);
-                const uint64_t db = make_smem_desc_sw128(baddr + k * 32, 16, 1024);
-                umma_bf16(tmem_d, da, db, idesc, (kc | tap | k) != 0);
+              const int sub = p.G == 3 ? kwi : 0;
+              if (sub == 0) {
+                mbar_wait(&bfull[slot], bphase);
+                tc_fence_after();
               }
-              umma_commit(&bempty[slot]);
-              if (++slot == p.b_slots) { slot = 0; bphase ^= 1; }
+              const bool last_of_slot = sub == p.G - 1;
+              const bool last_tap = tap == ntaps - 1;
+              if (elect_one()) {
+                const uint64_t da = da_row + (uint64_t)(kwi * 8);
+                const uint64_t db = make_smem_desc_sw128(
+                    smem_u32(sB + (size_t)slot * b_bytes + (size_t)sub * tap_bytes), 16, 1024);
+#pragma unroll 4
+                for (int k = 0; k < nk; ++k)
+                  umma_bf16(tmem_d, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc,
+                            (kc | tap | k) != 0);
+                if (last_of_slot) umma_commit(&bempty[slot]);
+                if (last_tap) {
+                  umma_commit(&aempty[stage]);
+                  if (kc == p.kchunks - 1) umma_commit(&tfull[acc]);
+                }
+              }
+              __syncwarp();
+              if (last_of_slot && ++slot == p.b_slots) { slot = 0; bphase ^= 1; }
             }
-        umma_commit(&aempty[stage]);
+          }
         if (++stage == p.a_stages) { stage = 0; aphase ^= 1; }
       }
-      umma_commit(&tfull[acc]);
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
@@ -524,12 +551,15 @@ static int tc_gemm_halo(const TcGemmProblem& p, cudaStream_t stream) {
   a.kdim = p.kdim; a.kchunks = (p.kdim + 63) / 64;
   a.a_stage_bytes = ((kHaloPlaneBytes * p.kd) + 1023) / 1024 * 1024;
   a.a_stages = 2;
-  const int b_bytes = a.BN * 128;
   int rem = kSmemBudget - 2048 - a.a_stages * a.a_stage_bytes;
-  if (p.kd == 1 && rem - 4 * b_bytes >= 2 * a.a_stage_bytes) {  // 2D: cheap stages, go deeper
+  if (p.kd == 1 && rem - 4 * a.BN * 128 >= 2 * a.a_stage_bytes + 64 * 1024) {  // 2D: cheap stages
     a.a_stages = 4;
     rem = kSmemBudget - 2048 - a.a_stages * a.a_stage_bytes;
   }
+  // narrow N: short MMAs make the issuing thread the limiter, so fetch a whole kw row of taps per
+  // weight slot (one 3-tap TMA box, one barrier round-trip per 12 MMAs instead of per 4)
+  a.G = (2 * 3 * a.BN * 128 <= rem) ? 3 : 1;
+  const int b_bytes = a.G * a.BN * 128;
   a.b_slots = rem / b_bytes;
   if (a.b_slots > 12) a.b_slots = 12;
   if (a.b_slots < 2) return B200_ERR_UNSUPPORTED;
@@ -551,7 +581,7 @@ static int tc_gemm_halo(const TcGemmProblem& p, cudaStream_t stream) {
     const int ntaps = p.kd * 9;
     uint64_t dims[3] = {(uint64_t)p.kdim, (uint64_t)p.ncols, (uint64_t)ntaps};
     uint64_t str[3] = {1, (uint64_t)p.kdim, (uint64_t)p.kdim * p.ncols};
-    uint32_t box[3] = {64, (uint32_t)a.BN, 1};
+    uint32_t box[3] = {64, (uint32_t)a.BN, (uint32_t)a.G};
     int rc = make_tmap_bf16(&tmB, p.wp, 3, dims, str, box);
     if (rc) return rc;
   }
@@ -675,12 +705,13 @@ __global__ void __launch_bounds__(256, 1)
   if (mt_end > p.m_tiles) mt_end = p.m_tiles;
   const int tap0 = tg * p.T;
 
-  if (warp == 0 && lane == 0) {
+  if (warp == 0) {
     int stage = 0;
     uint32_t phase = 0;
     for (int mt = mt_begin; mt < mt_end; ++mt) {
       const TileCoord tc = decode_tile(mt, p.tiles_d, p.tiles_h, p.tiles_w, p.tdl, p.thl, p.twl);
       mbar_wait(&empty[stage], phase ^ 1);
+      if (elect_one()) {
       uint8_t* sM = tiles + (size_t)stage * stage_bytes;
       uint8_t* sN = sM + mboxes * kABytes;
       mbar_arrive_expect_tx(&full[stage], (uint32_t)stage_bytes);
@@ -701,9 +732,11 @@ __global__ void __launch_bounds__(256, 1)
           tma_load_5d(sN + t * kABytes, &tmN, &full[stage], nb * 64, kwi, tc.w0, khi,
                       tc.n * p.ph + tc.h0);
       }
+      }
+      __syncwarp();
       if (++stage == p.stages) { stage = 0; phase ^= 1; }
     }
-  } else if (warp == 1 && lane == 0) {
+  } else if (warp == 1) {
     const uint32_t idesc = make_idesc_bf16(p.M, 64, 1, 1);
     int stage = 0;
     uint32_t phase = 0;
@@ -713,18 +746,23 @@ __global__ void __launch_bounds__(256, 1)
       tc_fence_after();
       const uint32_t maddr = smem_u32(tiles + (size_t)stage * stage_bytes);
       const uint32_t naddr = maddr + mboxes * kABytes;
-      for (int t = 0; t < p.T; ++t) {
-        for (int k = 0; k < 8; ++k) {  // 16 positions (= 2 KB of rows) per MMA
-          const uint64_t da = make_smem_desc_sw128(maddr + k * 2048, kABytes, 1024);
-          const uint64_t db = make_smem_desc_sw128(naddr + t * kABytes + k * 2048, kABytes, 1024);
-          umma_bf16(tmem_base + t * 64, da, db, idesc, !(first && k == 0));
+      if (elect_one()) {
+        const uint64_t da0 = make_smem_desc_sw128(maddr, kABytes, 1024);
+        for (int t = 0; t < p.T; ++t) {
+          const uint64_t db0 = make_smem_desc_sw128(naddr + t * kABytes, kABytes, 1024);
+#pragma unroll
+          for (int k = 0; k < 8; ++k)  // 16 positions (= 2 KB of rows) per MMA
+            umma_bf16(tmem_base + t * 64, da0 + (uint64_t)(k * 128), db0 + (uint64_t)(k * 128), idesc,
+                      !(first && k == 0));
         }
+        umma_commit(&empty[stage]);
+        if (mt == mt_end - 1) umma_commit(&tfull[0]);
       }
+      __syncwarp();
       first = false;
-      umma_commit(&empty[stage]);
       if (++stage == p.stages) { stage = 0; phase ^= 1; }
     }
-    umma_commit(&tfull[0]);
+    if (mt_end <= mt_begin && elect_one()) umma_commit(&tfull[0]);
   } else if (warp >= 4) {
     const int q = warp - 4;
     int m_local;
@@ -818,20 +856,23 @@ __global__ void __launch_bounds__(256, 1)
   int mt_end = mt_begin + p.tiles_per_split;
   if (mt_end > p.m_tiles) mt_end = p.m_tiles;
 
-  if (warp == 0 && lane == 0) {
+  if (warp == 0) {
     int stage = 0;
     uint32_t phase = 0;
     for (int mt = mt_begin; mt < mt_end; ++mt) {
       const TileCoord tc = decode_tile(mt, p.pd, p.tiles_h, p.tiles_w, 0, 4, 3);
       mbar_wait(&empty[stage], phase ^ 1);
-      uint8_t* sX = tiles + (size_t)stage * stage_bytes;
-      uint8_t* sY = sX + x_bytes;
-      mbar_arrive_expect_tx(&full[stage], (uint32_t)(kHaloPlaneBytes + kABytes));
-      tma_load_5d(sX, &tmX, &full[stage], cib * 64, tc.w0 - 1, tc.h0 - 1, tc.d0 + kdi - (p.kd >> 1), tc.n);
-      tma_load_5d(sY, &tmDY, &full[stage], cob * 64, tc.w0, tc.h0, tc.d0, tc.n);
+      if (elect_one()) {
+        uint8_t* sX = tiles + (size_t)stage * stage_bytes;
+        uint8_t* sY = sX + x_bytes;
+        mbar_arrive_expect_tx(&full[stage], (uint32_t)(kHaloPlaneBytes + kABytes));
+        tma_load_5d(sX, &tmX, &full[stage], cib * 64, tc.w0 - 1, tc.h0 - 1, tc.d0 + kdi - (p.kd >> 1), tc.n);
+        tma_load_5d(sY, &tmDY, &full[stage], cob * 64, tc.w0, tc.h0, tc.d0, tc.n);
+      }
+      __syncwarp();
       if (++stage == p.stages) { stage = 0; phase ^= 1; }
     }
-  } else if (warp == 1 && lane == 0) {
+  } else if (warp == 1) {
     const uint32_t idesc = make_idesc_bf16(128, p.N, 1, 1);
     int stage = 0;
     uint32_t phase = 0;
@@ -841,21 +882,27 @@ __global__ void __launch_bounds__(256, 1)
       tc_fence_after();
       const uint32_t xaddr = smem_u32(tiles + (size_t)stage * stage_bytes);
       const uint32_t yaddr = xaddr + x_bytes;
+      if (elect_one()) {
+      const uint64_t db0 = make_smem_desc_sw128(yaddr, kABytes, 1024);
+#pragma unroll
       for (int g = 0; g < 5; ++g) {
         const int ta = g < 4 ? 2 * g : 7, tb = ta + 1;
         const int ra = (ta / 3) * kHaloW + (ta % 3), rb = (tb / 3) * kHaloW + (tb % 3);
-        for (int j = 0; j < 8; ++j) {  // 16 positions = 2 W-rows of the tile per MMA
-          const uint64_t da = make_smem_desc_sw128(xaddr + (uint32_t)((ra + j * 2 * kHaloW) * 128),
-                                                   (uint32_t)((rb - ra) * 128), kHaloW * 128);
-          const uint64_t db = make_smem_desc_sw128(yaddr + j * 2048, kABytes, 1024);
-          umma_bf16(tmem_base + g * 64, da, db, idesc, !(first && j == 0));
-        }
+        const uint64_t da0 = make_smem_desc_sw128(xaddr + (uint32_t)(ra * 128), (uint32_t)((rb - ra) * 128),
+                                                  kHaloW * 128);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)  // 16 positions = 2 W-rows of the tile per MMA
+          umma_bf16(tmem_base + g * 64, da0 + (uint64_t)(j * ((2 * kHaloW * 128) >> 4)),
+                    db0 + (uint64_t)(j * (2048 >> 4)), idesc, !(first && j == 0));
       }
-      first = false;
       umma_commit(&empty[stage]);
+      if (mt == mt_end - 1) umma_commit(&tfull[0]);
+      }
+      __syncwarp();
+      first = false;
       if (++stage == p.stages) { stage = 0; phase ^= 1; }
     }
-    umma_commit(&tfull[0]);
+    if (mt_end <= mt_begin && elect_one()) umma_commit(&tfull[0]);
   } else if (warp >= 4) {
     const int q = warp - 4;
     const int m = q * 32 + lane;           // 0..127: (tap half, ci)
