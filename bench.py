@@ -178,8 +178,10 @@ class KernelProfiler:
                 key = "tc_gemm_kernel" if impl == 1 else "direct_gemm_kernel"
             elif name in ("b200_conv_bwd_weight", "b200_convt2x2_bwd_weight"):
                 key = "tc_wgrad_kernel" if impl == 1 else "direct_wgrad_kernel"
-            elif name.startswith("b200_deconv3s2"):
-                key = "deconv_direct"
+            elif name in ("b200_deconv3s2_fwd", "b200_deconv3s2_bwd_data"):
+                key = "tc_gemm_kernel(deconv)" if impl == 1 else "direct_gemm_kernel(deconv)"
+            elif name == "b200_deconv3s2_bwd_weight":
+                key = "tc_wgrad_kernel(deconv)" if impl == 1 else "direct_wgrad_kernel(deconv)"
             else:
                 key = name.replace("b200_", "")
             f = fam.setdefault(key, dict(ms=0.0, flops=0.0, launches=0))

@@ -86,24 +86,28 @@ int b200_convt2x2_bwd_weight(const b200_convt_desc* desc, const void* x, const v
                              b200_stream_t stream);
 
 /* ---- ConvTranspose(kernel 3, stride 2, padding 1, no bias) -------------------------------------
- * replaces the conv_transposed of TransposeConvUpsampling  model/unet3d/buildingblocks.py:699-717;
- * the F.interpolate(size=skip) that follows it (:703) is b200_upsample_nearest_*.
- * x: (n,d,h,w,c_in) -> y: (n,od,oh,ow,c_out) with o* = 2*in - 1; d = od = 1 for the 2D variant. */
+ * replaces the conv_transposed of TransposeConvUpsampling  model/unet3d/buildingblocks.py:699-717.
+ * The (2d-1, 2h-1, 2w-1) result is kept as PARITY PLANES: a dense bf16 buffer
+ * (classes*n, d, h, w, c_out), classes = 8 (kd = 3) or 4 (kd = 1, 2D), where plane (pd,ph,pw) holds
+ * ct[2m + p] at position m.  Each plane is a small tap-shift implicit GEMM on the tensor cores
+ * (1/2/4/8 taps); backward-data and backward-weight are 27-tap (9-tap) GEMMs that read the planes.
+ * The F.interpolate(size=skip) that follows (:703) is b200_deconv_planes_resize_*. */
 typedef struct b200_deconv_desc {
-  int32_t n, d, h, w;
-  int32_t od, oh, ow;
+  int32_t n, d, h, w;          /* input positions (d = 1 for 2D)      */
   int32_t c_in, c_out;
-  int32_t in_ctot, in_coff;
-  int32_t out_ctot, out_coff;
+  int32_t kd;                  /* 3 (ConvTranspose3d) or 1 (2D)       */
+  int32_t in_ctot, in_coff;    /* layout of x / dx                    */
+  int32_t impl;
 } b200_deconv_desc;
-/* w fp32 (c_in, c_out, kd, 3, 3) -> wp bf16 [tap][c_in][c_out] */
-int b200_deconv3s2_repack_weight(const b200_deconv_desc* desc, const float* w, void* wp,
-                                 b200_stream_t stream);
-int b200_deconv3s2_fwd(const b200_deconv_desc* desc, const void* x, const void* wp, void* y,
+/* w fp32 (c_in, c_out, kd, 3, 3) -> wp_fwd bf16 [tap][c_out][c_in], wp_bwd bf16 [tap][c_in][c_out] */
+int b200_deconv3s2_repack_weight(const b200_deconv_desc* desc, const float* w, void* wp_fwd,
+                                 void* wp_bwd, b200_stream_t stream);
+int b200_deconv3s2_fwd(const b200_deconv_desc* desc, const void* x, const void* wp_fwd, void* yp,
                        b200_stream_t stream);
-int b200_deconv3s2_bwd_data(const b200_deconv_desc* desc, const void* dy, const void* wp, void* dx,
-                            b200_stream_t stream);
-int b200_deconv3s2_bwd_weight(const b200_deconv_desc* desc, const void* x, const void* dy,
+int b200_deconv3s2_bwd_data(const b200_deconv_desc* desc, const void* dyp, const void* wp_bwd,
+                            void* dx, b200_stream_t stream);
+/* dw fp32 (c_in, c_out, kd, 3, 3) accumulated into */
+int b200_deconv3s2_bwd_weight(const b200_deconv_desc* desc, const void* x, const void* dyp,
                               float* dw, b200_stream_t stream);
 
 /* ---- memory-bound tensor ops -------------------------------------------------------------------
@@ -129,6 +133,14 @@ int b200_upsample_nearest_fwd(int32_t n, int32_t id, int32_t ih, int32_t iw, int
 int b200_upsample_nearest_bwd(int32_t n, int32_t id, int32_t ih, int32_t iw, int32_t od,
                               int32_t oh, int32_t ow, int32_t c, b200_view dy, b200_view dx,
                               b200_stream_t stream);
+/* parity planes (see b200_deconv3s2_*) <-> nearest-resized (n, od, oh, ow, c) tensor; the backward
+ * writes every plane element (zeros in the unused m = size-1 rows of odd planes) */
+int b200_deconv_planes_resize_fwd(int32_t n, int32_t d, int32_t h, int32_t w, int32_t c, int32_t kd,
+                                  int32_t od, int32_t oh, int32_t ow, b200_view yp, b200_view y,
+                                  b200_stream_t stream);
+int b200_deconv_planes_resize_bwd(int32_t n, int32_t d, int32_t h, int32_t w, int32_t c, int32_t kd,
+                                  int32_t od, int32_t oh, int32_t ow, b200_view dy, b200_view dyp,
+                                  b200_stream_t stream);
 /* torch.cat halves — layers.py:188, buildingblocks.py:547: copy c channels of npos positions */
 int b200_copy_channels(int64_t npos, int32_t c, b200_view src, b200_view dst, b200_stream_t stream);
 /* dz = dy * (a > 0) (ReLU backward), optionally db[c] += sum_pos dz (conv bias gradient) */

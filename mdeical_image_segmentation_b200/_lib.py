@@ -30,8 +30,7 @@ class ConvTDesc(C.Structure):
 
 class DeconvDesc(C.Structure):
     _fields_ = [(k, C.c_int32) for k in (
-        "n", "d", "h", "w", "od", "oh", "ow", "c_in", "c_out",
-        "in_ctot", "in_coff", "out_ctot", "out_coff")]
+        "n", "d", "h", "w", "c_in", "c_out", "kd", "in_ctot", "in_coff", "impl")]
 
 
 class View(C.Structure):
@@ -51,7 +50,9 @@ SIGNATURES = {
     "b200_convt2x2_fwd": [_PT, _P, _P, _P, _P, _P],
     "b200_convt2x2_bwd_data": [_PT, _P, _P, _P, _P, _P],
     "b200_convt2x2_bwd_weight": [_PT, _P, _P, _P, _P],
-    "b200_deconv3s2_repack_weight": [_PD, _P, _P, _P],
+    "b200_deconv3s2_repack_weight": [_PD, _P, _P, _P, _P],
+    "b200_deconv_planes_resize_fwd": [_I, _I, _I, _I, _I, _I, _I, _I, _I, View, View, _P],
+    "b200_deconv_planes_resize_bwd": [_I, _I, _I, _I, _I, _I, _I, _I, _I, View, View, _P],
     "b200_deconv3s2_fwd": [_PD, _P, _P, _P, _P],
     "b200_deconv3s2_bwd_data": [_PD, _P, _P, _P, _P],
     "b200_deconv3s2_bwd_weight": [_PD, _P, _P, _P, _P],
@@ -133,7 +134,7 @@ def check(rc: int, what: str = "") -> None:
 
 
 # kernels launched per successful C-ABI call (for bench.py's `gpu_launches` accounting)
-LAUNCHES_PER_CALL = {"b200_gn_stats": 2, "b200_gn_bwd": 3}
+LAUNCHES_PER_CALL = {"b200_gn_stats": 2, "b200_gn_bwd": 3, "b200_deconv3s2_fwd": 8}
 launch_count = 0
 # optional profiler hook: fn(name, args) -> context manager, installed by bench.py for per-kernel timing
 profile_hook = None

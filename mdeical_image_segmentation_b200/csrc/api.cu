@@ -8,16 +8,6 @@ extern int g_halo_mode;
 extern int g_wgrad_halo_mode;
 int direct_gemm_conv(const TcGemmProblem& p, cudaStream_t stream);
 int direct_wgrad(const TcWgradProblem& p, cudaStream_t stream);
-struct DeconvArgs {
-  const bf16* x; int n, d, h, w, c_in, in_ctot, in_coff;
-  bf16* y; int od, oh, ow, c_out, out_ctot, out_coff;
-  const bf16* wp;
-  int kd;
-};
-int deconv_fwd(const DeconvArgs& a, cudaStream_t s);
-int deconv_bwd_data(const DeconvArgs& a, cudaStream_t s);
-int deconv_bwd_weight(const DeconvArgs& a, float* dw, cudaStream_t s);
-
 static thread_local int g_last_impl = 0;
 
 // w (c_out, c_in, taps) fp32 -> fwd [tap][c_out][c_in], bwd [ntaps-1-tap][c_in][c_out]
@@ -44,15 +34,54 @@ __global__ void convt_repack_kernel(int c_in, int c_out, const float* w, bf16* f
     if (bwd) bwd[((long)ij * c_in + ci) * c_out + co] = v;
   }
 }
-// w (c_in, c_out, taps) fp32 -> [tap][c_in][c_out]
-__global__ void deconv_repack_kernel(int c_in, int c_out, int ntaps, const float* w, bf16* wp) {
+// w (c_in, c_out, taps) fp32 -> fwd [tap][c_out][c_in], bwd [tap][c_in][c_out]
+__global__ void deconv_repack_kernel(int c_in, int c_out, int ntaps, const float* w, bf16* fwd, bf16* bwd) {
   const long total = (long)c_in * c_out * ntaps;
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
     const int tap = (int)(i % ntaps);
     const int co = (int)((i / ntaps) % c_out);
     const int ci = (int)(i / ((long)ntaps * c_out));
-    wp[((long)tap * c_in + ci) * c_out + co] = __float2bfloat16(w[i]);
+    const bf16 v = __float2bfloat16(w[i]);
+    if (fwd) fwd[((long)tap * c_out + co) * c_in + ci] = v;
+    if (bwd) bwd[((long)tap * c_in + ci) * c_out + co] = v;
   }
+}
+
+// Tap lists of the stride-2 / kernel-3 / padding-1 transposed convolution, per axis:
+//   output z = 2m + p:  p = 0 <- (k = 1, x[m]);   p = 1 <- (k = 2, x[m]) and (k = 0, x[m + 1])
+//   input  i:           k = 1 -> plane p = 0 at m = i;  k = 2 -> p = 1 at m = i;  k = 0 -> p = 1 at m = i - 1
+static void deconv_fwd_table(int kd, int cls, TapTable* t) {
+  const int p[3] = {(cls >> 2) & 1, (cls >> 1) & 1, cls & 1};
+  int kopt[3][2], sopt[3][2], nopt[3];
+  for (int a = 0; a < 3; ++a) {
+    if (a == 0 && kd == 1) { nopt[a] = 1; kopt[a][0] = 0; sopt[a][0] = 0; continue; }
+    if (p[a] == 0) { nopt[a] = 1; kopt[a][0] = 1; sopt[a][0] = 0; }
+    else { nopt[a] = 2; kopt[a][0] = 2; sopt[a][0] = 0; kopt[a][1] = 0; sopt[a][1] = 1; }
+  }
+  t->ntaps = 0;
+  for (int i = 0; i < nopt[0]; ++i)
+    for (int j = 0; j < nopt[1]; ++j)
+      for (int k = 0; k < nopt[2]; ++k) {
+        const int q = t->ntaps++;
+        t->dd[q] = (signed char)sopt[0][i]; t->dh[q] = (signed char)sopt[1][j]; t->dw[q] = (signed char)sopt[2][k];
+        t->dn[q] = 0;
+        t->widx[q] = (signed char)(kd == 1 ? kopt[1][j] * 3 + kopt[2][k]
+                                           : (kopt[0][i] * 3 + kopt[1][j]) * 3 + kopt[2][k]);
+      }
+}
+static void deconv_bwd_table(int kd, int n, TapTable* t) {
+  static const int pk[3] = {1, 0, 1};    // parity plane read by kernel index k
+  static const int sk[3] = {-1, 0, 0};   // position shift for kernel index k
+  t->ntaps = 0;
+  for (int a = 0; a < (kd == 1 ? 1 : 3); ++a)
+    for (int b = 0; b < 3; ++b)
+      for (int c = 0; c < 3; ++c) {
+        const int q = t->ntaps++;
+        const int pd = kd == 1 ? 0 : pk[a];
+        t->dd[q] = (signed char)(kd == 1 ? 0 : sk[a]); t->dh[q] = (signed char)sk[b]; t->dw[q] = (signed char)sk[c];
+        t->dn[q] = ((pd * 2 + pk[b]) * 2 + pk[c]) * n;
+        t->widx[q] = (signed char)q;
+      }
 }
 
 static int check_conv(const b200_conv_desc* d) {
@@ -243,53 +272,81 @@ int b200_convt2x2_bwd_weight(const b200_convt_desc* d, const void* x, const void
   return run_wgrad(p, d->impl, (cudaStream_t)stream);
 }
 
-// ---- ConvTranspose k3 s2 p1
+// ---- ConvTranspose k3 s2 p1 through parity planes
 static int check_deconv(const b200_deconv_desc* d) {
   if (!d || d->n <= 0 || d->d <= 0 || d->h <= 0 || d->w <= 0 || d->c_in <= 0 || d->c_out <= 0)
     return B200_ERR_BAD_ARG;
-  if (d->oh != 2 * d->h - 1 || d->ow != 2 * d->w - 1) return B200_ERR_BAD_ARG;
-  if (!((d->d == 1 && d->od == 1) || d->od == 2 * d->d - 1)) return B200_ERR_BAD_ARG;
+  if (d->kd != 1 && d->kd != 3) return B200_ERR_BAD_ARG;
+  if (d->kd == 1 && d->d != 1) return B200_ERR_BAD_ARG;
   if (d->in_coff < 0 || d->in_coff + d->c_in > d->in_ctot) return B200_ERR_BAD_ARG;
-  if (d->out_coff < 0 || d->out_coff + d->c_out > d->out_ctot) return B200_ERR_BAD_ARG;
   return B200_OK;
 }
-static DeconvArgs mk_deconv(const b200_deconv_desc* d, const void* x, const void* y, const void* wp) {
-  DeconvArgs a;
-  a.x = (const bf16*)x; a.n = d->n; a.d = d->d; a.h = d->h; a.w = d->w; a.c_in = d->c_in;
-  a.in_ctot = d->in_ctot; a.in_coff = d->in_coff;
-  a.y = (bf16*)const_cast<void*>(y); a.od = d->od; a.oh = d->oh; a.ow = d->ow; a.c_out = d->c_out;
-  a.out_ctot = d->out_ctot; a.out_coff = d->out_coff;
-  a.wp = (const bf16*)wp;
-  a.kd = (d->d == 1 && d->od == 1) ? 1 : 3;
-  return a;
-}
-int b200_deconv3s2_repack_weight(const b200_deconv_desc* d, const float* w, void* wp,
+int b200_deconv3s2_repack_weight(const b200_deconv_desc* d, const float* w, void* wp_fwd, void* wp_bwd,
                                  b200_stream_t stream) {
   int rc = check_deconv(d);
   if (rc) return rc;
-  const int ntaps = ((d->d == 1 && d->od == 1) ? 1 : 3) * 9;
+  const int ntaps = d->kd * 9;
   deconv_repack_kernel<<<grid_for((long)d->c_in * d->c_out * ntaps), 256, 0, (cudaStream_t)stream>>>(
-      d->c_in, d->c_out, ntaps, w, (bf16*)wp);
+      d->c_in, d->c_out, ntaps, w, (bf16*)wp_fwd, (bf16*)wp_bwd);
   B200_LAUNCH_CHECK();
   return B200_OK;
 }
-int b200_deconv3s2_fwd(const b200_deconv_desc* d, const void* x, const void* wp, void* y,
+int b200_deconv3s2_fwd(const b200_deconv_desc* d, const void* x, const void* wp_fwd, void* yp,
                        b200_stream_t stream) {
   int rc = check_deconv(d);
   if (rc) return rc;
-  return deconv_fwd(mk_deconv(d, x, y, wp), (cudaStream_t)stream);
+  const int classes = d->kd == 1 ? 4 : 8;
+  const long plane = (long)d->n * d->d * d->h * d->w * d->c_out;
+  for (int cls = 0; cls < classes; ++cls) {
+    TapTable t;
+    deconv_fwd_table(d->kd, cls, &t);
+    TcGemmProblem p{};
+    p.a = ActView{(const bf16*)x, d->n, d->d, d->h, d->w, d->c_in, d->in_ctot, d->in_coff};
+    p.wp = (const bf16*)wp_fwd;
+    p.ncols = d->c_out; p.kdim = d->c_in;
+    p.kd = d->kd; p.kh = 3; p.kw = 3;
+    p.tap_mode = TC_TAP_SHIFT; p.table = &t; p.out_mode = TC_OUT_CONV;
+    p.pn = d->n; p.pd = d->d; p.ph = d->h; p.pw = d->w;
+    p.out = (bf16*)yp + cls * plane; p.out_ctot = d->c_out; p.out_coff = 0;
+    rc = run_gemm(p, d->impl, (cudaStream_t)stream);
+    if (rc) return rc;
+  }
+  return B200_OK;
 }
-int b200_deconv3s2_bwd_data(const b200_deconv_desc* d, const void* dy, const void* wp, void* dx,
+int b200_deconv3s2_bwd_data(const b200_deconv_desc* d, const void* dyp, const void* wp_bwd, void* dx,
                             b200_stream_t stream) {
   int rc = check_deconv(d);
   if (rc) return rc;
-  return deconv_bwd_data(mk_deconv(d, dx, dy, wp), (cudaStream_t)stream);
+  const int classes = d->kd == 1 ? 4 : 8;
+  TapTable t;
+  deconv_bwd_table(d->kd, d->n, &t);
+  TcGemmProblem p{};
+  p.a = ActView{(const bf16*)dyp, classes * d->n, d->d, d->h, d->w, d->c_out, d->c_out, 0};
+  p.wp = (const bf16*)wp_bwd;
+  p.ncols = d->c_in; p.kdim = d->c_out;
+  p.kd = d->kd; p.kh = 3; p.kw = 3;
+  p.tap_mode = TC_TAP_SHIFT; p.table = &t; p.out_mode = TC_OUT_CONV;
+  p.pn = d->n; p.pd = d->d; p.ph = d->h; p.pw = d->w;
+  p.out = (bf16*)dx; p.out_ctot = d->in_ctot; p.out_coff = d->in_coff;
+  return run_gemm(p, d->impl, (cudaStream_t)stream);
 }
-int b200_deconv3s2_bwd_weight(const b200_deconv_desc* d, const void* x, const void* dy, float* dw,
+int b200_deconv3s2_bwd_weight(const b200_deconv_desc* d, const void* x, const void* dyp, float* dw,
                               b200_stream_t stream) {
   int rc = check_deconv(d);
   if (rc) return rc;
-  return deconv_bwd_weight(mk_deconv(d, x, dy, nullptr), dw, (cudaStream_t)stream);
+  const int classes = d->kd == 1 ? 4 : 8;
+  TapTable t;
+  deconv_bwd_table(d->kd, d->n, &t);
+  TcWgradProblem p{};
+  p.mop = ActView{(const bf16*)x, d->n, d->d, d->h, d->w, d->c_in, d->in_ctot, d->in_coff};
+  p.nop = ActView{(const bf16*)dyp, classes * d->n, d->d, d->h, d->w, d->c_out, d->c_out, 0};
+  p.kd = d->kd; p.kh = 3; p.kw = 3;
+  p.tap_mode = TC_TAP_SHIFT; p.table = &t;
+  p.pn = d->n; p.pd = d->d; p.ph = d->h; p.pw = d->w;
+  p.dw = dw;
+  const int ntaps = d->kd * 9;
+  p.s_m = (long)d->c_out * ntaps; p.s_n = ntaps;  // dw (c_in, c_out, taps)
+  return run_wgrad(p, d->impl, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -1,7 +1,6 @@
 // CUDA-core implementations of the same implicit-GEMM problems as conv_tc.cu. They serve the layers
 // the tensor-core path cannot take (first layers with 1..4 input channels, channel counts that are
 // not multiples of 8) and act as an on-device cross-check of the tcgen05 kernels in the tests.
-// Also holds the stride-2 transposed convolution (kernel 3, padding 1) of the 3D 'deconv' decoder.
 #include "conv_tc.cuh"
 
 namespace b200 {
@@ -24,9 +23,9 @@ __device__ __forceinline__ long tap_row(const ActView& v, int tap_mode, int n, i
 #define DIRECT_CK 16
 
 __global__ void __launch_bounds__(128)
-    direct_gemm_kernel(const TcGemmProblem p, const long npos) {
+    direct_gemm_kernel(const TcGemmProblem p, const long npos, const int use_table, const TapTable tt) {
   __shared__ float ws[27 * DIRECT_CK * DIRECT_CO];
-  const int ntaps = p.kd * p.kh * p.kw;
+  const int ntaps = use_table ? tt.ntaps : p.kd * p.kh * p.kw;
   const int n0 = blockIdx.y * DIRECT_CO;
   const long pos = (long)blockIdx.x * blockDim.x + threadIdx.x;
   const bool active = pos < npos;
@@ -49,8 +48,9 @@ __global__ void __launch_bounds__(128)
     for (int i = threadIdx.x; i < ntaps * DIRECT_CK * DIRECT_CO; i += blockDim.x) {
       const int j = i % DIRECT_CO, ck = (i / DIRECT_CO) % DIRECT_CK, tap = i / (DIRECT_CO * DIRECT_CK);
       float v = 0.f;
+      const int wt_ = use_table ? tt.widx[tap] : tap;
       if (c0 + ck < p.kdim && n0 + j < p.ncols)
-        v = ldbf(p.wp + ((long)tap * p.ncols + (n0 + j)) * p.kdim + c0 + ck);
+        v = ldbf(p.wp + ((long)wt_ * p.ncols + (n0 + j)) * p.kdim + c0 + ck);
       ws[i] = v;
     }
     __syncthreads();
@@ -58,8 +58,11 @@ __global__ void __launch_bounds__(128)
     const int ckn = min(DIRECT_CK, p.kdim - c0);
     for (int tap = 0; tap < ntaps; ++tap) {
       const int kwi = tap % p.kw, khi = (tap / p.kw) % p.kh, kdi = tap / (p.kw * p.kh);
-      const long row = tap_row(p.a, p.tap_mode, n, d, h, w, kdi, khi, kwi, shift ? pad_d : 0,
-                               shift ? pad_h : 0, shift ? pad_w : 0);
+      const long row = use_table
+                           ? tap_row(p.a, TC_TAP_SHIFT, n + tt.dn[tap], d, h, w, tt.dd[tap], tt.dh[tap],
+                                     tt.dw[tap], 0, 0, 0)
+                           : tap_row(p.a, p.tap_mode, n, d, h, w, kdi, khi, kwi, shift ? pad_d : 0,
+                                     shift ? pad_h : 0, shift ? pad_w : 0);
       if (row < 0) continue;
       const bf16* src = p.a.ptr + row * p.a.ctot + p.a.coff + c0;
       const float* wt = ws + tap * DIRECT_CK * DIRECT_CO;
@@ -95,11 +98,13 @@ __global__ void __launch_bounds__(128)
 
 int direct_gemm_conv(const TcGemmProblem& p, cudaStream_t stream) {
   if (p.kd * p.kh * p.kw > 27) return B200_ERR_UNSUPPORTED;
+  TapTable tt{};
+  if (p.table) tt = *p.table;
   if (p.out_mode == TC_OUT_K2S2_SCATTER && p.cout_t % DIRECT_CO) return B200_ERR_UNSUPPORTED;
   const long npos = (long)p.pn * p.pd * p.ph * p.pw;
   if (npos == 0) return B200_OK;
   dim3 grid((unsigned)((npos + 127) / 128), (unsigned)((p.ncols + DIRECT_CO - 1) / DIRECT_CO));
-  direct_gemm_kernel<<<grid, 128, 0, stream>>>(p, npos);
+  direct_gemm_kernel<<<grid, 128, 0, stream>>>(p, npos, p.table != nullptr, tt);
   B200_LAUNCH_CHECK();
   return B200_OK;
 }
@@ -109,23 +114,25 @@ int direct_gemm_conv(const TcGemmProblem& p, cudaStream_t stream) {
 // reduces over a chunk of positions, then one atomicAdd per accumulator.
 #define WG_ACC 7
 __global__ void __launch_bounds__(256)
-    direct_wgrad_kernel(const TcWgradProblem p, const long npos, const long chunk) {
-  const int ntaps = p.kd * p.kh * p.kw;
+    direct_wgrad_kernel(const TcWgradProblem p, const long npos, const long chunk, const int use_table,
+                        const TapTable tt) {
+  const int ntaps = use_table ? tt.ntaps : p.kd * p.kh * p.kw;
   const int m = blockIdx.y * 64 + (threadIdx.x & 63);
   const int grp = threadIdx.x >> 6;
   const int combos = p.nop.c * ntaps;
   const int cbase = (blockIdx.z * 4 + grp) * WG_ACC;
-  int cn[WG_ACC], ckd[WG_ACC], ckh[WG_ACC], ckw[WG_ACC];
+  int cn[WG_ACC], ckd[WG_ACC], ckh[WG_ACC], ckw[WG_ACC], ctap[WG_ACC];
   float acc[WG_ACC];
 #pragma unroll
   for (int a = 0; a < WG_ACC; ++a) {
     const int c = cbase + a;
     acc[a] = 0.f;
     cn[a] = -1;
-    ckd[a] = ckh[a] = ckw[a] = 0;
+    ckd[a] = ckh[a] = ckw[a] = ctap[a] = 0;
     if (c < combos) {
       const int tap = c % ntaps;
       cn[a] = c / ntaps;
+      ctap[a] = tap;
       ckw[a] = tap % p.kw; ckh[a] = (tap / p.kw) % p.kh; ckd[a] = tap / (p.kw * p.kh);
     }
   }
@@ -144,8 +151,10 @@ __global__ void __launch_bounds__(256)
 #pragma unroll
       for (int a = 0; a < WG_ACC; ++a) {
         if (cn[a] < 0) continue;
-        const long row = tap_row(p.nop, p.tap_mode, n, d, h, w, ckd[a], ckh[a], ckw[a], pad_d,
-                                 pad_h, pad_w);
+        const long row = use_table ? tap_row(p.nop, TC_TAP_SHIFT, n + tt.dn[ctap[a]], d, h, w,
+                                             tt.dd[ctap[a]], tt.dh[ctap[a]], tt.dw[ctap[a]], 0, 0, 0)
+                                   : tap_row(p.nop, p.tap_mode, n, d, h, w, ckd[a], ckh[a], ckw[a], pad_d,
+                                             pad_h, pad_w);
         if (row < 0) continue;
         acc[a] = fmaf(mv, ldbf(p.nop.ptr + row * p.nop.ctot + p.nop.coff + cn[a]), acc[a]);
       }
@@ -153,7 +162,7 @@ __global__ void __launch_bounds__(256)
 #pragma unroll
     for (int a = 0; a < WG_ACC; ++a) {
       if (cn[a] < 0) continue;
-      const int tap = (ckd[a] * p.kh + ckh[a]) * p.kw + ckw[a];
+      const int tap = use_table ? tt.widx[ctap[a]] : (ckd[a] * p.kh + ckh[a]) * p.kw + ckw[a];
       atomicAdd(p.dw + (long)m * p.s_m + (long)cn[a] * p.s_n + tap, acc[a]);
     }
   }
@@ -162,7 +171,9 @@ __global__ void __launch_bounds__(256)
 int direct_wgrad(const TcWgradProblem& p, cudaStream_t stream) {
   const long npos = (long)p.pn * p.pd * p.ph * p.pw;
   if (npos == 0) return B200_OK;
-  const int ntaps = p.kd * p.kh * p.kw;
+  TapTable tt{};
+  if (p.table) tt = *p.table;
+  const int ntaps = p.table ? tt.ntaps : p.kd * p.kh * p.kw;
   const int combos = p.nop.c * ntaps;
   const unsigned gy = (p.mop.c + 63) / 64, gz = (combos + 4 * WG_ACC - 1) / (4 * WG_ACC);
   long want_x = (148L * 8 + (long)gy * gz - 1) / ((long)gy * gz);
@@ -171,175 +182,7 @@ int direct_wgrad(const TcWgradProblem& p, cudaStream_t stream) {
   if (chunk < 32) chunk = 32;
   const unsigned gx = (unsigned)((npos + chunk - 1) / chunk);
   if (gz > 65535 || gy > 65535) return B200_ERR_UNSUPPORTED;
-  direct_wgrad_kernel<<<dim3(gx, gy, gz), 256, 0, stream>>>(p, npos, chunk);
-  B200_LAUNCH_CHECK();
-  return B200_OK;
-}
-
-// ---------------------------------------------------------------------------------- deconv k3 s2 p1
-// ct[n, z, co] = sum_{i, k : 2i - 1 + k = z} x[n, i, ci] * W[ci][co][k]   (per axis; ct = 2*in - 1)
-// wp: bf16 [tap][c_in][c_out]
-struct DeconvArgs {
-  const bf16* x; int n, d, h, w, c_in, in_ctot, in_coff;
-  bf16* y; int od, oh, ow, c_out, out_ctot, out_coff;
-  const bf16* wp;
-  int kd;  // 3 (3D) or 1 (2D: d = od = 1)
-};
-
-__global__ void __launch_bounds__(128) deconv_fwd_kernel(const DeconvArgs a, const long npos) {
-  const long pos = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  const int co0 = blockIdx.y * DIRECT_CO;
-  if (pos >= npos) return;
-  long r = pos;
-  const int zw = (int)(r % a.ow); r /= a.ow;
-  const int zh = (int)(r % a.oh); r /= a.oh;
-  const int zd = (int)(r % a.od); r /= a.od;
-  const int n = (int)r;
-  float acc[DIRECT_CO];
-#pragma unroll
-  for (int j = 0; j < DIRECT_CO; ++j) acc[j] = 0.f;
-  for (int kdi = 0; kdi < a.kd; ++kdi) {
-    int id = 0;
-    if (a.kd == 3) {
-      const int t = zd + 1 - kdi;
-      if (t < 0 || (t & 1)) continue;
-      id = t >> 1;
-      if (id >= a.d) continue;
-    }
-    for (int khi = 0; khi < 3; ++khi) {
-      const int th = zh + 1 - khi;
-      if (th < 0 || (th & 1) || (th >> 1) >= a.h) continue;
-      for (int kwi = 0; kwi < 3; ++kwi) {
-        const int tw = zw + 1 - kwi;
-        if (tw < 0 || (tw & 1) || (tw >> 1) >= a.w) continue;
-        const long row = (((long)n * a.d + id) * a.h + (th >> 1)) * a.w + (tw >> 1);
-        const bf16* xs = a.x + row * a.in_ctot + a.in_coff;
-        const bf16* wt = a.wp + (long)((kdi * 3 + khi) * 3 + kwi) * a.c_in * a.c_out + co0;
-        for (int ci = 0; ci < a.c_in; ++ci) {
-          const float xv = ldbf(xs + ci);
-#pragma unroll
-          for (int j = 0; j < DIRECT_CO; ++j)
-            if (co0 + j < a.c_out) acc[j] = fmaf(xv, ldbf(wt + (long)ci * a.c_out + j), acc[j]);
-        }
-      }
-    }
-  }
-  bf16* orow = a.y + pos * a.out_ctot + a.out_coff + co0;
-#pragma unroll
-  for (int j = 0; j < DIRECT_CO; ++j)
-    if (co0 + j < a.c_out) orow[j] = __float2bfloat16(acc[j]);
-}
-
-// dx[n, i, ci] = sum_k sum_co dy[n, 2i - 1 + k, co] * W[ci][co][k]
-__global__ void __launch_bounds__(128) deconv_bwd_data_kernel(const DeconvArgs a, const long npos) {
-  const long pos = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  const int ci0 = blockIdx.y * DIRECT_CO;
-  if (pos >= npos) return;
-  long r = pos;
-  const int iw = (int)(r % a.w); r /= a.w;
-  const int ih = (int)(r % a.h); r /= a.h;
-  const int id = (int)(r % a.d); r /= a.d;
-  const int n = (int)r;
-  float acc[DIRECT_CO];
-#pragma unroll
-  for (int j = 0; j < DIRECT_CO; ++j) acc[j] = 0.f;
-  for (int kdi = 0; kdi < a.kd; ++kdi) {
-    const int zd = a.kd == 3 ? 2 * id - 1 + kdi : 0;
-    if (zd < 0 || zd >= a.od) continue;
-    for (int khi = 0; khi < 3; ++khi) {
-      const int zh = 2 * ih - 1 + khi;
-      if (zh < 0 || zh >= a.oh) continue;
-      for (int kwi = 0; kwi < 3; ++kwi) {
-        const int zw = 2 * iw - 1 + kwi;
-        if (zw < 0 || zw >= a.ow) continue;
-        const long row = (((long)n * a.od + zd) * a.oh + zh) * a.ow + zw;
-        const bf16* ds = a.y + row * a.out_ctot + a.out_coff;
-        const bf16* wt = a.wp + (long)((kdi * 3 + khi) * 3 + kwi) * a.c_in * a.c_out;
-        for (int co = 0; co < a.c_out; ++co) {
-          const float dv = ldbf(ds + co);
-#pragma unroll
-          for (int j = 0; j < DIRECT_CO; ++j)
-            if (ci0 + j < a.c_in) acc[j] = fmaf(dv, ldbf(wt + (long)(ci0 + j) * a.c_out + co), acc[j]);
-        }
-      }
-    }
-  }
-  bf16* orow = const_cast<bf16*>(a.x) + pos * a.in_ctot + a.in_coff + ci0;
-#pragma unroll
-  for (int j = 0; j < DIRECT_CO; ++j)
-    if (ci0 + j < a.c_in) orow[j] = __float2bfloat16(acc[j]);
-}
-
-// dw[ci][co][k] += sum_{n,i} x[n,i,ci] * dy[n, 2i-1+k, co];  dw fp32 (c_in, c_out, kd, 3, 3)
-__global__ void __launch_bounds__(256)
-    deconv_bwd_weight_kernel(const DeconvArgs a, float* dw, const long npos, const long chunk) {
-  const int ntaps = a.kd * 9;
-  const int co = blockIdx.y * 64 + (threadIdx.x & 63);
-  const int grp = threadIdx.x >> 6;
-  const int combos = a.c_in * ntaps;
-  const int cbase = (blockIdx.z * 4 + grp) * WG_ACC;
-  float acc[WG_ACC];
-#pragma unroll
-  for (int q = 0; q < WG_ACC; ++q) acc[q] = 0.f;
-  const long pbeg = (long)blockIdx.x * chunk;
-  const long pend = min(npos, pbeg + chunk);
-  if (co >= a.c_out) return;
-  for (long pos = pbeg; pos < pend; ++pos) {
-    long r = pos;
-    const int iw = (int)(r % a.w); r /= a.w;
-    const int ih = (int)(r % a.h); r /= a.h;
-    const int id = (int)(r % a.d); r /= a.d;
-    const int n = (int)r;
-#pragma unroll
-    for (int q = 0; q < WG_ACC; ++q) {
-      const int c = cbase + q;
-      if (c >= combos) continue;
-      const int tap = c % ntaps, ci = c / ntaps;
-      const int kwi = tap % 3, khi = (tap / 3) % 3, kdi = tap / 9;
-      const int zd = a.kd == 3 ? 2 * id - 1 + kdi : 0, zh = 2 * ih - 1 + khi, zw = 2 * iw - 1 + kwi;
-      if (zd < 0 || zd >= a.od || zh < 0 || zh >= a.oh || zw < 0 || zw >= a.ow) continue;
-      const long row = (((long)n * a.od + zd) * a.oh + zh) * a.ow + zw;
-      acc[q] = fmaf(ldbf(a.x + pos * a.in_ctot + a.in_coff + ci),
-                    ldbf(a.y + row * a.out_ctot + a.out_coff + co), acc[q]);
-    }
-  }
-#pragma unroll
-  for (int q = 0; q < WG_ACC; ++q) {
-    const int c = cbase + q;
-    if (c >= combos) continue;
-    const int tap = c % ntaps, ci = c / ntaps;
-    atomicAdd(dw + ((long)ci * a.c_out + co) * ntaps + tap, acc[q]);
-  }
-}
-
-int deconv_fwd(const DeconvArgs& a, cudaStream_t s) {
-  const long npos = (long)a.n * a.od * a.oh * a.ow;
-  if (!npos) return B200_OK;
-  dim3 grid((unsigned)((npos + 127) / 128), (unsigned)((a.c_out + DIRECT_CO - 1) / DIRECT_CO));
-  deconv_fwd_kernel<<<grid, 128, 0, s>>>(a, npos);
-  B200_LAUNCH_CHECK();
-  return B200_OK;
-}
-int deconv_bwd_data(const DeconvArgs& a, cudaStream_t s) {
-  const long npos = (long)a.n * a.d * a.h * a.w;
-  if (!npos) return B200_OK;
-  dim3 grid((unsigned)((npos + 127) / 128), (unsigned)((a.c_in + DIRECT_CO - 1) / DIRECT_CO));
-  deconv_bwd_data_kernel<<<grid, 128, 0, s>>>(a, npos);
-  B200_LAUNCH_CHECK();
-  return B200_OK;
-}
-int deconv_bwd_weight(const DeconvArgs& a, float* dw, cudaStream_t s) {
-  const long npos = (long)a.n * a.d * a.h * a.w;
-  if (!npos) return B200_OK;
-  const int combos = a.c_in * a.kd * 9;
-  const unsigned gy = (a.c_out + 63) / 64, gz = (combos + 4 * WG_ACC - 1) / (4 * WG_ACC);
-  if (gz > 65535) return B200_ERR_UNSUPPORTED;
-  long want_x = (148L * 8 + (long)gy * gz - 1) / ((long)gy * gz);
-  if (want_x < 1) want_x = 1;
-  long chunk = (npos + want_x - 1) / want_x;
-  if (chunk < 32) chunk = 32;
-  const unsigned gx = (unsigned)((npos + chunk - 1) / chunk);
-  deconv_bwd_weight_kernel<<<dim3(gx, gy, gz), 256, 0, s>>>(a, dw, npos, chunk);
+  direct_wgrad_kernel<<<dim3(gx, gy, gz), 256, 0, stream>>>(p, npos, chunk, p.table != nullptr, tt);
   B200_LAUNCH_CHECK();
   return B200_OK;
 }

@@ -104,6 +104,8 @@ struct GemmArgs {
   int relu;
   const bf16* mask;
   int mask_ctot, mask_coff;
+  int use_table;
+  TapTable tt;
 };
 
 __global__ void __launch_bounds__(256, 1)
@@ -158,12 +160,17 @@ __global__ void __launch_bounds__(256, 1)
             uint8_t* sA = tiles + (size_t)stage * stage_bytes;
             uint8_t* sB = sA + kABytes;
             mbar_arrive_expect_tx(&full[stage], (uint32_t)stage_bytes);
-            if (p.tap_mode == TC_TAP_SHIFT)
+            int wtap = tap;
+            if (p.use_table) {
+              tma_load_5d(sA, &tmA, &full[stage], kc * 64, tc.w0 + p.tt.dw[tap], tc.h0 + p.tt.dh[tap],
+                          tc.d0 + p.tt.dd[tap], tc.n + p.tt.dn[tap]);
+              wtap = p.tt.widx[tap];
+            } else if (p.tap_mode == TC_TAP_SHIFT)
               tma_load_5d(sA, &tmA, &full[stage], kc * 64, tc.w0 + kwi - p.pad_w,
                           tc.h0 + khi - p.pad_h, tc.d0 + kdi - p.pad_d, tc.n);
             else
               tma_load_5d(sA, &tmA, &full[stage], kc * 64, kwi, tc.w0, khi, tc.n * p.ph + tc.h0);
-            tma_load_3d(sB, &tmB, &full[stage], kc * 64, nt * p.BN, tap);
+            tma_load_3d(sB, &tmB, &full[stage], kc * 64, nt * p.BN, wtap);
           }
           __syncwarp();
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
@@ -535,7 +542,7 @@ static int sm_count();
 int g_halo_mode = 1;  // 0 disables the halo-reuse kernel (A/B testing from the bench tools)
 
 static bool halo_eligible(const TcGemmProblem& p) {
-  return g_halo_mode && p.tap_mode == TC_TAP_SHIFT && p.out_mode == TC_OUT_CONV && p.kh == 3 &&
+  return g_halo_mode && !p.table && p.tap_mode == TC_TAP_SHIFT && p.out_mode == TC_OUT_CONV && p.kh == 3 &&
          p.kw == 3 && (p.kd == 3 || p.kd == 1) && p.ph >= 12 && p.pw >= 8;
 }
 
@@ -613,6 +620,14 @@ int tc_gemm_conv(const TcGemmProblem& p, cudaStream_t stream) {
   a.total = a.m_tiles * a.n_tiles;
   a.ntaps = p.kd * p.kh * p.kw; a.kh = p.kh; a.kw = p.kw;
   a.pad_d = p.kd / 2; a.pad_h = p.kh / 2; a.pad_w = p.kw / 2;
+  int wslabs = a.ntaps;
+  if (p.table) {
+    a.use_table = 1;
+    a.tt = *p.table;
+    a.ntaps = p.table->ntaps;
+    wslabs = 0;
+    for (int t = 0; t < a.ntaps; ++t) wslabs = wslabs > a.tt.widx[t] + 1 ? wslabs : a.tt.widx[t] + 1;
+  }
   a.tap_mode = p.tap_mode; a.out_mode = p.out_mode;
   a.kdim = p.kdim; a.kchunks = (p.kdim + 63) / 64;
   const int stage_bytes = kABytes + a.BN * 128;
@@ -627,7 +642,7 @@ int tc_gemm_conv(const TcGemmProblem& p, cudaStream_t stream) {
   int rc = make_act_tmap(&tmA, p.a, p.tap_mode, g);
   if (rc) return rc;
   {
-    uint64_t dims[3] = {(uint64_t)p.kdim, (uint64_t)p.ncols, (uint64_t)a.ntaps};
+    uint64_t dims[3] = {(uint64_t)p.kdim, (uint64_t)p.ncols, (uint64_t)wslabs};
     uint64_t str[3] = {1, (uint64_t)p.kdim, (uint64_t)p.kdim * p.ncols};
     uint32_t box[3] = {64, (uint32_t)a.BN, 1};
     rc = make_tmap_bf16(&tmB, p.wp, 3, dims, str, box);
@@ -659,6 +674,8 @@ struct WgradArgs {
   int stages;
   float* dw;
   long s_m, s_n;
+  int use_table;
+  TapTable tt;
 };
 
 __global__ void __launch_bounds__(256, 1)
@@ -725,7 +742,10 @@ __global__ void __launch_bounds__(256, 1)
       for (int t = 0; t < p.T; ++t) {
         const int tap = tap0 + t;
         const int kwi = tap % p.kw, khi = (tap / p.kw) % p.kh, kdi = tap / (p.kw * p.kh);
-        if (p.tap_mode == TC_TAP_SHIFT)
+        if (p.use_table)
+          tma_load_5d(sN + t * kABytes, &tmN, &full[stage], nb * 64, tc.w0 + p.tt.dw[tap],
+                      tc.h0 + p.tt.dh[tap], tc.d0 + p.tt.dd[tap], tc.n + p.tt.dn[tap]);
+        else if (p.tap_mode == TC_TAP_SHIFT)
           tma_load_5d(sN + t * kABytes, &tmN, &full[stage], nb * 64, tc.w0 + kwi - p.pad_w,
                       tc.h0 + khi - p.pad_h, tc.d0 + kdi - p.pad_d, tc.n);
         else
@@ -779,7 +799,7 @@ __global__ void __launch_bounds__(256, 1)
     tc_fence_after();
     const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
     for (int t = 0; t < p.T; ++t) {
-      const int tap = tap0 + t;
+      const int tap = p.use_table ? p.tt.widx[tap0 + t] : tap0 + t;
       for (int c0 = 0; c0 < 64; c0 += 16) {
         uint32_t v[16];
         tmem_ld16(taddr + t * 64 + c0, v);
@@ -939,7 +959,7 @@ __global__ void __launch_bounds__(256, 1)
 int g_wgrad_halo_mode = 1;
 
 static bool wgrad_halo_eligible(const TcWgradProblem& p) {
-  return g_wgrad_halo_mode && p.tap_mode == TC_TAP_SHIFT && p.kh == 3 && p.kw == 3 &&
+  return g_wgrad_halo_mode && !p.table && p.tap_mode == TC_TAP_SHIFT && p.kh == 3 && p.kw == 3 &&
          (p.kd == 3 || p.kd == 1) && p.ph >= 12 && p.pw >= 8;
 }
 
@@ -1014,6 +1034,11 @@ int tc_wgrad(const TcWgradProblem& p, cudaStream_t stream) {
   a.tiles_d = g.tiles_d; a.tiles_h = g.tiles_h; a.tiles_w = g.tiles_w; a.m_tiles = g.m_tiles;
   a.ntaps = p.kd * p.kh * p.kw; a.kh = p.kh; a.kw = p.kw;
   a.pad_d = p.kd / 2; a.pad_h = p.kh / 2; a.pad_w = p.kw / 2;
+  if (p.table) {
+    a.use_table = 1;
+    a.tt = *p.table;
+    a.ntaps = p.table->ntaps;
+  }
   a.tap_mode = p.tap_mode;
   a.cm = p.mop.c; a.cn = p.nop.c;
   a.M = a.cm > 64 ? 128 : 64;

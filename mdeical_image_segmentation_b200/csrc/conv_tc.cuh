@@ -17,6 +17,15 @@ enum { TC_OUT_CONV = 0, TC_OUT_K2S2_SCATTER = 1 };
 //   TC_TAP_K2S2  : operand is (N, 1, 2H, 2W, C); tap (i, j) selects positions (2h+i, 2w+j)
 enum { TC_TAP_SHIFT = 0, TC_TAP_K2S2 = 1 };
 
+// Optional explicit tap list (overrides kd/kh/kw in TC_TAP_SHIFT mode): per tap a position shift, a
+// batch-index offset (selects one of several stacked planes, e.g. the parity classes of a stride-2
+// transposed convolution) and the index of the weight slab to use.
+struct TapTable {
+  int ntaps;
+  signed char dd[27], dh[27], dw[27], widx[27];
+  int dn[27];
+};
+
 // Forward / data-gradient implicit GEMM over position tiles of 128 rows:
 //   out[pos][n] = sum_{tap, k} A[pos (+) tap][k] * Wp[tap][n][k]   (+ bias, ReLU, mask)
 struct TcGemmProblem {
@@ -25,6 +34,7 @@ struct TcGemmProblem {
   int ncols, kdim;        // GEMM N and per-tap K
   int kd, kh, kw;         // taps per axis (TC_TAP_K2S2: 1,2,2)
   int tap_mode;           // TC_TAP_*
+  const TapTable* table;  // host pointer or NULL
   int out_mode;           // TC_OUT_*
   int pn, pd, ph, pw;     // position grid the 128-row tiles enumerate
   bf16* out;
@@ -45,6 +55,7 @@ struct TcWgradProblem {
   ActView nop;            // tap-addressed operand (x for conv, dy for convT 2x2)
   int kd, kh, kw;
   int tap_mode;
+  const TapTable* table;  // host pointer or NULL (then taps = kd*kh*kw shifts)
   int pn, pd, ph, pw;     // position grid
   float* dw;
   long s_m, s_n;

@@ -192,6 +192,72 @@ __global__ void upsample_bwd_kernel(int n, int id, int ih, int iw, int od, int o
   }
 }
 
+// ------------------------------------------------------------------------------------ parity planes
+// The stride-2 transposed convolution is produced as 8 (3D) / 4 (2D) parity planes of the input's size:
+// ct[z] with z = 2m + p lives in plane (pd,ph,pw) at position m.  These kernels fuse the gather from /
+// scatter to that layout with the nearest resize to the skip's size (buildingblocks.py:703).
+template <int V>
+__global__ void planes_resize_fwd_kernel(int n, int d, int h, int w, int c, int kd, int od, int oh, int ow,
+                                         View yp, View y) {
+  const int cv = c / V;
+  const int zd = kd == 1 ? 1 : 2 * d - 1, zh = 2 * h - 1, zw = 2 * w - 1;
+  const float sd = (float)zd / od, sh = (float)zh / oh, sw = (float)zw / ow;
+  const long total = (long)n * od * oh * ow * cv;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    long r = i;
+    const int ch = (int)(r % cv) * V; r /= cv;
+    const int xw = (int)(r % ow); r /= ow;
+    const int xh = (int)(r % oh); r /= oh;
+    const int xd = (int)(r % od); r /= od;
+    const int b = (int)r;
+    const int a = nearest_src(xd, sd, zd), e = nearest_src(xh, sh, zh), g = nearest_src(xw, sw, zw);
+    const int cls = kd == 1 ? ((e & 1) * 2 + (g & 1)) : (((a & 1) * 2 + (e & 1)) * 2 + (g & 1));
+    const int md = kd == 1 ? 0 : a >> 1;
+    const long ipos = ((((long)cls * n + b) * d + md) * h + (e >> 1)) * w + (g >> 1);
+    float f[V];
+    Vec<V>::load(yp.at(ipos, ch), f);
+    Vec<V>::store(y.at((((long)b * od + xd) * oh + xh) * ow + xw, ch), f);
+  }
+}
+template <int V>
+__global__ void planes_resize_bwd_kernel(int n, int d, int h, int w, int c, int kd, int od, int oh, int ow,
+                                         View dy, View dyp) {
+  const int cv = c / V;
+  const int classes = kd == 1 ? 4 : 8;
+  const int zd = kd == 1 ? 1 : 2 * d - 1, zh = 2 * h - 1, zw = 2 * w - 1;
+  const float sd = (float)zd / od, sh = (float)zh / oh, sw = (float)zw / ow;
+  const long total = (long)classes * n * d * h * w * cv;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    long r = i;
+    const int ch = (int)(r % cv) * V; r /= cv;
+    const int mw = (int)(r % w); r /= w;
+    const int mh = (int)(r % h); r /= h;
+    const int md = (int)(r % d); r /= d;
+    const int b = (int)(r % n); r /= n;
+    const int cls = (int)r;
+    const int pd = kd == 1 ? 0 : (cls >> 2) & 1, ph = (cls >> 1) & 1, pw = cls & 1;
+    const int a = kd == 1 ? 0 : 2 * md + pd, e = 2 * mh + ph, g = 2 * mw + pw;
+    float acc[V];
+#pragma unroll
+    for (int j = 0; j < V; ++j) acc[j] = 0.f;
+    if (a < zd && e < zh && g < zw) {
+      int d0, d1, h0, h1, w0, w1;
+      children(a, sd, zd, od, d0, d1);
+      children(e, sh, zh, oh, h0, h1);
+      children(g, sw, zw, ow, w0, w1);
+      for (int q = d0; q < d1; ++q)
+        for (int s = h0; s < h1; ++s)
+          for (int t = w0; t < w1; ++t) {
+            float f[V];
+            Vec<V>::load(dy.at((((long)b * od + q) * oh + s) * ow + t, ch), f);
+#pragma unroll
+            for (int j = 0; j < V; ++j) acc[j] += f[j];
+          }
+    }
+    Vec<V>::store(dyp.at(i / cv, ch), acc);
+  }
+}
+
 // ------------------------------------------------------------------------------------ copies
 template <int V>
 __global__ void copy_kernel(long npos, int c, View src, View dst) {
@@ -559,6 +625,26 @@ int b200_upsample_nearest_bwd(int32_t n, int32_t id, int32_t ih, int32_t iw, int
   const bool v = vec8(c, dy) && vec8(c, dx);
   DISPATCH_V(v, upsample_bwd_kernel, GRID1D(total / (v ? 8 : 1)), n, id, ih, iw, od, oh, ow, c, mk(dy),
              mk(dx));
+  return B200_OK;
+}
+int b200_deconv_planes_resize_fwd(int32_t n, int32_t d, int32_t h, int32_t w, int32_t c, int32_t kd,
+                                  int32_t od, int32_t oh, int32_t ow, b200_view yp, b200_view y,
+                                  b200_stream_t stream) {
+  const long total = (long)n * od * oh * ow * c;
+  if (total <= 0) return B200_OK;
+  const bool v = vec8(c, yp) && vec8(c, y);
+  DISPATCH_V(v, planes_resize_fwd_kernel, GRID1D(total / (v ? 8 : 1)), n, d, h, w, c, kd, od, oh, ow,
+             mk(yp), mk(y));
+  return B200_OK;
+}
+int b200_deconv_planes_resize_bwd(int32_t n, int32_t d, int32_t h, int32_t w, int32_t c, int32_t kd,
+                                  int32_t od, int32_t oh, int32_t ow, b200_view dy, b200_view dyp,
+                                  b200_stream_t stream) {
+  const long total = (long)(kd == 1 ? 4 : 8) * n * d * h * w * c;
+  if (total <= 0) return B200_OK;
+  const bool v = vec8(c, dy) && vec8(c, dyp);
+  DISPATCH_V(v, planes_resize_bwd_kernel, GRID1D(total / (v ? 8 : 1)), n, d, h, w, c, kd, od, oh, ow,
+             mk(dy), mk(dyp));
   return B200_OK;
 }
 int b200_copy_channels(int64_t npos, int32_t c, b200_view src, b200_view dst, b200_stream_t stream) {

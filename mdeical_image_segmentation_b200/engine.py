@@ -326,11 +326,11 @@ def unet3d_forward(net, x_in: torch.Tensor, training: bool, tape: Optional[list]
         up_dst = cat.slice(skip.c, cx)
         ct = getattr(getattr(dec.upsampling, "upsample", None), "conv_transposed", None)
         if ct is not None:
-            wp = ops.deconv_repack_weight(ct.weight)
-            y = ops.deconv_fwd(x, wp, is3d)
-            ops.upsample_nearest_fwd(y, size, out=up_dst)
+            wp_fwd, wp_bwd, kd = ops.deconv_repack_weight(ct.weight)
+            planes = ops.deconv_fwd(x, wp_fwd, kd, impl=IMPL)
+            ops.deconv_resize_fwd(planes, x.n, kd, size, out=up_dst)
             if tape is not None:
-                tape.append(("deconv", x, ct, wp, (y.d, y.h, y.w), skip.c, cx))
+                tape.append(("deconv", x, ct, wp_bwd, kd, skip.c, cx))
         else:
             ops.upsample_nearest_fwd(x, size, out=up_dst)
             if tape is not None:
@@ -362,10 +362,11 @@ def unet3d_backward(net, tape: list, dfeat: CL, grads: Grads) -> None:
         dcat = block_bwd(d, tape, 2, grads)
         rec = tape.pop()
         if rec[0] == "deconv":
-            _, x_in, ct, wp, ct_size, cs, cx = rec
-            d_ct = ops.upsample_nearest_bwd(dcat.slice(cs, cx), ct_size)
-            _acc(grads, ct.weight, ops.deconv_bwd_weight(x_in, d_ct, tuple(ct.weight.shape)))
-            d = ops.deconv_bwd_data(d_ct, wp, x_in.dims, is3d)
+            _, x_in, ct, wp_bwd, kd, cs, cx = rec
+            d_planes = ops.deconv_resize_bwd(dcat.slice(cs, cx), x_in.dims, kd)
+            _acc(grads, ct.weight, ops.deconv_bwd_weight(x_in, d_planes, tuple(ct.weight.shape), kd,
+                                                        impl=IMPL))
+            d = ops.deconv_bwd_data(d_planes, wp_bwd, x_in.dims, kd, impl=IMPL)
         else:
             _, in_size, cs, cx = rec
             d = ops.upsample_nearest_bwd(dcat.slice(cs, cx), in_size)

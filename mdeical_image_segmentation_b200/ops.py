@@ -205,48 +205,64 @@ def convt_bwd_weight(x: CL, dy: CL, impl: int = 0) -> torch.Tensor:
 
 # ------------------------------------------------------------------------------------- deconv k3 s2 p1
 def deconv_repack_weight(w: torch.Tensor):
+    """w fp32 (c_in, c_out, [3,] 3, 3) -> (wp_fwd [tap][c_out][c_in], wp_bwd [tap][c_in][c_out], kd)."""
     require_cuda(w)
     c_in, c_out = w.shape[0], w.shape[1]
-    k = tuple(w.shape[2:])
-    ntaps = 1
-    for v in k:
-        ntaps *= v
+    kd = 3 if w.dim() == 5 else 1
+    ntaps = kd * 9
     w = w.detach().contiguous().float()
-    wp = torch.empty((ntaps, c_in, c_out), dtype=bf16, device=w.device)
-    is3d = len(k) == 3
-    d = DeconvDesc(1, 2 if is3d else 1, 2, 2, 3 if is3d else 1, 3, 3, c_in, c_out, c_in, 0, c_out, 0)
-    call("b200_deconv3s2_repack_weight", C.byref(d), _p(w), _p(wp), _stream())
-    return wp
+    fwd = torch.empty((ntaps, c_out, c_in), dtype=bf16, device=w.device)
+    bwd = torch.empty((ntaps, c_in, c_out), dtype=bf16, device=w.device)
+    d = DeconvDesc(1, 1, 1, 1, c_in, c_out, kd, c_in, 0, 0)
+    call("b200_deconv3s2_repack_weight", C.byref(d), _p(w), _p(fwd), _p(bwd), _stream())
+    return fwd, bwd, kd
 
 
-def _deconv_desc(x: CL, y: CL) -> DeconvDesc:
-    return DeconvDesc(x.n, x.d, x.h, x.w, y.d, y.h, y.w, x.c, y.c, x.ctot, x.coff, y.ctot, y.coff)
+def _deconv_desc(x: CL, c_out: int, kd: int, impl: int = 0) -> DeconvDesc:
+    return DeconvDesc(x.n, x.d, x.h, x.w, x.c, c_out, kd, x.ctot, x.coff, impl)
 
 
-def deconv_out_dims(x: CL):
-    return (1 if x.d == 1 else 2 * x.d - 1, 2 * x.h - 1, 2 * x.w - 1)
+def deconv_fwd(x: CL, wp_fwd, kd: int, impl: int = 0) -> CL:
+    """Parity planes (classes*n, d, h, w, c_out) of the stride-2 transposed convolution."""
+    classes = 8 if kd == 3 else 4
+    c_out = wp_fwd.shape[1]
+    yp = CL.empty(classes * x.n, x.d, x.h, x.w, c_out, x.device)
+    call("b200_deconv3s2_fwd", C.byref(_deconv_desc(x, c_out, kd, impl)), _p(x.buf), _p(wp_fwd),
+         _p(yp.buf), _stream())
+    return yp
 
 
-def deconv_fwd(x: CL, wp, is3d: bool) -> CL:
-    od = 2 * x.d - 1 if is3d else 1
-    y = CL.empty(x.n, od, 2 * x.h - 1, 2 * x.w - 1, wp.shape[2], x.device)
-    call("b200_deconv3s2_fwd", C.byref(_deconv_desc(x, y)), _p(x.buf), _p(wp), _p(y.buf), _stream())
-    return y
-
-
-def deconv_bwd_data(dy: CL, wp, x_dims, is3d: bool) -> CL:
+def deconv_bwd_data(dyp: CL, wp_bwd, x_dims, kd: int, impl: int = 0) -> CL:
     n, d, h, w = x_dims
-    dx = CL.empty(n, d, h, w, wp.shape[1], dy.device)
-    call("b200_deconv3s2_bwd_data", C.byref(_deconv_desc(dx, dy)), _p(dy.buf), _p(wp), _p(dx.buf),
-         _stream())
+    dx = CL.empty(n, d, h, w, wp_bwd.shape[1], dyp.device)
+    call("b200_deconv3s2_bwd_data", C.byref(_deconv_desc(dx, dyp.c, kd, impl)), _p(dyp.buf),
+         _p(wp_bwd), _p(dx.buf), _stream())
     return dx
 
 
-def deconv_bwd_weight(x: CL, dy: CL, w_shape) -> torch.Tensor:
+def deconv_bwd_weight(x: CL, dyp: CL, w_shape, kd: int, impl: int = 0) -> torch.Tensor:
     dw = torch.zeros(w_shape, dtype=torch.float32, device=x.device)
-    call("b200_deconv3s2_bwd_weight", C.byref(_deconv_desc(x, dy)), _p(x.buf), _p(dy.buf), _p(dw),
-         _stream())
+    call("b200_deconv3s2_bwd_weight", C.byref(_deconv_desc(x, dyp.c, kd, impl)), _p(x.buf),
+         _p(dyp.buf), _p(dw), _stream())
     return dw
+
+
+def deconv_resize_fwd(yp: CL, n: int, kd: int, size, out: Optional[CL] = None) -> CL:
+    od, oh, ow = size
+    if out is None:
+        out = CL.empty(n, od, oh, ow, yp.c, yp.device)
+    call("b200_deconv_planes_resize_fwd", n, yp.d, yp.h, yp.w, yp.c, kd, od, oh, ow, yp.view(),
+         out.view(), _stream())
+    return out
+
+
+def deconv_resize_bwd(dy: CL, in_dims, kd: int) -> CL:
+    n, d, h, w = in_dims
+    classes = 8 if kd == 3 else 4
+    dyp = CL.empty(classes * n, d, h, w, dy.c, dy.device)
+    call("b200_deconv_planes_resize_bwd", n, d, h, w, dy.c, kd, dy.d, dy.h, dy.w, dy.view(),
+         dyp.view(), _stream())
+    return dyp
 
 
 _NULL_VIEW = View(0, 0, 0)

@@ -161,6 +161,45 @@ def group_convt(impls):
     return ok
 
 
+def group_deconv(impls):
+    ok = True
+    for (n, d, h, w, cin, cout, is3d) in [(1, 4, 6, 8, 32, 16, True), (2, 8, 8, 8, 128, 64, True),
+                                          (1, 1, 12, 20, 64, 32, False), (1, 16, 16, 16, 64, 64, True)]:
+        x = rnd_cl(n, d, h, w, cin, seed=11)
+        g = torch.Generator().manual_seed(12)
+        ks = (3, 3, 3) if is3d else (3, 3)
+        wt = (torch.randn((cin, cout) + ks, generator=g) / (cin * 4) ** 0.5).to(dev)
+        size = (2 * d, 2 * h, 2 * w) if is3d else (1, 2 * h, 2 * w)
+        dy = rnd_cl(n, size[0], size[1], size[2], cout, seed=13)
+        xin = x.to_nchw().requires_grad_(True)
+        wq = wt.to(torch.bfloat16).float().requires_grad_(True)
+        if is3d:
+            y = F.interpolate(F.conv_transpose3d(xin, wq, None, stride=2, padding=1), size=size)
+            y.backward(dy.to_nchw())
+            yref = y
+        else:
+            y = F.interpolate(F.conv_transpose2d(xin[:, :, 0], wq, None, stride=2, padding=1), size=size[1:])
+            y.backward(dy.to_nchw()[:, :, 0])
+            yref = y.unsqueeze(2)
+        fwd, bwd, kd = ops.deconv_repack_weight(wt)
+        for impl in impls:
+            try:
+                planes = ops.deconv_fwd(x, fwd, kd, impl=impl)
+                out = ops.deconv_resize_fwd(planes, n, kd, size)
+                torch.cuda.synchronize()
+                ok &= report(f"deconv_fwd[{n},{d},{h},{w},{cin}->{cout}] impl={impl}", out.to_nchw(), yref)
+                dpl = ops.deconv_resize_bwd(dy, x.dims, kd)
+                dx = ops.deconv_bwd_data(dpl, bwd, x.dims, kd, impl=impl)
+                dw = ops.deconv_bwd_weight(x, dpl, wt.shape, kd, impl=impl)
+                torch.cuda.synchronize()
+                ok &= report(f"deconv_dgrad[{cin}->{cout}] impl={impl}", dx.to_nchw(), xin.grad)
+                ok &= report(f"deconv_wgrad[{cin}->{cout}] impl={impl}", dw, wq.grad, tol=2e-2)
+            except Exception as e:  # noqa
+                ok = False
+                print(f"[BAD] deconv[{cin}->{cout}] impl={impl}: {e}", flush=True)
+    return ok
+
+
 def group_perf():
     """First timing of the tcgen05 kernels on the headline layer shapes."""
     shapes = [
@@ -266,6 +305,8 @@ def main():
         ok = group_convt([2])
     elif a.group == "tc_convt":
         ok = group_convt([1])
+    elif a.group == "deconv":
+        ok = group_deconv([2, 1])
     elif a.group == "perf":
         group_perf()
         ok = True
