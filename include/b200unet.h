@@ -123,9 +123,11 @@ typedef struct b200_view {
 int b200_maxpool2_fwd(int32_t n, int32_t d, int32_t h, int32_t w, int32_t c, int32_t pool_d,
                       b200_view x, b200_view y, b200_stream_t stream);
 /* dx fully written; ties go to the first maximum in (d,h,w) scan order, as ATen does.
- * add (ptr may be NULL): a second gradient of x's shape summed in (the skip branch of the U). */
+ * add (ptr may be NULL): a second gradient of x's shape summed in (the skip branch of the U).
+ * mask_relu != 0: x is a ReLU output; dx is zeroed where x <= 0 (its producer's ReLU backward). */
 int b200_maxpool2_bwd(int32_t n, int32_t d, int32_t h, int32_t w, int32_t c, int32_t pool_d,
-                      b200_view x, b200_view dy, b200_view add, b200_view dx, b200_stream_t stream);
+                      b200_view x, b200_view dy, b200_view add, b200_view dx, int32_t mask_relu,
+                      b200_stream_t stream);
 /* F.interpolate(mode='nearest') buildingblocks.py:671-673: src = floor(dst * in / out) */
 int b200_upsample_nearest_fwd(int32_t n, int32_t id, int32_t ih, int32_t iw, int32_t od,
                               int32_t oh, int32_t ow, int32_t c, b200_view x, b200_view y,
@@ -166,7 +168,7 @@ int b200_gn_apply(int32_t n, int64_t spatial, int32_t c, int32_t groups, b200_vi
  * scratch fp32 [n][2][c] + [n][groups][2], zeroed by the caller */
 int b200_gn_bwd(int32_t n, int64_t spatial, int32_t c, int32_t groups, b200_view x,
                 const float* stats, const float* gamma, b200_view dy, b200_view dx, float* dgamma,
-                float* dbeta, float* scratch, b200_stream_t stream);
+                float* dbeta, float* scratch, int32_t mask_relu, b200_stream_t stream);
 
 /* ---- BatchNorm (nn.BatchNorm2d/3d, layers.py:21, buildingblocks.py:93-103) ---------------------- */
 /* sums: fp64 [2][c] = (sum x, sum x^2) accumulated into (caller zeroes) */
@@ -181,16 +183,16 @@ int b200_bn_bwd_reduce(int64_t npos, int32_t c, b200_view x, b200_view dy, b200_
 /* pass 2: dx = gamma * rstd * (dz - red0/M - xhat * red1/M) */
 int b200_bn_bwd_apply(int64_t npos, int32_t c, b200_view x, b200_view dy, b200_view relu_out,
                       const float* mean, const float* rstd, const float* gamma, const float* red,
-                      b200_view dx, b200_stream_t stream);
+                      b200_view dx, int32_t mask_relu, b200_stream_t stream);
 
 /* ---- 1x1 head (nn.Conv2d(64,C,1) unet.py:89; nn.Conv3d(f0,C,1) model.py:110-113) ---------------- */
 /* logits fp32 (n, c_out, spatial) = x (n, spatial, c_in) . w^T + b;  w fp32 [c_out][c_in] */
 int b200_head_fwd(int32_t n, int64_t spatial, int32_t c_in, int32_t c_out, b200_view x,
                   const float* w, const float* b, float* logits, b200_stream_t stream);
-/* dx bf16, dw fp32 [c_out][c_in] and db fp32 [c_out] accumulated into */
+/* dx bf16, dw fp32 [c_out][c_in] and db fp32 [c_out] accumulated into; mask_relu as above */
 int b200_head_bwd(int32_t n, int64_t spatial, int32_t c_in, int32_t c_out, b200_view x,
                   const float* w, const float* dlogits, b200_view dx, float* dw, float* db,
-                  b200_stream_t stream);
+                  int32_t mask_relu, b200_stream_t stream);
 
 /* ---- losses ------------------------------------------------------------------------------------
  * One pass over fp32 logits (n, c, spatial) and a same-shape fp32 target produces the per-channel

@@ -57,7 +57,7 @@ SIGNATURES = {
     "b200_deconv3s2_bwd_data": [_PD, _P, _P, _P, _P],
     "b200_deconv3s2_bwd_weight": [_PD, _P, _P, _P, _P],
     "b200_maxpool2_fwd": [_I, _I, _I, _I, _I, _I, View, View, _P],
-    "b200_maxpool2_bwd": [_I, _I, _I, _I, _I, _I, View, View, View, View, _P],
+    "b200_maxpool2_bwd": [_I, _I, _I, _I, _I, _I, View, View, View, View, _I, _P],
     "b200_upsample_nearest_fwd": [_I, _I, _I, _I, _I, _I, _I, _I, View, View, _P],
     "b200_upsample_nearest_bwd": [_I, _I, _I, _I, _I, _I, _I, _I, View, View, _P],
     "b200_copy_channels": [_L, _I, View, View, _P],
@@ -67,13 +67,13 @@ SIGNATURES = {
     "b200_cl_bf16_to_nchw_f32": [_I, _I, _L, View, _P, _P],
     "b200_gn_stats": [_I, _L, _I, _I, _F, View, _P, _P, _P],
     "b200_gn_apply": [_I, _L, _I, _I, View, _P, _P, _P, _I, View, _P],
-    "b200_gn_bwd": [_I, _L, _I, _I, View, _P, _P, View, View, _P, _P, _P, _P],
+    "b200_gn_bwd": [_I, _L, _I, _I, View, _P, _P, View, View, _P, _P, _P, _I, _P],
     "b200_bn_stats": [_L, _I, View, _P, _P],
     "b200_bn_apply": [_L, _I, View, _P, _P, _P, _P, _I, View, _P],
     "b200_bn_bwd_reduce": [_L, _I, View, View, View, _P, _P, _P, _P],
-    "b200_bn_bwd_apply": [_L, _I, View, View, View, _P, _P, _P, _P, View, _P],
+    "b200_bn_bwd_apply": [_L, _I, View, View, View, _P, _P, _P, _P, View, _I, _P],
     "b200_head_fwd": [_I, _L, _I, _I, View, _P, _P, _P, _P],
-    "b200_head_bwd": [_I, _L, _I, _I, View, _P, _P, View, _P, _P, _P],
+    "b200_head_bwd": [_I, _L, _I, _I, View, _P, _P, View, _P, _P, _I, _P],
     "b200_seg_sums": [_I, _I, _L, _P, _P, _I, _P, _P],
     "b200_seg_loss_bwd": [_I, _I, _L, _P, _P, _P, _I, _P, _P],
     "b200_ce_fwd": [_I, _I, _L, _P, _P, _P, _P],

@@ -30,12 +30,13 @@ __device__ __forceinline__ double block_sum_d(double v, double* sh) {
 // ------------------------------------------------------------------------------------ head
 // 8 threads per position, each owning 8 consecutive input channels (one 16-byte load); a warp
 // therefore streams 512 contiguous bytes of x per pass.  c_in is processed in passes of 64.
-#define HEAD_MAX_CO 8
+#define HEAD_CO_LIMIT 8
 __device__ __forceinline__ void ld8(const bf16* p, float* f) {
   const uint4 u = *reinterpret_cast<const uint4*>(p);
   const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
   f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
 }
+template <int HEAD_MAX_CO>
 __global__ void __launch_bounds__(256)
     head_fwd_kernel(int n, long spatial, int c_in, int c_out, View x, const float* w, const float* b,
                     float* logits) {
@@ -84,9 +85,10 @@ __global__ void __launch_bounds__(256)
 }
 // One pass over x and dlogits: dx[pos][ci] = sum_co g[co] w[co][ci] (bf16 store) and
 // dw[co][ci] += sum_pos g[co] x[pos][ci], db[co] += sum_pos g[co].
+template <int HEAD_MAX_CO>
 __global__ void __launch_bounds__(256)
     head_bwd_kernel(int n, long spatial, int c_in, int c_out, long chunk, View x, const float* w,
-                    const float* dlogits, View dx, float* dw, float* db) {
+                    const float* dlogits, View dx, float* dw, float* db, int mask_relu) {
   extern __shared__ float sw[];       // [c_out][c_in] weights, then [32][c_out][8] reduction scratch
   float* sred = sw + c_out * c_in;
   for (int i = threadIdx.x; i < c_out * c_in; i += blockDim.x) sw[i] = w[i];
@@ -124,6 +126,11 @@ __global__ void __launch_bounds__(256)
           }
         }
         if (dx.p) {
+          if (mask_relu) {  // x is a ReLU output: dx doubles as the pre-activation gradient
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+              if (!(f[k] > 0.f)) o[k] = 0.f;
+          }
           uint4 u;
           u.x = pack_bf16x2(o[0], o[1]); u.y = pack_bf16x2(o[2], o[3]);
           u.z = pack_bf16x2(o[4], o[5]); u.w = pack_bf16x2(o[6], o[7]);
@@ -132,7 +139,9 @@ __global__ void __launch_bounds__(256)
       }
     }
     // reduce the 32 position-rows of the block, one output channel at a time
-    for (int j = 0; j < c_out; ++j) {
+#pragma unroll
+    for (int j = 0; j < HEAD_MAX_CO; ++j) {
+      if (j >= c_out) break;
       __syncthreads();
 #pragma unroll
       for (int k = 0; k < 8; ++k) sred[(prow * 8 + oct) * 8 + k] = aw[j][k];
@@ -344,25 +353,28 @@ int b200_head_fwd(int32_t n, int64_t spatial, int32_t c_in, int32_t c_out, b200_
   const long total = (long)n * spatial;
   if (total <= 0) return B200_OK;
   const size_t smem = ((size_t)c_out * c_in + c_out) * sizeof(float);
-  if (smem > 48 * 1024 || c_out > HEAD_MAX_CO || c_in % 8 || x.ctot % 8 || x.coff % 8)
+  if (smem > 48 * 1024 || c_out > HEAD_CO_LIMIT || c_in % 8 || x.ctot % 8 || x.coff % 8)
     return B200_ERR_UNSUPPORTED;
-  head_fwd_kernel<<<grid1d(total * 8), 256, smem, (cudaStream_t)stream>>>(n, (long)spatial, c_in, c_out, mk(x), w, b, logits);
+#define HEAD_FWD(CO) head_fwd_kernel<CO><<<grid1d(total * 8), 256, smem, (cudaStream_t)stream>>>(n, (long)spatial, c_in, c_out, mk(x), w, b, logits)
+  if (c_out <= 1) HEAD_FWD(1); else if (c_out <= 2) HEAD_FWD(2); else if (c_out <= 4) HEAD_FWD(4); else HEAD_FWD(8);
+#undef HEAD_FWD
   B200_LAUNCH_CHECK();
   return B200_OK;
 }
 int b200_head_bwd(int32_t n, int64_t spatial, int32_t c_in, int32_t c_out, b200_view x,
                   const float* w, const float* dlogits, b200_view dx, float* dw, float* db,
-                  b200_stream_t stream) {
+                  int32_t mask_relu, b200_stream_t stream) {
   const long total = (long)n * spatial;
   if (total <= 0) return B200_OK;
   const size_t smem = ((size_t)c_out * c_in + 2048) * sizeof(float);
-  if (smem > 48 * 1024 || c_out > HEAD_MAX_CO || c_in % 8 || x.ctot % 8 || x.coff % 8 ||
+  if (smem > 48 * 1024 || c_out > HEAD_CO_LIMIT || c_in % 8 || x.ctot % 8 || x.coff % 8 ||
       (dx.ptr && (dx.ctot % 8 || dx.coff % 8)))
     return B200_ERR_UNSUPPORTED;
-  long chunk = (total + 148L * 8 - 1) / (148L * 8);
+  long chunk = (total + 148L * 16 - 1) / (148L * 16);
   if (chunk < 256) chunk = 256;
-  head_bwd_kernel<<<(unsigned)((total + chunk - 1) / chunk), 256, smem, (cudaStream_t)stream>>>(
-      n, (long)spatial, c_in, c_out, chunk, mk(x), w, dlogits, mk(dx), dw, db);
+#define HEAD_BWD(CO) head_bwd_kernel<CO><<<(unsigned)((total + chunk - 1) / chunk), 256, smem, (cudaStream_t)stream>>>(n, (long)spatial, c_in, c_out, chunk, mk(x), w, dlogits, mk(dx), dw, db, mask_relu)
+  if (c_out <= 1) HEAD_BWD(1); else if (c_out <= 2) HEAD_BWD(2); else if (c_out <= 4) HEAD_BWD(4); else HEAD_BWD(8);
+#undef HEAD_BWD
   B200_LAUNCH_CHECK();
   return B200_OK;
 }

@@ -75,7 +75,8 @@ __global__ void maxpool_fwd_kernel(int n, int d, int h, int w, int c, int pd, Vi
 // one thread per pooling WINDOW (including the partial windows an odd edge leaves over): reads the
 // window once, routes dy to the first maximum in (d,h,w) scan order and writes every dx of the window
 template <int V>
-__global__ void maxpool_bwd_kernel(int n, int d, int h, int w, int c, int pd, View x, View dy, View add, View dx) {
+__global__ void maxpool_bwd_kernel(int n, int d, int h, int w, int c, int pd, View x, View dy, View add, View dx,
+                                   int mask_relu) {
   const int od = d / pd, oh = h / 2, ow = w / 2, cv = c / V;
   const int wd = (d + pd - 1) / pd, wh = (h + 1) / 2, ww = (w + 1) / 2;
   const long total = (long)n * wd * wh * ww * cv;
@@ -121,6 +122,13 @@ __global__ void maxpool_bwd_kernel(int n, int d, int h, int w, int c, int pd, Vi
           if (add.p) Vec<V>::load(add.at(pos, ch), out);
 #pragma unroll
           for (int j = 0; j < V; ++j) out[j] += (arg[j] == k) ? g_[j] : 0.f;
+          if (mask_relu) {  // x is a ReLU output: fold the ReLU backward of its producer in here
+            float xk[V];
+            Vec<V>::load(x.at(pos, ch), xk);
+#pragma unroll
+            for (int j = 0; j < V; ++j)
+              if (!(xk[j] > 0.f)) out[j] = 0.f;
+          }
           Vec<V>::store(dx.at(pos, ch), out);
         }
   }
@@ -292,8 +300,10 @@ __device__ __forceinline__ void column_pass(long npos, int c, long chunk, F f, O
     for (int j = 0; j < V; ++j) acc[k][j] = 0.f;
   const long pbeg = (long)blockIdx.x * chunk;
   const long pend = pbeg + chunk < npos ? pbeg + chunk : npos;
-  if (t_row < rows && my_cv < cv)
+  if (t_row < rows && my_cv < cv) {
+#pragma unroll 4
     for (long pos = pbeg + t_row; pos < pend; pos += rows) f(pos, my_cv * V, acc);
+  }
   if (!DO_RED) return;
   __shared__ float sred[256 * 8];
   for (int k = 0; k < NRED; ++k) {
@@ -361,6 +371,127 @@ __global__ void cl_to_nchw_kernel(int n, int c, long spatial, View src, float* d
     const long b = i / spatial, s = i % spatial;
     for (int ch = 0; ch < c; ++ch)
       dst[(b * c + ch) * spatial + s] = __bfloat162float(*src.at(i, ch));
+  }
+}
+
+// ------------------------------------------------------------------------------------ affine streams
+// y = relu?(x * sc[ch] + sh[ch]) and dx = a[ch] * g + b[ch] * x + c0[ch] (g = dy, masked by y > 0):
+// every normalisation forward / backward "apply" pass of the path has this form once the per-channel
+// constants are folded.  A thread owns one 8-channel vector (constants live in registers) and walks
+// positions 4 at a time, so there is no per-element index arithmetic and 4 x 16 B loads are in flight.
+struct ColMap {
+  int cv, cvb, rows, t_cv, t_row, my_cv;
+  __device__ __forceinline__ ColMap(int c, int V) {
+    cv = c / V;
+    cvb = cv < 256 ? cv : 256;
+    rows = 256 / cvb;
+    t_cv = threadIdx.x % cvb;
+    t_row = threadIdx.x / cvb;
+    my_cv = blockIdx.y * cvb + t_cv;
+  }
+  __device__ __forceinline__ bool active() const { return t_row < rows && my_cv < cv; }
+};
+
+// mode 0: GroupNorm (stats = [n][groups][2] mean/rstd), mode 1: BatchNorm (p0 = mean[c], p1 = rstd[c])
+template <int V>
+__global__ void __launch_bounds__(256)
+    norm_apply_kernel(long spatial, int c, int groups, long chunk, int mode, View x, const float* p0,
+                      const float* p1, const float* gamma, const float* beta, int relu, View y) {
+  const ColMap m(c, V);
+  if (!m.active()) return;
+  const int b = blockIdx.z, ch = m.my_cv * V;
+  float sc[V], sh[V];
+#pragma unroll
+  for (int j = 0; j < V; ++j) {
+    float mean, rstd;
+    if (mode == 0) {
+      const int g = (ch + j) / (c / groups);
+      mean = p0[(b * groups + g) * 2];
+      rstd = p0[(b * groups + g) * 2 + 1];
+    } else {
+      mean = p0[ch + j];
+      rstd = p1[ch + j];
+    }
+    sc[j] = rstd * gamma[ch + j];
+    sh[j] = beta[ch + j] - mean * sc[j];
+  }
+  const long base = (long)b * spatial;
+  const long pbeg = (long)blockIdx.x * chunk;
+  const long pend = pbeg + chunk < spatial ? pbeg + chunk : spatial;
+  for (long p = pbeg + m.t_row; p < pend; p += 4L * m.rows) {
+    float f[4][V];
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (p + (long)u * m.rows < pend) Vec<V>::load(x.at(base + p + (long)u * m.rows, ch), f[u]);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (p + (long)u * m.rows < pend) {
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+          const float v = fmaf(f[u][j], sc[j], sh[j]);
+          f[u][j] = relu ? fmaxf(v, 0.f) : v;
+        }
+        Vec<V>::store(y.at(base + p + (long)u * m.rows, ch), f[u]);
+      }
+    }
+  }
+}
+
+// mode 0: GroupNorm backward (p0 = stats, red = gsum [n][groups][2]); mode 1: BatchNorm backward
+// (p0 = mean, p1 = rstd, red = [2][c] or NULL for frozen statistics); ro = ReLU output for masking
+template <int V>
+__global__ void __launch_bounds__(256)
+    norm_bwd_apply_kernel(long spatial, int c, int groups, long chunk, int mode, float inv_m, View x,
+                          View dy, View ro, const float* p0, const float* p1, const float* gamma,
+                          const float* red, View dx, int mask_x) {
+  const ColMap m(c, V);
+  if (!m.active()) return;
+  const int b = blockIdx.z, ch = m.my_cv * V;
+  float ka[V], kb[V], kc[V];
+#pragma unroll
+  for (int j = 0; j < V; ++j) {
+    float mean, rstd, r0, r1;
+    if (mode == 0) {
+      const int g = b * groups + (ch + j) / (c / groups);
+      mean = p0[g * 2]; rstd = p0[g * 2 + 1];
+      r0 = red[g * 2]; r1 = red[g * 2 + 1];
+      ka[j] = rstd * gamma[ch + j];
+      kb[j] = -rstd * rstd * r1 * inv_m;
+      kc[j] = -rstd * inv_m * r0 - mean * kb[j];
+    } else {
+      mean = p0[ch + j]; rstd = p1[ch + j];
+      r0 = red ? red[ch + j] : 0.f; r1 = red ? red[c + ch + j] : 0.f;
+      const float gr = gamma[ch + j] * rstd;
+      ka[j] = gr;
+      kb[j] = -gr * rstd * r1 * inv_m;
+      kc[j] = -gr * r0 * inv_m - mean * kb[j];
+    }
+  }
+  const long base = (long)b * spatial;
+  const long pbeg = (long)blockIdx.x * chunk;
+  const long pend = pbeg + chunk < spatial ? pbeg + chunk : spatial;
+  for (long p = pbeg + m.t_row; p < pend; p += 2L * m.rows) {
+    float xv[2][V], g[2][V], o[2][V];
+#pragma unroll
+    for (int u = 0; u < 2; ++u)
+      if (p + (long)u * m.rows < pend) {
+        const long q = base + p + (long)u * m.rows;
+        Vec<V>::load(x.at(q, ch), xv[u]);
+        Vec<V>::load(dy.at(q, ch), g[u]);
+        if (ro.p) Vec<V>::load(ro.at(q, ch), o[u]);
+      }
+#pragma unroll
+    for (int u = 0; u < 2; ++u)
+      if (p + (long)u * m.rows < pend) {
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+          float gj = g[u][j];
+          if (ro.p && !(o[u][j] > 0.f)) gj = 0.f;
+          g[u][j] = fmaf(ka[j], gj, fmaf(kb[j], xv[u][j], kc[j]));
+          if (mask_x && !(xv[u][j] > 0.f)) g[u][j] = 0.f;  // x is a ReLU output of the layer before
+        }
+        Vec<V>::store(dx.at(base + p + (long)u * m.rows, ch), g[u]);
+      }
   }
 }
 
@@ -599,13 +730,14 @@ int b200_maxpool2_fwd(int32_t n, int32_t d, int32_t h, int32_t w, int32_t c, int
   return B200_OK;
 }
 int b200_maxpool2_bwd(int32_t n, int32_t d, int32_t h, int32_t w, int32_t c, int32_t pool_d,
-                      b200_view x, b200_view dy, b200_view add, b200_view dx, b200_stream_t stream) {
+                      b200_view x, b200_view dy, b200_view add, b200_view dx, int32_t mask_relu,
+                      b200_stream_t stream) {
   if (pool_d != 1 && pool_d != 2) return B200_ERR_BAD_ARG;
   if ((long)n * d * h * w * c <= 0) return B200_OK;
   const long total = (long)n * ((d + pool_d - 1) / pool_d) * ((h + 1) / 2) * ((w + 1) / 2) * c;
   const bool v = vec8(c, x) && vec8(c, dy) && vec8(c, dx) && (!add.ptr || vec8(c, add));
   DISPATCH_V(v, maxpool_bwd_kernel, GRID1D(total / (v ? 8 : 1)), n, d, h, w, c, pool_d, mk(x), mk(dy),
-             mk(add), mk(dx));
+             mk(add), mk(dx), mask_relu);
   return B200_OK;
 }
 int b200_upsample_nearest_fwd(int32_t n, int32_t id, int32_t ih, int32_t iw, int32_t od, int32_t oh,
@@ -721,16 +853,20 @@ int b200_gn_stats(int32_t n, int64_t spatial, int32_t c, int32_t groups, float e
 int b200_gn_apply(int32_t n, int64_t spatial, int32_t c, int32_t groups, b200_view x,
                   const float* stats, const float* gamma, const float* beta, int32_t relu,
                   b200_view y, b200_stream_t stream) {
-  const long total = (long)n * spatial * c;
-  if (total <= 0) return B200_OK;
+  if ((long)n * spatial * c <= 0) return B200_OK;
   const bool v = vec8(c, x) && vec8(c, y);
-  DISPATCH_V(v, gn_apply_kernel, GRID1D(total / (v ? 8 : 1)), n, (long)spatial, c, groups, mk(x), stats,
-             gamma, beta, relu, mk(y));
+  dim3 grid;
+  long chunk;
+  column_grid(spatial, c, v ? 8 : 1, grid, chunk);
+  grid.z = n;
+  if (v) norm_apply_kernel<8><<<grid, 256, 0, (cudaStream_t)stream>>>((long)spatial, c, groups, chunk, 0, mk(x), stats, nullptr, gamma, beta, relu, mk(y));
+  else norm_apply_kernel<1><<<grid, 256, 0, (cudaStream_t)stream>>>((long)spatial, c, groups, chunk, 0, mk(x), stats, nullptr, gamma, beta, relu, mk(y));
+  B200_LAUNCH_CHECK();
   return B200_OK;
 }
 int b200_gn_bwd(int32_t n, int64_t spatial, int32_t c, int32_t groups, b200_view x,
                 const float* stats, const float* gamma, b200_view dy, b200_view dx, float* dgamma,
-                float* dbeta, float* scratch, b200_stream_t stream) {
+                float* dbeta, float* scratch, int32_t mask_relu, b200_stream_t stream) {
   if (groups <= 0 || c % groups) return B200_ERR_BAD_ARG;
   const long total = (long)n * spatial * c;
   if (total <= 0) return B200_OK;
@@ -747,8 +883,13 @@ int b200_gn_bwd(int32_t n, int64_t spatial, int32_t c, int32_t groups, b200_view
   const int work = n * groups > c ? n * groups : c;
   gn_bwd_finalize_kernel<<<(work + 127) / 128, 128, 0, (cudaStream_t)stream>>>(n, c, groups, gamma, s, gsum, dgamma, dbeta);
   B200_LAUNCH_CHECK();
-  DISPATCH_V(v, gn_bwd_apply_kernel, GRID1D(total / (v ? 8 : 1)), n, (long)spatial, c, groups, mk(x),
-             mk(dy), stats, gamma, gsum, mk(dx));
+  column_grid(spatial, c, v ? 8 : 1, grid, chunk);
+  grid.z = n;
+  const float inv_m = 1.f / ((float)(c / groups) * (float)spatial);
+  b200_view none{nullptr, 0, 0};
+  if (v) norm_bwd_apply_kernel<8><<<grid, 256, 0, (cudaStream_t)stream>>>((long)spatial, c, groups, chunk, 0, inv_m, mk(x), mk(dy), mk(none), stats, nullptr, gamma, gsum, mk(dx), mask_relu);
+  else norm_bwd_apply_kernel<1><<<grid, 256, 0, (cudaStream_t)stream>>>((long)spatial, c, groups, chunk, 0, inv_m, mk(x), mk(dy), mk(none), stats, nullptr, gamma, gsum, mk(dx), mask_relu);
+  B200_LAUNCH_CHECK();
   return B200_OK;
 }
 
@@ -766,11 +907,14 @@ int b200_bn_stats(int64_t npos, int32_t c, b200_view x, double* sums, b200_strea
 int b200_bn_apply(int64_t npos, int32_t c, b200_view x, const float* mean, const float* rstd,
                   const float* gamma, const float* beta, int32_t relu, b200_view y,
                   b200_stream_t stream) {
-  const long total = (long)npos * c;
-  if (total <= 0) return B200_OK;
+  if ((long)npos * c <= 0) return B200_OK;
   const bool v = vec8(c, x) && vec8(c, y);
-  DISPATCH_V(v, bn_apply_kernel, GRID1D(total / (v ? 8 : 1)), (long)npos, c, mk(x), mean, rstd, gamma,
-             beta, relu, mk(y));
+  dim3 grid;
+  long chunk;
+  column_grid(npos, c, v ? 8 : 1, grid, chunk);
+  if (v) norm_apply_kernel<8><<<grid, 256, 0, (cudaStream_t)stream>>>((long)npos, c, 1, chunk, 1, mk(x), mean, rstd, gamma, beta, relu, mk(y));
+  else norm_apply_kernel<1><<<grid, 256, 0, (cudaStream_t)stream>>>((long)npos, c, 1, chunk, 1, mk(x), mean, rstd, gamma, beta, relu, mk(y));
+  B200_LAUNCH_CHECK();
   return B200_OK;
 }
 int b200_bn_bwd_reduce(int64_t npos, int32_t c, b200_view x, b200_view dy, b200_view relu_out,
@@ -787,12 +931,16 @@ int b200_bn_bwd_reduce(int64_t npos, int32_t c, b200_view x, b200_view dy, b200_
 }
 int b200_bn_bwd_apply(int64_t npos, int32_t c, b200_view x, b200_view dy, b200_view relu_out,
                       const float* mean, const float* rstd, const float* gamma, const float* red,
-                      b200_view dx, b200_stream_t stream) {
-  const long total = (long)npos * c;
-  if (total <= 0) return B200_OK;
+                      b200_view dx, int32_t mask_relu, b200_stream_t stream) {
+  if ((long)npos * c <= 0) return B200_OK;
   const bool v = vec8(c, x) && vec8(c, dy) && vec8(c, dx) && (!relu_out.ptr || vec8(c, relu_out));
-  DISPATCH_V(v, bn_bwd_apply_kernel, GRID1D(total / (v ? 8 : 1)), (long)npos, c, mk(x), mk(dy),
-             mk(relu_out), mean, rstd, gamma, red, mk(dx));
+  dim3 grid;
+  long chunk;
+  column_grid(npos, c, v ? 8 : 1, grid, chunk);
+  const float inv_m = 1.f / (float)npos;
+  if (v) norm_bwd_apply_kernel<8><<<grid, 256, 0, (cudaStream_t)stream>>>((long)npos, c, 1, chunk, 1, inv_m, mk(x), mk(dy), mk(relu_out), mean, rstd, gamma, red, mk(dx), mask_relu);
+  else norm_bwd_apply_kernel<1><<<grid, 256, 0, (cudaStream_t)stream>>>((long)npos, c, 1, chunk, 1, inv_m, mk(x), mk(dy), mk(relu_out), mean, rstd, gamma, red, mk(dx), mask_relu);
+  B200_LAUNCH_CHECK();
   return B200_OK;
 }
 

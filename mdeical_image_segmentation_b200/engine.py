@@ -80,11 +80,15 @@ def _bn_moments(bn: nn.Module, x: CL, training: bool):
 
 
 def single_conv_fwd(x: CL, spec: LayerSpec, training: bool, tape: Optional[list],
-                    out: Optional[CL] = None) -> CL:
-    """Runs one layer; ``out`` (optional) is the destination slice of its final result."""
+                    out: Optional[CL] = None, in_relu: bool = False):
+    """Runs one layer; ``out`` (optional) is the destination slice of its final result.
+    ``in_relu`` says the input is a ReLU output (>= 0, zero exactly where its producer was clipped):
+    the first op's backward then folds that producer's ReLU backward into its own output.
+    Returns (y, y_is_relu_output)."""
     letters = spec.order
     cur = x
     i = 0
+    out_relu = False
     while i < len(letters):
         ch = letters[i]
         fuse_relu = ch in "cgb" and i + 1 < len(letters) and letters[i + 1] == "r"
@@ -101,7 +105,8 @@ def single_conv_fwd(x: CL, spec: LayerSpec, training: bool, tape: Optional[list]
             bias = None if conv.bias is None else conv.bias.detach().float().contiguous()
             y = ops.conv_fwd(xin, wp_fwd, k, bias, fuse_relu, out=dst, impl=IMPL)
             if tape is not None:
-                tape.append(("conv", xin, conv, wp_bwd, k, y if fuse_relu else None, cur.zpad))
+                tape.append(("conv", xin, conv, wp_bwd, k, y if fuse_relu else None, cur.zpad,
+                             in_relu and i == 0))
             cur = y
         elif ch == "g":
             gn = spec.groupnorm
@@ -112,7 +117,7 @@ def single_conv_fwd(x: CL, spec: LayerSpec, training: bool, tape: Optional[list]
                 dst = cur.new_like_padded()
             y = ops.gn_apply(cur, gn.num_groups, stats, gamma, beta, fuse_relu, out=dst)
             if tape is not None:
-                tape.append(("gn", cur, gn, stats, gamma, y if fuse_relu else None))
+                tape.append(("gn", cur, gn, stats, gamma, y if fuse_relu else None, in_relu and i == 0))
             cur = y
         elif ch == "b":
             bn = spec.batchnorm
@@ -123,27 +128,34 @@ def single_conv_fwd(x: CL, spec: LayerSpec, training: bool, tape: Optional[list]
                 dst = cur.new_like_padded()
             y = ops.bn_apply(cur, mean, rstd, gamma, beta, fuse_relu, out=dst)
             if tape is not None:
-                tape.append(("bn", cur, bn, mean, rstd, gamma, y if fuse_relu else None, training))
+                tape.append(("bn", cur, bn, mean, rstd, gamma, y if fuse_relu else None, training,
+                             in_relu and i == 0))
             cur = y
         elif ch == "r":  # a ReLU that could not be fused into its producer (first letter never is)
             raise NotImplementedError(f"unfusable ReLU position in layer_order {letters!r}")
+        out_relu = fuse_relu
         i = nxt
     if out is not None and cur is not out:
         ops.copy_channels(cur, out)
         cur = out
-    return cur
+    return cur, out_relu
 
 
-def single_conv_bwd(dy: CL, recs: list, grads: Grads, need_dx: bool = True) -> Optional[CL]:
-    """Backward of one layer: consumes the layer's tape records (in reverse); dy may be clobbered."""
+def single_conv_bwd(dy: CL, recs: list, grads: Grads, need_dx: bool = True, premasked: bool = False):
+    """Backward of one layer: consumes the layer's tape records (in reverse); dy may be clobbered.
+    ``premasked``: dy already carries the ReLU backward of this layer's final ReLU (its producer fused
+    it).  Returns (dx, dx_premasked) where dx_premasked says dx carries the ReLU backward of the layer
+    that produced this layer's input."""
+    out_premasked = False
     for idx in range(len(recs) - 1, -1, -1):
         rec = recs[idx]
         kind = rec[0]
         last = idx == 0
+        pm = premasked and idx == len(recs) - 1
         if kind == "conv":
-            _, x_in, conv, wp_bwd, k, y_relu, zpad = rec
+            _, x_in, conv, wp_bwd, k, y_relu, zpad, mask_in = rec
             has_bias = conv.bias is not None and conv.bias.requires_grad
-            if y_relu is not None:
+            if y_relu is not None and not pm:
                 dy, db = ops.relu_bwd(dy, y_relu, has_bias, out=dy)
             else:
                 db = ops.bias_grad(dy) if has_bias else None
@@ -157,44 +169,56 @@ def single_conv_bwd(dy: CL, recs: list, grads: Grads, need_dx: bool = True) -> O
                     dw = dw[:, :conv.weight.shape[1]].contiguous()
                 _acc(grads, conv.weight, dw)
             if last and not need_dx:
-                return None
-            dy = ops.conv_bwd_data(dy, wp_bwd, k, impl=IMPL)
+                return None, False
+            # the fused mask must have the layout of the (dense) dx the kernel writes
+            fuse = bool(mask_in and not zpad and x_in.is_full())
+            dy = ops.conv_bwd_data(dy, wp_bwd, k, mask=x_in if fuse else None, impl=IMPL)
+            out_premasked = fuse
             if zpad:  # gradient w.r.t. the padding channels is meaningless: expose the real slice
                 dy = CL(dy.buf, dy.c - zpad, 0, zpad)
         elif kind == "gn":
-            _, x_in, gn, stats, gamma, y_relu = rec
-            if y_relu is not None:
+            _, x_in, gn, stats, gamma, y_relu, mask_in = rec
+            if y_relu is not None and not pm:
                 dy, _ = ops.relu_bwd(dy, y_relu, False, out=dy)
-            dx, dgamma, dbeta = ops.gn_bwd(x_in, gn.num_groups, stats, gamma, dy)
+            dx, dgamma, dbeta = ops.gn_bwd(x_in, gn.num_groups, stats, gamma, dy, mask_relu=mask_in)
             _acc(grads, gn.weight, dgamma)
             _acc(grads, gn.bias, dbeta)
             dy = dx
+            out_premasked = bool(mask_in)
         elif kind == "bn":
-            _, x_in, bn, mean, rstd, gamma, y_relu, was_training = rec
+            _, x_in, bn, mean, rstd, gamma, y_relu, was_training, mask_in = rec
             # eval-mode BN (frozen statistics) is a per-channel affine map: no mean/variance terms
-            dx, dgamma, dbeta = ops.bn_bwd(x_in, dy, y_relu, mean, rstd, gamma, frozen=not was_training)
+            dx, dgamma, dbeta = ops.bn_bwd(x_in, dy, None if pm else y_relu, mean, rstd, gamma,
+                                           frozen=not was_training, mask_relu=mask_in)
             _acc(grads, bn.weight, dgamma)
             _acc(grads, bn.bias, dbeta)
             dy = dx
-    return dy
+            out_premasked = bool(mask_in)
+    return dy, out_premasked
 
 
 def block_fwd(x: CL, specs: List[LayerSpec], training: bool, tape: Optional[list],
-              out: Optional[CL] = None) -> CL:
-    """A DoubleConv / DoubleConvolution / unetConv2: consecutive layers, last one writes ``out``."""
+              out: Optional[CL] = None, in_relu: bool = False):
+    """A DoubleConv / DoubleConvolution / unetConv2: consecutive layers, last one writes ``out``.
+    Returns (y, y_is_relu_output)."""
+    flag = in_relu
     for j, spec in enumerate(specs):
         sub = [] if tape is not None else None
-        x = single_conv_fwd(x, spec, training, sub, out=out if j == len(specs) - 1 else None)
+        x, flag = single_conv_fwd(x, spec, training, sub, out=out if j == len(specs) - 1 else None,
+                                  in_relu=flag)
         if tape is not None:
             tape.append(sub)
-    return x
+    return x, flag
 
 
-def block_bwd(dy: CL, tape: list, nlayers: int, grads: Grads, need_dx: bool = True) -> Optional[CL]:
+def block_bwd(dy: CL, tape: list, nlayers: int, grads: Grads, need_dx: bool = True,
+              premasked: bool = False):
+    """Returns (dx, dx_premasked) — see single_conv_bwd."""
+    pm = premasked
     for j in range(nlayers):
         recs = tape.pop()
-        dy = single_conv_bwd(dy, recs, grads, need_dx=need_dx or j < nlayers - 1)
-    return dy
+        dy, pm = single_conv_bwd(dy, recs, grads, need_dx=need_dx or j < nlayers - 1, premasked=pm)
+    return dy, pm
 
 
 # ===================================================================================== 2D U-Net
@@ -215,6 +239,7 @@ def unet2d_forward(net, images: torch.Tensor, training: bool, tape: Optional[lis
     x = ops.from_nchw(images, pad=True)
     n_lvl = len(net.down_conv)
     skips: List[CL] = []
+    relu = False          # is x a ReLU output?  (lets backward fold ReLU' into its neighbours)
     for i in range(n_lvl):
         c = net.down_conv[i].second.out_channels
         if x.h % 2 == 0 and x.w % 2 == 0 and _fits_after(x.h, x.w, n_lvl - i):
@@ -222,10 +247,10 @@ def unet2d_forward(net, images: torch.Tensor, training: bool, tape: Optional[lis
             dst = cat.slice(c, c)
         else:  # odd sizes need the centre crop of CropAndConcat: keep the skip in its own buffer
             dst = None
-        x = block_fwd(x, unet2d_specs(net.down_conv[i]), training, tape, out=dst)
+        x, relu = block_fwd(x, unet2d_specs(net.down_conv[i]), training, tape, out=dst, in_relu=relu)
         skips.append(x)
         x = ops.maxpool_fwd(x, 1)
-    x = block_fwd(x, unet2d_specs(net.middle_conv), training, tape)
+    x, relu = block_fwd(x, unet2d_specs(net.middle_conv), training, tape, in_relu=relu)
     for i in range(n_lvl):
         skip = skips[n_lvl - 1 - i]
         up = net.up_sample[i].up
@@ -243,10 +268,11 @@ def unet2d_forward(net, images: torch.Tensor, training: bool, tape: Optional[lis
             crop = (top, left)
         ops.convt_fwd(x, wp_fwd, bias, out=cat.slice(0, c), impl=IMPL)
         if tape is not None:
-            tape.append(("up", x, up, wp_bwd, c, crop, skip))
-        x = block_fwd(cat, unet2d_specs(net.up_conv[i]), training, tape)
+            tape.append(("up", x, up, wp_bwd, c, crop, skip, relu))
+        # the concat mixes a ConvTranspose output with a ReLU output: not maskable as a whole
+        x, relu = block_fwd(cat, unet2d_specs(net.up_conv[i]), training, tape, in_relu=False)
     if tape is not None:
-        tape.append(("skips", skips))
+        tape.append(("skips", skips, relu))
     return x
 
 
@@ -260,14 +286,14 @@ def _fits_after(h: int, w: int, levels_left: int) -> bool:
     return True
 
 
-def unet2d_backward(net, tape: list, dfeat: CL, grads: Grads) -> None:
+def unet2d_backward(net, tape: list, dfeat: CL, grads: Grads, premasked: bool) -> None:
     n_lvl = len(net.down_conv)
-    _, skips = tape.pop()
+    _, skips, _ = tape.pop()
     dskips: List[Optional[CL]] = [None] * n_lvl
-    d = dfeat
+    d, pm = dfeat, premasked
     for i in range(n_lvl - 1, -1, -1):
-        dcat = block_bwd(d, tape, 2, grads)
-        _, x_in, up, wp_bwd, c, crop, skip = tape.pop()
+        dcat, _ = block_bwd(d, tape, 2, grads, premasked=pm)
+        _, x_in, up, wp_bwd, c, crop, skip, x_relu = tape.pop()
         d_up = dcat.slice(0, c)
         if crop is None:
             dskips[n_lvl - 1 - i] = dcat.slice(c, skip.c)
@@ -279,11 +305,14 @@ def unet2d_backward(net, tape: list, dfeat: CL, grads: Grads) -> None:
         if up.bias is not None:
             _acc(grads, up.bias, ops.bias_grad(d_up))
         _acc(grads, up.weight, ops.convt_bwd_weight(x_in, d_up, impl=IMPL))
-        d = ops.convt_bwd_data(d_up, wp_bwd, impl=IMPL)
-    d = block_bwd(d, tape, 2, grads)
+        fuse = bool(x_relu and x_in.is_full())
+        d = ops.convt_bwd_data(d_up, wp_bwd, mask=x_in if fuse else None, impl=IMPL)
+        pm = fuse
+    d, pm = block_bwd(d, tape, 2, grads, premasked=pm)
     for i in range(n_lvl - 1, -1, -1):
-        d = ops.maxpool_bwd(skips[i], d, 1, add=dskips[i])
-        d = block_bwd(d, tape, 2, grads, need_dx=i > 0)
+        # skips are ReLU outputs of DoubleConvolution: fold their ReLU backward into the pool backward
+        d = ops.maxpool_bwd(skips[i], d, 1, add=dskips[i], mask_relu=True)
+        d, pm = block_bwd(d, tape, 2, grads, need_dx=i > 0, premasked=True)
 
 
 # ===================================================================================== 3D family
@@ -304,11 +333,13 @@ def unet3d_forward(net, x_in: torch.Tensor, training: bool, tape: Optional[list]
     x = ops.from_nchw(x_in, pad=True)
     n_enc = len(net.encoders)
     skips: List[CL] = []
+    relu = False
+    skip_relu: List[bool] = []
     for i, enc in enumerate(net.encoders):
         if enc.pooling is not None:
             pooled = ops.maxpool_fwd(x, 2 if is3d else 1)
             if tape is not None:
-                tape.append(("pool", x))
+                tape.append(("pool", x, relu))
             x = pooled
         cs = enc.basic_module.SingleConv2.conv.out_channels
         dst = None
@@ -316,8 +347,10 @@ def unet3d_forward(net, x_in: torch.Tensor, training: bool, tape: Optional[list]
             cx = _decoder_up_channels(net, n_enc - 2 - i)
             cat = CL.empty(x.n, x.d, x.h, x.w, cs + cx, x.device)
             dst = cat.slice(0, cs)
-        x = block_fwd(x, double_conv_specs(enc.basic_module, order), training, tape, out=dst)
+        x, relu = block_fwd(x, double_conv_specs(enc.basic_module, order), training, tape, out=dst,
+                            in_relu=relu)
         skips.append(x)
+        skip_relu.append(relu)
     for j, dec in enumerate(net.decoders):
         skip = skips[n_enc - 2 - j]
         cat = CL(skip.buf)
@@ -331,13 +364,16 @@ def unet3d_forward(net, x_in: torch.Tensor, training: bool, tape: Optional[list]
             ops.deconv_resize_fwd(planes, x.n, kd, size, out=up_dst)
             if tape is not None:
                 tape.append(("deconv", x, ct, wp_bwd, kd, skip.c, cx))
+            cat_relu = False      # the transposed conv has no activation
         else:
             ops.upsample_nearest_fwd(x, size, out=up_dst)
             if tape is not None:
                 tape.append(("nearest", (x.d, x.h, x.w), skip.c, cx))
-        x = block_fwd(cat, double_conv_specs(dec.basic_module, order), training, tape)
+            cat_relu = relu and skip_relu[n_enc - 2 - j]   # both halves are ReLU outputs
+        x, relu = block_fwd(cat, double_conv_specs(dec.basic_module, order), training, tape,
+                            in_relu=cat_relu)
     if tape is not None:
-        tape.append(("skips", skips))
+        tape.append(("skips", skips, relu))
     return x
 
 
@@ -352,14 +388,15 @@ def _decoder_up_channels(net, j: int) -> int:
     return c_in - skip_c
 
 
-def unet3d_backward(net, tape: list, dfeat: CL, grads: Grads) -> None:
+def unet3d_backward(net, tape: list, dfeat: CL, grads: Grads, premasked: bool) -> None:
     is3d = net.is3d
     n_enc = len(net.encoders)
-    _, skips = tape.pop()
+    _, skips, _ = tape.pop()
     dskips: List[Optional[CL]] = [None] * n_enc
-    d = dfeat
+    d, pm = dfeat, premasked
     for j in range(len(net.decoders) - 1, -1, -1):
-        dcat = block_bwd(d, tape, 2, grads)
+        dcat, cat_pm = block_bwd(d, tape, 2, grads, premasked=pm)
+        pm = False   # up-sampling backward sums children: the result is not a masked gradient
         rec = tape.pop()
         if rec[0] == "deconv":
             _, x_in, ct, wp_bwd, kd, cs, cx = rec
@@ -370,13 +407,18 @@ def unet3d_backward(net, tape: list, dfeat: CL, grads: Grads) -> None:
         else:
             _, in_size, cs, cx = rec
             d = ops.upsample_nearest_bwd(dcat.slice(cs, cx), in_size)
+            # all children of a source voxel share its value, so a gradient masked by (up > 0) sums to
+            # a gradient masked by (source > 0): the ReLU backward of the producer is already in it
+            pm = cat_pm
         dskips[n_enc - 2 - j] = dcat.slice(0, cs)
     for i in range(n_enc - 1, -1, -1):
-        d = block_bwd(d, tape, 2, grads, need_dx=i > 0)
+        d, _ = block_bwd(d, tape, 2, grads, need_dx=i > 0, premasked=pm)
         if i > 0:
-            _, pre = tape.pop()
-            # the skip half of the concat gradient joins the gradient routed back through the pool
-            d = ops.maxpool_bwd(pre, d, 2 if is3d else 1, add=dskips[i - 1])
+            _, pre, pre_relu = tape.pop()
+            # the skip half of the concat gradient joins the gradient routed back through the pool;
+            # when the pooled tensor is a ReLU output its ReLU backward is folded in as well
+            d = ops.maxpool_bwd(pre, d, 2 if is3d else 1, add=dskips[i - 1], mask_relu=pre_relu)
+            pm = pre_relu
 
 
 # ===================================================================================== autograd glue
@@ -397,6 +439,7 @@ class _NetFunction(torch.autograd.Function):
             head = net.final_conv
             bias = None if head.bias is None else head.bias.detach().float().contiguous()
             logits = ops.head_fwd(feat, head.weight, bias, images.dim() == 5)
+        ctx.feat_relu = bool(tape[-1][2]) if need_grad else False
         ctx.net, ctx.kind, ctx.tape, ctx.feat = net, kind, tape, feat if need_grad else None
         ctx.params = params
         return logits
@@ -411,14 +454,14 @@ class _NetFunction(torch.autograd.Function):
         head = net.final_conv
         _REDUCER = getattr(net, "_b200_reducer", None)
         try:
-            dfeat, dw, db = ops.head_bwd(ctx.feat, head.weight, dlogits)
+            dfeat, dw, db = ops.head_bwd(ctx.feat, head.weight, dlogits, mask_relu=ctx.feat_relu)
             _acc(grads, head.weight, dw)
             if head.bias is not None:
                 _acc(grads, head.bias, db)
             if ctx.kind == "unet2d":
-                unet2d_backward(net, tape, dfeat, grads)
+                unet2d_backward(net, tape, dfeat, grads, ctx.feat_relu)
             else:
-                unet3d_backward(net, tape, dfeat, grads)
+                unet3d_backward(net, tape, dfeat, grads, ctx.feat_relu)
             if _REDUCER is not None:
                 _REDUCER.finish()
         finally:
@@ -443,7 +486,7 @@ class _BlockFunction(torch.autograd.Function):
         need_grad = any(ctx.needs_input_grad)
         tape = [] if need_grad else None
         with torch.no_grad():
-            y = block_fwd(ops.from_nchw(x), specs, mod.training, tape)
+            y, _ = block_fwd(ops.from_nchw(x), specs, mod.training, tape)
             out = ops.to_nchw(y, x.dim() == 5)
         ctx.tape, ctx.n, ctx.params, ctx.x_grad = tape, len(specs), params, ctx.needs_input_grad[2]
         return out
@@ -452,7 +495,7 @@ class _BlockFunction(torch.autograd.Function):
     def backward(ctx, dout):
         grads: Grads = {}
         dy = ops.from_nchw(dout)
-        dx = block_bwd(dy, ctx.tape, ctx.n, grads, need_dx=ctx.x_grad)
+        dx, _ = block_bwd(dy, ctx.tape, ctx.n, grads, need_dx=ctx.x_grad)
         gx = ops.to_nchw(dx, dout.dim() == 5) if ctx.x_grad else None
         return (None, None, gx) + tuple(grads.get(p) if p.requires_grad else None for p in ctx.params)
 

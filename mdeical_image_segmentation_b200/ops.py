@@ -277,11 +277,11 @@ def maxpool_fwd(x: CL, pool_d: int, out: Optional[CL] = None) -> CL:
 
 
 def maxpool_bwd(x: CL, dy: CL, pool_d: int, add: Optional[CL] = None,
-                out: Optional[CL] = None) -> CL:
+                out: Optional[CL] = None, mask_relu: bool = False) -> CL:
     if out is None:
         out = x.new_like()
     call("b200_maxpool2_bwd", x.n, x.d, x.h, x.w, x.c, pool_d, x.view(), dy.view(),
-         _NULL_VIEW if add is None else add.view(), out.view(), _stream())
+         _NULL_VIEW if add is None else add.view(), out.view(), int(mask_relu), _stream())
     return out
 
 
@@ -365,14 +365,14 @@ def gn_apply(x: CL, groups, stats, gamma, beta, relu: bool, out: Optional[CL] = 
     return out
 
 
-def gn_bwd(x: CL, groups, stats, gamma, dy: CL, out: Optional[CL] = None):
+def gn_bwd(x: CL, groups, stats, gamma, dy: CL, out: Optional[CL] = None, mask_relu: bool = False):
     if out is None:
         out = x.new_like()
     dgamma = torch.zeros(x.c, dtype=torch.float32, device=x.device)
     dbeta = torch.zeros(x.c, dtype=torch.float32, device=x.device)
     scratch = torch.zeros(x.n * x.c * 2 + x.n * groups * 2, dtype=torch.float32, device=x.device)
     call("b200_gn_bwd", x.n, x.spatial, x.c, groups, x.view(), _p(stats), _p(gamma), dy.view(),
-         out.view(), _p(dgamma), _p(dbeta), _p(scratch), _stream())
+         out.view(), _p(dgamma), _p(dbeta), _p(scratch), int(mask_relu), _stream())
     return out, dgamma, dbeta
 
 
@@ -391,7 +391,7 @@ def bn_apply(x: CL, mean, rstd, gamma, beta, relu: bool, out: Optional[CL] = Non
 
 
 def bn_bwd(x: CL, dy: CL, relu_out: Optional[CL], mean, rstd, gamma, out: Optional[CL] = None,
-           frozen: bool = False):
+           frozen: bool = False, mask_relu: bool = False):
     if out is None:
         out = x.new_like()
     red = torch.zeros((2, x.c), dtype=torch.float32, device=x.device)
@@ -401,7 +401,7 @@ def bn_bwd(x: CL, dy: CL, relu_out: Optional[CL], mean, rstd, gamma, out: Option
     # frozen statistics (eval-mode BN): the batch-mean / batch-variance terms vanish
     red_apply = torch.zeros_like(red) if frozen else red
     call("b200_bn_bwd_apply", x.npos, x.c, x.view(), dy.view(), rv, _p(mean), _p(rstd), _p(gamma),
-         _p(red_apply), out.view(), _stream())
+         _p(red_apply), out.view(), int(mask_relu), _stream())
     # dbeta = sum dz, dgamma = sum dz * xhat
     return out, red[1].clone(), red[0].clone()
 
@@ -416,7 +416,8 @@ def head_fwd(x: CL, w: torch.Tensor, b: Optional[torch.Tensor], is3d: bool) -> t
     return logits
 
 
-def head_bwd(x: CL, w: torch.Tensor, dlogits: torch.Tensor, need_dx: bool = True):
+def head_bwd(x: CL, w: torch.Tensor, dlogits: torch.Tensor, need_dx: bool = True,
+             mask_relu: bool = False):
     c_out = w.shape[0]
     w2 = w.detach().reshape(c_out, -1).contiguous().float()
     dlogits = dlogits.contiguous().float()
@@ -424,7 +425,7 @@ def head_bwd(x: CL, w: torch.Tensor, dlogits: torch.Tensor, need_dx: bool = True
     dw = torch.zeros((c_out, x.c), dtype=torch.float32, device=x.device)
     db = torch.zeros(c_out, dtype=torch.float32, device=x.device)
     call("b200_head_bwd", x.n, x.spatial, x.c, c_out, x.view(), _p(w2), _p(dlogits),
-         _NULL_VIEW if dx is None else dx.view(), _p(dw), _p(db), _stream())
+         _NULL_VIEW if dx is None else dx.view(), _p(dw), _p(db), int(mask_relu), _stream())
     return dx, dw.reshape(w.shape), db
 
 
