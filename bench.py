@@ -287,11 +287,15 @@ def run_b200(args, w):
     # ---- roofline: one instrumented step with per-call CUDA events on the launching stream
     pk = peaks()
     roofline, breakdown = None, None
+    # every rank runs the instrumented step (its backward contains the gradient all-reduce, so a
+    # rank-0-only step would wait for peers forever); only rank 0 records and reports
+    prof = KernelProfiler()
     if rank == 0:
-        prof = KernelProfiler()
         _lib.profile_hook = prof.hook
-        one_step(x, y)
-        _lib.profile_hook = None
+    one_step(x, y)
+    _lib.profile_hook = None
+    barrier()
+    if rank == 0:
         fam = prof.summarize()
         total_ms = sum(f["ms"] for f in fam.values())
         breakdown = {k: {"ms": round(f["ms"], 3), "share": round(f["ms"] / total_ms, 4),
