@@ -36,7 +36,8 @@ const char* b200_strerror(int code);
 /* last tcgen05/direct decision taken by a conv-like entry point on this thread (1 or 2) */
 int b200_last_impl(void);
 /* tuning / A-B knobs (process-wide): key 0 = halo-reuse fwd/dgrad kernel,
- * key 1 = halo-reuse weight-gradient kernel; value 1 = on (default), 0 = off */
+ * key 1 = halo-reuse weight-gradient kernel (value 1 = on (default), 0 = off),
+ * key 2 = max row-blocks per super-tile of the halo kernel (1, 2 or 4; default 4) */
 int b200_set_tuning(int key, int value);
 
 /* ---- 3x3 / 3x3x3 / 1x1 "same" convolution ------------------------------------------------------

@@ -6,6 +6,7 @@
 namespace b200 {
 extern int g_halo_mode;
 extern int g_wgrad_halo_mode;
+extern int g_halo_rmax;
 int direct_gemm_conv(const TcGemmProblem& p, cudaStream_t stream);
 int direct_wgrad(const TcWgradProblem& p, cudaStream_t stream);
 static thread_local int g_last_impl = 0;
@@ -148,6 +149,7 @@ int b200_last_impl(void) { return g_last_impl; }
 int b200_set_tuning(int key, int value) {
   if (key == 0) { b200::g_halo_mode = value; return B200_OK; }
   if (key == 1) { b200::g_wgrad_halo_mode = value; return B200_OK; }
+  if (key == 2) { b200::g_halo_rmax = value; return B200_OK; }
   return B200_ERR_BAD_ARG;
 }
 

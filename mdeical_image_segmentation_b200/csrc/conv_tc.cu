@@ -303,6 +303,8 @@ struct HaloArgs {
   int tiles_h, tiles_w, m_tiles, n_tiles, total;
   int kd;                // 1 or 3 depth taps (kh = kw = 3)
   int kchunks, kdim, BN;
+  int R;                 // 16x8 row-blocks per super-tile (1, 2 or 4): R accumulators share each weight slab
+  int halo_h;            // 16 R + 2
   int a_stage_bytes, a_stages, b_slots;
   int G;                 // taps per weight slot (3 = one kw row per TMA box, or 1)
   bf16* out;
@@ -313,6 +315,10 @@ struct HaloArgs {
   int mask_ctot, mask_coff;
 };
 
+// Super-tile = 1 x (16 R) x 8 output positions of one depth plane.  A stage = the halo of ONE input plane
+// (10 x (16R+2) positions x 64 channels); a weight slot = G taps; each weight slab is applied to all R
+// row-blocks (R accumulators in TMEM), which divides the weight traffic — the limiter of narrow-C_out
+// layers once the activations are halo-shared — by R.
 __global__ void __launch_bounds__(256, 1)
     tc_gemm_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                         const HaloArgs p) {
@@ -320,8 +326,8 @@ __global__ void __launch_bounds__(256, 1)
   const uint32_t sraw = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (sraw & 1023u)) & 1023u);
   uint64_t* afull = reinterpret_cast<uint64_t*>(smem);
-  uint64_t* aempty = afull + 4;
-  uint64_t* bfull = aempty + 4;
+  uint64_t* aempty = afull + 8;
+  uint64_t* bfull = aempty + 8;
   uint64_t* bempty = bfull + 16;
   uint64_t* tfull = bempty + 16;
   uint64_t* tempty = tfull + 2;
@@ -331,6 +337,7 @@ __global__ void __launch_bounds__(256, 1)
   const int tap_bytes = p.BN * 128;
   const int b_bytes = tap_bytes * p.G;
   const int ntaps = p.kd * 9;
+  const int thl = p.R == 4 ? 6 : (p.R == 2 ? 5 : 4);   // log2(16 R)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
@@ -342,7 +349,7 @@ __global__ void __launch_bounds__(256, 1)
     fence_barrier_init();
   }
   uint32_t tmem_cols = 32;
-  while (tmem_cols < (uint32_t)(2 * p.BN)) tmem_cols <<= 1;
+  while (tmem_cols < (uint32_t)(2 * p.R * p.BN)) tmem_cols <<= 1;
   if (warp == 2) tmem_alloc(tmem_slot, tmem_cols);
   tc_fence_before();
   __syncthreads();
@@ -350,23 +357,24 @@ __global__ void __launch_bounds__(256, 1)
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ---------------------------------------------------------------- A (halo) producer
+    // ---------------------------------------------------------------- A (halo plane) producer
     int stage = 0;
     uint32_t phase = 0;
-    const uint32_t halo_bytes = (uint32_t)(kHaloPlaneBytes * p.kd);
+    const uint32_t plane_bytes = (uint32_t)(kHaloW * p.halo_h * 128);
     for (int work = blockIdx.x; work < p.total; work += gridDim.x) {
       const int mt = work / p.n_tiles;
-      const TileCoord tc = decode_tile(mt, p.pd, p.tiles_h, p.tiles_w, 0, 4, 3);
-      for (int kc = 0; kc < p.kchunks; ++kc) {
-        mbar_wait(&aempty[stage], phase ^ 1);
-        if (elect_one()) {
-          mbar_arrive_expect_tx(&afull[stage], halo_bytes);
-          tma_load_5d(sA + (size_t)stage * p.a_stage_bytes, &tmA, &afull[stage], kc * 64, tc.w0 - 1,
-                      tc.h0 - 1, tc.d0 - (p.kd >> 1), tc.n);
+      const TileCoord tc = decode_tile(mt, p.pd, p.tiles_h, p.tiles_w, 0, thl, 3);
+      for (int kc = 0; kc < p.kchunks; ++kc)
+        for (int kdi = 0; kdi < p.kd; ++kdi) {
+          mbar_wait(&aempty[stage], phase ^ 1);
+          if (elect_one()) {
+            mbar_arrive_expect_tx(&afull[stage], plane_bytes);
+            tma_load_5d(sA + (size_t)stage * p.a_stage_bytes, &tmA, &afull[stage], kc * 64, tc.w0 - 1,
+                        tc.h0 - 1, tc.d0 + kdi - (p.kd >> 1), tc.n);
+          }
+          __syncwarp();
+          if (++stage == p.a_stages) { stage = 0; phase ^= 1; }
         }
-        __syncwarp();
-        if (++stage == p.a_stages) { stage = 0; phase ^= 1; }
-      }
     }
   } else if (warp == 3) {
     // ---------------------------------------------------------------- B (weights) producer
@@ -393,46 +401,48 @@ __global__ void __launch_bounds__(256, 1)
     for (int work = blockIdx.x; work < p.total; work += gridDim.x) {
       mbar_wait(&tempty[acc], acc_phase ^ 1);
       tc_fence_after();
-      const uint32_t tmem_d = tmem_base + acc * (uint32_t)p.BN;
+      const uint32_t tmem_d = tmem_base + acc * (uint32_t)(p.R * p.BN);
       for (int kc = 0; kc < p.kchunks; ++kc) {
         int nk = (p.kdim - kc * 64 + 15) >> 4;
         nk = nk > 4 ? 4 : nk;
-        mbar_wait(&afull[stage], aphase);
-        tc_fence_after();
-        // descriptors differ only in their 14-bit start-address field: build once, then add
-        const uint64_t da0 = make_smem_desc_sw128(smem_u32(sA + (size_t)stage * p.a_stage_bytes), 16,
-                                                  kHaloW * 128);
-        int tap = 0;
-        for (int kdi = 0; kdi < p.kd; ++kdi)
+        for (int kdi = 0; kdi < p.kd; ++kdi) {
+          mbar_wait(&afull[stage], aphase);
+          tc_fence_after();
+          // descriptors differ only in their 14-bit start-address field: build once, then add
+          const uint64_t da0 = make_smem_desc_sw128(smem_u32(sA + (size_t)stage * p.a_stage_bytes), 16,
+                                                    kHaloW * 128);
           for (int khi = 0; khi < 3; ++khi) {
-            const uint64_t da_row = da0 + (uint64_t)(((kdi * kHaloH + khi) * kHaloW * 128) >> 4);
-            for (int kwi = 0; kwi < 3; ++kwi, ++tap) {
+            for (int kwi = 0; kwi < 3; ++kwi) {
+              const int tap = (kdi * 3 + khi) * 3 + kwi;
               const int sub = p.G == 3 ? kwi : 0;
               if (sub == 0) {
                 mbar_wait(&bfull[slot], bphase);
                 tc_fence_after();
               }
               const bool last_of_slot = sub == p.G - 1;
-              const bool last_tap = tap == ntaps - 1;
+              const bool last_of_plane = khi == 2 && kwi == 2;
               if (elect_one()) {
-                const uint64_t da = da_row + (uint64_t)(kwi * 8);
                 const uint64_t db = make_smem_desc_sw128(
                     smem_u32(sB + (size_t)slot * b_bytes + (size_t)sub * tap_bytes), 16, 1024);
+                for (int r = 0; r < p.R; ++r) {
+                  const uint64_t da = da0 + (uint64_t)((((r * 16 + khi) * kHaloW + kwi) * 128) >> 4);
 #pragma unroll 4
-                for (int k = 0; k < nk; ++k)
-                  umma_bf16(tmem_d, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc,
-                            (kc | tap | k) != 0);
+                  for (int k = 0; k < nk; ++k)
+                    umma_bf16(tmem_d + r * p.BN, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc,
+                              (kc | tap | k) != 0);
+                }
                 if (last_of_slot) umma_commit(&bempty[slot]);
-                if (last_tap) {
+                if (last_of_plane) {
                   umma_commit(&aempty[stage]);
-                  if (kc == p.kchunks - 1) umma_commit(&tfull[acc]);
+                  if (kc == p.kchunks - 1 && kdi == p.kd - 1) umma_commit(&tfull[acc]);
                 }
               }
               __syncwarp();
               if (last_of_slot && ++slot == p.b_slots) { slot = 0; bphase ^= 1; }
             }
           }
-        if (++stage == p.a_stages) { stage = 0; aphase ^= 1; }
+          if (++stage == p.a_stages) { stage = 0; aphase ^= 1; }
+        }
       }
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
@@ -444,55 +454,58 @@ __global__ void __launch_bounds__(256, 1)
     uint32_t acc = 0, acc_phase = 0;
     for (int work = blockIdx.x; work < p.total; work += gridDim.x) {
       const int mt = work / p.n_tiles, nt = work - mt * p.n_tiles;
-      const TileCoord tc = decode_tile(mt, p.pd, p.tiles_h, p.tiles_w, 0, 4, 3);
+      const TileCoord tc = decode_tile(mt, p.pd, p.tiles_h, p.tiles_w, 0, thl, 3);
       const int wx = tc.w0 + (row & 7);
-      const int hy = tc.h0 + (row >> 3);
-      const bool valid = (wx < p.pw) && (hy < p.ph);
-      const long opos = (((long)tc.n * p.pd + tc.d0) * p.ph + hy) * p.pw + wx;
       const int ocol0 = nt * p.BN;
-      bf16* orow = p.out + opos * p.out_ctot + p.out_coff + ocol0;
-      const bf16* mrow = p.mask ? p.mask + opos * p.mask_ctot + p.mask_coff + ocol0 : nullptr;
       const float* brow = p.bias ? p.bias + ocol0 : nullptr;
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * (uint32_t)p.BN;
-      for (int c0 = 0; c0 < p.BN; c0 += 16) {
-        uint32_t v[16];
-        tmem_ld16(taddr + c0, v);
-        tmem_ld_wait();
-        if (valid) {
-          float f[16];
+      for (int r = 0; r < p.R; ++r) {
+        const int hy = tc.h0 + r * 16 + (row >> 3);
+        const bool valid = (wx < p.pw) && (hy < p.ph);
+        const long opos = (((long)tc.n * p.pd + tc.d0) * p.ph + hy) * p.pw + wx;
+        bf16* orow = p.out + opos * p.out_ctot + p.out_coff + ocol0;
+        const bf16* mrow = p.mask ? p.mask + opos * p.mask_ctot + p.mask_coff + ocol0 : nullptr;
+        const uint32_t taddr =
+            tmem_base + ((uint32_t)(q * 32) << 16) + (acc * (uint32_t)p.R + r) * (uint32_t)p.BN;
+        for (int c0 = 0; c0 < p.BN; c0 += 16) {
+          uint32_t v[16];
+          tmem_ld16(taddr + c0, v);
+          tmem_ld_wait();
+          if (valid) {
+            float f[16];
 #pragma unroll
-          for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
-          if (brow) {
+            for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
+            if (brow) {
 #pragma unroll
-            for (int j = 0; j < 16; j += 4) {
-              const float4 b4 = __ldg(reinterpret_cast<const float4*>(brow + c0 + j));
-              f[j] += b4.x; f[j + 1] += b4.y; f[j + 2] += b4.z; f[j + 3] += b4.w;
+              for (int j = 0; j < 16; j += 4) {
+                const float4 b4 = __ldg(reinterpret_cast<const float4*>(brow + c0 + j));
+                f[j] += b4.x; f[j + 1] += b4.y; f[j + 2] += b4.z; f[j + 3] += b4.w;
+              }
             }
-          }
-          if (p.relu) {
+            if (p.relu) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
-          }
-          if (mrow) {
-            const uint4 m0 = *reinterpret_cast<const uint4*>(mrow + c0);
-            const uint4 m1 = *reinterpret_cast<const uint4*>(mrow + c0 + 8);
-            const uint32_t mw[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float2 mv = unpack_bf16x2(mw[j]);
-              if (!(mv.x > 0.f)) f[2 * j] = 0.f;
-              if (!(mv.y > 0.f)) f[2 * j + 1] = 0.f;
+              for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
             }
+            if (mrow) {
+              const uint4 m0 = *reinterpret_cast<const uint4*>(mrow + c0);
+              const uint4 m1 = *reinterpret_cast<const uint4*>(mrow + c0 + 8);
+              const uint32_t mw[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float2 mv = unpack_bf16x2(mw[j]);
+                if (!(mv.x > 0.f)) f[2 * j] = 0.f;
+                if (!(mv.y > 0.f)) f[2 * j + 1] = 0.f;
+              }
+            }
+            uint4 o0, o1;
+            o0.x = pack_bf16x2(f[0], f[1]);   o0.y = pack_bf16x2(f[2], f[3]);
+            o0.z = pack_bf16x2(f[4], f[5]);   o0.w = pack_bf16x2(f[6], f[7]);
+            o1.x = pack_bf16x2(f[8], f[9]);   o1.y = pack_bf16x2(f[10], f[11]);
+            o1.z = pack_bf16x2(f[12], f[13]); o1.w = pack_bf16x2(f[14], f[15]);
+            *reinterpret_cast<uint4*>(orow + c0) = o0;
+            *reinterpret_cast<uint4*>(orow + c0 + 8) = o1;
           }
-          uint4 o0, o1;
-          o0.x = pack_bf16x2(f[0], f[1]);   o0.y = pack_bf16x2(f[2], f[3]);
-          o0.z = pack_bf16x2(f[4], f[5]);   o0.w = pack_bf16x2(f[6], f[7]);
-          o1.x = pack_bf16x2(f[8], f[9]);   o1.y = pack_bf16x2(f[10], f[11]);
-          o1.z = pack_bf16x2(f[12], f[13]); o1.w = pack_bf16x2(f[14], f[15]);
-          *reinterpret_cast<uint4*>(orow + c0) = o0;
-          *reinterpret_cast<uint4*>(orow + c0 + 8) = o1;
         }
       }
       tc_fence_before();
@@ -546,27 +559,41 @@ static bool halo_eligible(const TcGemmProblem& p) {
          p.kw == 3 && (p.kd == 3 || p.kd == 1) && p.ph >= 12 && p.pw >= 8;
 }
 
+int g_halo_rmax = 4;  // tuning knob: cap on row-blocks per super-tile
+
 static int tc_gemm_halo(const TcGemmProblem& p, cudaStream_t stream) {
   HaloArgs a{};
   a.pn = p.pn; a.pd = p.pd; a.ph = p.ph; a.pw = p.pw;
-  a.tiles_h = (p.ph + 15) / 16; a.tiles_w = (p.pw + 7) / 8;
-  a.m_tiles = p.pn * p.pd * a.tiles_h * a.tiles_w;
   a.BN = pick_bn(p.ncols, 256);
   a.n_tiles = p.ncols / a.BN;
-  a.total = a.m_tiles * a.n_tiles;
   a.kd = p.kd;
   a.kdim = p.kdim; a.kchunks = (p.kdim + 63) / 64;
-  a.a_stage_bytes = ((kHaloPlaneBytes * p.kd) + 1023) / 1024 * 1024;
+  // R row-blocks share every weight slab: as many as TMEM (2 R BN <= 512 columns), the plane height and
+  // shared memory allow
+  int R = 1;
+  for (int r : {4, 2}) {
+    if (r > g_halo_rmax || 2 * r * a.BN > 512) continue;
+    if (p.ph < 16 * r - (r == 2 ? 8 : 16)) continue;              // mostly-empty super-tiles
+    const int stage = (kHaloW * (16 * r + 2) * 128 + 1023) / 1024 * 1024;
+    if (kSmemBudget - 2048 - 2 * stage < 2 * 3 * a.BN * 128) continue;
+    R = r;
+    break;
+  }
+  a.R = R;
+  a.halo_h = 16 * R + 2;
+  a.tiles_h = (p.ph + 16 * R - 1) / (16 * R); a.tiles_w = (p.pw + 7) / 8;
+  a.m_tiles = p.pn * p.pd * a.tiles_h * a.tiles_w;
+  a.total = a.m_tiles * a.n_tiles;
+  a.a_stage_bytes = (kHaloW * a.halo_h * 128 + 1023) / 1024 * 1024;
   a.a_stages = 2;
   int rem = kSmemBudget - 2048 - a.a_stages * a.a_stage_bytes;
-  if (p.kd == 1 && rem - 4 * a.BN * 128 >= 2 * a.a_stage_bytes + 64 * 1024) {  // 2D: cheap stages
-    a.a_stages = 4;
-    rem = kSmemBudget - 2048 - a.a_stages * a.a_stage_bytes;
-  }
-  // narrow N: short MMAs make the issuing thread the limiter, so fetch a whole kw row of taps per
-  // weight slot (one 3-tap TMA box, one barrier round-trip per 12 MMAs instead of per 4)
   a.G = (2 * 3 * a.BN * 128 <= rem) ? 3 : 1;
-  const int b_bytes = a.G * a.BN * 128;
+  int b_bytes = a.G * a.BN * 128;
+  // spend what is left on more activation stages first (cheap, hides TMA latency), then weight slots
+  while (a.a_stages < 6 && rem - a.a_stage_bytes >= 3 * b_bytes) {
+    ++a.a_stages;
+    rem -= a.a_stage_bytes;
+  }
   a.b_slots = rem / b_bytes;
   if (a.b_slots > 12) a.b_slots = 12;
   if (a.b_slots < 2) return B200_ERR_UNSUPPORTED;
@@ -580,7 +607,7 @@ static int tc_gemm_halo(const TcGemmProblem& p, cudaStream_t stream) {
     uint64_t dims[5] = {(uint64_t)v.c, (uint64_t)v.w, (uint64_t)v.h, (uint64_t)v.d, (uint64_t)v.n};
     uint64_t str[5] = {1, (uint64_t)v.ctot, (uint64_t)v.w * v.ctot, (uint64_t)v.h * v.w * v.ctot,
                        (uint64_t)v.d * v.h * v.w * v.ctot};
-    uint32_t box[5] = {64, (uint32_t)kHaloW, (uint32_t)kHaloH, (uint32_t)p.kd, 1};
+    uint32_t box[5] = {64, (uint32_t)kHaloW, (uint32_t)a.halo_h, 1, 1};
     int rc = make_tmap_bf16(&tmA, v.ptr + v.coff, 5, dims, str, box);
     if (rc) return rc;
   }
