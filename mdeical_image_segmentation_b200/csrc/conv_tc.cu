@@ -690,6 +690,26 @@ int tc_gemm_conv(const TcGemmProblem& p, cudaStream_t stream) {
 }
 
 // ===================================================================== weight gradient
+// split-K factor for the weight-gradient kernels: the grid is base_ctas * splits one-shot CTAs, so pick
+// the split count whose total fills whole waves of the SMs (a 2.007-wave grid costs 3 waves)
+static int pick_splits(long base_ctas, int m_tiles, int sms) {
+  long best = 1;
+  double best_score = -1.0;
+  const long max_splits = m_tiles < 512 ? m_tiles : 512;
+  for (long sp = 1; sp <= max_splits; ++sp) {
+    const long total = base_ctas * sp;
+    const long waves = (total + sms - 1) / sms;
+    if (waves > 4 && sp > 1) break;
+    const double eff = (double)total / (double)(waves * sms);          // SM occupancy of the schedule
+    const long tiles = (m_tiles + sp - 1) / sp;
+    const double work_eff = (double)m_tiles / (double)(tiles * sp);     // padding of the last split
+    const double amort = (double)tiles / (double)(tiles + 2);           // prologue/epilogue per CTA
+    const double score = eff * work_eff * amort * (waves >= 2 ? 1.0 : 0.97);
+    if (score > best_score) { best_score = score; best = sp; }
+  }
+  return (int)best;
+}
+
 // Both operands are MN-major: a [128 positions x 64 channels] TMA box is read by the tensor core
 // with the positions as the reduction (K) dimension, 16 positions per tcgen05.mma.
 struct WgradArgs {
@@ -1004,9 +1024,7 @@ static int tc_wgrad_halo(const TcWgradProblem& p, cudaStream_t stream) {
   a.stages = (kSmemBudget - 2048) / stage_bytes;
   if (a.stages > 6) a.stages = 6;
   const long base_ctas = (long)a.ciblk * a.coblk * a.kd;
-  long want = (2L * sm_count() + base_ctas - 1) / base_ctas;
-  if (want < 1) want = 1;
-  if (want > a.m_tiles) want = a.m_tiles;
+  const long want = pick_splits(base_ctas, a.m_tiles, sm_count());
   a.tiles_per_split = (int)((a.m_tiles + want - 1) / want);
   a.splits = (a.m_tiles + a.tiles_per_split - 1) / a.tiles_per_split;
   a.dw = p.dw; a.s_co = p.s_m; a.s_ci = p.s_n;
@@ -1078,9 +1096,7 @@ int tc_wgrad(const TcWgradProblem& p, cudaStream_t stream) {
   if (a.stages > 8) a.stages = 8;
   if (a.stages < 2) return B200_ERR_UNSUPPORTED;
   const long base_ctas = (long)a.mblk * a.nblk * a.tap_groups;
-  long want = (3L * sm_count() + base_ctas - 1) / base_ctas;  // ~3 waves of CTAs
-  if (want < 1) want = 1;
-  if (want > a.m_tiles) want = a.m_tiles;
+  const long want = pick_splits(base_ctas, a.m_tiles, sm_count());
   a.tiles_per_split = (int)((a.m_tiles + want - 1) / want);
   a.splits = (a.m_tiles + a.tiles_per_split - 1) / a.tiles_per_split;
   a.dw = p.dw; a.s_m = p.s_m; a.s_n = p.s_n;
