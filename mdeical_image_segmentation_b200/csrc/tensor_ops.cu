@@ -301,11 +301,12 @@ __device__ __forceinline__ void column_pass(long npos, int c, long chunk, F f, O
   const long pbeg = (long)blockIdx.x * chunk;
   const long pend = pbeg + chunk < npos ? pbeg + chunk : npos;
   if (t_row < rows && my_cv < cv) {
-#pragma unroll 4
+#pragma unroll 2
     for (long pos = pbeg + t_row; pos < pend; pos += rows) f(pos, my_cv * V, acc);
   }
   if (!DO_RED) return;
   __shared__ float sred[256 * 8];
+#pragma unroll
   for (int k = 0; k < NRED; ++k) {
     __syncthreads();
 #pragma unroll
@@ -334,7 +335,7 @@ static inline void column_grid(long npos, int c, int V, dim3& grid, long& chunk)
 }
 
 template <int V, bool MASK, bool BIAS>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
     relu_bwd_kernel(long npos, int c, long chunk, View dy, View a, View dz, float* db) {
   float* outs[1] = {db};
   auto f = [&](long pos, int ch, float(*acc)[V]) {
@@ -394,7 +395,7 @@ struct ColMap {
 
 // mode 0: GroupNorm (stats = [n][groups][2] mean/rstd), mode 1: BatchNorm (p0 = mean[c], p1 = rstd[c])
 template <int V>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
     norm_apply_kernel(long spatial, int c, int groups, long chunk, int mode, View x, const float* p0,
                       const float* p1, const float* gamma, const float* beta, int relu, View y) {
   const ColMap m(c, V);
@@ -418,13 +419,13 @@ __global__ void __launch_bounds__(256)
   const long base = (long)b * spatial;
   const long pbeg = (long)blockIdx.x * chunk;
   const long pend = pbeg + chunk < spatial ? pbeg + chunk : spatial;
-  for (long p = pbeg + m.t_row; p < pend; p += 4L * m.rows) {
-    float f[4][V];
+  for (long p = pbeg + m.t_row; p < pend; p += 2L * m.rows) {
+    float f[2][V];
 #pragma unroll
-    for (int u = 0; u < 4; ++u)
+    for (int u = 0; u < 2; ++u)
       if (p + (long)u * m.rows < pend) Vec<V>::load(x.at(base + p + (long)u * m.rows, ch), f[u]);
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < 2; ++u) {
       if (p + (long)u * m.rows < pend) {
 #pragma unroll
         for (int j = 0; j < V; ++j) {
@@ -440,7 +441,7 @@ __global__ void __launch_bounds__(256)
 // mode 0: GroupNorm backward (p0 = stats, red = gsum [n][groups][2]); mode 1: BatchNorm backward
 // (p0 = mean, p1 = rstd, red = [2][c] or NULL for frozen statistics); ro = ReLU output for masking
 template <int V>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
     norm_bwd_apply_kernel(long spatial, int c, int groups, long chunk, int mode, float inv_m, View x,
                           View dy, View ro, const float* p0, const float* p1, const float* gamma,
                           const float* red, View dx, int mask_x) {
@@ -470,10 +471,10 @@ __global__ void __launch_bounds__(256)
   const long base = (long)b * spatial;
   const long pbeg = (long)blockIdx.x * chunk;
   const long pend = pbeg + chunk < spatial ? pbeg + chunk : spatial;
-  for (long p = pbeg + m.t_row; p < pend; p += 2L * m.rows) {
-    float xv[2][V], g[2][V], o[2][V];
+  for (long p = pbeg + m.t_row; p < pend; p += 1L * m.rows) {
+    float xv[1][V], g[1][V], o[1][V];
 #pragma unroll
-    for (int u = 0; u < 2; ++u)
+    for (int u = 0; u < 1; ++u)
       if (p + (long)u * m.rows < pend) {
         const long q = base + p + (long)u * m.rows;
         Vec<V>::load(x.at(q, ch), xv[u]);
@@ -481,7 +482,7 @@ __global__ void __launch_bounds__(256)
         if (ro.p) Vec<V>::load(ro.at(q, ch), o[u]);
       }
 #pragma unroll
-    for (int u = 0; u < 2; ++u)
+    for (int u = 0; u < 1; ++u)
       if (p + (long)u * m.rows < pend) {
 #pragma unroll
         for (int j = 0; j < V; ++j) {
@@ -498,7 +499,7 @@ __global__ void __launch_bounds__(256)
 // ------------------------------------------------------------------------------------ GroupNorm
 // sums: double [n][2][c] per-sample per-channel (sum x, sum x^2); finalize folds channels -> groups
 template <int V>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
     gn_sums_kernel(long spatial, int c, long chunk, View x, double* sums) {
   const int b = blockIdx.z;
   double* outs[2] = {sums + (long)b * c * 2, sums + (long)b * c * 2 + c};
@@ -549,7 +550,7 @@ __global__ void gn_apply_kernel(int n, long spatial, int c, int groups, View x, 
 }
 // per-sample per-channel sums: s[n][c][2] = (sum dy, sum dy * xhat)
 template <int V>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
     gn_bwd_reduce_kernel(long spatial, int c, int groups, long chunk, View x, View dy,
                          const float* stats, float* s) {
   const int b = blockIdx.z;
@@ -622,7 +623,7 @@ __global__ void gn_bwd_apply_kernel(int n, long spatial, int c, int groups, View
 
 // ------------------------------------------------------------------------------------ BatchNorm
 template <int V>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
     bn_stats_kernel(long npos, int c, long chunk, View x, double* sums) {
   double* outs[2] = {sums, sums + c};
   auto f = [&](long pos, int ch, float(*acc)[V]) {
@@ -652,7 +653,7 @@ __global__ void bn_apply_kernel(long npos, int c, View x, const float* mean, con
   }
 }
 template <int V>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
     bn_bwd_reduce_kernel(long npos, int c, long chunk, View x, View dy, View ro, const float* mean,
                          const float* rstd, float* red) {
   float* outs[2] = {red, red + c};
