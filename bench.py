@@ -303,11 +303,18 @@ def run_b200(args, w):
                          **({"tflops": round(f["flops"] / f["ms"] / 1e9, 1)} if f["flops"] else {})}
                      for k, f in sorted(fam.items(), key=lambda kv: -kv[1]["ms"])}
         top = max(fam.items(), key=lambda kv: kv[1]["ms"])
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "r01_dram_traffic.json")
+        if os.path.exists(tpath):   # DRAM bytes per launch of this kernel family from the committed ncu pass
+            traffic = json.load(open(tpath)).get(args.workload, {}).get(top[0], {}).get("dram_bytes_per_launch")
         if top[1]["flops"] > 0:
             ach = top[1]["flops"] / top[1]["ms"] / 1e9
             roofline = {"kernel": top[0], "bound": "tensor", "achieved": round(ach, 1),
                         "peak": pk["tf_sustained"], "unit": "TFLOP/s",
-                        "frac": round(ach / pk["tf_sustained"], 4), "traffic": None,
+                        "frac": round(ach / pk["tf_sustained"], 4),
+                        "traffic": None if traffic is None else round(traffic),
+                        "traffic_unit": "DRAM bytes per launch (ncu, profiles/r01_dram_traffic.json)",
+                        "algorithmic_flop_per_launch": round(top[1]["flops"] / top[1]["launches"]),
                         "peak_source": pk["source"] + " (sustained cuBLAS bf16)",
                         "avg_launch_ms": round(top[1]["ms"] / top[1]["launches"], 4)}
         step_tf = w["train_tf"] * batch
