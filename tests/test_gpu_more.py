@@ -1,0 +1,223 @@
+"""More GPU parity cases: ragged / odd sizes (centre-crop, floor pooling, nearest resize to the skip's
+size), every layer_order in scope as a stand-alone block, the HF-style 3D wrapper with its double
+sigmoid, inference mode, and 2-GPU data-parallel gradient averaging."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import rel_l2
+from oracle import unet as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def B():
+    import mdeical_image_segmentation_b200 as B
+    return B
+
+
+def _sd(mod):
+    return {k: v.detach().clone() for k, v in mod.state_dict().items()}
+
+
+def test_unet2d_odd_size_center_crop(B):
+    """40x36 input: pools floor to 20x18, 10x9, 5x4, 2x2; every skip is centre-cropped to the
+    up-sampled size (CropAndConcat, layers.py:186), so the logits come out 32x32 — in the reference too."""
+    torch.manual_seed(1)
+    net = B.UNet(2, 3)
+    sd = {k: v.requires_grad_(True) for k, v in _sd(net).items()}
+    g = torch.Generator().manual_seed(2)
+    x = torch.randn((1, 2, 40, 36), generator=g)
+    y = torch.randint(0, 3, (1, 32, 32), generator=g)
+    ref = O.unet2d_forward(sd, x)
+    ref_loss = F.cross_entropy(ref, y)
+    ref_loss.backward()
+    net = net.cuda().train()
+    out = net(x.cuda())
+    loss = B.CrossEntropyLoss()(out, y.cuda())
+    loss.backward()
+    assert rel_l2(out.detach().cpu(), ref.detach()) < 1e-2
+    assert abs(loss.item() - ref_loss.item()) < 2e-3
+    ga = torch.cat([p.grad.flatten().cpu() for p in net.parameters()])
+    gb = torch.cat([sd[k].grad.flatten() for k, _ in net.named_parameters()])
+    assert rel_l2(ga, gb) < 0.2      # random init + noise (see test_gpu_parity for the strict bound)
+
+
+@pytest.mark.parametrize("order,upsample", [("gcr", "default"), ("cbr", "deconv"), ("cr", "default")])
+def test_unet3d_ragged_volume(B, order, upsample):
+    """18x20x22 volume, 3 levels: 9x10x11 -> 4x5x5 (floor), decoders resize 4->9, 9->18 etc."""
+    torch.manual_seed(3)
+    net = B.UNet3D(2, 2, f_maps=[8, 16, 32], num_groups=4, layer_order=order, upsample=upsample)
+    sd = _sd(net)
+    for k, v in sd.items():
+        if v.is_floating_point() and "running" not in k:
+            v.requires_grad_(True)
+    g = torch.Generator().manual_seed(4)
+    x = torch.randn((2, 2, 18, 20, 22), generator=g)
+    t = (torch.rand((2, 2, 18, 20, 22), generator=g) > 0.6).float()
+    kw = dict(num_levels=3, layer_order=order, num_groups=4, upsample=upsample, is3d=True)
+    ref = O.unet3d_forward(sd, x, training=True, **kw)
+    ref_loss = O.bce_dice_loss(ref, t)
+    ref_loss.backward()
+    net = net.cuda().train()
+    out = net(x.cuda())
+    loss = B.BCEDiceLoss(1.0, 1.0)(out, t.cuda())
+    loss.backward()
+    assert rel_l2(out.detach().cpu(), ref.detach()) < 1e-1     # random init + noise bound
+    assert abs(loss.item() - ref_loss.item()) < 2e-2
+    names = [k for k, _ in net.named_parameters()]
+    ga = torch.cat([p.grad.flatten().cpu() for p in net.parameters()])
+    gb = torch.cat([sd[k].grad.flatten() for k in names])
+    assert rel_l2(ga, gb) < 0.35
+
+
+@pytest.mark.parametrize("order", ["cr", "gcr", "cgr", "cbr", "bcr", "crg", "c"])
+def test_single_conv_orders_standalone(B, order):
+    torch.manual_seed(5)
+    sc = B.SingleConv(16, 32, order=order, num_groups=4, is3d=True)
+    sd = _sd(sc)
+    g = torch.Generator().manual_seed(6)
+    x = torch.randn((2, 16, 6, 8, 8), generator=g)
+    xr = x.clone().requires_grad_(True)
+    for k, v in sd.items():
+        if v.is_floating_point() and "running" not in k:
+            v.requires_grad_(True)
+    ref = O.single_conv(sd, "", xr, order, 4, True, True)
+    # random projection as the loss: sum(out^2) is invariant under the normalisation that ends 'crg'
+    # (its true gradient is ~0), which would compare rounding noise with rounding noise
+    proj = torch.randn(ref.shape, generator=g)
+    (ref * proj).sum().backward()
+    sc = sc.cuda().train()
+    xc = x.cuda().requires_grad_(True)
+    out = sc(xc)
+    (out * proj.cuda()).sum().backward()
+    assert rel_l2(out.detach().cpu(), ref.detach()) < 1e-2, order
+    # with a random projection as dy, the few outputs whose pre-activation is within bf16 rounding of
+    # zero flip their ReLU mask (measured: 49 of 12 288 elements, identical for the tcgen05 and the
+    # CUDA-core kernel) — hence 1e-1 here; trained-weight parity holds 2e-2 in test_gpu_parity.py
+    assert rel_l2(xc.grad.cpu(), xr.grad) < 1e-1, order
+    gn = np.sqrt(sum(float(v.grad.square().sum()) for v in sd.values() if v.grad is not None))
+    for k, p in sc.named_parameters():
+        err = (p.grad.cpu() - sd[k].grad).norm().item()
+        assert err < 1e-1 * sd[k].grad.norm().item() + 1e-2 * gn, (order, k, err)
+
+
+def test_unetconv2_without_batchnorm(B):
+    torch.manual_seed(7)
+    blk = B.unetConv2(8, 16, False)
+    sd = _sd(blk)
+    x = torch.randn((2, 8, 12, 12), generator=torch.Generator().manual_seed(8))
+    ref = O.unet_conv2(sd, "", x, n=2, is_batchnorm=False)
+    out = blk.cuda()(x.cuda())
+    assert rel_l2(out.detach().cpu(), ref) < 1e-2
+
+
+def test_hf_wrapper_3d_double_sigmoid(B):
+    """UNet3D.py:134-154: activation BEFORE the criterion, BCEDiceLoss applies sigmoid again (F9)."""
+    torch.manual_seed(9)
+    cfg = B.UNet3DForMedicalSegmentationConfig(in_channels=1, out_channels=1, f_maps=[8, 16], num_groups=4,
+                                               num_levels=2)
+    model = B.UNet3DForMedicalSegmentation(cfg)
+    sd = {k[len("model."):]: v.detach().clone() for k, v in model.state_dict().items()}
+    g = torch.Generator().manual_seed(10)
+    x = torch.randn((1, 1, 16, 16, 16), generator=g)
+    t = (torch.rand((1, 1, 16, 16, 16), generator=g) > 0.5).float()
+    ref_act = torch.sigmoid(O.unet3d_forward(sd, x, num_levels=2, num_groups=4, training=True))
+    ref_loss = O.bce_dice_loss(ref_act, t)
+    model = model.cuda().train()
+    out = model(volume=x.cuda(), target=t.cuda())
+    assert rel_l2(out.logits.detach().cpu(), ref_act) < 2e-2
+    assert abs(out.loss.item() - ref_loss.item()) < 2e-3
+    out.loss.backward()
+    assert all(p.grad is not None for p in model.parameters())
+
+
+def test_inference_mode_matches_training_forward_and_keeps_no_tape(B):
+    torch.manual_seed(11)
+    net = B.UNet3D(1, 2, f_maps=[8, 16, 32], num_groups=4).cuda()
+    x = torch.randn((1, 1, 16, 16, 16), device="cuda")
+    net.train()
+    a = net(x).detach()
+    net.eval()
+    with torch.no_grad():
+        b = net(x)
+    assert not b.requires_grad and b.grad_fn is None
+    assert torch.equal(a, b)          # GroupNorm has no train/eval difference; same kernels, same order
+    g = B.UNet3D(1, 1, f_maps=[8, 16], num_levels=2, layer_order="cbr").cuda().eval()
+    with torch.no_grad():
+        assert torch.isfinite(g(x)).all()
+
+
+def test_metrics_accept_cuda_tensors(B):
+    g = torch.Generator().manual_seed(12)
+    logits = torch.randn((3, 1, 20, 20), generator=g)
+    labels = (torch.rand((3, 1, 20, 20), generator=g) > 0.5).float()
+    a = B.metrics.compute_metrics((logits.cuda(), labels.cuda()))
+    b = B.metrics.compute_metrics((logits.numpy(), labels.numpy()))
+    assert a == b
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _ddp_worker(rank, world, port, q):
+    import torch.distributed as dist
+    import mdeical_image_segmentation_b200 as B
+    from mdeical_image_segmentation_b200.parallel import DataParallelUNet
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    torch.manual_seed(100 + rank)                                   # broadcast must override this
+    net = B.UNet3D(1, 1, f_maps=[8, 16, 32], num_groups=4).cuda().train()
+    DataParallelUNet(net, bucket_mb=0.05)
+    g = torch.Generator().manual_seed(50 + rank)
+    x = torch.randn((1, 1, 16, 16, 16), generator=g).cuda()
+    t = (torch.rand((1, 1, 16, 16, 16), generator=g) > 0.6).float().cuda()
+    B.BCEDiceLoss(1.0, 1.0)(net(x), t).backward()
+    torch.cuda.synchronize()
+    q.put((rank, {k: v.detach().cpu().numpy() for k, v in net.state_dict().items()},
+           {k: p.grad.cpu().numpy() for k, p in net.named_parameters()}, x.cpu().numpy(), t.cpu().numpy()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_two_gpu_gradients_are_the_rank_mean(B):
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_ddp_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = sorted([q.get(timeout=300) for _ in range(2)], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    (_, sd0, g0, x0, t0), (_, sd1, g1, x1, t1) = got
+    for k in sd0:
+        assert (sd0[k] == sd1[k]).all(), k                           # weights broadcast from rank 0
+    for k in g0:
+        assert np.allclose(g0[k], g1[k], rtol=0, atol=0), k          # both ranks hold the same mean
+    # the mean equals the single-process gradients of each shard, averaged
+    net = B.UNet3D(1, 1, f_maps=[8, 16, 32], num_groups=4)
+    net.load_state_dict({k: torch.from_numpy(v) for k, v in sd0.items()})
+    net = net.cuda().train()
+    acc = None
+    for x, t in ((x0, t0), (x1, t1)):
+        net.zero_grad()
+        B.BCEDiceLoss(1.0, 1.0)(net(torch.from_numpy(x).cuda()), torch.from_numpy(t).cuda()).backward()
+        cur = {k: p.grad.cpu().numpy() / 2 for k, p in net.named_parameters()}
+        acc = cur if acc is None else {k: acc[k] + cur[k] for k in acc}
+    for k in g0:
+        assert np.abs(g0[k] - acc[k]).max() <= 1e-6 + 1e-5 * np.abs(acc[k]).max(), k
