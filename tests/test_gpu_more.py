@@ -219,5 +219,8 @@ def test_two_gpu_gradients_are_the_rank_mean(B):
         B.BCEDiceLoss(1.0, 1.0)(net(torch.from_numpy(x).cuda()), torch.from_numpy(t).cuda()).backward()
         cur = {k: p.grad.cpu().numpy() / 2 for k, p in net.named_parameters()}
         acc = cur if acc is None else {k: acc[k] + cur[k] for k in acc}
+    # fp32 atomics (weight gradient, norm reductions) make two runs differ by a few bf16 ulps of single
+    # activations; a wrong average would be off by a factor of 2
+    gnorm = np.sqrt(sum(float((v.astype(np.float64) ** 2).sum()) for v in acc.values()))
     for k in g0:
-        assert np.abs(g0[k] - acc[k]).max() <= 1e-6 + 1e-5 * np.abs(acc[k]).max(), k
+        assert np.linalg.norm(g0[k] - acc[k]) <= 5e-3 * np.linalg.norm(acc[k]) + 1e-4 * gnorm, k
