@@ -37,7 +37,8 @@ const char* b200_strerror(int code);
 int b200_last_impl(void);
 /* tuning / A-B knobs (process-wide): key 0 = halo-reuse fwd/dgrad kernel,
  * key 1 = halo-reuse weight-gradient kernel (value 1 = on (default), 0 = off),
- * key 2 = max row-blocks per super-tile of the halo kernel (1, 2 or 4; default 4) */
+ * key 2 = max row-blocks per super-tile of the halo kernel (1, 2 or 4; default 4),
+ * key 3 = weight-resident mode of the forward / dgrad kernels (1 = on (default), 0 = off) */
 int b200_set_tuning(int key, int value);
 
 /* ---- 3x3 / 3x3x3 / 1x1 "same" convolution ------------------------------------------------------
@@ -62,6 +63,18 @@ int b200_conv_fwd(const b200_conv_desc* desc, const void* x, const void* wp_fwd,
 /* dx = conv_transpose(dy); if relu_mask != NULL (same layout as dx) dx is zeroed where mask <= 0 */
 int b200_conv_bwd_data(const b200_conv_desc* desc, const void* dy, const void* wp_bwd,
                        const void* relu_mask, void* dx, b200_stream_t stream);
+/* Fused column statistics.  The *_stats variants do the same work and additionally accumulate, in the
+ * GEMM epilogue, per-sample per-channel sums of the STORED (bf16) result into colstats fp64
+ * [n][2][channels] (caller zeroes): [.][0][c] += sum_pos r, [.][1][c] += sum_pos r*r — or
+ * sum_pos r*dot when a dot operand (bf16, positions of the result, channel layout dot_ctot/dot_coff)
+ * is given.  They replace the separate passes of the op that follows the convolution:
+ * BatchNorm / GroupNorm statistics (buildingblocks.py:73-103) in forward; the conv bias gradient and
+ * the (sum dy, sum dy*x) reductions of the norm backward in backward.  colstats == NULL: plain call. */
+int b200_conv_fwd_stats(const b200_conv_desc* desc, const void* x, const void* wp_fwd,
+                        const float* bias, void* y, double* colstats, b200_stream_t stream);
+int b200_conv_bwd_data_stats(const b200_conv_desc* desc, const void* dy, const void* wp_bwd,
+                             const void* relu_mask, void* dx, const void* dot, int32_t dot_ctot,
+                             int32_t dot_coff, double* colstats, b200_stream_t stream);
 /* dw fp32 (c_out, c_in, kd, kh, kw) is ACCUMULATED into (caller zeroes it) */
 int b200_conv_bwd_weight(const b200_conv_desc* desc, const void* x, const void* dy, float* dw,
                          b200_stream_t stream);
@@ -83,6 +96,10 @@ int b200_convt2x2_fwd(const b200_convt_desc* desc, const void* x, const void* wp
                       const float* bias, void* y, b200_stream_t stream);
 int b200_convt2x2_bwd_data(const b200_convt_desc* desc, const void* dy, const void* wp_bwd,
                            const void* relu_mask, void* dx, b200_stream_t stream);
+/* colstats fp64 [n][2][c_in] += (sum dx, sum dx*dx), see b200_conv_bwd_data_stats */
+int b200_convt2x2_bwd_data_stats(const b200_convt_desc* desc, const void* dy, const void* wp_bwd,
+                                 const void* relu_mask, void* dx, double* colstats,
+                                 b200_stream_t stream);
 int b200_convt2x2_bwd_weight(const b200_convt_desc* desc, const void* x, const void* dy, float* dw,
                              b200_stream_t stream);
 
@@ -171,6 +188,18 @@ int b200_gn_bwd(int32_t n, int64_t spatial, int32_t c, int32_t groups, b200_view
                 const float* stats, const float* gamma, b200_view dy, b200_view dx, float* dgamma,
                 float* dbeta, float* scratch, int32_t mask_relu, b200_stream_t stream);
 
+/* (mean, rstd) per (sample, group) from per-channel sums: sums fp64 [n][2][c] = (sum x, sum x^2) as
+ * produced by b200_conv_fwd_stats (or b200_gn_stats' scratch) */
+int b200_gn_stats_finalize(int32_t n, int64_t spatial, int32_t c, int32_t groups, float eps,
+                           const double* sums, float* stats, b200_stream_t stream);
+/* GroupNorm backward in ONE pass over (x, dy): the reductions come from the producer of dy —
+ * colstats fp64 [n][2][c] = (sum dy, sum dy * x) (b200_conv_bwd_data_stats with dot = x).
+ * scratch fp32 [n][groups][2]. */
+int b200_gn_bwd_fused(int32_t n, int64_t spatial, int32_t c, int32_t groups, b200_view x,
+                      const float* stats, const float* gamma, b200_view dy, b200_view dx,
+                      float* dgamma, float* dbeta, const double* colstats, float* scratch,
+                      int32_t mask_relu, b200_stream_t stream);
+
 /* ---- BatchNorm (nn.BatchNorm2d/3d, layers.py:21, buildingblocks.py:93-103) ---------------------- */
 /* sums: fp64 [2][c] = (sum x, sum x^2) accumulated into (caller zeroes) */
 int b200_bn_stats(int64_t npos, int32_t c, b200_view x, double* sums, b200_stream_t stream);
@@ -181,6 +210,10 @@ int b200_bn_apply(int64_t npos, int32_t c, b200_view x, const float* mean, const
 /* pass 1: red fp32 [2][c] += (sum dz, sum dz * xhat) with dz = dy * (y > 0 if relu_out given) */
 int b200_bn_bwd_reduce(int64_t npos, int32_t c, b200_view x, b200_view dy, b200_view relu_out,
                        const float* mean, const float* rstd, float* red, b200_stream_t stream);
+/* pass 1 replaced by fused sums: colstats fp64 [n][2][c] = (sum dz, sum dz * x) ->
+ * red fp32 [2][c] = (sum dz, rstd * (sum dz*x - mean * sum dz)) */
+int b200_bn_bwd_red_from_sums(int32_t n, int32_t c, const double* colstats, const float* mean,
+                              const float* rstd, float* red, b200_stream_t stream);
 /* pass 2: dx = gamma * rstd * (dz - red0/M - xhat * red1/M) */
 int b200_bn_bwd_apply(int64_t npos, int32_t c, b200_view x, b200_view dy, b200_view relu_out,
                       const float* mean, const float* rstd, const float* gamma, const float* red,

@@ -46,6 +46,12 @@ SIGNATURES = {
     "b200_conv_fwd": [_PC, _P, _P, _P, _P, _P],
     "b200_conv_bwd_data": [_PC, _P, _P, _P, _P, _P],
     "b200_conv_bwd_weight": [_PC, _P, _P, _P, _P],
+    "b200_conv_fwd_stats": [_PC, _P, _P, _P, _P, _P, _P],
+    "b200_conv_bwd_data_stats": [_PC, _P, _P, _P, _P, _P, _I, _I, _P, _P],
+    "b200_convt2x2_bwd_data_stats": [_PT, _P, _P, _P, _P, _P, _P],
+    "b200_gn_stats_finalize": [_I, _L, _I, _I, _F, _P, _P, _P],
+    "b200_gn_bwd_fused": [_I, _L, _I, _I, View, _P, _P, View, View, _P, _P, _P, _P, _I, _P],
+    "b200_bn_bwd_red_from_sums": [_I, _I, _P, _P, _P, _P, _P],
     "b200_convt2x2_repack_weight": [_PT, _P, _P, _P, _P],
     "b200_convt2x2_fwd": [_PT, _P, _P, _P, _P, _P],
     "b200_convt2x2_bwd_data": [_PT, _P, _P, _P, _P, _P],
@@ -134,7 +140,7 @@ def check(rc: int, what: str = "") -> None:
 
 
 # kernels launched per successful C-ABI call (for bench.py's `gpu_launches` accounting)
-LAUNCHES_PER_CALL = {"b200_gn_stats": 2, "b200_gn_bwd": 3, "b200_deconv3s2_fwd": 8}
+LAUNCHES_PER_CALL = {"b200_gn_stats": 2, "b200_gn_bwd": 3, "b200_gn_bwd_fused": 2, "b200_deconv3s2_fwd": 8}
 launch_count = 0
 # optional profiler hook: fn(name, args) -> context manager, installed by bench.py for per-kernel timing
 profile_hook = None

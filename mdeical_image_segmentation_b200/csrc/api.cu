@@ -7,6 +7,9 @@ namespace b200 {
 extern int g_halo_mode;
 extern int g_wgrad_halo_mode;
 extern int g_halo_rmax;
+extern int g_halo_resident;
+extern int g_gemm_resident;
+extern int g_epi_dbg;
 int direct_gemm_conv(const TcGemmProblem& p, cudaStream_t stream);
 int direct_wgrad(const TcWgradProblem& p, cudaStream_t stream);
 static thread_local int g_last_impl = 0;
@@ -101,12 +104,45 @@ static unsigned grid_for(long total) {
   return (unsigned)(b > 148L * 8 ? 148L * 8 : (b < 1 ? 1 : b));
 }
 
+// Stand-alone column statistics of a stored tensor (what the tcgen05 epilogues fuse): one block row per
+// sample, a thread per channel.  Only the CUDA-core fallback path uses it.
+__global__ void colstats_kernel(long spatial, int c, const bf16* out, int octot, int ocoff, const bf16* dot,
+                                int dctot, int dcoff, double* stats) {
+  const int b = blockIdx.y;
+  const long chunk = (spatial + gridDim.x - 1) / gridDim.x;
+  const long pbeg = (long)blockIdx.x * chunk;
+  const long pend = pbeg + chunk < spatial ? pbeg + chunk : spatial;
+  for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
+    float s0 = 0.f, s1 = 0.f;
+    for (long pos = pbeg; pos < pend; ++pos) {
+      const long gp = (long)b * spatial + pos;
+      const float v = __bfloat162float(out[gp * octot + ocoff + ch]);
+      const float d = dot ? __bfloat162float(dot[gp * dctot + dcoff + ch]) : v;
+      s0 += v;
+      s1 = fmaf(v, d, s1);
+    }
+    if (pend > pbeg) {
+      atomicAdd(stats + ((long)b * 2 + 0) * c + ch, (double)s0);
+      atomicAdd(stats + ((long)b * 2 + 1) * c + ch, (double)s1);
+    }
+  }
+}
+
 static int run_gemm(const TcGemmProblem& p, int impl, cudaStream_t s) {
   const bool tc_ok = tc_gemm_supported(p);
   if (impl == B200_IMPL_TCGEN05 && !tc_ok) return B200_ERR_UNSUPPORTED;
   if (impl == B200_IMPL_DIRECT || !tc_ok) {
     g_last_impl = B200_IMPL_DIRECT;
-    return direct_gemm_conv(p, s);
+    int rc = direct_gemm_conv(p, s);
+    if (rc || !p.stats) return rc;
+    if (p.out_mode != TC_OUT_CONV) return B200_ERR_UNSUPPORTED;
+    const long spatial = (long)p.pd * p.ph * p.pw;
+    long gx = spatial / 256;
+    gx = gx < 1 ? 1 : (gx > 1024 ? 1024 : gx);
+    colstats_kernel<<<dim3((unsigned)gx, (unsigned)p.pn), 128, 0, s>>>(
+        spatial, p.ncols, p.out, p.out_ctot, p.out_coff, p.dot, p.dot_ctot, p.dot_coff, p.stats);
+    B200_LAUNCH_CHECK();
+    return B200_OK;
   }
   g_last_impl = B200_IMPL_TCGEN05;
   return tc_gemm_conv(p, s);
@@ -150,6 +186,8 @@ int b200_set_tuning(int key, int value) {
   if (key == 0) { b200::g_halo_mode = value; return B200_OK; }
   if (key == 1) { b200::g_wgrad_halo_mode = value; return B200_OK; }
   if (key == 2) { b200::g_halo_rmax = value; return B200_OK; }
+  if (key == 4) { b200::g_epi_dbg = value; return B200_OK; }
+  if (key == 3) { b200::g_halo_resident = value; b200::g_gemm_resident = value; return B200_OK; }
   return B200_ERR_BAD_ARG;
 }
 
@@ -167,6 +205,10 @@ int b200_conv_repack_weight(const b200_conv_desc* d, const float* w, void* wp_fw
 
 int b200_conv_fwd(const b200_conv_desc* d, const void* x, const void* wp_fwd, const float* bias,
                   void* y, b200_stream_t stream) {
+  return b200_conv_fwd_stats(d, x, wp_fwd, bias, y, nullptr, stream);
+}
+int b200_conv_fwd_stats(const b200_conv_desc* d, const void* x, const void* wp_fwd, const float* bias,
+                        void* y, double* colstats, b200_stream_t stream) {
   int rc = check_conv(d);
   if (rc) return rc;
   TcGemmProblem p{};
@@ -178,11 +220,17 @@ int b200_conv_fwd(const b200_conv_desc* d, const void* x, const void* wp_fwd, co
   p.pn = d->n; p.pd = d->d; p.ph = d->h; p.pw = d->w;
   p.out = (bf16*)y; p.out_ctot = d->out_ctot; p.out_coff = d->out_coff;
   p.bias = bias; p.relu = d->relu;
+  p.stats = colstats;
   return run_gemm(p, d->impl, (cudaStream_t)stream);
 }
 
 int b200_conv_bwd_data(const b200_conv_desc* d, const void* dy, const void* wp_bwd,
                        const void* relu_mask, void* dx, b200_stream_t stream) {
+  return b200_conv_bwd_data_stats(d, dy, wp_bwd, relu_mask, dx, nullptr, 0, 0, nullptr, stream);
+}
+int b200_conv_bwd_data_stats(const b200_conv_desc* d, const void* dy, const void* wp_bwd,
+                             const void* relu_mask, void* dx, const void* dot, int32_t dot_ctot,
+                             int32_t dot_coff, double* colstats, b200_stream_t stream) {
   int rc = check_conv(d);
   if (rc) return rc;
   TcGemmProblem p{};
@@ -194,6 +242,9 @@ int b200_conv_bwd_data(const b200_conv_desc* d, const void* dy, const void* wp_b
   p.pn = d->n; p.pd = d->d; p.ph = d->h; p.pw = d->w;
   p.out = (bf16*)dx; p.out_ctot = d->in_ctot; p.out_coff = d->in_coff;
   p.mask = (const bf16*)relu_mask; p.mask_ctot = d->in_ctot; p.mask_coff = d->in_coff;
+  p.stats = colstats;
+  p.dot = (const bf16*)dot; p.dot_ctot = dot_ctot; p.dot_coff = dot_coff;
+  if (dot && !colstats) return B200_ERR_BAD_ARG;
   return run_gemm(p, d->impl, (cudaStream_t)stream);
 }
 
@@ -246,6 +297,11 @@ int b200_convt2x2_fwd(const b200_convt_desc* d, const void* x, const void* wp_fw
 }
 int b200_convt2x2_bwd_data(const b200_convt_desc* d, const void* dy, const void* wp_bwd,
                            const void* relu_mask, void* dx, b200_stream_t stream) {
+  return b200_convt2x2_bwd_data_stats(d, dy, wp_bwd, relu_mask, dx, nullptr, stream);
+}
+int b200_convt2x2_bwd_data_stats(const b200_convt_desc* d, const void* dy, const void* wp_bwd,
+                                 const void* relu_mask, void* dx, double* colstats,
+                                 b200_stream_t stream) {
   int rc = check_convt(d);
   if (rc) return rc;
   TcGemmProblem p{};
@@ -257,6 +313,7 @@ int b200_convt2x2_bwd_data(const b200_convt_desc* d, const void* dy, const void*
   p.pn = d->n; p.pd = 1; p.ph = d->h; p.pw = d->w;
   p.out = (bf16*)dx; p.out_ctot = d->in_ctot; p.out_coff = d->in_coff;
   p.mask = (const bf16*)relu_mask; p.mask_ctot = d->in_ctot; p.mask_coff = d->in_coff;
+  p.stats = colstats;
   return run_gemm(p, d->impl, (cudaStream_t)stream);
 }
 int b200_convt2x2_bwd_weight(const b200_convt_desc* d, const void* x, const void* dy, float* dw,

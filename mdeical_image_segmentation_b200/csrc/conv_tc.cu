@@ -89,6 +89,183 @@ __device__ __forceinline__ TileCoord decode_tile(int mt, int tiles_d, int tiles_
   return t;
 }
 
+
+// ===================================================================== epilogue (both GEMM kernels)
+// Accumulator rows live one per TMEM lane, so tcgen05.ld hands every thread one output position and 32
+// consecutive channels: storing that directly makes each warp-wide 16-byte store touch 32 different
+// 128-byte lines.  Instead each epilogue warp packs its 32 rows x 32 channels to bf16 in a private
+// 2 KB shared-memory buffer (XOR-swizzled, conflict-free) and reads it back with 4 lanes per row, so
+// a store instruction covers 8 rows x 64 contiguous bytes, the ReLU-mask / dot operands are fetched
+// with the same coalesced pattern, and a lane always owns the same 8 channels — which makes the
+// per-channel reductions that follow a convolution (bias gradient, BatchNorm / GroupNorm statistics
+// and their backward sums) a few register adds in the epilogue instead of extra passes over HBM.
+static const int kEpiStageBytes = 2048;                          // per epilogue warp: 32 rows x 64 B
+static const int kCtrlBytes = 1024 + 4 * kEpiStageBytes + 2048;  // barriers | staging | column sums
+static const int kSmemOverhead = kCtrlBytes + 1024;              // + 1024-byte alignment slack
+
+struct EpiArgs {
+  bf16* out;
+  int out_ctot, out_coff;
+  const float* bias;
+  int relu;
+  const bf16* mask;          // out = 0 where mask <= 0 (geometry of out)
+  int mask_ctot, mask_coff;
+  const bf16* dot;           // second statistic = sum out * dot instead of sum out^2
+  int dot_ctot, dot_coff;
+  double* stats;             // fp64 [pn][2][stats_cols] accumulated into, or NULL
+  int stats_cols;
+  int dbg;                   // bring-up knob (b200_set_tuning key 4): 1 = no global stores, 2 = no epilogue work
+};
+
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+__device__ __forceinline__ uint32_t bf16x2_gt0_mask(uint32_t m) {
+  const __nv_bfloat162 v = *reinterpret_cast<const __nv_bfloat162*>(&m);
+  return __hgt2_mask(v, __float2bfloat162_rn(0.f));
+}
+
+// Mask / dot operands of one chunk, fetched one chunk ahead of their use so that the global-load
+// latency hides behind the TMEM -> shared-memory staging of the previous chunk.
+struct EpiAux {
+  uint4 m[4], d[4];
+};
+__device__ __forceinline__ void epi_prefetch(const EpiArgs& e, int col, int ncol, int lane,
+                                             const long (&opos)[4], bool do_stats, EpiAux& a) {
+  if ((lane & 3) * 8 >= ncol) return;   // 16-column chunks: lanes 2,3 of each row own nothing
+  const int c = col + (lane & 3) * 8;
+  if (e.mask) {
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+      const long op = opos[it] < 0 ? 0 : opos[it];   // invalid rows read position 0 (never used)
+      a.m[it] = ldg_nc_v4(e.mask + op * e.mask_ctot + e.mask_coff + c);
+    }
+  }
+  if (e.dot && do_stats) {
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+      const long op = opos[it] < 0 ? 0 : opos[it];
+      a.d[it] = ldg_nc_v4(e.dot + op * e.dot_ctot + e.dot_coff + c);
+    }
+  }
+}
+
+// One warp, one chunk: v = 32 (or 16) accumulator columns of row `lane`; opos[it] = output position of
+// tile row (warp_row0 + it*8 + lane/4) or -1.  col = first output channel of the chunk.
+__device__ __forceinline__ void epi_chunk(const EpiArgs& e, const uint32_t (&v)[32], int ncol, int col,
+                                          uint8_t* stg, int lane, const long (&opos)[4],
+                                          float (&acc)[16], bool do_stats, const EpiAux& aux) {
+  uint32_t pk[16];
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    if (h * 16 < ncol) {
+      float f[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[h * 16 + j]);
+      if (e.bias) {
+#pragma unroll
+        for (int j = 0; j < 16; j += 4) {
+          const float4 b4 = __ldg(reinterpret_cast<const float4*>(e.bias + col + h * 16 + j));
+          f[j] += b4.x; f[j + 1] += b4.y; f[j + 2] += b4.z; f[j + 3] += b4.w;
+        }
+      }
+      if (e.relu) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) pk[h * 8 + j] = pack_bf16x2(f[2 * j], f[2 * j + 1]);
+    }
+  }
+  {
+    const int sw = (lane >> 1) & 3;
+    uint4* srow = reinterpret_cast<uint4*>(stg + lane * 64);
+    srow[0 ^ sw] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+    srow[1 ^ sw] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+    if (ncol > 16) {
+      srow[2 ^ sw] = make_uint4(pk[8], pk[9], pk[10], pk[11]);
+      srow[3 ^ sw] = make_uint4(pk[12], pk[13], pk[14], pk[15]);
+    }
+  }
+  __syncwarp();
+  const int ch = lane & 3, rsub = lane >> 2;
+  if (ch * 8 < ncol) {
+    const int c = col + ch * 8;
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+      const int rr = it * 8 + rsub;
+      uint4 u = *reinterpret_cast<const uint4*>(stg + rr * 64 + ((ch ^ ((rr >> 1) & 3)) << 4));
+      const long op = opos[it];
+      if (op >= 0) {
+        if (e.mask) {
+          const uint4 m = aux.m[it];
+          u.x &= bf16x2_gt0_mask(m.x); u.y &= bf16x2_gt0_mask(m.y);
+          u.z &= bf16x2_gt0_mask(m.z); u.w &= bf16x2_gt0_mask(m.w);
+        }
+        if (do_stats) {
+          const uint32_t uw[4] = {u.x, u.y, u.z, u.w};
+          if (e.dot) {
+            const uint4 dd = aux.d[it];
+            const uint32_t dw[4] = {dd.x, dd.y, dd.z, dd.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float2 a = unpack_bf16x2(uw[j]), b = unpack_bf16x2(dw[j]);
+              acc[2 * j] += a.x; acc[2 * j + 1] += a.y;
+              acc[8 + 2 * j] = fmaf(a.x, b.x, acc[8 + 2 * j]);
+              acc[8 + 2 * j + 1] = fmaf(a.y, b.y, acc[8 + 2 * j + 1]);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float2 a = unpack_bf16x2(uw[j]);
+              acc[2 * j] += a.x; acc[2 * j + 1] += a.y;
+              acc[8 + 2 * j] = fmaf(a.x, a.x, acc[8 + 2 * j]);
+              acc[8 + 2 * j + 1] = fmaf(a.y, a.y, acc[8 + 2 * j + 1]);
+            }
+          }
+        }
+        if (e.dbg != 1) *reinterpret_cast<uint4*>(e.out + op * e.out_ctot + e.out_coff + c) = u;
+      }
+    }
+  }
+  __syncwarp();
+}
+
+// fold the per-lane partial column sums of one chunk into the CTA's shared column sums
+__device__ __forceinline__ void epi_fold_acc(float (&acc)[16], float* colsum, int c0, int ncol, int bn,
+                                             int lane) {
+#pragma unroll
+  for (int k = 0; k < 16; ++k) {
+    float a = acc[k];
+    a += __shfl_xor_sync(0xffffffffu, a, 4);
+    a += __shfl_xor_sync(0xffffffffu, a, 8);
+    a += __shfl_xor_sync(0xffffffffu, a, 16);
+    acc[k] = a;
+  }
+  const int ch = lane & 3;
+  if ((lane >> 2) == 0 && ch * 8 < ncol) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      atomicAdd(colsum + c0 + ch * 8 + k, acc[k]);
+      atomicAdd(colsum + bn + c0 + ch * 8 + k, acc[8 + k]);
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 16; ++k) acc[k] = 0.f;
+}
+
+// all 128 epilogue threads: shared column sums [2][bn] -> global fp64 stats[n][2][stats_cols]
+__device__ __forceinline__ void epi_flush_colsum(const EpiArgs& e, float* colsum, int bn, int n, int col0,
+                                                 int tid) {
+  epi_bar();
+  for (int i = tid; i < 2 * bn; i += 128) {
+    const float v = colsum[i];
+    const int s = i >= bn, cidx = i - s * bn;
+    if (v != 0.f) atomicAdd(e.stats + ((long)n * 2 + s) * e.stats_cols + col0 + cidx, (double)v);
+    colsum[i] = 0.f;
+  }
+  epi_bar();
+}
+
 // ===================================================================== forward / dgrad GEMM
 struct GemmArgs {
   int pn, pd, ph, pw;
@@ -97,13 +274,10 @@ struct GemmArgs {
   int ntaps, kh, kw, pad_d, pad_h, pad_w;
   int tap_mode, out_mode;
   int kchunks, kdim, BN, stages;
-  bf16* out;
-  int out_ctot, out_coff;
   int cout_t;
-  const float* bias;
-  int relu;
-  const bf16* mask;
-  int mask_ctot, mask_coff;
+  int chunk;             // epilogue chunk width: 32 columns (16 when a scatter block is not a multiple of 32)
+  int b_resident;        // the CTA keeps one column tile and all its weight slabs in shared memory
+  EpiArgs e;
   int use_table;
   TapTable tt;
 };
@@ -119,8 +293,17 @@ __global__ void __launch_bounds__(256, 1)
   uint64_t* tfull = empty + 16;
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
-  uint8_t* tiles = smem + 1024;
-  const int stage_bytes = kABytes + p.BN * 128;
+  uint8_t* tiles = smem + kCtrlBytes;
+  const int b_tile_bytes = p.BN * 128;
+  const int stage_bytes = p.b_resident ? kABytes : kABytes + b_tile_bytes;
+  uint8_t* bres = tiles + (size_t)p.stages * stage_bytes;   // resident weight slabs [tap][kchunk]
+  uint64_t* bres_full = &full[15];
+  // work items: (m tile, n tile) pairs strided over the grid, or — weight-resident — the m tiles of ONE
+  // n tile per CTA (grid is a multiple of n_tiles)
+  const int wstride = p.b_resident ? (int)gridDim.x / p.n_tiles : (int)gridDim.x;
+  const int wfirst = p.b_resident ? (int)blockIdx.x / p.n_tiles : (int)blockIdx.x;
+  const int wcount = p.b_resident ? p.m_tiles : p.total;
+  const int nt_fixed = (int)blockIdx.x % p.n_tiles;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
@@ -130,6 +313,7 @@ __global__ void __launch_bounds__(256, 1)
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], 1);
     }
+    mbar_init(bres_full, 1);
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull[a], 1);
       mbar_init(&tempty[a], 128);
@@ -149,8 +333,17 @@ __global__ void __launch_bounds__(256, 1)
     // ------------------------------------------------------------------ TMA producer
     int stage = 0;
     uint32_t phase = 0;
-    for (int work = blockIdx.x; work < p.total; work += gridDim.x) {
-      const int mt = work / p.n_tiles, nt = work - mt * p.n_tiles;
+    if (p.b_resident && wfirst < wcount && elect_one()) {
+      mbar_arrive_expect_tx(bres_full, (uint32_t)(num_kb * b_tile_bytes));
+      for (int tap = 0; tap < p.ntaps; ++tap)
+        for (int kc = 0; kc < p.kchunks; ++kc)
+          tma_load_3d(bres + (size_t)(tap * p.kchunks + kc) * b_tile_bytes, &tmB, bres_full, kc * 64,
+                      nt_fixed * p.BN, p.use_table ? p.tt.widx[tap] : tap);
+    }
+    __syncwarp();
+    for (int work = wfirst; work < wcount; work += wstride) {
+      const int mt = p.b_resident ? work : work / p.n_tiles;
+      const int nt = p.b_resident ? nt_fixed : work - mt * p.n_tiles;
       const TileCoord tc = decode_tile(mt, p.tiles_d, p.tiles_h, p.tiles_w, p.tdl, p.thl, p.twl);
       for (int tap = 0; tap < p.ntaps; ++tap) {
         const int kwi = tap % p.kw, khi = (tap / p.kw) % p.kh, kdi = tap / (p.kw * p.kh);
@@ -170,7 +363,7 @@ __global__ void __launch_bounds__(256, 1)
                           tc.h0 + khi - p.pad_h, tc.d0 + kdi - p.pad_d, tc.n);
             else
               tma_load_5d(sA, &tmA, &full[stage], kc * 64, kwi, tc.w0, khi, tc.n * p.ph + tc.h0);
-            tma_load_3d(sB, &tmB, &full[stage], kc * 64, nt * p.BN, wtap);
+            if (!p.b_resident) tma_load_3d(sB, &tmB, &full[stage], kc * 64, nt * p.BN, wtap);
           }
           __syncwarp();
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
@@ -182,7 +375,8 @@ __global__ void __launch_bounds__(256, 1)
     const uint32_t idesc = make_idesc_bf16(128, p.BN, 0, 0);
     int stage = 0;
     uint32_t phase = 0, acc = 0, acc_phase = 0;
-    for (int work = blockIdx.x; work < p.total; work += gridDim.x) {
+    if (p.b_resident && wfirst < wcount) mbar_wait(bres_full, 0);
+    for (int work = wfirst; work < wcount; work += wstride) {
       mbar_wait(&tempty[acc], acc_phase ^ 1);
       tc_fence_after();
       const uint32_t tmem_d = tmem_base + acc * (uint32_t)p.BN;
@@ -195,7 +389,8 @@ __global__ void __launch_bounds__(256, 1)
         const uint32_t aaddr = smem_u32(tiles + (size_t)stage * stage_bytes);
         if (elect_one()) {
           const uint64_t da = make_smem_desc_sw128(aaddr, 16, 1024);
-          const uint64_t db = make_smem_desc_sw128(aaddr + kABytes, 16, 1024);
+          const uint64_t db = make_smem_desc_sw128(
+              p.b_resident ? smem_u32(bres + (size_t)kb * b_tile_bytes) : aaddr + kABytes, 16, 1024);
 #pragma unroll 4
           for (int k = 0; k < nk; ++k)
             umma_bf16(tmem_d, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) != 0);
@@ -209,70 +404,97 @@ __global__ void __launch_bounds__(256, 1)
       if (acc == 0) acc_phase ^= 1;
     }
   } else if (warp >= 4) {
-    // ------------------------------------------------------------------ epilogue
-    const int q = warp - 4;
-    const int row = q * 32 + lane;
+    // ------------------------------------------------------------------ epilogue (see epi_chunk)
+    const int q = warp - 4, tid = threadIdx.x - 128, rsub = lane >> 2;
+    uint8_t* stg = smem + 1024 + q * kEpiStageBytes;
+    float* colsum = reinterpret_cast<float*>(smem + 1024 + 4 * kEpiStageBytes);
+    const EpiArgs& e = p.e;
+    const bool do_stats = e.stats != nullptr;
+    const bool has_aux = e.mask != nullptr || (e.dot != nullptr && do_stats);
+    if (do_stats) {
+      for (int i = tid; i < 2 * p.BN; i += 128) colsum[i] = 0.f;
+      epi_bar();
+    }
+    int cur_n = -1, cur_nt = -1;
+    float sacc[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) sacc[k] = 0.f;
+    const int nchunks = (p.BN + p.chunk - 1) / p.chunk;
     uint32_t acc = 0, acc_phase = 0;
-    for (int work = blockIdx.x; work < p.total; work += gridDim.x) {
-      const int mt = work / p.n_tiles, nt = work - mt * p.n_tiles;
+    for (int work = wfirst; work < wcount; work += wstride) {
+      const int mt = p.b_resident ? work : work / p.n_tiles;
+      const int nt = p.b_resident ? nt_fixed : work - mt * p.n_tiles;
       const TileCoord tc = decode_tile(mt, p.tiles_d, p.tiles_h, p.tiles_w, p.tdl, p.thl, p.twl);
-      const int wx = tc.w0 + (row & ((1 << p.twl) - 1));
-      const int hy = tc.h0 + ((row >> p.twl) & ((1 << p.thl) - 1));
-      const int dz = tc.d0 + (row >> (p.twl + p.thl));
-      const bool valid = (wx < p.pw) && (hy < p.ph) && (dz < p.pd);
-      long opos;
-      int ocol0 = nt * p.BN;
-      if (p.out_mode == TC_OUT_CONV) {
-        opos = (((long)tc.n * p.pd + dz) * p.ph + hy) * p.pw + wx;
-      } else {
-        const int ij = ocol0 / p.cout_t;
-        ocol0 -= ij * p.cout_t;
-        opos = ((long)tc.n * (2 * p.ph) + (2 * hy + (ij >> 1))) * (2 * p.pw) + (2 * wx + (ij & 1));
+      if (do_stats && (tc.n != cur_n || nt != cur_nt)) {
+        if (cur_n >= 0) epi_flush_colsum(e, colsum, p.BN, cur_n, cur_nt * p.BN, tid);
+        cur_n = tc.n; cur_nt = nt;
       }
-      bf16* orow = p.out + opos * p.out_ctot + p.out_coff + ocol0;
-      const bf16* mrow = p.mask ? p.mask + opos * p.mask_ctot + p.mask_coff + ocol0 : nullptr;
-      const float* brow = p.bias ? p.bias + ocol0 : nullptr;
-
+      // the 4 tile rows this lane stores in the read-back phase: q*32 + it*8 + lane/4
+      int hy[4], wx[4];
+      long cpos[4];
+#pragma unroll
+      for (int it = 0; it < 4; ++it) {
+        const int row = q * 32 + it * 8 + rsub;
+        wx[it] = tc.w0 + (row & ((1 << p.twl) - 1));
+        hy[it] = tc.h0 + ((row >> p.twl) & ((1 << p.thl) - 1));
+        const int dz = tc.d0 + (row >> (p.twl + p.thl));
+        const bool valid = (wx[it] < p.pw) && (hy[it] < p.ph) && (dz < p.pd);
+        cpos[it] = valid ? (((long)tc.n * p.pd + dz) * p.ph + hy[it]) * p.pw + wx[it] : -1;
+      }
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * (uint32_t)p.BN;
-      for (int c0 = 0; c0 < p.BN; c0 += 16) {
-        uint32_t v[16];
+      auto issue = [&](uint32_t (&v)[32], int ci) {
+        const int c0 = ci * p.chunk;
         tmem_ld16(taddr + c0, v);
+        if (p.chunk == 32 && p.BN - c0 > 16) tmem_ld16(taddr + c0 + 16, v + 16);
+      };
+      // output column and positions of chunk ci (scatter mode: column block ij -> pixel (2h+i, 2w+j))
+      auto place = [&](int ci, int& ocol, long (&opos)[4]) {
+        ocol = nt * p.BN + ci * p.chunk;
+        if (p.out_mode == TC_OUT_CONV) {
+#pragma unroll
+          for (int it = 0; it < 4; ++it) opos[it] = cpos[it];
+        } else {
+          const int ij = ocol / p.cout_t;
+          ocol -= ij * p.cout_t;
+#pragma unroll
+          for (int it = 0; it < 4; ++it)
+            opos[it] = cpos[it] < 0 ? -1
+                                    : ((long)tc.n * (2 * p.ph) + (2 * hy[it] + (ij >> 1))) * (2 * p.pw) +
+                                          (2 * wx[it] + (ij & 1));
+        }
+      };
+      auto prefetch = [&](EpiAux& aux, int ci) {
+        if (!has_aux) return;
+        int ocol;
+        long opos[4];
+        place(ci, ocol, opos);
+        epi_prefetch(e, ocol, (p.chunk == 32 && p.BN - ci * p.chunk > 16) ? 32 : 16, lane, opos, do_stats, aux);
+      };
+      auto process = [&](const uint32_t (&v)[32], const EpiAux& aux, int ci) {
+        const int c0 = ci * p.chunk;
+        const int ncol = (p.chunk == 32 && p.BN - c0 > 16) ? 32 : 16;
+        int ocol;
+        long opos[4];
+        place(ci, ocol, opos);
+        epi_chunk(e, v, ncol, ocol, stg, lane, opos, sacc, do_stats, aux);
+        if (do_stats) epi_fold_acc(sacc, colsum, c0, ncol, p.BN, lane);
+      };
+      uint32_t va[32], vb[32];
+      EpiAux xa, xb;
+      if (e.dbg != 2) {
+      issue(va, 0);
+      prefetch(xa, 0);
+      }
+      for (int ci = 0; ci < (e.dbg == 2 ? 0 : nchunks); ci += 2) {
         tmem_ld_wait();
-        if (valid) {
-          float f[16];
-#pragma unroll
-          for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
-          if (brow) {
-#pragma unroll
-            for (int j = 0; j < 16; j += 4) {
-              const float4 b4 = __ldg(reinterpret_cast<const float4*>(brow + c0 + j));
-              f[j] += b4.x; f[j + 1] += b4.y; f[j + 2] += b4.z; f[j + 3] += b4.w;
-            }
-          }
-          if (p.relu) {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
-          }
-          if (mrow) {
-            const uint4 m0 = *reinterpret_cast<const uint4*>(mrow + c0);
-            const uint4 m1 = *reinterpret_cast<const uint4*>(mrow + c0 + 8);
-            const uint32_t mw[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float2 mv = unpack_bf16x2(mw[j]);
-              if (!(mv.x > 0.f)) f[2 * j] = 0.f;
-              if (!(mv.y > 0.f)) f[2 * j + 1] = 0.f;
-            }
-          }
-          uint4 o0, o1;
-          o0.x = pack_bf16x2(f[0], f[1]);   o0.y = pack_bf16x2(f[2], f[3]);
-          o0.z = pack_bf16x2(f[4], f[5]);   o0.w = pack_bf16x2(f[6], f[7]);
-          o1.x = pack_bf16x2(f[8], f[9]);   o1.y = pack_bf16x2(f[10], f[11]);
-          o1.z = pack_bf16x2(f[12], f[13]); o1.w = pack_bf16x2(f[14], f[15]);
-          *reinterpret_cast<uint4*>(orow + c0) = o0;
-          *reinterpret_cast<uint4*>(orow + c0 + 8) = o1;
+        if (ci + 1 < nchunks) { issue(vb, ci + 1); prefetch(xb, ci + 1); }
+        process(va, xa, ci);
+        if (ci + 1 < nchunks) {
+          tmem_ld_wait();
+          if (ci + 2 < nchunks) { issue(va, ci + 2); prefetch(xa, ci + 2); }
+          process(vb, xb, ci + 1);
         }
       }
       tc_fence_before();
@@ -280,6 +502,7 @@ __global__ void __launch_bounds__(256, 1)
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
+    if (do_stats && cur_n >= 0) epi_flush_colsum(e, colsum, p.BN, cur_n, cur_nt * p.BN, tid);
   }
   tc_fence_before();
   __syncthreads();
@@ -307,13 +530,87 @@ struct HaloArgs {
   int halo_h;            // 16 R + 2
   int a_stage_bytes, a_stages, b_slots;
   int G;                 // taps per weight slot (3 = one kw row per TMA box, or 1)
-  bf16* out;
-  int out_ctot, out_coff;
-  const float* bias;
-  int relu;
-  const bf16* mask;
-  int mask_ctot, mask_coff;
+  int b_resident;        // all weight slabs of the (single) column tile fit in shared memory: loaded once
+  EpiArgs e;
 };
+
+// MMA issuer of the halo kernel.  One thread issues every tcgen05.mma, and with N = 64 an MMA retires
+// every ~28 ns, so the issue loop itself was the limiter (measured: ~200 ns of uniform-datapath
+// bookkeeping per tap + ~27 ns per MMA with run-time R / tap loops).  R (row-blocks) and G (taps per
+// weight slot) are template parameters and the 9 in-plane taps are unrolled, so every descriptor is
+// base + compile-time constant and a tap's R x 4 MMAs are issued back to back.
+template <int R, int G, bool K64>
+__device__ __forceinline__ void halo_mma_warp(const HaloArgs& p, uint32_t tmem_base, uint32_t sA_addr,
+                                              uint32_t sB_addr, uint64_t* afull, uint64_t* aempty,
+                                              uint64_t* bfull, uint64_t* bempty, uint64_t* tfull,
+                                              uint64_t* tempty) {
+  const int BN = p.BN, kchunks = p.kchunks, kd = p.kd, a_stages = p.a_stages, b_slots = p.b_slots;
+  const int kdim = p.kdim, total = p.total, resident = p.b_resident;
+  const uint32_t a_stage_bytes = (uint32_t)p.a_stage_bytes;
+  const uint32_t tap_bytes = (uint32_t)BN * 128u, b_bytes = tap_bytes * G;
+  const uint32_t idesc = make_idesc_bf16(128, BN, 0, 0);
+  const uint64_t adesc0 = make_smem_desc_sw128(0, 16, kHaloW * 128);
+  const uint64_t bdesc0 = make_smem_desc_sw128(0, 16, 1024);
+  int stage = 0, slot = 0;
+  uint32_t aphase = 0, bphase = 0, acc = 0, acc_phase = 0;
+  bool first_tile = true;
+  for (int work = blockIdx.x; work < total; work += gridDim.x) {
+    mbar_wait(&tempty[acc], acc_phase ^ 1);
+    tc_fence_after();
+    const uint32_t tmem_d = tmem_base + acc * (uint32_t)(R * BN);
+    for (int kc = 0; kc < kchunks; ++kc) {
+      int nk = (kdim - kc * 64 + 15) >> 4;
+      nk = nk > 4 ? 4 : nk;
+      for (int kdi = 0; kdi < kd; ++kdi) {
+        mbar_wait(&afull[stage], aphase);
+        tc_fence_after();
+        const uint64_t da0 = adesc0 + (uint64_t)((sA_addr + (uint32_t)stage * a_stage_bytes) >> 4);
+        const bool last_plane = kc == kchunks - 1 && kdi == kd - 1;
+#pragma unroll
+        for (int khi = 0; khi < 3; ++khi) {
+#pragma unroll
+          for (int kwi = 0; kwi < 3; ++kwi) {
+            const int sub = G == 3 ? kwi : 0;
+            if (sub == 0 && (!resident || first_tile)) {
+              mbar_wait(&bfull[slot], bphase);
+              tc_fence_after();
+            }
+            if (elect_one()) {
+              const uint64_t db =
+                  bdesc0 + (uint64_t)((sB_addr + (uint32_t)slot * b_bytes + (uint32_t)sub * tap_bytes) >> 4);
+              const uint32_t fresh = (kc | kdi | khi | kwi) == 0 ? 0u : 1u;  // first MMA of a tile overwrites
+#pragma unroll
+              for (int r = 0; r < R; ++r) {
+                const uint64_t da = da0 + (uint64_t)((((r * 16 + khi) * kHaloW + kwi) * 128) >> 4);
+                const uint32_t td = tmem_d + (uint32_t)(r * BN);
+                if (K64) {   // C_in a multiple of 64: every chunk is 4 K-steps
+                  umma_bf16(td, da, db, idesc, fresh);
+                  umma_bf16(td, da + 2, db + 2, idesc, 1u);
+                  umma_bf16(td, da + 4, db + 4, idesc, 1u);
+                  umma_bf16(td, da + 6, db + 6, idesc, 1u);
+                } else {
+                  for (int k = 0; k < nk; ++k)
+                    umma_bf16(td, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, k ? 1u : fresh);
+                }
+              }
+              if (sub == G - 1 && !resident) umma_commit(&bempty[slot]);
+              if (khi == 2 && kwi == 2) {
+                umma_commit(&aempty[stage]);
+                if (last_plane) umma_commit(&tfull[acc]);
+              }
+            }
+            __syncwarp();
+            if (sub == G - 1 && ++slot == b_slots) { slot = 0; bphase ^= 1; }
+          }
+        }
+        if (++stage == a_stages) { stage = 0; aphase ^= 1; }
+      }
+    }
+    acc ^= 1;
+    if (acc == 0) acc_phase ^= 1;
+    first_tile = false;
+  }
+}
 
 // Super-tile = 1 x (16 R) x 8 output positions of one depth plane.  A stage = the halo of ONE input plane
 // (10 x (16R+2) positions x 64 channels); a weight slot = G taps; each weight slab is applied to all R
@@ -332,7 +629,7 @@ __global__ void __launch_bounds__(256, 1)
   uint64_t* tfull = bempty + 16;
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
-  uint8_t* sA = smem + 1024;
+  uint8_t* sA = smem + kCtrlBytes;
   uint8_t* sB = sA + (size_t)p.a_stages * p.a_stage_bytes;
   const int tap_bytes = p.BN * 128;
   const int b_bytes = tap_bytes * p.G;
@@ -382,6 +679,7 @@ __global__ void __launch_bounds__(256, 1)
     uint32_t phase = 0;
     for (int work = blockIdx.x; work < p.total; work += gridDim.x) {
       const int nt = work % p.n_tiles;
+      if (p.b_resident && work != (int)blockIdx.x) break;   // weights stay put after the first tile
       for (int kc = 0; kc < p.kchunks; ++kc)
         for (int tap = 0; tap < ntaps; tap += p.G) {
           mbar_wait(&bempty[slot], phase ^ 1);
@@ -394,118 +692,96 @@ __global__ void __launch_bounds__(256, 1)
         }
     }
   } else if (warp == 1) {
-    // ---------------------------------------------------------------- MMA issuer
-    const uint32_t idesc = make_idesc_bf16(128, p.BN, 0, 0);
-    int stage = 0, slot = 0;
-    uint32_t aphase = 0, bphase = 0, acc = 0, acc_phase = 0;
-    for (int work = blockIdx.x; work < p.total; work += gridDim.x) {
-      mbar_wait(&tempty[acc], acc_phase ^ 1);
-      tc_fence_after();
-      const uint32_t tmem_d = tmem_base + acc * (uint32_t)(p.R * p.BN);
-      for (int kc = 0; kc < p.kchunks; ++kc) {
-        int nk = (p.kdim - kc * 64 + 15) >> 4;
-        nk = nk > 4 ? 4 : nk;
-        for (int kdi = 0; kdi < p.kd; ++kdi) {
-          mbar_wait(&afull[stage], aphase);
-          tc_fence_after();
-          // descriptors differ only in their 14-bit start-address field: build once, then add
-          const uint64_t da0 = make_smem_desc_sw128(smem_u32(sA + (size_t)stage * p.a_stage_bytes), 16,
-                                                    kHaloW * 128);
-          for (int khi = 0; khi < 3; ++khi) {
-            for (int kwi = 0; kwi < 3; ++kwi) {
-              const int tap = (kdi * 3 + khi) * 3 + kwi;
-              const int sub = p.G == 3 ? kwi : 0;
-              if (sub == 0) {
-                mbar_wait(&bfull[slot], bphase);
-                tc_fence_after();
-              }
-              const bool last_of_slot = sub == p.G - 1;
-              const bool last_of_plane = khi == 2 && kwi == 2;
-              if (elect_one()) {
-                const uint64_t db = make_smem_desc_sw128(
-                    smem_u32(sB + (size_t)slot * b_bytes + (size_t)sub * tap_bytes), 16, 1024);
-                for (int r = 0; r < p.R; ++r) {
-                  const uint64_t da = da0 + (uint64_t)((((r * 16 + khi) * kHaloW + kwi) * 128) >> 4);
-#pragma unroll 4
-                  for (int k = 0; k < nk; ++k)
-                    umma_bf16(tmem_d + r * p.BN, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc,
-                              (kc | tap | k) != 0);
-                }
-                if (last_of_slot) umma_commit(&bempty[slot]);
-                if (last_of_plane) {
-                  umma_commit(&aempty[stage]);
-                  if (kc == p.kchunks - 1 && kdi == p.kd - 1) umma_commit(&tfull[acc]);
-                }
-              }
-              __syncwarp();
-              if (last_of_slot && ++slot == p.b_slots) { slot = 0; bphase ^= 1; }
-            }
-          }
-          if (++stage == p.a_stages) { stage = 0; aphase ^= 1; }
-        }
-      }
-      acc ^= 1;
-      if (acc == 0) acc_phase ^= 1;
+    // ---------------------------------------------------------------- MMA issuer (halo_mma_warp)
+    const uint32_t sA_addr = smem_u32(sA), sB_addr = smem_u32(sB);
+#define HALO_MMA(RR, GG, KK) \
+  halo_mma_warp<RR, GG, KK>(p, tmem_base, sA_addr, sB_addr, afull, aempty, bfull, bempty, tfull, tempty)
+    const bool k64 = (p.kdim & 63) == 0;
+    if (p.G == 3) {
+      if (p.R == 4) { if (k64) HALO_MMA(4, 3, true); else HALO_MMA(4, 3, false); }
+      else if (p.R == 2) { if (k64) HALO_MMA(2, 3, true); else HALO_MMA(2, 3, false); }
+      else { if (k64) HALO_MMA(1, 3, true); else HALO_MMA(1, 3, false); }
+    } else {
+      if (p.R == 4) { if (k64) HALO_MMA(4, 1, true); else HALO_MMA(4, 1, false); }
+      else if (p.R == 2) { if (k64) HALO_MMA(2, 1, true); else HALO_MMA(2, 1, false); }
+      else { if (k64) HALO_MMA(1, 1, true); else HALO_MMA(1, 1, false); }
     }
+#undef HALO_MMA
   } else if (warp >= 4) {
-    // ---------------------------------------------------------------- epilogue
-    const int q = warp - 4;
-    const int row = q * 32 + lane;
+    // ---------------------------------------------------------------- epilogue (see epi_chunk)
+    const int q = warp - 4, tid = threadIdx.x - 128, rsub = lane >> 2;
+    uint8_t* stg = smem + 1024 + q * kEpiStageBytes;
+    float* colsum = reinterpret_cast<float*>(smem + 1024 + 4 * kEpiStageBytes);
+    const EpiArgs& e = p.e;
+    const bool do_stats = e.stats != nullptr;
+    const bool has_aux = e.mask != nullptr || (e.dot != nullptr && do_stats);
+    if (do_stats) {
+      for (int i = tid; i < 2 * p.BN; i += 128) colsum[i] = 0.f;
+      epi_bar();
+    }
+    int cur_n = -1, cur_nt = -1;
+    float sacc[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) sacc[k] = 0.f;
+    const int nchunks = (p.BN + 31) / 32;
+    const int items = nchunks * p.R;   // item = chunk * R + row-block: the R row-blocks of a chunk share sacc
     uint32_t acc = 0, acc_phase = 0;
     for (int work = blockIdx.x; work < p.total; work += gridDim.x) {
       const int mt = work / p.n_tiles, nt = work - mt * p.n_tiles;
       const TileCoord tc = decode_tile(mt, p.pd, p.tiles_h, p.tiles_w, 0, thl, 3);
-      const int wx = tc.w0 + (row & 7);
-      const int ocol0 = nt * p.BN;
-      const float* brow = p.bias ? p.bias + ocol0 : nullptr;
+      if (do_stats && (tc.n != cur_n || nt != cur_nt)) {
+        if (cur_n >= 0) epi_flush_colsum(e, colsum, p.BN, cur_n, cur_nt * p.BN, tid);
+        cur_n = tc.n; cur_nt = nt;
+      }
+      // read-back rows of this lane: tile row q*32 + it*8 + lane/4 -> w = lane/4, h = q*4 + it
+      const int wx = tc.w0 + rsub;
+      const long plane0 = ((long)tc.n * p.pd + tc.d0) * p.ph;
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
-      for (int r = 0; r < p.R; ++r) {
-        const int hy = tc.h0 + r * 16 + (row >> 3);
-        const bool valid = (wx < p.pw) && (hy < p.ph);
-        const long opos = (((long)tc.n * p.pd + tc.d0) * p.ph + hy) * p.pw + wx;
-        bf16* orow = p.out + opos * p.out_ctot + p.out_coff + ocol0;
-        const bf16* mrow = p.mask ? p.mask + opos * p.mask_ctot + p.mask_coff + ocol0 : nullptr;
-        const uint32_t taddr =
-            tmem_base + ((uint32_t)(q * 32) << 16) + (acc * (uint32_t)p.R + r) * (uint32_t)p.BN;
-        for (int c0 = 0; c0 < p.BN; c0 += 16) {
-          uint32_t v[16];
-          tmem_ld16(taddr + c0, v);
+      const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + acc * (uint32_t)(p.R * p.BN);
+      auto issue = [&](uint32_t (&v)[32], int item) {
+        const int ci = item / p.R, r = item - ci * p.R;
+        const uint32_t ta = tbase + (uint32_t)(r * p.BN + ci * 32);
+        tmem_ld16(ta, v);
+        if (p.BN - ci * 32 > 16) tmem_ld16(ta + 16, v + 16);
+      };
+      auto place = [&](int r, long (&opos)[4]) {
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+          const int hy = tc.h0 + r * 16 + q * 4 + it;
+          opos[it] = (wx < p.pw && hy < p.ph) ? (plane0 + hy) * p.pw + wx : -1;
+        }
+      };
+      auto prefetch = [&](EpiAux& aux, int item) {
+        if (!has_aux) return;
+        const int ci = item / p.R, r = item - ci * p.R;
+        long opos[4];
+        place(r, opos);
+        epi_prefetch(e, nt * p.BN + ci * 32, p.BN - ci * 32 > 16 ? 32 : 16, lane, opos, do_stats, aux);
+      };
+      auto process = [&](const uint32_t (&v)[32], const EpiAux& aux, int item) {
+        const int ci = item / p.R, r = item - ci * p.R;
+        const int c0 = ci * 32;
+        const int ncol = p.BN - c0 > 16 ? 32 : 16;
+        long opos[4];
+        place(r, opos);
+        epi_chunk(e, v, ncol, nt * p.BN + c0, stg, lane, opos, sacc, do_stats, aux);
+        if (do_stats && r == p.R - 1) epi_fold_acc(sacc, colsum, c0, ncol, p.BN, lane);
+      };
+      uint32_t va[32], vb[32];
+      EpiAux xa, xb;
+      if (e.dbg != 2) {
+      issue(va, 0);
+      prefetch(xa, 0);
+      }
+      for (int item = 0; item < (e.dbg == 2 ? 0 : items); item += 2) {
+        tmem_ld_wait();
+        if (item + 1 < items) { issue(vb, item + 1); prefetch(xb, item + 1); }
+        process(va, xa, item);
+        if (item + 1 < items) {
           tmem_ld_wait();
-          if (valid) {
-            float f[16];
-#pragma unroll
-            for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
-            if (brow) {
-#pragma unroll
-              for (int j = 0; j < 16; j += 4) {
-                const float4 b4 = __ldg(reinterpret_cast<const float4*>(brow + c0 + j));
-                f[j] += b4.x; f[j + 1] += b4.y; f[j + 2] += b4.z; f[j + 3] += b4.w;
-              }
-            }
-            if (p.relu) {
-#pragma unroll
-              for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
-            }
-            if (mrow) {
-              const uint4 m0 = *reinterpret_cast<const uint4*>(mrow + c0);
-              const uint4 m1 = *reinterpret_cast<const uint4*>(mrow + c0 + 8);
-              const uint32_t mw[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
-#pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                const float2 mv = unpack_bf16x2(mw[j]);
-                if (!(mv.x > 0.f)) f[2 * j] = 0.f;
-                if (!(mv.y > 0.f)) f[2 * j + 1] = 0.f;
-              }
-            }
-            uint4 o0, o1;
-            o0.x = pack_bf16x2(f[0], f[1]);   o0.y = pack_bf16x2(f[2], f[3]);
-            o0.z = pack_bf16x2(f[4], f[5]);   o0.w = pack_bf16x2(f[6], f[7]);
-            o1.x = pack_bf16x2(f[8], f[9]);   o1.y = pack_bf16x2(f[10], f[11]);
-            o1.z = pack_bf16x2(f[12], f[13]); o1.w = pack_bf16x2(f[14], f[15]);
-            *reinterpret_cast<uint4*>(orow + c0) = o0;
-            *reinterpret_cast<uint4*>(orow + c0 + 8) = o1;
-          }
+          if (item + 2 < items) { issue(va, item + 2); prefetch(xa, item + 2); }
+          process(vb, xb, item + 1);
         }
       }
       tc_fence_before();
@@ -513,10 +789,23 @@ __global__ void __launch_bounds__(256, 1)
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
+    if (do_stats && cur_n >= 0) epi_flush_colsum(e, colsum, p.BN, cur_n, cur_nt * p.BN, tid);
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 2) tmem_dealloc(tmem_base, tmem_cols);
+}
+
+int g_epi_dbg = 0;
+static EpiArgs make_epi(const TcGemmProblem& p) {
+  EpiArgs e{};
+  e.out = p.out; e.out_ctot = p.out_ctot; e.out_coff = p.out_coff;
+  e.bias = p.bias; e.relu = p.relu;
+  e.mask = p.mask; e.mask_ctot = p.mask_ctot; e.mask_coff = p.mask_coff;
+  e.dot = p.dot; e.dot_ctot = p.dot_ctot; e.dot_coff = p.dot_coff;
+  e.stats = p.stats; e.stats_cols = p.ncols;
+  e.dbg = g_epi_dbg;
+  return e;
 }
 
 static int sm_count() {
@@ -542,9 +831,9 @@ bool tc_gemm_supported(const TcGemmProblem& p) {
   if (p.out_ctot % 8 || p.out_coff % 8) return false;
   if (p.mask && (p.mask_ctot % 8 || p.mask_coff % 8)) return false;
   if (p.ncols % 16) return false;
-  if (p.out_mode == TC_OUT_K2S2_SCATTER) {
-    if (p.cout_t % 16 || pick_bn(p.cout_t, 256) == 0) return false;
-  }
+  if (p.out_mode == TC_OUT_K2S2_SCATTER && (p.cout_t % 16 || p.stats)) return false;
+  if (p.stats && (p.table || p.out_mode != TC_OUT_CONV)) return false;
+  if (p.dot && (p.dot_ctot % 8 || p.dot_coff % 8)) return false;
   if (p.tap_mode == TC_TAP_K2S2 && (p.pd != 1 || p.a.h != 2 * p.ph || p.a.w != 2 * p.pw))
     return false;
   return true;
@@ -554,12 +843,14 @@ static int pick_bn(int ncols, int limit);
 static int sm_count();
 int g_halo_mode = 1;  // 0 disables the halo-reuse kernel (A/B testing from the bench tools)
 
+int g_halo_rmax = 4;  // tuning knob: cap on row-blocks per super-tile
 static bool halo_eligible(const TcGemmProblem& p) {
   return g_halo_mode && !p.table && p.tap_mode == TC_TAP_SHIFT && p.out_mode == TC_OUT_CONV && p.kh == 3 &&
          p.kw == 3 && (p.kd == 3 || p.kd == 1) && p.ph >= 12 && p.pw >= 8;
 }
 
-int g_halo_rmax = 4;  // tuning knob: cap on row-blocks per super-tile
+int g_halo_resident = 1;  // tuning knob: weight-resident mode of the halo kernel
+int g_gemm_resident = 1;  // tuning knob: weight-resident mode of the per-tap kernel
 
 static int tc_gemm_halo(const TcGemmProblem& p, cudaStream_t stream) {
   HaloArgs a{};
@@ -575,9 +866,29 @@ static int tc_gemm_halo(const TcGemmProblem& p, cudaStream_t stream) {
     if (r > g_halo_rmax || 2 * r * a.BN > 512) continue;
     if (p.ph < 16 * r - (r == 2 ? 8 : 16)) continue;              // mostly-empty super-tiles
     const int stage = (kHaloW * (16 * r + 2) * 128 + 1023) / 1024 * 1024;
-    if (kSmemBudget - 2048 - 2 * stage < 2 * 3 * a.BN * 128) continue;
+    if (kSmemBudget - kSmemOverhead - 2 * stage < 2 * 3 * a.BN * 128) continue;
     R = r;
     break;
+  }
+  // Weight-resident mode: when every weight slab of the layer fits in shared memory next to two
+  // activation stages (2D layers with C_in * C_out <= 128 * 64) it is loaded once per CTA instead of
+  // once per super-tile — those layers were bound by re-streaming 74-147 KB of weights from L2 per
+  // 4 us of MMA work.  Weight sharing across row-blocks then buys nothing, so R only has to fit.
+  const int ntaps_all = p.kd * 9;
+  const long w_bytes = (long)ntaps_all * a.kchunks * a.BN * 128;
+  a.b_resident = 0;
+  if (g_halo_resident && a.n_tiles == 1 && ntaps_all * a.kchunks / 3 <= 16) {
+    for (int r : {4, 2, 1}) {
+      if (r > g_halo_rmax || 2 * r * a.BN > 512) continue;
+      if (r == 4 && p.ph < 48) continue;
+      if (r == 2 && p.ph < 24) continue;
+      const long stage = (kHaloW * (16 * r + 2) * 128 + 1023) / 1024 * 1024;
+      if (kSmemBudget - kSmemOverhead - w_bytes >= 2 * stage * (p.kd == 3 ? 2 : 1)) {
+        a.b_resident = 1;
+        R = r;
+        break;
+      }
+    }
   }
   a.R = R;
   a.halo_h = 16 * R + 2;
@@ -586,20 +897,30 @@ static int tc_gemm_halo(const TcGemmProblem& p, cudaStream_t stream) {
   a.total = a.m_tiles * a.n_tiles;
   a.a_stage_bytes = (kHaloW * a.halo_h * 128 + 1023) / 1024 * 1024;
   a.a_stages = 2;
-  int rem = kSmemBudget - 2048 - a.a_stages * a.a_stage_bytes;
-  a.G = (2 * 3 * a.BN * 128 <= rem) ? 3 : 1;
-  int b_bytes = a.G * a.BN * 128;
-  // spend what is left on more activation stages first (cheap, hides TMA latency), then weight slots
-  while (a.a_stages < 6 && rem - a.a_stage_bytes >= 3 * b_bytes) {
-    ++a.a_stages;
-    rem -= a.a_stage_bytes;
+  int rem = kSmemBudget - kSmemOverhead - a.a_stages * a.a_stage_bytes;
+  int b_bytes;
+  if (a.b_resident) {
+    a.G = 3;
+    b_bytes = a.G * a.BN * 128;
+    a.b_slots = ntaps_all * a.kchunks / 3;
+    rem -= (int)w_bytes;
+    while (a.a_stages < 6 && rem >= a.a_stage_bytes) {
+      ++a.a_stages;
+      rem -= a.a_stage_bytes;
+    }
+  } else {
+    a.G = (2 * 3 * a.BN * 128 <= rem) ? 3 : 1;
+    b_bytes = a.G * a.BN * 128;
+    // spend what is left on more activation stages first (cheap, hides TMA latency), then weight slots
+    while (a.a_stages < 6 && rem - a.a_stage_bytes >= 3 * b_bytes) {
+      ++a.a_stages;
+      rem -= a.a_stage_bytes;
+    }
+    a.b_slots = rem / b_bytes;
+    if (a.b_slots > 12) a.b_slots = 12;
+    if (a.b_slots < 2) return B200_ERR_UNSUPPORTED;
   }
-  a.b_slots = rem / b_bytes;
-  if (a.b_slots > 12) a.b_slots = 12;
-  if (a.b_slots < 2) return B200_ERR_UNSUPPORTED;
-  a.out = p.out; a.out_ctot = p.out_ctot; a.out_coff = p.out_coff;
-  a.bias = p.bias; a.relu = p.relu;
-  a.mask = p.mask; a.mask_ctot = p.mask_ctot; a.mask_coff = p.mask_coff;
+  a.e = make_epi(p);
 
   CUtensorMap tmA, tmB;
   {
@@ -619,7 +940,7 @@ static int tc_gemm_halo(const TcGemmProblem& p, cudaStream_t stream) {
     int rc = make_tmap_bf16(&tmB, p.wp, 3, dims, str, box);
     if (rc) return rc;
   }
-  const int smem = a.a_stages * a.a_stage_bytes + a.b_slots * b_bytes + 2048;
+  const int smem = a.a_stages * a.a_stage_bytes + a.b_slots * b_bytes + kSmemOverhead;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(tc_gemm_halo_kernel,
@@ -642,7 +963,8 @@ int tc_gemm_conv(const TcGemmProblem& p, cudaStream_t stream) {
   a.tdl = g.tdl; a.thl = g.thl; a.twl = g.twl;
   a.tiles_d = g.tiles_d; a.tiles_h = g.tiles_h; a.tiles_w = g.tiles_w;
   a.m_tiles = g.m_tiles;
-  a.BN = p.out_mode == TC_OUT_K2S2_SCATTER ? pick_bn(p.cout_t, 256) : pick_bn(p.ncols, 256);
+  a.BN = pick_bn(p.ncols, 256);  // scatter mode: a tile may span several (i,j) blocks of cout_t columns
+  a.chunk = (p.out_mode == TC_OUT_K2S2_SCATTER && p.cout_t % 32) ? 16 : 32;
   a.n_tiles = p.ncols / a.BN;
   a.total = a.m_tiles * a.n_tiles;
   a.ntaps = p.kd * p.kh * p.kw; a.kh = p.kh; a.kw = p.kw;
@@ -657,13 +979,23 @@ int tc_gemm_conv(const TcGemmProblem& p, cudaStream_t stream) {
   }
   a.tap_mode = p.tap_mode; a.out_mode = p.out_mode;
   a.kdim = p.kdim; a.kchunks = (p.kdim + 63) / 64;
-  const int stage_bytes = kABytes + a.BN * 128;
-  a.stages = (kSmemBudget - 2048) / stage_bytes;
+  // Weight-resident mode: with few taps and a short K (ConvTranspose 2x2 forward / backward-data) the
+  // weight slabs of one column tile fit in shared memory; each CTA then keeps ONE column tile and only
+  // streams activations (per-tile L2 traffic drops from A + B to A).
+  const long w_bytes = (long)a.ntaps * a.kchunks * a.BN * 128;
+  int grid = a.total < sm_count() ? a.total : sm_count();
+  a.b_resident = 0;
+  if (g_gemm_resident && kSmemBudget - kSmemOverhead - w_bytes >= 4L * kABytes &&
+      a.m_tiles >= 2 * (sm_count() / a.n_tiles) && a.n_tiles <= sm_count()) {
+    a.b_resident = 1;
+    grid = (sm_count() / a.n_tiles) * a.n_tiles;
+  }
+  const int stage_bytes = a.b_resident ? kABytes : kABytes + a.BN * 128;
+  a.stages = (int)((kSmemBudget - kSmemOverhead - (a.b_resident ? w_bytes : 0)) / stage_bytes);
   if (a.stages > 12) a.stages = 12;
   if (a.stages < 2) return B200_ERR_UNSUPPORTED;
-  a.out = p.out; a.out_ctot = p.out_ctot; a.out_coff = p.out_coff; a.cout_t = p.cout_t;
-  a.bias = p.bias; a.relu = p.relu;
-  a.mask = p.mask; a.mask_ctot = p.mask_ctot; a.mask_coff = p.mask_coff;
+  a.cout_t = p.cout_t;
+  a.e = make_epi(p);
 
   CUtensorMap tmA, tmB;
   int rc = make_act_tmap(&tmA, p.a, p.tap_mode, g);
@@ -675,7 +1007,7 @@ int tc_gemm_conv(const TcGemmProblem& p, cudaStream_t stream) {
     rc = make_tmap_bf16(&tmB, p.wp, 3, dims, str, box);
     if (rc) return rc;
   }
-  const int smem = a.stages * stage_bytes + 2048;
+  const int smem = a.stages * stage_bytes + kSmemOverhead + (a.b_resident ? (int)w_bytes : 0);
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -683,7 +1015,6 @@ int tc_gemm_conv(const TcGemmProblem& p, cudaStream_t stream) {
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
   }
-  int grid = a.total < sm_count() ? a.total : sm_count();
   tc_gemm_kernel<<<grid, 256, smem, stream>>>(tmA, tmB, a);
   B200_LAUNCH_CHECK();
   return B200_OK;

@@ -44,6 +44,12 @@ struct TcGemmProblem {
   int relu;
   const bf16* mask;       // optional: out = 0 where mask <= 0; same geometry as out
   int mask_ctot, mask_coff;
+  // optional per-sample column statistics of the stored (bf16) output, accumulated into
+  // stats fp64 [pn][2][ncols]: [.][0][c] += sum out, [.][1][c] += sum out^2, or sum out * dot when a
+  // dot operand (same geometry as out) is given.  Fused into the epilogue of the tcgen05 kernels.
+  double* stats;
+  const bf16* dot;
+  int dot_ctot, dot_coff;
 };
 int tc_gemm_conv(const TcGemmProblem& p, cudaStream_t stream);
 bool tc_gemm_supported(const TcGemmProblem& p);

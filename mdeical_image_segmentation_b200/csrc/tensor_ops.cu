@@ -596,6 +596,50 @@ __global__ void gn_bwd_finalize_kernel(int n, int c, int groups, const float* ga
     if (dgamma) atomicAdd(dgamma + i, bb);
   }
 }
+// fused variant: raw[n][2][c] fp64 = (sum dy, sum dy * x) from the dgrad epilogue;
+// sum dy * xhat = rstd * (sum dy*x - mean * sum dy)
+__global__ void gn_bwd_finalize_raw_kernel(int n, int c, int groups, const float* gamma,
+                                           const float* stats, const double* raw, float* gsum,
+                                           float* dgamma, float* dbeta) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int cpg = c / groups;
+  if (i < n * groups) {
+    const int b = i / groups, g = i % groups;
+    const double mean = stats[2 * i], rstd = stats[2 * i + 1];
+    double a = 0, bb = 0;
+    for (int ch = g * cpg; ch < (g + 1) * cpg; ++ch) {
+      const double s1 = raw[((long)b * 2) * c + ch], sx = raw[((long)b * 2 + 1) * c + ch];
+      a += gamma[ch] * s1;
+      bb += gamma[ch] * rstd * (sx - mean * s1);
+    }
+    gsum[2 * i] = (float)a;
+    gsum[2 * i + 1] = (float)bb;
+  }
+  if (i < c) {
+    const int g = i / cpg;
+    double a = 0, bb = 0;
+    for (int b = 0; b < n; ++b) {
+      const double mean = stats[2 * (b * groups + g)], rstd = stats[2 * (b * groups + g) + 1];
+      const double s1 = raw[((long)b * 2) * c + i], sx = raw[((long)b * 2 + 1) * c + i];
+      a += s1;
+      bb += rstd * (sx - mean * s1);
+    }
+    if (dbeta) atomicAdd(dbeta + i, (float)a);
+    if (dgamma) atomicAdd(dgamma + i, (float)bb);
+  }
+}
+__global__ void bn_red_from_sums_kernel(int n, int c, const double* raw, const float* mean,
+                                        const float* rstd, float* red) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= c) return;
+  double a = 0, sx = 0;
+  for (int b = 0; b < n; ++b) {
+    a += raw[((long)b * 2) * c + i];
+    sx += raw[((long)b * 2 + 1) * c + i];
+  }
+  red[i] = (float)a;
+  red[c + i] = (float)((double)rstd[i] * (sx - (double)mean[i] * a));
+}
 template <int V>
 __global__ void gn_bwd_apply_kernel(int n, long spatial, int c, int groups, View x, View dy,
                                     const float* stats, const float* gamma, const float* gsum,
@@ -890,6 +934,47 @@ int b200_gn_bwd(int32_t n, int64_t spatial, int32_t c, int32_t groups, b200_view
   b200_view none{nullptr, 0, 0};
   if (v) norm_bwd_apply_kernel<8><<<grid, 256, 0, (cudaStream_t)stream>>>((long)spatial, c, groups, chunk, 0, inv_m, mk(x), mk(dy), mk(none), stats, nullptr, gamma, gsum, mk(dx), mask_relu);
   else norm_bwd_apply_kernel<1><<<grid, 256, 0, (cudaStream_t)stream>>>((long)spatial, c, groups, chunk, 0, inv_m, mk(x), mk(dy), mk(none), stats, nullptr, gamma, gsum, mk(dx), mask_relu);
+  B200_LAUNCH_CHECK();
+  return B200_OK;
+}
+
+int b200_gn_stats_finalize(int32_t n, int64_t spatial, int32_t c, int32_t groups, float eps,
+                           const double* sums, float* stats, b200_stream_t stream) {
+  if (groups <= 0 || c % groups) return B200_ERR_BAD_ARG;
+  if ((long)n * spatial <= 0) return B200_OK;
+  gn_finalize_kernel<<<(n * groups + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
+      n, c, groups, (double)(c / groups) * (double)spatial, eps, sums, stats);
+  B200_LAUNCH_CHECK();
+  return B200_OK;
+}
+int b200_gn_bwd_fused(int32_t n, int64_t spatial, int32_t c, int32_t groups, b200_view x,
+                      const float* stats, const float* gamma, b200_view dy, b200_view dx,
+                      float* dgamma, float* dbeta, const double* colstats, float* scratch,
+                      int32_t mask_relu, b200_stream_t stream) {
+  if (groups <= 0 || c % groups || !colstats || !scratch) return B200_ERR_BAD_ARG;
+  const long total = (long)n * spatial * c;
+  if (total <= 0) return B200_OK;
+  const bool v = vec8(c, x) && vec8(c, dy) && vec8(c, dx);
+  float* gsum = scratch;  // [n][groups][2]
+  const int work = n * groups > c ? n * groups : c;
+  gn_bwd_finalize_raw_kernel<<<(work + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
+      n, c, groups, gamma, stats, colstats, gsum, dgamma, dbeta);
+  B200_LAUNCH_CHECK();
+  dim3 grid;
+  long chunk;
+  column_grid(spatial, c, v ? 8 : 1, grid, chunk);
+  grid.z = n;
+  const float inv_m = 1.f / ((float)(c / groups) * (float)spatial);
+  b200_view none{nullptr, 0, 0};
+  if (v) norm_bwd_apply_kernel<8><<<grid, 256, 0, (cudaStream_t)stream>>>((long)spatial, c, groups, chunk, 0, inv_m, mk(x), mk(dy), mk(none), stats, nullptr, gamma, gsum, mk(dx), mask_relu);
+  else norm_bwd_apply_kernel<1><<<grid, 256, 0, (cudaStream_t)stream>>>((long)spatial, c, groups, chunk, 0, inv_m, mk(x), mk(dy), mk(none), stats, nullptr, gamma, gsum, mk(dx), mask_relu);
+  B200_LAUNCH_CHECK();
+  return B200_OK;
+}
+int b200_bn_bwd_red_from_sums(int32_t n, int32_t c, const double* colstats, const float* mean,
+                              const float* rstd, float* red, b200_stream_t stream) {
+  if (n <= 0 || c <= 0 || !colstats || !red) return B200_ERR_BAD_ARG;
+  bn_red_from_sums_kernel<<<(c + 127) / 128, 128, 0, (cudaStream_t)stream>>>(n, c, colstats, mean, rstd, red);
   B200_LAUNCH_CHECK();
   return B200_OK;
 }

@@ -57,11 +57,12 @@ class LayerSpec:
         self.order, self.conv, self.groupnorm, self.batchnorm = order, conv, groupnorm, batchnorm
 
 
-def _bn_moments(bn: nn.Module, x: CL, training: bool):
+def _bn_moments(bn: nn.Module, x: CL, training: bool, in_sums: Optional[torch.Tensor] = None):
     """mean / rstd for BatchNorm; in training also updates the running statistics the way
-    nn.BatchNorm does (momentum 0.1, unbiased running variance)."""
+    nn.BatchNorm does (momentum 0.1, unbiased running variance).  ``in_sums`` (fp64 [n][2][c],
+    per-sample sum x / sum x^2 from the producing conv's epilogue) replaces the statistics pass."""
     if training or bn.running_mean is None:
-        sums = ops.bn_stats(x)
+        sums = in_sums.sum(0) if in_sums is not None else ops.bn_stats(x)
         m = float(x.npos)
         mean = sums[0] / m
         var = (sums[1] / m - mean * mean).clamp_(min=0.0)
@@ -80,13 +81,17 @@ def _bn_moments(bn: nn.Module, x: CL, training: bool):
 
 
 def single_conv_fwd(x: CL, spec: LayerSpec, training: bool, tape: Optional[list],
-                    out: Optional[CL] = None, in_relu: bool = False):
+                    out: Optional[CL] = None, in_relu: bool = False,
+                    in_sums: Optional[torch.Tensor] = None, want_sums: bool = False):
     """Runs one layer; ``out`` (optional) is the destination slice of its final result.
     ``in_relu`` says the input is a ReLU output (>= 0, zero exactly where its producer was clipped):
     the first op's backward then folds that producer's ReLU backward into its own output.
-    Returns (y, y_is_relu_output)."""
+    ``in_sums`` / ``want_sums``: per-sample per-channel (sum, sum of squares) of the input / of the
+    result (fp64 [n][2][c]), produced in conv epilogues so that a norm never re-reads its input for
+    statistics.  Returns (y, y_is_relu_output, y_sums or None)."""
     letters = spec.order
     cur = x
+    cur_sums = in_sums if (in_sums is not None and in_sums.shape[2] == x.c) else None
     i = 0
     out_relu = False
     while i < len(letters):
@@ -103,14 +108,22 @@ def single_conv_fwd(x: CL, spec: LayerSpec, training: bool, tape: Optional[list]
                 w = torch.nn.functional.pad(w, (0, 0) * (w.dim() - 2) + (0, cur.zpad))
             wp_fwd, wp_bwd, k = ops.conv_repack_weight(w, need_bwd=tape is not None)
             bias = None if conv.bias is None else conv.bias.detach().float().contiguous()
-            y = ops.conv_fwd(xin, wp_fwd, k, bias, fuse_relu, out=dst, impl=IMPL)
+            need = (letters[nxt] in "gb") if nxt < len(letters) else want_sums
+            if need:
+                y, cur_sums = ops.conv_fwd(xin, wp_fwd, k, bias, fuse_relu, out=dst, impl=IMPL, stats=True)
+            else:
+                y, cur_sums = ops.conv_fwd(xin, wp_fwd, k, bias, fuse_relu, out=dst, impl=IMPL), None
             if tape is not None:
                 tape.append(("conv", xin, conv, wp_bwd, k, y if fuse_relu else None, cur.zpad,
                              in_relu and i == 0))
             cur = y
         elif ch == "g":
             gn = spec.groupnorm
-            stats = ops.gn_stats(cur, gn.num_groups, gn.eps)
+            if cur_sums is not None:
+                stats = ops.gn_stats_from_sums(cur_sums, cur.spatial, gn.num_groups, gn.eps)
+            else:
+                stats = ops.gn_stats(cur, gn.num_groups, gn.eps)
+            cur_sums = None
             gamma = gn.weight.detach().float().contiguous()
             beta = gn.bias.detach().float().contiguous()
             if dst is None and cur.zpad:
@@ -121,7 +134,8 @@ def single_conv_fwd(x: CL, spec: LayerSpec, training: bool, tape: Optional[list]
             cur = y
         elif ch == "b":
             bn = spec.batchnorm
-            mean, rstd = _bn_moments(bn, cur, training)
+            mean, rstd = _bn_moments(bn, cur, training, cur_sums)
+            cur_sums = None
             gamma = bn.weight.detach().float().contiguous()
             beta = bn.bias.detach().float().contiguous()
             if dst is None and cur.zpad:
@@ -138,27 +152,56 @@ def single_conv_fwd(x: CL, spec: LayerSpec, training: bool, tape: Optional[list]
     if out is not None and cur is not out:
         ops.copy_channels(cur, out)
         cur = out
-    return cur, out_relu
+    return cur, out_relu, cur_sums
 
 
-def single_conv_bwd(dy: CL, recs: list, grads: Grads, need_dx: bool = True, premasked: bool = False):
+def _consumer_plan(consumer, fuse_mask: bool):
+    """What the kernel producing a gradient should reduce for the op that consumes it (``consumer`` =
+    that op's tape record, or ("sum",) for a plain per-channel sum).  Returns (want_stats, dot) where
+    dot is the tensor to correlate the gradient with (None: sum of squares, unused)."""
+    if consumer is None:
+        return False, None
+    kind = consumer[0]
+    if kind == "sum":
+        return True, None
+    relu_out = consumer[5] if kind in ("conv", "gn") else consumer[6] if kind == "bn" else None
+    if relu_out is not None and not fuse_mask:
+        return False, None       # the consumer's ReLU backward is not folded into this gradient
+    if kind == "conv":           # bias gradient = per-channel sum of the (masked) gradient
+        conv = consumer[2]
+        return bool(conv.bias is not None and conv.bias.requires_grad), None
+    if kind in ("gn", "bn"):     # (sum g, sum g * x) with x = the norm's input
+        if kind == "bn" and not consumer[7]:
+            return False, None   # frozen statistics: no batch terms, the reduction path handles dgamma
+        return True, consumer[1]
+    return False, None
+
+
+def single_conv_bwd(dy: CL, recs: list, grads: Grads, need_dx: bool = True, premasked: bool = False,
+                    dy_sums: Optional[torch.Tensor] = None, consumer=None):
     """Backward of one layer: consumes the layer's tape records (in reverse); dy may be clobbered.
     ``premasked``: dy already carries the ReLU backward of this layer's final ReLU (its producer fused
-    it).  Returns (dx, dx_premasked) where dx_premasked says dx carries the ReLU backward of the layer
-    that produced this layer's input."""
+    it).  ``dy_sums``: fp64 [n][2][c] reductions of dy that its producer computed for this layer's last
+    op (see _consumer_plan).  ``consumer``: tape record of the op that will receive dx.
+    Returns (dx, dx_premasked, dx_sums)."""
     out_premasked = False
+    sums = dy_sums
     for idx in range(len(recs) - 1, -1, -1):
         rec = recs[idx]
         kind = rec[0]
         last = idx == 0
         pm = premasked and idx == len(recs) - 1
+        nxt_consumer = recs[idx - 1] if idx > 0 else consumer
         if kind == "conv":
             _, x_in, conv, wp_bwd, k, y_relu, zpad, mask_in = rec
             has_bias = conv.bias is not None and conv.bias.requires_grad
             if y_relu is not None and not pm:
                 dy, db = ops.relu_bwd(dy, y_relu, has_bias, out=dy)
+            elif has_bias and sums is not None:
+                db = sums[:, 0, :].sum(0).float()
             else:
                 db = ops.bias_grad(dy) if has_bias else None
+            sums = None
             if has_bias:
                 _acc(grads, conv.bias, db)
             if conv.weight.requires_grad:
@@ -169,56 +212,82 @@ def single_conv_bwd(dy: CL, recs: list, grads: Grads, need_dx: bool = True, prem
                     dw = dw[:, :conv.weight.shape[1]].contiguous()
                 _acc(grads, conv.weight, dw)
             if last and not need_dx:
-                return None, False
+                return None, False, None
             # the fused mask must have the layout of the (dense) dx the kernel writes
             fuse = bool(mask_in and not zpad and x_in.is_full())
-            dy = ops.conv_bwd_data(dy, wp_bwd, k, mask=x_in if fuse else None, impl=IMPL)
+            want, dot = _consumer_plan(nxt_consumer, fuse)
+            if want and dot is not None:
+                dot = dot.widened()
+                if dot.c != x_in.c or dot.dims != x_in.dims:
+                    want, dot = False, None
+            if want:
+                dy, sums = ops.conv_bwd_data(dy, wp_bwd, k, mask=x_in if fuse else None, impl=IMPL,
+                                             stats=True, dot=dot)
+            else:
+                dy = ops.conv_bwd_data(dy, wp_bwd, k, mask=x_in if fuse else None, impl=IMPL)
             out_premasked = fuse
             if zpad:  # gradient w.r.t. the padding channels is meaningless: expose the real slice
                 dy = CL(dy.buf, dy.c - zpad, 0, zpad)
+                if sums is not None:
+                    sums = sums[:, :, :dy.c].contiguous()
         elif kind == "gn":
             _, x_in, gn, stats, gamma, y_relu, mask_in = rec
             if y_relu is not None and not pm:
                 dy, _ = ops.relu_bwd(dy, y_relu, False, out=dy)
-            dx, dgamma, dbeta = ops.gn_bwd(x_in, gn.num_groups, stats, gamma, dy, mask_relu=mask_in)
+                sums = None
+            if sums is not None:
+                dx, dgamma, dbeta = ops.gn_bwd_fused(x_in, gn.num_groups, stats, gamma, dy, sums,
+                                                     mask_relu=mask_in)
+            else:
+                dx, dgamma, dbeta = ops.gn_bwd(x_in, gn.num_groups, stats, gamma, dy, mask_relu=mask_in)
+            sums = None
             _acc(grads, gn.weight, dgamma)
             _acc(grads, gn.bias, dbeta)
             dy = dx
             out_premasked = bool(mask_in)
         elif kind == "bn":
             _, x_in, bn, mean, rstd, gamma, y_relu, was_training, mask_in = rec
+            if not was_training or (y_relu is not None and not pm):
+                sums = None
             # eval-mode BN (frozen statistics) is a per-channel affine map: no mean/variance terms
             dx, dgamma, dbeta = ops.bn_bwd(x_in, dy, None if pm else y_relu, mean, rstd, gamma,
-                                           frozen=not was_training, mask_relu=mask_in)
+                                           frozen=not was_training, mask_relu=mask_in, colstats=sums)
+            sums = None
             _acc(grads, bn.weight, dgamma)
             _acc(grads, bn.bias, dbeta)
             dy = dx
             out_premasked = bool(mask_in)
-    return dy, out_premasked
+    return dy, out_premasked, sums
 
 
 def block_fwd(x: CL, specs: List[LayerSpec], training: bool, tape: Optional[list],
-              out: Optional[CL] = None, in_relu: bool = False):
+              out: Optional[CL] = None, in_relu: bool = False,
+              in_sums: Optional[torch.Tensor] = None, want_sums: bool = False):
     """A DoubleConv / DoubleConvolution / unetConv2: consecutive layers, last one writes ``out``.
-    Returns (y, y_is_relu_output)."""
-    flag = in_relu
+    Returns (y, y_is_relu_output, y_sums) — see single_conv_fwd for the sums."""
+    flag, sums = in_relu, in_sums
     for j, spec in enumerate(specs):
         sub = [] if tape is not None else None
-        x, flag = single_conv_fwd(x, spec, training, sub, out=out if j == len(specs) - 1 else None,
-                                  in_relu=flag)
+        is_last = j == len(specs) - 1
+        want = want_sums if is_last else specs[j + 1].order[0] in "gb"
+        x, flag, sums = single_conv_fwd(x, spec, training, sub, out=out if is_last else None,
+                                        in_relu=flag, in_sums=sums, want_sums=want)
         if tape is not None:
             tape.append(sub)
-    return x, flag
+    return x, flag, sums
 
 
 def block_bwd(dy: CL, tape: list, nlayers: int, grads: Grads, need_dx: bool = True,
-              premasked: bool = False):
-    """Returns (dx, dx_premasked) — see single_conv_bwd."""
-    pm = premasked
+              premasked: bool = False, dy_sums: Optional[torch.Tensor] = None, consumer=None):
+    """Returns (dx, dx_premasked, dx_sums) — see single_conv_bwd."""
+    pm, sums = premasked, dy_sums
     for j in range(nlayers):
         recs = tape.pop()
-        dy, pm = single_conv_bwd(dy, recs, grads, need_dx=need_dx or j < nlayers - 1, premasked=pm)
-    return dy, pm
+        inner = j < nlayers - 1
+        nxt = tape[-1][-1] if inner else consumer   # the previous layer's last op receives our dx
+        dy, pm, sums = single_conv_bwd(dy, recs, grads, need_dx=need_dx or inner, premasked=pm,
+                                       dy_sums=sums, consumer=nxt)
+    return dy, pm, sums
 
 
 # ===================================================================================== 2D U-Net
@@ -247,10 +316,10 @@ def unet2d_forward(net, images: torch.Tensor, training: bool, tape: Optional[lis
             dst = cat.slice(c, c)
         else:  # odd sizes need the centre crop of CropAndConcat: keep the skip in its own buffer
             dst = None
-        x, relu = block_fwd(x, unet2d_specs(net.down_conv[i]), training, tape, out=dst, in_relu=relu)
+        x, relu, _ = block_fwd(x, unet2d_specs(net.down_conv[i]), training, tape, out=dst, in_relu=relu)
         skips.append(x)
         x = ops.maxpool_fwd(x, 1)
-    x, relu = block_fwd(x, unet2d_specs(net.middle_conv), training, tape, in_relu=relu)
+    x, relu, _ = block_fwd(x, unet2d_specs(net.middle_conv), training, tape, in_relu=relu)
     for i in range(n_lvl):
         skip = skips[n_lvl - 1 - i]
         up = net.up_sample[i].up
@@ -270,7 +339,7 @@ def unet2d_forward(net, images: torch.Tensor, training: bool, tape: Optional[lis
         if tape is not None:
             tape.append(("up", x, up, wp_bwd, c, crop, skip, relu))
         # the concat mixes a ConvTranspose output with a ReLU output: not maskable as a whole
-        x, relu = block_fwd(cat, unet2d_specs(net.up_conv[i]), training, tape, in_relu=False)
+        x, relu, _ = block_fwd(cat, unet2d_specs(net.up_conv[i]), training, tape, in_relu=False)
     if tape is not None:
         tape.append(("skips", skips, relu))
     return x
@@ -290,9 +359,12 @@ def unet2d_backward(net, tape: list, dfeat: CL, grads: Grads, premasked: bool) -
     n_lvl = len(net.down_conv)
     _, skips, _ = tape.pop()
     dskips: List[Optional[CL]] = [None] * n_lvl
-    d, pm = dfeat, premasked
+    d, pm, d_sums = dfeat, premasked, None
     for i in range(n_lvl - 1, -1, -1):
-        dcat, _ = block_bwd(d, tape, 2, grads, premasked=pm)
+        # the ConvTranspose bias gradient is the column sum of its half of dcat: have dgrad produce it
+        want_up_bias = net.up_sample[i].up.bias is not None
+        dcat, _, dcat_sums = block_bwd(d, tape, 2, grads, premasked=pm, dy_sums=d_sums,
+                                       consumer=("sum",) if want_up_bias else None)
         _, x_in, up, wp_bwd, c, crop, skip, x_relu = tape.pop()
         d_up = dcat.slice(0, c)
         if crop is None:
@@ -303,16 +375,24 @@ def unet2d_backward(net, tape: list, dfeat: CL, grads: Grads, premasked: bool) -
             full[:, :, top:top + dcat.h, left:left + dcat.w, :] = dcat.dense()[..., c:]
             dskips[n_lvl - 1 - i] = CL(full.contiguous())
         if up.bias is not None:
-            _acc(grads, up.bias, ops.bias_grad(d_up))
+            if dcat_sums is not None:
+                _acc(grads, up.bias, dcat_sums[:, 0, :c].sum(0).float())
+            else:
+                _acc(grads, up.bias, ops.bias_grad(d_up))
         _acc(grads, up.weight, ops.convt_bwd_weight(x_in, d_up, impl=IMPL))
         fuse = bool(x_relu and x_in.is_full())
-        d = ops.convt_bwd_data(d_up, wp_bwd, mask=x_in if fuse else None, impl=IMPL)
+        # x_in is the ReLU output of the block below: its second conv's bias gradient is the column
+        # sum of the masked gradient this kernel writes
+        if fuse:
+            d, d_sums = ops.convt_bwd_data(d_up, wp_bwd, mask=x_in, impl=IMPL, stats=True)
+        else:
+            d, d_sums = ops.convt_bwd_data(d_up, wp_bwd, mask=None, impl=IMPL), None
         pm = fuse
-    d, pm = block_bwd(d, tape, 2, grads, premasked=pm)
+    d, pm, _ = block_bwd(d, tape, 2, grads, premasked=pm, dy_sums=d_sums)
     for i in range(n_lvl - 1, -1, -1):
         # skips are ReLU outputs of DoubleConvolution: fold their ReLU backward into the pool backward
         d = ops.maxpool_bwd(skips[i], d, 1, add=dskips[i], mask_relu=True)
-        d, pm = block_bwd(d, tape, 2, grads, need_dx=i > 0, premasked=True)
+        d, pm, _ = block_bwd(d, tape, 2, grads, need_dx=i > 0, premasked=True)
 
 
 # ===================================================================================== 3D family
@@ -335,22 +415,27 @@ def unet3d_forward(net, x_in: torch.Tensor, training: bool, tape: Optional[list]
     skips: List[CL] = []
     relu = False
     skip_relu: List[bool] = []
+    skip_sums: List[Optional[torch.Tensor]] = []
+    x_sums: Optional[torch.Tensor] = None
+    norm_first = order[0] in "gb"   # blocks start with a norm: their producers hand over statistics
     for i, enc in enumerate(net.encoders):
         if enc.pooling is not None:
             pooled = ops.maxpool_fwd(x, 2 if is3d else 1)
             if tape is not None:
                 tape.append(("pool", x, relu))
-            x = pooled
+            x, x_sums = pooled, None
         cs = enc.basic_module.SingleConv2.conv.out_channels
         dst = None
         if i < n_enc - 1:
             cx = _decoder_up_channels(net, n_enc - 2 - i)
             cat = CL.empty(x.n, x.d, x.h, x.w, cs + cx, x.device)
             dst = cat.slice(0, cs)
-        x, relu = block_fwd(x, double_conv_specs(enc.basic_module, order), training, tape, out=dst,
-                            in_relu=relu)
+        x, relu, x_sums = block_fwd(x, double_conv_specs(enc.basic_module, order), training, tape,
+                                    out=dst, in_relu=relu, in_sums=x_sums,
+                                    want_sums=norm_first and len(net.decoders) > 0)
         skips.append(x)
         skip_relu.append(relu)
+        skip_sums.append(x_sums)
     for j, dec in enumerate(net.decoders):
         skip = skips[n_enc - 2 - j]
         cat = CL(skip.buf)
@@ -358,6 +443,7 @@ def unet3d_forward(net, x_in: torch.Tensor, training: bool, tape: Optional[list]
         size = (skip.d, skip.h, skip.w)
         up_dst = cat.slice(skip.c, cx)
         ct = getattr(getattr(dec.upsampling, "upsample", None), "conv_transposed", None)
+        cat_sums: Optional[torch.Tensor] = None
         if ct is not None:
             wp_fwd, wp_bwd, kd = ops.deconv_repack_weight(ct.weight)
             planes = ops.deconv_fwd(x, wp_fwd, kd, impl=IMPL)
@@ -370,8 +456,18 @@ def unet3d_forward(net, x_in: torch.Tensor, training: bool, tape: Optional[list]
             if tape is not None:
                 tape.append(("nearest", (x.d, x.h, x.w), skip.c, cx))
             cat_relu = relu and skip_relu[n_enc - 2 - j]   # both halves are ReLU outputs
-        x, relu = block_fwd(cat, double_conv_specs(dec.basic_module, order), training, tape,
-                            in_relu=cat_relu)
+            # nearest up-sampling by whole factors replicates every voxel f times: the statistics of
+            # the concat buffer are those of its two producers, no extra pass
+            s_skip = skip_sums[n_enc - 2 - j]
+            exact = size[0] % x.d == 0 and size[1] % x.h == 0 and size[2] % x.w == 0
+            if x_sums is not None and s_skip is not None and exact:
+                f = (size[0] // x.d) * (size[1] // x.h) * (size[2] // x.w)
+                cat_sums = torch.cat([s_skip, x_sums * float(f)], dim=2)
+        if ct is not None:
+            cat_sums = None
+        x, relu, x_sums = block_fwd(cat, double_conv_specs(dec.basic_module, order), training, tape,
+                                    in_relu=cat_relu, in_sums=cat_sums,
+                                    want_sums=norm_first and j < len(net.decoders) - 1)
     if tape is not None:
         tape.append(("skips", skips, relu))
     return x
@@ -395,7 +491,7 @@ def unet3d_backward(net, tape: list, dfeat: CL, grads: Grads, premasked: bool) -
     dskips: List[Optional[CL]] = [None] * n_enc
     d, pm = dfeat, premasked
     for j in range(len(net.decoders) - 1, -1, -1):
-        dcat, cat_pm = block_bwd(d, tape, 2, grads, premasked=pm)
+        dcat, cat_pm, _ = block_bwd(d, tape, 2, grads, premasked=pm)
         pm = False   # up-sampling backward sums children: the result is not a masked gradient
         rec = tape.pop()
         if rec[0] == "deconv":
@@ -412,7 +508,7 @@ def unet3d_backward(net, tape: list, dfeat: CL, grads: Grads, premasked: bool) -
             pm = cat_pm
         dskips[n_enc - 2 - j] = dcat.slice(0, cs)
     for i in range(n_enc - 1, -1, -1):
-        d, _ = block_bwd(d, tape, 2, grads, need_dx=i > 0, premasked=pm)
+        d, _, _ = block_bwd(d, tape, 2, grads, need_dx=i > 0, premasked=pm)
         if i > 0:
             _, pre, pre_relu = tape.pop()
             # the skip half of the concat gradient joins the gradient routed back through the pool;
@@ -486,7 +582,7 @@ class _BlockFunction(torch.autograd.Function):
         need_grad = any(ctx.needs_input_grad)
         tape = [] if need_grad else None
         with torch.no_grad():
-            y, _ = block_fwd(ops.from_nchw(x), specs, mod.training, tape)
+            y, _, _ = block_fwd(ops.from_nchw(x), specs, mod.training, tape)
             out = ops.to_nchw(y, x.dim() == 5)
         ctx.tape, ctx.n, ctx.params, ctx.x_grad = tape, len(specs), params, ctx.needs_input_grad[2]
         return out
@@ -495,7 +591,7 @@ class _BlockFunction(torch.autograd.Function):
     def backward(ctx, dout):
         grads: Grads = {}
         dy = ops.from_nchw(dout)
-        dx, _ = block_bwd(dy, ctx.tape, ctx.n, grads, need_dx=ctx.x_grad)
+        dx, _, _ = block_bwd(dy, ctx.tape, ctx.n, grads, need_dx=ctx.x_grad)
         gx = ops.to_nchw(dx, dout.dim() == 5) if ctx.x_grad else None
         return (None, None, gx) + tuple(grads.get(p) if p.requires_grad else None for p in ctx.params)
 

@@ -126,19 +126,34 @@ def conv_repack_weight(w: torch.Tensor, need_bwd: bool = True):
     return fwd, bwd, k
 
 
+def colstats_buffer(n: int, c: int, device) -> torch.Tensor:
+    """fp64 [n][2][c] accumulator for the fused epilogue statistics (sum r, sum r*r | sum r*dot)."""
+    return torch.zeros((n, 2, c), dtype=torch.float64, device=device)
+
+
 def conv_fwd(x: CL, wp_fwd: torch.Tensor, k, bias: Optional[torch.Tensor], relu: bool,
-             out: Optional[CL] = None, impl: int = 0) -> CL:
+             out: Optional[CL] = None, impl: int = 0, stats: bool = False):
+    """``stats=True`` also returns fp64 [n][2][c_out] = per-sample (sum y, sum y^2) of the stored
+    output, accumulated in the GEMM epilogue (b200_conv_fwd_stats)."""
     c_out = wp_fwd.shape[1]
     if out is None:
         out = CL.empty(x.n, x.d, x.h, x.w, c_out, x.device)
     assert out.c == c_out and out.dims == x.dims and wp_fwd.shape[2] == x.c
     d = conv_desc(x, c_out, k, out.ctot, out.coff, relu, impl)
-    call("b200_conv_fwd", C.byref(d), _p(x.buf), _p(wp_fwd), _p(bias), _p(out.buf), _stream())
-    return out
+    if not stats:
+        call("b200_conv_fwd", C.byref(d), _p(x.buf), _p(wp_fwd), _p(bias), _p(out.buf), _stream())
+        return out
+    cs = colstats_buffer(x.n, c_out, x.device)
+    call("b200_conv_fwd_stats", C.byref(d), _p(x.buf), _p(wp_fwd), _p(bias), _p(out.buf), _p(cs),
+         _stream())
+    return out, cs
 
 
 def conv_bwd_data(dy: CL, wp_bwd: torch.Tensor, k, mask: Optional[CL] = None,
-                  out: Optional[CL] = None, impl: int = 0) -> CL:
+                  out: Optional[CL] = None, impl: int = 0, stats: bool = False,
+                  dot: Optional[CL] = None):
+    """``stats=True`` also returns fp64 [n][2][c_in] = per-sample (sum dx, sum dx^2), or
+    (sum dx, sum dx*dot) when ``dot`` (a tensor of dx's shape) is given."""
     c_in, c_out = wp_bwd.shape[1], wp_bwd.shape[2]
     assert dy.c == c_out
     if out is None:
@@ -147,9 +162,18 @@ def conv_bwd_data(dy: CL, wp_bwd: torch.Tensor, k, mask: Optional[CL] = None,
         assert mask.ctot == out.ctot and mask.coff == out.coff and mask.dims == out.dims
     d = ConvDesc(dy.n, dy.d, dy.h, dy.w, c_in, c_out, k[0], k[1], k[2], out.ctot, out.coff,
                  dy.ctot, dy.coff, 0, impl)
-    call("b200_conv_bwd_data", C.byref(d), _p(dy.buf), _p(wp_bwd),
-         _p(None if mask is None else mask.buf), _p(out.buf), _stream())
-    return out
+    if not stats:
+        call("b200_conv_bwd_data", C.byref(d), _p(dy.buf), _p(wp_bwd),
+             _p(None if mask is None else mask.buf), _p(out.buf), _stream())
+        return out
+    if dot is not None:
+        assert dot.c == c_in and dot.dims == out.dims
+    cs = colstats_buffer(dy.n, c_in, dy.device)
+    call("b200_conv_bwd_data_stats", C.byref(d), _p(dy.buf), _p(wp_bwd),
+         _p(None if mask is None else mask.buf), _p(out.buf),
+         _p(None if dot is None else dot.buf), 0 if dot is None else dot.ctot,
+         0 if dot is None else dot.coff, _p(cs), _stream())
+    return out, cs
 
 
 def conv_bwd_weight(x: CL, dy: CL, k, w_shape, impl: int = 0) -> torch.Tensor:
@@ -184,16 +208,21 @@ def convt_fwd(x: CL, wp_fwd, bias, out: Optional[CL] = None, impl: int = 0) -> C
 
 
 def convt_bwd_data(dy: CL, wp_bwd, mask: Optional[CL] = None, out: Optional[CL] = None,
-                   impl: int = 0) -> CL:
+                   impl: int = 0, stats: bool = False):
     c_in, c_out = wp_bwd.shape[1], wp_bwd.shape[2]
     assert dy.c == c_out and dy.d == 1
     h, w = dy.h // 2, dy.w // 2
     if out is None:
         out = CL.empty(dy.n, 1, h, w, c_in, dy.device)
     d = ConvTDesc(dy.n, h, w, c_in, c_out, out.ctot, out.coff, dy.ctot, dy.coff, impl)
-    call("b200_convt2x2_bwd_data", C.byref(d), _p(dy.buf), _p(wp_bwd),
-         _p(None if mask is None else mask.buf), _p(out.buf), _stream())
-    return out
+    if not stats:
+        call("b200_convt2x2_bwd_data", C.byref(d), _p(dy.buf), _p(wp_bwd),
+             _p(None if mask is None else mask.buf), _p(out.buf), _stream())
+        return out
+    cs = colstats_buffer(dy.n, c_in, dy.device)
+    call("b200_convt2x2_bwd_data_stats", C.byref(d), _p(dy.buf), _p(wp_bwd),
+         _p(None if mask is None else mask.buf), _p(out.buf), _p(cs), _stream())
+    return out, cs
 
 
 def convt_bwd_weight(x: CL, dy: CL, impl: int = 0) -> torch.Tensor:
@@ -357,6 +386,14 @@ def gn_stats(x: CL, groups: int, eps: float) -> torch.Tensor:
     return stats
 
 
+def gn_stats_from_sums(sums: torch.Tensor, spatial: int, groups: int, eps: float) -> torch.Tensor:
+    """(mean, rstd) per (sample, group) from fp64 [n][2][c] per-channel (sum x, sum x^2)."""
+    n, _, c = sums.shape
+    stats = torch.empty((n, groups, 2), dtype=torch.float32, device=sums.device)
+    call("b200_gn_stats_finalize", n, spatial, c, groups, eps, _p(sums.contiguous()), _p(stats), _stream())
+    return stats
+
+
 def gn_apply(x: CL, groups, stats, gamma, beta, relu: bool, out: Optional[CL] = None) -> CL:
     if out is None:
         out = x.new_like()
@@ -376,6 +413,20 @@ def gn_bwd(x: CL, groups, stats, gamma, dy: CL, out: Optional[CL] = None, mask_r
     return out, dgamma, dbeta
 
 
+def gn_bwd_fused(x: CL, groups, stats, gamma, dy: CL, colstats: torch.Tensor,
+                 out: Optional[CL] = None, mask_relu: bool = False):
+    """GroupNorm backward in one pass: ``colstats`` fp64 [n][2][c] = (sum dy, sum dy*x) came out of the
+    epilogue of the kernel that produced dy."""
+    if out is None:
+        out = x.new_like()
+    dgamma = torch.zeros(x.c, dtype=torch.float32, device=x.device)
+    dbeta = torch.zeros(x.c, dtype=torch.float32, device=x.device)
+    scratch = torch.empty(x.n * groups * 2, dtype=torch.float32, device=x.device)
+    call("b200_gn_bwd_fused", x.n, x.spatial, x.c, groups, x.view(), _p(stats), _p(gamma), dy.view(),
+         out.view(), _p(dgamma), _p(dbeta), _p(colstats), _p(scratch), int(mask_relu), _stream())
+    return out, dgamma, dbeta
+
+
 def bn_stats(x: CL) -> torch.Tensor:
     sums = torch.zeros((2, x.c), dtype=torch.float64, device=x.device)
     call("b200_bn_stats", x.npos, x.c, x.view(), _p(sums), _stream())
@@ -391,13 +442,19 @@ def bn_apply(x: CL, mean, rstd, gamma, beta, relu: bool, out: Optional[CL] = Non
 
 
 def bn_bwd(x: CL, dy: CL, relu_out: Optional[CL], mean, rstd, gamma, out: Optional[CL] = None,
-           frozen: bool = False, mask_relu: bool = False):
+           frozen: bool = False, mask_relu: bool = False, colstats: Optional[torch.Tensor] = None):
+    """``colstats`` fp64 [n][2][c] = (sum dz, sum dz*x) from the producer of dy (already masked)
+    replaces the reduction pass."""
     if out is None:
         out = x.new_like()
-    red = torch.zeros((2, x.c), dtype=torch.float32, device=x.device)
     rv = _NULL_VIEW if relu_out is None else relu_out.view()
-    call("b200_bn_bwd_reduce", x.npos, x.c, x.view(), dy.view(), rv, _p(mean), _p(rstd), _p(red),
-         _stream())
+    if colstats is not None:
+        red = torch.empty((2, x.c), dtype=torch.float32, device=x.device)
+        call("b200_bn_bwd_red_from_sums", x.n, x.c, _p(colstats), _p(mean), _p(rstd), _p(red), _stream())
+    else:
+        red = torch.zeros((2, x.c), dtype=torch.float32, device=x.device)
+        call("b200_bn_bwd_reduce", x.npos, x.c, x.view(), dy.view(), rv, _p(mean), _p(rstd), _p(red),
+             _stream())
     # frozen statistics (eval-mode BN): the batch-mean / batch-variance terms vanish
     red_apply = torch.zeros_like(red) if frozen else red
     call("b200_bn_bwd_apply", x.npos, x.c, x.view(), dy.view(), rv, _p(mean), _p(rstd), _p(gamma),

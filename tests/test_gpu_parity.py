@@ -359,3 +359,77 @@ def test_empty_batch_is_a_noop(B):
     x = ops.CL(torch.empty((0, 1, 8, 8, 16), dtype=torch.bfloat16, device="cuda"))
     y = ops.maxpool_fwd(x, 1)
     assert y.n == 0
+
+
+def test_fused_epilogue_statistics(B):
+    """Column statistics fused into the GEMM epilogues (b200_conv_*_stats) equal the sums of the tensor
+    the kernel stored: (sum y, sum y^2) in forward; (sum dx, sum dx*dot) with the ReLU mask applied in
+    backward-data; tensor-core and CUDA-core paths agree; channel-slice outputs and ragged planes."""
+    from mdeical_image_segmentation_b200 import ops
+    from mdeical_image_segmentation_b200.ops import CL
+    g = torch.Generator().manual_seed(3)
+    cases = [(2, 1, 40, 24, 64, 64), (2, 6, 20, 12, 32, 96), (3, 4, 4, 4, 128, 256), (1, 1, 19, 23, 64, 16),
+             (2, 1, 64, 64, 128, 512)]
+    for (n, d, h, w, cin, cout) in cases:
+        x = CL(torch.randn((n, d, h, w, cin), generator=g).to(torch.bfloat16).cuda())
+        dy = CL(torch.randn((n, d, h, w, cout), generator=g).to(torch.bfloat16).cuda())
+        ks = (3, 3, 3) if d > 1 else (3, 3)
+        wt = (torch.randn((cout, cin) + ks, generator=g) / (cin * 9) ** 0.5).cuda()
+        bias = torch.randn(cout, generator=g).cuda()
+        fwd, bwd, k = ops.conv_repack_weight(wt)
+        for impl in (1, 2):
+            # forward into a channel slice of a wider buffer
+            cat = CL.empty(n, d, h, w, cout + 32, "cuda")
+            y, cs = ops.conv_fwd(x, fwd, k, bias, True, out=cat.slice(32, cout), impl=impl, stats=True)
+            yd = y.dense().double()
+            ref = torch.stack([yd.sum((1, 2, 3)), (yd * yd).sum((1, 2, 3))], 1)      # [n][2][c]
+            assert rel_l2(cs.cpu(), ref.cpu()) < 2e-5, (impl, n, d, h, w, cin, cout)
+            # plain call stores the same tensor
+            y0 = ops.conv_fwd(x, fwd, k, bias, True, impl=impl).dense()
+            assert torch.equal(y0, y.dense())
+            # backward data with mask + dot
+            dx, cs2 = ops.conv_bwd_data(dy, bwd, k, mask=x, impl=impl, stats=True, dot=x)
+            dxd = dx.dense().double()
+            assert bool((dxd[x.dense() <= 0] == 0).all())
+            ref2 = torch.stack([dxd.sum((1, 2, 3)), (dxd * x.dense().double()).sum((1, 2, 3))], 1)
+            assert rel_l2(cs2.cpu(), ref2.cpu()) < 2e-5, (impl, "bwd")
+            dx0 = ops.conv_bwd_data(dy, bwd, k, mask=x, impl=impl).dense()
+            assert torch.equal(dx0, dx.dense())
+    # ConvTranspose 2x2 backward-data with the fused column sum
+    xt = CL(torch.randn((2, 1, 16, 24, 128), generator=g).to(torch.bfloat16).cuda())
+    dyt = CL(torch.randn((2, 1, 32, 48, 64), generator=g).to(torch.bfloat16).cuda())
+    wtt = (torch.randn((128, 64, 2, 2), generator=g) / 16).cuda()
+    wf, wb = ops.convt_repack_weight(wtt)
+    for impl in (1, 2):
+        dxt, cst = ops.convt_bwd_data(dyt, wb, mask=xt, impl=impl, stats=True)
+        dd = dxt.dense().double()
+        reft = torch.stack([dd.sum((1, 2, 3)), (dd * dd).sum((1, 2, 3))], 1)
+        assert rel_l2(cst.cpu(), reft.cpu()) < 2e-5
+        # scatter epilogue (forward) against the CUDA-core kernel
+    y1 = ops.convt_fwd(xt, wf, None, impl=1).dense().float()
+    y2 = ops.convt_fwd(xt, wf, None, impl=2).dense().float()
+    assert rel_l2(y1.cpu(), y2.cpu()) < 3e-3
+    # planes large enough for the weight-resident schedules (one column tile per CTA; 1 and 2 column tiles)
+    for (n, hh, ww, ci, co) in [(4, 128, 128, 128, 64), (2, 128, 128, 256, 128)]:
+        xb = CL(torch.randn((n, 1, hh, ww, ci), generator=g).to(torch.bfloat16).cuda())
+        wb_ = (torch.randn((ci, co, 2, 2), generator=g) / ci ** 0.5).cuda()
+        bb = torch.randn(co, generator=g).cuda()
+        wf2, wb2 = ops.convt_repack_weight(wb_)
+        a1 = ops.convt_fwd(xb, wf2, bb, impl=1).dense().float()
+        a2 = ops.convt_fwd(xb, wf2, bb, impl=2).dense().float()
+        assert rel_l2(a1.cpu(), a2.cpu()) < 3e-3, (n, hh, ww, ci, co)
+        dyb = CL(torch.randn((n, 1, 2 * hh, 2 * ww, co), generator=g).to(torch.bfloat16).cuda())
+        b1 = ops.convt_bwd_data(dyb, wb2, mask=xb, impl=1).dense().float()
+        b2 = ops.convt_bwd_data(dyb, wb2, mask=xb, impl=2).dense().float()
+        assert rel_l2(b1.cpu(), b2.cpu()) < 3e-3, (n, hh, ww, ci, co)
+    # weight-resident halo schedule (2D, C_in * C_out small) against the streaming one
+    lib = __import__("mdeical_image_segmentation_b200._lib", fromlist=["lib"]).lib()
+    xr = CL(torch.randn((4, 1, 96, 80, 64), generator=g).to(torch.bfloat16).cuda())
+    for cout in (64, 128):
+        wr = (torch.randn((cout, 64, 3, 3), generator=g) / 24).cuda()
+        fr, br, kr = ops.conv_repack_weight(wr)
+        r1 = ops.conv_fwd(xr, fr, kr, None, True, impl=1).dense()
+        lib.b200_set_tuning(3, 0)
+        r0 = ops.conv_fwd(xr, fr, kr, None, True, impl=1).dense()
+        lib.b200_set_tuning(3, 1)
+        assert torch.equal(r0, r1), cout
