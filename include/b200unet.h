@@ -38,7 +38,9 @@ int b200_last_impl(void);
 /* tuning / A-B knobs (process-wide): key 0 = halo-reuse fwd/dgrad kernel,
  * key 1 = halo-reuse weight-gradient kernel (value 1 = on (default), 0 = off),
  * key 2 = max row-blocks per super-tile of the halo kernel (1, 2 or 4; default 4),
- * key 3 = weight-resident mode of the forward / dgrad kernels (1 = on (default), 0 = off) */
+ * key 3 = weight-resident mode of the forward / dgrad kernels (1 = on (default), 0 = off),
+ * key 4 = epilogue bring-up mode (0 = normal; 1 = no global stores, 2 = no epilogue work: timing only),
+ * key 5 = epilogue warps of the forward / dgrad kernels (0 = heuristic (default), 4 or 8) */
 int b200_set_tuning(int key, int value);
 
 /* ---- 3x3 / 3x3x3 / 1x1 "same" convolution ------------------------------------------------------
@@ -72,9 +74,14 @@ int b200_conv_bwd_data(const b200_conv_desc* desc, const void* dy, const void* w
  * the (sum dy, sum dy*x) reductions of the norm backward in backward.  colstats == NULL: plain call. */
 int b200_conv_fwd_stats(const b200_conv_desc* desc, const void* x, const void* wp_fwd,
                         const float* bias, void* y, double* colstats, b200_stream_t stream);
+#define B200_STATS_NONE 0
+#define B200_STATS_SUM 1      /* only [.][0][c] (e.g. a bias gradient); [.][1][c] is left untouched */
+#define B200_STATS_SUM_SQ 2   /* sum r, sum r*r                                                    */
+#define B200_STATS_SUM_DOT 3  /* sum r, sum r*dot                                                  */
 int b200_conv_bwd_data_stats(const b200_conv_desc* desc, const void* dy, const void* wp_bwd,
-                             const void* relu_mask, void* dx, const void* dot, int32_t dot_ctot,
-                             int32_t dot_coff, double* colstats, b200_stream_t stream);
+                             const void* relu_mask, void* dx, int32_t stats_kind, const void* dot,
+                             int32_t dot_ctot, int32_t dot_coff, double* colstats,
+                             b200_stream_t stream);
 /* dw fp32 (c_out, c_in, kd, kh, kw) is ACCUMULATED into (caller zeroes it) */
 int b200_conv_bwd_weight(const b200_conv_desc* desc, const void* x, const void* dy, float* dw,
                          b200_stream_t stream);
@@ -96,9 +103,10 @@ int b200_convt2x2_fwd(const b200_convt_desc* desc, const void* x, const void* wp
                       const float* bias, void* y, b200_stream_t stream);
 int b200_convt2x2_bwd_data(const b200_convt_desc* desc, const void* dy, const void* wp_bwd,
                            const void* relu_mask, void* dx, b200_stream_t stream);
-/* colstats fp64 [n][2][c_in] += (sum dx, sum dx*dx), see b200_conv_bwd_data_stats */
+/* colstats fp64 [n][2][c_in] += column statistics of dx (B200_STATS_SUM or _SUM_SQ), see
+ * b200_conv_bwd_data_stats */
 int b200_convt2x2_bwd_data_stats(const b200_convt_desc* desc, const void* dy, const void* wp_bwd,
-                                 const void* relu_mask, void* dx, double* colstats,
+                                 const void* relu_mask, void* dx, int32_t stats_kind, double* colstats,
                                  b200_stream_t stream);
 int b200_convt2x2_bwd_weight(const b200_convt_desc* desc, const void* x, const void* dy, float* dw,
                              b200_stream_t stream);

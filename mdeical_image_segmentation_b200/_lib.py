@@ -47,8 +47,8 @@ SIGNATURES = {
     "b200_conv_bwd_data": [_PC, _P, _P, _P, _P, _P],
     "b200_conv_bwd_weight": [_PC, _P, _P, _P, _P],
     "b200_conv_fwd_stats": [_PC, _P, _P, _P, _P, _P, _P],
-    "b200_conv_bwd_data_stats": [_PC, _P, _P, _P, _P, _P, _I, _I, _P, _P],
-    "b200_convt2x2_bwd_data_stats": [_PT, _P, _P, _P, _P, _P, _P],
+    "b200_conv_bwd_data_stats": [_PC, _P, _P, _P, _P, _I, _P, _I, _I, _P, _P],
+    "b200_convt2x2_bwd_data_stats": [_PT, _P, _P, _P, _P, _I, _P, _P],
     "b200_gn_stats_finalize": [_I, _L, _I, _I, _F, _P, _P, _P],
     "b200_gn_bwd_fused": [_I, _L, _I, _I, View, _P, _P, View, View, _P, _P, _P, _P, _I, _P],
     "b200_bn_bwd_red_from_sums": [_I, _I, _P, _P, _P, _P, _P],

@@ -10,6 +10,7 @@ extern int g_halo_rmax;
 extern int g_halo_resident;
 extern int g_gemm_resident;
 extern int g_epi_dbg;
+extern int g_epi_warps;
 int direct_gemm_conv(const TcGemmProblem& p, cudaStream_t stream);
 int direct_wgrad(const TcWgradProblem& p, cudaStream_t stream);
 static thread_local int g_last_impl = 0;
@@ -107,7 +108,7 @@ static unsigned grid_for(long total) {
 // Stand-alone column statistics of a stored tensor (what the tcgen05 epilogues fuse): one block row per
 // sample, a thread per channel.  Only the CUDA-core fallback path uses it.
 __global__ void colstats_kernel(long spatial, int c, const bf16* out, int octot, int ocoff, const bf16* dot,
-                                int dctot, int dcoff, double* stats) {
+                                int dctot, int dcoff, double* stats, int sum_only) {
   const int b = blockIdx.y;
   const long chunk = (spatial + gridDim.x - 1) / gridDim.x;
   const long pbeg = (long)blockIdx.x * chunk;
@@ -123,7 +124,7 @@ __global__ void colstats_kernel(long spatial, int c, const bf16* out, int octot,
     }
     if (pend > pbeg) {
       atomicAdd(stats + ((long)b * 2 + 0) * c + ch, (double)s0);
-      atomicAdd(stats + ((long)b * 2 + 1) * c + ch, (double)s1);
+      if (!sum_only) atomicAdd(stats + ((long)b * 2 + 1) * c + ch, (double)s1);
     }
   }
 }
@@ -140,7 +141,8 @@ static int run_gemm(const TcGemmProblem& p, int impl, cudaStream_t s) {
     long gx = spatial / 256;
     gx = gx < 1 ? 1 : (gx > 1024 ? 1024 : gx);
     colstats_kernel<<<dim3((unsigned)gx, (unsigned)p.pn), 128, 0, s>>>(
-        spatial, p.ncols, p.out, p.out_ctot, p.out_coff, p.dot, p.dot_ctot, p.dot_coff, p.stats);
+        spatial, p.ncols, p.out, p.out_ctot, p.out_coff, p.dot, p.dot_ctot, p.dot_coff, p.stats,
+        p.stats_kind == B200_STATS_SUM && !p.dot);
     B200_LAUNCH_CHECK();
     return B200_OK;
   }
@@ -187,6 +189,7 @@ int b200_set_tuning(int key, int value) {
   if (key == 1) { b200::g_wgrad_halo_mode = value; return B200_OK; }
   if (key == 2) { b200::g_halo_rmax = value; return B200_OK; }
   if (key == 4) { b200::g_epi_dbg = value; return B200_OK; }
+  if (key == 5) { b200::g_epi_warps = value; return B200_OK; }
   if (key == 3) { b200::g_halo_resident = value; b200::g_gemm_resident = value; return B200_OK; }
   return B200_ERR_BAD_ARG;
 }
@@ -220,17 +223,19 @@ int b200_conv_fwd_stats(const b200_conv_desc* d, const void* x, const void* wp_f
   p.pn = d->n; p.pd = d->d; p.ph = d->h; p.pw = d->w;
   p.out = (bf16*)y; p.out_ctot = d->out_ctot; p.out_coff = d->out_coff;
   p.bias = bias; p.relu = d->relu;
-  p.stats = colstats;
+  p.stats = colstats; p.stats_kind = B200_STATS_SUM_SQ;
   return run_gemm(p, d->impl, (cudaStream_t)stream);
 }
 
 int b200_conv_bwd_data(const b200_conv_desc* d, const void* dy, const void* wp_bwd,
                        const void* relu_mask, void* dx, b200_stream_t stream) {
-  return b200_conv_bwd_data_stats(d, dy, wp_bwd, relu_mask, dx, nullptr, 0, 0, nullptr, stream);
+  return b200_conv_bwd_data_stats(d, dy, wp_bwd, relu_mask, dx, B200_STATS_NONE, nullptr, 0, 0, nullptr,
+                                  stream);
 }
 int b200_conv_bwd_data_stats(const b200_conv_desc* d, const void* dy, const void* wp_bwd,
-                             const void* relu_mask, void* dx, const void* dot, int32_t dot_ctot,
-                             int32_t dot_coff, double* colstats, b200_stream_t stream) {
+                             const void* relu_mask, void* dx, int32_t stats_kind, const void* dot,
+                             int32_t dot_ctot, int32_t dot_coff, double* colstats,
+                             b200_stream_t stream) {
   int rc = check_conv(d);
   if (rc) return rc;
   TcGemmProblem p{};
@@ -242,9 +247,11 @@ int b200_conv_bwd_data_stats(const b200_conv_desc* d, const void* dy, const void
   p.pn = d->n; p.pd = d->d; p.ph = d->h; p.pw = d->w;
   p.out = (bf16*)dx; p.out_ctot = d->in_ctot; p.out_coff = d->in_coff;
   p.mask = (const bf16*)relu_mask; p.mask_ctot = d->in_ctot; p.mask_coff = d->in_coff;
-  p.stats = colstats;
+  if (stats_kind < B200_STATS_NONE || stats_kind > B200_STATS_SUM_DOT) return B200_ERR_BAD_ARG;
+  if ((stats_kind != B200_STATS_NONE) != (colstats != nullptr)) return B200_ERR_BAD_ARG;
+  if ((stats_kind == B200_STATS_SUM_DOT) != (dot != nullptr)) return B200_ERR_BAD_ARG;
+  p.stats = colstats; p.stats_kind = stats_kind;
   p.dot = (const bf16*)dot; p.dot_ctot = dot_ctot; p.dot_coff = dot_coff;
-  if (dot && !colstats) return B200_ERR_BAD_ARG;
   return run_gemm(p, d->impl, (cudaStream_t)stream);
 }
 
@@ -297,10 +304,10 @@ int b200_convt2x2_fwd(const b200_convt_desc* d, const void* x, const void* wp_fw
 }
 int b200_convt2x2_bwd_data(const b200_convt_desc* d, const void* dy, const void* wp_bwd,
                            const void* relu_mask, void* dx, b200_stream_t stream) {
-  return b200_convt2x2_bwd_data_stats(d, dy, wp_bwd, relu_mask, dx, nullptr, stream);
+  return b200_convt2x2_bwd_data_stats(d, dy, wp_bwd, relu_mask, dx, B200_STATS_NONE, nullptr, stream);
 }
 int b200_convt2x2_bwd_data_stats(const b200_convt_desc* d, const void* dy, const void* wp_bwd,
-                                 const void* relu_mask, void* dx, double* colstats,
+                                 const void* relu_mask, void* dx, int32_t stats_kind, double* colstats,
                                  b200_stream_t stream) {
   int rc = check_convt(d);
   if (rc) return rc;
@@ -313,7 +320,10 @@ int b200_convt2x2_bwd_data_stats(const b200_convt_desc* d, const void* dy, const
   p.pn = d->n; p.pd = 1; p.ph = d->h; p.pw = d->w;
   p.out = (bf16*)dx; p.out_ctot = d->in_ctot; p.out_coff = d->in_coff;
   p.mask = (const bf16*)relu_mask; p.mask_ctot = d->in_ctot; p.mask_coff = d->in_coff;
-  p.stats = colstats;
+  if (stats_kind != B200_STATS_NONE && stats_kind != B200_STATS_SUM && stats_kind != B200_STATS_SUM_SQ)
+    return B200_ERR_BAD_ARG;
+  if ((stats_kind != B200_STATS_NONE) != (colstats != nullptr)) return B200_ERR_BAD_ARG;
+  p.stats = colstats; p.stats_kind = stats_kind;
   return run_gemm(p, d->impl, (cudaStream_t)stream);
 }
 int b200_convt2x2_bwd_weight(const b200_convt_desc* d, const void* x, const void* dy, float* dw,

@@ -99,9 +99,13 @@ __device__ __forceinline__ TileCoord decode_tile(int mt, int tiles_d, int tiles_
 // with the same coalesced pattern, and a lane always owns the same 8 channels — which makes the
 // per-channel reductions that follow a convolution (bias gradient, BatchNorm / GroupNorm statistics
 // and their backward sums) a few register adds in the epilogue instead of extra passes over HBM.
-static const int kEpiStageBytes = 2048;                          // per epilogue warp: 32 rows x 64 B
-static const int kCtrlBytes = 1024 + 4 * kEpiStageBytes + 2048;  // barriers | staging | column sums
-static const int kSmemOverhead = kCtrlBytes + 1024;              // + 1024-byte alignment slack
+static const int kEpiStageBytes = 2048;   // per epilogue warp: 32 rows x 64 B
+// control region at the start of dynamic shared memory: barriers | per-warp staging | column sums
+__host__ __device__ inline int epi_ctrl_bytes(int epi_warps) { return 1024 + epi_warps * kEpiStageBytes + 2048; }
+static inline int smem_overhead(int epi_warps) { return epi_ctrl_bytes(epi_warps) + 1024; }  // + alignment slack
+
+// statistics accumulated per (sample, output channel) over the stored result r
+enum { EPI_STATS_NONE = 0, EPI_STATS_SUM = 1, EPI_STATS_SUMSQ = 2, EPI_STATS_DOT = 3 };
 
 struct EpiArgs {
   bf16* out;
@@ -110,70 +114,90 @@ struct EpiArgs {
   int relu;
   const bf16* mask;          // out = 0 where mask <= 0 (geometry of out)
   int mask_ctot, mask_coff;
-  const bf16* dot;           // second statistic = sum out * dot instead of sum out^2
+  const bf16* dot;           // EPI_STATS_DOT: second statistic = sum out * dot
   int dot_ctot, dot_coff;
   double* stats;             // fp64 [pn][2][stats_cols] accumulated into, or NULL
   int stats_cols;
+  int epi_warps;             // 4 or 8 epilogue warps (two warps per TMEM lane quarter split the chunks)
   int dbg;                   // bring-up knob (b200_set_tuning key 4): 1 = no global stores, 2 = no epilogue work
 };
 
-__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar(int nthreads) {
+  asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory");
+}
 
 __device__ __forceinline__ uint32_t bf16x2_gt0_mask(uint32_t m) {
   const __nv_bfloat162 v = *reinterpret_cast<const __nv_bfloat162*>(&m);
   return __hgt2_mask(v, __float2bfloat162_rn(0.f));
 }
+__device__ __forceinline__ uint32_t bf16x2_relu(uint32_t v) {
+  __nv_bfloat162 h = *reinterpret_cast<__nv_bfloat162*>(&v);
+  h = __hmax2(h, __float2bfloat162_rn(0.f));
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+__device__ __forceinline__ void prefetch_l2(const void* p) {
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
 
 // Mask / dot operands of one chunk, fetched one chunk ahead of their use so that the global-load
 // latency hides behind the TMEM -> shared-memory staging of the previous chunk.
+template <bool MASK, int STATS>
 struct EpiAux {
-  uint4 m[4], d[4];
+  uint4 m[MASK ? 4 : 1];
+  uint4 d[STATS == EPI_STATS_DOT ? 4 : 1];
 };
+// Row placement of one chunk for the read-back phase: lane (4 lanes per row) stores rows it = 0..3.
+// Element offsets (position * ctot + coff) of each row's first channel in out / mask / dot; -1 = no row.
+struct EpiRows {
+  long ooff[4], moff[4], doff[4];
+};
+template <bool MASK, int STATS>
 __device__ __forceinline__ void epi_prefetch(const EpiArgs& e, int col, int ncol, int lane,
-                                             const long (&opos)[4], bool do_stats, EpiAux& a) {
+                                             const EpiRows& rw, EpiAux<MASK, STATS>& a) {
   if ((lane & 3) * 8 >= ncol) return;   // 16-column chunks: lanes 2,3 of each row own nothing
   const int c = col + (lane & 3) * 8;
-  if (e.mask) {
+  if (MASK) {
 #pragma unroll
-    for (int it = 0; it < 4; ++it) {
-      const long op = opos[it] < 0 ? 0 : opos[it];   // invalid rows read position 0 (never used)
-      a.m[it] = ldg_nc_v4(e.mask + op * e.mask_ctot + e.mask_coff + c);
-    }
+    for (int it = 0; it < 4; ++it)   // rows that do not exist read row 0 of the tensor (never used)
+      a.m[it] = ldg_nc_v4(e.mask + (rw.moff[it] < 0 ? (long)e.mask_coff : rw.moff[it]) + c);
   }
-  if (e.dot && do_stats) {
+  if (STATS == EPI_STATS_DOT) {
 #pragma unroll
-    for (int it = 0; it < 4; ++it) {
-      const long op = opos[it] < 0 ? 0 : opos[it];
-      a.d[it] = ldg_nc_v4(e.dot + op * e.dot_ctot + e.dot_coff + c);
-    }
+    for (int it = 0; it < 4; ++it)
+      a.d[it] = ldg_nc_v4(e.dot + (rw.doff[it] < 0 ? (long)e.dot_coff : rw.doff[it]) + c);
   }
 }
 
-// One warp, one chunk: v = 32 (or 16) accumulator columns of row `lane`; opos[it] = output position of
-// tile row (warp_row0 + it*8 + lane/4) or -1.  col = first output channel of the chunk.
+// One warp, one chunk: v = 32 (or 16) accumulator columns of row `lane`.  col = first output channel
+// of the chunk.  An epilogue warp shares its scheduler with at most one other epilogue warp, so every
+// instruction costs most of its latency: the variants are compile-time (MASK, STATS) so that each
+// carries only the code it needs, and all addresses are prepared by the caller.
+template <bool MASK, int STATS>
 __device__ __forceinline__ void epi_chunk(const EpiArgs& e, const uint32_t (&v)[32], int ncol, int col,
-                                          uint8_t* stg, int lane, const long (&opos)[4],
-                                          float (&acc)[16], bool do_stats, const EpiAux& aux) {
+                                          uint8_t* stg, int lane, const EpiRows& rw, float (&acc)[16],
+                                          const EpiAux<MASK, STATS>& aux) {
   uint32_t pk[16];
+  const float* bias = e.bias;
+  const bool relu = e.relu != 0;
 #pragma unroll
   for (int h = 0; h < 2; ++h) {
     if (h * 16 < ncol) {
       float f[16];
 #pragma unroll
       for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[h * 16 + j]);
-      if (e.bias) {
 #pragma unroll
-        for (int j = 0; j < 16; j += 4) {
-          const float4 b4 = __ldg(reinterpret_cast<const float4*>(e.bias + col + h * 16 + j));
-          f[j] += b4.x; f[j + 1] += b4.y; f[j + 2] += b4.z; f[j + 3] += b4.w;
-        }
-      }
-      if (e.relu) {
-#pragma unroll
-        for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
+      for (int j = 0; j < 16; j += 4) {
+        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (bias) b4 = __ldg(reinterpret_cast<const float4*>(bias + col + h * 16 + j));
+        f[j] += b4.x; f[j + 1] += b4.y; f[j + 2] += b4.z; f[j + 3] += b4.w;
       }
 #pragma unroll
       for (int j = 0; j < 8; ++j) pk[h * 8 + j] = pack_bf16x2(f[2 * j], f[2 * j + 1]);
+      if (relu) {   // max(round(x), 0) == round(max(x, 0)): clamp the packed pairs (half the instructions)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) pk[h * 8 + j] = bf16x2_relu(pk[h * 8 + j]);
+      }
     }
   }
   {
@@ -189,52 +213,51 @@ __device__ __forceinline__ void epi_chunk(const EpiArgs& e, const uint32_t (&v)[
   __syncwarp();
   const int ch = lane & 3, rsub = lane >> 2;
   if (ch * 8 < ncol) {
-    const int c = col + ch * 8;
+    bf16* const obase = e.out + (col + ch * 8);
+    const uint8_t* const sbase = stg + rsub * 64 + ((ch ^ ((rsub >> 1) & 3)) << 4);
+    const int dbg = e.dbg;
 #pragma unroll
     for (int it = 0; it < 4; ++it) {
-      const int rr = it * 8 + rsub;
-      uint4 u = *reinterpret_cast<const uint4*>(stg + rr * 64 + ((ch ^ ((rr >> 1) & 3)) << 4));
-      const long op = opos[it];
-      if (op >= 0) {
-        if (e.mask) {
+      uint4 u = *reinterpret_cast<const uint4*>(sbase + it * 512);   // row it*8 + rsub (same swizzle phase)
+      const long off = rw.ooff[it];
+      if (off >= 0) {
+        if (MASK) {
           const uint4 m = aux.m[it];
           u.x &= bf16x2_gt0_mask(m.x); u.y &= bf16x2_gt0_mask(m.y);
           u.z &= bf16x2_gt0_mask(m.z); u.w &= bf16x2_gt0_mask(m.w);
         }
-        if (do_stats) {
+        if (STATS != EPI_STATS_NONE) {
           const uint32_t uw[4] = {u.x, u.y, u.z, u.w};
-          if (e.dot) {
-            const uint4 dd = aux.d[it];
-            const uint32_t dw[4] = {dd.x, dd.y, dd.z, dd.w};
+          uint32_t dw[4] = {0, 0, 0, 0};
+          if (STATS == EPI_STATS_DOT) { dw[0] = aux.d[it].x; dw[1] = aux.d[it].y; dw[2] = aux.d[it].z; dw[3] = aux.d[it].w; }
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float2 a = unpack_bf16x2(uw[j]), b = unpack_bf16x2(dw[j]);
-              acc[2 * j] += a.x; acc[2 * j + 1] += a.y;
+          for (int j = 0; j < 4; ++j) {
+            const float2 a = unpack_bf16x2(uw[j]);
+            acc[2 * j] += a.x; acc[2 * j + 1] += a.y;
+            if (STATS == EPI_STATS_SUMSQ) {
+              acc[8 + 2 * j] = fmaf(a.x, a.x, acc[8 + 2 * j]);
+              acc[8 + 2 * j + 1] = fmaf(a.y, a.y, acc[8 + 2 * j + 1]);
+            } else if (STATS == EPI_STATS_DOT) {
+              const float2 b = unpack_bf16x2(dw[j]);
               acc[8 + 2 * j] = fmaf(a.x, b.x, acc[8 + 2 * j]);
               acc[8 + 2 * j + 1] = fmaf(a.y, b.y, acc[8 + 2 * j + 1]);
             }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float2 a = unpack_bf16x2(uw[j]);
-              acc[2 * j] += a.x; acc[2 * j + 1] += a.y;
-              acc[8 + 2 * j] = fmaf(a.x, a.x, acc[8 + 2 * j]);
-              acc[8 + 2 * j + 1] = fmaf(a.y, a.y, acc[8 + 2 * j + 1]);
-            }
           }
         }
-        if (e.dbg != 1) *reinterpret_cast<uint4*>(e.out + op * e.out_ctot + e.out_coff + c) = u;
+        if (dbg != 1) *reinterpret_cast<uint4*>(obase + off) = u;
       }
     }
   }
   __syncwarp();
 }
 
-// fold the per-lane partial column sums of one chunk into the CTA's shared column sums
+// fold the per-lane partial column sums of one chunk into the CTA's shared column sums [2][bn]
+template <int STATS>
 __device__ __forceinline__ void epi_fold_acc(float (&acc)[16], float* colsum, int c0, int ncol, int bn,
                                              int lane) {
+  constexpr int NS = STATS == EPI_STATS_SUM ? 8 : 16;
 #pragma unroll
-  for (int k = 0; k < 16; ++k) {
+  for (int k = 0; k < NS; ++k) {
     float a = acc[k];
     a += __shfl_xor_sync(0xffffffffu, a, 4);
     a += __shfl_xor_sync(0xffffffffu, a, 8);
@@ -246,24 +269,24 @@ __device__ __forceinline__ void epi_fold_acc(float (&acc)[16], float* colsum, in
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       atomicAdd(colsum + c0 + ch * 8 + k, acc[k]);
-      atomicAdd(colsum + bn + c0 + ch * 8 + k, acc[8 + k]);
+      if (NS == 16) atomicAdd(colsum + bn + c0 + ch * 8 + k, acc[8 + k]);
     }
   }
 #pragma unroll
   for (int k = 0; k < 16; ++k) acc[k] = 0.f;
 }
 
-// all 128 epilogue threads: shared column sums [2][bn] -> global fp64 stats[n][2][stats_cols]
+// all epilogue threads: shared column sums [2][bn] -> global fp64 stats[n][2][stats_cols]
 __device__ __forceinline__ void epi_flush_colsum(const EpiArgs& e, float* colsum, int bn, int n, int col0,
-                                                 int tid) {
-  epi_bar();
-  for (int i = tid; i < 2 * bn; i += 128) {
+                                                 int tid, int nthr) {
+  epi_bar(nthr);
+  for (int i = tid; i < 2 * bn; i += nthr) {
     const float v = colsum[i];
     const int s = i >= bn, cidx = i - s * bn;
     if (v != 0.f) atomicAdd(e.stats + ((long)n * 2 + s) * e.stats_cols + col0 + cidx, (double)v);
     colsum[i] = 0.f;
   }
-  epi_bar();
+  epi_bar(nthr);
 }
 
 // ===================================================================== forward / dgrad GEMM
@@ -282,7 +305,8 @@ struct GemmArgs {
   TapTable tt;
 };
 
-__global__ void __launch_bounds__(256, 1)
+template <bool MASK, int STATS>
+__global__ void __launch_bounds__(384, 1)
     tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                    const GemmArgs p) {
   extern __shared__ uint8_t smem_raw[];
@@ -293,7 +317,7 @@ __global__ void __launch_bounds__(256, 1)
   uint64_t* tfull = empty + 16;
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
-  uint8_t* tiles = smem + kCtrlBytes;
+  uint8_t* tiles = smem + epi_ctrl_bytes(p.e.epi_warps);
   const int b_tile_bytes = p.BN * 128;
   const int stage_bytes = p.b_resident ? kABytes : kABytes + b_tile_bytes;
   uint8_t* bres = tiles + (size_t)p.stages * stage_bytes;   // resident weight slabs [tap][kchunk]
@@ -316,7 +340,7 @@ __global__ void __launch_bounds__(256, 1)
     mbar_init(bres_full, 1);
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull[a], 1);
-      mbar_init(&tempty[a], 128);
+      mbar_init(&tempty[a], 32 * p.e.epi_warps);
     }
     fence_barrier_init();
   }
@@ -403,98 +427,125 @@ __global__ void __launch_bounds__(256, 1)
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
-  } else if (warp >= 4) {
+  } else if (warp >= 4 && warp < 4 + p.e.epi_warps) {
     // ------------------------------------------------------------------ epilogue (see epi_chunk)
-    const int q = warp - 4, tid = threadIdx.x - 128, rsub = lane >> 2;
-    uint8_t* stg = smem + 1024 + q * kEpiStageBytes;
-    float* colsum = reinterpret_cast<float*>(smem + 1024 + 4 * kEpiStageBytes);
+    // warp ew reads TMEM lanes 32*(ew%4).. (hardware rule); with 8 warps the two warps of a lane
+    // quarter take alternate chunks
+    const int ew = warp - 4, q = ew & 3, grp = ew >> 2, ngrp = p.e.epi_warps >> 2;
+    const int tid = threadIdx.x - 128, nthr = 32 * p.e.epi_warps, rsub = lane >> 2;
+    uint8_t* stg = smem + 1024 + ew * kEpiStageBytes;
+    float* colsum = reinterpret_cast<float*>(smem + 1024 + p.e.epi_warps * kEpiStageBytes);
     const EpiArgs& e = p.e;
-    const bool do_stats = e.stats != nullptr;
-    const bool has_aux = e.mask != nullptr || (e.dot != nullptr && do_stats);
-    if (do_stats) {
-      for (int i = tid; i < 2 * p.BN; i += 128) colsum[i] = 0.f;
-      epi_bar();
+    constexpr bool kStats = STATS != EPI_STATS_NONE;
+    constexpr bool kAux = MASK || STATS == EPI_STATS_DOT;
+    const int BN = p.BN, chunk = p.chunk;
+    const long out_ctot = e.out_ctot, out_coff = e.out_coff;
+    if (kStats) {
+      for (int i = tid; i < 2 * BN; i += nthr) colsum[i] = 0.f;
+      epi_bar(nthr);
     }
     int cur_n = -1, cur_nt = -1;
     float sacc[16];
 #pragma unroll
     for (int k = 0; k < 16; ++k) sacc[k] = 0.f;
-    const int nchunks = (p.BN + p.chunk - 1) / p.chunk;
+    const int nchunks = (BN + chunk - 1) / chunk;
     uint32_t acc = 0, acc_phase = 0;
     for (int work = wfirst; work < wcount; work += wstride) {
       const int mt = p.b_resident ? work : work / p.n_tiles;
       const int nt = p.b_resident ? nt_fixed : work - mt * p.n_tiles;
       const TileCoord tc = decode_tile(mt, p.tiles_d, p.tiles_h, p.tiles_w, p.tdl, p.thl, p.twl);
-      if (do_stats && (tc.n != cur_n || nt != cur_nt)) {
-        if (cur_n >= 0) epi_flush_colsum(e, colsum, p.BN, cur_n, cur_nt * p.BN, tid);
+      if (kStats && (tc.n != cur_n || nt != cur_nt)) {
+        if (cur_n >= 0) epi_flush_colsum(e, colsum, BN, cur_n, cur_nt * BN, tid, nthr);
         cur_n = tc.n; cur_nt = nt;
       }
+      if (kAux && work + wstride < wcount && p.out_mode == TC_OUT_CONV) {
+        // pull the next tile's mask / dot lines into L2 (see the halo kernel)
+        const int w2 = work + wstride;
+        const int mt2 = p.b_resident ? w2 : w2 / p.n_tiles;
+        const int nt2 = p.b_resident ? nt_fixed : w2 - mt2 * p.n_tiles;
+        const TileCoord t2 = decode_tile(mt2, p.tiles_d, p.tiles_h, p.tiles_w, p.tdl, p.thl, p.twl);
+        const int nl = (BN * 2 + 127) >> 7;
+        for (int i = tid; i < 128 * nl; i += nthr) {
+          const int l = i % nl, row = i / nl;
+          const int w_ = t2.w0 + (row & ((1 << p.twl) - 1));
+          const int h_ = t2.h0 + ((row >> p.twl) & ((1 << p.thl) - 1));
+          const int d_ = t2.d0 + (row >> (p.twl + p.thl));
+          if (w_ < p.pw && h_ < p.ph && d_ < p.pd) {
+            const long pos = (((long)t2.n * p.pd + d_) * p.ph + h_) * p.pw + w_;
+            if (MASK) prefetch_l2(e.mask + pos * e.mask_ctot + e.mask_coff + nt2 * BN + l * 64);
+            if (STATS == EPI_STATS_DOT) prefetch_l2(e.dot + pos * e.dot_ctot + e.dot_coff + nt2 * BN + l * 64);
+          }
+        }
+      }
       // the 4 tile rows this lane stores in the read-back phase: q*32 + it*8 + lane/4
-      int hy[4], wx[4];
-      long cpos[4];
+      long cpos[4];       // conv mode: output position; scatter mode: position of pixel (2h, 2w)
 #pragma unroll
       for (int it = 0; it < 4; ++it) {
         const int row = q * 32 + it * 8 + rsub;
-        wx[it] = tc.w0 + (row & ((1 << p.twl) - 1));
-        hy[it] = tc.h0 + ((row >> p.twl) & ((1 << p.thl) - 1));
+        const int wx = tc.w0 + (row & ((1 << p.twl) - 1));
+        const int hy = tc.h0 + ((row >> p.twl) & ((1 << p.thl) - 1));
         const int dz = tc.d0 + (row >> (p.twl + p.thl));
-        const bool valid = (wx[it] < p.pw) && (hy[it] < p.ph) && (dz < p.pd);
-        cpos[it] = valid ? (((long)tc.n * p.pd + dz) * p.ph + hy[it]) * p.pw + wx[it] : -1;
+        const bool valid = (wx < p.pw) && (hy < p.ph) && (dz < p.pd);
+        if (p.out_mode == TC_OUT_CONV)
+          cpos[it] = valid ? (((long)tc.n * p.pd + dz) * p.ph + hy) * p.pw + wx : -1;
+        else
+          cpos[it] = valid ? ((long)tc.n * (2 * p.ph) + 2 * hy) * (2 * p.pw) + 2 * wx : -1;
       }
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * (uint32_t)p.BN;
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * (uint32_t)BN;
       auto issue = [&](uint32_t (&v)[32], int ci) {
-        const int c0 = ci * p.chunk;
+        const int c0 = ci * chunk;
         tmem_ld16(taddr + c0, v);
-        if (p.chunk == 32 && p.BN - c0 > 16) tmem_ld16(taddr + c0 + 16, v + 16);
+        if (chunk == 32 && BN - c0 > 16) tmem_ld16(taddr + c0 + 16, v + 16);
       };
-      // output column and positions of chunk ci (scatter mode: column block ij -> pixel (2h+i, 2w+j))
-      auto place = [&](int ci, int& ocol, long (&opos)[4]) {
-        ocol = nt * p.BN + ci * p.chunk;
-        if (p.out_mode == TC_OUT_CONV) {
-#pragma unroll
-          for (int it = 0; it < 4; ++it) opos[it] = cpos[it];
-        } else {
+      // output column and rows of chunk ci (scatter mode: column block ij -> pixel (2h+i, 2w+j))
+      auto place = [&](int ci, int& ocol, EpiRows& rw) {
+        ocol = nt * BN + ci * chunk;
+        long shift = 0;
+        if (p.out_mode != TC_OUT_CONV) {
           const int ij = ocol / p.cout_t;
           ocol -= ij * p.cout_t;
+          shift = (long)(ij >> 1) * (2 * p.pw) + (ij & 1);
+        }
 #pragma unroll
-          for (int it = 0; it < 4; ++it)
-            opos[it] = cpos[it] < 0 ? -1
-                                    : ((long)tc.n * (2 * p.ph) + (2 * hy[it] + (ij >> 1))) * (2 * p.pw) +
-                                          (2 * wx[it] + (ij & 1));
+        for (int it = 0; it < 4; ++it) {
+          rw.ooff[it] = cpos[it] < 0 ? -1 : (cpos[it] + shift) * out_ctot + out_coff;
+          if (MASK) rw.moff[it] = cpos[it] < 0 ? -1 : cpos[it] * e.mask_ctot + e.mask_coff;
+          if (STATS == EPI_STATS_DOT) rw.doff[it] = cpos[it] < 0 ? -1 : cpos[it] * e.dot_ctot + e.dot_coff;
         }
       };
-      auto prefetch = [&](EpiAux& aux, int ci) {
-        if (!has_aux) return;
+      auto prefetch = [&](EpiAux<MASK, STATS>& aux, int ci) {
+        if (!kAux) return;
         int ocol;
-        long opos[4];
-        place(ci, ocol, opos);
-        epi_prefetch(e, ocol, (p.chunk == 32 && p.BN - ci * p.chunk > 16) ? 32 : 16, lane, opos, do_stats, aux);
+        EpiRows rw;
+        place(ci, ocol, rw);
+        epi_prefetch<MASK, STATS>(e, ocol, (chunk == 32 && BN - ci * chunk > 16) ? 32 : 16, lane, rw, aux);
       };
-      auto process = [&](const uint32_t (&v)[32], const EpiAux& aux, int ci) {
-        const int c0 = ci * p.chunk;
-        const int ncol = (p.chunk == 32 && p.BN - c0 > 16) ? 32 : 16;
+      auto process = [&](const uint32_t (&v)[32], const EpiAux<MASK, STATS>& aux, int ci) {
+        const int c0 = ci * chunk;
+        const int ncol = (chunk == 32 && BN - c0 > 16) ? 32 : 16;
         int ocol;
-        long opos[4];
-        place(ci, ocol, opos);
-        epi_chunk(e, v, ncol, ocol, stg, lane, opos, sacc, do_stats, aux);
-        if (do_stats) epi_fold_acc(sacc, colsum, c0, ncol, p.BN, lane);
+        EpiRows rw;
+        place(ci, ocol, rw);
+        epi_chunk<MASK, STATS>(e, v, ncol, ocol, stg, lane, rw, sacc, aux);
+        if (kStats) epi_fold_acc<STATS>(sacc, colsum, c0, ncol, BN, lane);
       };
       uint32_t va[32], vb[32];
-      EpiAux xa, xb;
-      if (e.dbg != 2) {
-      issue(va, 0);
-      prefetch(xa, 0);
-      }
-      for (int ci = 0; ci < (e.dbg == 2 ? 0 : nchunks); ci += 2) {
-        tmem_ld_wait();
-        if (ci + 1 < nchunks) { issue(vb, ci + 1); prefetch(xb, ci + 1); }
-        process(va, xa, ci);
-        if (ci + 1 < nchunks) {
+      EpiAux<MASK, STATS> xa, xb;
+      if (e.dbg != 2 && grp < nchunks) {
+        issue(va, grp);
+        prefetch(xa, grp);
+        for (int ci = grp; ci < nchunks; ci += 2 * ngrp) {
+          const int c1 = ci + ngrp, c2 = c1 + ngrp;
           tmem_ld_wait();
-          if (ci + 2 < nchunks) { issue(va, ci + 2); prefetch(xa, ci + 2); }
-          process(vb, xb, ci + 1);
+          if (c1 < nchunks) { issue(vb, c1); prefetch(xb, c1); }
+          process(va, xa, ci);
+          if (c1 < nchunks) {
+            tmem_ld_wait();
+            if (c2 < nchunks) { issue(va, c2); prefetch(xa, c2); }
+            process(vb, xb, c1);
+          }
         }
       }
       tc_fence_before();
@@ -502,7 +553,7 @@ __global__ void __launch_bounds__(256, 1)
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
-    if (do_stats && cur_n >= 0) epi_flush_colsum(e, colsum, p.BN, cur_n, cur_nt * p.BN, tid);
+    if (kStats && cur_n >= 0) epi_flush_colsum(e, colsum, BN, cur_n, cur_nt * BN, tid, nthr);
   }
   tc_fence_before();
   __syncthreads();
@@ -616,7 +667,8 @@ __device__ __forceinline__ void halo_mma_warp(const HaloArgs& p, uint32_t tmem_b
 // (10 x (16R+2) positions x 64 channels); a weight slot = G taps; each weight slab is applied to all R
 // row-blocks (R accumulators in TMEM), which divides the weight traffic — the limiter of narrow-C_out
 // layers once the activations are halo-shared — by R.
-__global__ void __launch_bounds__(256, 1)
+template <bool MASK, int STATS>
+__global__ void __launch_bounds__(384, 1)
     tc_gemm_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                         const HaloArgs p) {
   extern __shared__ uint8_t smem_raw[];
@@ -629,7 +681,7 @@ __global__ void __launch_bounds__(256, 1)
   uint64_t* tfull = bempty + 16;
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
-  uint8_t* sA = smem + kCtrlBytes;
+  uint8_t* sA = smem + epi_ctrl_bytes(p.e.epi_warps);
   uint8_t* sB = sA + (size_t)p.a_stages * p.a_stage_bytes;
   const int tap_bytes = p.BN * 128;
   const int b_bytes = tap_bytes * p.G;
@@ -642,7 +694,7 @@ __global__ void __launch_bounds__(256, 1)
     tma_prefetch_desc(&tmB);
     for (int s = 0; s < p.a_stages; ++s) { mbar_init(&afull[s], 1); mbar_init(&aempty[s], 1); }
     for (int s = 0; s < p.b_slots; ++s) { mbar_init(&bfull[s], 1); mbar_init(&bempty[s], 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 128); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 32 * p.e.epi_warps); }
     fence_barrier_init();
   }
   uint32_t tmem_cols = 32;
@@ -707,81 +759,115 @@ __global__ void __launch_bounds__(256, 1)
       else { if (k64) HALO_MMA(1, 1, true); else HALO_MMA(1, 1, false); }
     }
 #undef HALO_MMA
-  } else if (warp >= 4) {
+  } else if (warp >= 4 && warp < 4 + p.e.epi_warps) {
     // ---------------------------------------------------------------- epilogue (see epi_chunk)
-    const int q = warp - 4, tid = threadIdx.x - 128, rsub = lane >> 2;
-    uint8_t* stg = smem + 1024 + q * kEpiStageBytes;
-    float* colsum = reinterpret_cast<float*>(smem + 1024 + 4 * kEpiStageBytes);
+    const int ew = warp - 4, q = ew & 3, grp = ew >> 2, ngrp = p.e.epi_warps >> 2;
+    const int tid = threadIdx.x - 128, nthr = 32 * p.e.epi_warps, rsub = lane >> 2;
+    uint8_t* stg = smem + 1024 + ew * kEpiStageBytes;
+    float* colsum = reinterpret_cast<float*>(smem + 1024 + p.e.epi_warps * kEpiStageBytes);
     const EpiArgs& e = p.e;
-    const bool do_stats = e.stats != nullptr;
-    const bool has_aux = e.mask != nullptr || (e.dot != nullptr && do_stats);
-    if (do_stats) {
-      for (int i = tid; i < 2 * p.BN; i += 128) colsum[i] = 0.f;
-      epi_bar();
+    constexpr bool kStats = STATS != EPI_STATS_NONE;
+    constexpr bool kAux = MASK || STATS == EPI_STATS_DOT;
+    const int BN = p.BN, R = p.R, pw = p.pw, ph = p.ph;
+    const int rsh = R == 4 ? 2 : (R == 2 ? 1 : 0);
+    const long out_ctot = e.out_ctot, out_coff = e.out_coff;
+    const long row_elems = (long)pw * out_ctot;   // elements between vertically adjacent positions
+    const long mrow_elems = (long)pw * e.mask_ctot, drow_elems = (long)pw * e.dot_ctot;
+    if (kStats) {
+      for (int i = tid; i < 2 * BN; i += nthr) colsum[i] = 0.f;
+      epi_bar(nthr);
     }
     int cur_n = -1, cur_nt = -1;
     float sacc[16];
 #pragma unroll
     for (int k = 0; k < 16; ++k) sacc[k] = 0.f;
-    const int nchunks = (p.BN + 31) / 32;
-    const int items = nchunks * p.R;   // item = chunk * R + row-block: the R row-blocks of a chunk share sacc
+    const int nchunks = (BN + 31) / 32;
+    const int items = nchunks * R;   // item = chunk * R + row-block
     uint32_t acc = 0, acc_phase = 0;
     for (int work = blockIdx.x; work < p.total; work += gridDim.x) {
       const int mt = work / p.n_tiles, nt = work - mt * p.n_tiles;
       const TileCoord tc = decode_tile(mt, p.pd, p.tiles_h, p.tiles_w, 0, thl, 3);
-      if (do_stats && (tc.n != cur_n || nt != cur_nt)) {
-        if (cur_n >= 0) epi_flush_colsum(e, colsum, p.BN, cur_n, cur_nt * p.BN, tid);
+      if (kStats && (tc.n != cur_n || nt != cur_nt)) {
+        if (cur_n >= 0) epi_flush_colsum(e, colsum, BN, cur_n, cur_nt * BN, tid, nthr);
         cur_n = tc.n; cur_nt = nt;
+      }
+      if (kAux && work + (int)gridDim.x < p.total) {
+        // The mask / dot tensors are read once, straight from HBM, by 16-byte loads of a handful of
+        // warps: far too little memory-level parallelism to cover DRAM latency.  Pull the NEXT tile's
+        // lines into L2 now (a couple of prefetches per thread); the loads one chunk ahead then hit L2.
+        const int w2 = work + (int)gridDim.x;
+        const int mt2 = w2 / p.n_tiles, nt2 = w2 - mt2 * p.n_tiles;
+        const TileCoord t2 = decode_tile(mt2, p.pd, p.tiles_h, p.tiles_w, 0, thl, 3);
+        const int nl = (BN * 2 + 127) >> 7;                 // 128-byte lines per position
+        const int nlines = 16 * R * 8 * nl;
+        const long plane2 = ((long)t2.n * p.pd + t2.d0) * ph;
+        for (int i = tid; i < nlines; i += nthr) {
+          const int l = i % nl, pp = i / nl;
+          const int w_ = t2.w0 + (pp & 7), h_ = t2.h0 + (pp >> 3);
+          if (w_ < pw && h_ < ph) {
+            const long pos = (plane2 + h_) * pw + w_;
+            if (MASK) prefetch_l2(e.mask + pos * e.mask_ctot + e.mask_coff + nt2 * BN + l * 64);
+            if (STATS == EPI_STATS_DOT) prefetch_l2(e.dot + pos * e.dot_ctot + e.dot_coff + nt2 * BN + l * 64);
+          }
+        }
       }
       // read-back rows of this lane: tile row q*32 + it*8 + lane/4 -> w = lane/4, h = q*4 + it
       const int wx = tc.w0 + rsub;
-      const long plane0 = ((long)tc.n * p.pd + tc.d0) * p.ph;
+      const int hy0 = tc.h0 + q * 4;
+      const long pos0 = (wx < pw) ? (((long)tc.n * p.pd + tc.d0) * ph + hy0) * pw + wx : -1;
+      const long off0 = pos0 * out_ctot + out_coff;
+      const long moff0 = pos0 * e.mask_ctot + e.mask_coff, doff0 = pos0 * e.dot_ctot + e.dot_coff;
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
-      const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + acc * (uint32_t)(p.R * p.BN);
+      const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + acc * (uint32_t)(R * BN);
       auto issue = [&](uint32_t (&v)[32], int item) {
-        const int ci = item / p.R, r = item - ci * p.R;
-        const uint32_t ta = tbase + (uint32_t)(r * p.BN + ci * 32);
+        const int ci = item >> rsh, r = item & (R - 1);
+        const uint32_t ta = tbase + (uint32_t)(r * BN + ci * 32);
         tmem_ld16(ta, v);
-        if (p.BN - ci * 32 > 16) tmem_ld16(ta + 16, v + 16);
+        if (BN - ci * 32 > 16) tmem_ld16(ta + 16, v + 16);
       };
-      auto place = [&](int r, long (&opos)[4]) {
+      auto place = [&](int r, EpiRows& rw) {
+        const int hleft = ph - (hy0 + r * 16);              // rows it < hleft exist
 #pragma unroll
         for (int it = 0; it < 4; ++it) {
-          const int hy = tc.h0 + r * 16 + q * 4 + it;
-          opos[it] = (wx < p.pw && hy < p.ph) ? (plane0 + hy) * p.pw + wx : -1;
+          const bool ok = pos0 >= 0 && it < hleft;
+          rw.ooff[it] = ok ? off0 + (long)(r * 16 + it) * row_elems : -1;
+          if (MASK) rw.moff[it] = ok ? moff0 + (long)(r * 16 + it) * mrow_elems : -1;
+          if (STATS == EPI_STATS_DOT) rw.doff[it] = ok ? doff0 + (long)(r * 16 + it) * drow_elems : -1;
         }
       };
-      auto prefetch = [&](EpiAux& aux, int item) {
-        if (!has_aux) return;
-        const int ci = item / p.R, r = item - ci * p.R;
-        long opos[4];
-        place(r, opos);
-        epi_prefetch(e, nt * p.BN + ci * 32, p.BN - ci * 32 > 16 ? 32 : 16, lane, opos, do_stats, aux);
+      auto prefetch = [&](EpiAux<MASK, STATS>& aux, int item) {
+        if (!kAux) return;
+        const int ci = item >> rsh, r = item & (R - 1);
+        EpiRows rw;
+        place(r, rw);
+        epi_prefetch<MASK, STATS>(e, nt * BN + ci * 32, BN - ci * 32 > 16 ? 32 : 16, lane, rw, aux);
       };
-      auto process = [&](const uint32_t (&v)[32], const EpiAux& aux, int item) {
-        const int ci = item / p.R, r = item - ci * p.R;
+      auto process = [&](const uint32_t (&v)[32], const EpiAux<MASK, STATS>& aux, int item, int next) {
+        const int ci = item >> rsh, r = item & (R - 1);
         const int c0 = ci * 32;
-        const int ncol = p.BN - c0 > 16 ? 32 : 16;
-        long opos[4];
-        place(r, opos);
-        epi_chunk(e, v, ncol, nt * p.BN + c0, stg, lane, opos, sacc, do_stats, aux);
-        if (do_stats && r == p.R - 1) epi_fold_acc(sacc, colsum, c0, ncol, p.BN, lane);
+        const int ncol = BN - c0 > 16 ? 32 : 16;
+        EpiRows rw;
+        place(r, rw);
+        epi_chunk<MASK, STATS>(e, v, ncol, nt * BN + c0, stg, lane, rw, sacc, aux);
+        // this warp's partial sums of a chunk are complete when its next item belongs to another chunk
+        if (kStats && (next >= items || (next >> rsh) != ci)) epi_fold_acc<STATS>(sacc, colsum, c0, ncol, BN, lane);
       };
       uint32_t va[32], vb[32];
-      EpiAux xa, xb;
-      if (e.dbg != 2) {
-      issue(va, 0);
-      prefetch(xa, 0);
-      }
-      for (int item = 0; item < (e.dbg == 2 ? 0 : items); item += 2) {
-        tmem_ld_wait();
-        if (item + 1 < items) { issue(vb, item + 1); prefetch(xb, item + 1); }
-        process(va, xa, item);
-        if (item + 1 < items) {
+      EpiAux<MASK, STATS> xa, xb;
+      if (e.dbg != 2 && grp < items) {
+        issue(va, grp);
+        prefetch(xa, grp);
+        for (int item = grp; item < items; item += 2 * ngrp) {
+          const int i1 = item + ngrp, i2 = i1 + ngrp;
           tmem_ld_wait();
-          if (item + 2 < items) { issue(va, item + 2); prefetch(xa, item + 2); }
-          process(vb, xb, item + 1);
+          if (i1 < items) { issue(vb, i1); prefetch(xb, i1); }
+          process(va, xa, item, i1);
+          if (i1 < items) {
+            tmem_ld_wait();
+            if (i2 < items) { issue(va, i2); prefetch(xa, i2); }
+            process(vb, xb, i1, i2);
+          }
         }
       }
       tc_fence_before();
@@ -789,7 +875,7 @@ __global__ void __launch_bounds__(256, 1)
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
-    if (do_stats && cur_n >= 0) epi_flush_colsum(e, colsum, p.BN, cur_n, cur_nt * p.BN, tid);
+    if (kStats && cur_n >= 0) epi_flush_colsum(e, colsum, BN, cur_n, cur_nt * BN, tid, nthr);
   }
   tc_fence_before();
   __syncthreads();
@@ -804,9 +890,61 @@ static EpiArgs make_epi(const TcGemmProblem& p) {
   e.mask = p.mask; e.mask_ctot = p.mask_ctot; e.mask_coff = p.mask_coff;
   e.dot = p.dot; e.dot_ctot = p.dot_ctot; e.dot_coff = p.dot_coff;
   e.stats = p.stats; e.stats_cols = p.ncols;
+  e.epi_warps = 4;
   e.dbg = g_epi_dbg;
   return e;
 }
+
+static int stats_kind_of(const TcGemmProblem& p) {
+  if (!p.stats) return EPI_STATS_NONE;
+  if (p.dot) return EPI_STATS_DOT;
+  return p.stats_kind == EPI_STATS_SUM ? EPI_STATS_SUM : EPI_STATS_SUMSQ;
+}
+int g_epi_warps = 0;  // tuning knob: 0 = heuristic, 4 / 8 = forced
+// Two epilogue warps per TMEM lane quarter when a tile's MMA work is too short to hide a 4-warp
+// epilogue (~1000 cycles per 32x32 chunk per warp, latency-bound): small K = taps * C_in.
+static int pick_epi_warps(long k_total, bool aux) {
+  if (g_epi_warps == 4 || g_epi_warps == 8) return g_epi_warps;
+  return k_total <= (aux ? 2400 : 600) ? 8 : 4;   // measured: profiles/r01_epilogue_probe.log
+}
+
+template <class Args, class F>
+static int launch_variant(F pick, bool mask, int kind, int grid, int block, int smem, cudaStream_t stream,
+                          const CUtensorMap& tmA, const CUtensorMap& tmB, const Args& a) {
+  void (*fn)(CUtensorMap, CUtensorMap, Args) = pick(mask, kind);
+  if (!fn) return B200_ERR_UNSUPPORTED;
+  static void* configured[16];
+  static int nconf = 0;
+  bool done = false;
+  for (int i = 0; i < nconf; ++i) done |= configured[i] == (void*)fn;
+  if (!done) {
+    cudaError_t e = cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
+    if (e != cudaSuccess) return (int)e;
+    if (nconf < 16) configured[nconf++] = (void*)fn;
+  }
+  fn<<<grid, block, smem, stream>>>(tmA, tmB, a);
+  B200_LAUNCH_CHECK();
+  return B200_OK;
+}
+#define B200_PICK_VARIANT(KERNEL, ARGS)                                                     \
+  [](bool mask, int kind) -> void (*)(CUtensorMap, CUtensorMap, ARGS) {                     \
+    if (!mask) {                                                                            \
+      switch (kind) {                                                                       \
+        case EPI_STATS_NONE: return KERNEL<false, EPI_STATS_NONE>;                          \
+        case EPI_STATS_SUM: return KERNEL<false, EPI_STATS_SUM>;                            \
+        case EPI_STATS_SUMSQ: return KERNEL<false, EPI_STATS_SUMSQ>;                        \
+        case EPI_STATS_DOT: return KERNEL<false, EPI_STATS_DOT>;                            \
+      }                                                                                     \
+    } else {                                                                                \
+      switch (kind) {                                                                       \
+        case EPI_STATS_NONE: return KERNEL<true, EPI_STATS_NONE>;                           \
+        case EPI_STATS_SUM: return KERNEL<true, EPI_STATS_SUM>;                             \
+        case EPI_STATS_SUMSQ: return KERNEL<true, EPI_STATS_SUMSQ>;                         \
+        case EPI_STATS_DOT: return KERNEL<true, EPI_STATS_DOT>;                             \
+      }                                                                                     \
+    }                                                                                       \
+    return nullptr;                                                                         \
+  }
 
 static int sm_count() {
   static int n = 0;
@@ -859,6 +997,10 @@ static int tc_gemm_halo(const TcGemmProblem& p, cudaStream_t stream) {
   a.n_tiles = p.ncols / a.BN;
   a.kd = p.kd;
   a.kdim = p.kdim; a.kchunks = (p.kdim + 63) / 64;
+  a.e = make_epi(p);
+  const int kind = stats_kind_of(p);
+  a.e.epi_warps = pick_epi_warps((long)p.kd * 9 * p.kdim, p.mask || kind != EPI_STATS_NONE);
+  const int kSmemOverhead = smem_overhead(a.e.epi_warps);
   // R row-blocks share every weight slab: as many as TMEM (2 R BN <= 512 columns), the plane height and
   // shared memory allow
   int R = 1;
@@ -920,7 +1062,6 @@ static int tc_gemm_halo(const TcGemmProblem& p, cudaStream_t stream) {
     if (a.b_slots > 12) a.b_slots = 12;
     if (a.b_slots < 2) return B200_ERR_UNSUPPORTED;
   }
-  a.e = make_epi(p);
 
   CUtensorMap tmA, tmB;
   {
@@ -941,17 +1082,9 @@ static int tc_gemm_halo(const TcGemmProblem& p, cudaStream_t stream) {
     if (rc) return rc;
   }
   const int smem = a.a_stages * a.a_stage_bytes + a.b_slots * b_bytes + kSmemOverhead;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(tc_gemm_halo_kernel,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
-    if (e != cudaSuccess) return (int)e;
-    attr_set = true;
-  }
   const int grid = a.total < sm_count() ? a.total : sm_count();
-  tc_gemm_halo_kernel<<<grid, 256, smem, stream>>>(tmA, tmB, a);
-  B200_LAUNCH_CHECK();
-  return B200_OK;
+  return launch_variant<HaloArgs>(B200_PICK_VARIANT(tc_gemm_halo_kernel, HaloArgs), p.mask != nullptr, kind, grid,
+                                  128 + 32 * a.e.epi_warps, smem, stream, tmA, tmB, a);
 }
 
 int tc_gemm_conv(const TcGemmProblem& p, cudaStream_t stream) {
@@ -979,6 +1112,11 @@ int tc_gemm_conv(const TcGemmProblem& p, cudaStream_t stream) {
   }
   a.tap_mode = p.tap_mode; a.out_mode = p.out_mode;
   a.kdim = p.kdim; a.kchunks = (p.kdim + 63) / 64;
+  a.cout_t = p.cout_t;
+  a.e = make_epi(p);
+  const int kind = stats_kind_of(p);
+  a.e.epi_warps = pick_epi_warps((long)a.ntaps * p.kdim, p.mask || kind != EPI_STATS_NONE);
+  const int kSmemOverhead = smem_overhead(a.e.epi_warps);
   // Weight-resident mode: with few taps and a short K (ConvTranspose 2x2 forward / backward-data) the
   // weight slabs of one column tile fit in shared memory; each CTA then keeps ONE column tile and only
   // streams activations (per-tile L2 traffic drops from A + B to A).
@@ -994,8 +1132,6 @@ int tc_gemm_conv(const TcGemmProblem& p, cudaStream_t stream) {
   a.stages = (int)((kSmemBudget - kSmemOverhead - (a.b_resident ? w_bytes : 0)) / stage_bytes);
   if (a.stages > 12) a.stages = 12;
   if (a.stages < 2) return B200_ERR_UNSUPPORTED;
-  a.cout_t = p.cout_t;
-  a.e = make_epi(p);
 
   CUtensorMap tmA, tmB;
   int rc = make_act_tmap(&tmA, p.a, p.tap_mode, g);
@@ -1008,16 +1144,8 @@ int tc_gemm_conv(const TcGemmProblem& p, cudaStream_t stream) {
     if (rc) return rc;
   }
   const int smem = a.stages * stage_bytes + kSmemOverhead + (a.b_resident ? (int)w_bytes : 0);
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         kSmemBudget);
-    if (e != cudaSuccess) return (int)e;
-    attr_set = true;
-  }
-  tc_gemm_kernel<<<grid, 256, smem, stream>>>(tmA, tmB, a);
-  B200_LAUNCH_CHECK();
-  return B200_OK;
+  return launch_variant<GemmArgs>(B200_PICK_VARIANT(tc_gemm_kernel, GemmArgs), p.mask != nullptr, kind, grid,
+                                  128 + 32 * a.e.epi_warps, smem, stream, tmA, tmB, a);
 }
 
 // ===================================================================== weight gradient

@@ -48,6 +48,7 @@ struct TcGemmProblem {
   // stats fp64 [pn][2][ncols]: [.][0][c] += sum out, [.][1][c] += sum out^2, or sum out * dot when a
   // dot operand (same geometry as out) is given.  Fused into the epilogue of the tcgen05 kernels.
   double* stats;
+  int stats_kind;         // 1 = only the sum is needed ([.][1][c] left untouched); otherwise sum + second moment
   const bf16* dot;
   int dot_ctot, dot_coff;
 };

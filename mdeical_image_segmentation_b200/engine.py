@@ -24,6 +24,7 @@ from .ops import CL
 
 Grads = Dict[nn.Parameter, torch.Tensor]
 IMPL = 0  # B200_IMPL_AUTO; tests flip it to cross-check the tcgen05 and direct kernels
+FUSE_SUM_MIN_K = 2304  # fuse a bias-gradient column sum into a dgrad epilogue only if taps * C_out >= this
 
 
 _REDUCER = None  # parallel.GradReducer of the network whose backward is running (data parallel)
@@ -216,13 +217,18 @@ def single_conv_bwd(dy: CL, recs: list, grads: Grads, need_dx: bool = True, prem
             # the fused mask must have the layout of the (dense) dx the kernel writes
             fuse = bool(mask_in and not zpad and x_in.is_full())
             want, dot = _consumer_plan(nxt_consumer, fuse)
+            # Epilogue statistics ride for free only under a long enough MMA phase (taps * C_out of this
+            # dgrad); on shallow 2D layers the epilogue is the bottleneck and a separate HBM-speed pass
+            # is cheaper (measured: profiles/r01_epilogue_probe.log)
+            if want and dot is None and conv.weight.shape[0] * k[0] * k[1] * k[2] < FUSE_SUM_MIN_K:
+                want = False
             if want and dot is not None:
                 dot = dot.widened()
                 if dot.c != x_in.c or dot.dims != x_in.dims:
                     want, dot = False, None
-            if want:
+            if want:   # only sums are consumed unless a norm's (sum g, sum g*x) is asked for
                 dy, sums = ops.conv_bwd_data(dy, wp_bwd, k, mask=x_in if fuse else None, impl=IMPL,
-                                             stats=True, dot=dot)
+                                             stats="sum", dot=dot)
             else:
                 dy = ops.conv_bwd_data(dy, wp_bwd, k, mask=x_in if fuse else None, impl=IMPL)
             out_premasked = fuse
@@ -383,8 +389,10 @@ def unet2d_backward(net, tape: list, dfeat: CL, grads: Grads, premasked: bool) -
         fuse = bool(x_relu and x_in.is_full())
         # x_in is the ReLU output of the block below: its second conv's bias gradient is the column
         # sum of the masked gradient this kernel writes
-        if fuse:
-            d, d_sums = ops.convt_bwd_data(d_up, wp_bwd, mask=x_in, impl=IMPL, stats=True)
+        if fuse and 4 * c >= FUSE_SUM_MIN_K:
+            d, d_sums = ops.convt_bwd_data(d_up, wp_bwd, mask=x_in, impl=IMPL, stats="sum")
+        elif fuse:
+            d, d_sums = ops.convt_bwd_data(d_up, wp_bwd, mask=x_in, impl=IMPL), None
         else:
             d, d_sums = ops.convt_bwd_data(d_up, wp_bwd, mask=None, impl=IMPL), None
         pm = fuse

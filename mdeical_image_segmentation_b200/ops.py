@@ -149,11 +149,22 @@ def conv_fwd(x: CL, wp_fwd: torch.Tensor, k, bias: Optional[torch.Tensor], relu:
     return out, cs
 
 
+STATS_NONE, STATS_SUM, STATS_SUM_SQ, STATS_SUM_DOT = 0, 1, 2, 3
+
+
+def _stats_kind(stats, dot) -> int:
+    if dot is not None:
+        return STATS_SUM_DOT
+    if stats == "sum":
+        return STATS_SUM
+    return STATS_SUM_SQ if stats else STATS_NONE
+
+
 def conv_bwd_data(dy: CL, wp_bwd: torch.Tensor, k, mask: Optional[CL] = None,
-                  out: Optional[CL] = None, impl: int = 0, stats: bool = False,
+                  out: Optional[CL] = None, impl: int = 0, stats=False,
                   dot: Optional[CL] = None):
-    """``stats=True`` also returns fp64 [n][2][c_in] = per-sample (sum dx, sum dx^2), or
-    (sum dx, sum dx*dot) when ``dot`` (a tensor of dx's shape) is given."""
+    """``stats`` (True | "sum") also returns fp64 [n][2][c_in] = per-sample (sum dx, sum dx^2) — only the
+    sums for "sum" — or (sum dx, sum dx*dot) when ``dot`` (a tensor of dx's shape) is given."""
     c_in, c_out = wp_bwd.shape[1], wp_bwd.shape[2]
     assert dy.c == c_out
     if out is None:
@@ -170,7 +181,7 @@ def conv_bwd_data(dy: CL, wp_bwd: torch.Tensor, k, mask: Optional[CL] = None,
         assert dot.c == c_in and dot.dims == out.dims
     cs = colstats_buffer(dy.n, c_in, dy.device)
     call("b200_conv_bwd_data_stats", C.byref(d), _p(dy.buf), _p(wp_bwd),
-         _p(None if mask is None else mask.buf), _p(out.buf),
+         _p(None if mask is None else mask.buf), _p(out.buf), _stats_kind(stats, dot),
          _p(None if dot is None else dot.buf), 0 if dot is None else dot.ctot,
          0 if dot is None else dot.coff, _p(cs), _stream())
     return out, cs
@@ -208,7 +219,7 @@ def convt_fwd(x: CL, wp_fwd, bias, out: Optional[CL] = None, impl: int = 0) -> C
 
 
 def convt_bwd_data(dy: CL, wp_bwd, mask: Optional[CL] = None, out: Optional[CL] = None,
-                   impl: int = 0, stats: bool = False):
+                   impl: int = 0, stats=False):
     c_in, c_out = wp_bwd.shape[1], wp_bwd.shape[2]
     assert dy.c == c_out and dy.d == 1
     h, w = dy.h // 2, dy.w // 2
@@ -221,7 +232,7 @@ def convt_bwd_data(dy: CL, wp_bwd, mask: Optional[CL] = None, out: Optional[CL] 
         return out
     cs = colstats_buffer(dy.n, c_in, dy.device)
     call("b200_convt2x2_bwd_data_stats", C.byref(d), _p(dy.buf), _p(wp_bwd),
-         _p(None if mask is None else mask.buf), _p(out.buf), _p(cs), _stream())
+         _p(None if mask is None else mask.buf), _p(out.buf), _stats_kind(stats, None), _p(cs), _stream())
     return out, cs
 
 

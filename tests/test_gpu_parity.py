@@ -395,6 +395,13 @@ def test_fused_epilogue_statistics(B):
             assert rel_l2(cs2.cpu(), ref2.cpu()) < 2e-5, (impl, "bwd")
             dx0 = ops.conv_bwd_data(dy, bwd, k, mask=x, impl=impl).dense()
             assert torch.equal(dx0, dx.dense())
+            # sum-only and sum + sum-of-squares variants, without a mask
+            dx1, cs3 = ops.conv_bwd_data(dy, bwd, k, impl=impl, stats="sum")
+            d1 = dx1.dense().double()
+            assert rel_l2(cs3[:, 0].cpu(), d1.sum((1, 2, 3)).cpu()) < 2e-5 and float(cs3[:, 1].abs().max()) == 0.0
+            dx2, cs4 = ops.conv_bwd_data(dy, bwd, k, impl=impl, stats=True)
+            ref4 = torch.stack([d1.sum((1, 2, 3)), (d1 * d1).sum((1, 2, 3))], 1)
+            assert rel_l2(cs4.cpu(), ref4.cpu()) < 2e-5 and torch.equal(dx1.dense(), dx2.dense())
     # ConvTranspose 2x2 backward-data with the fused column sum
     xt = CL(torch.randn((2, 1, 16, 24, 128), generator=g).to(torch.bfloat16).cuda())
     dyt = CL(torch.randn((2, 1, 32, 48, 64), generator=g).to(torch.bfloat16).cuda())
@@ -433,3 +440,11 @@ def test_fused_epilogue_statistics(B):
         r0 = ops.conv_fwd(xr, fr, kr, None, True, impl=1).dense()
         lib.b200_set_tuning(3, 1)
         assert torch.equal(r0, r1), cout
+        for ew in (4, 8):   # 4 and 8 epilogue warps store the same tensor and the same statistics
+            lib.b200_set_tuning(5, ew)
+            r2, s2 = ops.conv_fwd(xr, fr, kr, None, True, impl=1, stats=True)
+            lib.b200_set_tuning(5, 0)
+            assert torch.equal(r2.dense(), r1), (cout, ew)
+            rd = r1.double()
+            refs = torch.stack([rd.sum((1, 2, 3)), (rd * rd).sum((1, 2, 3))], 1)
+            assert rel_l2(s2.cpu(), refs.cpu()) < 2e-5, (cout, ew)

@@ -32,19 +32,26 @@ for (name, n, d, h, w, cin, cout) in shapes:
     out = CL.empty(n, d, h, w, cout, dev)
     mask = CL(torch.randn((n, d, h, w, cout), device=dev).to(torch.bfloat16))
     flops = 2.0 * n * d * h * w * cin * cout * (27 if d > 1 else 9)
-    for resident in (0, 1):
-        for R in (1, 2, 4):
-            L.b200_set_tuning(3, resident); L.b200_set_tuning(2, R)
+    dy = CL(torch.randn((n, d, h, w, cout), device=dev).to(torch.bfloat16))
+    for resident in (1,):
+        for ew in (4, 8):
+            L.b200_set_tuning(3, resident); L.b200_set_tuning(5, ew)
             row = []
-            for dbg in (0, 1, 2):
+            for dbg in (0, 2):
                 L.b200_set_tuning(4, dbg)
                 ms = timeit(lambda: ops.conv_fwd(x, fwd, k, None, True, out=out, impl=1))
                 row.append(f"dbg{dbg} {ms:.3f}ms {flops/ms/1e9:5.0f}TF")
             L.b200_set_tuning(4, 0)
             ms = timeit(lambda: ops.conv_fwd(x, fwd, k, None, True, out=out, impl=1, stats=True))
-            row.append(f"stats {ms:.3f}ms")
-            print(f"{name} resident={resident} Rmax={R}: " + " | ".join(row), flush=True)
-    L.b200_set_tuning(3, 1); L.b200_set_tuning(2, 4); L.b200_set_tuning(4, 0)
+            row.append(f"fwd+sq {ms:.3f}ms")
+            ms = timeit(lambda: ops.conv_bwd_data(dy, bwd, k, mask=x, impl=1))
+            row.append(f"dgrad+mask {ms:.3f}ms")
+            ms = timeit(lambda: ops.conv_bwd_data(dy, bwd, k, mask=x, impl=1, stats="sum"))
+            row.append(f"dgrad+mask+sum {ms:.3f}ms")
+            ms = timeit(lambda: ops.conv_bwd_data(dy, bwd, k, impl=1, stats=True, dot=x))
+            row.append(f"dgrad+dot {ms:.3f}ms")
+            print(f"{name} resident={resident} epi_warps={ew}: " + " | ".join(row), flush=True)
+    L.b200_set_tuning(3, 1); L.b200_set_tuning(5, 0); L.b200_set_tuning(4, 0)
 # ConvTranspose 2x2 forward (scatter epilogue) and backward-data
 for (name, n, h, w, cin, cout) in [("convT 128->64 256^2 b32", 32, 256, 256, 128, 64), ("convT 256->128 128^2 b32", 32, 128, 128, 256, 128)]:
     x = CL(torch.randn((n, 1, h, w, cin), device=dev).to(torch.bfloat16))
@@ -53,14 +60,15 @@ for (name, n, h, w, cin, cout) in [("convT 128->64 256^2 b32", 32, 256, 256, 128
     out = CL.empty(n, 1, 2 * h, 2 * w, cout, dev)
     dy = CL(torch.randn((n, 1, 2 * h, 2 * w, cout), device=dev).to(torch.bfloat16))
     flops = 2.0 * n * h * w * cin * cout * 4
-    for resident in (0, 1):
-        L.b200_set_tuning(3, resident)
+    for resident in (1,):
+      for ew in (4, 8):
+        L.b200_set_tuning(3, resident); L.b200_set_tuning(5, ew)
         row = []
-        for dbg in (0, 1, 2):
+        for dbg in (0, 2):
             L.b200_set_tuning(4, dbg)
             ms = timeit(lambda: ops.convt_fwd(x, wf, None, out=out, impl=1))
-            ms2 = timeit(lambda: ops.convt_bwd_data(dy, wb, mask=x, impl=1))
-            row.append(f"dbg{dbg} fwd {ms:.3f}ms {flops/ms/1e9:5.0f}TF dgrad {ms2:.3f}ms")
+            ms2 = timeit(lambda: ops.convt_bwd_data(dy, wb, mask=x, impl=1, stats="sum"))
+            row.append(f"dbg{dbg} fwd {ms:.3f}ms {flops/ms/1e9:5.0f}TF dgrad+mask+sum {ms2:.3f}ms")
         L.b200_set_tuning(4, 0)
-        print(f"{name} resident={resident}: " + " | ".join(row), flush=True)
-L.b200_set_tuning(3, 1)
+        print(f"{name} resident={resident} epi_warps={ew}: " + " | ".join(row), flush=True)
+L.b200_set_tuning(3, 1); L.b200_set_tuning(5, 0)
