@@ -36,69 +36,70 @@ __device__ __forceinline__ void ld8(const bf16* p, float* f) {
   const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
   f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
 }
+// Forward: one thread per position (grid.y = sample, so no 64-bit div/mod per position).  The thread
+// streams its 128-byte-aligned channel row with 16-byte loads (each 32-byte sector is fetched once and
+// consumed by two consecutive loads) and the per-class stores of a warp are 128 contiguous bytes.
 template <int HEAD_MAX_CO>
 __global__ void __launch_bounds__(256)
-    head_fwd_kernel(int n, long spatial, int c_in, int c_out, View x, const float* w, const float* b,
+    head_fwd_kernel(long spatial, int c_in, int c_out, View x, const float* w, const float* b,
                     float* logits) {
   extern __shared__ float sw[];  // [c_out][c_in] + [c_out]
   for (int i = threadIdx.x; i < c_out * c_in; i += blockDim.x) sw[i] = w[i];
   for (int i = threadIdx.x; i < c_out; i += blockDim.x) sw[c_out * c_in + i] = b ? b[i] : 0.f;
   __syncthreads();
-  const long total = (long)n * spatial;
-  const int oct = threadIdx.x & 7;
-  // warp-uniform trip count (4 positions per warp per pass) so the full-mask shuffles are safe
-  const int sub = (threadIdx.x & 31) >> 3;
-  for (long p0 = (((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 4; p0 < total;
-       p0 += (((long)gridDim.x * blockDim.x) >> 5) * 4) {
-    const long pos = p0 + sub;
-    const bool valid = pos < total;
+  const long bi = blockIdx.y;
+  float* lbase = logits + bi * c_out * spatial;
+  for (long sp = (long)blockIdx.x * blockDim.x + threadIdx.x; sp < spatial; sp += (long)gridDim.x * blockDim.x) {
+    const bf16* xr = x.at(bi * spatial + sp, 0);
     float acc[HEAD_MAX_CO];
 #pragma unroll
     for (int j = 0; j < HEAD_MAX_CO; ++j) acc[j] = 0.f;
-    for (int c0 = oct * 8; valid && c0 < c_in; c0 += 64) {
-      float f[8];
-      ld8(x.at(pos, c0), f);
+#pragma unroll 2
+    for (int c0 = 0; c0 < c_in; c0 += 16) {
+      float f[16];
+      ld8(xr + c0, f);
+      if (c0 + 8 < c_in) ld8(xr + c0 + 8, f + 8);
 #pragma unroll
       for (int j = 0; j < HEAD_MAX_CO; ++j) {
         if (j < c_out) {
-          const float* wr = sw + j * c_in + c0;
+          const float* wr = sw + j * c_in + c0;   // warp-uniform address: shared-memory broadcast
 #pragma unroll
           for (int k = 0; k < 8; ++k) acc[j] = fmaf(f[k], wr[k], acc[j]);
+          if (c0 + 8 < c_in) {
+#pragma unroll
+            for (int k = 8; k < 16; ++k) acc[j] = fmaf(f[k], wr[k], acc[j]);
+          }
         }
       }
     }
 #pragma unroll
-    for (int j = 0; j < HEAD_MAX_CO; ++j) {
-      acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], 1);
-      acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], 2);
-      acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], 4);
-    }
-    if (valid && oct < c_out) {
-      const long bi = pos / spatial, sp = pos % spatial;
-      float v = 0.f;
-#pragma unroll
-      for (int j = 0; j < HEAD_MAX_CO; ++j)
-        if (j == oct) v = acc[j];
-      logits[(bi * c_out + oct) * spatial + sp] = v + sw[c_out * c_in + oct];
-    }
+    for (int j = 0; j < HEAD_MAX_CO; ++j)
+      if (j < c_out) lbase[(long)j * spatial + sp] = acc[j] + sw[c_out * c_in + j];
   }
 }
 // One pass over x and dlogits: dx[pos][ci] = sum_co g[co] w[co][ci] (bf16 store) and
 // dw[co][ci] += sum_pos g[co] x[pos][ci], db[co] += sum_pos g[co].
+// 8 threads per position, each owning 8 consecutive channels (its dw partials live in registers);
+// grid.y = sample; lane `oct` fetches g[oct] and the 8 lanes of a position share it by shuffle; two
+// positions per thread are in flight.
 template <int HEAD_MAX_CO>
 __global__ void __launch_bounds__(256)
-    head_bwd_kernel(int n, long spatial, int c_in, int c_out, long chunk, View x, const float* w,
+    head_bwd_kernel(long spatial, int c_in, int c_out, long chunk, View x, const float* w,
                     const float* dlogits, View dx, float* dw, float* db, int mask_relu) {
   extern __shared__ float sw[];       // [c_out][c_in] weights, then [32][c_out][8] reduction scratch
   float* sred = sw + c_out * c_in;
   for (int i = threadIdx.x; i < c_out * c_in; i += blockDim.x) sw[i] = w[i];
   __syncthreads();
-  const long total = (long)n * spatial;
-  const int oct = threadIdx.x & 7, prow = threadIdx.x >> 3;  // 32 positions per block pass
+  const long bi = blockIdx.y;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int oct = threadIdx.x & 7, sub = lane >> 3, prow = threadIdx.x >> 3;  // 32 positions per block pass
   const long pbeg = (long)blockIdx.x * chunk;
-  const long pend = pbeg + chunk < total ? pbeg + chunk : total;
+  const long pend = pbeg + chunk < spatial ? pbeg + chunk : spatial;
+  const float* gbase = dlogits + bi * c_out * spatial;
+  const long xbase = bi * spatial;
   for (int cb = 0; cb < c_in; cb += 64) {
     const int c0 = cb + oct * 8;
+    const bool cvalid = c0 < c_in;
     float aw[HEAD_MAX_CO][8];
     float ab[HEAD_MAX_CO];
 #pragma unroll
@@ -107,34 +108,44 @@ __global__ void __launch_bounds__(256)
 #pragma unroll
       for (int k = 0; k < 8; ++k) aw[j][k] = 0.f;
     }
-    if (c0 < c_in) {
-      for (long pos = pbeg + prow; pos < pend; pos += 32) {
-        const long bi = pos / spatial, sp = pos % spatial;
-        float f[8], o[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-        ld8(x.at(pos, c0), f);
+    // warp-uniform trip count (the shuffles need every lane): a warp covers positions s0 .. s0+3 and +32
+    for (long s0 = pbeg + warp * 4; s0 < pend; s0 += 64) {
+      long sp[2] = {s0 + sub, s0 + 32 + sub};
+      bool ok[2] = {sp[0] < pend, sp[1] < pend};
+      float gl[2], f[2][8];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        gl[u] = (ok[u] && oct < c_out) ? __ldg(gbase + (long)oct * spatial + sp[u]) : 0.f;
+        if (ok[u] && cvalid) ld8(x.at(xbase + sp[u], c0), f[u]);
+      }
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        float o[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 #pragma unroll
         for (int j = 0; j < HEAD_MAX_CO; ++j) {
           if (j < c_out) {
-            const float g = dlogits[(bi * c_out + j) * spatial + sp];
-            const float* wr = sw + j * c_in + c0;
-            ab[j] += g;
+            const float g = __shfl_sync(0xffffffffu, gl[u], (lane & ~7) + j);
+            if (ok[u] && cvalid) {
+              const float* wr = sw + j * c_in + c0;
+              ab[j] += g;
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
-              aw[j][k] = fmaf(g, f[k], aw[j][k]);
-              o[k] = fmaf(g, wr[k], o[k]);
+              for (int k = 0; k < 8; ++k) {
+                aw[j][k] = fmaf(g, f[u][k], aw[j][k]);
+                o[k] = fmaf(g, wr[k], o[k]);
+              }
             }
           }
         }
-        if (dx.p) {
+        if (dx.p && ok[u] && cvalid) {
           if (mask_relu) {  // x is a ReLU output: dx doubles as the pre-activation gradient
 #pragma unroll
             for (int k = 0; k < 8; ++k)
-              if (!(f[k] > 0.f)) o[k] = 0.f;
+              if (!(f[u][k] > 0.f)) o[k] = 0.f;
           }
-          uint4 u;
-          u.x = pack_bf16x2(o[0], o[1]); u.y = pack_bf16x2(o[2], o[3]);
-          u.z = pack_bf16x2(o[4], o[5]); u.w = pack_bf16x2(o[6], o[7]);
-          *reinterpret_cast<uint4*>(dx.at(pos, c0)) = u;
+          uint4 q;
+          q.x = pack_bf16x2(o[0], o[1]); q.y = pack_bf16x2(o[2], o[3]);
+          q.z = pack_bf16x2(o[4], o[5]); q.w = pack_bf16x2(o[6], o[7]);
+          *reinterpret_cast<uint4*>(dx.at(xbase + sp[u], c0)) = q;
         }
       }
     }
@@ -148,19 +159,19 @@ __global__ void __launch_bounds__(256)
       __syncthreads();
       if (threadIdx.x < 64) {
         const int o8 = threadIdx.x >> 3, k = threadIdx.x & 7;
-        float s = 0.f;
-        for (int r = 0; r < 32; ++r) s += sred[(r * 8 + o8) * 8 + k];
+        float s_ = 0.f;
+        for (int r = 0; r < 32; ++r) s_ += sred[(r * 8 + o8) * 8 + k];
         const int c = cb + o8 * 8 + k;
-        if (c < c_in && dw) atomicAdd(dw + (long)j * c_in + c, s);
+        if (c < c_in && dw) atomicAdd(dw + (long)j * c_in + c, s_);
       }
       if (cb == 0 && db) {
         __syncthreads();
         sred[threadIdx.x] = oct == 0 ? ab[j] : 0.f;
         __syncthreads();
         if (threadIdx.x == 0) {
-          float s = 0.f;
-          for (int r = 0; r < 256; r += 8) s += sred[r];
-          atomicAdd(db + j, s);
+          float s_ = 0.f;
+          for (int r = 0; r < 256; r += 8) s_ += sred[r];
+          atomicAdd(db + j, s_);
         }
       }
     }
@@ -353,9 +364,13 @@ int b200_head_fwd(int32_t n, int64_t spatial, int32_t c_in, int32_t c_out, b200_
   const long total = (long)n * spatial;
   if (total <= 0) return B200_OK;
   const size_t smem = ((size_t)c_out * c_in + c_out) * sizeof(float);
-  if (smem > 48 * 1024 || c_out > HEAD_CO_LIMIT || c_in % 8 || x.ctot % 8 || x.coff % 8)
+  if (smem > 48 * 1024 || c_out > HEAD_CO_LIMIT || c_in % 8 || x.ctot % 8 || x.coff % 8 || n > 65535)
     return B200_ERR_UNSUPPORTED;
-#define HEAD_FWD(CO) head_fwd_kernel<CO><<<grid1d(total * 8), 256, smem, (cudaStream_t)stream>>>(n, (long)spatial, c_in, c_out, mk(x), w, b, logits)
+  long gx = (spatial + 255) / 256;
+  const long cap = (148L * 16 + n - 1) / n;
+  if (gx > cap) gx = cap;
+  const dim3 grid((unsigned)(gx < 1 ? 1 : gx), (unsigned)n);
+#define HEAD_FWD(CO) head_fwd_kernel<CO><<<grid, 256, smem, (cudaStream_t)stream>>>((long)spatial, c_in, c_out, mk(x), w, b, logits)
   if (c_out <= 1) HEAD_FWD(1); else if (c_out <= 2) HEAD_FWD(2); else if (c_out <= 4) HEAD_FWD(4); else HEAD_FWD(8);
 #undef HEAD_FWD
   B200_LAUNCH_CHECK();
@@ -368,11 +383,14 @@ int b200_head_bwd(int32_t n, int64_t spatial, int32_t c_in, int32_t c_out, b200_
   if (total <= 0) return B200_OK;
   const size_t smem = ((size_t)c_out * c_in + 2048) * sizeof(float);
   if (smem > 48 * 1024 || c_out > HEAD_CO_LIMIT || c_in % 8 || x.ctot % 8 || x.coff % 8 ||
-      (dx.ptr && (dx.ctot % 8 || dx.coff % 8)))
+      (dx.ptr && (dx.ctot % 8 || dx.coff % 8)) || n > 65535)
     return B200_ERR_UNSUPPORTED;
-  long chunk = (total + 148L * 16 - 1) / (148L * 16);
+  long per = (148L * 16 + n - 1) / n;              // blocks per sample
+  long chunk = (spatial + per - 1) / per;
+  chunk = (chunk + 63) / 64 * 64;                  // whole 64-position block passes
   if (chunk < 256) chunk = 256;
-#define HEAD_BWD(CO) head_bwd_kernel<CO><<<(unsigned)((total + chunk - 1) / chunk), 256, smem, (cudaStream_t)stream>>>(n, (long)spatial, c_in, c_out, chunk, mk(x), w, dlogits, mk(dx), dw, db, mask_relu)
+  const dim3 grid((unsigned)((spatial + chunk - 1) / chunk), (unsigned)n);
+#define HEAD_BWD(CO) head_bwd_kernel<CO><<<grid, 256, smem, (cudaStream_t)stream>>>((long)spatial, c_in, c_out, chunk, mk(x), w, dlogits, mk(dx), dw, db, mask_relu)
   if (c_out <= 1) HEAD_BWD(1); else if (c_out <= 2) HEAD_BWD(2); else if (c_out <= 4) HEAD_BWD(4); else HEAD_BWD(8);
 #undef HEAD_BWD
   B200_LAUNCH_CHECK();

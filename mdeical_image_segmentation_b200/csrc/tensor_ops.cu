@@ -39,6 +39,12 @@ static inline View mk(const b200_view& v) { return View{(bf16*)v.ptr, v.ctot, v.
 static inline bool vec8(int c, const b200_view& a) {
   return c % 8 == 0 && a.ctot % 8 == 0 && a.coff % 8 == 0 && ((uintptr_t)a.ptr % 16) == 0;
 }
+// out = in * 2^k: ATen's float index map floor(dst * (in / out)) is then exactly dst >> k
+static inline bool pow2_factor(int in, int out) {
+  if (in <= 0 || out % in) return false;
+  const int f = out / in;
+  return (f & (f - 1)) == 0;
+}
 static inline unsigned blocks_for(long total, int threads) {
   return (unsigned)((total + threads - 1) / threads);
 }
@@ -159,6 +165,30 @@ __global__ void upsample_fwd_kernel(int n, int id, int ih, int iw, int od, int o
     Vec<V>::store(y.at((((long)b * od + xd) * oh + xh) * ow + xw, ch), f);
   }
 }
+// whole-factor up-sampling (the 2x of every U-Net decoder level): one thread per SOURCE vector writes
+// its fd*fh*fw children, so the index arithmetic is paid once per 16 bytes read, not per 16 bytes written
+template <int V>
+__global__ void upsample_exact_fwd_kernel(int n, int id, int ih, int iw, int fd, int fh, int fw, int c,
+                                          View x, View y) {
+  const int cv = c / V;
+  const int od = id * fd, oh = ih * fh, ow = iw * fw;
+  const long total = (long)n * id * ih * iw * cv;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    long r = i;
+    const int ch = (int)(r % cv) * V; r /= cv;
+    const int xw = (int)(r % iw); r /= iw;
+    const int xh = (int)(r % ih); r /= ih;
+    const int xd = (int)(r % id); r /= id;
+    const int b = (int)r;
+    float f[V];
+    Vec<V>::load(x.at((((long)b * id + xd) * ih + xh) * iw + xw, ch), f);
+    for (int a = 0; a < fd; ++a)
+      for (int e = 0; e < fh; ++e) {
+        const long row = (((long)b * od + xd * fd + a) * oh + xh * fh + e) * ow + (long)xw * fw;
+        for (int g = 0; g < fw; ++g) Vec<V>::store(y.at(row + g, ch), f);
+      }
+  }
+}
 // children of source index s along one axis: [lo, hi)
 __device__ __forceinline__ void children(int s, float scale, int in, int out, int& lo, int& hi) {
   int o = (int)floorf(s / scale) - 2;
@@ -170,7 +200,7 @@ __device__ __forceinline__ void children(int s, float scale, int in, int out, in
 }
 template <int V>
 __global__ void upsample_bwd_kernel(int n, int id, int ih, int iw, int od, int oh, int ow, int c,
-                                    View dy, View dx) {
+                                    View dy, View dx, int exact) {
   const int cv = c / V;
   const float sd = (float)id / od, sh = (float)ih / oh, sw = (float)iw / ow;
   const long total = (long)n * id * ih * iw * cv;
@@ -182,9 +212,15 @@ __global__ void upsample_bwd_kernel(int n, int id, int ih, int iw, int od, int o
     const int xd = (int)(r % id); r /= id;
     const int b = (int)r;
     int d0, d1, h0, h1, w0, w1;
-    children(xd, sd, id, od, d0, d1);
-    children(xh, sh, ih, oh, h0, h1);
-    children(xw, sw, iw, ow, w0, w1);
+    if (exact) {   // whole factors: children of s are [s*f, s*f + f)
+      d0 = xd * (od / id); d1 = d0 + od / id;
+      h0 = xh * (oh / ih); h1 = h0 + oh / ih;
+      w0 = xw * (ow / iw); w1 = w0 + ow / iw;
+    } else {
+      children(xd, sd, id, od, d0, d1);
+      children(xh, sh, ih, oh, h0, h1);
+      children(xw, sw, iw, ow, w0, w1);
+    }
     float acc[V];
 #pragma unroll
     for (int j = 0; j < V; ++j) acc[j] = 0.f;
@@ -790,6 +826,12 @@ int b200_upsample_nearest_fwd(int32_t n, int32_t id, int32_t ih, int32_t iw, int
   const long total = (long)n * od * oh * ow * c;
   if (total <= 0) return B200_OK;
   const bool v = vec8(c, x) && vec8(c, y);
+  if (pow2_factor(id, od) && pow2_factor(ih, oh) && pow2_factor(iw, ow)) {   // floor(dst * in / out) == dst / f
+    const long src = (long)n * id * ih * iw * c;
+    DISPATCH_V(v, upsample_exact_fwd_kernel, GRID1D(src / (v ? 8 : 1)), n, id, ih, iw, od / id, oh / ih,
+               ow / iw, c, mk(x), mk(y));
+    return B200_OK;
+  }
   DISPATCH_V(v, upsample_fwd_kernel, GRID1D(total / (v ? 8 : 1)), n, id, ih, iw, od, oh, ow, c, mk(x),
              mk(y));
   return B200_OK;
@@ -800,8 +842,9 @@ int b200_upsample_nearest_bwd(int32_t n, int32_t id, int32_t ih, int32_t iw, int
   const long total = (long)n * id * ih * iw * c;
   if (total <= 0) return B200_OK;
   const bool v = vec8(c, dy) && vec8(c, dx);
+  const int exact = pow2_factor(id, od) && pow2_factor(ih, oh) && pow2_factor(iw, ow);
   DISPATCH_V(v, upsample_bwd_kernel, GRID1D(total / (v ? 8 : 1)), n, id, ih, iw, od, oh, ow, c, mk(dy),
-             mk(dx));
+             mk(dx), exact);
   return B200_OK;
 }
 int b200_deconv_planes_resize_fwd(int32_t n, int32_t d, int32_t h, int32_t w, int32_t c, int32_t kd,

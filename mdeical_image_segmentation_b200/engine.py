@@ -467,7 +467,8 @@ def unet3d_forward(net, x_in: torch.Tensor, training: bool, tape: Optional[list]
             # nearest up-sampling by whole factors replicates every voxel f times: the statistics of
             # the concat buffer are those of its two producers, no extra pass
             s_skip = skip_sums[n_enc - 2 - j]
-            exact = size[0] % x.d == 0 and size[1] % x.h == 0 and size[2] % x.w == 0
+            exact = all(o % i == 0 and ((o // i) & (o // i - 1)) == 0
+                        for o, i in zip(size, (x.d, x.h, x.w)))   # power-of-two factors map exactly
             if x_sums is not None and s_skip is not None and exact:
                 f = (size[0] // x.d) * (size[1] // x.h) * (size[2] // x.w)
                 cat_sums = torch.cat([s_skip, x_sums * float(f)], dim=2)
