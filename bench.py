@@ -174,7 +174,8 @@ class KernelProfiler:
             ms = e0.elapsed_time(e1)
             if "repack" in name:
                 key = "repack"
-            elif name in ("b200_conv_fwd", "b200_conv_bwd_data", "b200_convt2x2_fwd", "b200_convt2x2_bwd_data"):
+            elif name in ("b200_conv_fwd", "b200_conv_bwd_data", "b200_convt2x2_fwd", "b200_convt2x2_bwd_data",
+                          "b200_conv_fwd_stats", "b200_conv_bwd_data_stats", "b200_convt2x2_bwd_data_stats"):
                 key = "tc_gemm_kernel" if impl == 1 else "direct_gemm_kernel"
             elif name in ("b200_conv_bwd_weight", "b200_convt2x2_bwd_weight"):
                 key = "tc_wgrad_kernel" if impl == 1 else "direct_wgrad_kernel"

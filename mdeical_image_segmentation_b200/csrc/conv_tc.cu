@@ -251,25 +251,40 @@ __device__ __forceinline__ void epi_chunk(const EpiArgs& e, const uint32_t (&v)[
   __syncwarp();
 }
 
-// fold the per-lane partial column sums of one chunk into the CTA's shared column sums [2][bn]
+// Fold the per-lane partial column sums of one chunk into the CTA's shared column sums [2][bn].
+// The 8 lanes that own the same 8 columns (lane bits 2..4) hold 8 or 16 partials each; a halving
+// exchange (send the half the partner keeps, add the half received) leaves every lane with 1 or 2
+// finished sums after 3 steps — 14 shuffles instead of the 48 of a plain butterfly.
 template <int STATS>
 __device__ __forceinline__ void epi_fold_acc(float (&acc)[16], float* colsum, int c0, int ncol, int bn,
                                              int lane) {
-  constexpr int NS = STATS == EPI_STATS_SUM ? 8 : 16;
-#pragma unroll
-  for (int k = 0; k < NS; ++k) {
-    float a = acc[k];
-    a += __shfl_xor_sync(0xffffffffu, a, 4);
-    a += __shfl_xor_sync(0xffffffffu, a, 8);
-    a += __shfl_xor_sync(0xffffffffu, a, 16);
-    acc[k] = a;
-  }
+  const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4;
   const int ch = lane & 3;
-  if ((lane >> 2) == 0 && ch * 8 < ncol) {
+  if (STATS == EPI_STATS_SUM) {
+    float a[4], b[2];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      atomicAdd(colsum + c0 + ch * 8 + k, acc[k]);
-      if (NS == 16) atomicAdd(colsum + bn + c0 + ch * 8 + k, acc[8 + k]);
+    for (int k = 0; k < 4; ++k)
+      a[k] = (b4 ? acc[4 + k] : acc[k]) + __shfl_xor_sync(0xffffffffu, b4 ? acc[k] : acc[4 + k], 16);
+#pragma unroll
+    for (int k = 0; k < 2; ++k)
+      b[k] = (b3 ? a[2 + k] : a[k]) + __shfl_xor_sync(0xffffffffu, b3 ? a[k] : a[2 + k], 8);
+    const float c = (b2 ? b[1] : b[0]) + __shfl_xor_sync(0xffffffffu, b2 ? b[0] : b[1], 4);
+    if (ch * 8 < ncol) atomicAdd(colsum + c0 + ch * 8 + (b4 ? 4 : 0) + (b3 ? 2 : 0) + (b2 ? 1 : 0), c);
+  } else {
+    float a[8], b[4], c[2];
+#pragma unroll
+    for (int k = 0; k < 8; ++k)   // bit 4 picks the statistic
+      a[k] = (b4 ? acc[8 + k] : acc[k]) + __shfl_xor_sync(0xffffffffu, b4 ? acc[k] : acc[8 + k], 16);
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      b[k] = (b3 ? a[4 + k] : a[k]) + __shfl_xor_sync(0xffffffffu, b3 ? a[k] : a[4 + k], 8);
+#pragma unroll
+    for (int k = 0; k < 2; ++k)
+      c[k] = (b2 ? b[2 + k] : b[k]) + __shfl_xor_sync(0xffffffffu, b2 ? b[k] : b[2 + k], 4);
+    if (ch * 8 < ncol) {
+      float* dst = colsum + (b4 ? bn : 0) + c0 + ch * 8 + (b3 ? 4 : 0) + (b2 ? 2 : 0);
+      atomicAdd(dst, c[0]);
+      atomicAdd(dst + 1, c[1]);
     }
   }
 #pragma unroll
@@ -590,7 +605,7 @@ struct HaloArgs {
 // bookkeeping per tap + ~27 ns per MMA with run-time R / tap loops).  R (row-blocks) and G (taps per
 // weight slot) are template parameters and the 9 in-plane taps are unrolled, so every descriptor is
 // base + compile-time constant and a tap's R x 4 MMAs are issued back to back.
-template <int R, int G, bool K64>
+template <int R, int G, int NK>   // NK = K-steps per 64-channel chunk when uniform (4, 2, 1), 0 = run time
 __device__ __forceinline__ void halo_mma_warp(const HaloArgs& p, uint32_t tmem_base, uint32_t sA_addr,
                                               uint32_t sB_addr, uint64_t* afull, uint64_t* aempty,
                                               uint64_t* bfull, uint64_t* bempty, uint64_t* tfull,
@@ -634,11 +649,10 @@ __device__ __forceinline__ void halo_mma_warp(const HaloArgs& p, uint32_t tmem_b
               for (int r = 0; r < R; ++r) {
                 const uint64_t da = da0 + (uint64_t)((((r * 16 + khi) * kHaloW + kwi) * 128) >> 4);
                 const uint32_t td = tmem_d + (uint32_t)(r * BN);
-                if (K64) {   // C_in a multiple of 64: every chunk is 4 K-steps
+                if (NK > 0) {   // uniform chunks (C_in = 16, 32 or a multiple of 64): fully unrolled
                   umma_bf16(td, da, db, idesc, fresh);
-                  umma_bf16(td, da + 2, db + 2, idesc, 1u);
-                  umma_bf16(td, da + 4, db + 4, idesc, 1u);
-                  umma_bf16(td, da + 6, db + 6, idesc, 1u);
+#pragma unroll
+                  for (int k = 1; k < NK; ++k) umma_bf16(td, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, 1u);
                 } else {
                   for (int k = 0; k < nk; ++k)
                     umma_bf16(td, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, k ? 1u : fresh);
@@ -748,16 +762,24 @@ __global__ void __launch_bounds__(384, 1)
     const uint32_t sA_addr = smem_u32(sA), sB_addr = smem_u32(sB);
 #define HALO_MMA(RR, GG, KK) \
   halo_mma_warp<RR, GG, KK>(p, tmem_base, sA_addr, sB_addr, afull, aempty, bfull, bempty, tfull, tempty)
-    const bool k64 = (p.kdim & 63) == 0;
+    const int nku = (p.kdim & 63) == 0 ? 4 : (p.kdim == 32 ? 2 : (p.kdim == 16 ? 1 : 0));
+#define HALO_MMA_NK(RR, GG)                                   \
+  do {                                                        \
+    if (nku == 4) HALO_MMA(RR, GG, 4);                        \
+    else if (nku == 2) HALO_MMA(RR, GG, 2);                   \
+    else if (nku == 1) HALO_MMA(RR, GG, 1);                   \
+    else HALO_MMA(RR, GG, 0);                                 \
+  } while (0)
     if (p.G == 3) {
-      if (p.R == 4) { if (k64) HALO_MMA(4, 3, true); else HALO_MMA(4, 3, false); }
-      else if (p.R == 2) { if (k64) HALO_MMA(2, 3, true); else HALO_MMA(2, 3, false); }
-      else { if (k64) HALO_MMA(1, 3, true); else HALO_MMA(1, 3, false); }
+      if (p.R == 4) HALO_MMA_NK(4, 3);
+      else if (p.R == 2) HALO_MMA_NK(2, 3);
+      else HALO_MMA_NK(1, 3);
     } else {
-      if (p.R == 4) { if (k64) HALO_MMA(4, 1, true); else HALO_MMA(4, 1, false); }
-      else if (p.R == 2) { if (k64) HALO_MMA(2, 1, true); else HALO_MMA(2, 1, false); }
-      else { if (k64) HALO_MMA(1, 1, true); else HALO_MMA(1, 1, false); }
+      if (p.R == 4) HALO_MMA_NK(4, 1);
+      else if (p.R == 2) HALO_MMA_NK(2, 1);
+      else HALO_MMA_NK(1, 1);
     }
+#undef HALO_MMA_NK
 #undef HALO_MMA
   } else if (warp >= 4 && warp < 4 + p.e.epi_warps) {
     // ---------------------------------------------------------------- epilogue (see epi_chunk)
