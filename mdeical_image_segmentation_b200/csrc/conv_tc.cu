@@ -632,40 +632,54 @@ __device__ __forceinline__ void halo_mma_warp(const HaloArgs& p, uint32_t tmem_b
         tc_fence_after();
         const uint64_t da0 = adesc0 + (uint64_t)((sA_addr + (uint32_t)stage * a_stage_bytes) >> 4);
         const bool last_plane = kc == kchunks - 1 && kdi == kd - 1;
+        // all MMAs of taps [t0, t1) of this plane; weight slab of tap t sits at slot_base + (t - t0) slabs
+        auto issue_taps = [&](int t0, int t1, uint32_t slab_addr) {
 #pragma unroll
-        for (int khi = 0; khi < 3; ++khi) {
+          for (int t = 0; t < 9; ++t) {
+            if (t < t0 || t >= t1) continue;
+            const int khi = t / 3, kwi = t - khi * 3;
+            const uint64_t db = bdesc0 + (uint64_t)((slab_addr + (uint32_t)(t - t0) * tap_bytes) >> 4);
+            const uint32_t fresh = (kc | kdi | t) == 0 ? 0u : 1u;   // first MMA of a tile overwrites
 #pragma unroll
-          for (int kwi = 0; kwi < 3; ++kwi) {
-            const int sub = G == 3 ? kwi : 0;
-            if (sub == 0 && (!resident || first_tile)) {
-              mbar_wait(&bfull[slot], bphase);
-              tc_fence_after();
-            }
-            if (elect_one()) {
-              const uint64_t db =
-                  bdesc0 + (uint64_t)((sB_addr + (uint32_t)slot * b_bytes + (uint32_t)sub * tap_bytes) >> 4);
-              const uint32_t fresh = (kc | kdi | khi | kwi) == 0 ? 0u : 1u;  // first MMA of a tile overwrites
+            for (int r = 0; r < R; ++r) {
+              const uint64_t da = da0 + (uint64_t)((((r * 16 + khi) * kHaloW + kwi) * 128) >> 4);
+              const uint32_t td = tmem_d + (uint32_t)(r * BN);
+              if (NK > 0) {   // uniform chunks (C_in = 16, 32 or a multiple of 64): fully unrolled
+                umma_bf16(td, da, db, idesc, fresh);
 #pragma unroll
-              for (int r = 0; r < R; ++r) {
-                const uint64_t da = da0 + (uint64_t)((((r * 16 + khi) * kHaloW + kwi) * 128) >> 4);
-                const uint32_t td = tmem_d + (uint32_t)(r * BN);
-                if (NK > 0) {   // uniform chunks (C_in = 16, 32 or a multiple of 64): fully unrolled
-                  umma_bf16(td, da, db, idesc, fresh);
-#pragma unroll
-                  for (int k = 1; k < NK; ++k) umma_bf16(td, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, 1u);
-                } else {
-                  for (int k = 0; k < nk; ++k)
-                    umma_bf16(td, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, k ? 1u : fresh);
-                }
+                for (int k = 1; k < NK; ++k) umma_bf16(td, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, 1u);
+              } else {
+                for (int k = 0; k < nk; ++k)
+                  umma_bf16(td, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, k ? 1u : fresh);
               }
-              if (sub == G - 1 && !resident) umma_commit(&bempty[slot]);
-              if (khi == 2 && kwi == 2) {
+            }
+          }
+        };
+        if (resident && !first_tile) {
+          // weights already in place: the whole plane (9 taps x R x NK MMAs) goes out in one elected block
+          if (elect_one()) {
+            issue_taps(0, 9, sB_addr + (uint32_t)slot * b_bytes);
+            umma_commit(&aempty[stage]);
+            if (last_plane) umma_commit(&tfull[acc]);
+          }
+          __syncwarp();
+          slot += 9 / G;
+          if (slot >= b_slots) { slot -= b_slots; bphase ^= 1; }
+        } else {
+#pragma unroll
+          for (int g = 0; g < 9 / G; ++g) {   // one weight slot (G taps) per elected block
+            mbar_wait(&bfull[slot], bphase);
+            tc_fence_after();
+            if (elect_one()) {
+              issue_taps(g * G, g * G + G, sB_addr + (uint32_t)slot * b_bytes);
+              if (!resident) umma_commit(&bempty[slot]);
+              if (g == 9 / G - 1) {
                 umma_commit(&aempty[stage]);
                 if (last_plane) umma_commit(&tfull[acc]);
               }
             }
             __syncwarp();
-            if (sub == G - 1 && ++slot == b_slots) { slot = 0; bphase ^= 1; }
+            if (++slot == b_slots) { slot = 0; bphase ^= 1; }
           }
         }
         if (++stage == a_stages) { stage = 0; aphase ^= 1; }
