@@ -4,7 +4,7 @@ arithmetic runs in hand-written CUDA (tcgen05/TMEM/TMA implicit-GEMM convolution
 kernels) behind a C ABI (``include/b200unet.h``).  There is no CPU / PyTorch-eager fallback."""
 from . import _lib, metrics  # noqa: F401
 from .losses import (BCEDiceLoss, BCEWithLogitsLoss, CrossEntropyLoss, DiceLoss, F1Loss, IoULoss,
-                     compute_per_channel_dice, get_loss_criterion)
+                     SegmentationLoss, compute_per_channel_dice, flatten, get_loss_criterion)
 from .unet2d import (CropAndConcat, DoubleConvolution, DownSample, UNet, UpSample, unetConv2)
 from .unet3d import (AbstractUNet, Decoder, DoubleConv, Encoder, SingleConv, UNet2D, UNet3D,
                      create_conv, number_of_features_per_level)

@@ -167,6 +167,42 @@ class F1Loss(nn.Module):
         return (1 - 2 * (precision * recall) / (precision + recall + self.epsilon)).float()
 
 
+class SegmentationLoss(nn.Module):
+    """model/unet2d/loss.py:59-70: ``F1 + MS-SSIM + IoU``.  The F1 and IoU terms come out of ONE pass over
+    the logits (the six-sum kernel); the MS-SSIM term is computed by the third-party ``pytorch_msssim``
+    package in the reference (loss.py:3-4,21-28), which is outside the B200 hot path:
+    pass ``ms_ssim_loss`` (any ``nn.Module`` taking (logits, targets)) to add it, otherwise the
+    criterion is the sum of the two reduction terms."""
+
+    def __init__(self, ms_ssim_loss: Optional[nn.Module] = None, epsilon: float = 1e-7):
+        super().__init__()
+        self.f1_loss = F1Loss(epsilon)
+        self.iou_loss = IoULoss(epsilon)
+        self.ms_ssim_loss = ms_ssim_loss
+        self.epsilon = epsilon
+
+    def forward(self, inputs, targets):
+        s = seg_sums(inputs, targets, "sigmoid").sum(dim=0)
+        tp = s[S_PT]
+        precision = tp / (s[S_P] + self.epsilon)
+        recall = tp / (s[S_T] + self.epsilon)
+        f1 = 1 - 2 * (precision * recall) / (precision + recall + self.epsilon)
+        union = s[S_P] + s[S_T] - tp
+        iou = 1 - (tp + self.epsilon) / (union + self.epsilon)
+        loss = (f1 + iou).float()
+        if self.ms_ssim_loss is not None:
+            loss = loss + self.ms_ssim_loss(inputs, targets)
+        return loss
+
+
+def flatten(tensor: torch.Tensor) -> torch.Tensor:
+    """model/unet3d/losses.py:258-270: (N, C, D, H, W) -> (C, N * D * H * W).  Public helper kept for
+    drop-in callers; the fused loss kernels reduce in place and never materialise this copy."""
+    c = tensor.size(1)
+    axis_order = (1, 0) + tuple(range(2, tensor.dim()))
+    return tensor.permute(axis_order).contiguous().view(c, -1)
+
+
 def get_loss_criterion(config):
     """losses.py:273-306 for the losses on the path; anything else is left to stock PyTorch by the
     caller (GeneralizedDice / weighted CE / pixel-wise CE are out of scope)."""

@@ -244,6 +244,14 @@ def test_losses_vs_reference_golden(B):
         l.backward()
         assert abs(l.item() - float(f[nm + "_loss"])) < 1e-5, nm
         assert rel_l2(x2.grad.cpu(), f[nm + "_grad"]) < 1e-4, nm
+    # SegmentationLoss (loss.py:59-70) without its third-party MS-SSIM term = F1 + IoU, one pass
+    x2 = torch.from_numpy(f["x2"]).cuda().requires_grad_(True)
+    l = B.SegmentationLoss()(x2, t2)
+    l.backward()
+    assert abs(l.item() - float(f["iou_loss"]) - float(f["f1_loss"])) < 2e-5
+    assert rel_l2(x2.grad.cpu(), f["iou_grad"] + f["f1_grad"]) < 1e-4
+    assert B.flatten(x).shape == (x.shape[1], x.numel() // x.shape[1])
+    assert torch.equal(B.flatten(x)[1], x[:, 1].reshape(-1))
     xc = torch.from_numpy(f["ce_x"]).cuda().requires_grad_(True)
     l = B.CrossEntropyLoss()(xc, torch.from_numpy(f["ce_y"]).cuda())
     l.backward()
