@@ -39,7 +39,22 @@ WORKLOADS = {
     "cfg3p": dict(kind="3d", cin=1, cout=1, size=(128, 128, 128), batch=2, train_tf=9.532, unit="vols/s",
                   order="cbr", upsample="deconv",
                   desc="UNet3D(1,1) cbr+deconv 128^3, batch 2 per GPU, BCEDice + Adam"),
+    "cfg4": dict(kind="3d", cin=4, cout=3, size=(160, 192, 160), batch=1, train_tf=26.675, unit="vols/s",
+                 order="gcr", upsample="default", loss="dice",
+                 desc="UNet3D(4,3) gcr+nearest 160x192x160 (BraTS-like), batch 1 per GPU, fused Dice + Adam"),
+    "cfg4p": dict(kind="3d", cin=4, cout=3, size=(160, 192, 160), batch=1, train_tf=22.394, unit="vols/s",
+                  order="cbr", upsample="deconv", loss="dice",
+                  desc="UNet3D(4,3) cbr+deconv 160x192x160 (BraTS-like), batch 1 per GPU, fused Dice + Adam"),
 }
+
+# cfg5 (BASELINE.json configs[4]): inference-only sweep, eval() + no_grad, as api/api.py:64 would call it.
+# (kind, batch, size, fwd TFLOP per sample)
+SWEEP = [("2d", 1, (256, 256), 0.0962), ("2d", 16, (256, 256), 0.0962), ("2d", 64, (256, 256), 0.0962),
+         ("2d", 256, (256, 256), 0.0962), ("2d", 1, (512, 512), 0.385), ("2d", 16, (512, 512), 0.385),
+         ("2d", 64, (512, 512), 0.385), ("2d", 1, (1024, 1024), 1.539), ("2d", 16, (1024, 1024), 1.539),
+         ("3d", 1, (96, 96, 96), 1.598), ("3d", 4, (96, 96, 96), 1.598), ("3d", 1, (128, 128, 128), 3.787),
+         ("3d", 2, (128, 128, 128), 3.787), ("3d", 8, (128, 128, 128), 3.787), ("3d", 1, (160, 160, 160), 7.40),
+         ("3d", 1, (192, 192, 192), 12.78)]
 
 
 def peaks():
@@ -60,6 +75,10 @@ def make_batch(w, batch, seed, device="cpu", pin=False):
             y = torch.randint(0, w["cout"], (batch,) + w["size"], generator=g)
         else:
             y = (torch.rand((batch, 1) + w["size"], generator=g) > 0.7).float()
+    elif w["cout"] > 1:   # one-hot float target of the input's shape (model/unet3d/losses.py:20)
+        x = torch.randn((batch, w["cin"]) + w["size"], generator=g)
+        cls = torch.randint(0, w["cout"], (batch,) + w["size"], generator=g)
+        y = torch.nn.functional.one_hot(cls, w["cout"]).movedim(-1, 1).float().contiguous()
     else:
         x = torch.randn((batch, w["cin"]) + w["size"], generator=g)
         y = (torch.rand((batch, w["cout"]) + w["size"], generator=g) > 0.7).float()
@@ -128,7 +147,7 @@ def build_model(w, device):
             return model(images=x, labels=y).loss
     else:
         net = B.UNet3D(w["cin"], w["cout"], layer_order=w["order"], upsample=w["upsample"]).to(device).train()
-        crit = B.BCEDiceLoss(1.0, 1.0)
+        crit = B.DiceLoss(normalization="sigmoid") if w.get("loss") == "dice" else B.BCEDiceLoss(1.0, 1.0)
         model = net
         opt = torch.optim.Adam(model.parameters(), lr=1e-4, fused=True)
 
@@ -346,6 +365,72 @@ def run_b200(args, w):
         dist.destroy_process_group()
 
 
+# --------------------------------------------------------------------------------------- cfg5 sweep
+def run_sweep(args):
+    """BASELINE.json configs[4]: inference-only sweep (eval + no_grad; logits out), one GPU.  Per point:
+    device-resident latency p50 / p99 over the timed iterations (CUDA events per call), throughput, the
+    fraction of the sustained bf16 peak, and the end-to-end latency of one request through the public
+    module call with a pinned host input (H2D) and the logits read back (D2H)."""
+    import mdeical_image_segmentation_b200 as B
+    from mdeical_image_segmentation_b200 import _lib
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    pk = peaks()
+    torch.manual_seed(0)
+    nets = {"2d": B.UNet(1, 1).to(device).eval(), "3d": B.UNet3D(1, 1).to(device).eval()}
+    rows = []
+    iters = max(args.steps, 5)
+    _lib.launch_count = 0
+    with ClockSampler(local) as clocks, torch.no_grad():
+        for kind, batch, size, tf in SWEEP:
+            net = nets[kind]
+            g = torch.Generator().manual_seed(batch)
+            xh = torch.randn((batch, 1) + size, generator=g).pin_memory()
+            x = xh.to(device)
+            for _ in range(max(args.warmup, 3)):
+                net(x)
+            torch.cuda.synchronize()
+            evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+                   for _ in range(iters)]
+            for e0, e1 in evs:
+                e0.record()
+                net(x)
+                e1.record()
+            torch.cuda.synchronize()
+            lat = sorted(e0.elapsed_time(e1) for e0, e1 in evs)
+            mean = sum(lat) / len(lat)
+            t0 = time.perf_counter()
+            for _ in range(3):
+                out = net(xh.to(device, non_blocking=True))
+                out.cpu()
+            e2e_ms = (time.perf_counter() - t0) / 3 * 1e3
+            rows.append({"model": "UNet(1,1)" if kind == "2d" else "UNet3D(1,1) gcr", "batch": batch,
+                         "size": "x".join(map(str, size)), "p50_ms": round(lat[len(lat) // 2], 3),
+                         "p99_ms": round(lat[min(len(lat) - 1, int(0.99 * len(lat)))], 3),
+                         "per_s": round(batch / (mean / 1e3), 2),
+                         "tflops": round(tf * batch / (mean / 1e3), 1),
+                         "frac_of_sustained_peak": round(tf * batch / (mean / 1e3) / pk["tf_sustained"], 4),
+                         "e2e_ms": round(e2e_ms, 3), "e2e_per_s": round(batch / (e2e_ms / 1e3), 2),
+                         "h2d_bytes": xh.numel() * 4, "d2h_bytes": out.numel() * 4})
+            del x, xh, out
+            torch.cuda.empty_cache()
+    head = next(r for r in rows if r["size"] == "128x128x128" and r["batch"] == 2)
+    print(json.dumps({
+        "metric": "inference vols/s", "value": head["per_s"], "unit": "vols/s", "n_gpus": 1, "steps": iters,
+        "warmup": max(args.warmup, 3), "ms_per_step": head["p50_ms"], "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": "cfg5: inference-only sweep, UNet(1,1) 256^2-1024^2 and UNet3D(1,1) 96^3-192^3; "
+                               "headline value = UNet3D 128^3 batch 2", "l2": "activations exceed L2 except "
+                               "at batch 1 256^2 (latency point)"},
+        "e2e": {"value": head["e2e_per_s"], "unit": "vols/s", "h2d_bytes_per_step": head["h2d_bytes"],
+                "d2h_bytes_per_step": head["d2h_bytes"]},
+        "gpu_launches": _lib.launch_count, "clocks": clocks.summary(), "roofline": None, "cpu_baseline": None,
+        "sweep": rows}), flush=True)
+
+
 # --------------------------------------------------------------------------------------- CPU arm
 def run_cpu_sample(w, steps, warmup, batch=None):
     """Reference path on host cores via the oracle port: fwd + loss + bwd + optimizer on a bounded
@@ -369,10 +454,12 @@ def run_cpu_sample(w, steps, warmup, batch=None):
               for k, v in net.state_dict().items()}
         crop = dict(w, size=(64, 64, 64))
         x, y = make_batch(crop, b, 7)
-        fwd = lambda: O.bce_dice_loss(O.unet3d_forward(sd, x, layer_order=w["order"], upsample=w["upsample"],  # noqa: E731
-                                                      training=True), y)
+        lossf = O.dice_loss if w.get("loss") == "dice" else O.bce_dice_loss
+        fwd = lambda: lossf(O.unet3d_forward(sd, x, layer_order=w["order"], upsample=w["upsample"],  # noqa: E731
+                                             training=True), y)
         scale = 64.0 ** 3 / (w["size"][0] * w["size"][1] * w["size"][2])
-        sample = f"{b} crop(s) of 64^3 per step, scaled by voxel count to {w['size'][0]}^3 volumes"
+        sample = (f"{b} crop(s) of 64^3 per step, scaled by voxel count to "
+                  f"{'x'.join(str(v) for v in w['size'])} volumes")
         opt = torch.optim.Adam([v for v in sd.values() if v.requires_grad], lr=1e-4)
 
     def step():
@@ -413,12 +500,17 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS) + ["cfg5"])
     ap.add_argument("--batch", type=int, default=0)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.workload == "cfg5":
+        if args.impl == "reference":
+            print(json.dumps({"impl": "reference", "unavailable": "cfg5 is a sweep; use cfg2/cfg3 for the CPU arm"}))
+            return
+        return run_sweep(args)
     w = WORKLOADS[args.workload]
     if args.gpus > 1 and "WORLD_SIZE" not in os.environ and args.impl == "b200":
         # convenience: re-launch under torch.distributed.run, one rank per GPU
