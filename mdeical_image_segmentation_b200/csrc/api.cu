@@ -11,6 +11,7 @@ extern int g_halo_resident;
 extern int g_gemm_resident;
 extern int g_epi_dbg;
 extern int g_epi_warps;
+extern int g_wgrad_wide;
 int direct_gemm_conv(const TcGemmProblem& p, cudaStream_t stream);
 int direct_wgrad(const TcWgradProblem& p, cudaStream_t stream);
 static thread_local int g_last_impl = 0;
@@ -191,6 +192,7 @@ int b200_set_tuning(int key, int value) {
   if (key == 4) { b200::g_epi_dbg = value; return B200_OK; }
   if (key == 5) { b200::g_epi_warps = value; return B200_OK; }
   if (key == 3) { b200::g_halo_resident = value; b200::g_gemm_resident = value; return B200_OK; }
+  if (key == 6) { b200::g_wgrad_wide = value; return B200_OK; }
   return B200_ERR_BAD_ARG;
 }
 

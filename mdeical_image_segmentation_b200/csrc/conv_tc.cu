@@ -1213,6 +1213,7 @@ struct WgradArgs {
   int ntaps, kh, kw, pad_d, pad_h, pad_w, tap_mode;
   int M, mblk, nblk, T, tap_groups, splits, tiles_per_split;
   int cm, cn;  // channel counts of the M / N operands
+  int NB;      // 64-channel boxes of the N operand per MMA (N = 64 NB <= 256; LBO = one box)
   int stages;
   float* dw;
   long s_m, s_n;
@@ -1232,7 +1233,8 @@ __global__ void __launch_bounds__(256, 1)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tfull + 2);
   uint8_t* tiles = smem + 1024;
   const int mboxes = p.M / 64;
-  const int stage_bytes = (mboxes + p.T) * kABytes;
+  const int NB = p.NB, ncols = 64 * NB;
+  const int stage_bytes = (mboxes + p.T * NB) * kABytes;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
@@ -1246,7 +1248,7 @@ __global__ void __launch_bounds__(256, 1)
     fence_barrier_init();
   }
   uint32_t tmem_cols = 32;
-  while (tmem_cols < (uint32_t)(p.T * 64)) tmem_cols <<= 1;
+  while (tmem_cols < (uint32_t)(p.T * ncols)) tmem_cols <<= 1;
   if (warp == 2) tmem_alloc(tmem_slot, tmem_cols);
   tc_fence_before();
   __syncthreads();
@@ -1284,22 +1286,25 @@ __global__ void __launch_bounds__(256, 1)
       for (int t = 0; t < p.T; ++t) {
         const int tap = tap0 + t;
         const int kwi = tap % p.kw, khi = (tap / p.kw) % p.kh, kdi = tap / (p.kw * p.kh);
-        if (p.use_table)
-          tma_load_5d(sN + t * kABytes, &tmN, &full[stage], nb * 64, tc.w0 + p.tt.dw[tap],
-                      tc.h0 + p.tt.dh[tap], tc.d0 + p.tt.dd[tap], tc.n + p.tt.dn[tap]);
-        else if (p.tap_mode == TC_TAP_SHIFT)
-          tma_load_5d(sN + t * kABytes, &tmN, &full[stage], nb * 64, tc.w0 + kwi - p.pad_w,
-                      tc.h0 + khi - p.pad_h, tc.d0 + kdi - p.pad_d, tc.n);
-        else
-          tma_load_5d(sN + t * kABytes, &tmN, &full[stage], nb * 64, kwi, tc.w0, khi,
-                      tc.n * p.ph + tc.h0);
+        for (int b = 0; b < NB; ++b) {
+          uint8_t* dst = sN + (t * NB + b) * kABytes;
+          const int c0 = (nb * NB + b) * 64;
+          if (p.use_table)
+            tma_load_5d(dst, &tmN, &full[stage], c0, tc.w0 + p.tt.dw[tap], tc.h0 + p.tt.dh[tap],
+                        tc.d0 + p.tt.dd[tap], tc.n + p.tt.dn[tap]);
+          else if (p.tap_mode == TC_TAP_SHIFT)
+            tma_load_5d(dst, &tmN, &full[stage], c0, tc.w0 + kwi - p.pad_w, tc.h0 + khi - p.pad_h,
+                        tc.d0 + kdi - p.pad_d, tc.n);
+          else
+            tma_load_5d(dst, &tmN, &full[stage], c0, kwi, tc.w0, khi, tc.n * p.ph + tc.h0);
+        }
       }
       }
       __syncwarp();
       if (++stage == p.stages) { stage = 0; phase ^= 1; }
     }
   } else if (warp == 1) {
-    const uint32_t idesc = make_idesc_bf16(p.M, 64, 1, 1);
+    const uint32_t idesc = make_idesc_bf16(p.M, ncols, 1, 1);
     int stage = 0;
     uint32_t phase = 0;
     bool first = true;
@@ -1311,10 +1316,10 @@ __global__ void __launch_bounds__(256, 1)
       if (elect_one()) {
         const uint64_t da0 = make_smem_desc_sw128(maddr, kABytes, 1024);
         for (int t = 0; t < p.T; ++t) {
-          const uint64_t db0 = make_smem_desc_sw128(naddr + t * kABytes, kABytes, 1024);
+          const uint64_t db0 = make_smem_desc_sw128(naddr + t * NB * kABytes, kABytes, 1024);
 #pragma unroll
           for (int k = 0; k < 8; ++k)  // 16 positions (= 2 KB of rows) per MMA
-            umma_bf16(tmem_base + t * 64, da0 + (uint64_t)(k * 128), db0 + (uint64_t)(k * 128), idesc,
+            umma_bf16(tmem_base + t * ncols, da0 + (uint64_t)(k * 128), db0 + (uint64_t)(k * 128), idesc,
                       !(first && k == 0));
         }
         umma_commit(&empty[stage]);
@@ -1342,14 +1347,14 @@ __global__ void __launch_bounds__(256, 1)
     const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
     for (int t = 0; t < p.T; ++t) {
       const int tap = p.use_table ? p.tt.widx[tap0 + t] : tap0 + t;
-      for (int c0 = 0; c0 < 64; c0 += 16) {
+      for (int c0 = 0; c0 < ncols; c0 += 16) {
         uint32_t v[16];
-        tmem_ld16(taddr + t * 64 + c0, v);
+        tmem_ld16(taddr + t * ncols + c0, v);
         tmem_ld_wait();
         if (m_ok) {
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
-            const int n = nb * 64 + c0 + j;
+            const int n = nb * ncols + c0 + j;
             if (n < p.cn) atomicAdd(p.dw + (long)m * p.s_m + (long)n * p.s_n + tap, __uint_as_float(v[j]));
           }
         }
@@ -1375,12 +1380,19 @@ struct WgradHaloArgs {
   int tiles_h, tiles_w, m_tiles;
   int kd;                       // depth taps (1 or 3); blockIdx decodes (split, kd, co blk, ci blk)
   int ciblk, coblk, splits, tiles_per_split;
-  int cin, cout, N;             // N = co tile (multiple of 16, <= 64)
+  int cin, cout, N;             // N = co tile (multiple of 16, <= 64; 128 in the wide variant)
   int stages;
   float* dw;
   long s_co, s_ci;
 };
 
+// WIDE variant (C_out >= 128): an N = 64 MMA reads 4 KB of A + 2 KB of B from shared memory per 32
+// tensor-core cycles — more than the 128 B/clk shared memory delivers — so the narrow kernel tops out at
+// ~70 % of the pipe (and spends 1 slot in 10 on the duplicated tap 7).  With N = 128 the same 4 KB of A
+// feeds twice the math.  TMEM holds 512 columns = FOUR tap pairs x 128 output channels, so the wide
+// kernel takes the pairs (0,1)(2,3)(5,6)(7,8) and leaves the un-shifted centre tap 4 — a plain
+// dy^T * x GEMM — to tc_wgrad_kernel (N = 256 column blocks).
+template <bool WIDE>
 __global__ void __launch_bounds__(256, 1)
     tc_wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmDY,
                          const WgradHaloArgs p) {
@@ -1392,8 +1404,12 @@ __global__ void __launch_bounds__(256, 1)
   uint64_t* tfull = empty + 16;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tfull + 2);
   uint8_t* tiles = smem + 1024;
-  const int x_bytes = 23552;                 // 180 rows x 128 B, padded to 1024
-  const int stage_bytes = x_bytes + kABytes;  // + dy tile (128 rows x 128 B)
+  constexpr int x_bytes = 23552;                 // 180 rows x 128 B, padded to 1024
+  constexpr int kYBoxes = WIDE ? 2 : 1;          // dy tile: 128 rows x 128 B per 64 output channels
+  constexpr int stage_bytes = x_bytes + kYBoxes * kABytes;
+  constexpr int kGroups = WIDE ? 4 : 5;
+  constexpr int kGroupCols = WIDE ? 128 : 64;
+  constexpr int kCoBlock = WIDE ? 128 : 64;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
@@ -1427,15 +1443,17 @@ __global__ void __launch_bounds__(256, 1)
       if (elect_one()) {
         uint8_t* sX = tiles + (size_t)stage * stage_bytes;
         uint8_t* sY = sX + x_bytes;
-        mbar_arrive_expect_tx(&full[stage], (uint32_t)(kHaloPlaneBytes + kABytes));
+        mbar_arrive_expect_tx(&full[stage], (uint32_t)(kHaloPlaneBytes + kYBoxes * kABytes));
         tma_load_5d(sX, &tmX, &full[stage], cib * 64, tc.w0 - 1, tc.h0 - 1, tc.d0 + kdi - (p.kd >> 1), tc.n);
-        tma_load_5d(sY, &tmDY, &full[stage], cob * 64, tc.w0, tc.h0, tc.d0, tc.n);
+#pragma unroll
+        for (int b = 0; b < kYBoxes; ++b)
+          tma_load_5d(sY + b * kABytes, &tmDY, &full[stage], cob * kCoBlock + b * 64, tc.w0, tc.h0, tc.d0, tc.n);
       }
       __syncwarp();
       if (++stage == p.stages) { stage = 0; phase ^= 1; }
     }
   } else if (warp == 1) {
-    const uint32_t idesc = make_idesc_bf16(128, p.N, 1, 1);
+    const uint32_t idesc = make_idesc_bf16(128, WIDE ? 128 : p.N, 1, 1);
     int stage = 0;
     uint32_t phase = 0;
     bool first = true;
@@ -1447,14 +1465,14 @@ __global__ void __launch_bounds__(256, 1)
       if (elect_one()) {
       const uint64_t db0 = make_smem_desc_sw128(yaddr, kABytes, 1024);
 #pragma unroll
-      for (int g = 0; g < 5; ++g) {
-        const int ta = g < 4 ? 2 * g : 7, tb = ta + 1;
+      for (int g = 0; g < kGroups; ++g) {
+        const int ta = WIDE ? (g < 2 ? 2 * g : 2 * g + 1) : (g < 4 ? 2 * g : 7), tb = ta + 1;
         const int ra = (ta / 3) * kHaloW + (ta % 3), rb = (tb / 3) * kHaloW + (tb % 3);
         const uint64_t da0 = make_smem_desc_sw128(xaddr + (uint32_t)(ra * 128), (uint32_t)((rb - ra) * 128),
                                                   kHaloW * 128);
 #pragma unroll
         for (int j = 0; j < 8; ++j)  // 16 positions = 2 W-rows of the tile per MMA
-          umma_bf16(tmem_base + g * 64, da0 + (uint64_t)(j * ((2 * kHaloW * 128) >> 4)),
+          umma_bf16(tmem_base + g * kGroupCols, da0 + (uint64_t)(j * ((2 * kHaloW * 128) >> 4)),
                     db0 + (uint64_t)(j * (2048 >> 4)), idesc, !(first && j == 0));
       }
       umma_commit(&empty[stage]);
@@ -1470,23 +1488,24 @@ __global__ void __launch_bounds__(256, 1)
     const int m = q * 32 + lane;           // 0..127: (tap half, ci)
     const int half = m >> 6;
     const int ci = cib * 64 + (m & 63);
+    const int ncols = WIDE ? 128 : p.N;
     mbar_wait(&tfull[0], 0);
     tc_fence_after();
     const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
-    for (int g = 0; g < 5; ++g) {
-      const int ta = g < 4 ? 2 * g : 7;
+    for (int g = 0; g < kGroups; ++g) {
+      const int ta = WIDE ? (g < 2 ? 2 * g : 2 * g + 1) : (g < 4 ? 2 * g : 7);
       const int tap = ta + half;
-      const bool dup = (g == 4 && half == 0);  // tap 7 was already produced by group 3
+      const bool dup = (!WIDE && g == 4 && half == 0);  // tap 7 was already produced by group 3
       const bool ok = !dup && ci < p.cin && mt_end > mt_begin;
       const long base = (long)ci * p.s_ci + (kdi * 9 + tap);
-      for (int c0 = 0; c0 < p.N; c0 += 16) {
+      for (int c0 = 0; c0 < ncols; c0 += 16) {
         uint32_t v[16];
-        tmem_ld16(taddr + g * 64 + c0, v);
+        tmem_ld16(taddr + g * kGroupCols + c0, v);
         tmem_ld_wait();
         if (ok) {
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
-            const int co = cob * 64 + c0 + j;
+            const int co = cob * kCoBlock + c0 + j;
             if (co < p.cout) atomicAdd(p.dw + (long)co * p.s_co + base, __uint_as_float(v[j]));
           }
         }
@@ -1505,6 +1524,9 @@ static bool wgrad_halo_eligible(const TcWgradProblem& p) {
          (p.kd == 3 || p.kd == 1) && p.ph >= 12 && p.pw >= 8;
 }
 
+int g_wgrad_wide = 1;   // tuning knob: N = 128 four-pair variant + centre-tap GEMM for C_out >= 128
+static int tc_wgrad_generic(const TcWgradProblem& p, cudaStream_t stream, bool wide_n);
+
 static int tc_wgrad_halo(const TcWgradProblem& p, cudaStream_t stream) {
   // conv: mop = dy (c_out), nop = x (c_in); dw index = co * s_m + ci * s_n + tap
   WgradHaloArgs a{};
@@ -1513,9 +1535,12 @@ static int tc_wgrad_halo(const TcWgradProblem& p, cudaStream_t stream) {
   a.m_tiles = p.pn * p.pd * a.tiles_h * a.tiles_w;
   a.kd = p.kd;
   a.cin = p.nop.c; a.cout = p.mop.c;
-  a.ciblk = (a.cin + 63) / 64; a.coblk = (a.cout + 63) / 64;
-  a.N = a.cout >= 64 ? 64 : ((a.cout + 15) / 16) * 16;
-  const int stage_bytes = 23552 + kABytes;
+  // wide pays when the centre-tap GEMM can use N >= 128 (C_in >= 128) and there are enough tiles to split
+  const bool wide = g_wgrad_wide && a.cout >= 128 && a.cout % 64 == 0 && a.cin >= 128 && a.m_tiles >= 128;
+  const int co_block = wide ? 128 : 64;
+  a.ciblk = (a.cin + 63) / 64; a.coblk = (a.cout + co_block - 1) / co_block;
+  a.N = wide ? 128 : (a.cout >= 64 ? 64 : ((a.cout + 15) / 16) * 16);
+  const int stage_bytes = 23552 + (wide ? 2 : 1) * kABytes;
   a.stages = (kSmemBudget - 2048) / stage_bytes;
   if (a.stages > 6) a.stages = 6;
   const long base_ctas = (long)a.ciblk * a.coblk * a.kd;
@@ -1546,15 +1571,36 @@ static int tc_wgrad_halo(const TcWgradProblem& p, cudaStream_t stream) {
   const int smem = a.stages * stage_bytes + 2048;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(tc_wgrad_halo_kernel,
+    cudaError_t e = cudaFuncSetAttribute(tc_wgrad_halo_kernel<false>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(tc_wgrad_halo_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               kSmemBudget);
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
   }
   const long grid = base_ctas * a.splits;
-  tc_wgrad_halo_kernel<<<(unsigned)grid, 256, smem, stream>>>(tmX, tmDY, a);
-  B200_LAUNCH_CHECK();
-  return B200_OK;
+  if (!wide) {
+    tc_wgrad_halo_kernel<false><<<(unsigned)grid, 256, smem, stream>>>(tmX, tmDY, a);
+    B200_LAUNCH_CHECK();
+    return B200_OK;
+  }
+  if (g_wgrad_wide != 3) {   // (2 / 3: timing probes — pairs only / centre taps only)
+    tc_wgrad_halo_kernel<true><<<(unsigned)grid, 256, smem, stream>>>(tmX, tmDY, a);
+    B200_LAUNCH_CHECK();
+  }
+  if (g_wgrad_wide == 2) return B200_OK;
+  // the centre tap of every depth plane: un-shifted in-plane, so a plain per-tap reduction GEMM
+  TapTable tt{};
+  tt.ntaps = p.kd;
+  for (int k = 0; k < p.kd; ++k) {
+    tt.dd[k] = (signed char)(k - (p.kd >> 1));
+    tt.dh[k] = 0; tt.dw[k] = 0; tt.dn[k] = 0;
+    tt.widx[k] = (signed char)(k * 9 + 4);
+  }
+  TcWgradProblem c = p;
+  c.table = &tt;
+  return tc_wgrad_generic(c, stream, true);
 }
 
 bool tc_wgrad_supported(const TcWgradProblem& p) {
@@ -1567,6 +1613,13 @@ bool tc_wgrad_supported(const TcWgradProblem& p) {
 int tc_wgrad(const TcWgradProblem& p, cudaStream_t stream) {
   if (!tc_wgrad_supported(p)) return B200_ERR_UNSUPPORTED;
   if (wgrad_halo_eligible(p)) return tc_wgrad_halo(p, stream);
+  return tc_wgrad_generic(p, stream, false);
+}
+
+// wide_n: one tap per CTA and up to four 64-channel boxes of the tap-addressed operand per MMA
+// (N = 256): the centre-tap GEMM of the wide halo variant has no halo reuse, so its arithmetic
+// intensity has to come from the tile shape.
+static int tc_wgrad_generic(const TcWgradProblem& p, cudaStream_t stream, bool wide_n) {
   WgradArgs a{};
   a.pn = p.pn; a.pd = p.pd; a.ph = p.ph; a.pw = p.pw;
   const TileGeom g = pick_tile(p.pn, p.pd, p.ph, p.pw, p.tap_mode == TC_TAP_K2S2 || p.pd == 1);
@@ -1585,8 +1638,15 @@ int tc_wgrad(const TcWgradProblem& p, cudaStream_t stream) {
   a.mblk = (a.cm + a.M - 1) / a.M;
   a.nblk = (a.cn + 63) / 64;
   a.T = (a.ntaps % 3 == 0) ? 3 : (a.ntaps % 4 == 0 ? 4 : 1);
+  a.NB = 1;
+  if (wide_n) {
+    a.T = 1;
+    const int boxes = (a.cn + 63) / 64;
+    a.NB = boxes % 4 == 0 ? 4 : (boxes % 3 == 0 ? 3 : (boxes % 2 == 0 ? 2 : 1));
+  }
+  a.nblk = (a.cn + 64 * a.NB - 1) / (64 * a.NB);
   a.tap_groups = a.ntaps / a.T;
-  const int stage_bytes = (a.M / 64 + a.T) * kABytes;
+  const int stage_bytes = (a.M / 64 + a.T * a.NB) * kABytes;
   a.stages = (kSmemBudget - 2048) / stage_bytes;
   if (a.stages > 8) a.stages = 8;
   if (a.stages < 2) return B200_ERR_UNSUPPORTED;

@@ -287,6 +287,53 @@ def group_perf():
             print(f"[BAD] cudnn {name}: {e}", flush=True)
 
 
+def group_wgrad_perf():
+    """Weight-gradient kernels on the headline layer shapes: narrow (N = 64, five tap pairs) vs wide
+    (N = 128, four tap pairs + centre-tap GEMM) variants."""
+    from mdeical_image_segmentation_b200 import _lib
+    shapes = [
+        ("3D 384->128 64^3 b2", 2, 64, 64, 64, 384, 128, True),
+        ("3D 128->128 64^3 b2", 2, 64, 64, 64, 128, 128, True),
+        ("3D 768->256 32^3 b2", 2, 32, 32, 32, 768, 256, True),
+        ("3D 256->256 32^3 b2", 2, 32, 32, 32, 256, 256, True),
+        ("3D 64->128 64^3 b2", 2, 64, 64, 64, 64, 128, True),
+        ("3D 256->512 16^3 b2", 2, 16, 16, 16, 256, 512, True),
+        ("2D 64->128 256^2 b64", 64, 1, 256, 256, 64, 128, False),
+        ("2D 128->128 256^2 b64", 64, 1, 256, 256, 128, 128, False),
+        ("2D 256->128 256^2 b64", 64, 1, 256, 256, 256, 128, False),
+        ("2D 256->256 128^2 b64", 64, 1, 128, 128, 256, 256, False),
+        ("2D 512->256 128^2 b64", 64, 1, 128, 128, 512, 256, False),
+        ("2D 512->512 64^2 b64", 64, 1, 64, 64, 512, 512, False),
+        ("2D 1024->512 64^2 b64", 64, 1, 64, 64, 1024, 512, False),
+        ("2D 1024->1024 32^2 b64", 64, 1, 32, 32, 1024, 1024, False),
+    ]
+    for (name, n, d, h, w, cin, cout, is3d) in shapes:
+        x = CL(torch.randn((n, d, h, w, cin), device=dev).to(torch.bfloat16))
+        dy = CL(torch.randn((n, d, h, w, cout), device=dev).to(torch.bfloat16))
+        wshape = (cout, cin, 3, 3, 3) if is3d else (cout, cin, 3, 3)
+        k = (3, 3, 3) if is3d else (1, 3, 3)
+        flops = 2.0 * n * d * h * w * cin * cout * (27 if is3d else 9)
+        res = {}
+        for wide in (0, 1, 2, 3):
+            _lib.lib().b200_set_tuning(6, wide)
+            for _ in range(2):
+                dw = ops.conv_bwd_weight(x, dy, k, wshape, impl=1)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(5):
+                ops.conv_bwd_weight(x, dy, k, wshape, impl=1)
+            e1.record()
+            torch.cuda.synchronize()
+            res[wide] = (e0.elapsed_time(e1) / 5, dw)
+        _lib.lib().b200_set_tuning(6, 1)
+        err = relerr(res[1][1], res[0][1])
+        print(f"[PERF] wgrad {name}: narrow {res[0][0]:.3f} ms {flops / res[0][0] / 1e9:.0f} TF/s | "
+              f"wide {res[1][0]:.3f} ms {flops / res[1][0] / 1e9:.0f} TF/s | pairs-only {res[2][0]:.3f} ms "
+              f"centre-only {res[3][0]:.3f} ms | wide-vs-narrow rel {err[0]:.2e}",
+              flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--group", required=True)
@@ -309,6 +356,8 @@ def main():
         ok = group_deconv([2, 1])
     elif a.group == "perf":
         group_perf()
+    elif a.group == "wgrad_perf":
+        group_wgrad_perf()
         ok = True
     else:
         raise SystemExit("unknown group")
