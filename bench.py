@@ -196,7 +196,7 @@ class KernelProfiler:
             elif name in ("b200_conv_fwd", "b200_conv_bwd_data", "b200_convt2x2_fwd", "b200_convt2x2_bwd_data",
                           "b200_conv_fwd_stats", "b200_conv_bwd_data_stats", "b200_convt2x2_bwd_data_stats"):
                 key = "tc_gemm_kernel" if impl == 1 else "direct_gemm_kernel"
-            elif name in ("b200_conv_bwd_weight", "b200_convt2x2_bwd_weight"):
+            elif name in ("b200_conv_bwd_weight", "b200_conv_bwd_weight_bias", "b200_convt2x2_bwd_weight"):
                 key = "tc_wgrad_kernel" if impl == 1 else "direct_wgrad_kernel"
             elif name in ("b200_deconv3s2_fwd", "b200_deconv3s2_bwd_data"):
                 key = "tc_gemm_kernel(deconv)" if impl == 1 else "direct_gemm_kernel(deconv)"

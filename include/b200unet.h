@@ -85,6 +85,11 @@ int b200_conv_bwd_data_stats(const b200_conv_desc* desc, const void* dy, const v
 /* dw fp32 (c_out, c_in, kd, kh, kw) is ACCUMULATED into (caller zeroes it) */
 int b200_conv_bwd_weight(const b200_conv_desc* desc, const void* x, const void* dy, float* dw,
                          b200_stream_t stream);
+/* same, plus the conv bias gradient dbias[c_out] += sum_pos dy (fp32, ACCUMULATED; NULL = skip): the
+ * second half of aten::convolution_backward for nn.Conv2d(bias=True) layers.py:122-125, fused into
+ * the weight-gradient kernel (the dy tiles are already in shared memory) */
+int b200_conv_bwd_weight_bias(const b200_conv_desc* desc, const void* x, const void* dy, float* dw,
+                              float* dbias, b200_stream_t stream);
 
 /* ---- ConvTranspose2d(kernel 2, stride 2) -------------------------------------------------------
  * replaces nn.ConvTranspose2d  model/unet2d/layers.py:165. x: (n,1,h,w,c_in) -> y: (n,1,2h,2w,c_out) */

@@ -46,6 +46,7 @@ SIGNATURES = {
     "b200_conv_fwd": [_PC, _P, _P, _P, _P, _P],
     "b200_conv_bwd_data": [_PC, _P, _P, _P, _P, _P],
     "b200_conv_bwd_weight": [_PC, _P, _P, _P, _P],
+    "b200_conv_bwd_weight_bias": [_PC, _P, _P, _P, _P, _P],
     "b200_conv_fwd_stats": [_PC, _P, _P, _P, _P, _P, _P],
     "b200_conv_bwd_data_stats": [_PC, _P, _P, _P, _P, _I, _P, _I, _I, _P, _P],
     "b200_convt2x2_bwd_data_stats": [_PT, _P, _P, _P, _P, _I, _P, _P],

@@ -259,6 +259,11 @@ int b200_conv_bwd_data_stats(const b200_conv_desc* d, const void* dy, const void
 
 int b200_conv_bwd_weight(const b200_conv_desc* d, const void* x, const void* dy, float* dw,
                          b200_stream_t stream) {
+  return b200_conv_bwd_weight_bias(d, x, dy, dw, nullptr, stream);
+}
+
+int b200_conv_bwd_weight_bias(const b200_conv_desc* d, const void* x, const void* dy, float* dw,
+                              float* dbias, b200_stream_t stream) {
   int rc = check_conv(d);
   if (rc) return rc;
   TcWgradProblem p{};
@@ -270,6 +275,17 @@ int b200_conv_bwd_weight(const b200_conv_desc* d, const void* x, const void* dy,
   p.dw = dw;
   const int ntaps = d->kd * d->kh * d->kw;
   p.s_m = (long)d->c_in * ntaps; p.s_n = ntaps;
+  if (dbias) {
+    // fused into the halo weight-gradient kernel when that is the kernel that runs; otherwise one
+    // HBM-speed column-sum pass
+    if (d->impl != B200_IMPL_DIRECT && tc_wgrad_fuses_bias(p)) {
+      p.dbias = dbias;
+    } else {
+      b200_view v{const_cast<void*>(dy), d->out_ctot, d->out_coff};
+      rc = b200_bias_grad((int64_t)d->n * d->d * d->h * d->w, d->c_out, v, dbias, stream);
+      if (rc) return rc;
+    }
+  }
   return run_wgrad(p, d->impl, (cudaStream_t)stream);
 }
 

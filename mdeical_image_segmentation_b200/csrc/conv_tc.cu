@@ -1384,6 +1384,7 @@ struct WgradHaloArgs {
   int stages;
   float* dw;
   long s_co, s_ci;
+  float* dbias;                 // optional: dbias[co] += sum_pos dy[pos][co] (conv bias gradient), or NULL
 };
 
 // WIDE variant (C_out >= 128): an N = 64 MMA reads 4 KB of A + 2 KB of B from shared memory per 32
@@ -1411,20 +1412,6 @@ __global__ void __launch_bounds__(256, 1)
   constexpr int kGroupCols = WIDE ? 128 : 64;
   constexpr int kCoBlock = WIDE ? 128 : 64;
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (threadIdx.x == 0) {
-    tma_prefetch_desc(&tmX);
-    tma_prefetch_desc(&tmDY);
-    for (int s = 0; s < p.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    mbar_init(&tfull[0], 1);
-    fence_barrier_init();
-  }
-  if (warp == 2) tmem_alloc(tmem_slot, 512);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
   int w = blockIdx.x;
   const int cib = w % p.ciblk; w /= p.ciblk;
   const int cob = w % p.coblk; w /= p.coblk;
@@ -1433,6 +1420,24 @@ __global__ void __launch_bounds__(256, 1)
   const int mt_begin = split * p.tiles_per_split;
   int mt_end = mt_begin + p.tiles_per_split;
   if (mt_end > p.m_tiles) mt_end = p.m_tiles;
+  // Bias gradient = column sums of dy: the dy tiles pass through this CTA's shared memory anyway, so
+  // the (otherwise idle until the end) epilogue warps of ONE CTA per (co block, split) add them up —
+  // a stage is then released by the MMA commit plus one arrival per summing warp.
+  const bool do_bias = p.dbias != nullptr && cib == 0 && kdi == 0;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmX);
+    tma_prefetch_desc(&tmDY);
+    for (int s = 0; s < p.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], do_bias ? 5 : 1); }
+    mbar_init(&tfull[0], 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
     int stage = 0;
@@ -1485,6 +1490,40 @@ __global__ void __launch_bounds__(256, 1)
     if (mt_end <= mt_begin && elect_one()) umma_commit(&tfull[0]);
   } else if (warp >= 4) {
     const int q = warp - 4;
+    if (do_bias) {
+      // warp q sums positions [32 q, 32 q + 32) of every dy tile; lane owns channels (2 lane, 2 lane + 1)
+      // of each 64-channel box: one conflict-free 128-byte row read per position (128-byte swizzle)
+      float bs[kYBoxes][2];
+#pragma unroll
+      for (int b = 0; b < kYBoxes; ++b) bs[b][0] = bs[b][1] = 0.f;
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int mt = mt_begin; mt < mt_end; ++mt) {
+        mbar_wait(&full[stage], phase);
+        const uint8_t* sY = tiles + (size_t)stage * stage_bytes + x_bytes;
+#pragma unroll
+        for (int b = 0; b < kYBoxes; ++b) {
+#pragma unroll 8
+          for (int r = 0; r < 32; ++r) {
+            const int row = q * 32 + r;
+            const uint32_t v = *reinterpret_cast<const uint32_t*>(
+                sY + b * kABytes + row * 128 + ((((lane >> 2) ^ (row & 7))) << 4) + ((lane & 3) << 2));
+            const float2 f = unpack_bf16x2(v);
+            bs[b][0] += f.x;
+            bs[b][1] += f.y;
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[stage]);
+        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+      }
+#pragma unroll
+      for (int b = 0; b < kYBoxes; ++b) {
+        const int co = cob * kCoBlock + b * 64 + 2 * lane;
+        if (co < p.cout) atomicAdd(p.dbias + co, bs[b][0]);
+        if (co + 1 < p.cout) atomicAdd(p.dbias + co + 1, bs[b][1]);
+      }
+    }
     const int m = q * 32 + lane;           // 0..127: (tap half, ci)
     const int half = m >> 6;
     const int ci = cib * 64 + (m & 63);
@@ -1548,6 +1587,7 @@ static int tc_wgrad_halo(const TcWgradProblem& p, cudaStream_t stream) {
   a.tiles_per_split = (int)((a.m_tiles + want - 1) / want);
   a.splits = (a.m_tiles + a.tiles_per_split - 1) / a.tiles_per_split;
   a.dw = p.dw; a.s_co = p.s_m; a.s_ci = p.s_n;
+  a.dbias = p.dbias;
 
   CUtensorMap tmX, tmDY;
   {
@@ -1608,6 +1648,10 @@ bool tc_wgrad_supported(const TcWgradProblem& p) {
   if (p.mop.ctot % 8 || p.mop.coff % 8 || p.nop.ctot % 8 || p.nop.coff % 8) return false;
   if (p.tap_mode == TC_TAP_K2S2 && p.pd != 1) return false;
   return true;
+}
+
+bool tc_wgrad_fuses_bias(const TcWgradProblem& p) {
+  return tc_wgrad_supported(p) && wgrad_halo_eligible(p);
 }
 
 int tc_wgrad(const TcWgradProblem& p, cudaStream_t stream) {

@@ -66,8 +66,10 @@ struct TcWgradProblem {
   int pn, pd, ph, pw;     // position grid
   float* dw;
   long s_m, s_n;
+  float* dbias;           // optional (only when tc_wgrad_fuses_bias): dbias[m] += sum_pos Mop[pos][m]
 };
 int tc_wgrad(const TcWgradProblem& p, cudaStream_t stream);
 bool tc_wgrad_supported(const TcWgradProblem& p);
+bool tc_wgrad_fuses_bias(const TcWgradProblem& p);
 
 }  // namespace b200

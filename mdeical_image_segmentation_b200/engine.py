@@ -196,22 +196,28 @@ def single_conv_bwd(dy: CL, recs: list, grads: Grads, need_dx: bool = True, prem
         if kind == "conv":
             _, x_in, conv, wp_bwd, k, y_relu, zpad, mask_in = rec
             has_bias = conv.bias is not None and conv.bias.requires_grad
+            db, db_in_wgrad = None, False
             if y_relu is not None and not pm:
                 dy, db = ops.relu_bwd(dy, y_relu, has_bias, out=dy)
             elif has_bias and sums is not None:
                 db = sums[:, 0, :].sum(0).float()
-            else:
-                db = ops.bias_grad(dy) if has_bias else None
+            elif has_bias and conv.weight.requires_grad:
+                db_in_wgrad = True      # column sums of dy come out of the weight-gradient kernel
+            elif has_bias:
+                db = ops.bias_grad(dy)
             sums = None
-            if has_bias:
-                _acc(grads, conv.bias, db)
             if conv.weight.requires_grad:
                 wshape = list(conv.weight.shape)
                 wshape[1] += zpad
-                dw = ops.conv_bwd_weight(x_in, dy, k, tuple(wshape), impl=IMPL)
+                if db_in_wgrad:
+                    dw, db = ops.conv_bwd_weight(x_in, dy, k, tuple(wshape), impl=IMPL, bias_grad=True)
+                else:
+                    dw = ops.conv_bwd_weight(x_in, dy, k, tuple(wshape), impl=IMPL)
                 if zpad:
                     dw = dw[:, :conv.weight.shape[1]].contiguous()
                 _acc(grads, conv.weight, dw)
+            if has_bias:
+                _acc(grads, conv.bias, db)
             if last and not need_dx:
                 return None, False, None
             # the fused mask must have the layout of the (dense) dx the kernel writes

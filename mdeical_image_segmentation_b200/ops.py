@@ -187,10 +187,15 @@ def conv_bwd_data(dy: CL, wp_bwd: torch.Tensor, k, mask: Optional[CL] = None,
     return out, cs
 
 
-def conv_bwd_weight(x: CL, dy: CL, k, w_shape, impl: int = 0) -> torch.Tensor:
+def conv_bwd_weight(x: CL, dy: CL, k, w_shape, impl: int = 0, bias_grad: bool = False):
+    """dw (and, with ``bias_grad``, (dw, db) — the bias gradient rides in the same kernel)."""
     dw = torch.zeros(w_shape, dtype=torch.float32, device=x.device)
     d = ConvDesc(x.n, x.d, x.h, x.w, x.c, dy.c, k[0], k[1], k[2], x.ctot, x.coff,
                  dy.ctot, dy.coff, 0, impl)
+    if bias_grad:
+        db = torch.zeros(dy.c, dtype=torch.float32, device=x.device)
+        call("b200_conv_bwd_weight_bias", C.byref(d), _p(x.buf), _p(dy.buf), _p(dw), _p(db), _stream())
+        return dw, db
     call("b200_conv_bwd_weight", C.byref(d), _p(x.buf), _p(dy.buf), _p(dw), _stream())
     return dw
 
