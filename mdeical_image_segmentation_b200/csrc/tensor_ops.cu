@@ -140,6 +140,67 @@ __global__ void maxpool_bwd_kernel(int n, int d, int h, int w, int c, int pd, Vi
   }
 }
 
+// Even sizes, 8 channels per thread: the whole window (x, the skip gradient and dy) is fetched by
+// independent 16-byte loads BEFORE any use — up to 17 loads in flight per thread, which is what it takes
+// to cover HBM latency at 2048 threads per SM (the generic kernel above keeps one load in flight).
+template <int PD, bool ADD, bool MASK>
+__global__ void __launch_bounds__(256)
+    maxpool_bwd_fast_kernel(int n, int d, int h, int w, int c, View x, View dy, View add, View dx) {
+  constexpr int K = PD * 4;
+  const int od = d / PD, oh = h / 2, ow = w / 2, cv = c / 8;
+  const long total = (long)n * od * oh * ow * cv;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    long r = i;
+    const int ch = (int)(r % cv) * 8; r /= cv;
+    const int pw_ = (int)(r % ow); r /= ow;
+    const int ph_ = (int)(r % oh); r /= oh;
+    const int pdd = (int)(r % od); r /= od;
+    const int b = (int)r;
+    long pos[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      const int a = k >> 2, e = (k >> 1) & 1, g = k & 1;
+      pos[k] = (((long)b * d + pdd * PD + a) * h + ph_ * 2 + e) * w + pw_ * 2 + g;
+    }
+    uint4 xv[K], av[ADD ? K : 1];
+#pragma unroll
+    for (int k = 0; k < K; ++k) xv[k] = ldg_nc_v4(x.at(pos[k], ch));
+    if (ADD) {
+#pragma unroll
+      for (int k = 0; k < K; ++k) av[k] = ldg_nc_v4(add.at(pos[k], ch));
+    }
+    const uint4 gv = ldg_nc_v4(dy.at((((long)b * od + pdd) * oh + ph_) * ow + pw_, ch));
+    uint4 ov[K];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {       // 32-bit word q = channels (2q, 2q + 1)
+      const float2 gg = unpack_bf16x2((&gv.x)[q]);
+      float2 m = unpack_bf16x2((&xv[0].x)[q]);
+      int a0 = 0, a1 = 0;
+#pragma unroll
+      for (int k = 1; k < K; ++k) {
+        const float2 f = unpack_bf16x2((&xv[k].x)[q]);
+        if (f.x > m.x) { m.x = f.x; a0 = k; }
+        if (f.y > m.y) { m.y = f.y; a1 = k; }
+      }
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        float2 o = make_float2(0.f, 0.f);
+        if (ADD) o = unpack_bf16x2((&av[k].x)[q]);
+        o.x += (a0 == k) ? gg.x : 0.f;
+        o.y += (a1 == k) ? gg.y : 0.f;
+        if (MASK) {
+          const float2 f = unpack_bf16x2((&xv[k].x)[q]);
+          if (!(f.x > 0.f)) o.x = 0.f;
+          if (!(f.y > 0.f)) o.y = 0.f;
+        }
+        (&ov[k].x)[q] = pack_bf16x2(o.x, o.y);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < K; ++k) *reinterpret_cast<uint4*>(dx.at(pos[k], ch)) = ov[k];
+  }
+}
+
 // ------------------------------------------------------------------------------------ nearest
 __device__ __forceinline__ int nearest_src(int dst, float scale, int in) {
   const int s = (int)floorf(dst * scale);
@@ -817,6 +878,22 @@ int b200_maxpool2_bwd(int32_t n, int32_t d, int32_t h, int32_t w, int32_t c, int
   if ((long)n * d * h * w * c <= 0) return B200_OK;
   const long total = (long)n * ((d + pool_d - 1) / pool_d) * ((h + 1) / 2) * ((w + 1) / 2) * c;
   const bool v = vec8(c, x) && vec8(c, dy) && vec8(c, dx) && (!add.ptr || vec8(c, add));
+  if (v && d % pool_d == 0 && h % 2 == 0 && w % 2 == 0) {
+    const unsigned grid = GRID1D(total / 8);
+#define POOL_BWD_FAST(PD, ADD, MASK) \
+  maxpool_bwd_fast_kernel<PD, ADD, MASK><<<grid, 256, 0, (cudaStream_t)stream>>>(n, d, h, w, c, mk(x), mk(dy), mk(add), mk(dx))
+    const bool a = add.ptr != nullptr, m = mask_relu != 0;
+    if (pool_d == 2) {
+      if (a && m) POOL_BWD_FAST(2, true, true); else if (a) POOL_BWD_FAST(2, true, false);
+      else if (m) POOL_BWD_FAST(2, false, true); else POOL_BWD_FAST(2, false, false);
+    } else {
+      if (a && m) POOL_BWD_FAST(1, true, true); else if (a) POOL_BWD_FAST(1, true, false);
+      else if (m) POOL_BWD_FAST(1, false, true); else POOL_BWD_FAST(1, false, false);
+    }
+#undef POOL_BWD_FAST
+    B200_LAUNCH_CHECK();
+    return B200_OK;
+  }
   DISPATCH_V(v, maxpool_bwd_kernel, GRID1D(total / (v ? 8 : 1)), n, d, h, w, c, pool_d, mk(x), mk(dy),
              mk(add), mk(dx), mask_relu);
   return B200_OK;
