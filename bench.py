@@ -222,6 +222,8 @@ def run_b200(args, w):
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
     if world > 1:
+        # stdout carries exactly ONE JSON line: NCCL's version / debug banner goes to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=device)
     batch = args.batch or w["batch"]
     model, opt, step_fn = build_model(w, device)
