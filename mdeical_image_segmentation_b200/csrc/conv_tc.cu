@@ -1575,7 +1575,9 @@ static int tc_wgrad_halo(const TcWgradProblem& p, cudaStream_t stream) {
   a.kd = p.kd;
   a.cin = p.nop.c; a.cout = p.mop.c;
   // wide pays when the centre-tap GEMM can use N >= 128 (C_in >= 128) and there are enough tiles to split
-  const bool wide = g_wgrad_wide && a.cout >= 128 && a.cout % 64 == 0 && a.cin >= 128 && a.m_tiles >= 128;
+  // (measured per layer: profiles/r01_kernel_perf_wgrad_wide.log, r01_layers_cfg3p_wide_vs_narrow.txt)
+  const bool wide = g_wgrad_wide && a.cout >= 128 && a.cout % 64 == 0 && a.cin >= 128 &&
+                    (a.cin >= 256 ? a.m_tiles >= 128 : a.m_tiles >= 2048);
   const int co_block = wide ? 128 : 64;
   a.ciblk = (a.cin + 63) / 64; a.coblk = (a.cout + co_block - 1) / co_block;
   a.N = wide ? 128 : (a.cout >= 64 ? 64 : ((a.cout + 15) / 16) * 16);

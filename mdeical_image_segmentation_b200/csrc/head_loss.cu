@@ -178,6 +178,180 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// ------------------------------------------------------------------------------------ head, C_in = 64
+// The U-Nets of the path always feed the head 64 channels (f_maps[0]); these variants are built for HBM
+// bandwidth.  A warp owns 32 consecutive positions; 8 lanes share one position, each holding 8 channels
+// (one 16-byte load, so a warp-wide load is 512 contiguous bytes) and ALL 8 loads of the 32 positions are
+// issued before the first use.  Weights live in registers.
+//
+// Forward: every lane forms 8 passes x CO partial dot products; a halving exchange over the 8 lanes of a
+// position group (send the half the partner keeps, add the half received: 7 CO shuffles instead of 24 CO)
+// leaves lane `oct` with the CO finished logits of pass `oct`, i.e. of position 4 oct + sub — the warp's
+// store of one class is then 128 contiguous bytes.
+template <int CO>
+__global__ void __launch_bounds__(256)
+    head_fwd64_kernel(long spatial, View x, const float* __restrict__ w, const float* __restrict__ b,
+                      float* __restrict__ logits) {
+  const int lane = threadIdx.x & 31, oct = lane & 7, sub = lane >> 3;
+  const long bi = blockIdx.y;
+  float wr[CO][8], bias[CO];
+#pragma unroll
+  for (int j = 0; j < CO; ++j) {
+    bias[j] = b ? __ldg(b + j) : 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) wr[j][k] = __ldg(w + j * 64 + oct * 8 + k);
+  }
+  float* lbase = logits + bi * CO * spatial;
+  const long ngroups = (spatial + 31) >> 5;
+  const long wstride = (long)gridDim.x * (blockDim.x >> 5);
+  for (long grp = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); grp < ngroups; grp += wstride) {
+    const long base = grp << 5;
+    uint4 xv[8];
+#pragma unroll
+    for (int p = 0; p < 8; ++p) {
+      long sp = base + 4 * p + sub;
+      sp = sp < spatial ? sp : spatial - 1;
+      xv[p] = ldg_nc_v4(x.at(bi * spatial + sp, oct * 8));
+    }
+    float v[8 * CO];   // v[p * CO + j]
+#pragma unroll
+    for (int p = 0; p < 8; ++p) {
+      const float2 a0 = unpack_bf16x2(xv[p].x), a1 = unpack_bf16x2(xv[p].y), a2 = unpack_bf16x2(xv[p].z),
+                   a3 = unpack_bf16x2(xv[p].w);
+      const float f[8] = {a0.x, a0.y, a1.x, a1.y, a2.x, a2.y, a3.x, a3.y};
+#pragma unroll
+      for (int j = 0; j < CO; ++j) {
+        float acc = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc = fmaf(f[k], wr[j][k], acc);
+        v[p * CO + j] = acc;
+      }
+    }
+    // halving exchange on the pass index: bit 2 with lane^4, bit 1 with lane^2, bit 0 with lane^1
+    const bool b2 = oct & 4, b1 = oct & 2, b0 = oct & 1;
+    float v4[4 * CO], v2[2 * CO], v1[CO];
+#pragma unroll
+    for (int i = 0; i < 4 * CO; ++i)
+      v4[i] = (b2 ? v[4 * CO + i] : v[i]) + __shfl_xor_sync(0xffffffffu, b2 ? v[i] : v[4 * CO + i], 4);
+#pragma unroll
+    for (int i = 0; i < 2 * CO; ++i)
+      v2[i] = (b1 ? v4[2 * CO + i] : v4[i]) + __shfl_xor_sync(0xffffffffu, b1 ? v4[i] : v4[2 * CO + i], 2);
+#pragma unroll
+    for (int i = 0; i < CO; ++i)
+      v1[i] = (b0 ? v2[CO + i] : v2[i]) + __shfl_xor_sync(0xffffffffu, b0 ? v2[i] : v2[CO + i], 1);
+    const long sp = base + 4 * oct + sub;   // lane oct holds pass oct
+    if (sp < spatial) {
+#pragma unroll
+      for (int j = 0; j < CO; ++j) lbase[(long)j * spatial + sp] = v1[j] + bias[j];
+    }
+  }
+}
+
+// Backward: dx[pos][ci] = (x > 0) * sum_j g[j] w[j][ci]; dw[j][ci] += g[j] x[pos][ci]; db[j] += g[j].
+// dlogits are fetched coalesced (lane l = position base + l, one 128-byte load per class) and handed to
+// the 8 lanes of each position by shuffle; dw partials stay in registers for the whole kernel.
+template <int CO>
+__global__ void __launch_bounds__(256, 2)
+    head_bwd64_kernel(int n, long spatial, View x, const float* __restrict__ w,
+                      const float* __restrict__ dlogits, View dx, float* dw, float* db, int mask_relu) {
+  __shared__ float sred[8][CO][64];
+  __shared__ float sdb[8][CO];
+  __shared__ __align__(16) float swt[CO][64];   // weights: 32 more accumulator registers would spill
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, oct = lane & 7, sub = lane >> 3;
+  for (int i = threadIdx.x; i < CO * 64; i += blockDim.x) swt[i >> 6][i & 63] = __ldg(w + i);
+  __syncthreads();
+  float aw[CO][8], ab[CO];
+#pragma unroll
+  for (int j = 0; j < CO; ++j) {
+    ab[j] = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) aw[j][k] = 0.f;
+  }
+  // work item = (sample, 32-position group), flattened so that the grid is exactly the resident blocks
+  const long gps = (spatial + 31) >> 5, ngroups = gps * n;
+  const long wstride = (long)gridDim.x * (blockDim.x >> 5);
+  for (long item = (long)blockIdx.x * (blockDim.x >> 5) + warp; item < ngroups; item += wstride) {
+    const long bi = item / gps;
+    const long base = (item - bi * gps) << 5;
+    const float* gbase = dlogits + bi * CO * spatial;
+    float gl[CO];
+#pragma unroll
+    for (int j = 0; j < CO; ++j) gl[j] = base + lane < spatial ? __ldg(gbase + (long)j * spatial + base + lane) : 0.f;
+#pragma unroll
+    for (int j = 0; j < CO; ++j) ab[j] += gl[j];
+    // two half-groups of 4 passes: 4 x 16 B per lane in flight keeps CO = 4 within 128 registers
+#pragma unroll 1
+    for (int hp = 0; hp < 8; hp += 4) {
+      uint4 xv[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        long sp = base + 4 * (hp + q) + sub;
+        sp = sp < spatial ? sp : spatial - 1;
+        xv[q] = ldg_nc_v4(x.at(bi * spatial + sp, oct * 8));
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int p = hp + q;
+        const float2 a0 = unpack_bf16x2(xv[q].x), a1 = unpack_bf16x2(xv[q].y), a2 = unpack_bf16x2(xv[q].z),
+                     a3 = unpack_bf16x2(xv[q].w);
+        const float f[8] = {a0.x, a0.y, a1.x, a1.y, a2.x, a2.y, a3.x, a3.y};
+        float o[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int j = 0; j < CO; ++j) {
+          const float g = __shfl_sync(0xffffffffu, gl[j], 4 * p + sub);   // 0 beyond the tail
+          const float4 w0 = *reinterpret_cast<const float4*>(&swt[j][oct * 8]);
+          const float4 w1 = *reinterpret_cast<const float4*>(&swt[j][oct * 8 + 4]);
+          const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            aw[j][k] = fmaf(g, f[k], aw[j][k]);
+            o[k] = fmaf(g, wv[k], o[k]);
+          }
+        }
+        const long sp = base + 4 * p + sub;
+        if (dx.p && sp < spatial) {
+          if (mask_relu) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+              if (!(f[k] > 0.f)) o[k] = 0.f;
+          }
+          uint4 qv;
+          qv.x = pack_bf16x2(o[0], o[1]); qv.y = pack_bf16x2(o[2], o[3]);
+          qv.z = pack_bf16x2(o[4], o[5]); qv.w = pack_bf16x2(o[6], o[7]);
+          *reinterpret_cast<uint4*>(dx.at(bi * spatial + sp, oct * 8)) = qv;
+        }
+      }
+    }
+  }
+  // dw: sum the 4 position sub-groups of the warp, then the 8 warps of the block
+#pragma unroll
+  for (int j = 0; j < CO; ++j) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      float a = aw[j][k];
+      a += __shfl_xor_sync(0xffffffffu, a, 8);
+      a += __shfl_xor_sync(0xffffffffu, a, 16);
+      if (sub == 0) sred[warp][j][oct * 8 + k] = a;
+    }
+    const float t = warp_sum(ab[j]);
+    if (lane == 0) sdb[warp][j] = t;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < CO * 64; i += blockDim.x) {
+    const int j = i >> 6, c = i & 63;
+    float a = 0.f;
+#pragma unroll
+    for (int wi = 0; wi < 8; ++wi) a += sred[wi][j][c];
+    if (dw) atomicAdd(dw + j * 64 + c, a);
+  }
+  if (db && threadIdx.x < CO) {
+    float a = 0.f;
+#pragma unroll
+    for (int wi = 0; wi < 8; ++wi) a += sdb[wi][threadIdx.x];
+    atomicAdd(db + threadIdx.x, a);
+  }
+}
+
 // ------------------------------------------------------------------------------------ seg sums
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + __expf(-x)); }
 // numerically stable BCE-with-logits: max(x,0) - x*t + log(1 + exp(-|x|))
@@ -370,6 +544,13 @@ int b200_head_fwd(int32_t n, int64_t spatial, int32_t c_in, int32_t c_out, b200_
   const long cap = (148L * 16 + n - 1) / n;
   if (gx > cap) gx = cap;
   const dim3 grid((unsigned)(gx < 1 ? 1 : gx), (unsigned)n);
+  if (c_in == 64 && (c_out == 1 || c_out == 2 || c_out == 4 || c_out == 8) && ((uintptr_t)x.ptr % 16) == 0) {
+#define HEAD_FWD64(CO) head_fwd64_kernel<CO><<<grid, 256, 0, (cudaStream_t)stream>>>((long)spatial, mk(x), w, b, logits)
+    if (c_out == 1) HEAD_FWD64(1); else if (c_out == 2) HEAD_FWD64(2); else if (c_out == 4) HEAD_FWD64(4); else HEAD_FWD64(8);
+#undef HEAD_FWD64
+    B200_LAUNCH_CHECK();
+    return B200_OK;
+  }
 #define HEAD_FWD(CO) head_fwd_kernel<CO><<<grid, 256, smem, (cudaStream_t)stream>>>((long)spatial, c_in, c_out, mk(x), w, b, logits)
   if (c_out <= 1) HEAD_FWD(1); else if (c_out <= 2) HEAD_FWD(2); else if (c_out <= 4) HEAD_FWD(4); else HEAD_FWD(8);
 #undef HEAD_FWD
@@ -385,6 +566,17 @@ int b200_head_bwd(int32_t n, int64_t spatial, int32_t c_in, int32_t c_out, b200_
   if (smem > 48 * 1024 || c_out > HEAD_CO_LIMIT || c_in % 8 || x.ctot % 8 || x.coff % 8 ||
       (dx.ptr && (dx.ctot % 8 || dx.coff % 8)) || n > 65535)
     return B200_ERR_UNSUPPORTED;
+  if (c_in == 64 && (c_out == 1 || c_out == 2 || c_out == 4) && ((uintptr_t)x.ptr % 16) == 0 &&
+      (!dx.ptr || ((uintptr_t)dx.ptr % 16) == 0)) {
+    long gx = (total + 255) / 256;
+    if (gx > 148L * 2) gx = 148L * 2;              // 2 resident blocks per SM, dw partials flushed once per block
+    const dim3 grid64((unsigned)gx);
+#define HEAD_BWD64(CO) head_bwd64_kernel<CO><<<grid64, 256, 0, (cudaStream_t)stream>>>(n, (long)spatial, mk(x), w, dlogits, mk(dx), dw, db, mask_relu)
+    if (c_out == 1) HEAD_BWD64(1); else if (c_out == 2) HEAD_BWD64(2); else HEAD_BWD64(4);
+#undef HEAD_BWD64
+    B200_LAUNCH_CHECK();
+    return B200_OK;
+  }
   long per = (148L * 16 + n - 1) / n;              // blocks per sample
   long chunk = (spatial + per - 1) / per;
   chunk = (chunk + 63) / 64 * 64;                  // whole 64-position block passes

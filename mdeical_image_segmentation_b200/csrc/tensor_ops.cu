@@ -516,6 +516,35 @@ __global__ void __launch_bounds__(256, 4)
   const long base = (long)b * spatial;
   const long pbeg = (long)blockIdx.x * chunk;
   const long pend = pbeg + chunk < spatial ? pbeg + chunk : spatial;
+  if (V == 8) {
+    // 4 positions per trip, raw 16-byte loads all issued before the first use (4 x 16 B in flight per
+    // thread at 1024 threads per SM is what HBM latency needs), unpacked only when consumed
+    for (long p = pbeg + m.t_row; p < pend; p += 4L * m.rows) {
+      uint4 r[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const long q = p + (long)u * m.rows;
+        if (q < pend) r[u] = ldg_nc_v4(x.at(base + q, ch));
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const long q = p + (long)u * m.rows;
+        if (q < pend) {
+          uint4 o;
+#pragma unroll
+          for (int w = 0; w < 4; ++w) {
+            float2 f = unpack_bf16x2((&r[u].x)[w]);
+            f.x = fmaf(f.x, sc[2 * w], sh[2 * w]);
+            f.y = fmaf(f.y, sc[2 * w + 1], sh[2 * w + 1]);
+            if (relu) { f.x = fmaxf(f.x, 0.f); f.y = fmaxf(f.y, 0.f); }
+            (&o.x)[w] = pack_bf16x2(f.x, f.y);
+          }
+          *reinterpret_cast<uint4*>(y.at(base + q, ch)) = o;
+        }
+      }
+    }
+    return;
+  }
   for (long p = pbeg + m.t_row; p < pend; p += 2L * m.rows) {
     float f[2][V];
 #pragma unroll

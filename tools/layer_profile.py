@@ -11,6 +11,10 @@ import bench  # noqa: E402
 from mdeical_image_segmentation_b200 import _lib  # noqa: E402
 
 wl = sys.argv[1] if len(sys.argv) > 1 else "cfg3"
+for kv in os.environ.get("B200_TUNING", "").split(","):   # e.g. B200_TUNING=6:0 (tuning key:value pairs)
+    if kv:
+        k, v = kv.split(":")
+        _lib.lib().b200_set_tuning(int(k), int(v))
 w = bench.WORKLOADS[wl]
 dev = torch.device("cuda", 0)
 model, opt, step_fn = bench.build_model(w, dev)
