@@ -404,20 +404,38 @@ def run_sweep(args):
             torch.cuda.synchronize()
             lat = sorted(e0.elapsed_time(e1) for e0, e1 in evs)
             mean = sum(lat) / len(lat)
+            # the same forward captured once as a CUDA graph (one launch per request)
+            g = B.GraphedInference(net, x)
+            for _ in range(3):
+                g(x)
+            torch.cuda.synchronize()
+            gl = []
+            for _ in range(iters):
+                t0 = time.perf_counter()
+                g(x)
+                torch.cuda.synchronize()
+                gl.append((time.perf_counter() - t0) * 1e3)
+            gl.sort()
+            del g
+            out = net(x)
+            oh = torch.empty(out.shape, dtype=out.dtype).pin_memory()
             t0 = time.perf_counter()
             for _ in range(3):
                 out = net(xh.to(device, non_blocking=True))
-                out.cpu()
+                oh.copy_(out, non_blocking=True)
+                torch.cuda.synchronize()
             e2e_ms = (time.perf_counter() - t0) / 3 * 1e3
             rows.append({"model": "UNet(1,1)" if kind == "2d" else "UNet3D(1,1) gcr", "batch": batch,
                          "size": "x".join(map(str, size)), "p50_ms": round(lat[len(lat) // 2], 3),
                          "p99_ms": round(lat[min(len(lat) - 1, int(0.99 * len(lat)))], 3),
                          "per_s": round(batch / (mean / 1e3), 2),
+                         "graph_p50_ms": round(gl[len(gl) // 2], 3),
+                         "graph_p99_ms": round(gl[min(len(gl) - 1, int(0.99 * len(gl)))], 3),
                          "tflops": round(tf * batch / (mean / 1e3), 1),
                          "frac_of_sustained_peak": round(tf * batch / (mean / 1e3) / pk["tf_sustained"], 4),
                          "e2e_ms": round(e2e_ms, 3), "e2e_per_s": round(batch / (e2e_ms / 1e3), 2),
                          "h2d_bytes": xh.numel() * 4, "d2h_bytes": out.numel() * 4})
-            del x, xh, out
+            del x, xh, out, oh
             torch.cuda.empty_cache()
     head = next(r for r in rows if r["size"] == "128x128x128" and r["batch"] == 2)
     print(json.dumps({

@@ -3,6 +3,7 @@ a-green-hand-jack/mdeical_image_segmentation: drop-in ``nn.Module`` classes, los
 arithmetic runs in hand-written CUDA (tcgen05/TMEM/TMA implicit-GEMM convolutions + HBM-bound fused
 kernels) behind a C ABI (``include/b200unet.h``).  There is no CPU / PyTorch-eager fallback."""
 from . import _lib, metrics  # noqa: F401
+from .graph import GraphedInference
 from .losses import (BCEDiceLoss, BCEWithLogitsLoss, CrossEntropyLoss, DiceLoss, F1Loss, IoULoss,
                      SegmentationLoss, compute_per_channel_dice, flatten, get_loss_criterion)
 from .unet2d import (CropAndConcat, DoubleConvolution, DownSample, UNet, UpSample, unetConv2)

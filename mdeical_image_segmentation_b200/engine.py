@@ -14,6 +14,8 @@ backward replays the tape in reverse.  That gives the executor what autograd can
 """
 from __future__ import annotations
 
+import os
+
 from typing import Dict, List, Optional, Tuple
 
 import torch
@@ -25,6 +27,7 @@ from .ops import CL
 Grads = Dict[nn.Parameter, torch.Tensor]
 IMPL = 0  # B200_IMPL_AUTO; tests flip it to cross-check the tcgen05 and direct kernels
 FUSE_SUM_MIN_K = 2304  # fuse a bias-gradient column sum into a dgrad epilogue only if taps * C_out >= this
+FUSE_DOT = os.environ.get("B200_FUSE_DOT", "1") != "0"   # A/B knob: norm-backward sums in the dgrad epilogue
 
 
 _REDUCER = None  # parallel.GradReducer of the network whose backward is running (data parallel)
@@ -172,6 +175,8 @@ def _consumer_plan(consumer, fuse_mask: bool):
         conv = consumer[2]
         return bool(conv.bias is not None and conv.bias.requires_grad), None
     if kind in ("gn", "bn"):     # (sum g, sum g * x) with x = the norm's input
+        if not FUSE_DOT:
+            return False, None
         if kind == "bn" and not consumer[7]:
             return False, None   # frozen statistics: no batch terms, the reduction path handles dgamma
         return True, consumer[1]

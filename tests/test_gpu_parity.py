@@ -304,6 +304,31 @@ def test_tcgen05_and_direct_kernels_agree(B):
         assert rel_l2(w1.cpu(), w2.cpu()) < 1e-4
 
 
+def test_wide_weight_gradient_and_fused_bias_gradient(B):
+    """Shapes that take the N = 128 four-tap-pair weight-gradient kernel + centre-tap GEMM (C_in >= 256,
+    or C_in = 128 on a large plane), including a ragged plane and a channel slice of a wider buffer,
+    against the CUDA-core kernel; and the bias gradient that rides in the same kernel against the
+    stand-alone column-sum pass."""
+    from mdeical_image_segmentation_b200 import ops
+    from mdeical_image_segmentation_b200.ops import CL
+    g = torch.Generator().manual_seed(11)
+    cases = [(4, 1, 64, 64, 256, 128, 0), (2, 4, 24, 40, 256, 256, 0), (3, 1, 50, 44, 320, 192, 64),
+             (16, 1, 128, 128, 128, 128, 0), (2, 1, 32, 24, 64, 64, 0), (1, 3, 16, 16, 32, 48, 0)]
+    for (n, d, h, w, cin, cout, extra) in cases:
+        xb = torch.randn((n, d, h, w, cin + extra), generator=g).to(torch.bfloat16).cuda()
+        x = CL(xb, cin, extra)                          # channels [extra, extra + cin) of a wider buffer
+        dy = CL(torch.randn((n, d, h, w, cout), generator=g).to(torch.bfloat16).cuda())
+        ks = (3, 3, 3) if d > 1 else (3, 3)
+        k = (3, 3, 3) if d > 1 else (1, 3, 3)
+        wshape = (cout, cin) + ks
+        w1, b1 = ops.conv_bwd_weight(x, dy, k, wshape, impl=1, bias_grad=True)
+        w2 = ops.conv_bwd_weight(x, dy, k, wshape, impl=2)
+        assert rel_l2(w1.cpu(), w2.cpu()) < 2e-4, (n, d, h, w, cin, cout)
+        b2 = ops.bias_grad(dy)
+        bref = dy.dense().float().sum(dim=(0, 1, 2, 3))
+        assert rel_l2(b1.cpu(), bref.cpu()) < 1e-4 and rel_l2(b2.cpu(), bref.cpu()) < 1e-4
+
+
 def test_maxpool_tie_routing_and_odd_sizes(B):
     """Post-ReLU all-zero windows: the gradient goes to the FIRST element in (d,h,w) order, as ATen."""
     from mdeical_image_segmentation_b200 import ops
