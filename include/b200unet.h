@@ -181,6 +181,12 @@ int b200_relu_bwd(int64_t npos, int32_t c, b200_view dy, b200_view a, b200_view 
                   b200_stream_t stream);
 /* db[c] += sum_pos dy */
 int b200_bias_grad(int64_t npos, int32_t c, b200_view dy, float* db, b200_stream_t stream);
+/* First convolution of a network (1-4 input channels; nn.Conv3d buildingblocks.py:63-70 with
+ * in_channels = the volume's): taps concatenated along K — a[pos][tap * c_in + ci] bf16 (n*d*h*w, kp),
+ * zero padding 1 (none in depth when kd = 1), zero beyond kd*9*c_in; kp a multiple of 8.  The weight
+ * gradient of that layer is then b200_conv_bwd_weight of a 1x1x1 convolution with c_in = kp. */
+int b200_im2col3(int32_t n, int32_t d, int32_t h, int32_t w, int32_t c_in, int32_t kd, int32_t kp,
+                 b200_view x, void* a, b200_stream_t stream);
 /* layout / precision boundary: fp32 NC(spatial) <-> bf16 channels-last */
 int b200_nchw_f32_to_cl_bf16(int32_t n, int32_t c, int64_t spatial, const float* src, b200_view dst,
                              b200_stream_t stream);

@@ -472,6 +472,49 @@ __global__ void cl_to_nchw_kernel(int n, int c, long spatial, View src, float* d
   }
 }
 
+// ------------------------------------------------------------------------------------ narrow-input im2col
+// The network's first convolution has 1-4 input channels.  As an implicit GEMM its weight gradient issues
+// one K = 16 MMA per tap with 12-15 of the 16 K lanes zero (and M = 2 taps x 64 rows with 1-4 real ones);
+// with the taps concatenated along K instead (a[pos][tap * c_in + ci], K' = taps * c_in rounded up to
+// 16 <= 64) it is one short reduction GEMM that streams a and dy at HBM speed.
+// One thread per position: the kd x 3 x 3 neighbourhood is gathered once (taps and channels are
+// compile-time, so there is no per-element index arithmetic) and the K' row leaves as 16-byte stores.
+template <int KD, int CIN>
+__global__ void __launch_bounds__(256)
+    im2col3_kernel(int n, int d, int h, int w, int kp, View x, bf16* __restrict__ a) {
+  constexpr int NT = KD * 9, KR = NT * CIN, KV = (KR + 7) / 8;   // 16-byte vectors that hold real taps
+  const int kv = kp / 8;
+  const long total = (long)n * d * h * w;
+  for (long pos = (long)blockIdx.x * blockDim.x + threadIdx.x; pos < total; pos += (long)gridDim.x * blockDim.x) {
+    long r = pos;
+    const int xw = (int)(r % w); r /= w;
+    const int xh = (int)(r % h); r /= h;
+    const int xd = (int)(r % d); r /= d;
+    const long b = r;
+    unsigned short e[KV * 8];
+#pragma unroll
+    for (int k = KR; k < KV * 8; ++k) e[k] = 0;
+#pragma unroll
+    for (int tap = 0; tap < NT; ++tap) {
+      const int kwi = tap % 3, khi = (tap / 3) % 3, kdi = tap / 9;
+      const int zd = xd + kdi - (KD >> 1), zh = xh + khi - 1, zw = xw + kwi - 1;
+      const bool ok = zd >= 0 && zd < d && zh >= 0 && zh < h && zw >= 0 && zw < w;
+      const unsigned short* src =
+          reinterpret_cast<const unsigned short*>(x.at(ok ? ((b * d + zd) * h + zh) * w + zw : pos, 0));
+#pragma unroll
+      for (int ci = 0; ci < CIN; ++ci) e[tap * CIN + ci] = ok ? src[ci] : (unsigned short)0;
+    }
+    uint4* dst = reinterpret_cast<uint4*>(a + pos * kp);
+#pragma unroll
+    for (int v = 0; v < KV; ++v) {
+      uint4 o;
+      o.x = e[8 * v] | ((uint32_t)e[8 * v + 1] << 16); o.y = e[8 * v + 2] | ((uint32_t)e[8 * v + 3] << 16);
+      o.z = e[8 * v + 4] | ((uint32_t)e[8 * v + 5] << 16); o.w = e[8 * v + 6] | ((uint32_t)e[8 * v + 7] << 16);
+      dst[v] = o;
+    }
+    for (int v = KV; v < kv; ++v) dst[v] = make_uint4(0, 0, 0, 0);
+  }
+}
 // ------------------------------------------------------------------------------------ affine streams
 // y = relu?(x * sc[ch] + sh[ch]) and dx = a[ch] * g + b[ch] * x + c0[ch] (g = dy, masked by y > 0):
 // every normalisation forward / backward "apply" pass of the path has this form once the per-channel
@@ -1015,6 +1058,22 @@ int b200_nchw_f32_to_cl_bf16(int32_t n, int32_t c, int64_t spatial, const float*
   const long total = (long)n * spatial;
   if (total <= 0) return B200_OK;
   nchw_to_cl_kernel<<<GRID1D(total), 256, 0, (cudaStream_t)stream>>>(n, c, (long)spatial, src, mk(dst));
+  B200_LAUNCH_CHECK();
+  return B200_OK;
+}
+int b200_im2col3(int32_t n, int32_t d, int32_t h, int32_t w, int32_t c_in, int32_t kd, int32_t kp,
+                 b200_view x, void* a, b200_stream_t stream) {
+  if ((kd != 1 && kd != 3) || c_in <= 0 || kp % 8 || kp < kd * 9 * c_in || ((uintptr_t)a % 16)) return B200_ERR_BAD_ARG;
+  const long total = (long)n * d * h * w;
+  if (total <= 0) return B200_OK;
+  if (c_in > 4 || kd * 9 * c_in > 64) return B200_ERR_UNSUPPORTED;
+#define IM2COL(KD, CIN) im2col3_kernel<KD, CIN><<<GRID1D(total), 256, 0, (cudaStream_t)stream>>>(n, d, h, w, kp, mk(x), (bf16*)a)
+  if (kd == 1) {
+    if (c_in == 1) IM2COL(1, 1); else if (c_in == 2) IM2COL(1, 2); else if (c_in == 3) IM2COL(1, 3); else IM2COL(1, 4);
+  } else {
+    if (c_in == 1) IM2COL(3, 1); else if (c_in == 2) IM2COL(3, 2); else return B200_ERR_UNSUPPORTED;
+  }
+#undef IM2COL
   B200_LAUNCH_CHECK();
   return B200_OK;
 }

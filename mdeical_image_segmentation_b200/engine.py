@@ -84,6 +84,27 @@ def _bn_moments(bn: nn.Module, x: CL, training: bool, in_sums: Optional[torch.Te
     return mean, rstd
 
 
+def _im2col_kp(x_real: CL, conv: nn.Module) -> int:
+    """K' = taps * c_in rounded up to 16 when the first layer's WEIGHT GRADIENT should run as one short-K
+    GEMM over an im2col of the narrow input, else 0.  Measured (tools/first_layer_probe.py,
+    profiles/r01_first_layer_probe.log): 3D 1->32 @128^3 0.72 -> 0.20 + 0.18 ms; the forward / data
+    gradient lose (a 128-row tile with two MMAs is bound by the ~1700-cycle accumulator hand-shake, which
+    the halo kernel amortises over 512-position super-tiles) and so does 2D, where the im2col write costs
+    what the weight gradient saves."""
+    w = conv.weight
+    if w.dim() != 5 or tuple(w.shape[2:]) != (3, 3, 3) or x_real.coff != 0 or w.shape[1] != x_real.c:
+        return 0
+    kp = (27 * x_real.c + 15) // 16 * 16
+    return kp if kp <= 64 else 0
+
+
+def _im2col_weight_grad(dw2: torch.Tensor, w: torch.Tensor) -> torch.Tensor:
+    """(c_out, kp) with k' = tap * c_in + ci  ->  the conv's own (c_out, c_in, kd, kh, kw) layout."""
+    co, ci = w.shape[0], w.shape[1]
+    taps = w[0, 0].numel()
+    return dw2.reshape(co, -1)[:, :taps * ci].reshape(co, taps, ci).permute(0, 2, 1).reshape(w.shape).contiguous()
+
+
 def single_conv_fwd(x: CL, spec: LayerSpec, training: bool, tape: Optional[list],
                     out: Optional[CL] = None, in_relu: bool = False,
                     in_sums: Optional[torch.Tensor] = None, want_sums: bool = False):
@@ -211,7 +232,16 @@ def single_conv_bwd(dy: CL, recs: list, grads: Grads, need_dx: bool = True, prem
             elif has_bias:
                 db = ops.bias_grad(dy)
             sums = None
-            if conv.weight.requires_grad:
+            kp = _im2col_kp(CL(x_in.buf, x_in.c - zpad, x_in.coff, zpad), conv) if zpad else 0
+            if conv.weight.requires_grad and kp:
+                a = ops.im2col(CL(x_in.buf, x_in.c - zpad, x_in.coff, zpad), 3, kp)
+                shape2 = (conv.weight.shape[0], kp, 1, 1, 1)
+                if db_in_wgrad:
+                    dw2, db = ops.conv_bwd_weight(a, dy, (1, 1, 1), shape2, impl=IMPL, bias_grad=True)
+                else:
+                    dw2 = ops.conv_bwd_weight(a, dy, (1, 1, 1), shape2, impl=IMPL)
+                _acc(grads, conv.weight, _im2col_weight_grad(dw2, conv.weight))
+            elif conv.weight.requires_grad:
                 wshape = list(conv.weight.shape)
                 wshape[1] += zpad
                 if db_in_wgrad:

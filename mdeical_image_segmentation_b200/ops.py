@@ -387,6 +387,13 @@ def from_nchw(x: torch.Tensor, out: Optional[CL] = None, pad: bool = False) -> C
     return out
 
 
+def im2col(x: CL, kd: int, kp: int) -> CL:
+    """Narrow first-layer input -> (n, d, h, w, kp) with the 3x3(x3) taps concatenated along channels."""
+    a = CL.empty(x.n, x.d, x.h, x.w, kp, x.device)
+    call("b200_im2col3", x.n, x.d, x.h, x.w, x.c, kd, kp, x.view(), _p(a.buf), _stream())
+    return a
+
+
 def to_nchw(x: CL, is3d: bool) -> torch.Tensor:
     shape = (x.n, x.c, x.d, x.h, x.w) if is3d else (x.n, x.c, x.h, x.w)
     out = torch.empty(shape, dtype=torch.float32, device=x.device)
