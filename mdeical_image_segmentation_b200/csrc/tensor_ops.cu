@@ -363,6 +363,59 @@ __global__ void planes_resize_bwd_kernel(int n, int d, int h, int w, int c, int 
   }
 }
 
+// Exact 2x case (od, oh, ow) = 2 (d, h, w) of the 3D backward above: with src = max(dst - 1, 0) per axis a
+// plane element has ONE child (dst = src + 1) unless src = 0 (children 0 and 1), so an interior thread
+// moves the 8 parity classes of one (md, mh, mw) with 8 independent 16-byte loads in flight and no index
+// search; only the three low faces take the summing path.
+__global__ void __launch_bounds__(256)
+    planes_resize_bwd2x_kernel(int n, int d, int h, int w, int c, View dy, View dyp) {
+  const int cv = c / 8;
+  const int od = 2 * d, oh = 2 * h, ow = 2 * w;
+  const long total = (long)n * d * h * w * cv;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    long r = i;
+    const int ch = (int)(r % cv) * 8; r /= cv;
+    const int mw = (int)(r % w); r /= w;
+    const int mh = (int)(r % h); r /= h;
+    const int md = (int)(r % d); r /= d;
+    const long b = r;
+    const long plane_pos = ((b * d + md) * h + mh) * w + mw;
+    const long cls_stride = (long)n * d * h * w;
+    if (md > 0 && mh > 0 && mw > 0) {
+      uint4 v[8];
+#pragma unroll
+      for (int cls = 0; cls < 8; ++cls) {
+        const int a = 2 * md + (cls >> 2), e = 2 * mh + ((cls >> 1) & 1), g = 2 * mw + (cls & 1);
+        v[cls] = make_uint4(0, 0, 0, 0);
+        if (a < od - 1 && e < oh - 1 && g < ow - 1)
+          v[cls] = ldg_nc_v4(dy.at(((b * od + a + 1) * oh + e + 1) * ow + g + 1, ch));
+      }
+#pragma unroll
+      for (int cls = 0; cls < 8; ++cls)
+        *reinterpret_cast<uint4*>(dyp.at(cls * cls_stride + plane_pos, ch)) = v[cls];
+    } else {
+      for (int cls = 0; cls < 8; ++cls) {
+        const int a = 2 * md + (cls >> 2), e = 2 * mh + ((cls >> 1) & 1), g = 2 * mw + (cls & 1);
+        float acc[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+        if (a < od - 1 && e < oh - 1 && g < ow - 1) {
+          const int d0 = a ? a + 1 : 0, h0 = e ? e + 1 : 0, w0 = g ? g + 1 : 0;
+          for (int q = d0; q <= a + 1; ++q)
+            for (int t = h0; t <= e + 1; ++t)
+              for (int u = w0; u <= g + 1; ++u) {
+                float f[8];
+                Vec<8>::load(dy.at(((b * od + q) * oh + t) * ow + u, ch), f);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[j] += f[j];
+              }
+        }
+        Vec<8>::store(dyp.at(cls * cls_stride + plane_pos, ch), acc);
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------ copies
 template <int V>
 __global__ void copy_kernel(long npos, int c, View src, View dst) {
@@ -1012,6 +1065,11 @@ int b200_deconv_planes_resize_bwd(int32_t n, int32_t d, int32_t h, int32_t w, in
   const long total = (long)(kd == 1 ? 4 : 8) * n * d * h * w * c;
   if (total <= 0) return B200_OK;
   const bool v = vec8(c, dy) && vec8(c, dyp);
+  if (v && kd == 3 && od == 2 * d && oh == 2 * h && ow == 2 * w) {
+    planes_resize_bwd2x_kernel<<<GRID1D(total / 64), 256, 0, (cudaStream_t)stream>>>(n, d, h, w, c, mk(dy), mk(dyp));
+    B200_LAUNCH_CHECK();
+    return B200_OK;
+  }
   DISPATCH_V(v, planes_resize_bwd_kernel, GRID1D(total / (v ? 8 : 1)), n, d, h, w, c, kd, od, oh, ow,
              mk(dy), mk(dyp));
   return B200_OK;

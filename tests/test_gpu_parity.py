@@ -361,6 +361,25 @@ def test_nearest_resize_index_map(B):
         assert torch.equal(dx, xr.grad)
 
 
+def test_deconv_plane_resize_backward_is_the_adjoint_of_forward(B):
+    """Parity planes of ConvTranspose3d(k3,s2,p1) <-> nearest resize to the skip's size: the backward
+    (exact-2x kernel with 8 loads in flight, and the generic kernel on a ragged size) must be the exact
+    transpose of the forward gather — checked with small integers, so the identity is bit-exact."""
+    from mdeical_image_segmentation_b200 import ops
+    from mdeical_image_segmentation_b200.ops import CL
+    g = torch.Generator().manual_seed(5)
+    for (n, d, h, w, c, size) in [(2, 4, 6, 8, 16, (8, 12, 16)), (1, 3, 5, 4, 8, (7, 10, 9)),
+                                  (1, 16, 16, 16, 64, (32, 32, 32))]:
+        yp = CL(torch.randint(-3, 4, (8 * n, d, h, w, c), generator=g).to(torch.bfloat16).cuda())
+        gy = CL(torch.randint(-3, 4, (n,) + size + (c,), generator=g).to(torch.bfloat16).cuda())
+        y = ops.deconv_resize_fwd(yp, n, 3, size)
+        dyp = ops.deconv_resize_bwd(gy, (n, d, h, w), 3)
+        lhs = (y.dense().double() * gy.dense().double()).sum().item()
+        rhs = (yp.dense().double() * dyp.dense().double()).sum().item()
+        assert lhs == rhs, (n, d, h, w, size, lhs, rhs)
+        assert dyp.dense().double().sum().item() == gy.dense().double().sum().item()   # every child lands once
+
+
 def test_size_independent_properties_at_headline_size(B):
     """Linearity of the conv kernels and loss identities at a BASELINE-scale layer (128^3, 64 ch)."""
     from mdeical_image_segmentation_b200 import ops
