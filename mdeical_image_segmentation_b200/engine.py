@@ -27,6 +27,7 @@ from .ops import CL
 Grads = Dict[nn.Parameter, torch.Tensor]
 IMPL = 0  # B200_IMPL_AUTO; tests flip it to cross-check the tcgen05 and direct kernels
 FUSE_SUM_MIN_K = 2304  # fuse a bias-gradient column sum into a dgrad epilogue only if taps * C_out >= this
+FUSE_BIAS_IN_DGRAD = os.environ.get("B200_FUSE_BIAS_IN_DGRAD", "0") != "0"   # A/B knob (superseded by wgrad fusion)
 FUSE_DOT = os.environ.get("B200_FUSE_DOT", "1") != "0"   # A/B knob: norm-backward sums in the dgrad epilogue
 
 
@@ -192,9 +193,9 @@ def _consumer_plan(consumer, fuse_mask: bool):
     relu_out = consumer[5] if kind in ("conv", "gn") else consumer[6] if kind == "bn" else None
     if relu_out is not None and not fuse_mask:
         return False, None       # the consumer's ReLU backward is not folded into this gradient
-    if kind == "conv":           # bias gradient = per-channel sum of the (masked) gradient
+    if kind == "conv":           # its bias gradient rides in its own weight-gradient kernel (fused there)
         conv = consumer[2]
-        return bool(conv.bias is not None and conv.bias.requires_grad), None
+        return bool(FUSE_BIAS_IN_DGRAD and conv.bias is not None and conv.bias.requires_grad), None
     if kind in ("gn", "bn"):     # (sum g, sum g * x) with x = the norm's input
         if not FUSE_DOT:
             return False, None
