@@ -57,6 +57,29 @@ SWEEP = [("2d", 1, (256, 256), 0.0962), ("2d", 16, (256, 256), 0.0962), ("2d", 6
          ("3d", 1, (192, 192, 192), 12.78)]
 
 
+_JSON_FD = None
+
+
+def _claim_stdout():
+    """stdout carries exactly ONE JSON line: anything a library prints there (NCCL's version banner comes
+    through printf from inside init) is sent to stderr by pointing fd 1 at fd 2; the JSON line goes to a
+    duplicate of the original fd 1."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(obj) -> None:
+    line = (json.dumps(obj) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(line.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, line)
+
+
 def peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -222,8 +245,6 @@ def run_b200(args, w):
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
     if world > 1:
-        # stdout carries exactly ONE JSON line: NCCL's version / debug banner goes to stderr
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=device)
     batch = args.batch or w["batch"]
     model, opt, step_fn = build_model(w, device)
@@ -362,7 +383,7 @@ def run_b200(args, w):
             "roofline": roofline, "cpu_baseline": cpu, "breakdown": breakdown,
             "final_loss": final_loss,
         }
-        print(json.dumps(out), flush=True)
+        emit(out)
     if world > 1:
         dist.destroy_process_group()
 
@@ -439,7 +460,7 @@ def run_sweep(args):
             del x, xh, out, oh
             torch.cuda.empty_cache()
     head = next(r for r in rows if r["size"] == "128x128x128" and r["batch"] == 2)
-    print(json.dumps({
+    emit({
         "metric": "inference vols/s", "value": head["per_s"], "unit": "vols/s", "n_gpus": 1, "steps": iters,
         "warmup": max(args.warmup, 3), "ms_per_step": head["p50_ms"], "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
@@ -449,7 +470,7 @@ def run_sweep(args):
         "e2e": {"value": head["e2e_per_s"], "unit": "vols/s", "h2d_bytes_per_step": head["h2d_bytes"],
                 "d2h_bytes_per_step": head["d2h_bytes"]},
         "gpu_launches": _lib.launch_count, "clocks": clocks.summary(), "roofline": None, "cpu_baseline": None,
-        "sweep": rows}), flush=True)
+        "sweep": rows})
 
 
 # --------------------------------------------------------------------------------------- CPU arm
@@ -512,7 +533,7 @@ def run_reference(args, w):
            "config": {"workload": f"{args.workload}: {w['desc']}", "note": "CPU oracle port of the reference path"},
            "cpu_baseline": cpu, "gpu_launches": 0,
            "e2e": {"value": cpu["value"], "unit": w["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(out), flush=True)
+    emit(out)
 
 
 def main():
@@ -528,8 +549,9 @@ def main():
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.workload == "cfg5":
+        _claim_stdout()
         if args.impl == "reference":
-            print(json.dumps({"impl": "reference", "unavailable": "cfg5 is a sweep; use cfg2/cfg3 for the CPU arm"}))
+            emit({"impl": "reference", "unavailable": "cfg5 is a sweep; use cfg2/cfg3 for the CPU arm"})
             return
         return run_sweep(args)
     w = WORKLOADS[args.workload]
@@ -538,6 +560,7 @@ def main():
         os.execvp(sys.executable, [sys.executable, "-m", "torch.distributed.run", "--nnodes=1",
                                    f"--nproc-per-node={args.gpus}", "--master-addr", "127.0.0.1",
                                    "--master-port", "29531", os.path.abspath(__file__)] + sys.argv[1:])
+    _claim_stdout()
     if args.impl == "reference":
         run_reference(args, w)
     else:
