@@ -33,6 +33,66 @@ FUSE_DOT = os.environ.get("B200_FUSE_DOT", "1") != "0"   # A/B knob: norm-backwa
 
 _REDUCER = None  # parallel.GradReducer of the network whose backward is running (data parallel)
 
+# Weight gradients are off the critical path of backward (only the optimizer / all-reduce consume them),
+# so inside a whole-network backward they are enqueued on a side stream: the HBM-bound kernels of the main
+# chain (norm backward, pool / up-sampling backward) then run next to a tensor-core-bound weight-gradient
+# kernel instead of after it, and each stream fills the other's tail waves.
+WGRAD_STREAM = os.environ.get("B200_WGRAD_STREAM", "1") != "0"
+_SIDE = {}          # device index -> side stream
+_side_active = None  # side stream of the backward that is running, or None
+
+
+class _OnSide:
+    """Runs the body on the side stream, ordered after everything enqueued so far on the current stream;
+    ``keep`` are tensors the body reads: the caching allocator must not recycle them early."""
+
+    def __init__(self, *keep):
+        self.keep = keep
+        self.ctx = None
+
+    def __enter__(self):
+        side = _side_active
+        if side is None:
+            return self
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream())
+        side.wait_event(ev)
+        for t in self.keep:
+            if t is not None:
+                t.record_stream(side)
+        self.ctx = torch.cuda.stream(side)
+        self.ctx.__enter__()
+        return self
+
+    def __exit__(self, *exc):
+        if self.ctx is not None:
+            self.ctx.__exit__(*exc)
+        return False
+
+
+def _side_begin(device: torch.device):
+    global _side_active
+    if not WGRAD_STREAM or device.type != "cuda":
+        _side_active = None
+        return
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    if idx not in _SIDE:
+        _SIDE[idx] = torch.cuda.Stream(device=device)
+    _side_active = _SIDE[idx]
+
+
+def _side_end(grads: "Grads"):
+    """Order the current stream after the side stream; gradients allocated there are now used here."""
+    global _side_active
+    side, _side_active = _side_active, None
+    if side is None:
+        return
+    cur = torch.cuda.current_stream()
+    cur.wait_stream(side)
+    for g in grads.values():
+        if g is not None:
+            g.record_stream(cur)
+
 
 def _acc(grads: Grads, p: Optional[nn.Parameter], g: torch.Tensor) -> None:
     """Record the (final) gradient of a parameter; under data parallelism hand it to the bucketed
@@ -234,26 +294,27 @@ def single_conv_bwd(dy: CL, recs: list, grads: Grads, need_dx: bool = True, prem
                 db = ops.bias_grad(dy)
             sums = None
             kp = _im2col_kp(CL(x_in.buf, x_in.c - zpad, x_in.coff, zpad), conv) if zpad else 0
-            if conv.weight.requires_grad and kp:
-                a = ops.im2col(CL(x_in.buf, x_in.c - zpad, x_in.coff, zpad), 3, kp)
-                shape2 = (conv.weight.shape[0], kp, 1, 1, 1)
-                if db_in_wgrad:
-                    dw2, db = ops.conv_bwd_weight(a, dy, (1, 1, 1), shape2, impl=IMPL, bias_grad=True)
-                else:
-                    dw2 = ops.conv_bwd_weight(a, dy, (1, 1, 1), shape2, impl=IMPL)
-                _acc(grads, conv.weight, _im2col_weight_grad(dw2, conv.weight))
-            elif conv.weight.requires_grad:
-                wshape = list(conv.weight.shape)
-                wshape[1] += zpad
-                if db_in_wgrad:
-                    dw, db = ops.conv_bwd_weight(x_in, dy, k, tuple(wshape), impl=IMPL, bias_grad=True)
-                else:
-                    dw = ops.conv_bwd_weight(x_in, dy, k, tuple(wshape), impl=IMPL)
-                if zpad:
-                    dw = dw[:, :conv.weight.shape[1]].contiguous()
-                _acc(grads, conv.weight, dw)
-            if has_bias:
-                _acc(grads, conv.bias, db)
+            with _OnSide(x_in.buf, dy.buf, db):
+                if conv.weight.requires_grad and kp:
+                    a = ops.im2col(CL(x_in.buf, x_in.c - zpad, x_in.coff, zpad), 3, kp)
+                    shape2 = (conv.weight.shape[0], kp, 1, 1, 1)
+                    if db_in_wgrad:
+                        dw2, db = ops.conv_bwd_weight(a, dy, (1, 1, 1), shape2, impl=IMPL, bias_grad=True)
+                    else:
+                        dw2 = ops.conv_bwd_weight(a, dy, (1, 1, 1), shape2, impl=IMPL)
+                    _acc(grads, conv.weight, _im2col_weight_grad(dw2, conv.weight))
+                elif conv.weight.requires_grad:
+                    wshape = list(conv.weight.shape)
+                    wshape[1] += zpad
+                    if db_in_wgrad:
+                        dw, db = ops.conv_bwd_weight(x_in, dy, k, tuple(wshape), impl=IMPL, bias_grad=True)
+                    else:
+                        dw = ops.conv_bwd_weight(x_in, dy, k, tuple(wshape), impl=IMPL)
+                    if zpad:
+                        dw = dw[:, :conv.weight.shape[1]].contiguous()
+                    _acc(grads, conv.weight, dw)
+                if has_bias:
+                    _acc(grads, conv.bias, db)
             if last and not need_dx:
                 return None, False, None
             # the fused mask must have the layout of the (dense) dx the kernel writes
@@ -426,8 +487,10 @@ def unet2d_backward(net, tape: list, dfeat: CL, grads: Grads, premasked: bool) -
             if dcat_sums is not None:
                 _acc(grads, up.bias, dcat_sums[:, 0, :c].sum(0).float())
             else:
-                _acc(grads, up.bias, ops.bias_grad(d_up))
-        _acc(grads, up.weight, ops.convt_bwd_weight(x_in, d_up, impl=IMPL))
+                with _OnSide(d_up.buf):
+                    _acc(grads, up.bias, ops.bias_grad(d_up))
+        with _OnSide(x_in.buf, d_up.buf):
+            _acc(grads, up.weight, ops.convt_bwd_weight(x_in, d_up, impl=IMPL))
         fuse = bool(x_relu and x_in.is_full())
         # x_in is the ReLU output of the block below: its second conv's bias gradient is the column
         # sum of the masked gradient this kernel writes
@@ -548,8 +611,9 @@ def unet3d_backward(net, tape: list, dfeat: CL, grads: Grads, premasked: bool) -
         if rec[0] == "deconv":
             _, x_in, ct, wp_bwd, kd, cs, cx = rec
             d_planes = ops.deconv_resize_bwd(dcat.slice(cs, cx), x_in.dims, kd)
-            _acc(grads, ct.weight, ops.deconv_bwd_weight(x_in, d_planes, tuple(ct.weight.shape), kd,
-                                                        impl=IMPL))
+            with _OnSide(x_in.buf, d_planes.buf):
+                _acc(grads, ct.weight, ops.deconv_bwd_weight(x_in, d_planes, tuple(ct.weight.shape), kd,
+                                                            impl=IMPL))
             d = ops.deconv_bwd_data(d_planes, wp_bwd, x_in.dims, kd, impl=IMPL)
         else:
             _, in_size, cs, cx = rec
@@ -600,6 +664,10 @@ class _NetFunction(torch.autograd.Function):
         grads: Grads = {}
         head = net.final_conv
         _REDUCER = getattr(net, "_b200_reducer", None)
+        # measured (profiles/r01_wgrad_stream_ab.txt): -3 % on the 3D nets, whose backward carries ~5 ms of
+        # HBM-bound norm / pool / up-sampling kernels to overlap; nothing on the norm-free 2D U-Net
+        if ctx.kind != "unet2d":
+            _side_begin(dlogits.device)
         try:
             dfeat, dw, db = ops.head_bwd(ctx.feat, head.weight, dlogits, mask_relu=ctx.feat_relu)
             _acc(grads, head.weight, dw)
@@ -609,10 +677,12 @@ class _NetFunction(torch.autograd.Function):
                 unet2d_backward(net, tape, dfeat, grads, ctx.feat_relu)
             else:
                 unet3d_backward(net, tape, dfeat, grads, ctx.feat_relu)
+            _side_end(grads)
             if _REDUCER is not None:
                 _REDUCER.finish()
         finally:
             _REDUCER = None
+            _side_end({})
         ctx.tape = ctx.feat = None
         out = tuple(grads.get(p) if p.requires_grad else None for p in ctx.params)
         return (None, None, None) + out
