@@ -159,6 +159,23 @@ int b200_maxpool2_fwd(int32_t n, int32_t d, int32_t h, int32_t w, int32_t c, int
 int b200_maxpool2_bwd(int32_t n, int32_t d, int32_t h, int32_t w, int32_t c, int32_t pool_d,
                       b200_view x, b200_view dy, b200_view add, b200_view dx, int32_t mask_relu,
                       b200_stream_t stream);
+/* ---- UNet 3+ (model/unet2d/unet.py:136-446), 2D only -------------------------------------------
+ * nn.MaxPool2d(k, k, ceil_mode=True) unet.py:175-187 on sizes divisible by k (the network only accepts
+ * multiples of 16, where ceil mode = floor mode).  bwd: ties to the first maximum in scan order; dx fully
+ * written; add (ptr may be NULL) = a gradient of x's shape summed in. */
+int b200_maxpoolk_fwd(int32_t n, int32_t h, int32_t w, int32_t c, int32_t k, b200_view x, b200_view y,
+                      b200_stream_t stream);
+int b200_maxpoolk_bwd(int32_t n, int32_t h, int32_t w, int32_t c, int32_t k, b200_view x, b200_view dy,
+                      b200_view add, b200_view dx, b200_stream_t stream);
+/* nn.Upsample(scale_factor=scale, mode='bilinear') unet.py:198-315 (align_corners=False): (n, ih, iw, c)
+ * -> (n, ih*scale, iw*scale, c); bwd is its exact adjoint as a deterministic gather (+ add, may be NULL) */
+int b200_bilinear2d_fwd(int32_t n, int32_t ih, int32_t iw, int32_t c, int32_t scale, b200_view x,
+                        b200_view y, b200_stream_t stream);
+int b200_bilinear2d_bwd(int32_t n, int32_t ih, int32_t iw, int32_t c, int32_t scale, b200_view dy,
+                        b200_view add, b200_view dx, b200_stream_t stream);
+/* dst += src: gradient accumulation for tensors that feed several full-scale skip branches */
+int b200_add(int64_t npos, int32_t c, b200_view src, b200_view dst, b200_stream_t stream);
+
 /* F.interpolate(mode='nearest') buildingblocks.py:671-673: src = floor(dst * in / out) */
 int b200_upsample_nearest_fwd(int32_t n, int32_t id, int32_t ih, int32_t iw, int32_t od,
                               int32_t oh, int32_t ow, int32_t c, b200_view x, b200_view y,

@@ -201,6 +201,166 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// ------------------------------------------------------------------------------------ UNet 3+ ops
+// k x k / stride k max-pool on exact windows (nn.MaxPool2d(k, k, ceil_mode=True) of model/unet2d/unet.py:175-187;
+// the network only accepts sizes divisible by 16, where ceil mode equals floor mode), 2D, 8 channels per thread.
+__global__ void __launch_bounds__(256)
+    maxpoolk_fwd_kernel(int n, int h, int w, int c, int k, View x, View y) {
+  const int oh = h / k, ow = w / k, cv = c / 8;
+  const long total = (long)n * oh * ow * cv;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    long r = i;
+    const int ch = (int)(r % cv) * 8; r /= cv;
+    const int xw = (int)(r % ow); r /= ow;
+    const int xh = (int)(r % oh); r /= oh;
+    const long b = r;
+    float m[8];
+    for (int e = 0; e < k; ++e) {
+#pragma unroll 4
+      for (int g = 0; g < k; ++g) {
+        float f[8];
+        Vec<8>::load(x.at((b * h + xh * k + e) * w + xw * k + g, ch), f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) m[j] = (e | g) == 0 ? f[j] : fmaxf(m[j], f[j]);
+      }
+    }
+    Vec<8>::store(y.at((b * oh + xh) * ow + xw, ch), m);
+  }
+}
+// one thread per window: first maximum in (h, w) scan order receives dy; every dx of the window is written
+// (+ add: a gradient of x's shape accumulated in, NULL = none)
+__global__ void __launch_bounds__(256)
+    maxpoolk_bwd_kernel(int n, int h, int w, int c, int k, View x, View dy, View add, View dx) {
+  const int oh = h / k, ow = w / k, cv = c / 8;
+  const long total = (long)n * oh * ow * cv;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    long r = i;
+    const int ch = (int)(r % cv) * 8; r /= cv;
+    const int xw = (int)(r % ow); r /= ow;
+    const int xh = (int)(r % oh); r /= oh;
+    const long b = r;
+    float m[8];
+    int arg[8];
+    for (int e = 0; e < k; ++e)
+      for (int g = 0; g < k; ++g) {
+        float f[8];
+        Vec<8>::load(x.at((b * h + xh * k + e) * w + xw * k + g, ch), f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if ((e | g) == 0 || f[j] > m[j]) { m[j] = f[j]; arg[j] = e * k + g; }
+      }
+    float gy[8];
+    Vec<8>::load(dy.at((b * oh + xh) * ow + xw, ch), gy);
+    for (int e = 0; e < k; ++e)
+      for (int g = 0; g < k; ++g) {
+        const long pos = (b * h + xh * k + e) * w + xw * k + g;
+        float o[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = 0.f;
+        if (add.p) Vec<8>::load(add.at(pos, ch), o);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] += (arg[j] == e * k + g) ? gy[j] : 0.f;
+        Vec<8>::store(dx.at(pos, ch), o);
+      }
+  }
+}
+
+// nn.Upsample(scale_factor = s, mode = 'bilinear') (align_corners = False), model/unet2d/unet.py:198-315:
+// src = max((dst + 0.5) / s - 0.5, 0), i0 = floor(src), i1 = min(i0 + 1, in - 1), weights (1 - l, l).
+__device__ __forceinline__ void bilinear_src(int dst, float inv_s, int in, int& i0, int& i1, float& l0, float& l1) {
+  float src = inv_s * (dst + 0.5f) - 0.5f;
+  src = src < 0.f ? 0.f : src;
+  i0 = (int)src;
+  i0 = i0 < in - 1 ? i0 : in - 1;
+  i1 = i0 + (i0 < in - 1 ? 1 : 0);
+  l1 = src - (float)i0;
+  l0 = 1.f - l1;
+}
+__global__ void __launch_bounds__(256)
+    bilinear2d_fwd_kernel(int n, int ih, int iw, int c, int s, View x, View y) {
+  const int oh = ih * s, ow = iw * s, cv = c / 8;
+  const float inv_s = 1.f / (float)s;
+  const long total = (long)n * oh * ow * cv;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    long r = i;
+    const int ch = (int)(r % cv) * 8; r /= cv;
+    const int xw = (int)(r % ow); r /= ow;
+    const int xh = (int)(r % oh); r /= oh;
+    const long b = r;
+    int h0, h1, w0, w1;
+    float hl0, hl1, wl0, wl1;
+    bilinear_src(xh, inv_s, ih, h0, h1, hl0, hl1);
+    bilinear_src(xw, inv_s, iw, w0, w1, wl0, wl1);
+    float a00[8], a01[8], a10[8], a11[8], o[8];
+    Vec<8>::load(x.at((b * ih + h0) * iw + w0, ch), a00);
+    Vec<8>::load(x.at((b * ih + h0) * iw + w1, ch), a01);
+    Vec<8>::load(x.at((b * ih + h1) * iw + w0, ch), a10);
+    Vec<8>::load(x.at((b * ih + h1) * iw + w1, ch), a11);
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      o[j] = hl0 * (wl0 * a00[j] + wl1 * a01[j]) + hl1 * (wl0 * a10[j] + wl1 * a11[j]);
+    Vec<8>::store(y.at((b * oh + xh) * ow + xw, ch), o);
+  }
+}
+// adjoint as a gather (deterministic, no atomics): an input pixel collects from the ~2s x 2s outputs whose
+// i0 or i1 is that pixel; dx is fully written (+ add)
+__global__ void __launch_bounds__(256)
+    bilinear2d_bwd_kernel(int n, int ih, int iw, int c, int s, View dy, View add, View dx) {
+  const int oh = ih * s, ow = iw * s, cv = c / 8;
+  const float inv_s = 1.f / (float)s;
+  const long total = (long)n * ih * iw * cv;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    long r = i;
+    const int ch = (int)(r % cv) * 8; r /= cv;
+    const int xw = (int)(r % iw); r /= iw;
+    const int xh = (int)(r % ih); r /= ih;
+    const long b = r;
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    if (add.p) Vec<8>::load(add.at((b * ih + xh) * iw + xw, ch), acc);
+    int olo = xh * s - s / 2 - 1, ohi = xh * s + 3 * s / 2 + 2;
+    olo = olo < 0 ? 0 : olo; ohi = ohi > oh ? oh : ohi;
+    int plo = xw * s - s / 2 - 1, phi = xw * s + 3 * s / 2 + 2;
+    plo = plo < 0 ? 0 : plo; phi = phi > ow ? ow : phi;
+    for (int oy = olo; oy < ohi; ++oy) {
+      int h0, h1;
+      float hl0, hl1;
+      bilinear_src(oy, inv_s, ih, h0, h1, hl0, hl1);
+      const float wy = (h0 == xh ? hl0 : 0.f) + (h1 == xh ? hl1 : 0.f);
+      if (wy == 0.f) continue;
+      for (int ox = plo; ox < phi; ++ox) {
+        int w0, w1;
+        float wl0, wl1;
+        bilinear_src(ox, inv_s, iw, w0, w1, wl0, wl1);
+        const float wx = (w0 == xw ? wl0 : 0.f) + (w1 == xw ? wl1 : 0.f);
+        if (wx == 0.f) continue;
+        float g[8];
+        Vec<8>::load(dy.at((b * oh + oy) * ow + ox, ch), g);
+        const float wgt = wy * wx;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = fmaf(wgt, g[j], acc[j]);
+      }
+    }
+    Vec<8>::store(dx.at((b * ih + xh) * iw + xw, ch), acc);
+  }
+}
+// dst += src (gradient accumulation where a tensor feeds several branches)
+__global__ void __launch_bounds__(256) add_kernel(long npos, int c, View src, View dst) {
+  const int cv = c / 8;
+  const long total = npos * cv;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const long pos = i / cv;
+    const int ch = (int)(i % cv) * 8;
+    float a[8], b[8];
+    Vec<8>::load(dst.at(pos, ch), a);
+    Vec<8>::load(src.at(pos, ch), b);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) a[j] += b[j];
+    Vec<8>::store(dst.at(pos, ch), a);
+  }
+}
+
 // ------------------------------------------------------------------------------------ nearest
 __device__ __forceinline__ int nearest_src(int dst, float scale, int in) {
   const int s = (int)floorf(dst * scale);
@@ -1021,6 +1181,53 @@ int b200_maxpool2_bwd(int32_t n, int32_t d, int32_t h, int32_t w, int32_t c, int
   }
   DISPATCH_V(v, maxpool_bwd_kernel, GRID1D(total / (v ? 8 : 1)), n, d, h, w, c, pool_d, mk(x), mk(dy),
              mk(add), mk(dx), mask_relu);
+  return B200_OK;
+}
+int b200_maxpoolk_fwd(int32_t n, int32_t h, int32_t w, int32_t c, int32_t k, b200_view x, b200_view y,
+                      b200_stream_t stream) {
+  if (k < 2 || k > 16 || h % k || w % k || !vec8(c, x) || !vec8(c, y)) return B200_ERR_UNSUPPORTED;
+  const long total = (long)n * (h / k) * (w / k) * (c / 8);
+  if (total <= 0) return B200_OK;
+  maxpoolk_fwd_kernel<<<GRID1D(total), 256, 0, (cudaStream_t)stream>>>(n, h, w, c, k, mk(x), mk(y));
+  B200_LAUNCH_CHECK();
+  return B200_OK;
+}
+int b200_maxpoolk_bwd(int32_t n, int32_t h, int32_t w, int32_t c, int32_t k, b200_view x, b200_view dy,
+                      b200_view add, b200_view dx, b200_stream_t stream) {
+  if (k < 2 || k > 16 || h % k || w % k || !vec8(c, x) || !vec8(c, dy) || !vec8(c, dx) ||
+      (add.ptr && !vec8(c, add)))
+    return B200_ERR_UNSUPPORTED;
+  const long total = (long)n * (h / k) * (w / k) * (c / 8);
+  if (total <= 0) return B200_OK;
+  maxpoolk_bwd_kernel<<<GRID1D(total), 256, 0, (cudaStream_t)stream>>>(n, h, w, c, k, mk(x), mk(dy), mk(add), mk(dx));
+  B200_LAUNCH_CHECK();
+  return B200_OK;
+}
+int b200_bilinear2d_fwd(int32_t n, int32_t ih, int32_t iw, int32_t c, int32_t scale, b200_view x,
+                        b200_view y, b200_stream_t stream) {
+  if (scale < 1 || scale > 32 || !vec8(c, x) || !vec8(c, y)) return B200_ERR_UNSUPPORTED;
+  const long total = (long)n * ih * scale * iw * scale * (c / 8);
+  if (total <= 0) return B200_OK;
+  bilinear2d_fwd_kernel<<<GRID1D(total), 256, 0, (cudaStream_t)stream>>>(n, ih, iw, c, scale, mk(x), mk(y));
+  B200_LAUNCH_CHECK();
+  return B200_OK;
+}
+int b200_bilinear2d_bwd(int32_t n, int32_t ih, int32_t iw, int32_t c, int32_t scale, b200_view dy,
+                        b200_view add, b200_view dx, b200_stream_t stream) {
+  if (scale < 1 || scale > 32 || !vec8(c, dy) || !vec8(c, dx) || (add.ptr && !vec8(c, add)))
+    return B200_ERR_UNSUPPORTED;
+  const long total = (long)n * ih * iw * (c / 8);
+  if (total <= 0) return B200_OK;
+  bilinear2d_bwd_kernel<<<GRID1D(total), 256, 0, (cudaStream_t)stream>>>(n, ih, iw, c, scale, mk(dy), mk(add), mk(dx));
+  B200_LAUNCH_CHECK();
+  return B200_OK;
+}
+int b200_add(int64_t npos, int32_t c, b200_view src, b200_view dst, b200_stream_t stream) {
+  if (!vec8(c, src) || !vec8(c, dst)) return B200_ERR_UNSUPPORTED;
+  const long total = (long)npos * (c / 8);
+  if (total <= 0) return B200_OK;
+  add_kernel<<<GRID1D(total), 256, 0, (cudaStream_t)stream>>>((long)npos, c, mk(src), mk(dst));
+  B200_LAUNCH_CHECK();
   return B200_OK;
 }
 int b200_upsample_nearest_fwd(int32_t n, int32_t id, int32_t ih, int32_t iw, int32_t od, int32_t oh,

@@ -330,6 +330,40 @@ def maxpool_bwd(x: CL, dy: CL, pool_d: int, add: Optional[CL] = None,
     return out
 
 
+def maxpoolk_fwd(x: CL, k: int) -> CL:
+    """k x k / stride k max-pool of a 2D tensor (UNet 3+ full-scale skip branches)."""
+    assert x.d == 1
+    out = CL.empty(x.n, 1, x.h // k, x.w // k, x.c, x.device)
+    call("b200_maxpoolk_fwd", x.n, x.h, x.w, x.c, k, x.view(), out.view(), _stream())
+    return out
+
+
+def maxpoolk_bwd(x: CL, dy: CL, k: int, add: Optional[CL] = None) -> CL:
+    out = x.new_like()
+    call("b200_maxpoolk_bwd", x.n, x.h, x.w, x.c, k, x.view(), dy.view(),
+         _NULL_VIEW if add is None else add.view(), out.view(), _stream())
+    return out
+
+
+def bilinear_fwd(x: CL, scale: int) -> CL:
+    assert x.d == 1
+    out = CL.empty(x.n, 1, x.h * scale, x.w * scale, x.c, x.device)
+    call("b200_bilinear2d_fwd", x.n, x.h, x.w, x.c, scale, x.view(), out.view(), _stream())
+    return out
+
+
+def bilinear_bwd(dy: CL, scale: int, add: Optional[CL] = None) -> CL:
+    out = CL.empty(dy.n, 1, dy.h // scale, dy.w // scale, dy.c, dy.device)
+    call("b200_bilinear2d_bwd", dy.n, out.h, out.w, dy.c, scale, dy.view(),
+         _NULL_VIEW if add is None else add.view(), out.view(), _stream())
+    return out
+
+
+def add_(dst: CL, src: CL) -> CL:
+    call("b200_add", dst.npos, dst.c, src.view(), dst.view(), _stream())
+    return dst
+
+
 def upsample_nearest_fwd(x: CL, size, out: Optional[CL] = None) -> CL:
     od, oh, ow = size
     if out is None:

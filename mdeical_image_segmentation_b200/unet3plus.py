@@ -1,0 +1,218 @@
+"""UNet 3+ (model/unet2d/unet.py:136-446) on the B200 path — SURVEY.md §8(f) rank 1, the default model of
+the reference's ``train.py`` (train.py:101-105).
+
+Same constructor, attribute names and therefore ``state_dict`` keys as the reference.  The network is a
+small DAG: five ``unetConv2`` encoder levels (64..1024 channels) and four decoder stages, each of which
+gathers ALL five scales (max-pooled encoder maps, the same-scale encoder map, bilinearly up-sampled deeper
+decoder maps), gives every one a 3x3 conv + BatchNorm + ReLU to 64 channels, concatenates them (320) and
+fuses them with one more conv + BN + ReLU.  On this path
+
+* every 3x3 convolution runs on the tcgen05 implicit-GEMM kernels (conv -> BN statistics in the epilogue ->
+  one normalise + ReLU pass), the five branch results are written straight into their 64-channel slice of
+  the 320-channel concat buffer (no ``torch.cat``),
+* the k x k max-pools (k = 2, 4, 8) and the bilinear x2..x16 resizes are HBM-bound kernels
+  (``b200_maxpoolk_*``, ``b200_bilinear2d_*``) whose backward kernels accumulate straight into the gradient
+  of the tensor they read (an encoder map feeds up to five branches),
+* the 3x3 output conv (320 -> n_classes) is padded to 16 output channels so it too runs on tensor cores.
+
+The deep-supervision / CGM variants (unet.py:454-1153) are not implemented here.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional
+
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+from . import engine, ops
+from .ops import CL
+from .unet2d import unetConv2
+
+FILTERS = [64, 128, 256, 512, 1024]
+
+
+def _kaiming(m: nn.Module) -> None:
+    """init_weights(m, 'kaiming') — model/unet2d/init_weights.py:29-38."""
+    if isinstance(m, nn.Conv2d):
+        nn.init.kaiming_normal_(m.weight.data, a=0, mode="fan_in")
+    elif isinstance(m, nn.BatchNorm2d):
+        nn.init.normal_(m.weight.data, 1.0, 0.02)
+        nn.init.constant_(m.bias.data, 0.0)
+
+
+def _branch_name(level: int, stage: int) -> str:
+    """Attribute prefix of the branch that brings scale ``level`` (1..5) to decoder ``stage`` (1..4)."""
+    if level < stage:
+        return f"h{level}_PT_hd{stage}"
+    if level == stage:
+        return f"h{level}_Cat_hd{stage}"
+    return f"hd{level}_UT_hd{stage}"
+
+
+class UNet_3Plus(nn.Module):
+    """unet.py:136-446.  ``forward(inputs) -> logits`` (the sigmoid is commented out in the reference)."""
+
+    def __init__(self, in_channels=3, n_classes=1, feature_scale=4, is_deconv=True, is_batchnorm=True):
+        super().__init__()
+        if not is_batchnorm:
+            raise NotImplementedError("UNet_3Plus(is_batchnorm=False) is outside the B200 path")
+        self.is_deconv, self.in_channels = is_deconv, in_channels
+        self.is_batchnorm, self.feature_scale = is_batchnorm, feature_scale
+        f = FILTERS
+        self.conv1 = unetConv2(in_channels, f[0], True)
+        self.maxpool1 = nn.MaxPool2d(kernel_size=2)
+        self.conv2 = unetConv2(f[0], f[1], True)
+        self.maxpool2 = nn.MaxPool2d(kernel_size=2)
+        self.conv3 = unetConv2(f[1], f[2], True)
+        self.maxpool3 = nn.MaxPool2d(kernel_size=2)
+        self.conv4 = unetConv2(f[2], f[3], True)
+        self.maxpool4 = nn.MaxPool2d(kernel_size=2)
+        self.conv5 = unetConv2(f[3], f[4], True)
+        self.CatChannels, self.CatBlocks = f[0], 5
+        self.UpChannels = self.CatChannels * self.CatBlocks
+        for stage in (4, 3, 2, 1):          # same registration order as the reference -> same state_dict
+            for level in range(1, 6):
+                name = _branch_name(level, stage)
+                if level < stage:
+                    k = 2 ** (stage - level)
+                    setattr(self, name, nn.MaxPool2d(k, k, ceil_mode=True))
+                    cin = f[level - 1]
+                elif level == stage:
+                    cin = f[level - 1]
+                else:
+                    setattr(self, name, nn.Upsample(scale_factor=2 ** (level - stage), mode="bilinear"))
+                    cin = f[4] if level == 5 else self.UpChannels
+                setattr(self, name + "_conv", nn.Conv2d(cin, self.CatChannels, 3, padding=1))
+                setattr(self, name + "_bn", nn.BatchNorm2d(self.CatChannels))
+                setattr(self, name + "_relu", nn.ReLU(inplace=True))
+            setattr(self, f"conv{stage}d_1", nn.Conv2d(self.UpChannels, self.UpChannels, 3, padding=1))
+            setattr(self, f"bn{stage}d_1", nn.BatchNorm2d(self.UpChannels))
+            setattr(self, f"relu{stage}d_1", nn.ReLU(inplace=True))
+        self.outconv1 = nn.Conv2d(self.UpChannels, n_classes, 3, padding=1)
+        for m in self.modules():
+            _kaiming(m)
+
+    def forward(self, inputs: torch.Tensor) -> torch.Tensor:
+        params = tuple(self.parameters())
+        return _Net3PFunction.apply(self, inputs, *params)
+
+
+# ===================================================================================== executor
+def _spec(net: UNet_3Plus, prefix: str) -> engine.LayerSpec:
+    return engine.LayerSpec("cbr", getattr(net, prefix + "_conv"), batchnorm=getattr(net, prefix + "_bn"))
+
+
+def _forward(net: UNet_3Plus, images: torch.Tensor, training: bool, tape: Optional[dict]) -> CL:
+    if images.shape[2] % 16 or images.shape[3] % 16:
+        raise ValueError("UNet_3Plus needs H and W divisible by 16 (the reference's torch.cat fails otherwise)")
+    want = tape is not None
+    x = ops.from_nchw(images, pad=True)
+    h: Dict[int, CL] = {}          # scale level -> feature map (encoder h1..h5; h[5] is hd5)
+    relu = False
+    for lvl in range(1, 6):
+        t = [] if want else None
+        if lvl > 1:
+            x = ops.maxpool_fwd(h[lvl - 1], 1)
+        x, relu, _ = engine.block_fwd(x, getattr(net, f"conv{lvl}")._specs(), training, t, in_relu=relu)
+        h[lvl] = x
+        if want:
+            tape[("enc", lvl)] = t
+    hd: Dict[int, CL] = {5: h[5]}
+    for stage in (4, 3, 2, 1):
+        ref = h[stage]
+        cat = CL.empty(ref.n, 1, ref.h, ref.w, net.UpChannels, ref.device)
+        for level in range(1, 6):
+            name = _branch_name(level, stage)
+            if level < stage:
+                src = ops.maxpoolk_fwd(h[level], 2 ** (stage - level))
+            elif level == stage:
+                src = h[level]
+            else:
+                src = ops.bilinear_fwd(hd[level], 2 ** (level - stage))
+            t = [] if want else None
+            engine.single_conv_fwd(src, _spec(net, name), training, t,
+                                   out=cat.slice((level - 1) * net.CatChannels, net.CatChannels))
+            if want:
+                tape[("br", level, stage)] = t
+        t = [] if want else None
+        # the concat is five ReLU outputs: its gradient can carry their ReLU backward (in_relu)
+        hd[stage], _, _ = engine.single_conv_fwd(
+            cat, engine.LayerSpec("cbr", getattr(net, f"conv{stage}d_1"), batchnorm=getattr(net, f"bn{stage}d_1")),
+            training, t, in_relu=True)
+        if want:
+            tape[("fuse", stage)] = t
+    if want:
+        tape["h"], tape["hd"] = h, hd
+    return hd[1]
+
+
+def _pad16(w: torch.Tensor) -> torch.Tensor:
+    """(n_classes, C, 3, 3) -> (16, C, 3, 3): the output conv runs on the tensor cores with N = 16."""
+    return F.pad(w, (0, 0, 0, 0, 0, 0, 0, 16 - w.shape[0])) if w.shape[0] < 16 else w
+
+
+class _Net3PFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, net: UNet_3Plus, images: torch.Tensor, *params):
+        ops.require_cuda(images)
+        need_grad = any(ctx.needs_input_grad)
+        tape = {} if need_grad else None
+        with torch.no_grad():
+            feat = _forward(net, images, net.training, tape)
+            oc = net.outconv1
+            ncls = oc.weight.shape[0]
+            if ncls > 16:
+                raise NotImplementedError("UNet_3Plus with more than 16 classes")
+            wp_fwd, wp_bwd, k = ops.conv_repack_weight(_pad16(oc.weight.detach()), need_bwd=need_grad)
+            bias = None if oc.bias is None else F.pad(oc.bias.detach().float(), (0, 16 - ncls)).contiguous()
+            y = ops.conv_fwd(feat, wp_fwd, k, bias, False, impl=engine.IMPL)
+            logits = ops.to_nchw(y.slice(0, ncls), False)
+        ctx.net, ctx.tape, ctx.feat, ctx.params = net, tape, feat, params
+        ctx.head = (wp_bwd, k, ncls)
+        return logits
+
+    @staticmethod
+    def backward(ctx, dlogits):
+        net, tape = ctx.net, ctx.tape
+        if tape is None:
+            raise RuntimeError("backward through a forward that ran without grad")
+        grads: engine.Grads = {}
+        wp_bwd, k, ncls = ctx.head
+        oc = net.outconv1
+        dy = ops.from_nchw(F.pad(dlogits.contiguous().float(), (0, 0, 0, 0, 0, 16 - ncls)))
+        dw, db = ops.conv_bwd_weight(ctx.feat, dy, k, (16,) + tuple(oc.weight.shape[1:]), impl=engine.IMPL,
+                                     bias_grad=True)
+        engine._acc(grads, oc.weight, dw[:ncls].contiguous())
+        if oc.bias is not None:
+            engine._acc(grads, oc.bias, db[:ncls].contiguous())
+        # hd1 is a ReLU output: fold its ReLU backward into this data gradient
+        g = ops.conv_bwd_data(dy, wp_bwd, k, mask=ctx.feat, impl=engine.IMPL)
+        h, hd = tape["h"], tape["hd"]
+        dh: Dict[int, Optional[CL]] = {lvl: None for lvl in range(1, 6)}     # d(loss)/d h1..h5 (h5 = hd5)
+        dhd: Dict[int, Optional[CL]] = {4: None, 3: None, 2: None}
+        cc = net.CatChannels
+        for stage in (1, 2, 3, 4):
+            if stage > 1:
+                g = dhd[stage]
+            # g is premasked only for stage 1 (conv_bwd_data above); deeper stages accumulate raw gradients
+            dcat, pm, _ = engine.single_conv_bwd(g, tape[("fuse", stage)], grads, premasked=(stage == 1))
+            for level in range(1, 6):
+                d, _, _ = engine.single_conv_bwd(dcat.slice((level - 1) * cc, cc), tape[("br", level, stage)],
+                                                 grads, premasked=pm)
+                if level < stage:
+                    dh[level] = ops.maxpoolk_bwd(h[level], d, 2 ** (stage - level), add=dh[level])
+                elif level == stage:
+                    dh[level] = d if dh[level] is None else ops.add_(dh[level], d)
+                elif level == 5:
+                    dh[5] = ops.bilinear_bwd(d, 2 ** (level - stage), add=dh[5])
+                else:
+                    dhd[level] = ops.bilinear_bwd(d, 2 ** (level - stage), add=dhd[level])
+        d, pm = dh[5], False
+        for lvl in range(5, 0, -1):
+            d, _, _ = engine.block_bwd(d, tape[("enc", lvl)], 2, grads, need_dx=lvl > 1, premasked=pm)
+            if lvl > 1:   # h[lvl-1] is a ReLU output: the pool backward masks the summed gradient by it
+                d = ops.maxpool_bwd(h[lvl - 1], d, 1, add=dh[lvl - 1], mask_relu=True)
+                pm = True
+        ctx.tape = ctx.feat = None
+        return (None, None) + tuple(grads.get(p) if p.requires_grad else None for p in ctx.params)

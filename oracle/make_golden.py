@@ -205,6 +205,40 @@ def check_seed_init(ns):
     print("seeded init identical: reference vs product modules")
 
 
+def gen_unet3plus(ns):
+    """UNet 3+ (model/unet2d/unet.py:136-446), the default model of train.py: 27 M parameters, so the
+    fixture stores the seed of oracle.unet3plus.fill_state_dict_ (a deterministic fill by state_dict key)
+    instead of the weights, plus input, target, logits, loss, the gradients of a few small parameters and
+    the gradient norm of every parameter."""
+    from oracle import unet3plus as O3
+    torch.manual_seed(0)
+    net = ns.U2.UNet_3Plus(3, 1)
+    sd = {k: v.clone() for k, v in net.state_dict().items()}
+    O3.fill_state_dict_(sd, 7)
+    net.load_state_dict(sd)
+    net.train()
+    g = torch.Generator().manual_seed(21)
+    x = torch.randn((2, 3, 32, 48), generator=g)
+    y = blob_target((2, 1, 32, 48), 22)
+    logits = net(x)
+    loss = torch.nn.BCEWithLogitsLoss()(logits, y)
+    loss.backward()
+    names = [k for k, _ in net.named_parameters()]
+    keep = ["outconv1.weight", "outconv1.bias", "bn1d_1.weight", "bn1d_1.bias", "conv1.conv1.0.bias",
+            "conv1.conv1.1.weight", "h1_PT_hd4_bn.weight", "hd5_UT_hd1_bn.bias", "h3_Cat_hd3_conv.bias",
+            "conv5.conv2.1.weight"]
+    out = dict(seed=7, x=_np(x), y=_np(y), logits=_np(logits), loss=_np(loss),
+               grad_names=np.array(names), grad_norms=np.array([p.grad.norm().item() for _, p in net.named_parameters()]),
+               running_mean_bn1d_1=_np(net.state_dict()["bn1d_1.running_mean"]),
+               running_var_conv1=_np(net.state_dict()["conv1.conv1.1.running_var"]),
+               state_dict_keys=np.array(list(net.state_dict().keys())))
+    grads = dict(net.named_parameters())
+    for k in keep:
+        out["grad::" + k] = _np(grads[k].grad)
+    np.savez_compressed(os.path.join(OUT, "unet3plus_3_1.npz"), **out)
+    print("unet3plus_3_1", float(loss), logits.abs().max().item())
+
+
 def main():
     torch.set_num_threads(8)
     os.makedirs(OUT, exist_ok=True)
@@ -214,6 +248,7 @@ def main():
     gen_unet3d(ns)
     gen_blocks(ns)
     gen_losses_metrics(ns)
+    gen_unet3plus(ns)
 
 
 if __name__ == "__main__":
