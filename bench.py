@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Headline benchmark: U-Net training throughput on B200 (imgs/s for 2D, vols/s for 3D).
 
-    python bench.py --gpus N --steps K --warmup W [--workload cfg2|cfg3|cfg3p|cfg1] [--impl reference]
+    python bench.py --gpus N --steps K --warmup W [--workload cfg2|cfg3|cfg3p|cfg4|cfg4p|cfg1|u3p|u3pds|cfg5] [--impl reference]
 
 A step = forward + loss + backward + optimizer step on one per-GPU batch of synthetic data (random-init
 weights of the named architecture).  One JSON line on rank 0 (see the keys at the bottom).  For N > 1
@@ -45,6 +45,13 @@ WORKLOADS = {
     "cfg4p": dict(kind="3d", cin=4, cout=3, size=(160, 192, 160), batch=1, train_tf=22.394, unit="vols/s",
                   order="cbr", upsample="deconv", loss="dice",
                   desc="UNet3D(4,3) cbr+deconv 160x192x160 (BraTS-like), batch 1 per GPU, fused Dice + Adam"),
+    # the default model of the reference's train.py (train.py:101-105)
+    "u3p": dict(kind="2d", cin=3, cout=1, size=(512, 512), batch=8, train_tf=4.7428, unit="imgs/s",
+                unet_type="UNet_3Plus",
+                desc="UNet_3Plus(3,1) 512x512 binary seg, batch 8 per GPU, SegmentationLoss + AdamW"),
+    "u3pds": dict(kind="2d", cin=3, cout=1, size=(512, 512), batch=8, train_tf=4.7443, unit="imgs/s",
+                  unet_type="UNet_3Plus_DeepSup",
+                  desc="UNet_3Plus_DeepSup(3,1) 512x512 binary seg, batch 8 per GPU, SegmentationLoss over 5 heads + AdamW"),
 }
 
 # cfg5 (BASELINE.json configs[4]): inference-only sweep, eval() + no_grad, as api/api.py:64 would call it.
@@ -163,7 +170,7 @@ def build_model(w, device):
     import mdeical_image_segmentation_b200 as B
     torch.manual_seed(0)
     if w["kind"] == "2d":
-        model = B.UNetModel(B.UNetConfig(w["cin"], w["cout"])).to(device).train()
+        model = B.UNetModel(B.UNetConfig(w["cin"], w["cout"], w.get("unet_type", "UNet"))).to(device).train()
         opt = torch.optim.AdamW(model.parameters(), lr=1e-4, weight_decay=1e-3, fused=True)
 
         def step_fn(x, y):
@@ -490,7 +497,23 @@ def run_cpu_sample(w, steps, warmup, batch=None):
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     torch.manual_seed(0)
-    if w["kind"] == "2d":
+    if w.get("unet_type", "UNet") != "UNet":       # UNet 3+ family: one 256^2 crop per step, scaled by pixels
+        from oracle import unet3plus as O3
+        b = batch or 1
+        deep = w["unet_type"] == "UNet_3Plus_DeepSup"
+        net = getattr(B, w["unet_type"])(w["cin"], w["cout"])
+        sd = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and "running" not in k else v.clone())
+              for k, v in net.state_dict().items()}
+        x, y = make_batch(dict(w, size=(256, 256)), b, 7)
+        seg = lambda lo: O.f1_loss(lo, y) + O.iou_loss(lo, y)  # noqa: E731
+
+        def fwd():
+            out = O3.unet3plus_forward(sd, x, training=True, deep_sup=deep)
+            return sum(seg(d) for d in out) if deep else seg(out)
+        scale = 256.0 ** 2 / (w["size"][0] * w["size"][1])
+        sample = f"{b} crop(s) of 256x256 per step, scaled by pixel count to {w['size'][0]}x{w['size'][1]} images"
+        opt = torch.optim.AdamW([v for v in sd.values() if v.requires_grad], lr=1e-4, weight_decay=1e-3)
+    elif w["kind"] == "2d":
         b = batch or 1
         sd = {k: v.clone().requires_grad_(True) for k, v in B.UNet(w["cin"], w["cout"]).state_dict().items()}
         x, y = make_batch(w, b, 7)

@@ -15,7 +15,7 @@ import torch
 from torch import nn
 
 from . import engine
-from .losses import BCEWithLogitsLoss, CrossEntropyLoss, F1Loss, IoULoss  # noqa: F401
+from .losses import BCEWithLogitsLoss, CrossEntropyLoss, F1Loss, IoULoss, SegmentationLoss  # noqa: F401
 
 try:  # HF-style wrappers keep the reference's base classes when transformers is importable
     from transformers import PretrainedConfig, PreTrainedModel
@@ -189,12 +189,16 @@ if PreTrainedModel is not None:
 
         def __init__(self, config: UNetConfig):
             super().__init__(config)
-            if config.unet_type != "UNet":
-                raise NotImplementedError(
-                    f"unet_type={config.unet_type!r}: the UNet 3+ family is outside this round's hot path "
-                    "(SURVEY.md §8f)")
-            self.unet = UNet(config.in_channels, config.out_channels)
-            self.criterion = CrossEntropyLoss() if config.out_channels > 1 else BCEWithLogitsLoss()
+            if config.unet_type == "UNet":
+                self.unet = UNet(config.in_channels, config.out_channels)
+                self.criterion = CrossEntropyLoss() if config.out_channels > 1 else BCEWithLogitsLoss()
+            elif config.unet_type in ("UNet_3Plus", "UNet_3Plus_DeepSup"):       # unet.py:1189-1196
+                from . import unet3plus
+                self.unet = getattr(unet3plus, config.unet_type)(config.in_channels, config.out_channels)
+                self.criterion = SegmentationLoss()
+            else:
+                raise NotImplementedError(f"unet_type={config.unet_type!r} (the reference knows UNet, "
+                                          "UNet_3Plus and UNet_3Plus_DeepSup, unet.py:1166-1168)")
 
         def _init_weights(self, module):  # keep PyTorch's default init, as the reference does
             return
@@ -202,6 +206,10 @@ if PreTrainedModel is not None:
         def forward(self, images: torch.Tensor, labels: Optional[torch.Tensor] = None):
             logits = self.unet(images)
             loss = None
-            if labels is not None:
+            if isinstance(logits, tuple):          # deep supervision: criterion summed over d1..d5 (:1203-1208)
+                if labels is not None:
+                    loss = sum(self.criterion(d, labels) for d in logits)
+                logits = logits[0]
+            elif labels is not None:
                 loss = self.criterion(logits, labels)
             return UNetModelOutput(loss=loss, logits=logits, labels=labels)

@@ -15,7 +15,11 @@ fuses them with one more conv + BN + ReLU.  On this path
   of the tensor they read (an encoder map feeds up to five branches),
 * the 3x3 output conv (320 -> n_classes) is padded to 16 output channels so it too runs on tensor cores.
 
-The deep-supervision / CGM variants (unet.py:454-1153) are not implemented here.
+``UNet_3Plus_DeepSup`` (unet.py:454-787) adds the deep-supervision heads: a 3x3 conv to n_classes on every
+decoder scale (hd1..hd4 and the bottleneck hd5), bilinearly up-sampled to the input size; it returns the
+tuple (d1, .., d5) of logits that ``UNetModel.forward`` (unet.py:1203-1208) sums the criterion over.  The
+class-guided variant ``UNet_3Plus_DeepSup_CGM`` (unet.py:795-1153: dropout + arg-max gate, not reachable
+from ``UNetConfig.unet_type``) is not implemented here.
 """
 from __future__ import annotations
 
@@ -50,13 +54,17 @@ def _branch_name(level: int, stage: int) -> str:
     return f"hd{level}_UT_hd{stage}"
 
 
-class UNet_3Plus(nn.Module):
-    """unet.py:136-446.  ``forward(inputs) -> logits`` (the sigmoid is commented out in the reference)."""
+class _UNet3PlusBody(nn.Module):
+    """Encoder + four full-scale decoder stages shared by UNet_3Plus (unet.py:136-333) and
+    UNet_3Plus_DeepSup (unet.py:454-662); modules are registered in the reference's order."""
+    HEAD_SCALES = (1,)           # output head i reads hd{i+1} and is up-sampled by HEAD_SCALES[i]
 
     def __init__(self, in_channels=3, n_classes=1, feature_scale=4, is_deconv=True, is_batchnorm=True):
         super().__init__()
         if not is_batchnorm:
-            raise NotImplementedError("UNet_3Plus(is_batchnorm=False) is outside the B200 path")
+            raise NotImplementedError(f"{type(self).__name__}(is_batchnorm=False) is outside the B200 path")
+        if n_classes > 16:
+            raise NotImplementedError(f"{type(self).__name__} with more than 16 classes")
         self.is_deconv, self.in_channels = is_deconv, in_channels
         self.is_batchnorm, self.feature_scale = is_batchnorm, feature_scale
         f = FILTERS
@@ -89,21 +97,53 @@ class UNet_3Plus(nn.Module):
             setattr(self, f"conv{stage}d_1", nn.Conv2d(self.UpChannels, self.UpChannels, 3, padding=1))
             setattr(self, f"bn{stage}d_1", nn.BatchNorm2d(self.UpChannels))
             setattr(self, f"relu{stage}d_1", nn.ReLU(inplace=True))
-        self.outconv1 = nn.Conv2d(self.UpChannels, n_classes, 3, padding=1)
+        self._make_heads(n_classes)
         for m in self.modules():
             _kaiming(m)
 
-    def forward(self, inputs: torch.Tensor) -> torch.Tensor:
+    def _make_heads(self, n_classes: int) -> None:
+        raise NotImplementedError
+
+    def _run(self, inputs: torch.Tensor):
         params = tuple(self.parameters())
         return _Net3PFunction.apply(self, inputs, *params)
 
 
+class UNet_3Plus(_UNet3PlusBody):
+    """unet.py:136-446.  ``forward(inputs) -> logits`` (the sigmoid is commented out in the reference)."""
+
+    def _make_heads(self, n_classes):
+        self.outconv1 = nn.Conv2d(self.UpChannels, n_classes, 3, padding=1)
+
+    def forward(self, inputs: torch.Tensor) -> torch.Tensor:
+        return self._run(inputs)[0]
+
+
+class UNet_3Plus_DeepSup(_UNet3PlusBody):
+    """unet.py:454-787.  ``forward(inputs) -> (d1, d2, d3, d4, d5)``: logits of the five scales, each
+    bilinearly up-sampled to the input size (:760-787; the sigmoids at :786 are commented out)."""
+    HEAD_SCALES = (1, 2, 4, 8, 16)
+
+    def _make_heads(self, n_classes):
+        self.upscore6 = nn.Upsample(scale_factor=32, mode="bilinear")
+        self.upscore5 = nn.Upsample(scale_factor=16, mode="bilinear")
+        self.upscore4 = nn.Upsample(scale_factor=8, mode="bilinear")
+        self.upscore3 = nn.Upsample(scale_factor=4, mode="bilinear")
+        self.upscore2 = nn.Upsample(scale_factor=2, mode="bilinear")
+        for i in range(1, 5):
+            setattr(self, f"outconv{i}", nn.Conv2d(self.UpChannels, n_classes, 3, padding=1))
+        self.outconv5 = nn.Conv2d(FILTERS[4], n_classes, 3, padding=1)
+
+    def forward(self, inputs: torch.Tensor):
+        return self._run(inputs)
+
+
 # ===================================================================================== executor
-def _spec(net: UNet_3Plus, prefix: str) -> engine.LayerSpec:
+def _spec(net: nn.Module, prefix: str) -> engine.LayerSpec:
     return engine.LayerSpec("cbr", getattr(net, prefix + "_conv"), batchnorm=getattr(net, prefix + "_bn"))
 
 
-def _forward(net: UNet_3Plus, images: torch.Tensor, training: bool, tape: Optional[dict]) -> CL:
+def _forward(net: "_UNet3PlusBody", images: torch.Tensor, training: bool, tape: Optional[dict]) -> Dict[int, CL]:
     if images.shape[2] % 16 or images.shape[3] % 16:
         raise ValueError("UNet_3Plus needs H and W divisible by 16 (the reference's torch.cat fails otherwise)")
     want = tape is not None
@@ -143,8 +183,8 @@ def _forward(net: UNet_3Plus, images: torch.Tensor, training: bool, tape: Option
         if want:
             tape[("fuse", stage)] = t
     if want:
-        tape["h"], tape["hd"] = h, hd
-    return hd[1]
+        tape["h"] = h
+    return hd
 
 
 def _pad16(w: torch.Tensor) -> torch.Tensor:
@@ -153,49 +193,64 @@ def _pad16(w: torch.Tensor) -> torch.Tensor:
 
 
 class _Net3PFunction(torch.autograd.Function):
+    """The whole network as one autograd node: returns one logits tensor per output head."""
+
     @staticmethod
-    def forward(ctx, net: UNet_3Plus, images: torch.Tensor, *params):
+    def forward(ctx, net: _UNet3PlusBody, images: torch.Tensor, *params):
         ops.require_cuda(images)
         need_grad = any(ctx.needs_input_grad)
         tape = {} if need_grad else None
+        outs, heads = [], []
         with torch.no_grad():
-            feat = _forward(net, images, net.training, tape)
-            oc = net.outconv1
-            ncls = oc.weight.shape[0]
-            if ncls > 16:
-                raise NotImplementedError("UNet_3Plus with more than 16 classes")
-            wp_fwd, wp_bwd, k = ops.conv_repack_weight(_pad16(oc.weight.detach()), need_bwd=need_grad)
-            bias = None if oc.bias is None else F.pad(oc.bias.detach().float(), (0, 16 - ncls)).contiguous()
-            y = ops.conv_fwd(feat, wp_fwd, k, bias, False, impl=engine.IMPL)
-            logits = ops.to_nchw(y.slice(0, ncls), False)
-        ctx.net, ctx.tape, ctx.feat, ctx.params = net, tape, feat, params
-        ctx.head = (wp_bwd, k, ncls)
-        return logits
+            hd = _forward(net, images, net.training, tape)
+            for i, scale in enumerate(net.HEAD_SCALES):
+                oc = getattr(net, f"outconv{i + 1}")
+                ncls = oc.weight.shape[0]
+                wp_fwd, wp_bwd, k = ops.conv_repack_weight(_pad16(oc.weight.detach()), need_bwd=need_grad)
+                bias = None if oc.bias is None else F.pad(oc.bias.detach().float(), (0, 16 - ncls)).contiguous()
+                y = ops.conv_fwd(hd[i + 1], wp_fwd, k, bias, False, impl=engine.IMPL)
+                if scale > 1:       # upscore{2..5}: the logits of a coarse scale, bilinearly to full size
+                    y = ops.bilinear_fwd(y, scale)
+                outs.append(ops.to_nchw(y.slice(0, ncls), False))
+                heads.append((oc, wp_bwd, k, ncls, scale))
+        ctx.net, ctx.tape, ctx.params = net, tape, params
+        ctx.hd = hd if need_grad else None
+        ctx.heads = heads
+        return tuple(outs)
 
     @staticmethod
-    def backward(ctx, dlogits):
+    def backward(ctx, *dlogits):
         net, tape = ctx.net, ctx.tape
         if tape is None:
             raise RuntimeError("backward through a forward that ran without grad")
         grads: engine.Grads = {}
-        wp_bwd, k, ncls = ctx.head
-        oc = net.outconv1
-        dy = ops.from_nchw(F.pad(dlogits.contiguous().float(), (0, 0, 0, 0, 0, 16 - ncls)))
-        dw, db = ops.conv_bwd_weight(ctx.feat, dy, k, (16,) + tuple(oc.weight.shape[1:]), impl=engine.IMPL,
-                                     bias_grad=True)
-        engine._acc(grads, oc.weight, dw[:ncls].contiguous())
-        if oc.bias is not None:
-            engine._acc(grads, oc.bias, db[:ncls].contiguous())
-        # hd1 is a ReLU output: fold its ReLU backward into this data gradient
-        g = ops.conv_bwd_data(dy, wp_bwd, k, mask=ctx.feat, impl=engine.IMPL)
-        h, hd = tape["h"], tape["hd"]
+        h, hd = tape["h"], ctx.hd
+        # d(loss)/d hd1..hd5 from the output heads.  Every hd is a ReLU output, so its ReLU backward is
+        # folded into the head's data gradient (mask = hd); a masked gradient may be summed with the raw
+        # gradients that arrive later, because masking is idempotent.
+        ghd: Dict[int, Optional[CL]] = {s: None for s in range(1, 6)}
+        for i, (oc, wp_bwd, k, ncls, scale) in enumerate(ctx.heads):
+            if dlogits[i] is None:
+                continue
+            dy = ops.from_nchw(F.pad(dlogits[i].contiguous().float(), (0, 0, 0, 0, 0, 16 - ncls)))
+            if scale > 1:
+                dy = ops.bilinear_bwd(dy, scale)
+            dw, db = ops.conv_bwd_weight(hd[i + 1], dy, k, (16,) + tuple(oc.weight.shape[1:]), impl=engine.IMPL,
+                                         bias_grad=True)
+            engine._acc(grads, oc.weight, dw[:ncls].contiguous())
+            if oc.bias is not None:
+                engine._acc(grads, oc.bias, db[:ncls].contiguous())
+            ghd[i + 1] = ops.conv_bwd_data(dy, wp_bwd, k, mask=hd[i + 1], impl=engine.IMPL)
         dh: Dict[int, Optional[CL]] = {lvl: None for lvl in range(1, 6)}     # d(loss)/d h1..h5 (h5 = hd5)
-        dhd: Dict[int, Optional[CL]] = {4: None, 3: None, 2: None}
+        dh[5] = ghd[5]
+        dhd: Dict[int, Optional[CL]] = {4: ghd[4], 3: ghd[3], 2: ghd[2]}
         cc = net.CatChannels
         for stage in (1, 2, 3, 4):
-            if stage > 1:
-                g = dhd[stage]
-            # g is premasked only for stage 1 (conv_bwd_data above); deeper stages accumulate raw gradients
+            g = ghd[1] if stage == 1 else dhd[stage]
+            if g is None:
+                raise RuntimeError("UNet 3+ backward without a gradient for the full-resolution output")
+            # only stage 1's gradient is fully masked (it has a single consumer, the head conv above);
+            # deeper stages have accumulated raw gradients from the bilinear branches
             dcat, pm, _ = engine.single_conv_bwd(g, tape[("fuse", stage)], grads, premasked=(stage == 1))
             for level in range(1, 6):
                 d, _, _ = engine.single_conv_bwd(dcat.slice((level - 1) * cc, cc), tape[("br", level, stage)],
@@ -214,5 +269,5 @@ class _Net3PFunction(torch.autograd.Function):
             if lvl > 1:   # h[lvl-1] is a ReLU output: the pool backward masks the summed gradient by it
                 d = ops.maxpool_bwd(h[lvl - 1], d, 1, add=dh[lvl - 1], mask_relu=True)
                 pm = True
-        ctx.tape = ctx.feat = None
+        ctx.tape = ctx.hd = None
         return (None, None) + tuple(grads.get(p) if p.requires_grad else None for p in ctx.params)

@@ -239,6 +239,37 @@ def gen_unet3plus(ns):
     print("unet3plus_3_1", float(loss), logits.abs().max().item())
 
 
+def gen_unet3plus_deepsup(ns):
+    """UNet_3Plus_DeepSup (unet.py:454-787) through the reference's own UNetModel-style loss sum
+    (unet.py:1203-1208) with BCE as the criterion: the five per-scale logits, the summed loss, gradient
+    norms of every parameter and the gradients of the five output convs' biases + two small tensors."""
+    from oracle import unet3plus as O3
+    torch.manual_seed(0)
+    net = ns.U2.UNet_3Plus_DeepSup(3, 1)
+    sd = {k: v.clone() for k, v in net.state_dict().items()}
+    O3.fill_state_dict_(sd, 11)
+    net.load_state_dict(sd)
+    net.train()
+    g = torch.Generator().manual_seed(31)
+    x = torch.randn((2, 3, 32, 32), generator=g)
+    y = blob_target((2, 1, 32, 32), 32)
+    ds = net(x)
+    bce = torch.nn.BCEWithLogitsLoss()
+    loss = sum(bce(d, y) for d in ds)
+    loss.backward()
+    names = [k for k, _ in net.named_parameters()]
+    grads = dict(net.named_parameters())
+    out = dict(seed=11, x=_np(x), y=_np(y), loss=_np(loss), grad_names=np.array(names),
+               grad_norms=np.array([p.grad.norm().item() for _, p in net.named_parameters()]),
+               state_dict_keys=np.array(list(net.state_dict().keys())))
+    for i, d in enumerate(ds):
+        out[f"d{i + 1}"] = _np(d)
+    for k in [f"outconv{i}.bias" for i in range(1, 6)] + ["outconv5.weight", "bn4d_1.weight"]:
+        out["grad::" + k] = _np(grads[k].grad)
+    np.savez_compressed(os.path.join(OUT, "unet3plus_deepsup_3_1.npz"), **out)
+    print("unet3plus_deepsup_3_1", float(loss), [float(d.abs().max()) for d in ds])
+
+
 def main():
     torch.set_num_threads(8)
     os.makedirs(OUT, exist_ok=True)
@@ -249,6 +280,7 @@ def main():
     gen_blocks(ns)
     gen_losses_metrics(ns)
     gen_unet3plus(ns)
+    gen_unet3plus_deepsup(ns)
 
 
 if __name__ == "__main__":

@@ -40,11 +40,14 @@ def conv_bn_relu(sd: SD, conv: str, bn: str, x: torch.Tensor, training: bool, em
     return _bf(x) if emulate_bf16 else x
 
 
-def unet3plus_forward(sd: SD, x: torch.Tensor, training: bool = True, emulate_bf16: bool = False) -> torch.Tensor:
+def unet3plus_forward(sd: SD, x: torch.Tensor, training: bool = True, emulate_bf16: bool = False,
+                      deep_sup: bool = False):
     """unet.py:335-446: encoder (unetConv2 + MaxPool2d(2)) -> four full-scale decoder stages -> 3x3 output
     conv; returns logits (the sigmoid at :445 is commented out).  ``emulate_bf16`` rounds weights and every
     stored activation to bf16 where the B200 path stores bf16 (fp32 accumulation kept): the yardstick that
-    separates storage-precision noise — large for random weights on a 19-layer BatchNorm net — from bugs."""
+    separates storage-precision noise — large for random weights on a 19-layer BatchNorm net — from bugs.
+    ``deep_sup``: UNet_3Plus_DeepSup (unet.py:454-787) — the tuple (d1..d5) of per-scale logits, each
+    bilinearly up-sampled to the input size."""
     h = {}
     for lvl in range(1, 6):
         if lvl > 1:
@@ -72,8 +75,18 @@ def unet3plus_forward(sd: SD, x: torch.Tensor, training: bool = True, emulate_bf
             parts.append(conv_bn_relu(sd, name + "_conv", name + "_bn", src, training, emulate_bf16))
         hd[stage] = conv_bn_relu(sd, f"conv{stage}d_1", f"bn{stage}d_1", torch.cat(parts, 1), training,
                                  emulate_bf16)
-    wo = _bf(sd["outconv1.weight"]) if emulate_bf16 else sd["outconv1.weight"]
-    return F.conv2d(hd[1], wo, sd["outconv1.bias"], padding=1)
+    def head(i):
+        w = sd[f"outconv{i}.weight"]
+        y = F.conv2d(hd[i], _bf(w) if emulate_bf16 else w, sd[f"outconv{i}.bias"], padding=1)
+        return _bf(y) if emulate_bf16 else y
+
+    if not deep_sup:
+        return head(1)
+    outs = [head(1)]                                                           # unet.py:760-787
+    for i in range(2, 6):
+        y = F.interpolate(head(i), scale_factor=2 ** (i - 1), mode="bilinear")
+        outs.append(_bf(y) if emulate_bf16 else y)
+    return tuple(outs)
 
 
 def fill_state_dict_(sd: SD, seed: int) -> None:

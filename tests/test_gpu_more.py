@@ -434,3 +434,57 @@ def test_unet3plus_trained_parity(B):
         ev = net(x.cuda()).cpu()
     assert rel_l2(ev, ref_eval) < 2e-2, rel_l2(ev, ref_eval)
     _mask_agreement(ev, ref_eval, overall=0.99)   # 30 steps of running statistics: many logits near 0
+
+
+def test_unet3plus_deepsup_vs_reference_golden(B):
+    """UNet_3Plus_DeepSup (unet.py:454-787) through UNetModel's loss sum over the five heads
+    (unet.py:1203-1208): per-scale logits and loss against the reference's own run; gradients against the
+    fp32 reference and the bf16-storage emulation (random weights: the bounds of the UNet 3+ golden test)."""
+    from conftest import load_golden
+    from oracle import unet3plus as O3
+    fix = load_golden("unet3plus_deepsup_3_1")
+    net = B.UNet_3Plus_DeepSup(3, 1)
+    sd = {k: v.clone() for k, v in net.state_dict().items()}
+    assert list(sd.keys()) == [str(k) for k in fix["state_dict_keys"]]
+    O3.fill_state_dict_(sd, int(fix["seed"]))
+    net.load_state_dict(sd)
+    net = net.cuda().train()
+    x, y = torch.from_numpy(fix["x"]).cuda(), torch.from_numpy(fix["y"]).cuda()
+    ds = net(x)
+    assert isinstance(ds, tuple) and len(ds) == 5
+    sd_e = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and "running" not in k else v.clone())
+            for k, v in sd.items()}
+    emu = O3.unet3plus_forward(sd_e, x.cpu(), training=True, emulate_bf16=True, deep_sup=True)
+    errs = [(rel_l2(d.detach().cpu(), fix[f"d{i + 1}"]), rel_l2(d.detach().cpu(), emu[i].detach())) for i, d in enumerate(ds)]
+    print("UNet3+ DeepSup logits rel-L2 per head (vs fp32 reference, vs bf16 emulation):", errs)
+    crit = B.BCEWithLogitsLoss()
+    loss = sum(crit(d, y) for d in ds)
+    assert all(a < 1e-1 and b < 5e-2 for a, b in errs), errs
+    assert abs(loss.item() - float(fix["loss"])) < 3e-2
+    loss.backward()
+    sum(torch.nn.functional.binary_cross_entropy_with_logits(e, y.cpu()) for e in emu).backward()
+    grads = dict(net.named_parameters())
+    gnorm = float(np.sqrt((fix["grad_norms"] ** 2).sum()))
+    for k, v in fix.items():
+        if k.startswith("grad::"):
+            mine = grads[k[6:]].grad.cpu()
+            e_ref, e_emu = (mine - torch.from_numpy(v)).norm().item(), (mine - sd_e[k[6:]].grad).norm().item()
+            assert e_ref < 0.25 * np.linalg.norm(v) + 1e-2 * gnorm, (k, e_ref, np.linalg.norm(v))
+            assert e_emu < 0.15 * np.linalg.norm(v) + 1e-2 * gnorm, (k, e_emu, np.linalg.norm(v))
+    names = [str(s) for s in fix["grad_names"]]
+    mine = torch.cat([grads[k].grad.flatten().cpu() for k in names])
+    emug = torch.cat([sd_e[k].grad.flatten() for k in names])
+    norms = np.array([grads[k].grad.norm().item() for k in names])
+    dev = np.abs(norms - fix["grad_norms"]) / (0.3 * fix["grad_norms"] + 2e-3 * gnorm)
+    print(f"UNet3+ DeepSup all-parameter gradient vs bf16 emulation: rel-L2 {rel_l2(mine, emug):.4f}; worst per-tensor "
+          f"norm deviation {dev.max():.3f} of its bound ({names[int(dev.argmax())]})")
+    assert rel_l2(mine, emug) < 0.3, rel_l2(mine, emug)
+    assert dev.max() < 1.0, (names[int(dev.argmax())], dev.max())
+    # the HF-style wrapper: unet_type="UNet_3Plus_DeepSup" sums the criterion over the tuple, logits = d1
+    model = B.UNetModel(B.UNetConfig(3, 1, "UNet_3Plus_DeepSup"))
+    model.unet.load_state_dict(sd)
+    model = model.cuda().train()
+    out = model(images=x, labels=y)
+    assert out.logits.shape == ds[0].shape and torch.isfinite(out.loss)
+    out.loss.backward()
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in model.parameters())

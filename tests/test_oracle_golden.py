@@ -147,12 +147,12 @@ def test_analytic_known_answers():
     assert abs(O.dice_loss(-big, m).item() - 1.0) < 1e-6          # disjoint masks -> dice 0
 
 
-def _unet3plus_sd(seed, requires_grad=True):
+def _unet3plus_sd(seed, requires_grad=True, deep_sup=False):
     """UNet 3+ weights of the fixture: the product module's state_dict layout (checked against the
     reference's key list stored in the fixture) filled by oracle.unet3plus.fill_state_dict_(seed)."""
-    from mdeical_image_segmentation_b200.unet3plus import UNet_3Plus
+    from mdeical_image_segmentation_b200.unet3plus import UNet_3Plus, UNet_3Plus_DeepSup
     from oracle import unet3plus as O3
-    sd = {k: v.clone() for k, v in UNet_3Plus(3, 1).state_dict().items()}
+    sd = {k: v.clone() for k, v in (UNet_3Plus_DeepSup if deep_sup else UNet_3Plus)(3, 1).state_dict().items()}
     O3.fill_state_dict_(sd, seed)
     if requires_grad:
         sd = {k: (v.requires_grad_(True) if v.is_floating_point() and "running" not in k else v) for k, v in sd.items()}
@@ -173,6 +173,29 @@ def test_unet3plus_matches_reference():
     assert abs(loss.item() - float(fix["loss"])) < 1e-5
     assert rel_l2(sd["bn1d_1.running_mean"], fix["running_mean_bn1d_1"]) < 1e-4
     assert rel_l2(sd["conv1.conv1.1.running_var"], fix["running_var_conv1"]) < 1e-4
+    loss.backward()
+    names = [str(s) for s in fix["grad_names"]]
+    l2 = np.array([sd[k].grad.norm().item() for k in names])
+    np.testing.assert_allclose(l2, fix["grad_norms"], rtol=5e-3, atol=1e-6)
+    for k, v in fix.items():
+        if k.startswith("grad::"):
+            assert rel_l2(sd[k[6:]].grad, v) < 2e-3, k
+
+
+def test_unet3plus_deepsup_matches_reference():
+    """UNet_3Plus_DeepSup (unet.py:454-787): the five per-scale logits, the summed BCE loss
+    (unet.py:1203-1208) and the gradients of the oracle against the reference's own run."""
+    from oracle import unet3plus as O3
+    fix = load_golden("unet3plus_deepsup_3_1")
+    sd = _unet3plus_sd(int(fix["seed"]), deep_sup=True)
+    assert list(sd.keys()) == [str(k) for k in fix["state_dict_keys"]]
+    x, y = torch.from_numpy(fix["x"]), torch.from_numpy(fix["y"])
+    ds = O3.unet3plus_forward(sd, x, training=True, deep_sup=True)
+    assert len(ds) == 5
+    for i, d in enumerate(ds):
+        assert rel_l2(d, fix[f"d{i + 1}"]) < TOL, i
+    loss = sum(torch.nn.functional.binary_cross_entropy_with_logits(d, y) for d in ds)
+    assert abs(loss.item() - float(fix["loss"])) < 1e-5
     loss.backward()
     names = [str(s) for s in fix["grad_names"]]
     l2 = np.array([sd[k].grad.norm().item() for k in names])
