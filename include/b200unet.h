@@ -168,11 +168,12 @@ int b200_maxpoolk_fwd(int32_t n, int32_t h, int32_t w, int32_t c, int32_t k, b20
 int b200_maxpoolk_bwd(int32_t n, int32_t h, int32_t w, int32_t c, int32_t k, b200_view x, b200_view dy,
                       b200_view add, b200_view dx, b200_stream_t stream);
 /* nn.Upsample(scale_factor=scale, mode='bilinear') unet.py:198-315 (align_corners=False): (n, ih, iw, c)
- * -> (n, ih*scale, iw*scale, c); bwd is its exact adjoint as a deterministic gather (+ add, may be NULL) */
+ * -> (n, ih*scale, iw*scale, c); bwd is its exact adjoint, separable (along W into scratch, then along H),
+ * deterministic, + add (ptr may be NULL).  scratch: n * ih*scale * iw * c floats, 16-byte aligned, caller-owned. */
 int b200_bilinear2d_fwd(int32_t n, int32_t ih, int32_t iw, int32_t c, int32_t scale, b200_view x,
                         b200_view y, b200_stream_t stream);
 int b200_bilinear2d_bwd(int32_t n, int32_t ih, int32_t iw, int32_t c, int32_t scale, b200_view dy,
-                        b200_view add, b200_view dx, b200_stream_t stream);
+                        b200_view add, b200_view dx, void* scratch, b200_stream_t stream);
 /* dst += src: gradient accumulation for tensors that feed several full-scale skip branches */
 int b200_add(int64_t npos, int32_t c, b200_view src, b200_view dst, b200_stream_t stream);
 

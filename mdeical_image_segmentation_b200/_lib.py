@@ -73,7 +73,7 @@ SIGNATURES = {
     "b200_maxpoolk_fwd": [_I, _I, _I, _I, _I, View, View, _P],
     "b200_maxpoolk_bwd": [_I, _I, _I, _I, _I, View, View, View, View, _P],
     "b200_bilinear2d_fwd": [_I, _I, _I, _I, _I, View, View, _P],
-    "b200_bilinear2d_bwd": [_I, _I, _I, _I, _I, View, View, View, _P],
+    "b200_bilinear2d_bwd": [_I, _I, _I, _I, _I, View, View, View, _P, _P],
     "b200_add": [_L, _I, View, View, _P],
     "b200_im2col3": [_I, _I, _I, _I, _I, _I, _I, View, _P, _P],
     "b200_nchw_f32_to_cl_bf16": [_I, _I, _L, _P, View, _P],

@@ -354,8 +354,9 @@ def bilinear_fwd(x: CL, scale: int) -> CL:
 
 def bilinear_bwd(dy: CL, scale: int, add: Optional[CL] = None) -> CL:
     out = CL.empty(dy.n, 1, dy.h // scale, dy.w // scale, dy.c, dy.device)
+    scratch = torch.empty((dy.n, dy.h, out.w, dy.c), dtype=torch.float32, device=dy.device)   # W-reduced dy
     call("b200_bilinear2d_bwd", dy.n, out.h, out.w, dy.c, scale, dy.view(),
-         _NULL_VIEW if add is None else add.view(), out.view(), _stream())
+         _NULL_VIEW if add is None else add.view(), out.view(), _p(scratch), _stream())
     return out
 
 

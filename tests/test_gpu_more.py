@@ -268,8 +268,10 @@ def test_unet3plus_ops_vs_aten(B):
         ref.backward(gy)
         dx = ops.to_nchw(ops.maxpoolk_bwd(xc, ops.from_nchw(gy.cuda()), k, add=ops.from_nchw(add.cuda())), False).cpu()
         assert torch.equal(dx, x.grad + add)          # ties (many here) go to the first maximum, as ATen
-    for s in (2, 4, 16):
-        x = torch.randn((2, 8, 4, 6), generator=g).bfloat16().float().requires_grad_(True)
+    # (scale, input shape): tiny planes, several runs per line along both axes (40 / 24 outputs), odd scale
+    for s, shp in ((2, (2, 8, 4, 6)), (4, (2, 8, 4, 6)), (16, (2, 8, 4, 6)), (2, (1, 16, 40, 24)), (4, (2, 8, 24, 40)),
+                   (3, (1, 8, 17, 9)), (8, (1, 24, 9, 17))):
+        x = torch.randn(shp, generator=g).bfloat16().float().requires_grad_(True)
         ref = F.interpolate(x, scale_factor=s, mode="bilinear")
         out = ops.to_nchw(ops.bilinear_fwd(ops.from_nchw(x.detach().cuda()), s), False).cpu()
         assert (out - ref.detach()).abs().max() < 2e-2 * ref.abs().max()      # one bf16 rounding of the result
