@@ -505,7 +505,8 @@ def run_cpu_sample(w, steps, warmup, batch=None):
         sd = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and "running" not in k else v.clone())
               for k, v in net.state_dict().items()}
         x, y = make_batch(dict(w, size=(256, 256)), b, 7)
-        seg = lambda lo: O.f1_loss(lo, y) + O.iou_loss(lo, y)  # noqa: E731
+        from oracle.msssim import segmentation_loss
+        seg = lambda lo: segmentation_loss(lo, y)  # noqa: E731  (F1 + MS-SSIM + IoU, loss.py:59-70)
 
         def fwd():
             out = O3.unet3plus_forward(sd, x, training=True, deep_sup=deep)

@@ -288,6 +288,21 @@ int b200_ce_fwd(int32_t n, int32_t c, int64_t spatial, const float* logits, cons
 int b200_ce_bwd(int32_t n, int32_t c, int64_t spatial, const float* logits, const int64_t* labels,
                 const float* scale, float* dlogits, b200_stream_t stream);
 
+/* ---- MS-SSIM term of SegmentationLoss (model/unet2d/loss.py:21-28 -> pytorch-msssim==1.0.0 MS_SSIM(data_range,
+ * channel=1), requirements.txt:127) on sigmoid(logits) vs targets, both fp32 (n, 1, h, w); min(h, w) > 160 as the
+ * package asserts.  A pyramid buffer holds the 5 scales of one image stack packed back to back:
+ * b200_msssim_pyramid_floats(n, h, w) floats (negative = unsupported shape); all buffers are caller-owned.
+ * fwd: fills pyr_x / pyr_y and sums (fp64 [5][n], zeroed inside): per sample the SUM over valid positions of the
+ *      cs map (scales 0-3) / ssim map (scale 4); valid positions of scale l = (h_l - 10) * (w_l - 10),
+ *      h_{l+1} = ceil(h_l / 2).
+ * bwd: gmeans fp32 [5][n] = d(loss)/d(per-sample MEAN of each scale's map) read from device memory;
+ *      pyr_dx = scratch pyramid; dlogits (n, 1, h, w) fully written. */
+int64_t b200_msssim_pyramid_floats(int32_t n, int32_t h, int32_t w);
+int b200_msssim_fwd(int32_t n, int32_t h, int32_t w, const float* logits, const float* targets, float* pyr_x,
+                    float* pyr_y, double* sums, float data_range, b200_stream_t stream);
+int b200_msssim_bwd(int32_t n, int32_t h, int32_t w, const float* pyr_x, const float* pyr_y, const float* gmeans,
+                    float* pyr_dx, float* dlogits, float data_range, b200_stream_t stream);
+
 /* ---- metrics -----------------------------------------------------------------------------------
  * trainer/metrcis.py:61-109,153-168: p = 1/(1+exp(-x)+1e-6); psum (fp64 [1]) += sum p */
 int b200_metric_prob_sum(int64_t numel, const float* logits, double* psum, b200_stream_t stream);

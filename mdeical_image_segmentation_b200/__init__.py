@@ -5,7 +5,7 @@ kernels) behind a C ABI (``include/b200unet.h``).  There is no CPU / PyTorch-eag
 from . import _lib, metrics  # noqa: F401
 from .graph import GraphedInference
 from .unet3plus import UNet_3Plus, UNet_3Plus_DeepSup
-from .losses import (BCEDiceLoss, BCEWithLogitsLoss, CrossEntropyLoss, DiceLoss, F1Loss, IoULoss,
+from .losses import (BCEDiceLoss, BCEWithLogitsLoss, CrossEntropyLoss, DiceLoss, F1Loss, IoULoss, MSSSIMLoss,
                      SegmentationLoss, compute_per_channel_dice, flatten, get_loss_criterion)
 from .unet2d import (CropAndConcat, DoubleConvolution, DownSample, UNet, UpSample, unetConv2)
 from .unet3d import (AbstractUNet, Decoder, DoubleConv, Encoder, SingleConv, UNet2D, UNet3D,

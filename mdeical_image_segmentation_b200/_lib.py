@@ -75,6 +75,8 @@ SIGNATURES = {
     "b200_bilinear2d_fwd": [_I, _I, _I, _I, _I, View, View, _P],
     "b200_bilinear2d_bwd": [_I, _I, _I, _I, _I, View, View, View, _P, _P],
     "b200_add": [_L, _I, View, View, _P],
+    "b200_msssim_fwd": [_I, _I, _I, _P, _P, _P, _P, _P, _F, _P],
+    "b200_msssim_bwd": [_I, _I, _I, _P, _P, _P, _P, _P, _F, _P],
     "b200_im2col3": [_I, _I, _I, _I, _I, _I, _I, View, _P, _P],
     "b200_nchw_f32_to_cl_bf16": [_I, _I, _L, _P, View, _P],
     "b200_cl_bf16_to_nchw_f32": [_I, _I, _L, View, _P, _P],
@@ -100,6 +102,7 @@ _SPECIAL = {
     "b200_strerror": ([C.c_int], C.c_char_p),
     "b200_last_impl": ([], C.c_int),
     "b200_set_tuning": ([C.c_int, C.c_int], C.c_int),
+    "b200_msssim_pyramid_floats": ([_I, _I, _I], C.c_int64),
 }
 ALL_SYMBOLS = sorted(list(SIGNATURES) + list(_SPECIAL))
 

@@ -310,6 +310,55 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// Forward for power-of-two scales (all the network uses): one thread per (source CELL, 8-channel vector).  Cell
+// (cy, cx), cy in [-1, ih-1], holds the S x S outputs whose lower source index is (cy, cx) (border cells are
+// half-size and collapse onto one source row / column): 4 corner loads feed S*S stores, the vertical lerp is done
+// once per output row, column weights are compile-time constants.  ~30 instructions per 16-byte store instead of
+// ~110, and 4/S^2 loads per output instead of 4.
+template <int S>
+__global__ void __launch_bounds__(256)
+    bilinear2d_fwd_cell_kernel(int n, int ih, int iw, int c, View x, View y) {
+  const int oh = ih * S, ow = iw * S, cv = c / 8;
+  const long total = (long)n * (ih + 1) * (iw + 1) * cv;
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  long r = i;
+  const int ch = (int)(r % cv) * 8; r /= cv;
+  const int cx = (int)(r % (iw + 1)) - 1; r /= (iw + 1);
+  const int cy = (int)(r % (ih + 1)) - 1;
+  const long b = r / (ih + 1);
+  const int h0 = cy < 0 ? 0 : cy, h1 = cy + 1 < ih ? cy + 1 : ih - 1;
+  const int w0 = cx < 0 ? 0 : cx, w1 = cx + 1 < iw ? cx + 1 : iw - 1;
+  const bool ey = h0 == h1, ex = w0 == w1;     // border cell (or a 1-pixel axis): a single source row / column
+  float a00[8], a01[8], a10[8], a11[8];
+  Vec<8>::load(x.at((b * ih + h0) * iw + w0, ch), a00);
+  Vec<8>::load(x.at((b * ih + h0) * iw + w1, ch), a01);
+  Vec<8>::load(x.at((b * ih + h1) * iw + w0, ch), a10);
+  Vec<8>::load(x.at((b * ih + h1) * iw + w1, ch), a11);
+  for (int ty = 0; ty < S; ++ty) {
+    const int oy = S * cy + S / 2 + ty;
+    if (oy < 0 || oy >= oh) continue;
+    const float hl1 = ey ? 0.f : ((float)ty + 0.5f) * (1.f / S), hl0 = 1.f - hl1;
+    float l[8], rr[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      l[q] = hl0 * a00[q] + hl1 * a10[q];
+      rr[q] = hl0 * a01[q] + hl1 * a11[q];
+    }
+    const long orow = (b * oh + oy) * ow;
+#pragma unroll
+    for (int tx = 0; tx < S; ++tx) {
+      const int ox = S * cx + S / 2 + tx;
+      if (ox < 0 || ox >= ow) continue;
+      const float wl1 = ex ? 0.f : ((float)tx + 0.5f) * (1.f / S), wl0 = 1.f - wl1;
+      float o[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) o[q] = wl0 * l[q] + wl1 * rr[q];
+      Vec<8>::store(y.at(orow + ox, ch), o);
+    }
+  }
+}
+
 // Backward = the exact adjoint, separable: first along W (dy bf16 -> fp32 scratch [n*oh][iw][c]), then along H
 // (scratch -> dx bf16, + add).  Each pass is ONE sequential walk along the axis per thread: source index i0 is
 // non-decreasing in the destination index, so a two-entry register window (sums for out[j] and out[j+1]) slides
@@ -1272,7 +1321,21 @@ int b200_bilinear2d_fwd(int32_t n, int32_t ih, int32_t iw, int32_t c, int32_t sc
   const long rows = (long)n * ih * scale;
   if (rows <= 0 || iw <= 0) return B200_OK;
   if (rows > 0x7fffffffL) return B200_ERR_UNSUPPORTED;
-  bilinear2d_fwd_kernel<<<(unsigned)rows, 256, 0, (cudaStream_t)stream>>>(n, ih, iw, c, scale, mk(x), mk(y));
+  const long cells = (long)n * (ih + 1) * (iw + 1) * (c / 8);
+#define BILINEAR_CELL(S_)                                                                                         \
+  case S_:                                                                                                        \
+    bilinear2d_fwd_cell_kernel<S_><<<blocks_for(cells, 256), 256, 0, (cudaStream_t)stream>>>(n, ih, iw, c, mk(x), \
+                                                                                             mk(y));              \
+    break;
+  switch (scale) {
+    BILINEAR_CELL(2)
+    BILINEAR_CELL(4)
+    BILINEAR_CELL(8)
+    BILINEAR_CELL(16)
+    default:
+      bilinear2d_fwd_kernel<<<(unsigned)rows, 256, 0, (cudaStream_t)stream>>>(n, ih, iw, c, scale, mk(x), mk(y));
+  }
+#undef BILINEAR_CELL
   B200_LAUNCH_CHECK();
   return B200_OK;
 }

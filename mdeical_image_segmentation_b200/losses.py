@@ -167,18 +167,57 @@ class F1Loss(nn.Module):
         return (1 - 2 * (precision * recall) / (precision + recall + self.epsilon)).float()
 
 
+class _MSSSIMMeans(torch.autograd.Function):
+    """(5, n) per-sample means of the MS-SSIM scale maps of (sigmoid(logits), targets)."""
+
+    @staticmethod
+    def forward(ctx, logits: torch.Tensor, targets: torch.Tensor, data_range: float):
+        logits = logits.contiguous().float()
+        targets = targets.contiguous().float()
+        sums, pyr_x, pyr_y = ops.msssim_fwd(logits, targets, data_range)
+        ctx.save_for_backward(pyr_x, pyr_y)
+        ctx.shape, ctx.data_range = tuple(logits.shape), data_range
+        counts = torch.tensor(ops.msssim_valid_counts(logits.shape[2], logits.shape[3]), dtype=torch.float64)
+        return (sums / counts.to(sums.device)[:, None]).float()
+
+    @staticmethod
+    def backward(ctx, gmeans):
+        pyr_x, pyr_y = ctx.saved_tensors
+        return ops.msssim_bwd(ctx.shape, pyr_x, pyr_y, gmeans, ctx.data_range), None, None
+
+
+MS_SSIM_WEIGHTS = (0.0448, 0.2856, 0.3001, 0.2363, 0.1333)
+
+
+class MSSSIMLoss(nn.Module):
+    """model/unet2d/loss.py:21-28: ``1 - MS_SSIM(data_range=1.0, size_average=True, channel=1)(sigmoid(x), t)``
+    (pytorch-msssim==1.0.0).  The filtering, the scale pyramid and their adjoints run in
+    ``b200_msssim_fwd/bwd``; the five numbers per sample are combined here exactly as the package does
+    (ReLU, weights as exponents, product over scales, batch mean)."""
+
+    def __init__(self, data_range: float = 1.0):
+        super().__init__()
+        self.data_range = data_range
+
+    def forward(self, inputs, targets):
+        if inputs.shape != targets.shape:
+            raise ValueError("Input images should have the same dimensions.")
+        means = _MSSSIMMeans.apply(inputs, targets, self.data_range)          # (5, n)
+        weights = means.new_tensor(MS_SSIM_WEIGHTS).view(-1, 1)
+        ms_ssim_val = torch.prod(torch.relu(means) ** weights, dim=0)
+        return 1 - ms_ssim_val.mean()
+
+
 class SegmentationLoss(nn.Module):
     """model/unet2d/loss.py:59-70: ``F1 + MS-SSIM + IoU``.  The F1 and IoU terms come out of ONE pass over
-    the logits (the six-sum kernel); the MS-SSIM term is computed by the third-party ``pytorch_msssim``
-    package in the reference (loss.py:3-4,21-28), which is outside the B200 hot path:
-    pass ``ms_ssim_loss`` (any ``nn.Module`` taking (logits, targets)) to add it, otherwise the
-    criterion is the sum of the two reduction terms."""
+    the logits (the six-sum kernel), the MS-SSIM term from ``MSSSIMLoss``.  ``ms_ssim=False`` drops that
+    term (images not larger than 160 pixels, where the reference's package asserts), ``ms_ssim_loss`` replaces it."""
 
-    def __init__(self, ms_ssim_loss: Optional[nn.Module] = None, epsilon: float = 1e-7):
+    def __init__(self, ms_ssim_loss: Optional[nn.Module] = None, epsilon: float = 1e-7, ms_ssim: bool = True):
         super().__init__()
         self.f1_loss = F1Loss(epsilon)
         self.iou_loss = IoULoss(epsilon)
-        self.ms_ssim_loss = ms_ssim_loss
+        self.ms_ssim_loss = ms_ssim_loss if ms_ssim_loss is not None else (MSSSIMLoss() if ms_ssim else None)
         self.epsilon = epsilon
 
     def forward(self, inputs, targets):

@@ -556,6 +556,44 @@ def seg_sums(logits: torch.Tensor, target: torch.Tensor, normalization: int = 0)
     return sums
 
 
+def msssim_valid_counts(h: int, w: int):
+    """Valid positions (h_l - 10) * (w_l - 10) of the 5 MS-SSIM scales, h_{l+1} = ceil(h_l / 2)."""
+    out = []
+    for _ in range(5):
+        out.append((h - 10) * (w - 10))
+        h, w = (h + 1) // 2, (w + 1) // 2
+    return out
+
+
+def msssim_fwd(logits: torch.Tensor, target: torch.Tensor, data_range: float = 1.0):
+    """(5, n) fp64 per-sample SUMS of the cs maps (scales 0-3) / ssim map (scale 4) of
+    MS-SSIM(sigmoid(logits), target), plus the two image pyramids the backward pass re-reads."""
+    require_cuda(logits)
+    n, c, h, w = logits.shape
+    if c != 1:
+        raise NotImplementedError("MS-SSIM of the B200 path is single-channel (MS_SSIM(channel=1), loss.py:24)")
+    floats = _lib.lib().b200_msssim_pyramid_floats(n, h, w)
+    if floats < 0:
+        raise ValueError(f"MS-SSIM needs min(H, W) > 160 (pytorch_msssim's assertion); got {h}x{w}")
+    pyr_x = torch.empty(floats, dtype=torch.float32, device=logits.device)
+    pyr_y = torch.empty(floats, dtype=torch.float32, device=logits.device)
+    sums = torch.empty((5, n), dtype=torch.float64, device=logits.device)
+    call("b200_msssim_fwd", n, h, w, _p(logits), _p(target), _p(pyr_x), _p(pyr_y), _p(sums), float(data_range),
+         _stream())
+    return sums, pyr_x, pyr_y
+
+
+def msssim_bwd(shape, pyr_x: torch.Tensor, pyr_y: torch.Tensor, gmeans: torch.Tensor,
+               data_range: float = 1.0) -> torch.Tensor:
+    n, _, h, w = shape
+    gmeans = gmeans.contiguous().float()
+    pyr_dx = torch.empty_like(pyr_x)
+    out = torch.empty(shape, dtype=torch.float32, device=pyr_x.device)
+    call("b200_msssim_bwd", n, h, w, _p(pyr_x), _p(pyr_y), _p(gmeans), _p(pyr_dx), _p(out), float(data_range),
+         _stream())
+    return out
+
+
 def seg_loss_bwd(logits: torch.Tensor, target: torch.Tensor, coef: torch.Tensor,
                  normalization: int = 0) -> torch.Tensor:
     n, c = logits.shape[0], logits.shape[1]

@@ -486,7 +486,43 @@ def test_unet3plus_deepsup_vs_reference_golden(B):
     model = B.UNetModel(B.UNetConfig(3, 1, "UNet_3Plus_DeepSup"))
     model.unet.load_state_dict(sd)
     model = model.cuda().train()
+    with pytest.raises(ValueError):            # 32 x 32: the MS-SSIM term needs sides > 160 (the package asserts)
+        model(images=x, labels=y)
+    model.criterion = B.SegmentationLoss(ms_ssim=False)
     out = model(images=x, labels=y)
     assert out.logits.shape == ds[0].shape and torch.isfinite(out.loss)
     out.loss.backward()
     assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in model.parameters())
+
+
+def test_msssim_and_segmentation_loss_vs_oracle(B):
+    """MS-SSIM term (loss.py:21-28, pytorch-msssim 1.0.0 restated in oracle/msssim.py) and the full
+    SegmentationLoss = F1 + MS-SSIM + IoU (loss.py:59-70): value within 1e-5, d(loss)/d(logits) within 1e-4
+    relative, on even, odd (padded average pools) and non-square sizes; identical images give exactly 0."""
+    from oracle import msssim as OMS
+    g = torch.Generator().manual_seed(3)
+    for shape in ((2, 1, 176, 192), (1, 1, 161, 173), (3, 1, 256, 168)):
+        from test_gpu_parity import _blob_task
+        _, t = _blob_task(shape, 50 + shape[2])
+        x = (3.0 * (t - 0.5) + torch.randn(shape, generator=g)).requires_grad_(True)
+        ref = OMS.msssim_loss(x, t)
+        ref.backward()
+        xd = x.detach().cuda().requires_grad_(True)
+        out = B.MSSSIMLoss()(xd, t.cuda())
+        out.backward()
+        assert abs(out.item() - ref.item()) < 1e-5, (shape, out.item(), ref.item())
+        assert rel_l2(xd.grad.cpu(), x.grad) < 1e-4, (shape, rel_l2(xd.grad.cpu(), x.grad))
+        x.grad = None
+        ref = OMS.segmentation_loss(x, t)
+        ref.backward()
+        xd = x.detach().cuda().requires_grad_(True)
+        out = B.SegmentationLoss()(xd, t.cuda())
+        out.backward()
+        assert abs(out.item() - ref.item()) < 2e-5, (shape, out.item(), ref.item())
+        assert rel_l2(xd.grad.cpu(), x.grad) < 1e-4, shape
+    big = torch.full((1, 1, 176, 176), 30.0)
+    m = torch.zeros((1, 1, 176, 176))
+    m[..., 40:120, 30:140] = 1.0
+    assert abs(B.MSSSIMLoss()(((2 * m - 1) * big).cuda(), m.cuda()).item()) < 1e-6      # sigmoid(+-30) == mask
+    with pytest.raises(ValueError):
+        B.MSSSIMLoss()(torch.zeros((1, 1, 160, 200)).cuda(), torch.zeros((1, 1, 160, 200)).cuda())

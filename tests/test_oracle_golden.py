@@ -203,3 +203,34 @@ def test_unet3plus_deepsup_matches_reference():
     for k, v in fix.items():
         if k.startswith("grad::"):
             assert rel_l2(sd[k[6:]].grad, v) < 2e-3, k
+
+
+def test_msssim_oracle_known_answers():
+    """oracle/msssim.py restates pytorch-msssim 1.0.0 (absent here: parity unpinned for this term).  Known
+    answers: identical images -> 1; the separable valid Gaussian equals a dense 11 x 11 correlation; a single
+    scale agrees with SSIM computed from its definition; the size assertion; symmetry in (x, y)."""
+    from oracle import msssim as M
+    g = torch.Generator().manual_seed(0)
+    x = torch.rand((2, 1, 176, 192), generator=g)
+    y = torch.rand((2, 1, 176, 192), generator=g)
+    assert abs(M.ms_ssim(x, x).item() - 1.0) < 1e-6
+    assert abs(M.ms_ssim(x, y).item() - M.ms_ssim(y, x).item()) < 1e-6
+    win = M.fspecial_gauss_1d()
+    assert abs(win.sum().item() - 1.0) < 1e-6 and win.shape == (1, 1, 11)
+    dense = (win.view(11, 1) * win.view(1, 11)).view(1, 1, 11, 11)
+    a = M.gaussian_filter(x, win)
+    b = torch.nn.functional.conv2d(x, dense)
+    assert a.shape == (2, 1, 166, 182) and (a - b).abs().max() < 1e-6
+    mu1, mu2 = b, torch.nn.functional.conv2d(y, dense)
+    s1 = torch.nn.functional.conv2d(x * x, dense) - mu1 ** 2
+    s2 = torch.nn.functional.conv2d(y * y, dense) - mu2 ** 2
+    s12 = torch.nn.functional.conv2d(x * y, dense) - mu1 * mu2
+    c1, c2 = 0.01 ** 2, 0.03 ** 2
+    ssim = ((2 * mu1 * mu2 + c1) * (2 * s12 + c2)) / ((mu1 ** 2 + mu2 ** 2 + c1) * (s1 + s2 + c2))
+    got, _ = M.ssim_maps(x, y)
+    assert (got.flatten() - ssim.flatten(1).mean(1)).abs().max() < 1e-5
+    import pytest
+    with pytest.raises(AssertionError):
+        M.ms_ssim(x[..., :160, :], y[..., :160, :])
+    t = (x > 0.5).float()
+    assert M.msssim_loss(40 * (t - 0.5), t).item() < 1e-6
