@@ -400,6 +400,129 @@ __device__ __forceinline__ void bilinear_adjoint_walk(int s, int li, int j0, int
   if (j >= j0 && j < j1) emit(j, a0);
   if (j + 1 >= j0 && j + 1 < j1) emit(j + 1, a1);
 }
+// Power-of-two scales (all the network uses): the same walk cell by cell.  Cell j (j = -1 .. li-1) holds the S
+// destinations S*j + S/2 + t whose lower source index is j; slot t gives (1 - (t + .5)/S) to out[j] and (t + .5)/S to
+// out[j+1] — compile-time weights, no per-element index search (the generic walk costs ~120 instructions per
+// 16-byte load, this one ~30) — and the border cells (-1 and li-1, half-size) give everything to out[0] / out[li-1].
+// out[j] = right part of cell j-1 + left part of cell j; 8 loads are issued before the first is consumed.
+struct RawBf8 {
+  uint4 v;
+  __device__ __forceinline__ void zero() { v = make_uint4(0u, 0u, 0u, 0u); }
+  __device__ __forceinline__ void unpack(float* f) const {
+    const float2 a = unpack_bf16x2(v.x), b = unpack_bf16x2(v.y), c = unpack_bf16x2(v.z), d = unpack_bf16x2(v.w);
+    f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
+  }
+};
+struct RawF8 {
+  float4 a, b;
+  __device__ __forceinline__ void zero() { a = b = make_float4(0.f, 0.f, 0.f, 0.f); }
+  __device__ __forceinline__ void unpack(float* f) const {
+    f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+  }
+};
+template <int S, class Raw, class Load, class Emit>
+__device__ __forceinline__ void bilinear_adjoint_cells(int li, int j0, int j1, Load load, Emit emit) {
+  constexpr int NB = 8;                          // loads in flight per thread
+  constexpr int G = S <= NB ? NB / S : 1;        // whole cells per batch (S <= 8)
+  constexpr int PARTS = S <= NB ? 1 : S / NB;    // batches per cell (S = 16)
+  const int lo = li * S;
+  float prev[8], left[8], right[8];
+#pragma unroll
+  for (int q = 0; q < 8; ++q) prev[q] = left[q] = right[q] = 0.f;
+  for (int jb = j0 - 1; jb < j1; jb += G) {
+#pragma unroll
+    for (int part = 0; part < PARTS; ++part) {
+      Raw g[NB];
+#pragma unroll
+      for (int u = 0; u < NB; ++u) {
+        const int j = jb + (S <= NB ? u / S : 0);
+        const int t = S <= NB ? u % S : part * NB + u;
+        const int d = S * j + S / 2 + t;
+        if (j < j1 && d >= 0 && d < lo) load(d, g[u]); else g[u].zero();
+      }
+#pragma unroll
+      for (int u = 0; u < NB; ++u) {
+        const int j = jb + (S <= NB ? u / S : 0);
+        const int t = S <= NB ? u % S : part * NB + u;
+        const bool first = j < 0, last = j == li - 1;
+        const float w1c = ((float)t + 0.5f) * (1.f / S);
+        const float w1 = first ? 1.f : (last ? 0.f : w1c), w0 = 1.f - w1;
+        float f[8];
+        g[u].unpack(f);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) { left[q] = fmaf(w0, f[q], left[q]); right[q] = fmaf(w1, f[q], right[q]); }
+        if (t == S - 1) {                        // cell complete
+          if (j >= j0 && j < j1) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) left[q] += prev[q];
+            emit(j, left);
+          }
+#pragma unroll
+          for (int q = 0; q < 8; ++q) { prev[q] = right[q]; left[q] = right[q] = 0.f; }
+        }
+      }
+    }
+  }
+}
+template <int S>
+__global__ void __launch_bounds__(256)
+    bilinear2d_bwd_w_cell_kernel(long rows, int iw, int c, int runs, int per_run, View dy, float* __restrict__ tmp) {
+  const int cv = c / 8;
+  const long total = rows * runs * cv;
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int ch = (int)(i % cv) * 8;
+  const long r = i / cv;
+  const int run = (int)(r % runs);
+  const long row = r / runs;
+  const int j0 = run * per_run, j1 = min(iw, j0 + per_run);
+  const bf16* ibase = dy.at(row * (long)iw * S, ch);
+  const long istride = dy.ctot;
+  float* obase = tmp + row * (long)iw * c + ch;
+  bilinear_adjoint_cells<S, RawBf8>(
+      iw, j0, j1, [&](int d, RawBf8& g) { g.v = ldg_nc_v4(ibase + d * istride); },
+      [&](int j, const float* a) {
+        float4* o = reinterpret_cast<float4*>(obase + (long)j * c);
+        o[0] = make_float4(a[0], a[1], a[2], a[3]);
+        o[1] = make_float4(a[4], a[5], a[6], a[7]);
+      });
+}
+template <int S>
+__global__ void __launch_bounds__(256)
+    bilinear2d_bwd_h_cell_kernel(int n, int ih, int iw, int c, int runs, int per_run, const float* __restrict__ tmp,
+                                 View add, View dx) {
+  const int cv = c / 8;
+  const long line = (long)iw * cv;
+  const long total = (long)n * runs * line;
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const long q = i % line;
+  const long r = i / line;
+  const int run = (int)(r % runs);
+  const int b = (int)(r / runs);
+  const int xw = (int)(q / cv), ch = (int)(q % cv) * 8;
+  const int j0 = run * per_run, j1 = min(ih, j0 + per_run);
+  const float* ibase = tmp + ((long)b * ih * S * iw + xw) * c + ch;
+  const long rowstride = (long)iw * c;
+  bilinear_adjoint_cells<S, RawF8>(
+      ih, j0, j1,
+      [&](int d, RawF8& g) {
+        const float4* p = reinterpret_cast<const float4*>(ibase + d * rowstride);
+        g.a = p[0];
+        g.b = p[1];
+      },
+      [&](int j, const float* a) {
+        const long pos = ((long)b * ih + j) * iw + xw;
+        float o[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) o[k] = 0.f;
+        if (add.p) Vec<8>::load(add.at(pos, ch), o);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) o[k] += a[k];
+        Vec<8>::store(dx.at(pos, ch), o);
+      });
+}
+
 // pass 1, along W: thread = (row of n*oh, run, channel vector)
 __global__ void __launch_bounds__(256)
     bilinear2d_bwd_w_kernel(long rows, int iw, int c, int s, int runs, int per_run, View dy, float* __restrict__ tmp) {
@@ -1357,15 +1480,42 @@ int b200_bilinear2d_bwd(int32_t n, int32_t ih, int32_t iw, int32_t c, int32_t sc
   const int cv = c / 8;
   const long rows = (long)n * ih * scale;
   int runs, per_run;
+  cudaStream_t st = (cudaStream_t)stream;
   adjoint_runs(rows * cv, iw, &runs, &per_run);
   long total = rows * runs * cv;
-  bilinear2d_bwd_w_kernel<<<blocks_for(total, 256), 256, 0, (cudaStream_t)stream>>>(rows, iw, c, scale, runs, per_run,
-                                                                                mk(dy), (float*)scratch);
+#define BILINEAR_BWD_W(S_)                                                                                     \
+  case S_:                                                                                                     \
+    bilinear2d_bwd_w_cell_kernel<S_><<<blocks_for(total, 256), 256, 0, st>>>(rows, iw, c, runs, per_run, mk(dy), \
+                                                                              (float*)scratch);                \
+    break;
+  switch (scale) {
+    BILINEAR_BWD_W(2)
+    BILINEAR_BWD_W(4)
+    BILINEAR_BWD_W(8)
+    BILINEAR_BWD_W(16)
+    default:
+      bilinear2d_bwd_w_kernel<<<blocks_for(total, 256), 256, 0, st>>>(rows, iw, c, scale, runs, per_run, mk(dy),
+                                                                      (float*)scratch);
+  }
+#undef BILINEAR_BWD_W
   B200_LAUNCH_CHECK();
   adjoint_runs((long)n * iw * cv, ih, &runs, &per_run);
   total = (long)n * runs * iw * cv;
-  bilinear2d_bwd_h_kernel<<<blocks_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
-      n, ih, iw, c, scale, runs, per_run, (const float*)scratch, mk(add), mk(dx));
+#define BILINEAR_BWD_H(S_)                                                                                   \
+  case S_:                                                                                                   \
+    bilinear2d_bwd_h_cell_kernel<S_><<<blocks_for(total, 256), 256, 0, st>>>(                                \
+        n, ih, iw, c, runs, per_run, (const float*)scratch, mk(add), mk(dx));                                \
+    break;
+  switch (scale) {
+    BILINEAR_BWD_H(2)
+    BILINEAR_BWD_H(4)
+    BILINEAR_BWD_H(8)
+    BILINEAR_BWD_H(16)
+    default:
+      bilinear2d_bwd_h_kernel<<<blocks_for(total, 256), 256, 0, st>>>(n, ih, iw, c, scale, runs, per_run,
+                                                                      (const float*)scratch, mk(add), mk(dx));
+  }
+#undef BILINEAR_BWD_H
   B200_LAUNCH_CHECK();
   return B200_OK;
 }
