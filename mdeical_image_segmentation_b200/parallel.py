@@ -102,7 +102,8 @@ class DataParallelUNet(nn.Module):
                 dist.broadcast(t.data, src=0, group=group)
         self.reducer = GradReducer(module.parameters(), bucket_mb=bucket_mb, group=group)
         for m in module.modules():
-            if hasattr(m, "final_conv") and hasattr(m, "forward"):
+            # whole-network executors: the U-Nets (final_conv) and the UNet 3+ family (_b200_executor)
+            if (hasattr(m, "final_conv") or getattr(m, "_b200_executor", False)) and hasattr(m, "forward"):
                 m._b200_reducer = self.reducer
 
     def forward(self, *args, **kwargs):

@@ -58,6 +58,7 @@ class _UNet3PlusBody(nn.Module):
     """Encoder + four full-scale decoder stages shared by UNet_3Plus (unet.py:136-333) and
     UNet_3Plus_DeepSup (unet.py:454-662); modules are registered in the reference's order."""
     HEAD_SCALES = (1,)           # output head i reads hd{i+1} and is up-sampled by HEAD_SCALES[i]
+    _b200_executor = True        # parallel.DataParallelUNet attaches its gradient reducer to such modules
 
     def __init__(self, in_channels=3, n_classes=1, feature_scale=4, is_deconv=True, is_batchnorm=True):
         super().__init__()
@@ -224,50 +225,62 @@ class _Net3PFunction(torch.autograd.Function):
         if tape is None:
             raise RuntimeError("backward through a forward that ran without grad")
         grads: engine.Grads = {}
-        h, hd = tape["h"], ctx.hd
-        # d(loss)/d hd1..hd5 from the output heads.  Every hd is a ReLU output, so its ReLU backward is
-        # folded into the head's data gradient (mask = hd); a masked gradient may be summed with the raw
-        # gradients that arrive later, because masking is idempotent.
-        ghd: Dict[int, Optional[CL]] = {s: None for s in range(1, 6)}
-        for i, (oc, wp_bwd, k, ncls, scale) in enumerate(ctx.heads):
-            if dlogits[i] is None:
-                continue
-            dy = ops.from_nchw(F.pad(dlogits[i].contiguous().float(), (0, 0, 0, 0, 0, 16 - ncls)))
-            if scale > 1:
-                dy = ops.bilinear_bwd(dy, scale)
-            dw, db = ops.conv_bwd_weight(hd[i + 1], dy, k, (16,) + tuple(oc.weight.shape[1:]), impl=engine.IMPL,
-                                         bias_grad=True)
-            engine._acc(grads, oc.weight, dw[:ncls].contiguous())
-            if oc.bias is not None:
-                engine._acc(grads, oc.bias, db[:ncls].contiguous())
-            ghd[i + 1] = ops.conv_bwd_data(dy, wp_bwd, k, mask=hd[i + 1], impl=engine.IMPL)
-        dh: Dict[int, Optional[CL]] = {lvl: None for lvl in range(1, 6)}     # d(loss)/d h1..h5 (h5 = hd5)
-        dh[5] = ghd[5]
-        dhd: Dict[int, Optional[CL]] = {4: ghd[4], 3: ghd[3], 2: ghd[2]}
-        cc = net.CatChannels
-        for stage in (1, 2, 3, 4):
-            g = ghd[1] if stage == 1 else dhd[stage]
-            if g is None:
-                raise RuntimeError("UNet 3+ backward without a gradient for the full-resolution output")
-            # only stage 1's gradient is fully masked (it has a single consumer, the head conv above);
-            # deeper stages have accumulated raw gradients from the bilinear branches
-            dcat, pm, _ = engine.single_conv_bwd(g, tape[("fuse", stage)], grads, premasked=(stage == 1))
-            for level in range(1, 6):
-                d, _, _ = engine.single_conv_bwd(dcat.slice((level - 1) * cc, cc), tape[("br", level, stage)],
-                                                 grads, premasked=pm)
-                if level < stage:
-                    dh[level] = ops.maxpoolk_bwd(h[level], d, 2 ** (stage - level), add=dh[level])
-                elif level == stage:
-                    dh[level] = d if dh[level] is None else ops.add_(dh[level], d)
-                elif level == 5:
-                    dh[5] = ops.bilinear_bwd(d, 2 ** (level - stage), add=dh[5])
-                else:
-                    dhd[level] = ops.bilinear_bwd(d, 2 ** (level - stage), add=dhd[level])
-        d, pm = dh[5], False
-        for lvl in range(5, 0, -1):
-            d, _, _ = engine.block_bwd(d, tape[("enc", lvl)], 2, grads, need_dx=lvl > 1, premasked=pm)
-            if lvl > 1:   # h[lvl-1] is a ReLU output: the pool backward masks the summed gradient by it
-                d = ops.maxpool_bwd(h[lvl - 1], d, 1, add=dh[lvl - 1], mask_relu=True)
-                pm = True
+        # as engine._NetFunction.backward: parameter gradients go to the data-parallel reducer the moment they
+        # are final, weight-gradient GEMMs run on the side stream next to the HBM-bound BatchNorm / resize /
+        # pool backward kernels of the main chain
+        engine._REDUCER = getattr(net, "_b200_reducer", None)
+        engine._side_begin(dlogits[0].device if dlogits[0] is not None else ctx.hd[1].device)
+        try:
+            h, hd = tape["h"], ctx.hd
+            # d(loss)/d hd1..hd5 from the output heads.  Every hd is a ReLU output, so its ReLU backward is
+            # folded into the head's data gradient (mask = hd); a masked gradient may be summed with the raw
+            # gradients that arrive later, because masking is idempotent.
+            ghd: Dict[int, Optional[CL]] = {s: None for s in range(1, 6)}
+            for i, (oc, wp_bwd, k, ncls, scale) in enumerate(ctx.heads):
+                if dlogits[i] is None:
+                    continue
+                dy = ops.from_nchw(F.pad(dlogits[i].contiguous().float(), (0, 0, 0, 0, 0, 16 - ncls)))
+                if scale > 1:
+                    dy = ops.bilinear_bwd(dy, scale)
+                dw, db = ops.conv_bwd_weight(hd[i + 1], dy, k, (16,) + tuple(oc.weight.shape[1:]), impl=engine.IMPL,
+                                             bias_grad=True)
+                engine._acc(grads, oc.weight, dw[:ncls].contiguous())
+                if oc.bias is not None:
+                    engine._acc(grads, oc.bias, db[:ncls].contiguous())
+                ghd[i + 1] = ops.conv_bwd_data(dy, wp_bwd, k, mask=hd[i + 1], impl=engine.IMPL)
+            dh: Dict[int, Optional[CL]] = {lvl: None for lvl in range(1, 6)}     # d(loss)/d h1..h5 (h5 = hd5)
+            dh[5] = ghd[5]
+            dhd: Dict[int, Optional[CL]] = {4: ghd[4], 3: ghd[3], 2: ghd[2]}
+            cc = net.CatChannels
+            for stage in (1, 2, 3, 4):
+                g = ghd[1] if stage == 1 else dhd[stage]
+                if g is None:
+                    raise RuntimeError("UNet 3+ backward without a gradient for the full-resolution output")
+                # only stage 1's gradient is fully masked (it has a single consumer, the head conv above);
+                # deeper stages have accumulated raw gradients from the bilinear branches
+                dcat, pm, _ = engine.single_conv_bwd(g, tape[("fuse", stage)], grads, premasked=(stage == 1))
+                for level in range(1, 6):
+                    d, _, _ = engine.single_conv_bwd(dcat.slice((level - 1) * cc, cc), tape[("br", level, stage)],
+                                                     grads, premasked=pm)
+                    if level < stage:
+                        dh[level] = ops.maxpoolk_bwd(h[level], d, 2 ** (stage - level), add=dh[level])
+                    elif level == stage:
+                        dh[level] = d if dh[level] is None else ops.add_(dh[level], d)
+                    elif level == 5:
+                        dh[5] = ops.bilinear_bwd(d, 2 ** (level - stage), add=dh[5])
+                    else:
+                        dhd[level] = ops.bilinear_bwd(d, 2 ** (level - stage), add=dhd[level])
+            d, pm = dh[5], False
+            for lvl in range(5, 0, -1):
+                d, _, _ = engine.block_bwd(d, tape[("enc", lvl)], 2, grads, need_dx=lvl > 1, premasked=pm)
+                if lvl > 1:   # h[lvl-1] is a ReLU output: the pool backward masks the summed gradient by it
+                    d = ops.maxpool_bwd(h[lvl - 1], d, 1, add=dh[lvl - 1], mask_relu=True)
+                    pm = True
+            engine._side_end(grads)
+            if engine._REDUCER is not None:
+                engine._REDUCER.finish()
+        finally:
+            engine._REDUCER = None
+            engine._side_end({})
         ctx.tape = ctx.hd = None
         return (None, None) + tuple(grads.get(p) if p.requires_grad else None for p in ctx.params)

@@ -63,3 +63,19 @@ def test_bucketed_allreduce_two_ranks():
         mean = (ga + gb) / 2
         assert abs(ra - mean).max() < 1e-6 and abs(rb - mean).max() < 1e-6
     assert l0 == l1 == 0.5
+
+
+def test_reducer_is_attached_to_every_executor():
+    """DataParallelUNet must hand its GradReducer to every whole-network executor it wraps — the U-Nets
+    (``final_conv``) and the UNet 3+ family, also behind the HF-style ``UNetModel`` wrapper — otherwise the
+    backward pass would silently skip the gradient all-reduce."""
+    import mdeical_image_segmentation_b200 as B
+    from mdeical_image_segmentation_b200.parallel import DataParallelUNet
+    for make, inner in ((lambda: B.UNet3D(1, 1, f_maps=[8, 16]), lambda m: m),
+                        (lambda: B.UNetModel(B.UNetConfig(1, 1)), lambda m: m.unet),
+                        (lambda: B.UNetModel(B.UNetConfig(3, 1, "UNet_3Plus")), lambda m: m.unet),
+                        (lambda: B.UNet_3Plus_DeepSup(3, 1), lambda m: m)):
+        model = make()
+        dp = DataParallelUNet(model)
+        assert inner(model)._b200_reducer is dp.reducer, type(inner(model)).__name__
+        assert sum(p.numel() for p in dp.reducer.params) == sum(p.numel() for p in model.parameters())
