@@ -303,6 +303,18 @@ int b200_msssim_fwd(int32_t n, int32_t h, int32_t w, const float* logits, const 
 int b200_msssim_bwd(int32_t n, int32_t h, int32_t w, const float* pyr_x, const float* pyr_y, const float* gmeans,
                     float* pyr_dx, float* dlogits, float data_range, b200_stream_t stream);
 
+/* ---- class-guided module of UNet_3Plus_DeepSup_CGM (model/unet2d/unet.py:999-1017, 1036-1038, 1147-1153) ----
+ * gate fp32 [n] = argmax over the 2 classes of sigmoid(max over positions of conv1x1(dropout(x)) + bias), x = hd5
+ * (n, npos, c) channels-last bf16, w fp32 [2][c].  keep: channels-last uint8 [n][npos][c] dropout mask (NULL = eval
+ * mode), kept values are scaled by keep_scale = 1 / (1 - p).  cls (may be NULL): fp32 [n][2] class probabilities. */
+int b200_cgm_gate(int32_t n, int64_t npos, int32_t c, b200_view x, const float* w, const float* bias,
+                  const uint8_t* keep, float keep_scale, float* gate, float* cls, b200_stream_t stream);
+/* y = sigmoid(x * gate[sample]) (dotProduct + F.sigmoid, unet.py:1012-1017, 1153); dx = dy * y (1 - y) * gate */
+int b200_gate_sigmoid_fwd(int32_t n, int64_t per_sample, const float* x, const float* gate, float* y,
+                          b200_stream_t stream);
+int b200_gate_sigmoid_bwd(int32_t n, int64_t per_sample, const float* y, const float* dy, const float* gate,
+                          float* dx, b200_stream_t stream);
+
 /* ---- metrics -----------------------------------------------------------------------------------
  * trainer/metrcis.py:61-109,153-168: p = 1/(1+exp(-x)+1e-6); psum (fp64 [1]) += sum p */
 int b200_metric_prob_sum(int64_t numel, const float* logits, double* psum, b200_stream_t stream);

@@ -4,7 +4,7 @@ arithmetic runs in hand-written CUDA (tcgen05/TMEM/TMA implicit-GEMM convolution
 kernels) behind a C ABI (``include/b200unet.h``).  There is no CPU / PyTorch-eager fallback."""
 from . import _lib, metrics  # noqa: F401
 from .graph import GraphedInference
-from .unet3plus import UNet_3Plus, UNet_3Plus_DeepSup
+from .unet3plus import UNet_3Plus, UNet_3Plus_DeepSup, UNet_3Plus_DeepSup_CGM
 from .losses import (BCEDiceLoss, BCEWithLogitsLoss, CrossEntropyLoss, DiceLoss, F1Loss, IoULoss, MSSSIMLoss,
                      SegmentationLoss, compute_per_channel_dice, flatten, get_loss_criterion)
 from .unet2d import (CropAndConcat, DoubleConvolution, DownSample, UNet, UpSample, unetConv2)

@@ -556,6 +556,33 @@ def seg_sums(logits: torch.Tensor, target: torch.Tensor, normalization: int = 0)
     return sums
 
 
+def cgm_gate(x: CL, weight: torch.Tensor, bias: torch.Tensor, keep: Optional[torch.Tensor] = None,
+             keep_scale: float = 1.0):
+    """(gate (n,), cls (n, 2)): arg-max class gate of the UNet 3+ classification branch on hd5."""
+    assert x.d == 1
+    w = weight.detach().reshape(2, x.c).float().contiguous()
+    b = bias.detach().float().contiguous()
+    gate = torch.empty(x.n, dtype=torch.float32, device=x.device)
+    cls = torch.empty((x.n, 2), dtype=torch.float32, device=x.device)
+    call("b200_cgm_gate", x.n, x.h * x.w, x.c, x.view(), _p(w), _p(b), _p(keep), float(keep_scale), _p(gate),
+         _p(cls), _stream())
+    return gate, cls
+
+
+def gate_sigmoid_fwd(x: torch.Tensor, gate: torch.Tensor) -> torch.Tensor:
+    x = x.contiguous().float()
+    y = torch.empty_like(x)
+    call("b200_gate_sigmoid_fwd", x.shape[0], x[0].numel(), _p(x), _p(gate), _p(y), _stream())
+    return y
+
+
+def gate_sigmoid_bwd(y: torch.Tensor, dy: torch.Tensor, gate: torch.Tensor) -> torch.Tensor:
+    dy = dy.contiguous().float()
+    dx = torch.empty_like(y)
+    call("b200_gate_sigmoid_bwd", y.shape[0], y[0].numel(), _p(y), _p(dy), _p(gate), _p(dx), _stream())
+    return dx
+
+
 def msssim_valid_counts(h: int, w: int):
     """Valid positions (h_l - 10) * (w_l - 10) of the 5 MS-SSIM scales, h_{l+1} = ceil(h_l / 2)."""
     out = []

@@ -18,8 +18,9 @@ fuses them with one more conv + BN + ReLU.  On this path
 ``UNet_3Plus_DeepSup`` (unet.py:454-787) adds the deep-supervision heads: a 3x3 conv to n_classes on every
 decoder scale (hd1..hd4 and the bottleneck hd5), bilinearly up-sampled to the input size; it returns the
 tuple (d1, .., d5) of logits that ``UNetModel.forward`` (unet.py:1203-1208) sums the criterion over.  The
-class-guided variant ``UNet_3Plus_DeepSup_CGM`` (unet.py:795-1153: dropout + arg-max gate, not reachable
-from ``UNetConfig.unet_type``) is not implemented here.
+class-guided variant ``UNet_3Plus_DeepSup_CGM`` (unet.py:795-1153) adds the classification branch on the
+bottleneck (dropout, 1x1 conv to 2 classes, global max, sigmoid, arg-max) whose 0/1 result gates the five
+maps per sample before a sigmoid (``b200_cgm_gate``, ``b200_gate_sigmoid_*``); it returns probabilities.
 """
 from __future__ import annotations
 
@@ -139,6 +140,38 @@ class UNet_3Plus_DeepSup(_UNet3PlusBody):
         return self._run(inputs)
 
 
+class _GateSigmoid(torch.autograd.Function):
+    """sigmoid(d * gate[sample]) — dotProduct (unet.py:1012-1017) + F.sigmoid (:1153); the gate is an arg-max
+    result and carries no gradient."""
+
+    @staticmethod
+    def forward(ctx, d: torch.Tensor, gate: torch.Tensor):
+        y = ops.gate_sigmoid_fwd(d, gate)
+        ctx.save_for_backward(y, gate)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        y, gate = ctx.saved_tensors
+        return ops.gate_sigmoid_bwd(y, dy, gate), None
+
+
+class UNet_3Plus_DeepSup_CGM(_UNet3PlusBody):
+    """unet.py:795-1153.  ``forward(inputs) -> (p1, .., p5)``: class-gated probabilities of the five scales.
+    ``self.last_cls`` keeps the (n, 2) class probabilities of the last forward for inspection."""
+    HEAD_SCALES = (1, 2, 4, 8, 16)
+
+    def _make_heads(self, n_classes):
+        UNet_3Plus_DeepSup._make_heads(self, n_classes)
+        self.cls = nn.Sequential(nn.Dropout(p=0.5), nn.Conv2d(FILTERS[4], 2, 1), nn.AdaptiveMaxPool2d(1),
+                                 nn.Sigmoid())
+        self.last_cls = None
+
+    def forward(self, inputs: torch.Tensor):
+        *ds, gate = self._run(inputs)
+        return tuple(_GateSigmoid.apply(d, gate) for d in ds)
+
+
 # ===================================================================================== executor
 def _spec(net: nn.Module, prefix: str) -> engine.LayerSpec:
     return engine.LayerSpec("cbr", getattr(net, prefix + "_conv"), batchnorm=getattr(net, prefix + "_bn"))
@@ -214,10 +247,21 @@ class _Net3PFunction(torch.autograd.Function):
                     y = ops.bilinear_fwd(y, scale)
                 outs.append(ops.to_nchw(y.slice(0, ncls), False))
                 heads.append((oc, wp_bwd, k, ncls, scale))
+            gate = None
+            if hasattr(net, "cls"):      # classification branch on hd5 (unet.py:1035-1038)
+                drop, conv = net.cls[0], net.cls[1]
+                keep, scale = None, 1.0
+                if net.training and drop.p > 0:
+                    keep = (torch.rand((hd[5].n, hd[5].h * hd[5].w, hd[5].c), device=images.device) >= drop.p)
+                    keep, scale = keep.to(torch.uint8), 1.0 / (1.0 - drop.p)
+                gate, net.last_cls = ops.cgm_gate(hd[5], conv.weight, conv.bias, keep, scale)
         ctx.net, ctx.tape, ctx.params = net, tape, params
         ctx.hd = hd if need_grad else None
         ctx.heads = heads
-        return tuple(outs)
+        if gate is None:
+            return tuple(outs)
+        ctx.mark_non_differentiable(gate)
+        return tuple(outs) + (gate,)
 
     @staticmethod
     def backward(ctx, *dlogits):

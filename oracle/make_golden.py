@@ -270,6 +270,39 @@ def gen_unet3plus_deepsup(ns):
     print("unet3plus_deepsup_3_1", float(loss), [float(d.abs().max()) for d in ds])
 
 
+def gen_unet3plus_cgm(ns):
+    """UNet_3Plus_DeepSup_CGM (unet.py:795-1153) with the dropout of its classification branch switched off
+    (p = 0: a random mask cannot be pinned), training-mode BatchNorm, 4 samples so that both gate values occur;
+    BCE on the five probability maps.  Stores the class probabilities so that the test can see the margin."""
+    from oracle import unet3plus as O3
+    torch.manual_seed(0)
+    net = ns.U2.UNet_3Plus_DeepSup_CGM(3, 1)
+    sd = {k: v.clone() for k, v in net.state_dict().items()}
+    O3.fill_state_dict_(sd, 27)      # a seed whose gates are mixed with a margin (0.087)
+    net.load_state_dict(sd)
+    net.train()
+    net.cls[0].p = 0.0
+    g = torch.Generator().manual_seed(41)
+    x = torch.randn((4, 3, 32, 32), generator=g)
+    y = blob_target((4, 1, 32, 32), 42)
+    feats = {}
+    hook = net.conv5.register_forward_hook(lambda m, i, o: feats.__setitem__("hd5", o.detach()))
+    ds = net(x)
+    hook.remove()
+    cls = net.cls(feats["hd5"]).squeeze(3).squeeze(2)
+    loss = sum(torch.nn.functional.binary_cross_entropy(d, y) for d in ds)
+    loss.backward()
+    names = [k for k, p in net.named_parameters()]
+    has_grad = np.array([p.grad is not None for _, p in net.named_parameters()])
+    out = dict(seed=27, x=_np(x), y=_np(y), loss=_np(loss), cls=_np(cls), grad_names=np.array(names), has_grad=has_grad,
+               grad_norms=np.array([0.0 if p.grad is None else p.grad.norm().item() for _, p in net.named_parameters()]),
+               state_dict_keys=np.array(list(net.state_dict().keys())))
+    for i, d in enumerate(ds):
+        out[f"d{i + 1}"] = _np(d)
+    np.savez_compressed(os.path.join(OUT, "unet3plus_cgm_3_1.npz"), **out)
+    print("unet3plus_cgm_3_1", float(loss), "cls", cls.detach().numpy().round(4).tolist())
+
+
 def main():
     torch.set_num_threads(8)
     os.makedirs(OUT, exist_ok=True)
@@ -281,6 +314,7 @@ def main():
     gen_losses_metrics(ns)
     gen_unet3plus(ns)
     gen_unet3plus_deepsup(ns)
+    gen_unet3plus_cgm(ns)
 
 
 if __name__ == "__main__":

@@ -41,13 +41,14 @@ def conv_bn_relu(sd: SD, conv: str, bn: str, x: torch.Tensor, training: bool, em
 
 
 def unet3plus_forward(sd: SD, x: torch.Tensor, training: bool = True, emulate_bf16: bool = False,
-                      deep_sup: bool = False):
+                      deep_sup: bool = False, cgm: bool = False):
     """unet.py:335-446: encoder (unetConv2 + MaxPool2d(2)) -> four full-scale decoder stages -> 3x3 output
     conv; returns logits (the sigmoid at :445 is commented out).  ``emulate_bf16`` rounds weights and every
     stored activation to bf16 where the B200 path stores bf16 (fp32 accumulation kept): the yardstick that
     separates storage-precision noise — large for random weights on a 19-layer BatchNorm net — from bugs.
     ``deep_sup``: UNet_3Plus_DeepSup (unet.py:454-787) — the tuple (d1..d5) of per-scale logits, each
-    bilinearly up-sampled to the input size."""
+    bilinearly up-sampled to the input size.  ``cgm`` (with deep_sup): UNet_3Plus_DeepSup_CGM (unet.py:795-1153)
+    — the five maps gated per sample by the classification branch, as probabilities."""
     h = {}
     for lvl in range(1, 6):
         if lvl > 1:
@@ -86,7 +87,13 @@ def unet3plus_forward(sd: SD, x: torch.Tensor, training: bool = True, emulate_bf
     for i in range(2, 6):
         y = F.interpolate(head(i), scale_factor=2 ** (i - 1), mode="bilinear")
         outs.append(_bf(y) if emulate_bf16 else y)
-    return tuple(outs)
+    if not cgm:
+        return tuple(outs)
+    # class-guided module, unet.py:999-1004, 1035-1038, 1012-1017, 1147-1153 (dropout: identity, i.e. eval mode
+    # or p = 0; its random mask cannot be pinned)
+    cls = torch.sigmoid(F.conv2d(hd[5], sd["cls.1.weight"], sd["cls.1.bias"]).amax(dim=(2, 3)))     # (B, 2)
+    gate = cls.argmax(dim=1).float().view(-1, 1, 1, 1)
+    return tuple(torch.sigmoid(d * gate) for d in outs)
 
 
 def fill_state_dict_(sd: SD, seed: int) -> None:

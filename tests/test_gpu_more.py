@@ -526,3 +526,53 @@ def test_msssim_and_segmentation_loss_vs_oracle(B):
     assert abs(B.MSSSIMLoss()(((2 * m - 1) * big).cuda(), m.cuda()).item()) < 1e-6      # sigmoid(+-30) == mask
     with pytest.raises(ValueError):
         B.MSSSIMLoss()(torch.zeros((1, 1, 160, 200)).cuda(), torch.zeros((1, 1, 160, 200)).cuda())
+
+
+def test_unet3plus_cgm_vs_reference_golden(B):
+    """UNet_3Plus_DeepSup_CGM (unet.py:795-1153) against the reference's own run with the classification
+    dropout switched off: class probabilities, the per-sample gate, the five gated probability maps, the BCE loss
+    and gradients (none for the cls convolution: arg-max).  Then the dropout path: mask statistics and eval mode."""
+    from conftest import load_golden
+    from oracle import unet3plus as O3
+    fix = load_golden("unet3plus_cgm_3_1")
+    net = B.UNet_3Plus_DeepSup_CGM(3, 1)
+    sd = {k: v.clone() for k, v in net.state_dict().items()}
+    assert list(sd.keys()) == [str(k) for k in fix["state_dict_keys"]]
+    O3.fill_state_dict_(sd, int(fix["seed"]))
+    net.load_state_dict(sd)
+    net = net.cuda().train()
+    net.cls[0].p = 0.0
+    x, y = torch.from_numpy(fix["x"]).cuda(), torch.from_numpy(fix["y"]).cuda()
+    ds = net(x)
+    assert len(ds) == 5
+    cls = net.last_cls.cpu().numpy()
+    print("CGM class probabilities (B200 / reference):", cls.round(4).tolist(), fix["cls"].round(4).tolist())
+    assert np.abs(cls - fix["cls"]).max() < 3e-2
+    gates = fix["cls"].argmax(1)
+    assert (cls.argmax(1) == gates).all()
+    for i, d in enumerate(ds):
+        d = d.detach().cpu()
+        assert torch.all(d[gates == 0] == 0.5)                               # gated-off samples: sigmoid(0)
+        # probabilities of a random-weight fixture: logits carry ~5e-2 of bf16 storage noise (see the golden test)
+        assert (d - torch.from_numpy(fix[f"d{i + 1}"])).abs().max() < 8e-2, i
+        assert rel_l2(d, fix[f"d{i + 1}"]) < 4e-2, (i, rel_l2(d, fix[f"d{i + 1}"]))
+    loss = sum(torch.nn.functional.binary_cross_entropy(d, y) for d in ds)
+    assert abs(loss.item() - float(fix["loss"])) < 2e-2
+    loss.backward()
+    named = dict(net.named_parameters())
+    names = [str(s) for s in fix["grad_names"]]
+    gnorm = float(np.sqrt((fix["grad_norms"] ** 2).sum()))
+    for k, has, norm in zip(names, fix["has_grad"], fix["grad_norms"]):
+        if not has:
+            assert named[k].grad is None, k
+        else:
+            assert abs(named[k].grad.norm().item() - norm) < 0.3 * norm + 2e-3 * gnorm, (k, named[k].grad.norm().item(), norm)
+    # dropout on (training mode, p = 0.5): still a 0/1 gate per sample, finite outputs; eval mode is deterministic
+    net.cls[0].p = 0.5
+    torch.manual_seed(5)
+    out = net(x)
+    assert all(torch.isfinite(d).all() for d in out) and net.last_cls.shape == (4, 2)
+    net.eval()
+    with torch.no_grad():
+        a, b = net(x), net(x)
+    assert all(torch.equal(p, q) for p, q in zip(a, b))

@@ -147,12 +147,13 @@ def test_analytic_known_answers():
     assert abs(O.dice_loss(-big, m).item() - 1.0) < 1e-6          # disjoint masks -> dice 0
 
 
-def _unet3plus_sd(seed, requires_grad=True, deep_sup=False):
+def _unet3plus_sd(seed, requires_grad=True, deep_sup=False, cls_name=None):
     """UNet 3+ weights of the fixture: the product module's state_dict layout (checked against the
     reference's key list stored in the fixture) filled by oracle.unet3plus.fill_state_dict_(seed)."""
-    from mdeical_image_segmentation_b200.unet3plus import UNet_3Plus, UNet_3Plus_DeepSup
+    from mdeical_image_segmentation_b200 import unet3plus as P3
     from oracle import unet3plus as O3
-    sd = {k: v.clone() for k, v in (UNet_3Plus_DeepSup if deep_sup else UNet_3Plus)(3, 1).state_dict().items()}
+    cls = getattr(P3, cls_name) if cls_name else (P3.UNet_3Plus_DeepSup if deep_sup else P3.UNet_3Plus)
+    sd = {k: v.clone() for k, v in cls(3, 1).state_dict().items()}
     O3.fill_state_dict_(sd, seed)
     if requires_grad:
         sd = {k: (v.requires_grad_(True) if v.is_floating_point() and "running" not in k else v) for k, v in sd.items()}
@@ -234,3 +235,28 @@ def test_msssim_oracle_known_answers():
         M.ms_ssim(x[..., :160, :], y[..., :160, :])
     t = (x > 0.5).float()
     assert M.msssim_loss(40 * (t - 0.5), t).item() < 1e-6
+
+
+def test_unet3plus_cgm_matches_reference():
+    """UNet_3Plus_DeepSup_CGM (unet.py:795-1153, classification dropout off): gated probabilities of the five
+    scales, BCE loss, gradient norms (the cls convolution receives none: arg-max) against the reference's run."""
+    from oracle import unet3plus as O3
+    fix = load_golden("unet3plus_cgm_3_1")
+    sd = _unet3plus_sd(int(fix["seed"]), cls_name="UNet_3Plus_DeepSup_CGM")
+    assert list(sd.keys()) == [str(k) for k in fix["state_dict_keys"]]
+    x, y = torch.from_numpy(fix["x"]), torch.from_numpy(fix["y"])
+    ds = O3.unet3plus_forward(sd, x, training=True, deep_sup=True, cgm=True)
+    gates = fix["cls"].argmax(1)
+    assert 0 < gates.sum() < len(gates)                      # the fixture exercises both gate values
+    for i, d in enumerate(ds):
+        assert (d.detach() - torch.from_numpy(fix[f"d{i + 1}"])).abs().max() < 1e-5, i
+        assert torch.all(d.detach()[gates == 0] == 0.5)
+    loss = sum(torch.nn.functional.binary_cross_entropy(d, y) for d in ds)
+    assert abs(loss.item() - float(fix["loss"])) < 1e-5
+    loss.backward()
+    names = [str(s) for s in fix["grad_names"]]
+    for k, has, norm in zip(names, fix["has_grad"], fix["grad_norms"]):
+        if not has:
+            assert k.startswith("cls.") and sd[k].grad is None
+        else:
+            assert abs(sd[k].grad.norm().item() - norm) < 5e-3 * norm + 1e-6, k
