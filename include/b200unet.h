@@ -315,6 +315,23 @@ int b200_gate_sigmoid_fwd(int32_t n, int64_t per_sample, const float* x, const f
 int b200_gate_sigmoid_bwd(int32_t n, int64_t per_sample, const float* y, const float* dy, const float* gate,
                           float* dx, b200_stream_t stream);
 
+/* ---- sliding-window prediction on the device (model/unet3d/predictor.py:65-165; SliceBuilder / mirror_pad /
+ * remove_padding of dataset/unet3d_dataset/utils.py:40-131, 314-361).  fp32 NCDHW, caller-owned buffers.
+ * gather: out (c, pd, ph, pw) = the window of vol (c, d, h, w) that starts `halo` before the patch origin (oz, oy, ox),
+ *         read with np.pad(mode='reflect') indexing — the padded volume is never materialised; pd = patch + 2 * hz ...
+ * accumulate: map[ch, o + v] += pred[ch (or `channel` if >= 0), v + halo], norm[...] += 1 over the inner patch
+ *         (predictor.py:147-150); map (c, d, h, w) fp32, norm uint8 of the same shape; one call per patch keeps the
+ *         reference's summation order (deterministic, bit-identical).
+ * finalize: map /= norm in place; seg (may be NULL) int32 (d*h*w) = arg-max over channels (predictor.py:161-165). */
+int b200_patch_gather(int32_t c, int32_t d, int32_t h, int32_t w, const float* vol, int32_t oz, int32_t oy,
+                      int32_t ox, int32_t hz, int32_t hy, int32_t hx, int32_t pd, int32_t ph, int32_t pw, float* out,
+                      b200_stream_t stream);
+int b200_patch_accumulate(int32_t c, int32_t d, int32_t h, int32_t w, int32_t pd, int32_t ph, int32_t pw, int32_t hz,
+                          int32_t hy, int32_t hx, const float* pred, int32_t c_pred, int32_t channel, int32_t oz,
+                          int32_t oy, int32_t ox, float* map, uint8_t* norm, b200_stream_t stream);
+int b200_prediction_finalize(int32_t c, int64_t nvox, float* map, const uint8_t* norm, int32_t* seg,
+                             b200_stream_t stream);
+
 /* ---- metrics -----------------------------------------------------------------------------------
  * trainer/metrcis.py:61-109,153-168: p = 1/(1+exp(-x)+1e-6); psum (fp64 [1]) += sum p */
 int b200_metric_prob_sum(int64_t numel, const float* logits, double* psum, b200_stream_t stream);

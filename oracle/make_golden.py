@@ -303,6 +303,33 @@ def gen_unet3plus_cgm(ns):
     print("unet3plus_cgm_3_1", float(loss), "cls", cls.detach().numpy().round(4).tolist())
 
 
+def gen_predictor(ns):
+    """Patch logic of the sliding-window predictor from the reference's own dataset/unet3d_dataset/utils.py
+    (loaded by path: the package __init__ needs albumentations): slice lists for several volume / patch / stride
+    combinations, mirror_pad and remove_padding outputs."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location(
+        "_ref_ds_utils", os.path.join(ref_loader.REF_ROOT, "dataset", "unet3d_dataset", "utils.py"))
+    U = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(U)
+    cases = [((40, 70, 66), (16, 64, 64), (8, 32, 32)), ((32, 64, 64), (32, 64, 64), (32, 64, 64)),
+             ((33, 65, 130), (16, 64, 64), (16, 64, 64)), ((20, 96, 100), (8, 64, 64), (5, 17, 23)),
+             ((17, 64, 64), (16, 64, 64), (3, 64, 64))]
+    out = {"cases": np.array(cases)}
+    for i, (shape, patch, stride) in enumerate(cases):
+        sl = U.SliceBuilder._build_slices(np.zeros(shape, dtype=np.uint8), patch, stride)
+        out[f"slices{i}"] = np.array([[s.start for s in idx] + [s.stop for s in idx] for idx in sl])
+    rng = np.random.default_rng(0)
+    a3 = rng.standard_normal((6, 7, 9)).astype(np.float32)
+    a4 = rng.standard_normal((2, 6, 7, 9)).astype(np.float32)
+    out["pad_in3"], out["pad_in4"] = a3, a4
+    out["pad_out3"] = U.mirror_pad(a3, (2, 3, 4))
+    out["pad_out4"] = U.mirror_pad(a4, (1, 0, 5))
+    out["unpad_out4"] = U.remove_padding(U.mirror_pad(a4, (1, 0, 5))[None], (1, 0, 5))[0]
+    np.savez_compressed(os.path.join(OUT, "predictor_slices.npz"), **out)
+    print("predictor_slices", [len(out[f"slices{i}"]) for i in range(len(cases))])
+
+
 def main():
     torch.set_num_threads(8)
     os.makedirs(OUT, exist_ok=True)
@@ -315,6 +342,7 @@ def main():
     gen_unet3plus(ns)
     gen_unet3plus_deepsup(ns)
     gen_unet3plus_cgm(ns)
+    gen_predictor(ns)
 
 
 if __name__ == "__main__":

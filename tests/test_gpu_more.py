@@ -576,3 +576,79 @@ def test_unet3plus_cgm_vs_reference_golden(B):
     with torch.no_grad():
         a, b = net(x), net(x)
     assert all(torch.equal(p, q) for p, q in zip(a, b))
+
+
+class _RampModel(torch.nn.Module):
+    """A stand-in network whose output depends on the position INSIDE the patch and on a halo neighbourhood, so that
+    overlapping patches disagree and a wrong halo / reflect index / accumulation order shows up."""
+
+    def __init__(self, out_channels):
+        super().__init__()
+        self.w = torch.nn.Parameter(torch.linspace(0.5, 1.5, out_channels))
+
+    def forward(self, x):
+        d, h, w = x.shape[-3:]
+        ramp = (torch.arange(d, device=x.device).view(d, 1, 1) * 0.01 + torch.arange(h, device=x.device).view(1, h, 1)
+                * 0.001 + torch.arange(w, device=x.device).view(1, 1, w) * 0.0001).float()
+        nb = x[:, :1] + 0.5 * torch.roll(x[:, :1], shifts=(1, -2, 3), dims=(-3, -2, -1))
+        return (nb + ramp) * self.w.view(1, -1, 1, 1, 1)
+
+
+def test_sliding_window_predictor_vs_oracle(B):
+    """StandardPredictor on the device (predictor.py:65-165) against the numpy restatement of the reference's
+    loop: overlapping patches, mirror-padded halos, last patch flush with the end of the axis, channel selection,
+    arg-max segmentation — bit-identical (same fp32 summation order); then a real UNet3D through both entry points."""
+    from mdeical_image_segmentation_b200.predictor import StandardPredictor, build_slices
+    from oracle import predictor as OP
+    rng = np.random.default_rng(3)
+    raw = rng.standard_normal((2, 21, 70, 75)).astype(np.float32)
+    model = _RampModel(3).cuda()
+
+    def model_fn(batch):
+        with torch.no_grad():
+            return model(torch.from_numpy(batch).cuda()).cpu().numpy()
+
+    for halo, patch, stride, bs in (((0, 0, 0), (8, 64, 64), (8, 64, 64), 1), ((2, 4, 3), (8, 64, 64), (5, 3, 6), 3),
+                                    ((1, 0, 2), (21, 64, 70), (4, 5, 5), 2)):
+        want = OP.standard_predict(model_fn, raw, patch, stride, halo, out_channels=3, batch_size=bs)
+        got = StandardPredictor(model, out_channels=3).predict_volume(raw, patch, stride, halo, batch_size=bs)
+        assert got.shape == want.shape == (3, 21, 70, 75) and got.dtype == np.float32
+        assert np.array_equal(got, want), (halo, np.abs(got - want).max())
+        want = OP.standard_predict(model_fn, raw, patch, stride, halo, out_channels=3, prediction_channel=2, batch_size=bs)
+        got = StandardPredictor(model, out_channels=3, prediction_channel=2).predict_volume(raw, patch, stride, halo, bs)
+        assert got.shape == (1, 21, 70, 75) and np.array_equal(got, want)
+        want = OP.standard_predict(model_fn, raw, patch, stride, halo, out_channels=3, save_segmentation=True, batch_size=bs)
+        got = StandardPredictor(model, out_channels=3, save_segmentation=True).predict_volume(raw, patch, stride, halo, bs)
+        assert got.dtype == np.uint16 and np.array_equal(got, want)
+    # a real network (eval, no_grad) through predict_volume and through the reference-style loader protocol
+    torch.manual_seed(0)
+    net = B.UNet3D(1, 2, f_maps=[16, 32], num_levels=2, final_sigmoid=False).cuda()
+    vol = rng.standard_normal((24, 80, 72)).astype(np.float32)
+    patch, stride, halo = (16, 64, 64), (8, 16, 8), (0, 0, 0)
+
+    def net_fn(batch):
+        net.eval()
+        with torch.no_grad():
+            return net(torch.from_numpy(batch).cuda()).float().cpu().numpy()
+
+    want = OP.standard_predict(net_fn, vol, patch, stride, halo, out_channels=2)
+    got = StandardPredictor(net, out_channels=2).predict_volume(vol, patch, stride, halo, batch_size=1)
+    assert np.array_equal(got, want)
+    got4 = StandardPredictor(net, out_channels=2).predict_volume(vol, patch, stride, halo, batch_size=4)
+    assert np.abs(got4 - want).max() < 2e-2 * np.abs(want).max()          # batch 4 may pick other conv schedules
+
+    class _DS:
+        halo_shape = [0, 0, 0]
+
+        def volume_shape(self):
+            return vol.shape
+
+    class _Loader:                                                        # (input, indices) batches, as hdf5.py yields
+        dataset = _DS()
+
+        def __iter__(self):
+            for idx in build_slices(vol.shape, patch, stride):
+                yield torch.from_numpy(vol[idx][None, None]), [idx]
+
+    got2 = StandardPredictor(net, None, 2)(_Loader())
+    assert np.array_equal(got2, want)

@@ -260,3 +260,29 @@ def test_unet3plus_cgm_matches_reference():
             assert k.startswith("cls.") and sd[k].grad is None
         else:
             assert abs(sd[k].grad.norm().item() - norm) < 5e-3 * norm + 1e-6, k
+
+
+def test_predictor_patch_logic_matches_reference():
+    """SliceBuilder._build_slices / mirror_pad / remove_padding of the reference (fixture made from
+    dataset/unet3d_dataset/utils.py) against the oracle restatement AND the product's host-side logic."""
+    from oracle import predictor as OP
+    from mdeical_image_segmentation_b200 import predictor as PP
+    fix = load_golden("predictor_slices")
+    for i, (shape, patch, stride) in enumerate(fix["cases"].tolist()):
+        want = fix[f"slices{i}"].tolist()
+        for build in (OP.build_slices, PP.build_slices):
+            got = [[s.start for s in idx] + [s.stop for s in idx] for idx in build(shape, patch, stride)]
+            assert got == want, (i, build.__module__)
+    assert np.array_equal(OP.mirror_pad(fix["pad_in3"], (2, 3, 4)), fix["pad_out3"])
+    assert np.array_equal(OP.mirror_pad(fix["pad_in4"], (1, 0, 5)), fix["pad_out4"])
+    assert np.array_equal(OP.remove_padding(fix["pad_out4"][None], (1, 0, 5))[0], fix["unpad_out4"])
+    assert np.array_equal(fix["unpad_out4"], fix["pad_in4"])
+    assert PP.gen_indices(10, 10, 3) == [0] and PP.gen_indices(11, 4, 4) == [0, 4, 7]
+    import pytest
+    with pytest.raises(AssertionError):
+        PP.gen_indices(3, 4, 1)
+    # the whole oracle loop: an identity model through overlapping patches and a halo gives the volume back
+    rng = np.random.default_rng(1)
+    raw = rng.standard_normal((20, 70, 66)).astype(np.float32)
+    out = OP.standard_predict(lambda b: b, raw, (8, 64, 64), (5, 3, 2), halo_shape=(2, 4, 4))
+    assert out.shape == (1, 20, 70, 66) and np.abs(out[0] - raw).max() < 1e-6
