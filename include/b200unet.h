@@ -174,6 +174,8 @@ int b200_bilinear2d_fwd(int32_t n, int32_t ih, int32_t iw, int32_t c, int32_t sc
                         b200_view y, b200_stream_t stream);
 int b200_bilinear2d_bwd(int32_t n, int32_t ih, int32_t iw, int32_t c, int32_t scale, b200_view dy,
                         b200_view add, b200_view dx, void* scratch, b200_stream_t stream);
+/* y = relu(a + b): residual join of ResNetBlock (model/unet3d/buildingblocks.py:319-323) */
+int b200_add_relu(int64_t npos, int32_t c, b200_view a, b200_view b, b200_view y, b200_stream_t stream);
 /* dst += src: gradient accumulation for tensors that feed several full-scale skip branches */
 int b200_add(int64_t npos, int32_t c, b200_view src, b200_view dst, b200_stream_t stream);
 

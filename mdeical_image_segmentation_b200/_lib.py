@@ -75,6 +75,7 @@ SIGNATURES = {
     "b200_bilinear2d_fwd": [_I, _I, _I, _I, _I, View, View, _P],
     "b200_bilinear2d_bwd": [_I, _I, _I, _I, _I, View, View, View, _P, _P],
     "b200_add": [_L, _I, View, View, _P],
+    "b200_add_relu": [_L, _I, View, View, View, _P],
     "b200_msssim_fwd": [_I, _I, _I, _P, _P, _P, _P, _P, _F, _P],
     "b200_msssim_bwd": [_I, _I, _I, _P, _P, _P, _P, _P, _F, _P],
     "b200_cgm_gate": [_I, _L, _I, View, _P, _P, _P, _F, _P, _P, _P],

@@ -580,6 +580,21 @@ __global__ void __launch_bounds__(256)
         Vec<8>::store(dx.at(pos, ch), o);
       });
 }
+// y = relu(a + b): residual join of ResNetBlock (model/unet3d/buildingblocks.py:319-323)
+__global__ void __launch_bounds__(256) add_relu_kernel(long npos, int c, View a, View b, View y) {
+  const int cv = c / 8;
+  const long total = npos * cv;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const long pos = i / cv;
+    const int ch = (int)(i % cv) * 8;
+    float u[8], v[8];
+    Vec<8>::load(a.at(pos, ch), u);
+    Vec<8>::load(b.at(pos, ch), v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) u[j] = fmaxf(u[j] + v[j], 0.f);
+    Vec<8>::store(y.at(pos, ch), u);
+  }
+}
 // dst += src (gradient accumulation where a tensor feeds several branches)
 __global__ void __launch_bounds__(256) add_kernel(long npos, int c, View src, View dst) {
   const int cv = c / 8;
@@ -1516,6 +1531,14 @@ int b200_bilinear2d_bwd(int32_t n, int32_t ih, int32_t iw, int32_t c, int32_t sc
                                                                       (const float*)scratch, mk(add), mk(dx));
   }
 #undef BILINEAR_BWD_H
+  B200_LAUNCH_CHECK();
+  return B200_OK;
+}
+int b200_add_relu(int64_t npos, int32_t c, b200_view a, b200_view b, b200_view y, b200_stream_t stream) {
+  if (!vec8(c, a) || !vec8(c, b) || !vec8(c, y)) return B200_ERR_UNSUPPORTED;
+  const long total = (long)npos * (c / 8);
+  if (total <= 0) return B200_OK;
+  add_relu_kernel<<<GRID1D(total), 256, 0, (cudaStream_t)stream>>>((long)npos, c, mk(a), mk(b), mk(y));
   B200_LAUNCH_CHECK();
   return B200_OK;
 }

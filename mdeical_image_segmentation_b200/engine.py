@@ -645,6 +645,9 @@ class _NetFunction(torch.autograd.Function):
         with torch.no_grad():
             if kind == "unet2d":
                 feat = unet2d_forward(net, images, training, tape)
+            elif kind == "resunet3d":
+                from . import resnet_exec
+                feat = resnet_exec.forward(net, images, training, tape)
             else:
                 feat = unet3d_forward(net, images, training, tape)
             head = net.final_conv
@@ -675,6 +678,9 @@ class _NetFunction(torch.autograd.Function):
                 _acc(grads, head.bias, db)
             if ctx.kind == "unet2d":
                 unet2d_backward(net, tape, dfeat, grads, ctx.feat_relu)
+            elif ctx.kind == "resunet3d":
+                from . import resnet_exec
+                resnet_exec.backward(net, tape, dfeat, grads, ctx.feat_relu)
             else:
                 unet3d_backward(net, tape, dfeat, grads, ctx.feat_relu)
             _side_end(grads)

@@ -360,6 +360,13 @@ def bilinear_bwd(dy: CL, scale: int, add: Optional[CL] = None) -> CL:
     return out
 
 
+def add_relu(a: CL, b: CL) -> CL:
+    """relu(a + b) into a new tensor (residual join)."""
+    out = a.new_like()
+    call("b200_add_relu", a.npos, a.c, a.view(), b.view(), out.view(), _stream())
+    return out
+
+
 def add_(dst: CL, src: CL) -> CL:
     call("b200_add", dst.npos, dst.c, src.view(), dst.view(), _stream())
     return dst

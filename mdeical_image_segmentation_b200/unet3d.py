@@ -106,6 +106,34 @@ class DoubleConv(nn.Sequential):
         return engine.run_block(self, engine.double_conv_specs(self, self.order), x)
 
 
+class ResNetBlock(nn.Module):
+    """buildingblocks.py:255-325 — ``relu(conv3(conv2(r)) + r)`` with ``r = conv1(x)`` (1x1x1 conv when the channel
+    count changes).  Inside ``ResidualUNet3D`` the whole-network executor (resnet_exec.py) runs it; the
+    non-linearity is the ReLU of the ``r`` letter (``l`` / ``e`` orders are outside the B200 path)."""
+
+    def __init__(self, in_channels, out_channels, kernel_size=3, order="cge", num_groups=8, is3d=True, **kwargs):
+        super().__init__()
+        if "l" in order or "e" in order:
+            raise NotImplementedError("ResNetBlock with LeakyReLU / ELU (order letters l, e) is outside the B200 "
+                                      "hot path; use an order with 'r' (ResidualUNet3D's default is 'gcr')")
+        if in_channels != out_channels:
+            self.conv1 = (nn.Conv3d if is3d else nn.Conv2d)(in_channels, out_channels, 1)
+        else:
+            self.conv1 = nn.Identity()
+        self.conv2 = SingleConv(out_channels, out_channels, kernel_size=kernel_size, order=order,
+                                num_groups=num_groups, is3d=is3d)
+        n_order = order
+        for c in "rel":
+            n_order = n_order.replace(c, "")
+        self.conv3 = SingleConv(out_channels, out_channels, kernel_size=kernel_size, order=n_order,
+                                num_groups=num_groups, is3d=is3d)
+        self.non_linearity = nn.ReLU(inplace=True)
+        self.order = order
+
+    def forward(self, x):
+        raise NotImplementedError("ResNetBlock runs inside ResidualUNet3D's whole-network executor")
+
+
 class Encoder(nn.Module):
     """buildingblocks.py:365-439 — optional 2x max-pool, then the basic module."""
 
@@ -114,8 +142,8 @@ class Encoder(nn.Module):
                  num_groups=8, padding=1, upscale=2, dropout_prob=0.1, is3d=True):
         super().__init__()
         assert pool_type in ["max", "avg"]
-        if basic_module is not DoubleConv:
-            raise NotImplementedError("only DoubleConv encoders are on the B200 hot path")
+        if basic_module not in (DoubleConv, ResNetBlock):
+            raise NotImplementedError("only DoubleConv / ResNetBlock encoders are on the B200 hot path")
         if apply_pooling:
             if pool_type != "max" or pool_kernel_size != 2:
                 raise NotImplementedError("the B200 path implements 2x max-pooling")
@@ -194,19 +222,27 @@ class Decoder(nn.Module):
                  basic_module=DoubleConv, conv_layer_order="gcr", num_groups=8, padding=1,
                  upsample="default", dropout_prob=0.1, is3d=True):
         super().__init__()
-        if basic_module is not DoubleConv:
-            raise NotImplementedError("only DoubleConv decoders are on the B200 hot path")
+        if basic_module not in (DoubleConv, ResNetBlock):
+            raise NotImplementedError("only DoubleConv / ResNetBlock decoders are on the B200 hot path")
         if upsample is None or upsample == "none":
             raise NotImplementedError("decoders without up-sampling are outside the B200 hot path")
-        if upsample == "default":
-            upsample = "nearest"
+        concat = True
+        if upsample == "default":          # buildingblocks.py:486-501
+            if basic_module is DoubleConv:
+                upsample = "nearest"
+            else:
+                upsample, concat = "deconv", False      # learned up-sampling, summation joining,
+        if basic_module is ResNetBlock and (upsample != "deconv" or concat):
+            raise NotImplementedError("ResNetBlock decoders run with upsample='default' (deconv + summation)")
         if upsample == "deconv":
             self.upsampling = TransposeConvUpsampling(in_channels=in_channels, out_channels=out_channels,
                                                       kernel_size=conv_kernel_size,
                                                       scale_factor=scale_factor, is3d=is3d)
         else:
             self.upsampling = InterpolateUpsampling(mode=upsample)
-        self.joining = partial(self._joining, concat=True)
+        self.joining = partial(self._joining, concat=concat)
+        if not concat:
+            in_channels = out_channels                  # adapt_channels, buildingblocks.py:524-526
         self.basic_module = basic_module(in_channels, out_channels, encoder=False,
                                          kernel_size=conv_kernel_size, order=conv_layer_order,
                                          num_groups=num_groups, padding=padding,
@@ -272,8 +308,25 @@ class AbstractUNet(nn.Module):
         else:
             self.final_activation = None
 
+        self._kind = "resunet3d" if basic_module is ResNetBlock else "unet3d"
+
     def forward(self, x):
-        return engine.run_network(self, "unet3d", x)
+        return engine.run_network(self, self._kind, x)
+
+
+class ResidualUNet3D(AbstractUNet):
+    """model.py:197-238 — ResNetBlock levels, transposed-conv up-sampling, summation joining; 5 levels by
+    default.  ``state_dict`` keys as the reference: ``encoders.i.basic_module.{conv1,conv2.*,conv3.*}``,
+    ``decoders.i.upsampling.upsample.conv_transposed.weight``, ``final_conv``."""
+
+    def __init__(self, in_channels, out_channels, final_sigmoid=True, f_maps=64, layer_order="gcr",
+                 num_groups=8, num_levels=5, is_segmentation=True, conv_padding=1, conv_upscale=2,
+                 upsample="default", dropout_prob=0.1, **kwargs):
+        super().__init__(in_channels=in_channels, out_channels=out_channels,
+                         final_sigmoid=final_sigmoid, basic_module=ResNetBlock, f_maps=f_maps,
+                         layer_order=layer_order, num_groups=num_groups, num_levels=num_levels,
+                         is_segmentation=is_segmentation, conv_padding=conv_padding,
+                         conv_upscale=conv_upscale, upsample=upsample, dropout_prob=dropout_prob, is3d=True)
 
 
 class UNet3D(AbstractUNet):

@@ -105,6 +105,30 @@ def gen_unet3d(ns):
         print(name, "loss", loss.item())
 
 
+def gen_resunet3d(ns):
+    """ResidualUNet3D (model/unet3d/model.py:197-238) from the reference: weights, logits, loss, gradients."""
+    torch.manual_seed(0)
+    net = ns.M3.ResidualUNet3D(2, 2, f_maps=[8, 16, 32], num_groups=4)
+    net.train()
+    g = torch.Generator().manual_seed(78)
+    x = torch.randn((2, 2, 16, 16, 16), generator=g)
+    t = blob_target((2, 2, 16, 16, 16), 6)
+    sd0 = {k: v.clone() for k, v in net.state_dict().items()}
+    logits = net(x)
+    loss = ns.L3.BCEDiceLoss(1.0, 1.0)(logits, t)
+    loss.backward()
+    out = dict(x=_np(x), t=_np(t), logits=_np(logits), loss=_np(loss))
+    for k, v in sd0.items():
+        out["sd__" + k] = _np(v)
+    for k, p in net.named_parameters():
+        out["grad__" + k] = _np(p.grad)
+    net.eval()
+    with torch.no_grad():
+        out["logits_eval"] = _np(net(x))
+    np.savez_compressed(os.path.join(OUT, "resunet3d_gcr.npz"), **out)
+    print("resunet3d_gcr loss", loss.item(), len(sd0), "tensors")
+
+
 def gen_blocks(ns):
     torch.manual_seed(3)
     blk = ns.L2.unetConv2(3, 8, True)
@@ -337,6 +361,7 @@ def main():
     check_seed_init(ns)
     gen_unet2d(ns)
     gen_unet3d(ns)
+    gen_resunet3d(ns)
     gen_blocks(ns)
     gen_losses_metrics(ns)
     gen_unet3plus(ns)

@@ -153,6 +153,41 @@ def unet3d_forward(sd: SD, x: torch.Tensor, *, num_levels: int = 4, layer_order:
     return conv(x, sd[prefix + "final_conv.weight"], sd[prefix + "final_conv.bias"])
 
 
+def resnet_block(sd: SD, p: str, x, order, num_groups, is3d, training):
+    """buildingblocks.py:255-325 ResNetBlock: residual = conv1(x) (1x1 conv iff the channel count changes),
+    conv2 (SingleConv ``order``), conv3 (``order`` without its non-linearity), add, ReLU."""
+    conv = F.conv3d if is3d else F.conv2d
+    res = conv(x, sd[p + "conv1.weight"], sd[p + "conv1.bias"]) if p + "conv1.weight" in sd else x
+    n_order = order
+    for ch in "rel":
+        n_order = n_order.replace(ch, "")
+    out = single_conv(sd, p + "conv2.", res, order, num_groups, is3d, training)
+    out = single_conv(sd, p + "conv3.", out, n_order, num_groups, is3d, training)
+    return F.relu(out + res)
+
+
+def residual_unet3d_forward(sd: SD, x: torch.Tensor, *, num_levels: int = 5, layer_order: str = "gcr",
+                            num_groups: int = 8, is3d: bool = True, training: bool = True) -> torch.Tensor:
+    """model/unet3d/model.py:197-238 ResidualUNet3D: ResNetBlock levels, decoder = ConvTranspose(k3, s2, p1, no
+    bias) + nearest resize to the skip's size (buildingblocks.py:703-717), summation joining (:549),
+    ResNetBlock(out, out); 1x1 head; logits."""
+    pool = F.max_pool3d if is3d else F.max_pool2d
+    feats: List[torch.Tensor] = []
+    for i in range(num_levels):
+        if i > 0:
+            x = pool(x, 2)
+        x = resnet_block(sd, f"encoders.{i}.basic_module.", x, layer_order, num_groups, is3d, training)
+        feats.insert(0, x)
+    ct = F.conv_transpose3d if is3d else F.conv_transpose2d
+    for i, skip in enumerate(feats[1:]):
+        w = sd[f"decoders.{i}.upsampling.upsample.conv_transposed.weight"]
+        x = F.interpolate(ct(x, w, None, stride=2, padding=1), size=skip.shape[2:])
+        x = skip + x
+        x = resnet_block(sd, f"decoders.{i}.basic_module.", x, layer_order, num_groups, is3d, training)
+    conv = F.conv3d if is3d else F.conv2d
+    return conv(x, sd["final_conv.weight"], sd["final_conv.bias"])
+
+
 # ----------------------------------------------------------------------------------------- 3D losses
 def flatten_channels_first(t: torch.Tensor) -> torch.Tensor:
     """model/unet3d/losses.py:258-270 — (N, C, ...) -> (C, N * ...)."""
