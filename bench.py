@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Headline benchmark: U-Net training throughput on B200 (imgs/s for 2D, vols/s for 3D).
 
-    python bench.py --gpus N --steps K --warmup W [--workload cfg2|cfg3|cfg3p|cfg4|cfg4p|cfg1|u3p|u3pds|cfg5] [--impl reference]
+    python bench.py --gpus N --steps K --warmup W [--workload cfg2|cfg3|cfg3p|cfg4|cfg4p|cfg1|u3p|u3pds|res3d|cfg5] [--impl reference]
 
 A step = forward + loss + backward + optimizer step on one per-GPU batch of synthetic data (random-init
 weights of the named architecture).  One JSON line on rank 0 (see the keys at the bottom).  For N > 1
@@ -45,6 +45,10 @@ WORKLOADS = {
     "cfg4p": dict(kind="3d", cin=4, cout=3, size=(160, 192, 160), batch=1, train_tf=22.394, unit="vols/s",
                   order="cbr", upsample="deconv", loss="dice",
                   desc="UNet3D(4,3) cbr+deconv 160x192x160 (BraTS-like), batch 1 per GPU, fused Dice + Adam"),
+    # ResidualUNet3D(1,1), 5 levels 64..1024 (model/unet3d/model.py:197-238)
+    "res3d": dict(kind="3d", cin=1, cout=1, size=(128, 128, 128), batch=2, train_tf=11.2885, unit="vols/s",
+                  order="gcr", upsample="default", residual=True,
+                  desc="ResidualUNet3D(1,1) gcr, deconv + summation joining, 128^3, batch 2 per GPU, BCEDice + Adam"),
     # the default model of the reference's train.py (train.py:101-105)
     "u3p": dict(kind="2d", cin=3, cout=1, size=(512, 512), batch=8, train_tf=4.7428, unit="imgs/s",
                 unet_type="UNet_3Plus",
@@ -176,7 +180,10 @@ def build_model(w, device):
         def step_fn(x, y):
             return model(images=x, labels=y).loss
     else:
-        net = B.UNet3D(w["cin"], w["cout"], layer_order=w["order"], upsample=w["upsample"]).to(device).train()
+        if w.get("residual"):
+            net = B.ResidualUNet3D(w["cin"], w["cout"], layer_order=w["order"]).to(device).train()
+        else:
+            net = B.UNet3D(w["cin"], w["cout"], layer_order=w["order"], upsample=w["upsample"]).to(device).train()
         crit = B.DiceLoss(normalization="sigmoid") if w.get("loss") == "dice" else B.BCEDiceLoss(1.0, 1.0)
         model = net
         opt = torch.optim.Adam(model.parameters(), lr=1e-4, fused=True)
@@ -523,14 +530,20 @@ def run_cpu_sample(w, steps, warmup, batch=None):
         opt = torch.optim.AdamW(sd.values(), lr=1e-4, weight_decay=1e-3)
     else:
         b = batch or 1
-        net = B.UNet3D(w["cin"], w["cout"], layer_order=w["order"], upsample=w["upsample"])
+        if w.get("residual"):
+            net = B.ResidualUNet3D(w["cin"], w["cout"], layer_order=w["order"])
+        else:
+            net = B.UNet3D(w["cin"], w["cout"], layer_order=w["order"], upsample=w["upsample"])
         sd = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and "running" not in k else v.clone())
               for k, v in net.state_dict().items()}
         crop = dict(w, size=(64, 64, 64))
         x, y = make_batch(crop, b, 7)
         lossf = O.dice_loss if w.get("loss") == "dice" else O.bce_dice_loss
-        fwd = lambda: lossf(O.unet3d_forward(sd, x, layer_order=w["order"], upsample=w["upsample"],  # noqa: E731
-                                             training=True), y)
+        if w.get("residual"):
+            fwd = lambda: lossf(O.residual_unet3d_forward(sd, x, layer_order=w["order"]), y)  # noqa: E731
+        else:
+            fwd = lambda: lossf(O.unet3d_forward(sd, x, layer_order=w["order"], upsample=w["upsample"],  # noqa: E731
+                                                 training=True), y)
         scale = 64.0 ** 3 / (w["size"][0] * w["size"][1] * w["size"][2])
         sample = (f"{b} crop(s) of 64^3 per step, scaled by voxel count to "
                   f"{'x'.join(str(v) for v in w['size'])} volumes")

@@ -4,7 +4,7 @@ model/unet3d/buildingblocks.py and model/unet3d/model.py, executed by the sm_100
 
 In scope: ``layer_order`` strings over {g, b, c, r}, max-pool encoders, nearest or
 'deconv' (ConvTranspose k3 s2 p1 + nearest resize) decoders with concat joining, 1x1 head.
-Residual / SE blocks, LeakyReLU / ELU / dropout letters and avg-pool raise ``NotImplementedError``.
+SE blocks, LeakyReLU / ELU / dropout letters and avg-pool raise ``NotImplementedError``.
 """
 from __future__ import annotations
 

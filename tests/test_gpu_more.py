@@ -687,7 +687,7 @@ def test_residual_unet3d_vs_reference_golden_and_trained(B):
     shape = (2, 1, 32, 32, 32)
     fwd = lambda s, xx: O.residual_unet3d_forward(s, xx, num_levels=3)  # noqa: E731
     sd = _train_oracle(sd, fwd, O.bce_dice_loss, shape, steps=40)
-    x, m = _blob_task(shape, 999)
+    x, m = _blob_task((2, 1, 48, 48, 48), 999)   # fully convolutional: compared on a larger volume than it trained on
     for v in sd.values():
         v.grad = None
     ref_logits = fwd(sd, x)
