@@ -317,6 +317,22 @@ int b200_gate_sigmoid_fwd(int32_t n, int64_t per_sample, const float* x, const f
 int b200_gate_sigmoid_bwd(int32_t n, int64_t per_sample, const float* y, const float* dy, const float* gate,
                           float* dx, b200_stream_t stream);
 
+/* ---- concurrent spatial and channel squeeze-and-excitation (model/unet3d/se.py:18-113 ChannelSpatialSELayer3D as
+ * applied by ResNetBlockSE, buildingblocks.py:328-362) on a channels-last bf16 ReLU output y (n, spatial, c), c <= 1024:
+ *   z = max(y * a[n,c], y * sigmoid(s[n,pos])) = y * max(a, b);  a = cSE gate (fp32 [n][c], computed by the caller from
+ *   the squeeze with two small FCs), s = sSE logits (fp32 [n][spatial], the 1x1x1 conv = b200_head_fwd).
+ * channel_sums: sums fp64 [n][c] += sum_pos y (caller zeroes).   gate_fwd: z.
+ * gate_bwd_reduce: da fp64 [n][c] += sum_pos g*y*[a >= b] (caller zeroes); ds fp32 [n][spatial] = d(loss)/d(s).
+ * gate_bwd_apply: dy = g*max(a,b) + (y > 0 ? dmean[n][c] : 0) + dsse, with dmean = d(loss)/d(squeeze) / spatial and
+ *   dsse = the sSE conv's data gradient (b200_head_bwd, masked by y > 0); g must already carry z's ReLU mask. */
+int b200_se_channel_sums(int32_t n, int64_t spatial, int32_t c, b200_view y, double* sums, b200_stream_t stream);
+int b200_se_gate_fwd(int32_t n, int64_t spatial, int32_t c, b200_view y, const float* a, const float* s, b200_view z,
+                     b200_stream_t stream);
+int b200_se_gate_bwd_reduce(int32_t n, int64_t spatial, int32_t c, b200_view y, const float* a, const float* s,
+                            b200_view g, double* da, float* ds, b200_stream_t stream);
+int b200_se_gate_bwd_apply(int32_t n, int64_t spatial, int32_t c, b200_view y, const float* a, const float* s,
+                           b200_view g, const float* dmean, b200_view dsse, b200_view dy, b200_stream_t stream);
+
 /* ---- sliding-window prediction on the device (model/unet3d/predictor.py:65-165; SliceBuilder / mirror_pad /
  * remove_padding of dataset/unet3d_dataset/utils.py:40-131, 314-361).  fp32 NCDHW, caller-owned buffers.
  * gather: out (c, pd, ph, pw) = the window of vol (c, d, h, w) that starts `halo` before the patch origin (oz, oy, ox),

@@ -84,6 +84,10 @@ SIGNATURES = {
     "b200_patch_gather": [_I, _I, _I, _I, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P],
     "b200_patch_accumulate": [_I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _I, _I, _I, _I, _I, _P, _P, _P],
     "b200_prediction_finalize": [_I, _L, _P, _P, _P, _P],
+    "b200_se_channel_sums": [_I, _L, _I, View, _P, _P],
+    "b200_se_gate_fwd": [_I, _L, _I, View, _P, _P, View, _P],
+    "b200_se_gate_bwd_reduce": [_I, _L, _I, View, _P, _P, View, _P, _P, _P],
+    "b200_se_gate_bwd_apply": [_I, _L, _I, View, _P, _P, View, _P, View, View, _P],
     "b200_im2col3": [_I, _I, _I, _I, _I, _I, _I, View, _P, _P],
     "b200_nchw_f32_to_cl_bf16": [_I, _I, _L, _P, View, _P],
     "b200_cl_bf16_to_nchw_f32": [_I, _I, _L, View, _P, _P],

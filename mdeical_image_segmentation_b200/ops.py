@@ -563,6 +563,34 @@ def seg_sums(logits: torch.Tensor, target: torch.Tensor, normalization: int = 0)
     return sums
 
 
+def se_channel_means(y: CL) -> torch.Tensor:
+    """(n, c) fp32 per-sample channel means of y (the squeeze of cSE, se.py:46)."""
+    sums = torch.zeros((y.n, y.c), dtype=torch.float64, device=y.device)
+    call("b200_se_channel_sums", y.n, y.spatial, y.c, y.view(), _p(sums), _stream())
+    return (sums / float(y.spatial)).float()
+
+
+def se_gate_fwd(y: CL, a: torch.Tensor, s: torch.Tensor) -> CL:
+    """z = y * max(a[n, c], sigmoid(s[n, pos]))."""
+    z = y.new_like()
+    call("b200_se_gate_fwd", y.n, y.spatial, y.c, y.view(), _p(a), _p(s), z.view(), _stream())
+    return z
+
+
+def se_gate_bwd_reduce(y: CL, a: torch.Tensor, s: torch.Tensor, g: CL):
+    da = torch.zeros((y.n, y.c), dtype=torch.float64, device=y.device)
+    ds = torch.empty_like(s)
+    call("b200_se_gate_bwd_reduce", y.n, y.spatial, y.c, y.view(), _p(a), _p(s), g.view(), _p(da), _p(ds), _stream())
+    return da.float(), ds
+
+
+def se_gate_bwd_apply(y: CL, a: torch.Tensor, s: torch.Tensor, g: CL, dmean: torch.Tensor, dsse: CL) -> CL:
+    dy = y.new_like()
+    call("b200_se_gate_bwd_apply", y.n, y.spatial, y.c, y.view(), _p(a), _p(s), g.view(), _p(dmean), dsse.view(),
+         dy.view(), _stream())
+    return dy
+
+
 def cgm_gate(x: CL, weight: torch.Tensor, bias: torch.Tensor, keep: Optional[torch.Tensor] = None,
              keep_scale: float = 1.0):
     """(gate (n,), cls (n, 2)): arg-max class gate of the UNet 3+ classification branch on hd5."""

@@ -1,5 +1,5 @@
-"""Whole-network executor of the residual U-Net (``ResidualUNet3D``, model/unet3d/model.py:197-238) —
-SURVEY.md §8(f) rank 2.
+"""Whole-network executor of the residual U-Nets (``ResidualUNet3D`` / ``ResidualUNetSE3D``,
+model/unet3d/model.py:197-280) — SURVEY.md §8(f) rank 2.
 
 Topology (buildingblocks.py:255-325, 442-550, 604-639): encoder level = [2x max-pool] -> ResNetBlock; decoder
 level = ConvTranspose(k3, s2, p1, no bias) + nearest resize to the skip's size -> **summation** joining ->
@@ -46,12 +46,50 @@ def _block_fwd(block, order: str, x: CL, training: bool, want: bool):
     out, _, _ = engine.single_conv_fwd(res, s2, training, t2)
     out, _, _ = engine.single_conv_fwd(out, s3, training, t3)
     y = ops.add_relu(out, res)
-    return y, (t1, t2, t3, isinstance(block.conv1, nn.Identity))
+    se_rec = None
+    if hasattr(block, "se_module"):
+        y, se_rec = _se_fwd(block.se_module, y, want)
+    return y, (t1, t2, t3, isinstance(block.conv1, nn.Identity), se_rec)
+
+
+def _se_fwd(se, y: CL, want: bool):
+    """ChannelSpatialSELayer3D (se.py:100-113) on a block output: z = y * max(cSE gate, sSE gate)."""
+    cse, sse = se.cSE, se.sSE
+    squeeze = ops.se_channel_means(y)                                    # (n, c), se.py:46
+    with torch.enable_grad():                                             # two tiny FCs: library GEMMs + autograd
+        sq = squeeze.detach().requires_grad_(want)
+        hidden = torch.relu(torch.nn.functional.linear(sq, cse.fc1.weight, cse.fc1.bias))
+        a = torch.sigmoid(torch.nn.functional.linear(hidden, cse.fc2.weight, cse.fc2.bias))
+    a_val = a.detach().float().contiguous()
+    bias = None if sse.conv.bias is None else sse.conv.bias.detach().float().contiguous()
+    s = ops.head_fwd(y, sse.conv.weight, bias, True)                      # sSE logits (n, 1, d, h, w), se.py:88
+    z = ops.se_gate_fwd(y, a_val, s)
+    return z, ((y, a, sq, a_val, s, se) if want else None)
+
+
+def _se_bwd(g: CL, rec, grads: engine.Grads) -> CL:
+    """g = d(loss)/dz masked by z > 0 (== y > 0).  Returns d(loss)/d(out + residual), masked."""
+    y, a, sq, a_val, s, se = rec
+    cse, sse = se.cSE, se.sSE
+    da, ds = ops.se_gate_bwd_reduce(y, a_val, s, g)
+    params = [cse.fc1.weight, cse.fc1.bias, cse.fc2.weight, cse.fc2.bias]
+    dsq, *dps = torch.autograd.grad(a, [sq] + params, grad_outputs=da.to(a.dtype), allow_unused=True)
+    for p, dp in zip(params, dps):
+        if dp is not None:
+            engine._acc(grads, p, dp.float())
+    dsse, dw, db = ops.head_bwd(y, sse.conv.weight, ds, mask_relu=True)
+    engine._acc(grads, sse.conv.weight, dw)
+    if sse.conv.bias is not None:
+        engine._acc(grads, sse.conv.bias, db)
+    dmean = (dsq.float() / float(y.spatial)).contiguous()
+    return ops.se_gate_bwd_apply(y, a_val, s, g, dmean, dsse)
 
 
 def _block_bwd(g: CL, rec, grads: engine.Grads, need_dx: bool = True) -> Optional[CL]:
     """g = d(loss)/d(out + residual), i.e. already masked by the block's final ReLU.  g is only read."""
-    t1, t2, t3, identity = rec
+    t1, t2, t3, identity, se_rec = rec
+    if se_rec is not None:
+        g = _se_bwd(g, se_rec, grads)
     d, _, _ = engine.single_conv_bwd(g, t3, grads)            # conv3 has no ReLU: g is not clobbered
     d, _, _ = engine.single_conv_bwd(d, t2, grads)
     d = ops.add_(d, g)                                        # + the skip connection's share

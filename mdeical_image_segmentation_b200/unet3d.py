@@ -134,6 +134,49 @@ class ResNetBlock(nn.Module):
         raise NotImplementedError("ResNetBlock runs inside ResidualUNet3D's whole-network executor")
 
 
+class ChannelSELayer3D(nn.Module):
+    """se.py:18-57 (parameter container: ``fc1``, ``fc2``)."""
+
+    def __init__(self, num_channels, reduction_ratio=2):
+        super().__init__()
+        self.reduction_ratio = reduction_ratio
+        self.fc1 = nn.Linear(num_channels, num_channels // reduction_ratio, bias=True)
+        self.fc2 = nn.Linear(num_channels // reduction_ratio, num_channels, bias=True)
+
+
+class SpatialSELayer3D(nn.Module):
+    """se.py:60-97 (parameter container: ``conv`` = Conv3d(C, 1, 1))."""
+
+    def __init__(self, num_channels):
+        super().__init__()
+        self.conv = nn.Conv3d(num_channels, 1, 1)
+
+
+class ChannelSpatialSELayer3D(nn.Module):
+    """se.py:100-113: ``max(cSE(x), sSE(x))`` — executed by ``b200_se_*`` inside the residual executor."""
+
+    def __init__(self, num_channels, reduction_ratio=2):
+        super().__init__()
+        self.cSE = ChannelSELayer3D(num_channels, reduction_ratio)
+        self.sSE = SpatialSELayer3D(num_channels)
+
+
+class ResNetBlockSE(ResNetBlock):
+    """buildingblocks.py:328-362 — ResNetBlock followed by the concurrent spatial and channel SE gate
+    (``se_module='scse'``, the only variant ``ResidualUNetSE3D`` builds)."""
+
+    def __init__(self, in_channels, out_channels, kernel_size=3, order="cge", num_groups=8, se_module="scse",
+                 **kwargs):
+        super().__init__(in_channels, out_channels, kernel_size=kernel_size, order=order,
+                         num_groups=num_groups, **kwargs)
+        assert se_module in ["scse", "cse", "sse"]
+        if se_module != "scse":
+            raise NotImplementedError("the B200 path implements se_module='scse' (ResidualUNetSE3D's default)")
+        if out_channels > 1024:
+            raise NotImplementedError("SE blocks wider than 1024 channels are outside the B200 path")
+        self.se_module = ChannelSpatialSELayer3D(num_channels=out_channels, reduction_ratio=1)
+
+
 class Encoder(nn.Module):
     """buildingblocks.py:365-439 — optional 2x max-pool, then the basic module."""
 
@@ -142,8 +185,8 @@ class Encoder(nn.Module):
                  num_groups=8, padding=1, upscale=2, dropout_prob=0.1, is3d=True):
         super().__init__()
         assert pool_type in ["max", "avg"]
-        if basic_module not in (DoubleConv, ResNetBlock):
-            raise NotImplementedError("only DoubleConv / ResNetBlock encoders are on the B200 hot path")
+        if basic_module not in (DoubleConv, ResNetBlock, ResNetBlockSE):
+            raise NotImplementedError("only DoubleConv / ResNetBlock(SE) encoders are on the B200 hot path")
         if apply_pooling:
             if pool_type != "max" or pool_kernel_size != 2:
                 raise NotImplementedError("the B200 path implements 2x max-pooling")
@@ -222,8 +265,8 @@ class Decoder(nn.Module):
                  basic_module=DoubleConv, conv_layer_order="gcr", num_groups=8, padding=1,
                  upsample="default", dropout_prob=0.1, is3d=True):
         super().__init__()
-        if basic_module not in (DoubleConv, ResNetBlock):
-            raise NotImplementedError("only DoubleConv / ResNetBlock decoders are on the B200 hot path")
+        if basic_module not in (DoubleConv, ResNetBlock, ResNetBlockSE):
+            raise NotImplementedError("only DoubleConv / ResNetBlock(SE) decoders are on the B200 hot path")
         if upsample is None or upsample == "none":
             raise NotImplementedError("decoders without up-sampling are outside the B200 hot path")
         concat = True
@@ -232,7 +275,7 @@ class Decoder(nn.Module):
                 upsample = "nearest"
             else:
                 upsample, concat = "deconv", False      # learned up-sampling, summation joining,
-        if basic_module is ResNetBlock and (upsample != "deconv" or concat):
+        if basic_module is not DoubleConv and (upsample != "deconv" or concat):
             raise NotImplementedError("ResNetBlock decoders run with upsample='default' (deconv + summation)")
         if upsample == "deconv":
             self.upsampling = TransposeConvUpsampling(in_channels=in_channels, out_channels=out_channels,
@@ -308,7 +351,7 @@ class AbstractUNet(nn.Module):
         else:
             self.final_activation = None
 
-        self._kind = "resunet3d" if basic_module is ResNetBlock else "unet3d"
+        self._kind = "unet3d" if basic_module is DoubleConv else "resunet3d"
 
     def forward(self, x):
         return engine.run_network(self, self._kind, x)
@@ -324,6 +367,19 @@ class ResidualUNet3D(AbstractUNet):
                  upsample="default", dropout_prob=0.1, **kwargs):
         super().__init__(in_channels=in_channels, out_channels=out_channels,
                          final_sigmoid=final_sigmoid, basic_module=ResNetBlock, f_maps=f_maps,
+                         layer_order=layer_order, num_groups=num_groups, num_levels=num_levels,
+                         is_segmentation=is_segmentation, conv_padding=conv_padding,
+                         conv_upscale=conv_upscale, upsample=upsample, dropout_prob=dropout_prob, is3d=True)
+
+
+class ResidualUNetSE3D(AbstractUNet):
+    """model.py:241-280 — ResidualUNet3D with ResNetBlockSE levels (scSE gate after every block)."""
+
+    def __init__(self, in_channels, out_channels, final_sigmoid=True, f_maps=64, layer_order="gcr",
+                 num_groups=8, num_levels=5, is_segmentation=True, conv_padding=1, conv_upscale=2,
+                 upsample="default", dropout_prob=0.1, **kwargs):
+        super().__init__(in_channels=in_channels, out_channels=out_channels,
+                         final_sigmoid=final_sigmoid, basic_module=ResNetBlockSE, f_maps=f_maps,
                          layer_order=layer_order, num_groups=num_groups, num_levels=num_levels,
                          is_segmentation=is_segmentation, conv_padding=conv_padding,
                          conv_upscale=conv_upscale, upsample=upsample, dropout_prob=dropout_prob, is3d=True)
@@ -393,9 +449,11 @@ if PreTrainedModel is not None:
 
         def __init__(self, config):
             super().__init__(config)
-            if config.unet_type != "UNet3D":
-                raise NotImplementedError(f"{config.unet_type}: residual variants are outside the hot path")
-            self.model = UNet3D(in_channels=config.in_channels, out_channels=config.out_channels,
+            nets = {"UNet3D": UNet3D, "ResidualUNet3D": ResidualUNet3D, "ResidualUNetSE3D": ResidualUNetSE3D}
+            if config.unet_type not in nets:                                 # UNet3D.py:72-118
+                raise NotImplementedError(f"unet_type={config.unet_type!r} (the reference knows {sorted(nets)})")
+            net_cls = nets[config.unet_type]
+            self.model = net_cls(in_channels=config.in_channels, out_channels=config.out_channels,
                                 final_sigmoid=config.final_sigmoid, f_maps=config.f_maps,
                                 layer_order=config.layer_order, num_groups=config.num_groups,
                                 num_levels=config.num_levels, is_segmentation=config.is_segmentation,

@@ -107,8 +107,13 @@ def gen_unet3d(ns):
 
 def gen_resunet3d(ns):
     """ResidualUNet3D (model/unet3d/model.py:197-238) from the reference: weights, logits, loss, gradients."""
+    for name, cls in (("resunet3d_gcr", ns.M3.ResidualUNet3D), ("resunetse3d_gcr", ns.M3.ResidualUNetSE3D)):
+        _gen_resunet3d(ns, name, cls)
+
+
+def _gen_resunet3d(ns, name, cls):
     torch.manual_seed(0)
-    net = ns.M3.ResidualUNet3D(2, 2, f_maps=[8, 16, 32], num_groups=4)
+    net = cls(2, 2, f_maps=[8, 16, 32], num_groups=4)
     net.train()
     g = torch.Generator().manual_seed(78)
     x = torch.randn((2, 2, 16, 16, 16), generator=g)
@@ -125,8 +130,8 @@ def gen_resunet3d(ns):
     net.eval()
     with torch.no_grad():
         out["logits_eval"] = _np(net(x))
-    np.savez_compressed(os.path.join(OUT, "resunet3d_gcr.npz"), **out)
-    print("resunet3d_gcr loss", loss.item(), len(sd0), "tensors")
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
+    print(name, "loss", loss.item(), len(sd0), "tensors")
 
 
 def gen_blocks(ns):

@@ -155,7 +155,8 @@ def unet3d_forward(sd: SD, x: torch.Tensor, *, num_levels: int = 4, layer_order:
 
 def resnet_block(sd: SD, p: str, x, order, num_groups, is3d, training):
     """buildingblocks.py:255-325 ResNetBlock: residual = conv1(x) (1x1 conv iff the channel count changes),
-    conv2 (SingleConv ``order``), conv3 (``order`` without its non-linearity), add, ReLU."""
+    conv2 (SingleConv ``order``), conv3 (``order`` without its non-linearity), add, ReLU; with ``se_module.*``
+    weights present, ResNetBlockSE (:328-362): the scSE gate of model/unet3d/se.py:18-113 on the result."""
     conv = F.conv3d if is3d else F.conv2d
     res = conv(x, sd[p + "conv1.weight"], sd[p + "conv1.bias"]) if p + "conv1.weight" in sd else x
     n_order = order
@@ -163,7 +164,15 @@ def resnet_block(sd: SD, p: str, x, order, num_groups, is3d, training):
         n_order = n_order.replace(ch, "")
     out = single_conv(sd, p + "conv2.", res, order, num_groups, is3d, training)
     out = single_conv(sd, p + "conv3.", out, n_order, num_groups, is3d, training)
-    return F.relu(out + res)
+    out = F.relu(out + res)
+    q = p + "se_module."
+    if q + "cSE.fc1.weight" in sd:                                  # ResNetBlockSE, buildingblocks.py:328-362
+        squeeze = out.mean(dim=(2, 3, 4))                           # se.py:46 (AdaptiveAvgPool3d(1))
+        a = torch.sigmoid(F.linear(F.relu(F.linear(squeeze, sd[q + "cSE.fc1.weight"], sd[q + "cSE.fc1.bias"])),
+                                   sd[q + "cSE.fc2.weight"], sd[q + "cSE.fc2.bias"]))          # :49-50
+        b = torch.sigmoid(F.conv3d(out, sd[q + "sSE.conv.weight"], sd[q + "sSE.conv.bias"]))    # :88-90
+        out = torch.max(out * a[:, :, None, None, None], out * b)                               # :52, :93, :112
+    return out
 
 
 def residual_unet3d_forward(sd: SD, x: torch.Tensor, *, num_levels: int = 5, layer_order: str = "gcr",

@@ -654,15 +654,16 @@ def test_sliding_window_predictor_vs_oracle(B):
     assert np.array_equal(got2, want)
 
 
-def test_residual_unet3d_vs_reference_golden_and_trained(B):
+@pytest.mark.parametrize("name,cls", [("resunet3d_gcr", "ResidualUNet3D"), ("resunetse3d_gcr", "ResidualUNetSE3D")])
+def test_residual_unet3d_vs_reference_golden_and_trained(B, name, cls):
     """ResidualUNet3D (model.py:197-238): (i) the reference's own run (random init +
     noise: the loose bounds of the other golden tests), (ii) a trained fixture at the north-star tolerances —
     logits rel-L2 / max-norm <= 2e-2, masks >= 99.9 %, loss <= 1e-3, concatenated parameter gradient <= 2e-2."""
     from conftest import load_golden, sd_from
     from oracle import unet as O
     from test_gpu_parity import _blob_task, _global_rel, _grads, _train_oracle
-    fix = load_golden("resunet3d_gcr")
-    net = B.ResidualUNet3D(2, 2, f_maps=[8, 16, 32], num_groups=4)
+    fix = load_golden(name)
+    net = getattr(B, cls)(2, 2, f_maps=[8, 16, 32], num_groups=4)
     net.load_state_dict(sd_from(fix), strict=True)
     net = net.cuda().train()
     x, t = torch.from_numpy(fix["x"]).cuda(), torch.from_numpy(fix["t"]).cuda()
@@ -674,7 +675,7 @@ def test_residual_unet3d_vs_reference_golden_and_trained(B):
     g = _grads(net)
     ref = {k[6:]: torch.from_numpy(v) for k, v in fix.items() if k.startswith("grad__")}
     assert set(g) == set(ref)
-    print("ResidualUNet3D golden: logits", rel_l2(logits.cpu(), fix["logits"]), "gradient", _global_rel(g, ref, sorted(ref)))
+    print(cls, "golden: logits", rel_l2(logits.cpu(), fix["logits"]), "gradient", _global_rel(g, ref, sorted(ref)))
     assert _global_rel(g, ref, sorted(ref)) < 0.35
     net.eval()
     with torch.no_grad():
@@ -682,7 +683,7 @@ def test_residual_unet3d_vs_reference_golden_and_trained(B):
     # ---- trained fixture
     torch.manual_seed(0)
     torch.set_num_threads(max(1, min(8, torch.get_num_threads())))
-    net = B.ResidualUNet3D(1, 1, f_maps=[16, 32, 64])
+    net = getattr(B, cls)(1, 1, f_maps=[16, 32, 64])
     sd = {k: v.clone() for k, v in net.state_dict().items()}
     shape = (2, 1, 32, 32, 32)
     fwd = lambda s, xx: O.residual_unet3d_forward(s, xx, num_levels=3)  # noqa: E731
@@ -701,7 +702,7 @@ def test_residual_unet3d_vs_reference_golden_and_trained(B):
     loss.backward()
     lg, rl = logits.detach().cpu(), ref_logits.detach()
     g = _grads(net)
-    print("ResidualUNet3D trained: logits", rel_l2(lg, rl), "gradient", _global_rel(g, ref_g, sorted(ref_g)),
+    print(cls, "trained: logits", rel_l2(lg, rl), "gradient", _global_rel(g, ref_g, sorted(ref_g)),
           "masks", ((lg > 0) == (rl > 0)).float().mean().item())
     assert rel_l2(lg, rl) < 2e-2
     assert (lg - rl).abs().max() / rl.abs().max() < 2e-2

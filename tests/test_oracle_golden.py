@@ -288,10 +288,11 @@ def test_predictor_patch_logic_matches_reference():
     assert out.shape == (1, 20, 70, 66) and np.abs(out[0] - raw).max() < 1e-6
 
 
-def test_residual_unet3d_matches_reference():
-    """ResidualUNet3D (model.py:197-238): oracle restatement against the reference's run — logits, loss, every
-    parameter gradient, eval mode — and the product module's state_dict layout against the reference's keys."""
-    fix = load_golden("resunet3d_gcr")
+@pytest.mark.parametrize("name,cls", [("resunet3d_gcr", "ResidualUNet3D"), ("resunetse3d_gcr", "ResidualUNetSE3D")])
+def test_residual_unet3d_matches_reference(name, cls):
+    """ResidualUNet3D / ResidualUNetSE3D (model.py:197-280): oracle restatement against the reference's run —
+    logits, loss, every parameter gradient — and the product module's state_dict layout against the reference's."""
+    fix = load_golden(name)
     sd = sd_from(fix)
     for v in sd.values():
         v.requires_grad_(True)
@@ -306,13 +307,12 @@ def test_residual_unet3d_matches_reference():
             err = (sd[k[6:]].grad - torch.from_numpy(v)).norm().item()
             assert err < 1e-3 * (np.linalg.norm(v) + 1e-4), (k, err)
     import mdeical_image_segmentation_b200 as B
-    net = B.ResidualUNet3D(2, 2, f_maps=[8, 16, 32], num_groups=4)
+    net = getattr(B, cls)(2, 2, f_maps=[8, 16, 32], num_groups=4)
     assert list(net.state_dict().keys()) == [k[4:] for k in fix if k.startswith("sd__")]
     net.load_state_dict(sd_from(fix), strict=True)
     assert [tuple(v.shape) for v in net.state_dict().values()] == [fix[k].shape for k in fix if k.startswith("sd__")]
-    default = B.ResidualUNet3D(1, 1)                     # 5 levels, 64..1024 feature maps (model.py:207-213)
+    default = getattr(B, cls)(1, 1)                      # 5 levels, 64..1024 feature maps (model.py:207-213)
     assert len(default.encoders) == 5 and len(default.decoders) == 4
     assert default.encoders[4].basic_module.conv2.conv.out_channels == 1024
-    import pytest
     with pytest.raises(NotImplementedError):
         B.ResidualUNet3D(1, 1, layer_order="cge")
