@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Headline benchmark: U-Net training throughput on B200 (imgs/s for 2D, vols/s for 3D).
 
-    python bench.py --gpus N --steps K --warmup W [--workload cfg2|cfg3|cfg3p|cfg4|cfg4p|cfg1|u3p|u3pds|res3d|cfg5] [--impl reference]
+    python bench.py --gpus N --steps K --warmup W [--workload cfg2|cfg3|cfg3p|cfg4|cfg4p|cfg1|u3p|u3pds|res3d|res3dse|cfg5] [--impl reference]
 
 A step = forward + loss + backward + optimizer step on one per-GPU batch of synthetic data (random-init
 weights of the named architecture).  One JSON line on rank 0 (see the keys at the bottom).  For N > 1
@@ -49,6 +49,9 @@ WORKLOADS = {
     "res3d": dict(kind="3d", cin=1, cout=1, size=(128, 128, 128), batch=2, train_tf=11.2885, unit="vols/s",
                   order="gcr", upsample="default", residual=True,
                   desc="ResidualUNet3D(1,1) gcr, deconv + summation joining, 128^3, batch 2 per GPU, BCEDice + Adam"),
+    "res3dse": dict(kind="3d", cin=1, cout=1, size=(128, 128, 128), batch=2, train_tf=11.2885, unit="vols/s",
+                    order="gcr", upsample="default", residual="se",
+                    desc="ResidualUNetSE3D(1,1) gcr (scSE gate after every block), 128^3, batch 2 per GPU, BCEDice + Adam"),
     # the default model of the reference's train.py (train.py:101-105)
     "u3p": dict(kind="2d", cin=3, cout=1, size=(512, 512), batch=8, train_tf=4.7428, unit="imgs/s",
                 unet_type="UNet_3Plus",
@@ -181,7 +184,8 @@ def build_model(w, device):
             return model(images=x, labels=y).loss
     else:
         if w.get("residual"):
-            net = B.ResidualUNet3D(w["cin"], w["cout"], layer_order=w["order"]).to(device).train()
+            cls = B.ResidualUNetSE3D if w["residual"] == "se" else B.ResidualUNet3D
+            net = cls(w["cin"], w["cout"], layer_order=w["order"]).to(device).train()
         else:
             net = B.UNet3D(w["cin"], w["cout"], layer_order=w["order"], upsample=w["upsample"]).to(device).train()
         crit = B.DiceLoss(normalization="sigmoid") if w.get("loss") == "dice" else B.BCEDiceLoss(1.0, 1.0)
@@ -531,7 +535,8 @@ def run_cpu_sample(w, steps, warmup, batch=None):
     else:
         b = batch or 1
         if w.get("residual"):
-            net = B.ResidualUNet3D(w["cin"], w["cout"], layer_order=w["order"])
+            net = (B.ResidualUNetSE3D if w["residual"] == "se" else B.ResidualUNet3D)(w["cin"], w["cout"],
+                                                                                      layer_order=w["order"])
         else:
             net = B.UNet3D(w["cin"], w["cout"], layer_order=w["order"], upsample=w["upsample"])
         sd = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and "running" not in k else v.clone())
