@@ -711,3 +711,34 @@ def test_residual_unet3d_vs_reference_golden_and_trained(B, name, cls):
     # the SE gate's max(a, b) hands a position's gradient to ONE of the two gates: where they are close, bf16 noise
     # flips the branch, so the SE variant sits at the 2e-2 bar itself (measured 1.99e-2; plain residual 7.7e-3)
     assert _global_rel(g, ref_g, sorted(ref_g)) < (3e-2 if "SE" in cls else 2e-2)
+
+
+@pytest.mark.parametrize("c", [8, 24, 64, 256, 512, 1024])
+def test_se_gate_kernels_vs_torch(B, c):
+    """The four scSE kernels (every lane-mapping variant: 1..32 lanes per position, 1/2/4 vectors per lane) against
+    the formulas of model/unet3d/se.py written in torch on the same bf16-representable inputs."""
+    from mdeical_image_segmentation_b200 import ops
+    g = torch.Generator().manual_seed(c)
+    n, dims = 2, (3, 5, 7)
+    spatial = dims[0] * dims[1] * dims[2]
+    y = torch.relu(torch.randn((n, c) + dims, generator=g)).bfloat16().float().cuda()         # a ReLU output
+    a = torch.sigmoid(torch.randn((n, c), generator=g)).cuda().contiguous()
+    s = torch.randn((n, 1) + dims, generator=g).cuda().contiguous()
+    gz = torch.randn((n, c) + dims, generator=g).bfloat16().float().cuda() * (y > 0)           # masked, as the executor's
+    dsse = torch.randn((n, c) + dims, generator=g).bfloat16().float().cuda()
+    dmean = torch.randn((n, c), generator=g).cuda().contiguous()
+    ycl, gcl, dcl = ops.from_nchw(y), ops.from_nchw(gz), ops.from_nchw(dsse)
+    assert torch.allclose(ops.se_channel_means(ycl), y.mean(dim=(2, 3, 4)), rtol=1e-5, atol=1e-6)
+    b = torch.sigmoid(s)
+    gate = torch.maximum(a[:, :, None, None, None], b)
+    z = ops.to_nchw(ops.se_gate_fwd(ycl, a, s), True)
+    assert rel_l2(z, (y * gate).bfloat16().float()) < 1e-3
+    da, ds = ops.se_gate_bwd_reduce(ycl, a, s, gcl)
+    a_wins = a[:, :, None, None, None] >= b
+    want_da = (gz * y * a_wins).sum(dim=(2, 3, 4))
+    want_ds = (gz * y * ~a_wins).sum(dim=1, keepdim=True) * b * (1 - b)
+    assert rel_l2(da, want_da) < 1e-4 and rel_l2(ds, want_ds) < 1e-4
+    dy = ops.to_nchw(ops.se_gate_bwd_apply(ycl, a, s, gcl, dmean, dcl), True)
+    want = gz * gate + (y > 0) * dmean[:, :, None, None, None] + dsse
+    assert rel_l2(dy, want) < 5e-3            # one bf16 rounding of the result
+    assert spatial == ycl.spatial
