@@ -13,7 +13,7 @@ stay per replica, as under DataParallel.
 """
 from __future__ import annotations
 
-from typing import Dict, List, Optional
+from typing import Dict, List
 
 import torch
 import torch.distributed as dist

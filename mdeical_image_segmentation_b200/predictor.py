@@ -12,7 +12,7 @@ b200_prediction_finalize``; only the final map crosses PCIe.  There is no CPU fa
 from __future__ import annotations
 
 import os
-from typing import Iterable, List, Optional, Sequence, Tuple
+from typing import Iterable, List, Optional, Sequence
 
 import numpy as np
 import torch

@@ -68,3 +68,19 @@ def test_state_dict_layouts_are_the_reference_ones():
     sd2 = B.UNetModel(B.UNetConfig(3, 4)).state_dict()
     assert len(sd2) == 46 and "unet.up_sample.3.up.weight" in sd2 and "unet.final_conv.bias" in sd2
     assert tuple(sd2["unet.up_sample.0.up.weight"].shape) == (1024, 512, 2, 2)
+
+
+def test_msssim_pyramid_layout_host_side():
+    """b200_msssim_pyramid_floats is pure host arithmetic: 5 scales, ceil-halving, 4-float alignment, and the
+    package's size assertion (smaller side > 160) as an error code — must agree with ops.msssim_valid_counts."""
+    from mdeical_image_segmentation_b200 import _lib, ops
+    lib = _lib.lib()
+    for n, h, w in ((2, 176, 192), (1, 161, 173), (3, 512, 512)):
+        total, hh, ww, counts = 0, h, w, []
+        for _ in range(5):
+            total += (n * hh * ww + 3) // 4 * 4
+            counts.append((hh - 10) * (ww - 10))
+            hh, ww = (hh + 1) // 2, (ww + 1) // 2
+        assert lib.b200_msssim_pyramid_floats(n, h, w) == total
+        assert ops.msssim_valid_counts(h, w) == counts and min(counts) >= 1
+    assert lib.b200_msssim_pyramid_floats(1, 160, 400) < 0 and lib.b200_msssim_pyramid_floats(1, 400, 100) < 0
