@@ -84,3 +84,39 @@ def test_msssim_pyramid_layout_host_side():
         assert lib.b200_msssim_pyramid_floats(n, h, w) == total
         assert ops.msssim_valid_counts(h, w) == counts and min(counts) >= 1
     assert lib.b200_msssim_pyramid_floats(1, 160, 400) < 0 and lib.b200_msssim_pyramid_floats(1, 400, 100) < 0
+
+
+def test_new_entry_points_validate_before_touching_the_device():
+    """The UNet 3+ / MS-SSIM / SE / predictor entry points reject unsupported arguments with error codes before any
+    CUDA call (so this runs without a GPU), and the widened networks keep the no-CPU-fallback rule."""
+    import mdeical_image_segmentation_b200 as B
+    lib = _lib.lib()
+    V = _lib.View
+    ok16 = V(ctypes.c_void_p(4096), 16, 0)            # never dereferenced: validation fails first
+    odd = V(ctypes.c_void_p(4096), 12, 0)             # channel total not a multiple of 8
+    assert lib.b200_bilinear2d_fwd(1, 4, 4, 16, 2, odd, ok16, None) == -2
+    assert lib.b200_bilinear2d_fwd(1, 4, 4, 16, 64, ok16, ok16, None) == -2          # scale > 32
+    assert lib.b200_bilinear2d_bwd(1, 4, 4, 16, 2, ok16, V(None, 0, 0), ok16, None, None) == -2   # no scratch
+    assert lib.b200_maxpoolk_fwd(1, 6, 8, 16, 4, ok16, ok16, None) == -2              # 6 % 4 != 0
+    assert lib.b200_add_relu(4, 12, ok16, ok16, ok16, None) == -2
+    assert lib.b200_msssim_fwd(1, 160, 400, None, None, None, None, None, ctypes.c_float(1.0), None) == -2
+    assert lib.b200_msssim_bwd(1, 100, 100, None, None, None, None, None, ctypes.c_float(1.0), None) == -2
+    big = V(ctypes.c_void_p(4096), 2048, 0)
+    assert lib.b200_se_channel_sums(1, 8, 2048, big, ctypes.c_void_p(4096), None) == -2   # c > 1024
+    assert lib.b200_se_gate_fwd(1, 8, 16, ok16, None, None, ok16, None) == -2             # no gates
+    assert lib.b200_cgm_gate(1, 4, 12, odd, None, None, None, ctypes.c_float(1.0), None, None, None) == -2
+    assert lib.b200_patch_gather(1, 8, 8, 8, None, 0, 0, 0, 0, 0, 0, 4, 4, 4, None, None) == -1   # null buffers
+    assert lib.b200_patch_gather(1, 8, 8, 8, ctypes.c_void_p(4096), 0, 0, 0, 8, 0, 0, 4, 4, 4,
+                                 ctypes.c_void_p(4096), None) == -1                               # halo >= size
+    assert lib.b200_patch_accumulate(1, 8, 8, 8, 4, 4, 4, 0, 0, 0, ctypes.c_void_p(4096), 1, -1, 6, 0, 0,
+                                     ctypes.c_void_p(4096), ctypes.c_void_p(4096), None) == -1    # patch leaves the map
+    assert lib.b200_prediction_finalize(0, 8, None, None, None, None) == -1
+    for make, shape in ((lambda: B.UNet_3Plus(3, 1), (1, 3, 32, 32)),
+                        (lambda: B.ResidualUNet3D(1, 1, f_maps=[8, 16]), (1, 1, 8, 8, 8))):
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            make()(torch.zeros(shape))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        B.MSSSIMLoss()(torch.zeros(1, 1, 176, 176), torch.zeros(1, 1, 176, 176))
+    from mdeical_image_segmentation_b200.predictor import StandardPredictor
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        StandardPredictor(torch.nn.Conv3d(1, 1, 1), None, 1).predict_volume(torch.zeros(8, 64, 64), (8, 64, 64), (8, 64, 64))
