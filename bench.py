@@ -8,9 +8,15 @@ weights of the named architecture).  One JSON line on rank 0 (see the keys at th
 the driver launches this file under torch.distributed.run; ranks shard by batch (weak scaling) and the
 gradient all-reduce overlaps backward (mdeical_image_segmentation_b200/parallel.py).
 
-`--impl reference` times the reference's CPU implementation of the same path: /root/reference is a
-pure-Python project that cannot travel to the GPU box, so the arm runs the oracle port (oracle/unet.py,
-a functional restatement pinned to the reference by tests/golden) on all host threads.
+Default workload = cfg3 (the north-star configuration: UNet3D(1,1) gcr + nearest, 128^3, batch 2 per GPU);
+the same line carries short device-resident measurements of cfg2 and cfg3p under "extra".
+
+`--impl reference` times the reference's own CPU implementation of the same path on all host threads: the
+UNMODIFIED reference modules from oracle/_ref (a copy of the path's files made by oracle/build_ref.py in the
+build container; git-ignored, travels with the snapshot) -- "kind": "reference" -- or, when oracle/_ref is
+absent, the oracle port (oracle/unet.py, pinned to the reference by tests/golden) -- "kind": "port".  A step
+of that arm is a bounded sample of the workload (the per-GPU batch of 64^3 crops / 256^2 crops, throughput
+scaled by voxel count) so that --steps / --warmup are honoured as given.
 """
 from __future__ import annotations
 
@@ -197,15 +203,25 @@ def build_model(w, device):
     return model, opt, step_fn
 
 
-def conv_flops(name, args):
-    """Algorithmic FLOPs of one C-ABI conv-family call, from its descriptor."""
+def conv_flops(name, args, real_cin=None):
+    """Algorithmic FLOPs of one C-ABI conv-family call, from its descriptor.  The narrow network input is
+    stored zero-padded to 16 channels (and its 3D weight gradient runs over an im2col with K' = 32): those
+    calls count the REAL input channels, 2 * positions * taps * C_in * C_out."""
     d = args[0]._obj if hasattr(args[0], "_obj") else None
     if d is None:
         return 0.0
     if name.startswith("b200_convt2x2"):
         return 2.0 * d.n * d.h * d.w * d.c_in * d.c_out * 4
     if name.startswith("b200_conv_"):
-        return 2.0 * d.n * d.d * d.h * d.w * d.c_in * d.c_out * d.kd * d.kh * d.kw
+        c_in, c_out, taps = d.c_in, d.c_out, d.kd * d.kh * d.kw
+        if real_cin is not None and real_cin < 16:
+            full_taps = 27 if d.d > 1 else 9
+            kp = (full_taps * real_cin + 15) // 16 * 16
+            if c_in == 16 and taps == full_taps:
+                c_in = real_cin                 # first layer on the padded input (fwd / dgrad / wgrad descriptors)
+            elif taps == 1 and c_in == kp:
+                c_in, taps = real_cin, full_taps   # im2col weight gradient: K' = taps * C_in rounded up
+        return 2.0 * d.n * d.d * d.h * d.w * c_in * c_out * taps
     if name.startswith("b200_deconv3s2"):
         return 2.0 * d.n * d.d * d.h * d.w * d.c_in * d.c_out * (27 if d.d > 1 else 9)
     return 0.0
@@ -214,8 +230,9 @@ def conv_flops(name, args):
 class KernelProfiler:
     """Per-call CUDA-event timing on the launching stream for one instrumented step."""
 
-    def __init__(self):
+    def __init__(self, real_cin=None):
         self.records = []
+        self.real_cin = real_cin
 
     @contextlib.contextmanager
     def hook(self, name, args):
@@ -225,7 +242,7 @@ class KernelProfiler:
         yield
         e1.record()
         impl = _lib.lib().b200_last_impl() if ("conv" in name and "repack" not in name) else 0
-        self.records.append((name, impl, conv_flops(name, args), e0, e1))
+        self.records.append((name, impl, conv_flops(name, args, self.real_cin), e0, e1))
 
     def summarize(self):
         torch.cuda.synchronize()
@@ -252,23 +269,37 @@ class KernelProfiler:
         return fam
 
 
-def run_b200(args, w):
+REFERENCE_SAMPLE = {
+    "3d": "the --impl reference arm and cpu_baseline time the per-GPU batch of 64^3 crops per step on the host "
+          "cores, throughput scaled by voxel count to the workload's volume",
+    "2d": "the --impl reference arm and cpu_baseline time one 512x512 image per step on the host cores "
+          "(UNet 3+: one 256x256 crop, scaled by pixel count)",
+}
+
+
+def traffic_for(workload, family):
+    """DRAM bytes per launch of a kernel family from the newest committed ncu pass (STATIC: measured once
+    under ncu by tools/ncu_summary.py, not in this run)."""
+    for name in ("r02_dram_traffic.json", "r01_dram_traffic.json"):
+        path = os.path.join(ROOT, "profiles", name)
+        if os.path.exists(path):
+            v = json.load(open(path)).get(workload, {}).get(family, {}).get("dram_bytes_per_launch")
+            if v is not None:
+                return round(v), "profiles/" + name
+    return None, None
+
+
+def measure(args, name, w, steps, warmup, device, world, rank, full):
+    """Times one workload on this rank's GPU.  full: also e2e, instrumented roofline step, launch count."""
     import torch.distributed as dist
     from mdeical_image_segmentation_b200 import _lib
+    from mdeical_image_segmentation_b200 import engine as _engine
     from mdeical_image_segmentation_b200.parallel import DataParallelUNet
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    device = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=device)
-    batch = args.batch or w["batch"]
+    batch = (args.batch if full else 0) or w["batch"]
     model, opt, step_fn = build_model(w, device)
     if world > 1:
         DataParallelUNet(model)
-
     x, y = make_batch(w, batch, 1234 + rank, device)
 
     def one_step(xb, yb):
@@ -284,14 +315,14 @@ def run_b200(args, w):
         torch.cuda.synchronize()
 
     # ---- device-resident timing
-    for _ in range(args.warmup):
+    for _ in range(warmup):
         one_step(x, y)
     barrier()
     _lib.launch_count = 0
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local) as clocks:
+    with ClockSampler(device.index) as clocks:
         e0.record()
-        for _ in range(args.steps):
+        for _ in range(steps):
             loss = one_step(x, y)
         e1.record()
         barrier()
@@ -299,12 +330,21 @@ def run_b200(args, w):
     ms = torch.tensor([e0.elapsed_time(e1)], device=device)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    ms_step = ms.item() / args.steps
-    value = world * batch / (ms_step / 1e3)
-    final_loss = float(loss.item())
+    ms_step = ms.item() / steps
+    pk = peaks()
+    step_tf = w["train_tf"] * batch
+    res = {"value": world * batch / (ms_step / 1e3), "ms_step": ms_step, "batch": batch, "launches": launches,
+           "clocks": clocks.summary(), "final_loss": float(loss.item()),
+           "step": {"algorithmic_tflop_per_step": round(step_tf, 2),
+                    "step_tflops": round(step_tf / (ms_step / 1e3), 1),
+                    "frac_of_sustained_peak": round(step_tf / (ms_step / 1e3) / pk["tf_sustained"], 4)}}
+    if not full:
+        del model, opt, x, y
+        torch.cuda.empty_cache()
+        return res
 
     # ---- end to end: pinned host batch -> H2D every step (prefetched on a copy stream), loss -> host
-    e2e = None
+    res["e2e"] = None
     if not args.no_e2e:
         host = [make_batch(w, batch, 99 + rank + i, "cpu", pin=True) for i in range(2)]
         copy_stream = torch.cuda.Stream(device=device)
@@ -330,38 +370,35 @@ def run_b200(args, w):
                 yb.record_stream(torch.cuda.current_stream())
                 l.item()                                   # D2H read of the step's result
 
-        e2e_loop(max(1, min(args.warmup, 2)))
+        e2e_loop(max(1, min(warmup, 2)))
         barrier()
         t0 = time.perf_counter()
         s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s0.record()
-        e2e_loop(args.steps)
+        e2e_loop(steps)
         s1.record()
         barrier()
         wall_ms = (time.perf_counter() - t0) * 1e3
         ems = torch.tensor([max(s0.elapsed_time(s1), wall_ms)], device=device)
         if world > 1:
             dist.all_reduce(ems, op=dist.ReduceOp.MAX)
-        e2e = {"value": world * batch / (ems.item() / args.steps / 1e3), "unit": w["unit"],
-               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4}
+        res["e2e"] = {"value": world * batch / (ems.item() / steps / 1e3), "unit": w["unit"],
+                      "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4}
 
-    # ---- roofline: one instrumented step with per-call CUDA events on the launching stream
-    pk = peaks()
-    roofline, breakdown = None, None
-    # every rank runs the instrumented step (its backward contains the gradient all-reduce, so a
-    # rank-0-only step would wait for peers forever); only rank 0 records and reports
-    prof = KernelProfiler()
+    # ---- roofline: one instrumented step with per-call CUDA events on the launching stream.
+    # Every rank runs it (its backward contains the gradient all-reduce, so a rank-0-only step would wait
+    # for peers forever); only rank 0 records and reports.  Per-kernel times must not include the contention
+    # of the overlapped weight-gradient stream: the instrumented step runs single-stream.
+    prof = KernelProfiler(real_cin=w["cin"])
     if rank == 0:
         _lib.profile_hook = prof.hook
-    # per-kernel times must not include the contention of the overlapped weight-gradient stream:
-    # the instrumented step runs single-stream (the timed steps above do not)
-    from mdeical_image_segmentation_b200 import engine as _engine
     side_was = _engine.WGRAD_STREAM
     _engine.WGRAD_STREAM = False
     one_step(x, y)
     _engine.WGRAD_STREAM = side_was
     _lib.profile_hook = None
     barrier()
+    res["roofline"], res["breakdown"] = None, None
     if rank == 0:
         fam = prof.summarize()
         total_ms = sum(f["ms"] for f in fam.values())
@@ -370,48 +407,87 @@ def run_b200(args, w):
                          **({"tflops": round(f["flops"] / f["ms"] / 1e9, 1)} if f["flops"] else {})}
                      for k, f in sorted(fam.items(), key=lambda kv: -kv[1]["ms"])}
         top = max(fam.items(), key=lambda kv: kv[1]["ms"])
-        traffic = None
-        tpath = os.path.join(ROOT, "profiles", "r01_dram_traffic.json")
-        if os.path.exists(tpath):   # DRAM bytes per launch of this kernel family from the committed ncu pass
-            traffic = json.load(open(tpath)).get(args.workload, {}).get(top[0], {}).get("dram_bytes_per_launch")
         if top[1]["flops"] > 0:
+            traffic, tsrc = traffic_for(name, top[0])
             ach = top[1]["flops"] / top[1]["ms"] / 1e9
-            roofline = {"kernel": top[0], "bound": "tensor", "achieved": round(ach, 1),
-                        "peak": pk["tf_sustained"], "unit": "TFLOP/s",
-                        "frac": round(ach / pk["tf_sustained"], 4),
-                        "traffic": None if traffic is None else round(traffic),
-                        "traffic_unit": "DRAM bytes per launch (ncu, profiles/r01_dram_traffic.json)",
-                        "algorithmic_flop_per_launch": round(top[1]["flops"] / top[1]["launches"]),
-                        "peak_source": pk["source"] + " (sustained cuBLAS bf16)",
-                        "avg_launch_ms": round(top[1]["ms"] / top[1]["launches"], 4)}
-        step_tf = w["train_tf"] * batch
-        breakdown["_step"] = {"algorithmic_tflop_per_step": round(step_tf, 2),
-                              "step_tflops": round(step_tf / (ms_step / 1e3), 1),
-                              "frac_of_sustained_peak": round(step_tf / (ms_step / 1e3) / pk["tf_sustained"], 4)}
+            res["roofline"] = {
+                "kernel": top[0], "bound": "tensor", "achieved": round(ach, 1),
+                "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": round(ach / pk["tf_sustained"], 4),
+                "traffic": traffic,
+                "traffic_unit": "DRAM bytes per launch",
+                "traffic_source": None if tsrc is None else
+                f"STATIC: one ncu pass of this workload committed as {tsrc}; not measured in this run",
+                "algorithmic_flop_per_launch": round(top[1]["flops"] / top[1]["launches"]),
+                "peak_source": pk["source"] + " (sustained cuBLAS bf16)",
+                "avg_launch_ms": round(top[1]["ms"] / top[1]["launches"], 4)}
+        breakdown["_step"] = res["step"]
+        res["breakdown"] = breakdown
+    del model, opt, x, y
+    torch.cuda.empty_cache()
+    return res
 
-    # ---- reference CPU baseline (oracle port) on a bounded sample, rank 0 at N = 1 only
+
+EXTRA_WORKLOADS = ("cfg2", "cfg3p")
+
+
+def run_b200(args, w):
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    head = measure(args, args.workload, w, args.steps, args.warmup, device, world, rank, full=True)
+    batch = head["batch"]
+
+    # ---- the other two training configurations, device-resident, a few steps each (not the headline)
+    extra = None
+    if args.extras and args.workload == "cfg3" and not args.batch:
+        extra = {}
+        for name in EXTRA_WORKLOADS:
+            try:
+                r = measure(args, name, WORKLOADS[name], max(3, min(args.steps, 6)), 3, device, world, rank,
+                            full=False)
+                extra[name] = {"workload": WORKLOADS[name]["desc"], "value": round(r["value"], 3),
+                               "unit": WORKLOADS[name]["unit"], "ms_per_step": round(r["ms_step"], 3),
+                               "per_gpu_batch": r["batch"], "gpu_launches": r["launches"], **r["step"],
+                               "clocks": r["clocks"]}
+            except Exception as e:   # an extra must never take the headline line down with it
+                extra[name] = {"error": f"{type(e).__name__}: {e}"[:300]}
+                torch.cuda.empty_cache()
+
+    # ---- reference CPU baseline on a bounded sample, rank 0 at N = 1 only
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu = run_cpu_sample(w, steps=1, warmup=0)
+        cpu = run_cpu_sample(w, steps=2, warmup=1)
 
     if rank == 0:
         out = {
-            "metric": "train " + w["unit"], "value": round(value, 3), "unit": w["unit"], "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_step, 3),
+            "metric": "train " + w["unit"], "value": round(head["value"], 3), "unit": w["unit"], "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(head["ms_step"], 3),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
             "data": "synthetic",
-            "config": {"workload": f"{args.workload}: {w['desc']}", "per_gpu_batch": batch,
-                       "global_batch": batch * world, "parallelism": f"dp{world}",
-                       "l2": "per-step inputs + activations far exceed the 126 MB L2 (no flush needed)",
-                       "streams": "weight gradients on a side stream in the timed steps; the roofline / "
-                                  "breakdown step runs single-stream"},
-            "e2e": e2e, "gpu_launches": launches, "clocks": clocks.summary(),
-            "roofline": roofline, "cpu_baseline": cpu, "breakdown": breakdown,
-            "final_loss": final_loss,
+            "config": bench_config(args.workload, w, batch, world),
+            "e2e": head["e2e"], "gpu_launches": head["launches"], "clocks": head["clocks"],
+            "roofline": head["roofline"], "cpu_baseline": cpu, "breakdown": head["breakdown"],
+            "final_loss": head["final_loss"], "extra": extra,
         }
         emit(out)
     if world > 1:
         dist.destroy_process_group()
+
+
+def bench_config(name, w, batch, world):
+    """`config` of the JSON line — the SAME dict in both arms (the driver compares them)."""
+    return {"workload": f"{name}: {w['desc']}", "per_gpu_batch": batch,
+            "global_batch": batch * world, "parallelism": f"dp{world}",
+            "l2": "per-step inputs + activations far exceed the 126 MB L2 (no flush needed)",
+            "streams": "weight gradients on a side stream in the timed steps; the roofline / "
+                       "breakdown step runs single-stream",
+            "reference_sample": REFERENCE_SAMPLE[w["kind"]]}
 
 
 # --------------------------------------------------------------------------------------- cfg5 sweep
@@ -500,59 +576,107 @@ def run_sweep(args):
 
 
 # --------------------------------------------------------------------------------------- CPU arm
-def run_cpu_sample(w, steps, warmup, batch=None):
-    """Reference path on host cores via the oracle port: fwd + loss + bwd + optimizer on a bounded
-    sample (2D: one 512^2 image per step; 3D: one 64^3 crop per step, throughput scaled by voxels)."""
+def _cpu_sample_shape(w):
+    """Bounded sample of the workload for the host-core arm: (size, scale = sample voxels / workload voxels)."""
+    if w["kind"] == "3d":
+        size = (64, 64, 64)
+    elif w.get("unet_type", "UNet") != "UNet":
+        size = (256, 256)
+    else:
+        size = w["size"]
+    vox, full = 1, 1
+    for a, b in zip(size, w["size"]):
+        vox, full = vox * a, full * b
+    return size, vox / full
+
+
+def _reference_step_fn(w, x, y):
+    """fwd + loss of the reference's OWN modules (oracle/_ref, unmodified), or None when they cannot run
+    here (copy absent, or the UNet 3+ loss: its pytorch_msssim dependency is not installed)."""
+    if w.get("unet_type", "UNet") != "UNet" or w.get("residual") == "se":
+        return None
+    try:
+        from oracle import ref_loader
+        if not ref_loader.use_copy():
+            return None
+        ns = ref_loader.load()
+    except Exception as e:   # noqa: BLE001
+        print(f"reference copy not importable ({type(e).__name__}: {e}); using the oracle port", file=sys.stderr)
+        return None
+    torch.manual_seed(0)
+    if w["kind"] == "2d":
+        with contextlib.redirect_stdout(sys.stderr):
+            model = ns.U2.UNetModel(ns.U2.UNetConfig(w["cin"], w["cout"], "UNet")).train()
+        params = list(model.parameters())
+        return (lambda: model(images=x, labels=y).loss), params, torch.optim.AdamW(params, lr=1e-4,
+                                                                                    weight_decay=1e-3)
+    cls = ns.M3.ResidualUNet3D if w.get("residual") else ns.M3.UNet3D
+    kw = {} if w.get("residual") else {"upsample": w["upsample"]}
+    net = cls(w["cin"], w["cout"], layer_order=w["order"], **kw).train()
+    crit = ns.L3.DiceLoss(normalization="sigmoid") if w.get("loss") == "dice" else ns.L3.BCEDiceLoss(1.0, 1.0)
+    params = list(net.parameters())
+    return (lambda: crit(net(x), y)), params, torch.optim.Adam(params, lr=1e-4)
+
+
+def _port_step_fn(w, x, y):
+    """The same step through the oracle port (oracle/unet.py, pinned to the reference by tests/golden)."""
     from oracle import unet as O
     import mdeical_image_segmentation_b200 as B
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
     torch.manual_seed(0)
-    if w.get("unet_type", "UNet") != "UNet":       # UNet 3+ family: one 256^2 crop per step, scaled by pixels
+
+    def leaves(net):
+        return {k: (v.clone().requires_grad_(True) if v.is_floating_point() and "running" not in k else v.clone())
+                for k, v in net.state_dict().items()}
+
+    if w.get("unet_type", "UNet") != "UNet":       # UNet 3+ family
         from oracle import unet3plus as O3
-        b = batch or 1
-        deep = w["unet_type"] == "UNet_3Plus_DeepSup"
-        net = getattr(B, w["unet_type"])(w["cin"], w["cout"])
-        sd = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and "running" not in k else v.clone())
-              for k, v in net.state_dict().items()}
-        x, y = make_batch(dict(w, size=(256, 256)), b, 7)
         from oracle.msssim import segmentation_loss
-        seg = lambda lo: segmentation_loss(lo, y)  # noqa: E731  (F1 + MS-SSIM + IoU, loss.py:59-70)
+        deep = w["unet_type"] == "UNet_3Plus_DeepSup"
+        sd = leaves(getattr(B, w["unet_type"])(w["cin"], w["cout"]))
 
         def fwd():
             out = O3.unet3plus_forward(sd, x, training=True, deep_sup=deep)
-            return sum(seg(d) for d in out) if deep else seg(out)
-        scale = 256.0 ** 2 / (w["size"][0] * w["size"][1])
-        sample = f"{b} crop(s) of 256x256 per step, scaled by pixel count to {w['size'][0]}x{w['size'][1]} images"
-        opt = torch.optim.AdamW([v for v in sd.values() if v.requires_grad], lr=1e-4, weight_decay=1e-3)
-    elif w["kind"] == "2d":
-        b = batch or 1
-        sd = {k: v.clone().requires_grad_(True) for k, v in B.UNet(w["cin"], w["cout"]).state_dict().items()}
-        x, y = make_batch(w, b, 7)
-        fwd = lambda: O.unet_model_loss(O.unet2d_forward(sd, x), y, w["cout"])  # noqa: E731
-        scale, sample = 1.0, f"{b} image(s) of {w['size'][0]}x{w['size'][1]} per step"
-        opt = torch.optim.AdamW(sd.values(), lr=1e-4, weight_decay=1e-3)
+            return sum(segmentation_loss(d, y) for d in out) if deep else segmentation_loss(out, y)
+        params = [v for v in sd.values() if v.requires_grad]
+        return fwd, params, torch.optim.AdamW(params, lr=1e-4, weight_decay=1e-3)
+    if w["kind"] == "2d":
+        sd = leaves(B.UNet(w["cin"], w["cout"]))
+        params = list(sd.values())
+        return (lambda: O.unet_model_loss(O.unet2d_forward(sd, x), y, w["cout"])), params, \
+            torch.optim.AdamW(params, lr=1e-4, weight_decay=1e-3)
+    if w.get("residual"):
+        net = (B.ResidualUNetSE3D if w["residual"] == "se" else B.ResidualUNet3D)(w["cin"], w["cout"],
+                                                                                  layer_order=w["order"])
     else:
-        b = batch or 1
-        if w.get("residual"):
-            net = (B.ResidualUNetSE3D if w["residual"] == "se" else B.ResidualUNet3D)(w["cin"], w["cout"],
-                                                                                      layer_order=w["order"])
-        else:
-            net = B.UNet3D(w["cin"], w["cout"], layer_order=w["order"], upsample=w["upsample"])
-        sd = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and "running" not in k else v.clone())
-              for k, v in net.state_dict().items()}
-        crop = dict(w, size=(64, 64, 64))
-        x, y = make_batch(crop, b, 7)
-        lossf = O.dice_loss if w.get("loss") == "dice" else O.bce_dice_loss
-        if w.get("residual"):
-            fwd = lambda: lossf(O.residual_unet3d_forward(sd, x, layer_order=w["order"]), y)  # noqa: E731
-        else:
-            fwd = lambda: lossf(O.unet3d_forward(sd, x, layer_order=w["order"], upsample=w["upsample"],  # noqa: E731
-                                                 training=True), y)
-        scale = 64.0 ** 3 / (w["size"][0] * w["size"][1] * w["size"][2])
-        sample = (f"{b} crop(s) of 64^3 per step, scaled by voxel count to "
-                  f"{'x'.join(str(v) for v in w['size'])} volumes")
-        opt = torch.optim.Adam([v for v in sd.values() if v.requires_grad], lr=1e-4)
+        net = B.UNet3D(w["cin"], w["cout"], layer_order=w["order"], upsample=w["upsample"])
+    sd = leaves(net)
+    lossf = O.dice_loss if w.get("loss") == "dice" else O.bce_dice_loss
+    if w.get("residual"):
+        fwd = lambda: lossf(O.residual_unet3d_forward(sd, x, layer_order=w["order"]), y)  # noqa: E731
+    else:
+        fwd = lambda: lossf(O.unet3d_forward(sd, x, layer_order=w["order"], upsample=w["upsample"],  # noqa: E731
+                                             training=True), y)
+    params = [v for v in sd.values() if v.requires_grad]
+    return fwd, params, torch.optim.Adam(params, lr=1e-4)
+
+
+def run_cpu_sample(w, steps, warmup, batch=None):
+    """The reference path on the host cores: fwd + loss + bwd + optimizer step on a bounded sample (3D: the
+    per-GPU batch of 64^3 crops per step; 2D: one image per step; throughput scaled by voxel count)."""
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    size, frac = _cpu_sample_shape(w)
+    b = batch or (w["batch"] if w["kind"] == "3d" else 1)
+    x, y = make_batch(dict(w, size=size), b, 7)
+    made = _reference_step_fn(w, x, y)
+    kind = "reference"
+    if made is None:
+        made, kind = _port_step_fn(w, x, y), "port"
+    fwd, _, opt = made
+    dims = "x".join(str(v) for v in size)
+    sample = f"{b} sample(s) of {dims} per step"
+    if frac != 1.0:
+        sample += f", scaled by voxel count to {'x'.join(str(v) for v in w['size'])}"
 
     def step():
         opt.zero_grad()
@@ -566,21 +690,22 @@ def run_cpu_sample(w, steps, warmup, batch=None):
     for _ in range(steps):
         step()
     dt = (time.perf_counter() - t0) / steps
-    return {"value": round(b * scale / dt, 5), "unit": w["unit"], "cores": cores, "kind": "port",
+    return {"value": round(b * frac / dt, 5), "unit": w["unit"], "cores": cores, "kind": kind,
             "sample": sample, "s_per_step": round(dt, 3)}
 
 
 def run_reference(args, w):
+    """`--impl reference`: --steps / --warmup are honoured as given (a step = the bounded sample above)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps = max(1, min(args.steps, 8))
-    cpu = run_cpu_sample(w, steps=steps, warmup=min(args.warmup, 1))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    cpu = run_cpu_sample(w, steps=max(1, args.steps), warmup=max(0, args.warmup))
     out = {"impl": "reference", "metric": "train " + w["unit"], "value": cpu["value"], "unit": w["unit"],
-           "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": steps, "warmup": min(args.warmup, 1),
+           "n_gpus": world, "steps": max(1, args.steps), "warmup": max(0, args.warmup),
            "ms_per_step": cpu["s_per_step"] * 1e3, "higher_is_better": True, "scaling": "weak",
            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-           "config": {"workload": f"{args.workload}: {w['desc']}", "note": "CPU oracle port of the reference path"},
+           "config": bench_config(args.workload, w, args.batch or w["batch"], world),
            "cpu_baseline": cpu, "gpu_launches": 0,
            "e2e": {"value": cpu["value"], "unit": w["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit(out)
@@ -592,7 +717,9 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS) + ["cfg5"])
+    ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS) + ["cfg5"])
+    ap.add_argument("--no-extras", dest="extras", action="store_false",
+                    help="skip the short cfg2 / cfg3p measurements nested under 'extra'")
     ap.add_argument("--batch", type=int, default=0)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")

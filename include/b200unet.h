@@ -174,6 +174,29 @@ int b200_bilinear2d_fwd(int32_t n, int32_t ih, int32_t iw, int32_t c, int32_t sc
                         b200_view y, b200_stream_t stream);
 int b200_bilinear2d_bwd(int32_t n, int32_t ih, int32_t iw, int32_t c, int32_t scale, b200_view dy,
                         b200_view add, b200_view dx, void* scratch, b200_stream_t stream);
+/* ---- layer_order letters 'l' / 'e' / 'd' / 'D' and avg-pool encoders ----------------------------
+ * replaces nn.LeakyReLU / nn.ELU (buildingblocks.py:55-59; ResNetBlock's non_linearity :306-311, applied to
+ * out + residual :319-323), nn.Dropout / nn.Dropout2d (:104-107) and nn.AvgPool2d/3d (:414-418).
+ * y = act(a [+ b]) (b.ptr may be NULL); param = negative slope (LEAKY_RELU) or alpha (ELU). */
+#define B200_ACT_RELU 0
+#define B200_ACT_LEAKY_RELU 1
+#define B200_ACT_ELU 2
+int b200_act_fwd(int64_t npos, int32_t c, int32_t kind, float param, b200_view a, b200_view b, b200_view y,
+                 b200_stream_t stream);
+/* dx = dy * act'(.) with the derivative recovered from the stored OUTPUT y (y > 0 ? 1 : 0 | slope | y + alpha) */
+int b200_act_bwd(int64_t npos, int32_t c, int32_t kind, float param, b200_view dy, b200_view y, b200_view dx,
+                 b200_stream_t stream);
+/* y = x * scale * (keep ? keep[pos][c] != 0 : 1) * (chan ? chan[n][c] : 1): dropout forward and backward.
+ * keep: dense uint8 [n * spatial][c] (element-wise dropout) or NULL; chan: fp32 [n][c] (channel-wise dropout,
+ * 0 or 1) or NULL.  The mask itself comes from the caller's RNG. */
+int b200_scale_mask(int32_t n, int64_t spatial, int32_t c, b200_view x, const uint8_t* keep, const float* chan,
+                    float scale, b200_view y, b200_stream_t stream);
+/* 2x2 (pool_d = 1) / 2x2x2 (pool_d = 2) average pool, stride 2, floor mode; bwd: dx = dy / window (+ add,
+ * ptr may be NULL), zeroed where x <= 0 when mask_relu (x may be NULL otherwise). */
+int b200_avgpool2_fwd(int32_t n, int32_t d, int32_t h, int32_t w, int32_t c, int32_t pool_d, b200_view x,
+                      b200_view y, b200_stream_t stream);
+int b200_avgpool2_bwd(int32_t n, int32_t d, int32_t h, int32_t w, int32_t c, int32_t pool_d, b200_view x,
+                      b200_view dy, b200_view add, b200_view dx, int32_t mask_relu, b200_stream_t stream);
 /* y = relu(a + b): residual join of ResNetBlock (model/unet3d/buildingblocks.py:319-323) */
 int b200_add_relu(int64_t npos, int32_t c, b200_view a, b200_view b, b200_view y, b200_stream_t stream);
 /* dst += src: gradient accumulation for tensors that feed several full-scale skip branches */
@@ -283,7 +306,11 @@ int b200_seg_sums(int32_t n, int32_t c, int64_t spatial, const float* logits, co
 int b200_seg_loss_bwd(int32_t n, int32_t c, int64_t spatial, const float* logits,
                       const float* target, const float* coef, int32_t normalization, float* dlogits,
                       b200_stream_t stream);
-/* nn.CrossEntropyLoss() (unet.py:1185): nll_sum (fp64 [1]) += sum_pos -log softmax(x)[label] */
+/* nn.CrossEntropyLoss() (unet.py:1185): nll_sum is fp64 [3] accumulated into:
+ * [0] += sum over valid positions of -log softmax(x)[label], [1] += number of valid positions (label !=
+ * ignore_index = -100), [2] += number of labels outside [0, c) other than -100 (never dereferenced; the
+ * host wrapper turns a non-zero count into a NaN loss).  b200_ce_bwd writes zero gradient at ignored /
+ * invalid positions. */
 int b200_ce_fwd(int32_t n, int32_t c, int64_t spatial, const float* logits, const int64_t* labels,
                 double* nll_sum, b200_stream_t stream);
 /* dlogits = scale[0] * (softmax(x) - onehot(label)) */

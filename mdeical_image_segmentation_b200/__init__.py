@@ -8,9 +8,12 @@ from .unet3plus import UNet_3Plus, UNet_3Plus_DeepSup, UNet_3Plus_DeepSup_CGM
 from .losses import (BCEDiceLoss, BCEWithLogitsLoss, CrossEntropyLoss, DiceLoss, F1Loss, IoULoss, MSSSIMLoss,
                      SegmentationLoss, compute_per_channel_dice, flatten, get_loss_criterion)
 from .unet2d import (CropAndConcat, DoubleConvolution, DownSample, UNet, UpSample, unetConv2)
-from .unet3d import (AbstractUNet, ChannelSpatialSELayer3D, Decoder, DoubleConv, Encoder, ResidualUNet3D,
-                     ResidualUNetSE3D, ResNetBlock, ResNetBlockSE, SingleConv, UNet2D, UNet3D, create_conv,
+from .unet3d import (AbstractUNet, ChannelSELayer3D, ChannelSpatialSELayer3D, Decoder, DoubleConv, Encoder,
+                     ResidualUNet2D, ResidualUNet3D, ResidualUNetSE3D, ResNetBlock, ResNetBlockSE, SingleConv,
+                     SpatialSELayer3D, UNet2D, UNet3D, create_conv, create_decoders, create_encoders, get_model,
                      number_of_features_per_level)
+from .predictor import LazyPredictor, StandardPredictor
+from .serving import SegmentationService, create_app
 
 try:
     from .unet2d import UNetConfig, UNetModel, UNetModelOutput

@@ -75,6 +75,11 @@ SIGNATURES = {
     "b200_bilinear2d_fwd": [_I, _I, _I, _I, _I, View, View, _P],
     "b200_bilinear2d_bwd": [_I, _I, _I, _I, _I, View, View, View, _P, _P],
     "b200_add": [_L, _I, View, View, _P],
+    "b200_act_fwd": [_L, _I, _I, _F, View, View, View, _P],
+    "b200_act_bwd": [_L, _I, _I, _F, View, View, View, _P],
+    "b200_scale_mask": [_I, _L, _I, View, _P, _P, _F, View, _P],
+    "b200_avgpool2_fwd": [_I, _I, _I, _I, _I, _I, View, View, _P],
+    "b200_avgpool2_bwd": [_I, _I, _I, _I, _I, _I, View, View, View, View, _I, _P],
     "b200_add_relu": [_L, _I, View, View, View, _P],
     "b200_msssim_fwd": [_I, _I, _I, _P, _P, _P, _P, _P, _F, _P],
     "b200_msssim_bwd": [_I, _I, _I, _P, _P, _P, _P, _P, _F, _P],

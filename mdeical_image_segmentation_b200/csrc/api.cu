@@ -4,14 +4,14 @@
 #include "conv_tc.cuh"
 
 namespace b200 {
-extern int g_halo_mode;
-extern int g_wgrad_halo_mode;
-extern int g_halo_rmax;
-extern int g_halo_resident;
-extern int g_gemm_resident;
-extern int g_epi_dbg;
-extern int g_epi_warps;
-extern int g_wgrad_wide;
+extern thread_local int g_halo_mode;
+extern thread_local int g_wgrad_halo_mode;
+extern thread_local int g_halo_rmax;
+extern thread_local int g_halo_resident;
+extern thread_local int g_gemm_resident;
+extern thread_local int g_epi_dbg;
+extern thread_local int g_epi_warps;
+extern thread_local int g_wgrad_wide;
 int direct_gemm_conv(const TcGemmProblem& p, cudaStream_t stream);
 int direct_wgrad(const TcWgradProblem& p, cudaStream_t stream);
 static thread_local int g_last_impl = 0;

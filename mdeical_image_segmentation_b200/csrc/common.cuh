@@ -23,6 +23,42 @@ typedef __nv_bfloat16 bf16;
 
 static inline int ceil_div_i(long a, long b) { return (int)((a + b - 1) / b); }
 
+// Per-DEVICE host-side caches (a process may drive several GPUs from several threads): the SM count and
+// the set of kernels whose dynamic shared-memory limit was already raised on that device.
+#include <mutex>
+namespace b200 {
+static const int kMaxDevices = 64;
+inline int current_device() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return dev < 0 || dev >= kMaxDevices ? 0 : dev;
+}
+inline int sm_count() {
+  static int n[kMaxDevices];
+  static std::mutex mu;
+  const int dev = current_device();
+  std::lock_guard<std::mutex> lock(mu);
+  if (!n[dev]) {
+    cudaDeviceGetAttribute(&n[dev], cudaDevAttrMultiProcessorCount, dev);
+    if (n[dev] <= 0) n[dev] = 148;
+  }
+  return n[dev];
+}
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device property of the function
+inline cudaError_t ensure_dynamic_smem(const void* fn, int bytes) {
+  static const void* done[kMaxDevices][64];
+  static int ndone[kMaxDevices];
+  static std::mutex mu;
+  const int dev = current_device();
+  std::lock_guard<std::mutex> lock(mu);
+  for (int i = 0; i < ndone[dev]; ++i)
+    if (done[dev][i] == fn) return cudaSuccess;
+  cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess && ndone[dev] < 64) done[dev][ndone[dev]++] = fn;
+  return e;
+}
+}  // namespace b200
+
 namespace b200 {
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {

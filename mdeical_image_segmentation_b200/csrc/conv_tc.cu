@@ -918,7 +918,7 @@ __global__ void __launch_bounds__(384, 1)
   if (warp == 2) tmem_dealloc(tmem_base, tmem_cols);
 }
 
-int g_epi_dbg = 0;
+thread_local int g_epi_dbg = 0;
 static EpiArgs make_epi(const TcGemmProblem& p) {
   EpiArgs e{};
   e.out = p.out; e.out_ctot = p.out_ctot; e.out_coff = p.out_coff;
@@ -936,7 +936,7 @@ static int stats_kind_of(const TcGemmProblem& p) {
   if (p.dot) return EPI_STATS_DOT;
   return p.stats_kind == EPI_STATS_SUM ? EPI_STATS_SUM : EPI_STATS_SUMSQ;
 }
-int g_epi_warps = 0;  // tuning knob: 0 = heuristic, 4 / 8 = forced
+thread_local int g_epi_warps = 0;  // tuning knob: 0 = heuristic, 4 / 8 = forced
 // Two epilogue warps per TMEM lane quarter when a tile's MMA work is too short to hide a 4-warp
 // epilogue (~1000 cycles per 32x32 chunk per warp, latency-bound): small K = taps * C_in.
 static int pick_epi_warps(long k_total, bool aux) {
@@ -949,15 +949,8 @@ static int launch_variant(F pick, bool mask, int kind, int grid, int block, int 
                           const CUtensorMap& tmA, const CUtensorMap& tmB, const Args& a) {
   void (*fn)(CUtensorMap, CUtensorMap, Args) = pick(mask, kind);
   if (!fn) return B200_ERR_UNSUPPORTED;
-  static void* configured[16];
-  static int nconf = 0;
-  bool done = false;
-  for (int i = 0; i < nconf; ++i) done |= configured[i] == (void*)fn;
-  if (!done) {
-    cudaError_t e = cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
-    if (e != cudaSuccess) return (int)e;
-    if (nconf < 16) configured[nconf++] = (void*)fn;
-  }
+  cudaError_t ce = ensure_dynamic_smem((const void*)fn, kSmemBudget);
+  if (ce != cudaSuccess) return (int)ce;
   fn<<<grid, block, smem, stream>>>(tmA, tmB, a);
   B200_LAUNCH_CHECK();
   return B200_OK;
@@ -982,17 +975,6 @@ static int launch_variant(F pick, bool mask, int kind, int grid, int block, int 
     return nullptr;                                                                         \
   }
 
-static int sm_count() {
-  static int n = 0;
-  if (!n) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
-  }
-  return n;
-}
-
 static int pick_bn(int ncols, int limit) {
   for (int bn = limit; bn >= 16; bn -= 16)
     if (ncols % bn == 0) return bn;
@@ -1014,17 +996,16 @@ bool tc_gemm_supported(const TcGemmProblem& p) {
 }
 
 static int pick_bn(int ncols, int limit);
-static int sm_count();
-int g_halo_mode = 1;  // 0 disables the halo-reuse kernel (A/B testing from the bench tools)
+thread_local int g_halo_mode = 1;  // 0 disables the halo-reuse kernel (A/B testing from the bench tools)
 
-int g_halo_rmax = 4;  // tuning knob: cap on row-blocks per super-tile
+thread_local int g_halo_rmax = 4;  // tuning knob: cap on row-blocks per super-tile
 static bool halo_eligible(const TcGemmProblem& p) {
   return g_halo_mode && !p.table && p.tap_mode == TC_TAP_SHIFT && p.out_mode == TC_OUT_CONV && p.kh == 3 &&
          p.kw == 3 && (p.kd == 3 || p.kd == 1) && p.ph >= 12 && p.pw >= 8;
 }
 
-int g_halo_resident = 1;  // tuning knob: weight-resident mode of the halo kernel
-int g_gemm_resident = 1;  // tuning knob: weight-resident mode of the per-tap kernel
+thread_local int g_halo_resident = 1;  // tuning knob: weight-resident mode of the halo kernel
+thread_local int g_gemm_resident = 1;  // tuning knob: weight-resident mode of the per-tap kernel
 
 static int tc_gemm_halo(const TcGemmProblem& p, cudaStream_t stream) {
   HaloArgs a{};
@@ -1556,14 +1537,14 @@ __global__ void __launch_bounds__(256, 1)
   if (warp == 2) tmem_dealloc(tmem_base, 512);
 }
 
-int g_wgrad_halo_mode = 1;
+thread_local int g_wgrad_halo_mode = 1;
 
 static bool wgrad_halo_eligible(const TcWgradProblem& p) {
   return g_wgrad_halo_mode && !p.table && p.tap_mode == TC_TAP_SHIFT && p.kh == 3 && p.kw == 3 &&
          (p.kd == 3 || p.kd == 1) && p.ph >= 12 && p.pw >= 8;
 }
 
-int g_wgrad_wide = 1;   // tuning knob: N = 128 four-pair variant + centre-tap GEMM for C_out >= 128
+thread_local int g_wgrad_wide = 1;   // tuning knob: N = 128 four-pair variant + centre-tap GEMM for C_out >= 128
 static int tc_wgrad_generic(const TcWgradProblem& p, cudaStream_t stream, bool wide_n);
 
 static int tc_wgrad_halo(const TcWgradProblem& p, cudaStream_t stream) {
@@ -1611,15 +1592,10 @@ static int tc_wgrad_halo(const TcWgradProblem& p, cudaStream_t stream) {
     if (rc) return rc;
   }
   const int smem = a.stages * stage_bytes + 2048;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(tc_wgrad_halo_kernel<false>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
-    if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(tc_wgrad_halo_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               kSmemBudget);
+  {
+    cudaError_t e = ensure_dynamic_smem((const void*)tc_wgrad_halo_kernel<false>, kSmemBudget);
+    if (e == cudaSuccess) e = ensure_dynamic_smem((const void*)tc_wgrad_halo_kernel<true>, kSmemBudget);
     if (e != cudaSuccess) return (int)e;
-    attr_set = true;
   }
   const long grid = base_ctas * a.splits;
   if (!wide) {
@@ -1715,12 +1691,9 @@ static int tc_wgrad_generic(const TcWgradProblem& p, cudaStream_t stream, bool w
   }
   if (rc) return rc;
   const int smem = a.stages * stage_bytes + 2048;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(tc_wgrad_kernel,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
+  {
+    cudaError_t e = ensure_dynamic_smem((const void*)tc_wgrad_kernel, kSmemBudget);
     if (e != cudaSuccess) return (int)e;
-    attr_set = true;
   }
   const long grid = base_ctas * a.splits;
   tc_wgrad_kernel<<<(unsigned)grid, 256, smem, stream>>>(tmM, tmN, a);

@@ -398,24 +398,40 @@ __global__ void seg_loss_bwd_kernel(int c, long spatial, long total, const float
 }
 
 // ------------------------------------------------------------------------------------ cross entropy
+// nn.CrossEntropyLoss() semantics: labels equal to ignore_index (-100) contribute nothing and do not count in
+// the mean; labels outside [0, c) (other than -100) are counted in sums[2] — the host turns a non-zero count
+// into a NaN loss instead of reading out of bounds.  sums = {sum nll, valid positions, bad labels}.
+#define B200_CE_IGNORE_INDEX (-100)
 __global__ void __launch_bounds__(256)
     ce_fwd_kernel(int n, int c, long spatial, const float* logits, const int64_t* labels,
-                  double* nll_sum) {
+                  double* sums) {
   __shared__ double sh[8];
   const long total = (long)n * spatial;
   float acc = 0.f;
+  unsigned valid = 0, bad = 0;
   for (long pos = (long)blockIdx.x * blockDim.x + threadIdx.x; pos < total; pos += (long)gridDim.x * blockDim.x) {
+    const int64_t lab = labels[pos];
+    if (lab == B200_CE_IGNORE_INDEX) continue;
+    if (lab < 0 || lab >= c) { ++bad; continue; }
     const long b = pos / spatial, s = pos % spatial;
     const float* xr = logits + b * c * spatial + s;
     float m = -INFINITY;
     for (int k = 0; k < c; ++k) m = fmaxf(m, xr[(long)k * spatial]);
     float se = 0.f;
     for (int k = 0; k < c; ++k) se += expf(xr[(long)k * spatial] - m);
-    const int lab = (int)labels[pos];
-    acc += (m + logf(se)) - xr[(long)lab * spatial];
+    acc += (m + logf(se)) - xr[lab * spatial];
+    ++valid;
   }
   const double r = block_sum_d((double)acc, sh);
-  if (threadIdx.x == 0) atomicAdd(nll_sum, r);
+  __syncthreads();
+  const double v = block_sum_d((double)valid, sh);
+  __syncthreads();
+  const double bd = block_sum_d((double)bad, sh);
+  if (threadIdx.x == 0) {
+    atomicAdd(sums, r);
+    atomicAdd(sums + 1, v);
+    if (bd != 0.0) atomicAdd(sums + 2, bd);
+  }
 }
 __global__ void ce_bwd_kernel(int n, int c, long spatial, const float* logits, const int64_t* labels,
                               const float* scale, float* dlogits) {
@@ -425,14 +441,18 @@ __global__ void ce_bwd_kernel(int n, int c, long spatial, const float* logits, c
     const long b = pos / spatial, s = pos % spatial;
     const float* xr = logits + b * c * spatial + s;
     float* gr = dlogits + b * c * spatial + s;
+    const int64_t lab = labels[pos];
+    if (lab < 0 || lab >= c) {   // ignored (or invalid) position: no gradient
+      for (int k = 0; k < c; ++k) gr[(long)k * spatial] = 0.f;
+      continue;
+    }
     float m = -INFINITY;
     for (int k = 0; k < c; ++k) m = fmaxf(m, xr[(long)k * spatial]);
     float se = 0.f;
     for (int k = 0; k < c; ++k) se += expf(xr[(long)k * spatial] - m);
     const float inv = 1.f / se;
-    const int lab = (int)labels[pos];
     for (int k = 0; k < c; ++k)
-      gr[(long)k * spatial] = sc * (expf(xr[(long)k * spatial] - m) * inv - (k == lab ? 1.f : 0.f));
+      gr[(long)k * spatial] = sc * (expf(xr[(long)k * spatial] - m) * inv - (k == (int)lab ? 1.f : 0.f));
   }
 }
 

@@ -106,7 +106,9 @@ def _acc(grads: Grads, p: Optional[nn.Parameter], g: torch.Tensor) -> None:
 
 
 # ===================================================================================== SingleConv
-SUPPORTED_LETTERS = set("cgbr")
+SUPPORTED_LETTERS = set("cgbrledD")
+# activation letters of create_conv (buildingblocks.py:55-59): nn.LeakyReLU() default slope, nn.ELU() default alpha
+ACT_OF_LETTER = {"r": (ops.ACT_RELU, 0.0), "l": (ops.ACT_LEAKY_RELU, 0.01), "e": (ops.ACT_ELU, 1.0)}
 
 
 class LayerSpec:
@@ -114,12 +116,13 @@ class LayerSpec:
     ``conv`` plus optional ``groupnorm`` / ``batchnorm`` modules, applied in ``order``."""
 
     def __init__(self, order: str, conv: nn.Module, groupnorm: Optional[nn.GroupNorm] = None,
-                 batchnorm: Optional[nn.Module] = None):
+                 batchnorm: Optional[nn.Module] = None, dropout_p: float = 0.0):
         bad = set(order) - SUPPORTED_LETTERS
         if bad:
-            raise NotImplementedError(
-                f"layer_order letters {sorted(bad)} (LeakyReLU/ELU/dropout) are outside the B200 hot path")
+            raise ValueError(f"Unsupported layer type(s) {sorted(bad)}. MUST be one of "
+                             "['b', 'g', 'r', 'l', 'e', 'c', 'd', 'D']")
         self.order, self.conv, self.groupnorm, self.batchnorm = order, conv, groupnorm, batchnorm
+        self.dropout_p = float(dropout_p)
 
 
 def _bn_moments(bn: nn.Module, x: CL, training: bool, in_sums: Optional[torch.Tensor] = None):
@@ -231,8 +234,31 @@ def single_conv_fwd(x: CL, spec: LayerSpec, training: bool, tape: Optional[list]
                 tape.append(("bn", cur, bn, mean, rstd, gamma, y if fuse_relu else None, training,
                              in_relu and i == 0))
             cur = y
-        elif ch == "r":  # a ReLU that could not be fused into its producer (first letter never is)
-            raise NotImplementedError(f"unfusable ReLU position in layer_order {letters!r}")
+        elif ch in "rle":
+            # LeakyReLU / ELU (and a ReLU that follows neither a conv nor a norm): one element-wise pass; the
+            # backward recovers the derivative from the stored output
+            kind, param = ACT_OF_LETTER[ch]
+            y = ops.act_fwd(cur, kind, param, out=dst)
+            if tape is not None:
+                tape.append(("act", kind, param, y))
+            cur, cur_sums = y, None
+            fuse_relu = ch == "r"
+        elif ch in "dD":
+            # nn.Dropout (element-wise) / nn.Dropout2d (whole channels per sample), buildingblocks.py:104-107:
+            # identity in eval mode; the keep mask comes from torch's generator, the multiply is ours
+            p = spec.dropout_p
+            if training and p > 0.0:
+                scale = 0.0 if p >= 1.0 else 1.0 / (1.0 - p)
+                keep = chan = None
+                if ch == "d":
+                    keep = (torch.rand((cur.npos, cur.c), device=cur.device) >= p).to(torch.uint8)
+                else:
+                    chan = (torch.rand((cur.n, cur.c), device=cur.device) >= p).float()
+                y = ops.scale_mask(cur, keep, chan, scale, out=dst)
+                if tape is not None:
+                    tape.append(("drop", keep, chan, scale))
+                cur, cur_sums = y, None
+            fuse_relu = False if (training and p > 0.0) else out_relu
         out_relu = fuse_relu
         i = nxt
     if out is not None and cur is not out:
@@ -354,6 +380,17 @@ def single_conv_bwd(dy: CL, recs: list, grads: Grads, need_dx: bool = True, prem
             _acc(grads, gn.bias, dbeta)
             dy = dx
             out_premasked = bool(mask_in)
+        elif kind == "act":
+            _, akind, param, y_act = rec
+            if not (akind == ops.ACT_RELU and pm):
+                dy = ops.act_bwd(dy, y_act, akind, param, out=dy)
+            sums = None
+            out_premasked = False
+        elif kind == "drop":
+            _, keep, chan, scale = rec
+            dy = ops.scale_mask(dy, keep, chan, scale, out=dy)
+            sums = None
+            out_premasked = False
         elif kind == "bn":
             _, x_in, bn, mean, rstd, gamma, y_relu, was_training, mask_in = rec
             if not was_training or (y_relu is not None and not pm):
@@ -510,8 +547,11 @@ def unet2d_backward(net, tape: list, dfeat: CL, grads: Grads, premasked: bool) -
 
 # ===================================================================================== 3D family
 def single_conv_spec(sc, order: str) -> LayerSpec:
-    """SingleConv (model/unet3d/buildingblocks.py:116-159): children 'conv', 'groupnorm', 'batchnorm'."""
-    return LayerSpec(order, sc.conv, getattr(sc, "groupnorm", None), getattr(sc, "batchnorm", None))
+    """SingleConv (model/unet3d/buildingblocks.py:116-159): children 'conv', 'groupnorm', 'batchnorm',
+    'dropout' / 'dropout2d'."""
+    drop = getattr(sc, "dropout", None) or getattr(sc, "dropout2d", None)
+    return LayerSpec(order, sc.conv, getattr(sc, "groupnorm", None), getattr(sc, "batchnorm", None),
+                     dropout_p=drop.p if drop is not None else 0.0)
 
 
 def double_conv_specs(dc, order: str) -> List[LayerSpec]:
@@ -533,9 +573,10 @@ def unet3d_forward(net, x_in: torch.Tensor, training: bool, tape: Optional[list]
     norm_first = order[0] in "gb"   # blocks start with a norm: their producers hand over statistics
     for i, enc in enumerate(net.encoders):
         if enc.pooling is not None:
-            pooled = ops.maxpool_fwd(x, 2 if is3d else 1)
+            avg = getattr(enc, "pool_type", "max") == "avg"
+            pooled = (ops.avgpool_fwd if avg else ops.maxpool_fwd)(x, 2 if is3d else 1)
             if tape is not None:
-                tape.append(("pool", x, relu))
+                tape.append(("pool", x, relu, avg))
             x, x_sums = pooled, None
         cs = enc.basic_module.SingleConv2.conv.out_channels
         dst = None
@@ -625,10 +666,11 @@ def unet3d_backward(net, tape: list, dfeat: CL, grads: Grads, premasked: bool) -
     for i in range(n_enc - 1, -1, -1):
         d, _, _ = block_bwd(d, tape, 2, grads, need_dx=i > 0, premasked=pm)
         if i > 0:
-            _, pre, pre_relu = tape.pop()
+            _, pre, pre_relu, avg = tape.pop()
             # the skip half of the concat gradient joins the gradient routed back through the pool;
             # when the pooled tensor is a ReLU output its ReLU backward is folded in as well
-            d = ops.maxpool_bwd(pre, d, 2 if is3d else 1, add=dskips[i - 1], mask_relu=pre_relu)
+            d = (ops.avgpool_bwd if avg else ops.maxpool_bwd)(pre, d, 2 if is3d else 1, add=dskips[i - 1],
+                                                              mask_relu=pre_relu)
             pm = pre_relu
 
 
@@ -638,11 +680,10 @@ class _NetFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, net, kind: str, images: torch.Tensor, *params):
-        ops.require_cuda(images)
         training = net.training
         need_grad = any(ctx.needs_input_grad)
         tape: Optional[list] = [] if need_grad else None
-        with torch.no_grad():
+        with ops.on_device(images), torch.no_grad():
             if kind == "unet2d":
                 feat = unet2d_forward(net, images, training, tape)
             elif kind == "resunet3d":
@@ -669,6 +710,8 @@ class _NetFunction(torch.autograd.Function):
         _REDUCER = getattr(net, "_b200_reducer", None)
         # measured (profiles/r01_wgrad_stream_ab.txt): -3 % on the 3D nets, whose backward carries ~5 ms of
         # HBM-bound norm / pool / up-sampling kernels to overlap; nothing on the norm-free 2D U-Net
+        dev_ctx = ops.on_device(dlogits)
+        dev_ctx.__enter__()
         if ctx.kind != "unet2d":
             _side_begin(dlogits.device)
         try:
@@ -685,10 +728,11 @@ class _NetFunction(torch.autograd.Function):
                 unet3d_backward(net, tape, dfeat, grads, ctx.feat_relu)
             _side_end(grads)
             if _REDUCER is not None:
-                _REDUCER.finish()
+                grads.update(_REDUCER.finish())     # averaged gradients in fresh memory (never the bucket views)
         finally:
             _REDUCER = None
             _side_end({})
+            dev_ctx.__exit__(None, None, None)
         ctx.tape = ctx.feat = None
         out = tuple(grads.get(p) if p.requires_grad else None for p in ctx.params)
         return (None, None, None) + out
@@ -705,10 +749,9 @@ class _BlockFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, mod, specs, x: torch.Tensor, *params):
-        ops.require_cuda(x)
         need_grad = any(ctx.needs_input_grad)
         tape = [] if need_grad else None
-        with torch.no_grad():
+        with ops.on_device(x), torch.no_grad():
             y, _, _ = block_fwd(ops.from_nchw(x), specs, mod.training, tape)
             out = ops.to_nchw(y, x.dim() == 5)
         ctx.tape, ctx.n, ctx.params, ctx.x_grad = tape, len(specs), params, ctx.needs_input_grad[2]
@@ -717,11 +760,56 @@ class _BlockFunction(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dout):
         grads: Grads = {}
-        dy = ops.from_nchw(dout)
-        dx, _, _ = block_bwd(dy, ctx.tape, ctx.n, grads, need_dx=ctx.x_grad)
-        gx = ops.to_nchw(dx, dout.dim() == 5) if ctx.x_grad else None
+        with ops.on_device(dout):
+            dy = ops.from_nchw(dout)
+            dx, _, _ = block_bwd(dy, ctx.tape, ctx.n, grads, need_dx=ctx.x_grad)
+            gx = ops.to_nchw(dx, dout.dim() == 5) if ctx.x_grad else None
         return (None, None, gx) + tuple(grads.get(p) if p.requires_grad else None for p in ctx.params)
 
 
 def run_block(mod, specs: List[LayerSpec], x: torch.Tensor) -> torch.Tensor:
     return _BlockFunction.apply(mod, specs, x, *tuple(mod.parameters()))
+
+
+class _StandaloneFunction(torch.autograd.Function):
+    """Stand-alone use of a module that is normally run by a whole-network executor (Encoder pooling,
+    Decoder, ResNetBlock, SE layers): ``run(inputs, want_tape) -> (out fp32 NC[D]HW, bwd)`` launches the
+    kernels; ``bwd(dout) -> (input grads, {param: grad})`` replays its tape."""
+
+    @staticmethod
+    def forward(ctx, run, n_in: int, *tensors):
+        inputs, params = tensors[:n_in], tensors[n_in:]
+        need_grad = any(ctx.needs_input_grad)
+        with ops.on_device(inputs[0]), torch.no_grad():
+            out, bwd = run(inputs, need_grad)
+        ctx.bwd, ctx.params, ctx.n_in = bwd, params, n_in
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        if ctx.bwd is None:
+            raise RuntimeError("backward through a forward that ran without grad")
+        with ops.on_device(dout), torch.no_grad():
+            dins, grads = ctx.bwd(dout.contiguous().float())
+        ctx.bwd = None
+        dins = tuple(d if need else None for d, need in zip(dins, ctx.needs_input_grad[2:2 + ctx.n_in]))
+        return (None, None) + dins + tuple(grads.get(p) if p.requires_grad else None for p in ctx.params)
+
+
+def run_standalone(run, inputs, params) -> torch.Tensor:
+    return _StandaloneFunction.apply(run, len(inputs), *inputs, *params)
+
+
+def run_pool(x: torch.Tensor, is3d: bool, avg: bool) -> torch.Tensor:
+    """2x max / average pooling of an fp32 NC[D]HW tensor through the path's kernels (Encoder.forward)."""
+    pd = 2 if is3d else 1
+
+    def run(inputs, want):
+        xin = ops.from_nchw(inputs[0])
+        y = (ops.avgpool_fwd if avg else ops.maxpool_fwd)(xin, pd)
+
+        def bwd(dout):
+            d = (ops.avgpool_bwd if avg else ops.maxpool_bwd)(xin, ops.from_nchw(dout), pd)
+            return (ops.to_nchw(d, is3d),), {}
+        return ops.to_nchw(y, is3d), (bwd if want else None)
+    return run_standalone(run, (x,), ())

@@ -119,20 +119,28 @@ class _CrossEntropy(torch.autograd.Function):
     @staticmethod
     def forward(ctx, logits, labels):
         ops.require_cuda(logits)
+        if tuple(labels.shape) != (logits.shape[0],) + tuple(logits.shape[2:]):
+            raise ValueError(f"CrossEntropyLoss: class-index target of shape {tuple(labels.shape)} does not match "
+                             f"logits {tuple(logits.shape)} (expected (N, *spatial), as nn.CrossEntropyLoss)")
         logits = logits.contiguous().float()
         labels = labels.contiguous().long()
-        ctx.save_for_backward(logits, labels)
-        return (ops.ce_fwd(logits, labels)[0] / labels.numel()).float()
+        s = ops.ce_fwd(logits, labels)
+        # mean over the positions whose label is not ignore_index (-100); a label outside [0, C) poisons the
+        # loss with NaN (the stock op raises a device-side assert; an out-of-bounds read must never happen)
+        valid = torch.where(s[2] > 0, torch.full_like(s[1], float("nan")), s[1])
+        ctx.save_for_backward(logits, labels, valid)
+        return (s[0] / valid).float()
 
     @staticmethod
     def backward(ctx, g):
-        logits, labels = ctx.saved_tensors
-        scale = (g.float() / labels.numel()).reshape(1)
+        logits, labels, valid = ctx.saved_tensors
+        scale = (g.double() / valid).float().reshape(1)
         return ops.ce_bwd(logits, labels, scale), None
 
 
 class CrossEntropyLoss(nn.Module):
-    """nn.CrossEntropyLoss() (mean, class-index targets) as chosen at model/unet2d/unet.py:1185."""
+    """nn.CrossEntropyLoss() (mean, class-index targets, ignore_index = -100) as chosen at
+    model/unet2d/unet.py:1185."""
 
     def forward(self, input, target):
         return _CrossEntropy.apply(input, target)

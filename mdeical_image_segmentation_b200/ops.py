@@ -27,9 +27,23 @@ def _p(t: Optional[torch.Tensor]) -> C.c_void_p:
 
 
 def require_cuda(t: torch.Tensor) -> None:
+    """Every wrapper launches on the CURRENT device's current stream: a tensor that lives on another GPU
+    would be written from the wrong stream / context, so it is refused (the whole-network executors switch
+    device themselves, see ``on_device``)."""
     if not t.is_cuda:
         raise RuntimeError("mdeical_image_segmentation_b200 runs on sm_100a CUDA tensors only "
                            "(no CPU fallback): move the model and inputs to a B200 device")
+    if t.device.index != torch.cuda.current_device():
+        raise RuntimeError(f"tensor on {t.device} but the current CUDA device is {torch.cuda.current_device()}: "
+                           "call torch.cuda.set_device(...) or wrap the call in torch.cuda.device(...) "
+                           "(one process per GPU is the supported layout)")
+
+
+def on_device(t: torch.Tensor):
+    """Context manager: make ``t``'s GPU the current device for the kernels launched inside."""
+    if not t.is_cuda:
+        require_cuda(t)
+    return torch.cuda.device(t.device)
 
 
 class CL:
@@ -360,6 +374,48 @@ def bilinear_bwd(dy: CL, scale: int, add: Optional[CL] = None) -> CL:
     return out
 
 
+ACT_RELU, ACT_LEAKY_RELU, ACT_ELU = 0, 1, 2
+
+
+def act_fwd(a: CL, kind: int, param: float, add: Optional[CL] = None, out: Optional[CL] = None) -> CL:
+    """out = act(a [+ add]) — LeakyReLU / ELU letters and the residual join of ResNetBlock."""
+    if out is None:
+        out = a.new_like()
+    call("b200_act_fwd", a.npos, a.c, kind, float(param), a.view(), _NULL_VIEW if add is None else add.view(),
+         out.view(), _stream())
+    return out
+
+
+def act_bwd(dy: CL, y: CL, kind: int, param: float, out: Optional[CL] = None) -> CL:
+    """dx = dy * act'(.), the derivative recovered from the stored output y."""
+    if out is None:
+        out = dy.new_like()
+    call("b200_act_bwd", dy.npos, dy.c, kind, float(param), dy.view(), y.view(), out.view(), _stream())
+    return out
+
+
+def scale_mask(x: CL, keep: Optional[torch.Tensor], chan: Optional[torch.Tensor], scale: float,
+               out: Optional[CL] = None) -> CL:
+    """out = x * scale * keep[pos][c] * chan[n][c] (dropout forward / backward; either mask may be None)."""
+    if out is None:
+        out = x.new_like()
+    call("b200_scale_mask", x.n, x.spatial, x.c, x.view(), _p(keep), _p(chan), float(scale), out.view(), _stream())
+    return out
+
+
+def avgpool_fwd(x: CL, pool_d: int) -> CL:
+    out = CL.empty(x.n, x.d // pool_d, x.h // 2, x.w // 2, x.c, x.device)
+    call("b200_avgpool2_fwd", x.n, x.d, x.h, x.w, x.c, pool_d, x.view(), out.view(), _stream())
+    return out
+
+
+def avgpool_bwd(x: CL, dy: CL, pool_d: int, add: Optional[CL] = None, mask_relu: bool = False) -> CL:
+    out = x.new_like()
+    call("b200_avgpool2_bwd", x.n, x.d, x.h, x.w, x.c, pool_d, x.view(), dy.view(),
+         _NULL_VIEW if add is None else add.view(), out.view(), int(mask_relu), _stream())
+    return out
+
+
 def add_relu(a: CL, b: CL) -> CL:
     """relu(a + b) into a new tensor (residual join)."""
     out = a.new_like()
@@ -675,7 +731,7 @@ def ce_fwd(logits: torch.Tensor, labels: torch.Tensor) -> torch.Tensor:
     spatial = logits[0, 0].numel()
     logits = logits.contiguous().float()
     labels = labels.contiguous().long()
-    s = torch.zeros(1, dtype=torch.float64, device=logits.device)
+    s = torch.zeros(3, dtype=torch.float64, device=logits.device)   # sum nll, valid positions, bad labels
     call("b200_ce_fwd", n, c, spatial, _p(logits), _p(labels), _p(s), _stream())
     return s
 

@@ -39,11 +39,18 @@ class GradReducer:
         self.bucket_start = 0
         self.handles = []
         self.slots: Dict[nn.Parameter, torch.Tensor] = {}
+        self._writers = set()      # streams that wrote slots of the bucket being filled
 
     # ---- called from engine backward, in the order gradients become final
     def on_grad(self, p: nn.Parameter, g: torch.Tensor) -> torch.Tensor:
+        """Packs a final gradient into its bucket slot (on the CURRENT stream — the executor calls this from
+        its main stream and from its weight-gradient side stream) and returns the slot.  The slot is a view
+        of the persistent bucket memory: it is only valid until the next backward; ``finish()`` hands out the
+        tensors that may become ``p.grad``."""
         n = p.numel()
         view = self.flat[self.offset:self.offset + n]
+        if self.cuda:
+            self._writers.add(torch.cuda.current_stream())
         if self.world > 1:
             torch.div(g.reshape(-1), float(self.world), out=view)
         else:
@@ -63,9 +70,13 @@ class GradReducer:
             return
         self.launched_buckets += 1
         if self.cuda:
-            ev = torch.cuda.Event()
-            ev.record(torch.cuda.current_stream())
-            self.comm_stream.wait_event(ev)
+            # every stream that wrote a slot of this bucket (main AND side stream) must be ahead of the
+            # all-reduce, not only the one that happened to cross the bucket boundary
+            for st in self._writers | {torch.cuda.current_stream()}:
+                ev = torch.cuda.Event()
+                ev.record(st)
+                self.comm_stream.wait_event(ev)
+            self._writers = set()
             with torch.cuda.stream(self.comm_stream):
                 self.handles.append(dist.all_reduce(chunk, op=dist.ReduceOp.SUM, group=self.group,
                                                     async_op=True))
@@ -74,7 +85,10 @@ class GradReducer:
                                                 async_op=True))
 
     def finish(self) -> Dict[nn.Parameter, torch.Tensor]:
-        """Flush the last bucket and order the compute stream after every all-reduce."""
+        """Flush the last bucket, order the compute stream after every all-reduce and return the averaged
+        gradients as views of ONE freshly allocated tensor: autograd keeps what backward returns as
+        ``p.grad`` without cloning, so handing out views of the persistent bucket memory would let the next
+        backward overwrite ``p.grad`` in place (gradient accumulation / ``zero_grad(set_to_none=False)``)."""
         self._launch()
         for h in self.handles:
             if self.cuda:
@@ -82,9 +96,19 @@ class GradReducer:
                     h.wait()
             else:
                 h.wait()
-        if self.cuda and self.world > 1:
-            torch.cuda.current_stream().wait_stream(self.comm_stream)
-        out = self.slots
+        if self.cuda:
+            cur = torch.cuda.current_stream()
+            if self.world > 1:
+                cur.wait_stream(self.comm_stream)
+            for st in self._writers:          # world == 1: no all-reduce ordered the writers before us
+                if st != cur:
+                    cur.wait_stream(st)
+        fresh = self.flat[:self.offset].clone()
+        out, off = {}, 0
+        for p, slot in self.slots.items():    # insertion order == packing order
+            n = slot.numel()
+            out[p] = fresh[off:off + n].view(slot.shape)
+            off += n
         self._reset()
         return out
 

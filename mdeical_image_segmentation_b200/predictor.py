@@ -171,3 +171,117 @@ class StandardPredictor:
             with h5py.File(os.path.join(self.output_dir, name), "w") as f:
                 f.create_dataset(self.output_dataset, data=result, compression="gzip")
         return result
+
+
+class LazyPredictor(StandardPredictor):
+    """predictor.py:171-223 — for volumes whose prediction maps must not be held in (device) memory: the
+    network still runs on the device, but ``prediction_map`` / ``normalization_mask`` live in the output store
+    (HDF5 datasets when ``h5py`` is importable and ``output_dir`` is given, otherwise ``.npy`` memory maps under
+    ``output_dir``, otherwise host arrays) and every predicted patch — its halo already removed on the device by
+    ``b200_patch_accumulate`` — is added to the store as soon as it is computed.  ``_save_results`` is the
+    reference's: block-wise normalisation over slices of 1/27 of the volume with the visited block's mask reset
+    to 1, arg-max segmentation block by block.  Slower than ``StandardPredictor`` by construction (one D2H copy
+    per patch), exactly as the reference warns."""
+
+    # ------------------------------------------------------------------ store
+    def _allocate_prediction_maps(self, output_shape, name: str = "volume"):
+        self._h5 = None
+        if self.output_dir is not None:
+            os.makedirs(self.output_dir, exist_ok=True)
+            try:
+                import h5py
+                self._h5 = h5py.File(os.path.join(self.output_dir, name + "_predictions.h5"), "w")
+                pm = self._h5.create_dataset(self.output_dataset, shape=output_shape, dtype="float32", chunks=True,
+                                             compression="gzip")
+                nm = self._h5.create_dataset("normalization", shape=output_shape, dtype="uint8", chunks=True,
+                                             compression="gzip")
+                return pm, nm
+            except ImportError:
+                base = os.path.join(self.output_dir, name)
+                pm = np.lib.format.open_memmap(base + "_predictions.npy", mode="w+", dtype="float32",
+                                               shape=tuple(output_shape))
+                nm = np.lib.format.open_memmap(base + "_normalization.npy", mode="w+", dtype="uint8",
+                                               shape=tuple(output_shape))
+                pm[...] = 0
+                nm[...] = 0
+                return pm, nm
+        return np.zeros(output_shape, dtype="float32"), np.zeros(output_shape, dtype="uint8")
+
+    def _save_results(self, prediction_map, normalization_mask):
+        z, y, x = prediction_map.shape[1:]
+        block = (z // 3, y // 3, x // 3)
+        channels = prediction_map.shape[0]
+        seg = None
+        if self.save_segmentation:
+            seg = (self._h5.create_dataset("segmentation", shape=(z, y, x), dtype="uint16", chunks=True,
+                                           compression="gzip") if self._h5 is not None
+                   else np.zeros((z, y, x), dtype="uint16"))
+        for idx in build_slices((z, y, x), block, block):
+            index = (slice(0, channels),) + tuple(idx)
+            prediction_map[index] /= normalization_mask[index]
+            normalization_mask[index] = 1          # never normalise an overlapping block twice
+            if seg is not None:
+                seg[tuple(idx)] = np.argmax(prediction_map[index], axis=0).astype("uint16")
+        result = np.asarray(seg[...] if seg is not None else prediction_map[...])
+        if self._h5 is not None:
+            del self._h5["normalization"]
+            if self.save_segmentation:
+                del self._h5[self.output_dataset]
+            self._h5.close()
+            self._h5 = None
+        return result
+
+    def _add_patch(self, pred: torch.Tensor, origin, halo, prediction_map, normalization_mask) -> None:
+        """One predicted patch (C, pd, ph, pw) including its halo -> the store (host side accumulate)."""
+        inner = tuple(int(s) - 2 * int(hh) for s, hh in zip(pred.shape[1:], halo))
+        acc = PredictionAccumulator(self._channels(), inner, pred.device)     # halo removal + channel pick
+        acc.add(pred, (0, 0, 0), halo, self.prediction_channel)
+        patch = acc.map.cpu().numpy()
+        index = (slice(0, patch.shape[0]),) + tuple(slice(int(o), int(o) + n) for o, n in zip(origin, inner))
+        prediction_map[index] += patch
+        normalization_mask[index] += 1
+
+    # ------------------------------------------------------------------ entry points
+    def predict_volume(self, raw, patch_shape: Sequence[int], stride_shape: Sequence[int],
+                       halo_shape: Sequence[int] = (0, 0, 0), batch_size: int = 1) -> np.ndarray:
+        device = next(self.model.parameters()).device
+        if device.type != "cuda":
+            raise RuntimeError("LazyPredictor runs on a CUDA model only (no CPU fallback)")
+        vol = torch.as_tensor(np.asarray(raw) if not torch.is_tensor(raw) else raw).float()
+        if vol.dim() == 3:
+            vol = vol.unsqueeze(0)
+        vol = vol.to(device, non_blocking=True).contiguous()
+        halo = tuple(int(v) for v in halo_shape)
+        slices = build_slices(vol.shape[1:], patch_shape, stride_shape)
+        pm, nm = self._allocate_prediction_maps((self._channels(),) + tuple(vol.shape[1:]))
+        win = tuple(p + 2 * hh for p, hh in zip(patch_shape, halo))
+        self.model.eval()
+        with torch.no_grad():
+            for start in range(0, len(slices), batch_size):
+                chunk = slices[start:start + batch_size]
+                batch = torch.empty((len(chunk), vol.shape[0]) + win, dtype=torch.float32, device=device)
+                for b, idx in enumerate(chunk):
+                    gather_patch(vol, [s.start for s in idx], patch_shape, halo, batch[b])
+                pred = self._forward(batch)
+                for b, idx in enumerate(chunk):
+                    self._add_patch(pred[b], [s.start for s in idx], halo, pm, nm)
+        return self._save_results(pm, nm)
+
+    def __call__(self, test_loader: Iterable) -> np.ndarray:
+        dataset = test_loader.dataset
+        device = next(self.model.parameters()).device
+        if device.type != "cuda":
+            raise RuntimeError("LazyPredictor runs on a CUDA model only (no CPU fallback)")
+        volume_shape = tuple(dataset.volume_shape())
+        halo = tuple(int(v) for v in (getattr(dataset, "halo_shape", None) or (0, 0, 0)))
+        path = getattr(dataset, "file_path", None)
+        name = os.path.splitext(os.path.basename(str(path)))[0] if path is not None else "volume"
+        pm, nm = self._allocate_prediction_maps((self._channels(),) + volume_shape, name)
+        self.model.eval()
+        with torch.no_grad():
+            for inp, indices in test_loader:
+                pred = self._forward(inp.to(device, non_blocking=True))
+                for b, index in enumerate(indices):
+                    index = tuple(index)[-3:]
+                    self._add_patch(pred[b], [s.start for s in index], halo, pm, nm)
+        return self._save_results(pm, nm)

@@ -2,9 +2,10 @@
 same class names, constructor arguments, child names and ``state_dict`` keys as
 model/unet3d/buildingblocks.py and model/unet3d/model.py, executed by the sm_100a kernels.
 
-In scope: ``layer_order`` strings over {g, b, c, r}, max-pool encoders, nearest or
-'deconv' (ConvTranspose k3 s2 p1 + nearest resize) decoders with concat joining, 1x1 head.
-SE blocks, LeakyReLU / ELU / dropout letters and avg-pool raise ``NotImplementedError``.
+In scope: every ``layer_order`` letter {c, g, b, r, l, e, d, D}, max- and
+avg-pool encoders, nearest or 'deconv' (ConvTranspose k3 s2 p1 + nearest resize) decoders with concat or
+summation joining, DoubleConv / ResNetBlock / ResNetBlockSE (scse, cse, sse) levels, 1x1 head; every block
+class also runs stand-alone (``forward``) through the same kernels.
 """
 from __future__ import annotations
 
@@ -59,9 +60,14 @@ def create_conv(in_channels, out_channels, kernel_size, order, num_groups, paddi
             mods.append(("groupnorm", nn.GroupNorm(num_groups=groups, num_channels=nch)))
         elif ch == "b":
             mods.append(("batchnorm", BN(in_channels if before_conv else out_channels)))
-        elif ch in "ledD":
-            raise NotImplementedError(
-                f"layer_order letter '{ch}' (LeakyReLU/ELU/dropout) is outside the B200 hot path")
+        elif ch == "l":
+            mods.append(("LeakyReLU", nn.LeakyReLU(inplace=True)))
+        elif ch == "e":
+            mods.append(("ELU", nn.ELU(inplace=True)))
+        elif ch == "d":
+            mods.append(("dropout", nn.Dropout(p=dropout_prob)))
+        elif ch == "D":
+            mods.append(("dropout2d", nn.Dropout2d(p=dropout_prob)))
         else:
             raise ValueError(f"Unsupported layer type '{ch}'. MUST be one of "
                              "['b', 'g', 'r', 'l', 'e', 'c', 'd', 'D']")
@@ -107,15 +113,13 @@ class DoubleConv(nn.Sequential):
 
 
 class ResNetBlock(nn.Module):
-    """buildingblocks.py:255-325 — ``relu(conv3(conv2(r)) + r)`` with ``r = conv1(x)`` (1x1x1 conv when the channel
-    count changes).  Inside ``ResidualUNet3D`` the whole-network executor (resnet_exec.py) runs it; the
-    non-linearity is the ReLU of the ``r`` letter (``l`` / ``e`` orders are outside the B200 path)."""
+    """buildingblocks.py:255-325 — ``act(conv3(conv2(r)) + r)`` with ``r = conv1(x)`` (1x1x1 conv when the channel
+    count changes); ``act`` = LeakyReLU(0.1) for 'l' orders, ELU for 'e' orders (the class default ``cge``), else
+    ReLU.  Inside ``ResidualUNet3D`` / ``ResidualUNet2D`` the whole-network executor (resnet_exec.py) runs it;
+    ``forward`` runs the same kernels stand-alone."""
 
     def __init__(self, in_channels, out_channels, kernel_size=3, order="cge", num_groups=8, is3d=True, **kwargs):
         super().__init__()
-        if "l" in order or "e" in order:
-            raise NotImplementedError("ResNetBlock with LeakyReLU / ELU (order letters l, e) is outside the B200 "
-                                      "hot path; use an order with 'r' (ResidualUNet3D's default is 'gcr')")
         if in_channels != out_channels:
             self.conv1 = (nn.Conv3d if is3d else nn.Conv2d)(in_channels, out_channels, 1)
         else:
@@ -127,15 +131,22 @@ class ResNetBlock(nn.Module):
             n_order = n_order.replace(c, "")
         self.conv3 = SingleConv(out_channels, out_channels, kernel_size=kernel_size, order=n_order,
                                 num_groups=num_groups, is3d=is3d)
-        self.non_linearity = nn.ReLU(inplace=True)
+        if "l" in order:
+            self.non_linearity = nn.LeakyReLU(negative_slope=0.1, inplace=True)
+        elif "e" in order:
+            self.non_linearity = nn.ELU(inplace=True)
+        else:
+            self.non_linearity = nn.ReLU(inplace=True)
         self.order = order
+        self.is3d = is3d
 
     def forward(self, x):
-        raise NotImplementedError("ResNetBlock runs inside ResidualUNet3D's whole-network executor")
+        from . import resnet_exec
+        return resnet_exec.run_block_standalone(self, x)
 
 
 class ChannelSELayer3D(nn.Module):
-    """se.py:18-57 (parameter container: ``fc1``, ``fc2``)."""
+    """se.py:18-57 (parameter container: ``fc1``, ``fc2``) — ``x * sigmoid(fc2(relu(fc1(mean(x)))))``."""
 
     def __init__(self, num_channels, reduction_ratio=2):
         super().__init__()
@@ -143,13 +154,23 @@ class ChannelSELayer3D(nn.Module):
         self.fc1 = nn.Linear(num_channels, num_channels // reduction_ratio, bias=True)
         self.fc2 = nn.Linear(num_channels // reduction_ratio, num_channels, bias=True)
 
+    def forward(self, x):
+        from . import resnet_exec
+        return resnet_exec.run_se_standalone(self, x)
+
 
 class SpatialSELayer3D(nn.Module):
-    """se.py:60-97 (parameter container: ``conv`` = Conv3d(C, 1, 1))."""
+    """se.py:60-97 (parameter container: ``conv`` = Conv3d(C, 1, 1)) — ``x * sigmoid(conv(x))``."""
 
     def __init__(self, num_channels):
         super().__init__()
         self.conv = nn.Conv3d(num_channels, 1, 1)
+
+    def forward(self, x, weights=None):
+        if weights is not None:
+            raise NotImplementedError("few-shot 'weights' of SpatialSELayer3D (se.py:81-84) are outside the path")
+        from . import resnet_exec
+        return resnet_exec.run_se_standalone(self, x)
 
 
 class ChannelSpatialSELayer3D(nn.Module):
@@ -160,25 +181,37 @@ class ChannelSpatialSELayer3D(nn.Module):
         self.cSE = ChannelSELayer3D(num_channels, reduction_ratio)
         self.sSE = SpatialSELayer3D(num_channels)
 
+    def forward(self, x):
+        from . import resnet_exec
+        return resnet_exec.run_se_standalone(self, x)
+
 
 class ResNetBlockSE(ResNetBlock):
-    """buildingblocks.py:328-362 — ResNetBlock followed by the concurrent spatial and channel SE gate
-    (``se_module='scse'``, the only variant ``ResidualUNetSE3D`` builds)."""
+    """buildingblocks.py:328-362 — ResNetBlock followed by a squeeze-and-excitation gate: ``scse`` (concurrent
+    spatial and channel, the variant ``ResidualUNetSE3D`` builds), ``cse`` or ``sse``.  The fused gate kernels use
+    ``max(y a, y b) = y max(a, b)``, which needs a non-negative block output: the block's non-linearity must be
+    ReLU (orders with 'r', e.g. the networks' ``gcr``); 'l' / 'e' orders raise."""
 
     def __init__(self, in_channels, out_channels, kernel_size=3, order="cge", num_groups=8, se_module="scse",
                  **kwargs):
         super().__init__(in_channels, out_channels, kernel_size=kernel_size, order=order,
                          num_groups=num_groups, **kwargs)
         assert se_module in ["scse", "cse", "sse"]
-        if se_module != "scse":
-            raise NotImplementedError("the B200 path implements se_module='scse' (ResidualUNetSE3D's default)")
+        if "l" in order or "e" in order:
+            raise NotImplementedError("ResNetBlockSE on the B200 path needs a ReLU block output (order with 'r'): "
+                                      "the fused SE gate relies on y >= 0")
         if out_channels > 1024:
             raise NotImplementedError("SE blocks wider than 1024 channels are outside the B200 path")
-        self.se_module = ChannelSpatialSELayer3D(num_channels=out_channels, reduction_ratio=1)
+        if se_module == "scse":
+            self.se_module = ChannelSpatialSELayer3D(num_channels=out_channels, reduction_ratio=1)
+        elif se_module == "cse":
+            self.se_module = ChannelSELayer3D(num_channels=out_channels, reduction_ratio=1)
+        else:
+            self.se_module = SpatialSELayer3D(num_channels=out_channels)
 
 
 class Encoder(nn.Module):
-    """buildingblocks.py:365-439 — optional 2x max-pool, then the basic module."""
+    """buildingblocks.py:365-439 — optional 2x max- or avg-pool, then the basic module."""
 
     def __init__(self, in_channels, out_channels, conv_kernel_size=3, apply_pooling=True,
                  pool_kernel_size=2, pool_type="max", basic_module=DoubleConv, conv_layer_order="gcr",
@@ -187,10 +220,14 @@ class Encoder(nn.Module):
         assert pool_type in ["max", "avg"]
         if basic_module not in (DoubleConv, ResNetBlock, ResNetBlockSE):
             raise NotImplementedError("only DoubleConv / ResNetBlock(SE) encoders are on the B200 hot path")
+        self.is3d, self.pool_type = is3d, pool_type
         if apply_pooling:
-            if pool_type != "max" or pool_kernel_size != 2:
-                raise NotImplementedError("the B200 path implements 2x max-pooling")
-            self.pooling = nn.MaxPool3d(kernel_size=2) if is3d else nn.MaxPool2d(kernel_size=2)
+            if pool_kernel_size != 2:
+                raise NotImplementedError("the B200 path implements 2x pooling (pool_kernel_size=2)")
+            if pool_type == "max":
+                self.pooling = nn.MaxPool3d(kernel_size=2) if is3d else nn.MaxPool2d(kernel_size=2)
+            else:
+                self.pooling = nn.AvgPool3d(kernel_size=2) if is3d else nn.AvgPool2d(kernel_size=2)
         else:
             self.pooling = None
         self.basic_module = basic_module(in_channels, out_channels, encoder=True,
@@ -200,7 +237,7 @@ class Encoder(nn.Module):
 
     def forward(self, x):  # stand-alone use; inside a network the executor fuses the whole level
         if self.pooling is not None:
-            x = self.pooling(x)
+            x = engine.run_pool(x, self.is3d, self.pool_type == "avg")   # the nn.*Pool child is only a marker
         return self.basic_module(x)
 
 
@@ -291,20 +328,27 @@ class Decoder(nn.Module):
                                          num_groups=num_groups, padding=padding,
                                          dropout_prob=dropout_prob, is3d=is3d)
 
+        self.concat, self.is3d = concat, is3d
+
+    def forward(self, encoder_features, x):
+        """buildingblocks.py:539-543, stand-alone: up-sample ``x`` to the skip's size, join, basic module."""
+        from . import resnet_exec
+        return resnet_exec.run_decoder_standalone(self, encoder_features, x)
+
     @staticmethod
     def _joining(encoder_features, x, concat):
         return torch.cat((encoder_features, x), dim=1) if concat else encoder_features + x
 
 
 def create_encoders(in_channels, f_maps, basic_module, conv_kernel_size, conv_padding, conv_upscale,
-                    dropout_prob, layer_order, num_groups, pool_kernel_size, is3d):
+                    dropout_prob, layer_order, num_groups, pool_kernel_size, is3d, pool_type="max"):
     """buildingblocks.py:553-601."""
     encoders = []
     for i, out_feature_num in enumerate(f_maps):
         encoders.append(Encoder(in_channels if i == 0 else f_maps[i - 1], out_feature_num,
                                 apply_pooling=i > 0, basic_module=basic_module,
                                 conv_layer_order=layer_order, conv_kernel_size=conv_kernel_size,
-                                num_groups=num_groups, pool_kernel_size=pool_kernel_size,
+                                num_groups=num_groups, pool_kernel_size=pool_kernel_size, pool_type=pool_type,
                                 padding=conv_padding, upscale=conv_upscale, dropout_prob=dropout_prob,
                                 is3d=is3d))
     return nn.ModuleList(encoders)
@@ -385,6 +429,19 @@ class ResidualUNetSE3D(AbstractUNet):
                          conv_upscale=conv_upscale, upsample=upsample, dropout_prob=dropout_prob, is3d=True)
 
 
+class ResidualUNet2D(AbstractUNet):
+    """model.py:323-359 — the residual U-Net with 2D convolutions / pooling / transposed convolutions."""
+
+    def __init__(self, in_channels, out_channels, final_sigmoid=True, f_maps=64, layer_order="gcr",
+                 num_groups=8, num_levels=5, is_segmentation=True, conv_padding=1, conv_upscale=2,
+                 upsample="default", dropout_prob=0.1, **kwargs):
+        super().__init__(in_channels=in_channels, out_channels=out_channels,
+                         final_sigmoid=final_sigmoid, basic_module=ResNetBlock, f_maps=f_maps,
+                         layer_order=layer_order, num_groups=num_groups, num_levels=num_levels,
+                         is_segmentation=is_segmentation, conv_padding=conv_padding,
+                         conv_upscale=conv_upscale, upsample=upsample, dropout_prob=dropout_prob, is3d=False)
+
+
 class UNet3D(AbstractUNet):
     """model.py:154-194."""
 
@@ -411,6 +468,15 @@ class UNet2D(AbstractUNet):
                          is_segmentation=is_segmentation, conv_padding=conv_padding,
                          conv_upscale=conv_upscale, upsample=upsample, dropout_prob=dropout_prob,
                          is3d=False)
+
+
+def get_model(model_config):
+    """model.py:362-364 — the YAML trainer's factory: ``{'name': 'UNet3D', ...}`` -> ``UNet3D(**config)``."""
+    classes = {c.__name__: c for c in (UNet3D, UNet2D, ResidualUNet3D, ResidualUNetSE3D, ResidualUNet2D)}
+    name = model_config["name"]
+    if name not in classes:
+        raise RuntimeError(f"Unsupported dataset class: {name}")     # utils.get_class's message (utils.py)
+    return classes[name](**model_config)
 
 
 if PreTrainedModel is not None:

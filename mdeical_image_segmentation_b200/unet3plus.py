@@ -322,7 +322,7 @@ class _Net3PFunction(torch.autograd.Function):
                     pm = True
             engine._side_end(grads)
             if engine._REDUCER is not None:
-                engine._REDUCER.finish()
+                grads.update(engine._REDUCER.finish())
         finally:
             engine._REDUCER = None
             engine._side_end({})

@@ -73,3 +73,44 @@ def standard_predict(model_fn, raw, patch_shape, stride_shape, halo_shape=(0, 0,
     if save_segmentation:
         result = np.argmax(result, axis=0).astype("uint16")
     return result
+
+
+def lazy_predict(model_fn, raw, patch_shape, stride_shape, halo_shape=(0, 0, 0), out_channels=1,
+                 prediction_channel=None, save_segmentation=False, batch_size=1):
+    """predictor.py:171-223 (``LazyPredictor``): the same accumulation as ``standard_predict`` into datasets of the
+    output file (arrays here — h5py is a storage detail), then ``_save_results``: block-wise normalisation over
+    slices of 1/27 of the volume (``SliceBuilder._build_slices`` with patch = stride = shape // 3), the visited
+    block's ``normalization_mask`` reset to 1 so that overlapping last blocks are not normalised twice, and the
+    arg-max segmentation written block by block."""
+    raw = np.asarray(raw, dtype=np.float32)
+    if raw.ndim == 3:
+        raw = raw[None]
+    padded = mirror_pad(raw, halo_shape)
+    channels = 1 if prediction_channel is not None else out_channels
+    prediction_map = np.zeros((channels,) + raw.shape[1:], dtype="float32")
+    normalization_mask = np.zeros((channels,) + raw.shape[1:], dtype="uint8")
+    slices = build_slices(raw.shape[1:], patch_shape, stride_shape)
+    for start in range(0, len(slices), batch_size):
+        chunk = slices[start:start + batch_size]
+        batch = np.stack([padded[(slice(None),) + tuple(slice(s.start, s.stop + 2 * h) for s, h in zip(idx, halo_shape))]
+                          for idx in chunk])
+        prediction = remove_padding(model_fn(batch), halo_shape)
+        for pred, index in zip(prediction, chunk):
+            if prediction_channel is None:
+                channel_slice = slice(0, out_channels)
+            else:
+                channel_slice = slice(0, 1)
+                pred = np.expand_dims(pred[prediction_channel], axis=0)
+            index = (channel_slice,) + tuple(index)
+            prediction_map[index] += pred
+            normalization_mask[index] += 1
+    z, y, x = prediction_map.shape[1:]
+    block = (z // 3, y // 3, x // 3)
+    segmentation = np.zeros((z, y, x), dtype="uint16") if save_segmentation else None
+    for idx in build_slices((z, y, x), block, block):
+        index = (slice(0, channels),) + tuple(idx)
+        prediction_map[index] /= normalization_mask[index]
+        normalization_mask[index] = 1
+        if save_segmentation:
+            segmentation[tuple(idx)] = np.argmax(prediction_map[index], axis=0).astype("uint16")
+    return segmentation if save_segmentation else prediction_map

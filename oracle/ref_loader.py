@@ -1,6 +1,7 @@
-"""Imports the UNMODIFIED reference modules from /root/reference with the import shims its stale
-import paths need.  Only usable inside the build container — the GPU box has
-no /root/reference — and only by oracle/make_golden.py and the CPU-side oracle pin test.
+"""Imports the UNMODIFIED reference modules with the import shims its stale import paths need (SURVEY.md
+Appendix C) — from /root/reference inside the build container (oracle/make_golden.py, the CPU-side oracle
+pin test) or from oracle/_ref, the verbatim copy of the path's files that oracle/build_ref.py makes and that
+travels to the GPU box (bench.py's CPU arm only).
 TEST INFRASTRUCTURE (see oracle/__init__)."""
 from __future__ import annotations
 
@@ -11,11 +12,24 @@ import types
 
 import torch
 
+_loaded = None
 REF_ROOT = os.environ.get("B200_REFERENCE_ROOT", "/root/reference")
+REF_COPY = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
 
 
 def available() -> bool:
     return os.path.isdir(os.path.join(REF_ROOT, "model", "unet2d"))
+
+
+def use_copy() -> bool:
+    """Point the loader at oracle/_ref (must be called before load()); False when the copy is absent."""
+    global REF_ROOT
+    if _loaded is not None:
+        return REF_ROOT == REF_COPY
+    if not os.path.isdir(os.path.join(REF_COPY, "model", "unet2d")):
+        return False
+    REF_ROOT = REF_COPY
+    return True
 
 
 def _stub(name: str, **attrs):
@@ -23,9 +37,6 @@ def _stub(name: str, **attrs):
     m.__dict__.update(attrs)
     sys.modules[name] = m
     return m
-
-
-_loaded = None
 
 
 def load():

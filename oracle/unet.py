@@ -96,8 +96,9 @@ def features_per_level(f_maps, num_levels: int) -> List[int]:
 
 
 def single_conv(sd: SD, p: str, x: torch.Tensor, order: str, num_groups: int, is3d: bool,
-                training: bool) -> torch.Tensor:
-    """model/unet3d/buildingblocks.py:14-159 — the layer_order mini-language over {g, b, c, r}."""
+                training: bool, dropout_prob: float = 0.1) -> torch.Tensor:
+    """model/unet3d/buildingblocks.py:14-159 — the layer_order mini-language over {g, b, c, r, l, e, d, D}
+    (dropout letters draw from torch's generator, as the reference's nn.Dropout / nn.Dropout2d do)."""
     conv = F.conv3d if is3d else F.conv2d
     for ch in order:
         if ch == "c":
@@ -112,6 +113,15 @@ def single_conv(sd: SD, p: str, x: torch.Tensor, order: str, num_groups: int, is
                              momentum=0.1, eps=1e-5)
         elif ch == "r":
             x = F.relu(x)
+        elif ch == "l":
+            x = F.leaky_relu(x)                                            # buildingblocks.py:57 (slope 0.01)
+        elif ch == "e":
+            x = F.elu(x)                                                   # :59
+        elif ch == "d":
+            x = F.dropout(x, dropout_prob, training)                       # :104-105
+        elif ch == "D":
+            x = F.dropout2d(x, dropout_prob, training) if x.dim() == 4 else \
+                F.dropout3d(x, dropout_prob, training)                     # :106-107 (channel-wise on 5-D input)
         else:
             raise ValueError(f"layer_order letter {ch!r} is outside the oracle's scope")
     return x
@@ -164,22 +174,73 @@ def resnet_block(sd: SD, p: str, x, order, num_groups, is3d, training):
         n_order = n_order.replace(ch, "")
     out = single_conv(sd, p + "conv2.", res, order, num_groups, is3d, training)
     out = single_conv(sd, p + "conv3.", out, n_order, num_groups, is3d, training)
-    out = F.relu(out + res)
-    q = p + "se_module."
-    if q + "cSE.fc1.weight" in sd:                                  # ResNetBlockSE, buildingblocks.py:328-362
-        squeeze = out.mean(dim=(2, 3, 4))                           # se.py:46 (AdaptiveAvgPool3d(1))
-        a = torch.sigmoid(F.linear(F.relu(F.linear(squeeze, sd[q + "cSE.fc1.weight"], sd[q + "cSE.fc1.bias"])),
-                                   sd[q + "cSE.fc2.weight"], sd[q + "cSE.fc2.bias"]))          # :49-50
-        b = torch.sigmoid(F.conv3d(out, sd[q + "sSE.conv.weight"], sd[q + "sSE.conv.bias"]))    # :88-90
-        out = torch.max(out * a[:, :, None, None, None], out * b)                               # :52, :93, :112
+    out = out + res
+    if "l" in order:                                                # buildingblocks.py:306-311
+        out = F.leaky_relu(out, 0.1)
+    elif "e" in order:
+        out = F.elu(out)
+    else:
+        out = F.relu(out)
+    if any(k.startswith(p + "se_module.") for k in sd):             # ResNetBlockSE, buildingblocks.py:328-362
+        out = se_layer(sd, p + "se_module.", out)
     return out
+
+
+def se_layer(sd: SD, q: str, x: torch.Tensor) -> torch.Tensor:
+    """model/unet3d/se.py: ChannelSELayer3D (:41-57, keys ``fc1/fc2``), SpatialSELayer3D (:75-97, key ``conv``) or
+    ChannelSpatialSELayer3D (:111-113, keys ``cSE.* / sSE.*``: element-wise max of the two)."""
+    def cse(k):
+        squeeze = x.mean(dim=(2, 3, 4))                             # :46 AdaptiveAvgPool3d(1)
+        a = torch.sigmoid(F.linear(F.relu(F.linear(squeeze, sd[k + "fc1.weight"], sd[k + "fc1.bias"])),
+                                   sd[k + "fc2.weight"], sd[k + "fc2.bias"]))          # :49-50
+        return x * a[:, :, None, None, None]                        # :52
+
+    def sse(k):
+        return x * torch.sigmoid(F.conv3d(x, sd[k + "conv.weight"], sd[k + "conv.bias"]))   # :88-93
+
+    if q + "cSE.fc1.weight" in sd:
+        return torch.max(cse(q + "cSE."), sse(q + "sSE."))          # :112
+    if q + "fc1.weight" in sd:
+        return cse(q)
+    return sse(q)
+
+
+def decoder_forward(sd: SD, p: str, skip: torch.Tensor, x: torch.Tensor, *, order: str = "gcr",
+                    num_groups: int = 8, is3d: bool = True, training: bool = True,
+                    residual: bool = False) -> torch.Tensor:
+    """buildingblocks.py:539-550 ``Decoder.forward(encoder_features, x)`` stand-alone: DoubleConv decoders
+    up-sample (nearest, or ConvTranspose k3 s2 p1 + nearest resize when a ``conv_transposed`` weight exists)
+    and concatenate ``(skip, x)``; ResNetBlock decoders (``residual``) up-sample by the transposed convolution
+    and sum."""
+    key = p + "upsampling.upsample.conv_transposed.weight"
+    if key in sd:
+        ct = F.conv_transpose3d if is3d else F.conv_transpose2d
+        x = F.interpolate(ct(x, sd[key], None, stride=2, padding=1), size=skip.shape[2:])
+    else:
+        x = F.interpolate(x, size=skip.shape[2:], mode="nearest")
+    if residual:
+        return resnet_block(sd, p + "basic_module.", skip + x, order, num_groups, is3d, training)
+    return double_conv(sd, p + "basic_module.", torch.cat((skip, x), dim=1), order, num_groups, is3d, training)
+
+
+def encoder_forward(sd: SD, p: str, x: torch.Tensor, *, order: str = "gcr", num_groups: int = 8,
+                    is3d: bool = True, training: bool = True, pool: Optional[str] = "max",
+                    residual: bool = False) -> torch.Tensor:
+    """buildingblocks.py:435-439 ``Encoder.forward``: optional 2x max / avg pooling (:409-418), basic module."""
+    if pool == "max":
+        x = (F.max_pool3d if is3d else F.max_pool2d)(x, 2)
+    elif pool == "avg":
+        x = (F.avg_pool3d if is3d else F.avg_pool2d)(x, 2)
+    if residual:
+        return resnet_block(sd, p + "basic_module.", x, order, num_groups, is3d, training)
+    return double_conv(sd, p + "basic_module.", x, order, num_groups, is3d, training)
 
 
 def residual_unet3d_forward(sd: SD, x: torch.Tensor, *, num_levels: int = 5, layer_order: str = "gcr",
                             num_groups: int = 8, is3d: bool = True, training: bool = True) -> torch.Tensor:
-    """model/unet3d/model.py:197-238 ResidualUNet3D: ResNetBlock levels, decoder = ConvTranspose(k3, s2, p1, no
-    bias) + nearest resize to the skip's size (buildingblocks.py:703-717), summation joining (:549),
-    ResNetBlock(out, out); 1x1 head; logits."""
+    """model/unet3d/model.py:197-238 ResidualUNet3D (and, with ``is3d=False``, ResidualUNet2D :323-359):
+    ResNetBlock levels, decoder = ConvTranspose(k3, s2, p1, no bias) + nearest resize to the skip's size
+    (buildingblocks.py:703-717), summation joining (:549), ResNetBlock(out, out); 1x1 head; logits."""
     pool = F.max_pool3d if is3d else F.max_pool2d
     feats: List[torch.Tensor] = []
     for i in range(num_levels):

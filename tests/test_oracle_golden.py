@@ -314,5 +314,7 @@ def test_residual_unet3d_matches_reference(name, cls):
     default = getattr(B, cls)(1, 1)                      # 5 levels, 64..1024 feature maps (model.py:207-213)
     assert len(default.encoders) == 5 and len(default.decoders) == 4
     assert default.encoders[4].basic_module.conv2.conv.out_channels == 1024
-    with pytest.raises(NotImplementedError):
-        B.ResidualUNet3D(1, 1, layer_order="cge")
+    elu = B.ResidualUNet3D(1, 1, layer_order="cge", f_maps=[8, 16])      # round 2: ELU / LeakyReLU orders build
+    assert isinstance(elu.encoders[0].basic_module.non_linearity, torch.nn.ELU)
+    with pytest.raises(NotImplementedError):                              # the fused SE gate needs a ReLU output
+        B.ResidualUNetSE3D(1, 1, layer_order="cge", f_maps=[8, 16])

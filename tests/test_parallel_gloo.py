@@ -79,3 +79,27 @@ def test_reducer_is_attached_to_every_executor():
         dp = DataParallelUNet(model)
         assert inner(model)._b200_reducer is dp.reducer, type(inner(model)).__name__
         assert sum(p.numel() for p in dp.reducer.params) == sum(p.numel() for p in model.parameters())
+
+
+def test_reducer_results_do_not_alias_bucket_memory():
+    """what backward returns becomes ``p.grad`` without a clone, so the reducer must hand out fresh
+    memory — a second backward (gradient accumulation, ``zero_grad(set_to_none=False)``) must not overwrite
+    the first result in place."""
+    from mdeical_image_segmentation_b200.parallel import GradReducer
+    net = nn.Sequential(nn.Linear(4, 3), nn.Linear(3, 2))
+    params = list(net.parameters())
+    red = GradReducer(params, bucket_mb=0.00001)
+    g1 = {p: torch.full(p.shape, 1.0) for p in params}
+    g2 = {p: torch.full(p.shape, 5.0) for p in params}
+    for p in reversed(params):
+        red.on_grad(p, g1[p])
+    first = red.finish()
+    keep = {p: first[p].clone() for p in params}
+    for p in reversed(params):
+        red.on_grad(p, g2[p])
+    second = red.finish()
+    for p in params:
+        assert first[p].data_ptr() != second[p].data_ptr()
+        assert torch.equal(first[p], keep[p]) and torch.equal(first[p], g1[p])
+        assert torch.equal(second[p], g2[p])
+        assert first[p].shape == p.shape
