@@ -339,8 +339,6 @@ def measure(args, name, w, steps, warmup, device, world, rank, full):
                     "step_tflops": round(step_tf / (ms_step / 1e3), 1),
                     "frac_of_sustained_peak": round(step_tf / (ms_step / 1e3) / pk["tf_sustained"], 4)}}
     if not full:
-        del model, opt, x, y
-        torch.cuda.empty_cache()
         return res
 
     # ---- end to end: pinned host batch -> H2D every step (prefetched on a copy stream), loss -> host
@@ -422,12 +420,19 @@ def measure(args, name, w, steps, warmup, device, world, rank, full):
                 "avg_launch_ms": round(top[1]["ms"] / top[1]["launches"], 4)}
         breakdown["_step"] = res["step"]
         res["breakdown"] = breakdown
-    del model, opt, x, y
-    torch.cuda.empty_cache()
     return res
 
 
-EXTRA_WORKLOADS = ("cfg2", "cfg3p")
+def release_device_memory():
+    """Between workloads: the model / optimizer / tape of the previous one are garbage only after measure()
+    has returned — collect them, then hand the cached blocks back so the next workload starts clean."""
+    import gc
+    gc.collect()
+    torch.cuda.synchronize()
+    torch.cuda.empty_cache()
+
+
+EXTRA_WORKLOADS = ("cfg3p", "cfg2")
 
 
 def run_b200(args, w):
@@ -442,6 +447,7 @@ def run_b200(args, w):
         dist.init_process_group("nccl", device_id=device)
     head = measure(args, args.workload, w, args.steps, args.warmup, device, world, rank, full=True)
     batch = head["batch"]
+    release_device_memory()
 
     # ---- the other two training configurations, device-resident, a few steps each (not the headline)
     extra = None
@@ -457,7 +463,7 @@ def run_b200(args, w):
                                "clocks": r["clocks"]}
             except Exception as e:   # an extra must never take the headline line down with it
                 extra[name] = {"error": f"{type(e).__name__}: {e}"[:300]}
-                torch.cuda.empty_cache()
+            release_device_memory()
 
     # ---- reference CPU baseline on a bounded sample, rank 0 at N = 1 only
     cpu = None

@@ -60,6 +60,16 @@ typedef struct b200_conv_desc {
  * wp_bwd bf16 [flipped tap][c_in][c_out]  (either output may be NULL). */
 int b200_conv_repack_weight(const b200_conv_desc* desc, const float* w, void* wp_fwd, void* wp_bwd,
                             b200_stream_t stream);
+/* The same re-pack for ALL filters of a network in one launch (the fp32 masters change every optimizer
+ * step).  c_in_pad >= c_in: the packs are written for c_in_pad input channels, the extra ones zero (narrow
+ * network inputs are stored zero-padded to 16 channels).  Either pack pointer may be NULL. */
+typedef struct b200_repack_item {
+  const float* w;              /* fp32 (c_out, c_in, ntaps)                                */
+  void* wp_fwd;                /* bf16 [tap][c_out][c_in_pad]                              */
+  void* wp_bwd;                /* bf16 [ntaps-1-tap][c_in_pad][c_out]                      */
+  int32_t c_out, c_in, c_in_pad, ntaps;
+} b200_repack_item;
+int b200_conv_repack_weights(int32_t count, const b200_repack_item* items, b200_stream_t stream);
 int b200_conv_fwd(const b200_conv_desc* desc, const void* x, const void* wp_fwd, const float* bias,
                   void* y, b200_stream_t stream);
 /* dx = conv_transpose(dy); if relu_mask != NULL (same layout as dx) dx is zeroed where mask <= 0 */
@@ -181,6 +191,7 @@ int b200_bilinear2d_bwd(int32_t n, int32_t ih, int32_t iw, int32_t c, int32_t sc
 #define B200_ACT_RELU 0
 #define B200_ACT_LEAKY_RELU 1
 #define B200_ACT_ELU 2
+#define B200_ACT_IDENTITY 3 /* y = a + b: the channel-count-agnostic form of b200_add */
 int b200_act_fwd(int64_t npos, int32_t c, int32_t kind, float param, b200_view a, b200_view b, b200_view y,
                  b200_stream_t stream);
 /* dx = dy * act'(.) with the derivative recovered from the stored OUTPUT y (y > 0 ? 1 : 0 | slope | y + alpha) */
@@ -227,7 +238,10 @@ int b200_bias_grad(int64_t npos, int32_t c, b200_view dy, float* db, b200_stream
 /* First convolution of a network (1-4 input channels; nn.Conv3d buildingblocks.py:63-70 with
  * in_channels = the volume's): taps concatenated along K — a[pos][tap * c_in + ci] bf16 (n*d*h*w, kp),
  * zero padding 1 (none in depth when kd = 1), zero beyond kd*9*c_in; kp a multiple of 8.  The weight
- * gradient of that layer is then b200_conv_bwd_weight of a 1x1x1 convolution with c_in = kp. */
+ * gradient of that layer is then b200_conv_bwd_weight of a 1x1x1 convolution with c_in = kp.
+ * A NEGATIVE c_in = -(real channels) appends one synthesised column per tap, k' = tap * (c + 1) + c, that is 1
+ * where the tap lies inside the volume: its weight gradient sum_q dy[q][co] [q + tap inside] yields the
+ * parameter gradients of a norm in front of this first conv without a data-gradient pass. */
 int b200_im2col3(int32_t n, int32_t d, int32_t h, int32_t w, int32_t c_in, int32_t kd, int32_t kp,
                  b200_view x, void* a, b200_stream_t stream);
 /* layout / precision boundary: fp32 NC(spatial) <-> bf16 channels-last */
@@ -250,6 +264,17 @@ int b200_gn_bwd(int32_t n, int64_t spatial, int32_t c, int32_t groups, b200_view
                 const float* stats, const float* gamma, b200_view dy, b200_view dx, float* dgamma,
                 float* dbeta, float* scratch, int32_t mask_relu, b200_stream_t stream);
 
+/* b200_gn_bwd_fused for the GroupNorm in front of a decoder's first conv, whose input is the concat
+ * (skip [0, cs) | nearest-upsampled [cs, cs + cx)) (buildingblocks.py:539-547, 671-673) with the up-sampling's
+ * backward folded in: x / dy are the (n, ld*fd, lh*fh, lw*fw, cs + cx) concat tensors (f* = 1 or 2 per axis);
+ * dskip receives the gradient of the skip half at full resolution, dlow (n, ld, lh, lw, cx) the gradient of the
+ * up-sampled half summed over each source voxel's children — the full-resolution gradient of that half and the
+ * separate F.interpolate backward pass do not exist.  colstats / scratch / dgamma / dbeta as b200_gn_bwd_fused. */
+int b200_gn_bwd_fused_up(int32_t n, int32_t ld, int32_t lh, int32_t lw, int32_t fd, int32_t fh, int32_t fw,
+                         int32_t cs, int32_t cx, int32_t groups, b200_view x, const float* stats,
+                         const float* gamma, b200_view dy, b200_view dskip, b200_view dlow, float* dgamma,
+                         float* dbeta, const double* colstats, float* scratch, int32_t mask_relu,
+                         b200_stream_t stream);
 /* (mean, rstd) per (sample, group) from per-channel sums: sums fp64 [n][2][c] = (sum x, sum x^2) as
  * produced by b200_conv_fwd_stats (or b200_gn_stats' scratch) */
 int b200_gn_stats_finalize(int32_t n, int64_t spatial, int32_t c, int32_t groups, float eps,

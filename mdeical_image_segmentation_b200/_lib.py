@@ -33,6 +33,11 @@ class DeconvDesc(C.Structure):
         "n", "d", "h", "w", "c_in", "c_out", "kd", "in_ctot", "in_coff", "impl")]
 
 
+class RepackItem(C.Structure):
+    _fields_ = [("w", C.c_void_p), ("wp_fwd", C.c_void_p), ("wp_bwd", C.c_void_p), ("c_out", C.c_int32),
+                ("c_in", C.c_int32), ("c_in_pad", C.c_int32), ("ntaps", C.c_int32)]
+
+
 class View(C.Structure):
     _fields_ = [("ptr", C.c_void_p), ("ctot", C.c_int32), ("coff", C.c_int32)]
 
@@ -43,6 +48,7 @@ _PC, _PT, _PD = C.POINTER(ConvDesc), C.POINTER(ConvTDesc), C.POINTER(DeconvDesc)
 # name -> argtypes (restype is always int unless listed in _SPECIAL)
 SIGNATURES = {
     "b200_conv_repack_weight": [_PC, _P, _P, _P, _P],
+    "b200_conv_repack_weights": [_I, C.POINTER(RepackItem), _P],
     "b200_conv_fwd": [_PC, _P, _P, _P, _P, _P],
     "b200_conv_bwd_data": [_PC, _P, _P, _P, _P, _P],
     "b200_conv_bwd_weight": [_PC, _P, _P, _P, _P],
@@ -52,6 +58,8 @@ SIGNATURES = {
     "b200_convt2x2_bwd_data_stats": [_PT, _P, _P, _P, _P, _I, _P, _P],
     "b200_gn_stats_finalize": [_I, _L, _I, _I, _F, _P, _P, _P],
     "b200_gn_bwd_fused": [_I, _L, _I, _I, View, _P, _P, View, View, _P, _P, _P, _P, _I, _P],
+    "b200_gn_bwd_fused_up": [_I, _I, _I, _I, _I, _I, _I, _I, _I, _I, View, _P, _P, View, View, View, _P, _P, _P, _P,
+                             _I, _P],
     "b200_bn_bwd_red_from_sums": [_I, _I, _P, _P, _P, _P, _P],
     "b200_convt2x2_repack_weight": [_PT, _P, _P, _P, _P],
     "b200_convt2x2_fwd": [_PT, _P, _P, _P, _P, _P],
@@ -166,7 +174,8 @@ def check(rc: int, what: str = "") -> None:
 
 
 # kernels launched per successful C-ABI call (for bench.py's `gpu_launches` accounting)
-LAUNCHES_PER_CALL = {"b200_gn_stats": 2, "b200_gn_bwd": 3, "b200_gn_bwd_fused": 2, "b200_deconv3s2_fwd": 8}
+LAUNCHES_PER_CALL = {"b200_gn_stats": 2, "b200_gn_bwd": 3, "b200_gn_bwd_fused": 2, "b200_deconv3s2_fwd": 8,
+                     "b200_gn_bwd_fused_up": 3}
 launch_count = 0
 # optional profiler hook: fn(name, args) -> context manager, installed by bench.py for per-kernel timing
 profile_hook = None

@@ -46,10 +46,11 @@ __device__ __forceinline__ void st(bf16* p, const float* f) {
   }
 }
 
-// kind: B200_ACT_RELU / LEAKY_RELU (param = negative slope) / ELU (param = alpha)
+// kind: B200_ACT_RELU / LEAKY_RELU (param = negative slope) / ELU (param = alpha) / IDENTITY (plain a + b)
 __device__ __forceinline__ float act_f(float x, int kind, float param) {
   if (kind == B200_ACT_LEAKY_RELU) return x > 0.f ? x : x * param;
   if (kind == B200_ACT_ELU) return x > 0.f ? x : param * expm1f(x);
+  if (kind == B200_ACT_IDENTITY) return x;
   return fmaxf(x, 0.f);
 }
 // derivative from the (bf16-stored) OUTPUT y: ReLU y > 0; LeakyReLU y > 0 ? 1 : slope (y and x share their
@@ -57,6 +58,7 @@ __device__ __forceinline__ float act_f(float x, int kind, float param) {
 __device__ __forceinline__ float act_df(float y, int kind, float param) {
   if (kind == B200_ACT_LEAKY_RELU) return y > 0.f ? 1.f : param;
   if (kind == B200_ACT_ELU) return y > 0.f ? 1.f : y + param;
+  if (kind == B200_ACT_IDENTITY) return 1.f;
   return y > 0.f ? 1.f : 0.f;
 }
 
@@ -209,7 +211,7 @@ using namespace b200;
   } while (0)
 
 static bool act_kind_ok(int kind) {
-  return kind == B200_ACT_RELU || kind == B200_ACT_LEAKY_RELU || kind == B200_ACT_ELU;
+  return kind == B200_ACT_RELU || kind == B200_ACT_LEAKY_RELU || kind == B200_ACT_ELU || kind == B200_ACT_IDENTITY;
 }
 
 int b200_act_fwd(int64_t npos, int32_t c, int32_t kind, float param, b200_view a, b200_view b, b200_view y,

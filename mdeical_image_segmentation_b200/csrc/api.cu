@@ -12,6 +12,7 @@ extern thread_local int g_gemm_resident;
 extern thread_local int g_epi_dbg;
 extern thread_local int g_epi_warps;
 extern thread_local int g_wgrad_wide;
+extern thread_local int g_halo_bn;
 int direct_gemm_conv(const TcGemmProblem& p, cudaStream_t stream);
 int direct_wgrad(const TcWgradProblem& p, cudaStream_t stream);
 static thread_local int g_last_impl = 0;
@@ -193,6 +194,7 @@ int b200_set_tuning(int key, int value) {
   if (key == 5) { b200::g_epi_warps = value; return B200_OK; }
   if (key == 3) { b200::g_halo_resident = value; b200::g_gemm_resident = value; return B200_OK; }
   if (key == 6) { b200::g_wgrad_wide = value; return B200_OK; }
+  if (key == 7) { b200::g_halo_bn = value; return B200_OK; }
   return B200_ERR_BAD_ARG;
 }
 
@@ -205,6 +207,69 @@ int b200_conv_repack_weight(const b200_conv_desc* d, const float* w, void* wp_fw
   conv_repack_kernel<<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(d->c_out, d->c_in, ntaps, w,
                                                                         (bf16*)wp_fwd, (bf16*)wp_bwd);
   B200_LAUNCH_CHECK();
+  return B200_OK;
+}
+
+// ---- all conv filters of a network in ONE launch -------------------------------------------------
+// A U-Net step re-packs 14-23 filters (the fp32 masters change every optimizer step); one launch per
+// filter cost 0.39-0.68 ms per step, mostly launch latency and 2-byte scattered stores.  Here a block
+// owns a 32 (c_out) x 32 (c_in) tile of one filter: the forward pack [tap][c_out][c_in] is written with
+// c_in along the warp, the backward pack [flipped tap][c_in][c_out] goes through a shared-memory
+// transpose so that c_out runs along the warp — both are contiguous 64-byte rows.
+namespace b200 {
+static const int kRepackMax = 24;
+struct RepackTable {
+  b200_repack_item it[kRepackMax];
+  int first_block[kRepackMax + 1];
+  int count;
+};
+__global__ void __launch_bounds__(1024) conv_repack_multi_kernel(const __grid_constant__ RepackTable t) {
+  __shared__ bf16 tile[32][33];
+  int k = 0;
+  while (k + 1 < t.count && (int)blockIdx.x >= t.first_block[k + 1]) ++k;
+  const b200_repack_item& it = t.it[k];
+  const int local = blockIdx.x - t.first_block[k];
+  const int ci_tiles = (it.c_in_pad + 31) / 32;
+  const int co0 = (local / ci_tiles) * 32, ci0 = (local % ci_tiles) * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int co = co0 + ty, ci = ci0 + tx;
+  const bool in_src = co < it.c_out && ci < it.c_in;          // padding channels read as zero
+  const float* src = it.w + ((long)co * it.c_in + ci) * it.ntaps;
+  bf16* fwd = (bf16*)it.wp_fwd;
+  bf16* bwd = (bf16*)it.wp_bwd;
+  const int co_t = co0 + tx, ci_t = ci0 + ty;                  // transposed roles for the backward pack
+  for (int tap = 0; tap < it.ntaps; ++tap) {
+    const bf16 v = __float2bfloat16(in_src ? src[tap] : 0.f);
+    if (fwd && co < it.c_out && ci < it.c_in_pad) fwd[((long)tap * it.c_out + co) * it.c_in_pad + ci] = v;
+    if (bwd) {
+      tile[ty][tx] = v;
+      __syncthreads();
+      if (co_t < it.c_out && ci_t < it.c_in_pad)
+        bwd[((long)(it.ntaps - 1 - tap) * it.c_in_pad + ci_t) * it.c_out + co_t] = tile[tx][ty];
+      __syncthreads();
+    }
+  }
+}
+}  // namespace b200
+
+int b200_conv_repack_weights(int32_t count, const b200_repack_item* items, b200_stream_t stream) {
+  if (count < 0 || (count > 0 && !items)) return B200_ERR_BAD_ARG;
+  for (int base = 0; base < count; base += b200::kRepackMax) {
+    b200::RepackTable t{};
+    t.count = count - base < b200::kRepackMax ? count - base : b200::kRepackMax;
+    int blocks = 0;
+    for (int i = 0; i < t.count; ++i) {
+      const b200_repack_item& it = items[base + i];
+      if (!it.w || it.c_out <= 0 || it.c_in <= 0 || it.c_in_pad < it.c_in || it.ntaps <= 0) return B200_ERR_BAD_ARG;
+      t.it[i] = it;
+      t.first_block[i] = blocks;
+      blocks += ((it.c_out + 31) / 32) * ((it.c_in_pad + 31) / 32);
+    }
+    t.first_block[t.count] = blocks;
+    if (blocks == 0) continue;
+    b200::conv_repack_multi_kernel<<<blocks, 1024, 0, (cudaStream_t)stream>>>(t);
+    B200_LAUNCH_CHECK();
+  }
   return B200_OK;
 }
 

@@ -1005,12 +1005,13 @@ static bool halo_eligible(const TcGemmProblem& p) {
 }
 
 thread_local int g_halo_resident = 1;  // tuning knob: weight-resident mode of the halo kernel
+thread_local int g_halo_bn = 0;        // tuning knob: 0 = heuristic column tile, else an upper bound on BN
 thread_local int g_gemm_resident = 1;  // tuning knob: weight-resident mode of the per-tap kernel
 
 static int tc_gemm_halo(const TcGemmProblem& p, cudaStream_t stream) {
   HaloArgs a{};
   a.pn = p.pn; a.pd = p.pd; a.ph = p.ph; a.pw = p.pw;
-  a.BN = pick_bn(p.ncols, 256);
+  a.BN = pick_bn(p.ncols, g_halo_bn >= 16 ? g_halo_bn : 256);
   a.n_tiles = p.ncols / a.BN;
   a.kd = p.kd;
   a.kdim = p.kdim; a.kchunks = (p.kdim + 63) / 64;

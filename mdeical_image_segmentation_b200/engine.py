@@ -105,6 +105,40 @@ def _acc(grads: Grads, p: Optional[nn.Parameter], g: torch.Tensor) -> None:
     grads[p] = _REDUCER.on_grad(p, g) if _REDUCER is not None else g
 
 
+# ===================================================================================== filter packs
+# The bf16 [tap][n][k] packs of all conv filters of a network are produced by ONE launch at the start of its
+# forward (b200_conv_repack_weights): the first forward records which (conv, padded c_in) pairs the executor
+# asks for, later forwards pre-pack that plan.  A conv that is not in the plan falls back to its own launch.
+PREPACK = os.environ.get("B200_PREPACK", "1") != "0"   # A/B knob
+_PACKS = None          # id(conv) -> (c_in_pad, wp_fwd, wp_bwd, k) while a network forward is running
+_PLAN_RECORD = None    # list being recorded during a first forward
+
+
+class prepacked:
+    """Context manager around a whole-network forward."""
+
+    def __init__(self, net, need_bwd: bool):
+        self.net, self.need_bwd = net, need_bwd
+
+    def __enter__(self):
+        global _PACKS, _PLAN_RECORD
+        plan = getattr(self.net, "_b200_pack_plan", None) if PREPACK else None
+        if plan:
+            res = ops.conv_repack_weights([c.weight for c, _ in plan], [p for _, p in plan], self.need_bwd)
+            _PACKS = {id(c): (p,) + r for (c, p), r in zip(plan, res)}
+            _PLAN_RECORD = None
+        else:
+            _PACKS, _PLAN_RECORD = None, ([] if PREPACK else None)
+        return self
+
+    def __exit__(self, *exc):
+        global _PACKS, _PLAN_RECORD
+        if _PLAN_RECORD and exc[0] is None:
+            self.net._b200_pack_plan = _PLAN_RECORD
+        _PACKS = _PLAN_RECORD = None
+        return False
+
+
 # ===================================================================================== SingleConv
 SUPPORTED_LETTERS = set("cgbrledD")
 # activation letters of create_conv (buildingblocks.py:55-59): nn.LeakyReLU() default slope, nn.ELU() default alpha
@@ -148,7 +182,25 @@ def _bn_moments(bn: nn.Module, x: CL, training: bool, in_sums: Optional[torch.Te
     return mean, rstd
 
 
-def _im2col_kp(x_real: CL, conv: nn.Module) -> int:
+def _first_norm_grads(norm_rec, conv: nn.Module, dw: torch.Tensor, dw_ones: torch.Tensor, grads: "Grads") -> None:
+    """dgamma / dbeta of the norm in front of the first conv from that conv's weight gradient (see
+    _plant_ones): a few hundred multiply-adds on (c_out, c_in, taps) tensors."""
+    kind = norm_rec[0]
+    norm = norm_rec[2]
+    w = conv.weight.detach().float()
+    dbeta = (w * dw_ones.unsqueeze(1)).flatten(2).sum(dim=(0, 2))                    # (c_in,)
+    gamma = norm.weight.detach().float()
+    beta = norm.bias.detach().float()
+    num = (w * dw).flatten(2).sum(dim=(0, 2)) - beta * dbeta
+    safe = gamma.abs() > 1e-12
+    dgamma = torch.where(safe, num / torch.where(safe, gamma, torch.ones_like(gamma)), torch.zeros_like(num))
+    if kind == "bn" and not norm_rec[7]:      # eval-mode BatchNorm: same affine map, same formulas
+        pass
+    _acc(grads, norm.weight, dgamma)
+    _acc(grads, norm.bias, dbeta)
+
+
+def _im2col_kp(x_real: CL, conv: nn.Module, c_col: Optional[int] = None) -> int:
     """K' = taps * c_in rounded up to 16 when the first layer's WEIGHT GRADIENT should run as one short-K
     GEMM over an im2col of the narrow input, else 0.  Measured (tools/first_layer_probe.py,
     profiles/r01_first_layer_probe.log): 3D 1->32 @128^3 0.72 -> 0.20 + 0.18 ms; the forward / data
@@ -156,17 +208,41 @@ def _im2col_kp(x_real: CL, conv: nn.Module) -> int:
     the halo kernel amortises over 512-position super-tiles) and so does 2D, where the im2col write costs
     what the weight gradient saves."""
     w = conv.weight
-    if w.dim() != 5 or tuple(w.shape[2:]) != (3, 3, 3) or x_real.coff != 0 or w.shape[1] != x_real.c:
+    c_col = x_real.c if c_col is None else c_col      # real channels (+ the planted ones channel)
+    if w.dim() != 5 or tuple(w.shape[2:]) != (3, 3, 3) or x_real.coff != 0 or c_col - w.shape[1] not in (0, 1):
         return 0
-    kp = (27 * x_real.c + 15) // 16 * 16
+    kp = (27 * c_col + 15) // 16 * 16
     return kp if kp <= 64 else 0
 
 
-def _im2col_weight_grad(dw2: torch.Tensor, w: torch.Tensor) -> torch.Tensor:
-    """(c_out, kp) with k' = tap * c_in + ci  ->  the conv's own (c_out, c_in, kd, kh, kw) layout."""
-    co, ci = w.shape[0], w.shape[1]
+def _im2col_weight_grad(dw2: torch.Tensor, w: torch.Tensor, c_col: Optional[int] = None) -> torch.Tensor:
+    """(c_out, kp) with k' = tap * c_col + ci  ->  (c_out, c_col, kd, kh, kw) (the conv's own layout when c_col
+    is its c_in)."""
+    co, ci = w.shape[0], (w.shape[1] if c_col is None else c_col)
     taps = w[0, 0].numel()
-    return dw2.reshape(co, -1)[:, :taps * ci].reshape(co, taps, ci).permute(0, 2, 1).reshape(w.shape).contiguous()
+    shape = (co, ci) + tuple(w.shape[2:])
+    return dw2.reshape(co, -1)[:, :taps * ci].reshape(co, taps, ci).permute(0, 2, 1).reshape(shape).contiguous()
+
+
+FIRST_NORM_FROM_WGRAD = os.environ.get("B200_FIRST_NORM_FROM_WGRAD", "1") != "0"   # A/B knob
+
+
+def _plant_ones(dst: CL, tape, i: int, letters: str, nxt: int, fuse_relu: bool, conv) -> int:
+    """A layer that starts ``norm -> conv`` on the narrow network input (stored zero-padded to 16 channels)
+    needs d(loss)/d(norm output) only for the norm's two parameter gradients.  With u = gamma * xhat + beta the
+    conv's input,
+        dbeta_c  = sum_pos du_c           = <w[:, c], dW1>            dW1[co, tap] = sum_q dy[q, co] [q + tap inside]
+        dgamma_c = sum_pos du_c * xhat_c  = (<w[:, c], dW[:, c]> - beta_c * dbeta_c) / gamma_c
+    and dW1 is exactly the weight gradient of an input channel that is 1 everywhere: it is planted in the first
+    padding channel (its filter taps are zero, so the forward is untouched) and rides in the layer's own
+    weight-gradient GEMM.  The data-gradient launch and the norm-backward pass of the first layer disappear
+    (cfg3: 0.70 + 0.08 ms of a 27.9 ms step).  Returns the channel index, or -1 when not applicable."""
+    if (not FIRST_NORM_FROM_WGRAD or tape is None or i != 0 or fuse_relu or nxt >= len(letters)
+            or letters[nxt] != "c" or dst.zpad < 1 or dst.coff != 0):
+        return -1
+    if not _im2col_kp(CL(dst.buf, dst.c + 1, 0, dst.zpad - 1), conv, dst.c + 1):
+        dst.buf[..., dst.c].fill_(1.0)      # (the im2col weight-gradient path synthesises the column instead)
+    return dst.c
 
 
 def single_conv_fwd(x: CL, spec: LayerSpec, training: bool, tape: Optional[list],
@@ -183,6 +259,7 @@ def single_conv_fwd(x: CL, spec: LayerSpec, training: bool, tape: Optional[list]
     cur_sums = in_sums if (in_sums is not None and in_sums.shape[2] == x.c) else None
     i = 0
     out_relu = False
+    ones_ch = -1          # index of a constant-one channel planted in the padding of the conv's input
     while i < len(letters):
         ch = letters[i]
         fuse_relu = ch in "cgb" and i + 1 < len(letters) and letters[i + 1] == "r"
@@ -192,10 +269,20 @@ def single_conv_fwd(x: CL, spec: LayerSpec, training: bool, tape: Optional[list]
             conv = spec.conv
             w = conv.weight.detach()
             xin = cur
-            if cur.zpad:  # narrow network input stored zero-padded: pad the filter's c_in to match
-                xin = cur.widened()
-                w = torch.nn.functional.pad(w, (0, 0) * (w.dim() - 2) + (0, cur.zpad))
-            wp_fwd, wp_bwd, k = ops.conv_repack_weight(w, need_bwd=tape is not None)
+            pk = _PACKS.get(id(conv)) if _PACKS is not None else None
+            if pk is not None and pk[0] == w.shape[1] + cur.zpad and (pk[2] is not None or tape is None):
+                wp_fwd, wp_bwd, k = pk[1], pk[2], pk[3]      # pre-packed (and channel-padded) by the one launch
+                if cur.zpad:
+                    xin = cur.widened()
+            else:
+                if cur.zpad:  # narrow network input stored zero-padded: pad the filter's c_in to match
+                    xin = cur.widened()
+                    if _PLAN_RECORD is not None:
+                        _PLAN_RECORD.append((conv, int(w.shape[1] + cur.zpad)))
+                    w = torch.nn.functional.pad(w, (0, 0) * (w.dim() - 2) + (0, cur.zpad))
+                elif _PLAN_RECORD is not None:
+                    _PLAN_RECORD.append((conv, int(w.shape[1])))
+                wp_fwd, wp_bwd, k = ops.conv_repack_weight(w, need_bwd=tape is not None)
             bias = None if conv.bias is None else conv.bias.detach().float().contiguous()
             need = (letters[nxt] in "gb") if nxt < len(letters) else want_sums
             if need:
@@ -204,7 +291,8 @@ def single_conv_fwd(x: CL, spec: LayerSpec, training: bool, tape: Optional[list]
                 y, cur_sums = ops.conv_fwd(xin, wp_fwd, k, bias, fuse_relu, out=dst, impl=IMPL), None
             if tape is not None:
                 tape.append(("conv", xin, conv, wp_bwd, k, y if fuse_relu else None, cur.zpad,
-                             in_relu and i == 0))
+                             in_relu and i == 0, ones_ch))
+            ones_ch = -1
             cur = y
         elif ch == "g":
             gn = spec.groupnorm
@@ -217,6 +305,7 @@ def single_conv_fwd(x: CL, spec: LayerSpec, training: bool, tape: Optional[list]
             beta = gn.bias.detach().float().contiguous()
             if dst is None and cur.zpad:
                 dst = cur.new_like_padded()
+                ones_ch = _plant_ones(dst, tape, i, letters, nxt, fuse_relu, spec.conv)
             y = ops.gn_apply(cur, gn.num_groups, stats, gamma, beta, fuse_relu, out=dst)
             if tape is not None:
                 tape.append(("gn", cur, gn, stats, gamma, y if fuse_relu else None, in_relu and i == 0))
@@ -229,6 +318,7 @@ def single_conv_fwd(x: CL, spec: LayerSpec, training: bool, tape: Optional[list]
             beta = bn.bias.detach().float().contiguous()
             if dst is None and cur.zpad:
                 dst = cur.new_like_padded()
+                ones_ch = _plant_ones(dst, tape, i, letters, nxt, fuse_relu, spec.conv)
             y = ops.bn_apply(cur, mean, rstd, gamma, beta, fuse_relu, out=dst)
             if tape is not None:
                 tape.append(("bn", cur, bn, mean, rstd, gamma, y if fuse_relu else None, training,
@@ -291,12 +381,27 @@ def _consumer_plan(consumer, fuse_mask: bool):
     return False, None
 
 
+FOLD_UPSAMPLE_BWD = os.environ.get("B200_FOLD_UPSAMPLE_BWD", "1") != "0"   # A/B knob
+
+
+class FoldedCatGrad:
+    """Gradient of a decoder concat buffer whose up-sampled half was reduced to its source resolution inside
+    the GroupNorm backward (b200_gn_bwd_fused_up): ``skip`` (full resolution) and ``low``."""
+    __slots__ = ("skip", "low")
+
+    def __init__(self, skip: CL, low: CL):
+        self.skip, self.low = skip, low
+
+
 def single_conv_bwd(dy: CL, recs: list, grads: Grads, need_dx: bool = True, premasked: bool = False,
-                    dy_sums: Optional[torch.Tensor] = None, consumer=None):
+                    dy_sums: Optional[torch.Tensor] = None, consumer=None, up_fold=None):
     """Backward of one layer: consumes the layer's tape records (in reverse); dy may be clobbered.
     ``premasked``: dy already carries the ReLU backward of this layer's final ReLU (its producer fused
     it).  ``dy_sums``: fp64 [n][2][c] reductions of dy that its producer computed for this layer's last
     op (see _consumer_plan).  ``consumer``: tape record of the op that will receive dx.
+    ``up_fold`` = (cs, low_dims): the layer's input is a decoder concat whose channels [cs, c) are an exact
+    nearest 1x/2x up-sampling of a (low_dims) tensor — when the layer starts with a GroupNorm whose sums came
+    from the data-gradient epilogue, dx is returned as a FoldedCatGrad (up-sampling backward folded in).
     Returns (dx, dx_premasked, dx_sums)."""
     out_premasked = False
     sums = dy_sums
@@ -307,7 +412,11 @@ def single_conv_bwd(dy: CL, recs: list, grads: Grads, need_dx: bool = True, prem
         pm = premasked and idx == len(recs) - 1
         nxt_consumer = recs[idx - 1] if idx > 0 else consumer
         if kind == "conv":
-            _, x_in, conv, wp_bwd, k, y_relu, zpad, mask_in = rec
+            _, x_in, conv, wp_bwd, k, y_relu, zpad, mask_in, ones_ch = rec
+            # first layer "norm -> conv" on the narrow input: the norm's parameter gradients come out of this
+            # layer's weight gradient (see _plant_ones) when nobody needs the data gradient itself
+            from_wgrad = (ones_ch >= 0 and idx == 1 and not need_dx and conv.weight.requires_grad
+                          and recs[0][0] in ("gn", "bn"))
             has_bias = conv.bias is not None and conv.bias.requires_grad
             db, db_in_wgrad = None, False
             if y_relu is not None and not pm:
@@ -319,16 +428,22 @@ def single_conv_bwd(dy: CL, recs: list, grads: Grads, need_dx: bool = True, prem
             elif has_bias:
                 db = ops.bias_grad(dy)
             sums = None
-            kp = _im2col_kp(CL(x_in.buf, x_in.c - zpad, x_in.coff, zpad), conv) if zpad else 0
+            c_real = x_in.c - zpad
+            c_col = c_real + (1 if from_wgrad else 0)     # channels the im2col has to carry
+            kp = _im2col_kp(CL(x_in.buf, c_col, x_in.coff, x_in.c - c_col), conv, c_col) if zpad else 0
+            dw_ones = None
             with _OnSide(x_in.buf, dy.buf, db):
                 if conv.weight.requires_grad and kp:
-                    a = ops.im2col(CL(x_in.buf, x_in.c - zpad, x_in.coff, zpad), 3, kp)
+                    a = ops.im2col(CL(x_in.buf, c_real, x_in.coff, x_in.c - c_real), 3, kp, ones=from_wgrad)
                     shape2 = (conv.weight.shape[0], kp, 1, 1, 1)
                     if db_in_wgrad:
                         dw2, db = ops.conv_bwd_weight(a, dy, (1, 1, 1), shape2, impl=IMPL, bias_grad=True)
                     else:
                         dw2 = ops.conv_bwd_weight(a, dy, (1, 1, 1), shape2, impl=IMPL)
-                    _acc(grads, conv.weight, _im2col_weight_grad(dw2, conv.weight))
+                    dw_all = _im2col_weight_grad(dw2, conv.weight, c_col)          # (c_out, c_col, kd, kh, kw)
+                    dw = dw_all[:, :c_real].contiguous() if from_wgrad else dw_all
+                    dw_ones = dw_all[:, c_real] if from_wgrad else None
+                    _acc(grads, conv.weight, dw)
                 elif conv.weight.requires_grad:
                     wshape = list(conv.weight.shape)
                     wshape[1] += zpad
@@ -337,10 +452,15 @@ def single_conv_bwd(dy: CL, recs: list, grads: Grads, need_dx: bool = True, prem
                     else:
                         dw = ops.conv_bwd_weight(x_in, dy, k, tuple(wshape), impl=IMPL)
                     if zpad:
+                        dw_ones = dw[:, ones_ch] if from_wgrad else None
                         dw = dw[:, :conv.weight.shape[1]].contiguous()
                     _acc(grads, conv.weight, dw)
                 if has_bias:
                     _acc(grads, conv.bias, db)
+                if from_wgrad:
+                    _first_norm_grads(recs[0], conv, dw, dw_ones, grads)
+            if from_wgrad:
+                return None, False, None
             if last and not need_dx:
                 return None, False, None
             # the fused mask must have the layout of the (dense) dx the kernel writes
@@ -370,7 +490,12 @@ def single_conv_bwd(dy: CL, recs: list, grads: Grads, need_dx: bool = True, prem
             if y_relu is not None and not pm:
                 dy, _ = ops.relu_bwd(dy, y_relu, False, out=dy)
                 sums = None
-            if sums is not None:
+            if (sums is not None and up_fold is not None and idx == 0 and FOLD_UPSAMPLE_BWD
+                    and x_in.is_full() and up_fold[0] % 8 == 0 and (x_in.c - up_fold[0]) % 8 == 0):
+                dskip, dlow, dgamma, dbeta = ops.gn_bwd_fused_up(x_in, gn.num_groups, stats, gamma, dy, sums,
+                                                                 up_fold[0], up_fold[1], mask_relu=mask_in)
+                dx = FoldedCatGrad(dskip, dlow)
+            elif sums is not None:
                 dx, dgamma, dbeta = ops.gn_bwd_fused(x_in, gn.num_groups, stats, gamma, dy, sums,
                                                      mask_relu=mask_in)
             else:
@@ -424,15 +549,15 @@ def block_fwd(x: CL, specs: List[LayerSpec], training: bool, tape: Optional[list
 
 
 def block_bwd(dy: CL, tape: list, nlayers: int, grads: Grads, need_dx: bool = True,
-              premasked: bool = False, dy_sums: Optional[torch.Tensor] = None, consumer=None):
-    """Returns (dx, dx_premasked, dx_sums) — see single_conv_bwd."""
+              premasked: bool = False, dy_sums: Optional[torch.Tensor] = None, consumer=None, up_fold=None):
+    """Returns (dx, dx_premasked, dx_sums) — see single_conv_bwd (``up_fold`` applies to the first layer)."""
     pm, sums = premasked, dy_sums
     for j in range(nlayers):
         recs = tape.pop()
         inner = j < nlayers - 1
         nxt = tape[-1][-1] if inner else consumer   # the previous layer's last op receives our dx
         dy, pm, sums = single_conv_bwd(dy, recs, grads, need_dx=need_dx or inner, premasked=pm,
-                                       dy_sums=sums, consumer=nxt)
+                                       dy_sums=sums, consumer=nxt, up_fold=None if inner else up_fold)
     return dy, pm, sums
 
 
@@ -646,9 +771,20 @@ def unet3d_backward(net, tape: list, dfeat: CL, grads: Grads, premasked: bool) -
     dskips: List[Optional[CL]] = [None] * n_enc
     d, pm = dfeat, premasked
     for j in range(len(net.decoders) - 1, -1, -1):
-        dcat, cat_pm, _ = block_bwd(d, tape, 2, grads, premasked=pm)
+        up_rec = tape[-3]       # [..., up-sampling record, layer 1 records, layer 2 records]
+        up_fold = None
+        if up_rec[0] == "nearest":
+            _, in_size, cs_, _cx = up_rec
+            skip = skips[n_enc - 2 - j]
+            if all(o == i or o == 2 * i for o, i in zip((skip.d, skip.h, skip.w), in_size)):
+                up_fold = (cs_, (skip.n,) + tuple(in_size))
+        dcat, cat_pm, _ = block_bwd(d, tape, 2, grads, premasked=pm, up_fold=up_fold)
         pm = False   # up-sampling backward sums children: the result is not a masked gradient
         rec = tape.pop()
+        if isinstance(dcat, FoldedCatGrad):        # the GroupNorm backward already reduced the up-sampled half
+            d, pm = dcat.low, cat_pm
+            dskips[n_enc - 2 - j] = dcat.skip
+            continue
         if rec[0] == "deconv":
             _, x_in, ct, wp_bwd, kd, cs, cx = rec
             d_planes = ops.deconv_resize_bwd(dcat.slice(cs, cx), x_in.dims, kd)
@@ -683,7 +819,7 @@ class _NetFunction(torch.autograd.Function):
         training = net.training
         need_grad = any(ctx.needs_input_grad)
         tape: Optional[list] = [] if need_grad else None
-        with ops.on_device(images), torch.no_grad():
+        with ops.on_device(images), torch.no_grad(), prepacked(net, need_grad):
             if kind == "unet2d":
                 feat = unet2d_forward(net, images, training, tape)
             elif kind == "resunet3d":

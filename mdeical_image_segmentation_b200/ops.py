@@ -13,7 +13,7 @@ from typing import Optional, Tuple
 import torch
 
 from . import _lib
-from ._lib import ConvDesc, ConvTDesc, DeconvDesc, View, call
+from ._lib import ConvDesc, ConvTDesc, DeconvDesc, RepackItem, View, call
 
 bf16 = torch.bfloat16
 
@@ -138,6 +138,40 @@ def conv_repack_weight(w: torch.Tensor, need_bwd: bool = True):
     d = ConvDesc(1, 1, 1, 1, c_in, c_out, k[0], k[1], k[2], c_in, 0, c_out, 0, 0, 0)
     call("b200_conv_repack_weight", C.byref(d), _p(w), _p(fwd), _p(bwd), _stream())
     return fwd, bwd, k
+
+
+def conv_repack_weights(weights, pads, need_bwd: bool = True):
+    """All filters of a network in ONE launch: weights = fp32 (c_out, c_in, [kd,] kh, kw) tensors, pads = the
+    padded input-channel count of each (>= c_in).  Returns [(wp_fwd, wp_bwd | None, k)] in order; the packs are
+    views of one allocation."""
+    if not weights:
+        return []
+    dev = weights[0].device
+    require_cuda(weights[0])
+    items = (RepackItem * len(weights))()
+    sizes, ks, keep = [], [], []
+    for w, cp in zip(weights, pads):
+        k = tuple(w.shape[2:])
+        k = (1,) * (3 - len(k)) + k
+        sizes.append((k[0] * k[1] * k[2] * w.shape[0] * cp + 63) // 64 * 64)   # packs stay 128-byte aligned (TMA)
+        ks.append(k)
+    total = sum(sizes)
+    buf = torch.empty(total * (2 if need_bwd else 1), dtype=bf16, device=dev)
+    out, off = [], 0
+    for i, (w, cp) in enumerate(zip(weights, pads)):
+        w32 = w.detach().contiguous().float()
+        keep.append(w32)
+        k, c_out, c_in = ks[i], w.shape[0], w.shape[1]
+        nt = k[0] * k[1] * k[2]
+        numel = nt * c_out * cp
+        fwd = buf[off:off + numel].view(nt, c_out, cp)
+        bwd = buf[total + off:total + off + numel].view(nt, cp, c_out) if need_bwd else None
+        off += sizes[i]
+        items[i] = RepackItem(w32.data_ptr(), fwd.data_ptr(), 0 if bwd is None else bwd.data_ptr(), c_out, c_in,
+                              cp, nt)
+        out.append((fwd, bwd, k))
+    call("b200_conv_repack_weights", len(weights), items, _stream())
+    return out
 
 
 def colstats_buffer(n: int, c: int, device) -> torch.Tensor:
@@ -374,7 +408,7 @@ def bilinear_bwd(dy: CL, scale: int, add: Optional[CL] = None) -> CL:
     return out
 
 
-ACT_RELU, ACT_LEAKY_RELU, ACT_ELU = 0, 1, 2
+ACT_RELU, ACT_LEAKY_RELU, ACT_ELU, ACT_IDENTITY = 0, 1, 2, 3
 
 
 def act_fwd(a: CL, kind: int, param: float, add: Optional[CL] = None, out: Optional[CL] = None) -> CL:
@@ -416,14 +450,22 @@ def avgpool_bwd(x: CL, dy: CL, pool_d: int, add: Optional[CL] = None, mask_relu:
     return out
 
 
+def _vec8(*ts: CL) -> bool:
+    return all(t.c % 8 == 0 and t.ctot % 8 == 0 and t.coff % 8 == 0 for t in ts)
+
+
 def add_relu(a: CL, b: CL) -> CL:
     """relu(a + b) into a new tensor (residual join)."""
+    if not _vec8(a, b):       # narrow test-size blocks: the channel-count-agnostic activation kernel
+        return act_fwd(a, ACT_RELU, 0.0, add=b)
     out = a.new_like()
     call("b200_add_relu", a.npos, a.c, a.view(), b.view(), out.view(), _stream())
     return out
 
 
 def add_(dst: CL, src: CL) -> CL:
+    if not _vec8(dst, src):
+        return act_fwd(dst, ACT_IDENTITY, 0.0, add=src, out=dst)
     call("b200_add", dst.npos, dst.c, src.view(), dst.view(), _stream())
     return dst
 
@@ -485,10 +527,11 @@ def from_nchw(x: torch.Tensor, out: Optional[CL] = None, pad: bool = False) -> C
     return out
 
 
-def im2col(x: CL, kd: int, kp: int) -> CL:
-    """Narrow first-layer input -> (n, d, h, w, kp) with the 3x3(x3) taps concatenated along channels."""
+def im2col(x: CL, kd: int, kp: int, ones: bool = False) -> CL:
+    """Narrow first-layer input -> (n, d, h, w, kp) with the 3x3(x3) taps concatenated along channels;
+    ``ones`` appends the synthesised inside-the-volume column per tap (x.c counts the real channels)."""
     a = CL.empty(x.n, x.d, x.h, x.w, kp, x.device)
-    call("b200_im2col3", x.n, x.d, x.h, x.w, x.c, kd, kp, x.view(), _p(a.buf), _stream())
+    call("b200_im2col3", x.n, x.d, x.h, x.w, -x.c if ones else x.c, kd, kp, x.view(), _p(a.buf), _stream())
     return a
 
 
@@ -546,6 +589,24 @@ def gn_bwd_fused(x: CL, groups, stats, gamma, dy: CL, colstats: torch.Tensor,
     call("b200_gn_bwd_fused", x.n, x.spatial, x.c, groups, x.view(), _p(stats), _p(gamma), dy.view(),
          out.view(), _p(dgamma), _p(dbeta), _p(colstats), _p(scratch), int(mask_relu), _stream())
     return out, dgamma, dbeta
+
+
+def gn_bwd_fused_up(x: CL, groups, stats, gamma, dy: CL, colstats: torch.Tensor, cs: int, low_dims,
+                    mask_relu: bool = False):
+    """GroupNorm backward over a decoder concat (skip | nearest-upsampled) with the up-sampling backward folded
+    in: returns (dskip full resolution (cs channels), dlow at the source resolution, dgamma, dbeta)."""
+    n, ld, lh, lw = low_dims
+    cx = x.c - cs
+    fd, fh, fw = x.d // ld, x.h // lh, x.w // lw
+    dskip = CL.empty(x.n, x.d, x.h, x.w, cs, x.device)
+    dlow = CL.empty(n, ld, lh, lw, cx, x.device)
+    dgamma = torch.zeros(x.c, dtype=torch.float32, device=x.device)
+    dbeta = torch.zeros(x.c, dtype=torch.float32, device=x.device)
+    scratch = torch.empty(x.n * groups * 2, dtype=torch.float32, device=x.device)
+    call("b200_gn_bwd_fused_up", n, ld, lh, lw, fd, fh, fw, cs, cx, groups, x.view(), _p(stats), _p(gamma),
+         dy.view(), dskip.view(), dlow.view(), _p(dgamma), _p(dbeta), _p(colstats), _p(scratch), int(mask_relu),
+         _stream())
+    return dskip, dlow, dgamma, dbeta
 
 
 def bn_stats(x: CL) -> torch.Tensor:

@@ -235,7 +235,7 @@ class _Net3PFunction(torch.autograd.Function):
         need_grad = any(ctx.needs_input_grad)
         tape = {} if need_grad else None
         outs, heads = [], []
-        with torch.no_grad():
+        with torch.no_grad(), engine.prepacked(net, need_grad):
             hd = _forward(net, images, net.training, tape)
             for i, scale in enumerate(net.HEAD_SCALES):
                 oc = getattr(net, f"outconv{i + 1}")

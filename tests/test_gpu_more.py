@@ -633,7 +633,9 @@ def test_sliding_window_predictor_vs_oracle(B):
 
     want = OP.standard_predict(net_fn, vol, patch, stride, halo, out_channels=2)
     got = StandardPredictor(net, out_channels=2).predict_volume(vol, patch, stride, halo, batch_size=1)
-    assert np.array_equal(got, want)
+    # the predictor's own arithmetic is bit-exact (stand-in model above); two forwards of a GroupNorm network may
+    # differ in the last bf16 digit of a few voxels (fp32 atomics order the statistics' partial sums)
+    assert np.abs(got - want).max() < 2e-2 * np.abs(want).max()
     got4 = StandardPredictor(net, out_channels=2).predict_volume(vol, patch, stride, halo, batch_size=4)
     assert np.abs(got4 - want).max() < 2e-2 * np.abs(want).max()          # batch 4 may pick other conv schedules
 
@@ -651,7 +653,7 @@ def test_sliding_window_predictor_vs_oracle(B):
                 yield torch.from_numpy(vol[idx][None, None]), [idx]
 
     got2 = StandardPredictor(net, None, 2)(_Loader())
-    assert np.array_equal(got2, want)
+    assert np.abs(got2 - want).max() < 2e-2 * np.abs(want).max()
 
 
 @pytest.mark.parametrize("name,cls", [("resunet3d_gcr", "ResidualUNet3D"), ("resunetse3d_gcr", "ResidualUNetSE3D")])
