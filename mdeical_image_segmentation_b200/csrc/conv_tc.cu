@@ -1169,7 +1169,7 @@ int tc_gemm_conv(const TcGemmProblem& p, cudaStream_t stream) {
 // ===================================================================== weight gradient
 // split-K factor for the weight-gradient kernels: the grid is base_ctas * splits one-shot CTAs, so pick
 // the split count whose total fills whole waves of the SMs (a 2.007-wave grid costs 3 waves)
-static int pick_splits(long base_ctas, int m_tiles, int sms) {
+static int pick_splits(long base_ctas, int m_tiles, int sms, double epi_tiles = 2.0) {
   long best = 1;
   double best_score = -1.0;
   const long max_splits = m_tiles < 512 ? m_tiles : 512;
@@ -1180,7 +1180,7 @@ static int pick_splits(long base_ctas, int m_tiles, int sms) {
     const double eff = (double)total / (double)(waves * sms);          // SM occupancy of the schedule
     const long tiles = (m_tiles + sp - 1) / sp;
     const double work_eff = (double)m_tiles / (double)(tiles * sp);     // padding of the last split
-    const double amort = (double)tiles / (double)(tiles + 2);           // prologue/epilogue per CTA
+    const double amort = (double)tiles / ((double)tiles + epi_tiles);   // prologue/epilogue per CTA, in tile times
     const double score = eff * work_eff * amort * (waves >= 2 ? 1.0 : 0.97);
     if (score > best_score) { best_score = score; best = sp; }
   }
@@ -1538,6 +1538,189 @@ __global__ void __launch_bounds__(256, 1)
   if (warp == 2) tmem_dealloc(tmem_base, 512);
 }
 
+// ===================================================================================== 3-D weight gradient, N = 192
+// ncu on the tap-pair kernel above (192 -> 64 @ 128^3, profiles/r02_wgrad_192_64_ncu.txt): the tensor pipe is 57 %
+// active while l1tex__data_pipe_tc_wavefronts_mem_shared sits at 84 % of its peak — an M = 128, N = 64, K = 16
+// MMA fetches 4 KB of A and 2 KB of B from shared memory (48 x 128-byte wavefronts, one per cycle) for 32 cycles of
+// math.  The operand fetch, not the math, bounds every N = 64 MMA, and with C_out = 64 the N side has nothing
+// more to give ... in ONE depth plane.  In 3-D the same x halo plane z meets THREE dy planes:
+//     dw[kd] += sum_q dy[plane z + 1 - kd][q] * x[plane z][q + (kh, kw)]          kd = 0, 1, 2
+// so the N operand is widened to 192 = (dy planes z-1 | z | z+1) x 64 output channels — one TMA box of depth 3
+// lands the three planes 16 KB apart, which is exactly the leading-dimension byte offset of a 3-atom MN-major
+// operand — and one MMA (80 wavefronts for 96 cycles of math: math-bound) produces all three depth taps of a
+// tap pair.  TMEM holds 512 columns = two N = 192 tap-pair groups + 128 columns, so the nine in-plane taps are
+// split over two CTA types that share nothing but the loads' L2 lines:
+//     type 0: pairs (0,1) (2,3) at N = 192, tap 8 against dy planes (z-1 | z) at N = 128       256 cycles / K step
+//     type 1: pairs (4,5) (6,7) at N = 192, tap 8 against dy plane  z+1      at N = 64        240 cycles / K step
+// against 3 x 5 x 48 = 720 for the tap-pair kernel run once per depth tap.  Tiles are indexed by the x plane z
+// (dy planes outside the volume are zero-filled by TMA), so there is no boundary case.  The bias gradient sums
+// the middle dy plane only.  The separate centre-tap GEMM of the wide variant is not needed for 3-D layers.
+struct WgradD3Args {
+  int pn, pd, ph, pw;
+  int tiles_h, tiles_w, m_tiles;
+  int ciblk, coblk, splits, tiles_per_split;
+  int cin, cout;
+  int stages;
+  float* dw;
+  long s_co, s_ci;
+  float* dbias;
+};
+
+static const int kD3XBytes = 23552;                    // 18 x 10 halo rows x 128 B, padded to 1024
+static const int kD3YBytes = 3 * kABytes;              // three dy planes of 128 positions x 64 channels
+static const int kD3StageBytes = kD3XBytes + kD3YBytes;
+
+__global__ void __launch_bounds__(256, 1)
+    tc_wgrad_d3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmDY,
+                       const WgradD3Args p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t sraw = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (sraw & 1023u)) & 1023u);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem);
+  uint64_t* empty = full + 16;
+  uint64_t* tfull = empty + 16;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tfull + 2);
+  uint8_t* tiles = smem + 1024;
+
+  int w = blockIdx.x;
+  const int cib = w % p.ciblk; w /= p.ciblk;
+  const int cob = w % p.coblk; w /= p.coblk;
+  const int type = w % 2; w /= 2;
+  const int split = w;
+  const int mt_begin = split * p.tiles_per_split;
+  int mt_end = mt_begin + p.tiles_per_split;
+  if (mt_end > p.m_tiles) mt_end = p.m_tiles;
+  const bool do_bias = p.dbias != nullptr && cib == 0 && type == 0;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmX);
+    tma_prefetch_desc(&tmDY);
+    for (int s = 0; s < p.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], do_bias ? 5 : 1); }
+    mbar_init(&tfull[0], 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int mt = mt_begin; mt < mt_end; ++mt) {
+      const TileCoord tc = decode_tile(mt, p.pd, p.tiles_h, p.tiles_w, 0, 4, 3);   // tc.d0 = x plane z
+      mbar_wait(&empty[stage], phase ^ 1);
+      if (elect_one()) {
+        uint8_t* sX = tiles + (size_t)stage * kD3StageBytes;
+        uint8_t* sY = sX + kD3XBytes;
+        mbar_arrive_expect_tx(&full[stage], (uint32_t)(kHaloPlaneBytes + kD3YBytes));
+        tma_load_5d(sX, &tmX, &full[stage], cib * 64, tc.w0 - 1, tc.h0 - 1, tc.d0, tc.n);
+        tma_load_5d(sY, &tmDY, &full[stage], cob * 64, tc.w0, tc.h0, tc.d0 - 1, tc.n);   // planes z-1, z, z+1
+      }
+      __syncwarp();
+      if (++stage == p.stages) { stage = 0; phase ^= 1; }
+    }
+  } else if (warp == 1) {
+    const uint32_t id192 = make_idesc_bf16(128, 192, 1, 1);
+    const uint32_t id_g2 = make_idesc_bf16(128, type == 0 ? 128 : 64, 1, 1);
+    int stage = 0;
+    uint32_t phase = 0;
+    bool first = true;
+    for (int mt = mt_begin; mt < mt_end; ++mt) {
+      mbar_wait(&full[stage], phase);
+      tc_fence_after();
+      const uint32_t xaddr = smem_u32(tiles + (size_t)stage * kD3StageBytes);
+      const uint32_t yaddr = xaddr + kD3XBytes;
+      if (elect_one()) {
+        const uint64_t db0 = make_smem_desc_sw128(yaddr, kABytes, 1024);                       // planes z-1 | z | z+1
+        const uint64_t db2 = make_smem_desc_sw128(yaddr + (type == 0 ? 0 : 2 * kABytes), kABytes, 1024);
+#pragma unroll
+        for (int g = 0; g < 3; ++g) {
+          // halo rows of the group's two taps: (0,1) (2,3) | (4,5) (6,7) | tap 8 twice (second half dropped)
+          const int ta = g < 2 ? (type * 4 + 2 * g) : 8, tb = g < 2 ? ta + 1 : 8;
+          const int ra = (ta / 3) * kHaloW + (ta % 3), rb = (tb / 3) * kHaloW + (tb % 3);
+          const uint64_t da0 = make_smem_desc_sw128(xaddr + (uint32_t)(ra * 128), (uint32_t)((rb - ra) * 128),
+                                                    kHaloW * 128);
+          const uint64_t dbg = g < 2 ? db0 : db2;
+          const uint32_t idesc = g < 2 ? id192 : id_g2;
+#pragma unroll
+          for (int j = 0; j < 8; ++j)   // 16 positions = 2 W-rows of the tile per MMA
+            umma_bf16(tmem_base + g * 192, da0 + (uint64_t)(j * ((2 * kHaloW * 128) >> 4)),
+                      dbg + (uint64_t)(j * (2048 >> 4)), idesc, !(first && j == 0));
+        }
+        umma_commit(&empty[stage]);
+        if (mt == mt_end - 1) umma_commit(&tfull[0]);
+      }
+      __syncwarp();
+      first = false;
+      if (++stage == p.stages) { stage = 0; phase ^= 1; }
+    }
+    if (mt_end <= mt_begin && elect_one()) umma_commit(&tfull[0]);
+  } else if (warp >= 4) {
+    const int q = warp - 4;
+    if (do_bias) {
+      // warp q sums positions [32 q, 32 q + 32) of the MIDDLE dy plane of every tile (each position once)
+      float bs0 = 0.f, bs1 = 0.f;
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int mt = mt_begin; mt < mt_end; ++mt) {
+        mbar_wait(&full[stage], phase);
+        const uint8_t* sY = tiles + (size_t)stage * kD3StageBytes + kD3XBytes + kABytes;
+#pragma unroll 8
+        for (int r = 0; r < 32; ++r) {
+          const int row = q * 32 + r;
+          const uint32_t v = *reinterpret_cast<const uint32_t*>(
+              sY + row * 128 + ((((lane >> 2) ^ (row & 7))) << 4) + ((lane & 3) << 2));
+          const float2 f = unpack_bf16x2(v);
+          bs0 += f.x;
+          bs1 += f.y;
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[stage]);
+        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+      }
+      const int co = cob * 64 + 2 * lane;
+      if (co < p.cout) atomicAdd(p.dbias + co, bs0);
+      if (co + 1 < p.cout) atomicAdd(p.dbias + co + 1, bs1);
+    }
+    const int m = q * 32 + lane;           // 0..127: (tap half, ci)
+    const int half = m >> 6;
+    const int ci = cib * 64 + (m & 63);
+    mbar_wait(&tfull[0], 0);
+    tc_fence_after();
+    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+    for (int g = 0; g < 3; ++g) {
+      const int tap = g < 2 ? (type * 4 + 2 * g + half) : 8;
+      const bool ok = !(g == 2 && half == 1) && ci < p.cin && mt_end > mt_begin;
+      const int nblk = g < 2 ? 3 : (type == 0 ? 2 : 1);         // 64-column blocks = dy planes of the group
+      for (int jb = 0; jb < nblk; ++jb) {
+        const int kd = g < 2 ? 2 - jb : (type == 0 ? 2 - jb : 0);   // dy plane z-1+jb  <->  depth tap 2-jb
+        const long base = (long)ci * p.s_ci + (kd * 9 + tap);
+        for (int c0 = 0; c0 < 64; c0 += 16) {
+          uint32_t v[16];
+          tmem_ld16(taddr + g * 192 + jb * 64 + c0, v);
+          tmem_ld_wait();
+          if (ok) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const int co = cob * 64 + c0 + j;
+              if (co < p.cout) atomicAdd(p.dw + (long)co * p.s_co + base, __uint_as_float(v[j]));
+            }
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, 512);
+}
+
+thread_local int g_wgrad_d3 = 1;   // tuning knob: N = 192 three-plane weight gradient for 3-D layers
+thread_local int g_wgrad_d3_epi = 80;   // tuning knob: epilogue cost (65 k fp32 reductions per CTA) in tile times
+
 thread_local int g_wgrad_halo_mode = 1;
 
 static bool wgrad_halo_eligible(const TcWgradProblem& p) {
@@ -1622,6 +1805,57 @@ static int tc_wgrad_halo(const TcWgradProblem& p, cudaStream_t stream) {
   return tc_wgrad_generic(c, stream, true);
 }
 
+static bool wgrad_d3_eligible(const TcWgradProblem& p) {
+  return g_wgrad_d3 && g_wgrad_halo_mode && !p.table && p.tap_mode == TC_TAP_SHIFT && p.kd == 3 && p.kh == 3 &&
+         p.kw == 3 && p.ph >= 12 && p.pw >= 8 && p.pd >= 2 && p.mop.c >= 48;
+}
+
+static int tc_wgrad_d3(const TcWgradProblem& p, cudaStream_t stream) {
+  // conv: mop = dy (c_out), nop = x (c_in); dw index = co * s_m + ci * s_n + tap
+  WgradD3Args a{};
+  a.pn = p.pn; a.pd = p.pd; a.ph = p.ph; a.pw = p.pw;
+  a.tiles_h = (p.ph + 15) / 16; a.tiles_w = (p.pw + 7) / 8;
+  a.m_tiles = p.pn * p.pd * a.tiles_h * a.tiles_w;
+  a.cin = p.nop.c; a.cout = p.mop.c;
+  a.ciblk = (a.cin + 63) / 64; a.coblk = (a.cout + 63) / 64;
+  a.stages = (kSmemBudget - 2048) / kD3StageBytes;
+  if (a.stages > 4) a.stages = 4;
+  if (a.stages < 2) return B200_ERR_UNSUPPORTED;
+  const long base_ctas = (long)a.ciblk * a.coblk * 2;
+  const long want = pick_splits(base_ctas, a.m_tiles, sm_count(), (double)g_wgrad_d3_epi);
+  a.tiles_per_split = (int)((a.m_tiles + want - 1) / want);
+  a.splits = (a.m_tiles + a.tiles_per_split - 1) / a.tiles_per_split;
+  a.dw = p.dw; a.s_co = p.s_m; a.s_ci = p.s_n;
+  a.dbias = p.dbias;
+
+  CUtensorMap tmX, tmDY;
+  {
+    const ActView& v = p.nop;
+    uint64_t dims[5] = {(uint64_t)v.c, (uint64_t)v.w, (uint64_t)v.h, (uint64_t)v.d, (uint64_t)v.n};
+    uint64_t str[5] = {1, (uint64_t)v.ctot, (uint64_t)v.w * v.ctot, (uint64_t)v.h * v.w * v.ctot,
+                       (uint64_t)v.d * v.h * v.w * v.ctot};
+    uint32_t box[5] = {64, (uint32_t)kHaloW, (uint32_t)kHaloH, 1, 1};
+    int rc = make_tmap_bf16(&tmX, v.ptr + v.coff, 5, dims, str, box);
+    if (rc) return rc;
+  }
+  {
+    const ActView& v = p.mop;
+    uint64_t dims[5] = {(uint64_t)v.c, (uint64_t)v.w, (uint64_t)v.h, (uint64_t)v.d, (uint64_t)v.n};
+    uint64_t str[5] = {1, (uint64_t)v.ctot, (uint64_t)v.w * v.ctot, (uint64_t)v.h * v.w * v.ctot,
+                       (uint64_t)v.d * v.h * v.w * v.ctot};
+    uint32_t box[5] = {64, 8, 16, 3, 1};      // three depth planes: 16 KB apart in shared memory
+    int rc = make_tmap_bf16(&tmDY, v.ptr + v.coff, 5, dims, str, box);
+    if (rc) return rc;
+  }
+  const int smem = a.stages * kD3StageBytes + 2048;
+  cudaError_t e = ensure_dynamic_smem((const void*)tc_wgrad_d3_kernel, kSmemBudget);
+  if (e != cudaSuccess) return (int)e;
+  const long grid = base_ctas * a.splits;
+  tc_wgrad_d3_kernel<<<(unsigned)grid, 256, smem, stream>>>(tmX, tmDY, a);
+  B200_LAUNCH_CHECK();
+  return B200_OK;
+}
+
 bool tc_wgrad_supported(const TcWgradProblem& p) {
   if (p.mop.c < 16 || p.nop.c < 16 || p.mop.c % 8 || p.nop.c % 8) return false;
   if (p.mop.ctot % 8 || p.mop.coff % 8 || p.nop.ctot % 8 || p.nop.coff % 8) return false;
@@ -1635,6 +1869,7 @@ bool tc_wgrad_fuses_bias(const TcWgradProblem& p) {
 
 int tc_wgrad(const TcWgradProblem& p, cudaStream_t stream) {
   if (!tc_wgrad_supported(p)) return B200_ERR_UNSUPPORTED;
+  if (wgrad_d3_eligible(p)) return tc_wgrad_d3(p, stream);
   if (wgrad_halo_eligible(p)) return tc_wgrad_halo(p, stream);
   return tc_wgrad_generic(p, stream, false);
 }

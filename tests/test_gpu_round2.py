@@ -387,10 +387,11 @@ KNOBS = {                      # b200_set_tuning(key, value) lists; () = default
     "streamed_weights": ((3, 0),),
     "epi4": ((5, 4),),
     "epi8": ((5, 8),),
-    "narrow_wgrad": ((6, 0),),
+    "narrow_wgrad": ((6, 0), (8, 0)),
+    "pair_wgrad": ((8, 0),),           # the tap-pair weight gradient instead of the 3-plane N = 192 kernel
     "per_tap": ((0, 0), (1, 0)),
 }
-DEFAULTS = {0: 1, 1: 1, 2: 4, 3: 1, 4: 0, 5: 0, 6: 1}
+DEFAULTS = {0: 1, 1: 1, 2: 4, 3: 1, 4: 0, 5: 0, 6: 1, 7: 0, 8: 1}
 
 LAYERS = [          # name, n, d, h, w, c_in, c_out  (SURVEY App. A headline shapes; batch cut to bound memory)
     ("3d_192_64_128", 1, 128, 128, 128, 192, 64),

@@ -16,12 +16,15 @@ LAYERS = {   # name: n, d, h, w, cin, cout
     "128_128": (2, 64, 64, 64, 128, 128),
     "768_256": (2, 32, 32, 32, 768, 256),
     "256_256": (2, 32, 32, 32, 256, 256),
+    "32_64": (2, 128, 128, 128, 32, 64),
+    "64_128": (2, 64, 64, 64, 64, 128),
+    "256_512": (2, 16, 16, 16, 256, 512),
     "2d_128_64": (16, 1, 512, 512, 128, 64),
     "2d_256_128": (16, 1, 256, 256, 256, 128),
     "2d_512_256": (16, 1, 128, 128, 512, 256),
     "2d_1024_512": (16, 1, 64, 64, 1024, 512),
 }
-DEFAULTS = {0: 1, 1: 1, 2: 4, 3: 1, 4: 0, 5: 0, 6: 1, 7: 0}
+DEFAULTS = {0: 1, 1: 1, 2: 4, 3: 1, 4: 0, 5: 0, 6: 1, 7: 0, 8: 1}
 lib = _lib.lib()
 
 
@@ -33,7 +36,7 @@ def set_knobs(pairs):
 
 
 def timeit(fn, iters=12):
-    for _ in range(3):
+    for _ in range(2):
         fn()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -59,13 +62,22 @@ def main():
         out = CL.empty(n, d, h, w, cout, "cuda")
         dx = CL.empty(n, d, h, w, cin, "cuda")
         fl = 2.0 * n * d * h * w * cin * cout * (27 if d > 1 else 9)
-        for cname, pairs in configs:
-            set_knobs(pairs)
-            tf = timeit(lambda: ops.conv_fwd(x, fwd, k, None, True, out=out, impl=1))
-            tb = timeit(lambda: ops.conv_bwd_data(dy, bwd, k, mask=x, out=dx, impl=1))
-            tw = timeit(lambda: ops.conv_bwd_weight(x, dy, k, tuple(wt.shape), impl=1))
-            print(f"{name:12s} {cname:16s} fwd {tf:7.3f} ms {fl / tf / 1e9:7.1f} TF/s | dgrad {tb:7.3f} ms "
-                  f"{fl / tb / 1e9:7.1f} TF/s | wgrad {tw:7.3f} ms {fl / tw / 1e9:7.1f} TF/s", flush=True)
+        which = os.environ.get("HALO_TUNE_OPS", "fwd,dgrad,wgrad").split(",")
+        fns = {"fwd": lambda: ops.conv_fwd(x, fwd, k, None, True, out=out, impl=1),
+               "dgrad": lambda: ops.conv_bwd_data(dy, bwd, k, mask=x, out=dx, impl=1),
+               "wgrad": lambda: ops.conv_bwd_weight(x, dy, k, tuple(wt.shape), impl=1)}
+        res = {(c, o): [] for c, _ in configs for o in which}
+        for rnd in range(7):                      # interleave the configurations: the power state drifts
+            for cname, pairs in configs:
+                set_knobs(pairs)
+                for o in which:
+                    res[(cname, o)].append(timeit(fns[o], iters=5))
+        for cname, _ in configs:
+            line = f"{name:12s} {cname:16s}"
+            for o in which:
+                t = sorted(res[(cname, o)])[len(res[(cname, o)]) // 2]
+                line += f" | {o} {t:7.3f} ms {fl / t / 1e9:7.1f} TF/s"
+            print(line, flush=True)
         set_knobs(())
         del x, dy, out, dx
 
