@@ -46,6 +46,51 @@ def on_device(t: torch.Tensor):
     return torch.cuda.device(t.device)
 
 
+class _ZeroPool:
+    """Zero-initialised accumulators (weight / bias / norm-parameter gradients, epilogue statistics, loss sums) are
+    carved out of large pre-zeroed chunks: a cfg3 step asked for 108 separate ``torch.zeros`` — 108 fill launches
+    (0.43 ms of kernels plus their launch gaps, ncu launch list profiles/r02_cfg3_launches.csv) — now a handful.
+    Every region is handed out once; a chunk lives as long as any tensor carved from it."""
+    CHUNK_BYTES = 1 << 20
+    MAX_TAKE = 64 << 10     # filters' gradients keep their own allocation: zeroed right before the weight-gradient
+                            # kernel they stay L2-resident for its fp32 reductions (measured: pooling them cost 1.2 ms)
+
+    def __init__(self):
+        self.cur = {}          # (device, stream, dtype) -> [chunk, offset]
+
+    def take(self, shape, dtype, device) -> torch.Tensor:
+        numel = 1
+        for v in shape:
+            numel *= int(v)
+        item = torch.empty((), dtype=dtype).element_size()
+        if numel * item > self.MAX_TAKE or torch.cuda.is_current_stream_capturing():
+            return torch.zeros(shape, dtype=dtype, device=device)
+        dev = torch.device(device)
+        # one chunk per (device, STREAM, dtype): a region must be zero in the stream that accumulates into it, and
+        # the chunk's fill was enqueued on the stream that allocated it
+        key = (dev.index if dev.index is not None else torch.cuda.current_device(),
+               torch.cuda.current_stream().cuda_stream, dtype)
+        padded = (numel * item + 255) // 256 * 256 // item         # regions stay 256-byte aligned
+        ent = self.cur.get(key)
+        if ent is None or ent[1] + padded > ent[0].numel():
+            ent = [torch.zeros(self.CHUNK_BYTES // item, dtype=dtype, device=device), 0]
+            self.cur[key] = ent
+        out = ent[0][ent[1]:ent[1] + numel].view(shape)
+        ent[1] += padded
+        return out
+
+
+_ZEROS = _ZeroPool()
+ZERO_POOL = True      # A/B knob (bench tools)
+
+
+def zeros(shape, dtype, device) -> torch.Tensor:
+    shape = (shape,) if isinstance(shape, int) else tuple(shape)
+    if not ZERO_POOL or torch.device(device).type != "cuda":
+        return torch.zeros(shape, dtype=dtype, device=device)
+    return _ZEROS.take(shape, dtype, device)
+
+
 class CL:
     """Channel slice of a channels-last bf16 buffer of shape (N, D, H, W, Ctot)."""
     __slots__ = ("buf", "c", "coff", "zpad")
@@ -176,7 +221,7 @@ def conv_repack_weights(weights, pads, need_bwd: bool = True):
 
 def colstats_buffer(n: int, c: int, device) -> torch.Tensor:
     """fp64 [n][2][c] accumulator for the fused epilogue statistics (sum r, sum r*r | sum r*dot)."""
-    return torch.zeros((n, 2, c), dtype=torch.float64, device=device)
+    return zeros((n, 2, c), torch.float64, device)
 
 
 def conv_fwd(x: CL, wp_fwd: torch.Tensor, k, bias: Optional[torch.Tensor], relu: bool,
@@ -237,11 +282,11 @@ def conv_bwd_data(dy: CL, wp_bwd: torch.Tensor, k, mask: Optional[CL] = None,
 
 def conv_bwd_weight(x: CL, dy: CL, k, w_shape, impl: int = 0, bias_grad: bool = False):
     """dw (and, with ``bias_grad``, (dw, db) — the bias gradient rides in the same kernel)."""
-    dw = torch.zeros(w_shape, dtype=torch.float32, device=x.device)
+    dw = zeros(w_shape, torch.float32, x.device)
     d = ConvDesc(x.n, x.d, x.h, x.w, x.c, dy.c, k[0], k[1], k[2], x.ctot, x.coff,
                  dy.ctot, dy.coff, 0, impl)
     if bias_grad:
-        db = torch.zeros(dy.c, dtype=torch.float32, device=x.device)
+        db = zeros(dy.c, torch.float32, x.device)
         call("b200_conv_bwd_weight_bias", C.byref(d), _p(x.buf), _p(dy.buf), _p(dw), _p(db), _stream())
         return dw, db
     call("b200_conv_bwd_weight", C.byref(d), _p(x.buf), _p(dy.buf), _p(dw), _stream())
@@ -290,7 +335,7 @@ def convt_bwd_data(dy: CL, wp_bwd, mask: Optional[CL] = None, out: Optional[CL] 
 
 
 def convt_bwd_weight(x: CL, dy: CL, impl: int = 0) -> torch.Tensor:
-    dw = torch.zeros((x.c, dy.c, 2, 2), dtype=torch.float32, device=x.device)
+    dw = zeros((x.c, dy.c, 2, 2), torch.float32, x.device)
     d = ConvTDesc(x.n, x.h, x.w, x.c, dy.c, x.ctot, x.coff, dy.ctot, dy.coff, impl)
     call("b200_convt2x2_bwd_weight", C.byref(d), _p(x.buf), _p(dy.buf), _p(dw), _stream())
     return dw
@@ -334,7 +379,7 @@ def deconv_bwd_data(dyp: CL, wp_bwd, x_dims, kd: int, impl: int = 0) -> CL:
 
 
 def deconv_bwd_weight(x: CL, dyp: CL, w_shape, kd: int, impl: int = 0) -> torch.Tensor:
-    dw = torch.zeros(w_shape, dtype=torch.float32, device=x.device)
+    dw = zeros(w_shape, torch.float32, x.device)
     call("b200_deconv3s2_bwd_weight", C.byref(_deconv_desc(x, dyp.c, kd, impl)), _p(x.buf),
          _p(dyp.buf), _p(dw), _stream())
     return dw
@@ -497,13 +542,13 @@ def copy_channels(src: CL, dst: CL) -> CL:
 def relu_bwd(dy: CL, a: CL, bias_grad: bool, out: Optional[CL] = None):
     if out is None:
         out = dy.new_like()
-    db = torch.zeros(dy.c, dtype=torch.float32, device=dy.device) if bias_grad else None
+    db = zeros(dy.c, torch.float32, dy.device) if bias_grad else None
     call("b200_relu_bwd", dy.npos, dy.c, dy.view(), a.view(), out.view(), _p(db), _stream())
     return out, db
 
 
 def bias_grad(dy: CL) -> torch.Tensor:
-    db = torch.zeros(dy.c, dtype=torch.float32, device=dy.device)
+    db = zeros(dy.c, torch.float32, dy.device)
     call("b200_bias_grad", dy.npos, dy.c, dy.view(), _p(db), _stream())
     return db
 
@@ -544,7 +589,7 @@ def to_nchw(x: CL, is3d: bool) -> torch.Tensor:
 
 # ------------------------------------------------------------------------------------- norms
 def gn_stats(x: CL, groups: int, eps: float) -> torch.Tensor:
-    sums = torch.zeros((x.n, 2, x.c), dtype=torch.float64, device=x.device)
+    sums = zeros((x.n, 2, x.c), torch.float64, x.device)
     stats = torch.empty((x.n, groups, 2), dtype=torch.float32, device=x.device)
     call("b200_gn_stats", x.n, x.spatial, x.c, groups, eps, x.view(), _p(sums), _p(stats), _stream())
     return stats
@@ -569,9 +614,9 @@ def gn_apply(x: CL, groups, stats, gamma, beta, relu: bool, out: Optional[CL] = 
 def gn_bwd(x: CL, groups, stats, gamma, dy: CL, out: Optional[CL] = None, mask_relu: bool = False):
     if out is None:
         out = x.new_like()
-    dgamma = torch.zeros(x.c, dtype=torch.float32, device=x.device)
-    dbeta = torch.zeros(x.c, dtype=torch.float32, device=x.device)
-    scratch = torch.zeros(x.n * x.c * 2 + x.n * groups * 2, dtype=torch.float32, device=x.device)
+    dgamma = zeros(x.c, torch.float32, x.device)
+    dbeta = zeros(x.c, torch.float32, x.device)
+    scratch = zeros(x.n * x.c * 2 + x.n * groups * 2, torch.float32, x.device)
     call("b200_gn_bwd", x.n, x.spatial, x.c, groups, x.view(), _p(stats), _p(gamma), dy.view(),
          out.view(), _p(dgamma), _p(dbeta), _p(scratch), int(mask_relu), _stream())
     return out, dgamma, dbeta
@@ -583,8 +628,8 @@ def gn_bwd_fused(x: CL, groups, stats, gamma, dy: CL, colstats: torch.Tensor,
     epilogue of the kernel that produced dy."""
     if out is None:
         out = x.new_like()
-    dgamma = torch.zeros(x.c, dtype=torch.float32, device=x.device)
-    dbeta = torch.zeros(x.c, dtype=torch.float32, device=x.device)
+    dgamma = zeros(x.c, torch.float32, x.device)
+    dbeta = zeros(x.c, torch.float32, x.device)
     scratch = torch.empty(x.n * groups * 2, dtype=torch.float32, device=x.device)
     call("b200_gn_bwd_fused", x.n, x.spatial, x.c, groups, x.view(), _p(stats), _p(gamma), dy.view(),
          out.view(), _p(dgamma), _p(dbeta), _p(colstats), _p(scratch), int(mask_relu), _stream())
@@ -600,8 +645,8 @@ def gn_bwd_fused_up(x: CL, groups, stats, gamma, dy: CL, colstats: torch.Tensor,
     fd, fh, fw = x.d // ld, x.h // lh, x.w // lw
     dskip = CL.empty(x.n, x.d, x.h, x.w, cs, x.device)
     dlow = CL.empty(n, ld, lh, lw, cx, x.device)
-    dgamma = torch.zeros(x.c, dtype=torch.float32, device=x.device)
-    dbeta = torch.zeros(x.c, dtype=torch.float32, device=x.device)
+    dgamma = zeros(x.c, torch.float32, x.device)
+    dbeta = zeros(x.c, torch.float32, x.device)
     scratch = torch.empty(x.n * groups * 2, dtype=torch.float32, device=x.device)
     call("b200_gn_bwd_fused_up", n, ld, lh, lw, fd, fh, fw, cs, cx, groups, x.view(), _p(stats), _p(gamma),
          dy.view(), dskip.view(), dlow.view(), _p(dgamma), _p(dbeta), _p(colstats), _p(scratch), int(mask_relu),
@@ -610,7 +655,7 @@ def gn_bwd_fused_up(x: CL, groups, stats, gamma, dy: CL, colstats: torch.Tensor,
 
 
 def bn_stats(x: CL) -> torch.Tensor:
-    sums = torch.zeros((2, x.c), dtype=torch.float64, device=x.device)
+    sums = zeros((2, x.c), torch.float64, x.device)
     call("b200_bn_stats", x.npos, x.c, x.view(), _p(sums), _stream())
     return sums
 
@@ -634,7 +679,7 @@ def bn_bwd(x: CL, dy: CL, relu_out: Optional[CL], mean, rstd, gamma, out: Option
         red = torch.empty((2, x.c), dtype=torch.float32, device=x.device)
         call("b200_bn_bwd_red_from_sums", x.n, x.c, _p(colstats), _p(mean), _p(rstd), _p(red), _stream())
     else:
-        red = torch.zeros((2, x.c), dtype=torch.float32, device=x.device)
+        red = zeros((2, x.c), torch.float32, x.device)
         call("b200_bn_bwd_reduce", x.npos, x.c, x.view(), dy.view(), rv, _p(mean), _p(rstd), _p(red),
              _stream())
     # frozen statistics (eval-mode BN): the batch-mean / batch-variance terms vanish
@@ -661,8 +706,8 @@ def head_bwd(x: CL, w: torch.Tensor, dlogits: torch.Tensor, need_dx: bool = True
     w2 = w.detach().reshape(c_out, -1).contiguous().float()
     dlogits = dlogits.contiguous().float()
     dx = x.new_like() if need_dx else None
-    dw = torch.zeros((c_out, x.c), dtype=torch.float32, device=x.device)
-    db = torch.zeros(c_out, dtype=torch.float32, device=x.device)
+    dw = zeros((c_out, x.c), torch.float32, x.device)
+    db = zeros(c_out, torch.float32, x.device)
     call("b200_head_bwd", x.n, x.spatial, x.c, c_out, x.view(), _p(w2), _p(dlogits),
          _NULL_VIEW if dx is None else dx.view(), _p(dw), _p(db), int(mask_relu), _stream())
     return dx, dw.reshape(w.shape), db
@@ -675,14 +720,14 @@ def seg_sums(logits: torch.Tensor, target: torch.Tensor, normalization: int = 0)
     spatial = logits[0, 0].numel()
     logits = logits.contiguous().float()
     target = target.contiguous().float()
-    sums = torch.zeros((c, 6), dtype=torch.float64, device=logits.device)
+    sums = zeros((c, 6), torch.float64, logits.device)
     call("b200_seg_sums", n, c, spatial, _p(logits), _p(target), normalization, _p(sums), _stream())
     return sums
 
 
 def se_channel_means(y: CL) -> torch.Tensor:
     """(n, c) fp32 per-sample channel means of y (the squeeze of cSE, se.py:46)."""
-    sums = torch.zeros((y.n, y.c), dtype=torch.float64, device=y.device)
+    sums = zeros((y.n, y.c), torch.float64, y.device)
     call("b200_se_channel_sums", y.n, y.spatial, y.c, y.view(), _p(sums), _stream())
     return (sums / float(y.spatial)).float()
 
@@ -695,7 +740,7 @@ def se_gate_fwd(y: CL, a: torch.Tensor, s: torch.Tensor) -> CL:
 
 
 def se_gate_bwd_reduce(y: CL, a: torch.Tensor, s: torch.Tensor, g: CL):
-    da = torch.zeros((y.n, y.c), dtype=torch.float64, device=y.device)
+    da = zeros((y.n, y.c), torch.float64, y.device)
     ds = torch.empty_like(s)
     call("b200_se_gate_bwd_reduce", y.n, y.spatial, y.c, y.view(), _p(a), _p(s), g.view(), _p(da), _p(ds), _stream())
     return da.float(), ds
@@ -792,7 +837,7 @@ def ce_fwd(logits: torch.Tensor, labels: torch.Tensor) -> torch.Tensor:
     spatial = logits[0, 0].numel()
     logits = logits.contiguous().float()
     labels = labels.contiguous().long()
-    s = torch.zeros(3, dtype=torch.float64, device=logits.device)   # sum nll, valid positions, bad labels
+    s = zeros(3, torch.float64, logits.device)   # sum nll, valid positions, bad labels
     call("b200_ce_fwd", n, c, spatial, _p(logits), _p(labels), _p(s), _stream())
     return s
 
@@ -812,7 +857,7 @@ def ce_bwd(logits: torch.Tensor, labels: torch.Tensor, scale: torch.Tensor) -> t
 def metric_prob_sum(logits: torch.Tensor) -> torch.Tensor:
     require_cuda(logits)
     logits = logits.contiguous().float()
-    s = torch.zeros(1, dtype=torch.float64, device=logits.device)
+    s = zeros(1, torch.float64, logits.device)
     call("b200_metric_prob_sum", logits.numel(), _p(logits), _p(s), _stream())
     return s
 
@@ -824,7 +869,7 @@ def metric_counts(logits: torch.Tensor, labels: torch.Tensor, thr: torch.Tensor,
     logits = logits.contiguous().float()
     labels = labels.contiguous().float()
     per = logits[0].numel()
-    counts = torch.zeros((n, 3), dtype=torch.float64, device=logits.device)
+    counts = zeros((n, 3), torch.float64, logits.device)
     call("b200_metric_counts", n, per, _p(logits), _p(labels), _p(thr.contiguous().float()), mode,
          _p(counts), _stream())
     return counts
@@ -836,6 +881,6 @@ def metric_argmax_counts(x: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
     spatial = x[0, 0].numel()
     x = x.contiguous().float()
     target = target.contiguous().float()
-    counts = torch.zeros((n, c, 2), dtype=torch.float64, device=x.device)
+    counts = zeros((n, c, 2), torch.float64, x.device)
     call("b200_metric_argmax_counts", n, c, spatial, _p(x), _p(target), _p(counts), _stream())
     return counts
