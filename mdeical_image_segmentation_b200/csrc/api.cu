@@ -15,6 +15,8 @@ extern thread_local int g_wgrad_wide;
 extern thread_local int g_halo_bn;
 extern thread_local int g_wgrad_d3;
 extern thread_local int g_wgrad_d3_epi;
+extern thread_local int g_roll_mode;
+extern thread_local int g_roll_seg;
 int direct_gemm_conv(const TcGemmProblem& p, cudaStream_t stream);
 int direct_wgrad(const TcWgradProblem& p, cudaStream_t stream);
 static thread_local int g_last_impl = 0;
@@ -199,6 +201,8 @@ int b200_set_tuning(int key, int value) {
   if (key == 7) { b200::g_halo_bn = value; return B200_OK; }
   if (key == 8) { b200::g_wgrad_d3 = value; return B200_OK; }
   if (key == 9) { b200::g_wgrad_d3_epi = value; return B200_OK; }
+  if (key == 10) { b200::g_roll_mode = value; return B200_OK; }
+  if (key == 11) { b200::g_roll_seg = value; return B200_OK; }
   return B200_ERR_BAD_ARG;
 }
 

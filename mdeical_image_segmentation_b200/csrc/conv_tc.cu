@@ -15,6 +15,7 @@
 #include "conv_tc.cuh"
 
 #include "tmap.cuh"
+#include <type_traits>
 
 namespace b200 {
 
@@ -918,6 +919,371 @@ __global__ void __launch_bounds__(384, 1)
   if (warp == 2) tmem_dealloc(tmem_base, tmem_cols);
 }
 
+// ===================================================================== depth-rolling forward / dgrad (N = 3 C_out)
+// ncu on the halo kernel above for a C_out = 64 layer (192 -> 64 @ 128^3, profiles/r02_fwd_192_64_ncu.txt): the
+// tensor pipe is 73 % busy while l1tex__data_pipe_tc_wavefronts_mem_shared runs at 90 % of its peak.  An M = 128,
+// N = 64, K = 16 MMA has 32 cycles of math but fetches 4 KB of A + 2 KB of B from shared memory — 48 wavefronts of
+// 128 B at one per cycle — so every N = 64 MMA is operand-fetch bound at 2/3 of the pipe, whatever the schedule.
+// The fetch per FLOP only falls with a wider N, and a 3-D convolution has one to offer: the input plane z feeds
+// THREE output planes, z+1, z and z-1, through the depth taps kd = 0, 1, 2.  This kernel walks a column of
+// (16 R x 8) positions along the depth axis: every input halo plane is loaded once and multiplied, tap by tap,
+// with the three depth slabs [kd=2 | kd=1 | kd=0] of the filter at once (N = 3 C_out = 192: 80 wavefronts for 96
+// cycles of math, math-bound), accumulating into the TMEM accumulators of the three output planes it touches.
+// The accumulators form a ring of S = 4 plane slots x R row-blocks (R S C_out = 512 columns = all of TMEM); a
+// plane is complete — and handed to the epilogue warps — as soon as the input plane after it has been consumed,
+// and its slot is recycled for the plane S further on.  A fresh accumulator is opened by splitting the first
+// K step of an input plane into per-plane MMAs (accumulate = 0 on the new plane only); everything else is one
+// MMA per (row-block, K step).  Activation traffic falls 3x (one halo plane per output plane instead of three).
+struct RollArgs {
+  int pn, pd, ph, pw;
+  int tiles_h, tiles_w, nseg, segL, total;
+  int kchunks, kdim, BN;
+  int R, S;              // row-blocks per tile, accumulator slots (R * S * BN <= 512)
+  int halo_h;            // 16 R + 2
+  int a_stage_bytes, a_stages, b_slots;
+  int b_resident;        // all 27 x kchunks filter slabs stay in shared memory (loaded once per CTA)
+  EpiArgs e;
+};
+
+struct RollItem {
+  int n, z0, Lw, h0, w0;
+};
+__device__ __forceinline__ RollItem roll_decode(const RollArgs& p, int work) {
+  RollItem it;
+  const int tw = work % p.tiles_w; work /= p.tiles_w;
+  const int th = work % p.tiles_h; work /= p.tiles_h;
+  const int seg = work % p.nseg; work /= p.nseg;
+  it.n = work;
+  it.z0 = seg * p.segL;
+  it.Lw = p.pd - it.z0 < p.segL ? p.pd - it.z0 : p.segL;
+  it.h0 = th * 16 * p.R;
+  it.w0 = tw * 8;
+  return it;
+}
+
+template <bool MASK, int STATS>
+__global__ void __launch_bounds__(384, 1)
+    tc_gemm_roll_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                        const RollArgs p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t sraw = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (sraw & 1023u)) & 1023u);
+  uint64_t* afull = reinterpret_cast<uint64_t*>(smem);
+  uint64_t* aempty = afull + 8;
+  uint64_t* bfull = aempty + 8;
+  uint64_t* bempty = bfull + 16;
+  uint64_t* tfull = bempty + 16;
+  uint64_t* tempty = tfull + 8;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 8);
+  uint8_t* sA = smem + epi_ctrl_bytes(p.e.epi_warps);
+  uint8_t* sB = sA + (size_t)p.a_stages * p.a_stage_bytes;
+  const int BN = p.BN, R = p.R, S = p.S;
+  const int tap_bytes = BN * 128;
+  const int b_bytes = 3 * tap_bytes;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < p.a_stages; ++s) { mbar_init(&afull[s], 1); mbar_init(&aempty[s], 1); }
+    for (int s = 0; s < p.b_slots; ++s) { mbar_init(&bfull[s], 1); mbar_init(&bempty[s], 1); }
+    for (int a = 0; a < S; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 32 * p.e.epi_warps); }
+    fence_barrier_init();
+  }
+  uint32_t tmem_cols = 32;
+  while (tmem_cols < (uint32_t)(R * S * BN)) tmem_cols <<= 1;
+  if (warp == 2) tmem_alloc(tmem_slot, tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ---------------------------------------------------------------- A (halo plane) producer
+    int stage = 0;
+    uint32_t phase = 0;
+    const uint32_t plane_bytes = (uint32_t)(kHaloW * p.halo_h * 128);
+    for (int work = blockIdx.x; work < p.total; work += gridDim.x) {
+      const RollItem it = roll_decode(p, work);
+      const int zb = it.z0 > 0 ? it.z0 - 1 : 0;
+      const int ze = it.z0 + it.Lw < p.pd ? it.z0 + it.Lw : p.pd - 1;
+      for (int z = zb; z <= ze; ++z)
+        for (int kc = 0; kc < p.kchunks; ++kc) {
+          mbar_wait(&aempty[stage], phase ^ 1);
+          if (elect_one()) {
+            mbar_arrive_expect_tx(&afull[stage], plane_bytes);
+            tma_load_5d(sA + (size_t)stage * p.a_stage_bytes, &tmA, &afull[stage], kc * 64, it.w0 - 1, it.h0 - 1, z,
+                        it.n);
+          }
+          __syncwarp();
+          if (++stage == p.a_stages) { stage = 0; phase ^= 1; }
+        }
+    }
+  } else if (warp == 3) {
+    // ---------------------------------------------------------------- B producer: slabs [kd=2 | kd=1 | kd=0] of (kh, kw)
+    int slot = 0;
+    uint32_t phase = 0;
+    if (p.b_resident) {
+      // slot (kc, g) holds its three depth slabs for the whole kernel
+      if ((int)blockIdx.x < p.total && elect_one()) {
+        for (int kc = 0; kc < p.kchunks; ++kc)
+          for (int g = 0; g < 9; ++g) {
+            const int sl = kc * 9 + g;
+            uint8_t* dst = sB + (size_t)sl * b_bytes;
+            mbar_arrive_expect_tx(&bfull[sl], (uint32_t)b_bytes);
+#pragma unroll
+            for (int j = 0; j < 3; ++j)
+              tma_load_3d(dst + j * tap_bytes, &tmB, &bfull[sl], kc * 64, 0, (2 - j) * 9 + g);
+          }
+      }
+      __syncwarp();
+    }
+    for (int work = blockIdx.x; work < p.total && !p.b_resident; work += gridDim.x) {
+      const RollItem it = roll_decode(p, work);
+      const int zb = it.z0 > 0 ? it.z0 - 1 : 0;
+      const int ze = it.z0 + it.Lw < p.pd ? it.z0 + it.Lw : p.pd - 1;
+      for (int z = zb; z <= ze; ++z)
+        for (int kc = 0; kc < p.kchunks; ++kc)
+          for (int g = 0; g < 9; ++g) {
+            mbar_wait(&bempty[slot], phase ^ 1);
+            if (elect_one()) {
+              uint8_t* dst = sB + (size_t)slot * b_bytes;
+              mbar_arrive_expect_tx(&bfull[slot], (uint32_t)b_bytes);
+#pragma unroll
+              for (int j = 0; j < 3; ++j)   // position j holds depth tap kd = 2 - j  <->  output plane z - 1 + j
+                tma_load_3d(dst + j * tap_bytes, &tmB, &bfull[slot], kc * 64, 0, (2 - j) * 9 + g);
+            }
+            __syncwarp();
+            if (++slot == p.b_slots) { slot = 0; phase ^= 1; }
+          }
+    }
+  } else if (warp == 1) {
+    // ---------------------------------------------------------------- MMA issuer
+    const uint32_t sA_addr = smem_u32(sA), sB_addr = smem_u32(sB);
+    const uint32_t idesc1 = make_idesc_bf16(128, BN, 0, 0), idesc2 = make_idesc_bf16(128, 2 * BN, 0, 0),
+                   idesc3 = make_idesc_bf16(128, 3 * BN, 0, 0);
+    const uint64_t adesc0 = make_smem_desc_sw128(0, 16, kHaloW * 128);
+    const uint64_t bdesc0 = make_smem_desc_sw128(0, 16, 1024);
+    int stage = 0, slot = 0;
+    uint32_t aphase = 0, bphase = 0;
+    const bool resident = p.b_resident != 0;
+    bool b_loaded = false;  // resident filters: the full barriers are waited for once
+    long gi_base = 0;      // output planes this CTA has opened so far: plane index -> accumulator slot and parity
+    for (int work = blockIdx.x; work < p.total; work += gridDim.x) {
+      const RollItem it = roll_decode(p, work);
+      const int zb = it.z0 > 0 ? it.z0 - 1 : 0;
+      const int ze = it.z0 + it.Lw < p.pd ? it.z0 + it.Lw : p.pd - 1;
+      const int p_last = it.z0 + it.Lw - 1;
+      for (int z = zb; z <= ze; ++z) {
+        const int p_lo = z - 1 > it.z0 ? z - 1 : it.z0;
+        const int p_hi = z + 1 < p_last ? z + 1 : p_last;
+        const int cnt = p_hi - p_lo + 1;                  // 1..3 output planes fed by this input plane
+        const int bpos = p_lo - (z - 1);                  // first filter slab position used
+        // planes that receive their first contribution now: z + 1, and plane 0 at z = 0
+        for (int pp = p_lo; pp <= p_hi; ++pp) {
+          const int zfirst = pp > 0 ? pp - 1 : 0;
+          if (zfirst == z) {
+            const long gi = gi_base + (pp - it.z0);
+            mbar_wait(&tempty[gi % S], (uint32_t)(((gi / S) & 1) ^ 1));
+          }
+        }
+        tc_fence_after();
+        const long gi_lo = gi_base + (p_lo - it.z0);
+        const int s_lo = (int)(gi_lo % S);
+        const int cnt1 = s_lo + cnt <= S ? cnt : S - s_lo;      // planes before the ring wraps
+        const uint32_t tc_a = (uint32_t)(s_lo * BN);
+        const uint32_t id_a = cnt1 == 3 ? idesc3 : (cnt1 == 2 ? idesc2 : idesc1);
+        const bool two = cnt1 < cnt;
+        const uint32_t id_b = cnt - cnt1 == 2 ? idesc2 : idesc1;
+        const uint64_t boff_b = (uint64_t)((cnt1 * tap_bytes) >> 4);
+        bool first_iter = true;
+        for (int kc = 0; kc < p.kchunks; ++kc) {
+          int nk = (p.kdim - kc * 64 + 15) >> 4;
+          nk = nk > 4 ? 4 : nk;
+          mbar_wait(&afull[stage], aphase);
+          tc_fence_after();
+          const uint64_t da0 = adesc0 + (uint64_t)((sA_addr + (uint32_t)stage * (uint32_t)p.a_stage_bytes) >> 4);
+          // the in-plane taps, fully unrolled: every descriptor is base + compile-time constant and the R x nk MMAs
+          // of a tap go out back to back (the run-time version of this loop spent longer issuing than the tensor
+          // pipe needs to execute: 755 -> TF/s, profiles/r02_roll_tune.txt)
+          auto issue_plane = [&](auto nk_tag) {
+            constexpr int NKC = decltype(nk_tag)::value;
+            const int nkk = NKC > 0 ? NKC : nk;
+#pragma unroll
+            for (int g = 0; g < 9; ++g) {
+              const int khi = g / 3, kwi = g - khi * 3;
+              const int bsl = resident ? kc * 9 + g : slot;
+              if (!resident || !b_loaded) {
+                mbar_wait(&bfull[bsl], resident ? 0u : bphase);
+                tc_fence_after();
+              }
+              if (elect_one()) {
+                const uint64_t db0 = bdesc0 + (uint64_t)((sB_addr + (uint32_t)bsl * (uint32_t)b_bytes +
+                                                          (uint32_t)bpos * (uint32_t)tap_bytes) >> 4);
+#pragma unroll
+                for (int r = 0; r < 2; ++r) {
+                  if (r >= R) break;
+                  const uint64_t da = da0 + (uint64_t)((((r * 16 + khi) * kHaloW + kwi) * 128) >> 4);
+                  const uint32_t tcol = tmem_base + (uint32_t)(r * S * BN);
+                  if (first_iter) {
+                    // open / continue every plane separately: only a fresh plane starts from zero
+                    for (int j = 0; j < cnt; ++j) {
+                      const int pp = p_lo + j;
+                      const int zfirst = pp > 0 ? pp - 1 : 0;
+                      umma_bf16(tcol + (uint32_t)(((s_lo + j) % S) * BN), da, db0 + (uint64_t)((j * tap_bytes) >> 4),
+                                idesc1, zfirst == z ? 0u : 1u);
+                    }
+                  } else {
+                    umma_bf16(tcol + tc_a, da, db0, id_a, 1u);
+                    if (two) umma_bf16(tcol, da, db0 + boff_b, id_b, 1u);
+                  }
+#pragma unroll
+                  for (int k = 1; k < 4; ++k) {
+                    if (k >= nkk) break;
+                    umma_bf16(tcol + tc_a, da + (uint64_t)(2 * k), db0 + (uint64_t)(2 * k), id_a, 1u);
+                    if (two) umma_bf16(tcol, da + (uint64_t)(2 * k), db0 + boff_b + (uint64_t)(2 * k), id_b, 1u);
+                  }
+                }
+                if (!resident) umma_commit(&bempty[slot]);
+                if (g == 8) umma_commit(&aempty[stage]);
+              }
+              __syncwarp();
+              first_iter = false;
+              if (!resident && ++slot == p.b_slots) { slot = 0; bphase ^= 1; }
+            }
+          };
+          if (nk == 4) issue_plane(std::integral_constant<int, 4>{});
+          else issue_plane(std::integral_constant<int, 0>{});
+          if (resident && kc == p.kchunks - 1) b_loaded = true;
+          if (++stage == p.a_stages) { stage = 0; aphase ^= 1; }
+        }
+        // planes whose last contribution this was: z - 1, and the volume's last plane at z = pd - 1
+        if (elect_one()) {
+          if (z - 1 >= it.z0 && z - 1 <= p_last) umma_commit(&tfull[(gi_base + (z - 1 - it.z0)) % S]);
+          if (z == p.pd - 1 && z <= p_last) umma_commit(&tfull[(gi_base + (z - it.z0)) % S]);
+        }
+        __syncwarp();
+      }
+      gi_base += it.Lw;
+    }
+  } else if (warp >= 4 && warp < 4 + p.e.epi_warps) {
+    // ---------------------------------------------------------------- epilogue (see epi_chunk)
+    const int ew = warp - 4, q = ew & 3, grp = ew >> 2, ngrp = p.e.epi_warps >> 2;
+    const int tid = threadIdx.x - 128, nthr = 32 * p.e.epi_warps, rsub = lane >> 2;
+    uint8_t* stg = smem + 1024 + ew * kEpiStageBytes;
+    float* colsum = reinterpret_cast<float*>(smem + 1024 + p.e.epi_warps * kEpiStageBytes);
+    const EpiArgs& e = p.e;
+    constexpr bool kStats = STATS != EPI_STATS_NONE;
+    constexpr bool kAux = MASK || STATS == EPI_STATS_DOT;
+    const int pw = p.pw, ph = p.ph;
+    const long out_ctot = e.out_ctot, out_coff = e.out_coff;
+    const long row_elems = (long)pw * out_ctot;
+    const long mrow_elems = (long)pw * e.mask_ctot, drow_elems = (long)pw * e.dot_ctot;
+    if (kStats) {
+      for (int i = tid; i < 2 * BN; i += nthr) colsum[i] = 0.f;
+      epi_bar(nthr);
+    }
+    int cur_n = -1;
+    float sacc[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) sacc[k] = 0.f;
+    const int nchunks = (BN + 31) / 32;
+    const int items = nchunks * R;       // item = chunk * R + row-block
+    long gi_base = 0;
+    for (int work = blockIdx.x; work < p.total; work += gridDim.x) {
+      const RollItem it = roll_decode(p, work);
+      if (kStats && it.n != cur_n) {
+        if (cur_n >= 0) epi_flush_colsum(e, colsum, BN, cur_n, 0, tid, nthr);
+        cur_n = it.n;
+      }
+      const int wx = it.w0 + rsub;
+      const int hy0 = it.h0 + q * 4;
+      for (int pl = 0; pl < it.Lw; ++pl) {
+        const int zp = it.z0 + pl;
+        const long gi = gi_base + pl;
+        const int sl = (int)(gi % S);
+        if (kAux && pl + 1 < it.Lw) {
+          // pull the NEXT plane's mask / dot lines of this tile into L2 (see the halo kernel)
+          const int nl = (BN * 2 + 127) >> 7;
+          const int nlines = 16 * R * 8 * nl;
+          const long plane2 = ((long)it.n * p.pd + zp + 1) * ph;
+          for (int i = tid; i < nlines; i += nthr) {
+            const int l = i % nl, pp = i / nl;
+            const int w_ = it.w0 + (pp & 7), h_ = it.h0 + (pp >> 3);
+            if (w_ < pw && h_ < ph) {
+              const long pos = (plane2 + h_) * pw + w_;
+              if (MASK) prefetch_l2(e.mask + pos * e.mask_ctot + e.mask_coff + l * 64);
+              if (STATS == EPI_STATS_DOT) prefetch_l2(e.dot + pos * e.dot_ctot + e.dot_coff + l * 64);
+            }
+          }
+        }
+        const long pos0 = (wx < pw) ? (((long)it.n * p.pd + zp) * ph + hy0) * pw + wx : -1;
+        const long off0 = pos0 * out_ctot + out_coff;
+        const long moff0 = pos0 * e.mask_ctot + e.mask_coff, doff0 = pos0 * e.dot_ctot + e.dot_coff;
+        mbar_wait(&tfull[sl], (uint32_t)((gi / S) & 1));
+        tc_fence_after();
+        const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(sl * BN);
+        auto issue = [&](uint32_t (&v)[32], int item) {
+          const int ci = item / R, r = item - ci * R;
+          const uint32_t ta = tbase + (uint32_t)(r * S * BN + ci * 32);
+          tmem_ld16(ta, v);
+          if (BN - ci * 32 > 16) tmem_ld16(ta + 16, v + 16);
+        };
+        auto place = [&](int r, EpiRows& rw) {
+          const int hleft = ph - (hy0 + r * 16);              // rows it < hleft exist
+#pragma unroll
+          for (int i2 = 0; i2 < 4; ++i2) {
+            const bool ok = pos0 >= 0 && i2 < hleft;
+            rw.ooff[i2] = ok ? off0 + (long)(r * 16 + i2) * row_elems : -1;
+            if (MASK) rw.moff[i2] = ok ? moff0 + (long)(r * 16 + i2) * mrow_elems : -1;
+            if (STATS == EPI_STATS_DOT) rw.doff[i2] = ok ? doff0 + (long)(r * 16 + i2) * drow_elems : -1;
+          }
+        };
+        auto prefetch = [&](EpiAux<MASK, STATS>& aux, int item) {
+          if (!kAux) return;
+          const int ci = item / R, r = item - ci * R;
+          EpiRows rw;
+          place(r, rw);
+          epi_prefetch<MASK, STATS>(e, ci * 32, BN - ci * 32 > 16 ? 32 : 16, lane, rw, aux);
+        };
+        auto process = [&](const uint32_t (&v)[32], const EpiAux<MASK, STATS>& aux, int item, int next) {
+          const int ci = item / R, r = item - ci * R;
+          const int c0 = ci * 32;
+          const int ncol = BN - c0 > 16 ? 32 : 16;
+          EpiRows rw;
+          place(r, rw);
+          epi_chunk<MASK, STATS>(e, v, ncol, c0, stg, lane, rw, sacc, aux);
+          if (kStats && (next >= items || next / R != ci)) epi_fold_acc<STATS>(sacc, colsum, c0, ncol, BN, lane);
+        };
+        uint32_t va[32], vb[32];
+        EpiAux<MASK, STATS> xa, xb;
+        if (e.dbg != 2 && grp < items) {
+          issue(va, grp);
+          prefetch(xa, grp);
+          for (int item = grp; item < items; item += 2 * ngrp) {
+            const int i1 = item + ngrp, i2 = i1 + ngrp;
+            tmem_ld_wait();
+            if (i1 < items) { issue(vb, i1); prefetch(xb, i1); }
+            process(va, xa, item, i1);
+            if (i1 < items) {
+              tmem_ld_wait();
+              if (i2 < items) { issue(va, i2); prefetch(xa, i2); }
+              process(vb, xb, i1, i2);
+            }
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(&tempty[sl]);
+      }
+      gi_base += it.Lw;
+    }
+    if (kStats && cur_n >= 0) epi_flush_colsum(e, colsum, BN, cur_n, 0, tid, nthr);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, tmem_cols);
+}
+
 thread_local int g_epi_dbg = 0;
 static EpiArgs make_epi(const TcGemmProblem& p) {
   EpiArgs e{};
@@ -1105,8 +1471,98 @@ static int tc_gemm_halo(const TcGemmProblem& p, cudaStream_t stream) {
                                   128 + 32 * a.e.epi_warps, smem, stream, tmA, tmB, a);
 }
 
+// tuning knob: depth-rolling N = 3 C_out kernel for narrow 3-D layers: 0 = off (default: measured slower than the halo
+// kernel on B200, see roll_eligible), 1 = where the filters fit in shared memory, 2 = every eligible layer
+thread_local int g_roll_mode = 0;
+thread_local int g_roll_seg = 0;    // tuning knob: 0 = heuristic segment length, else planes per segment
+
+// Where the 27 filter slabs fit in shared memory next to two halo stages (K * C_out <= 64 * 32: the first two
+// layers of a 3-D U-Net and their data gradients) the walk streams activations only and runs math-bound.  With
+// streamed filters it is bound by the L2 -> SM path instead — R = 2 row-blocks is all TMEM allows next to four
+// plane slots, so each 24 KB filter slot lasts 768 cycles (37 B/clk per SM; ncu: tensor pipe 56 % busy,
+// profiles/r02_roll_192_64_ncu.txt) and the halo kernel's R = 4 schedule wins (knob 10 = 2 forces the walk).
+static long roll_filter_bytes(const TcGemmProblem& p) {
+  return 27L * ((p.kdim + 63) / 64) * p.ncols * 128;
+}
+static bool roll_eligible(const TcGemmProblem& p) {
+  if (!g_roll_mode || !halo_eligible(p) || p.kd != 3 || p.ncols > 64 || p.ncols % 16 || p.pd < 4 || p.ph < 24)
+    return false;
+  if ((p.kdim + 63) / 64 * 9 > 16) return false;          // barrier slots of the resident mode
+  const long a_stage = (kHaloW * (16 * 2 + 2) * 128 + 1023) / 1024 * 1024;
+  const bool fits = roll_filter_bytes(p) + 2 * a_stage + smem_overhead(4) <= kSmemBudget;
+  return fits || g_roll_mode == 2;
+}
+
+static int tc_gemm_roll(const TcGemmProblem& p, cudaStream_t stream) {
+  RollArgs a{};
+  a.pn = p.pn; a.pd = p.pd; a.ph = p.ph; a.pw = p.pw;
+  a.BN = p.ncols;
+  a.kdim = p.kdim; a.kchunks = (p.kdim + 63) / 64;
+  a.e = make_epi(p);
+  const int kind = stats_kind_of(p);
+  a.e.epi_warps = g_epi_warps == 8 ? 8 : 4;     // a plane's MMAs (>= 6900 cycles) hide a 4-warp epilogue
+  const int kSmemOverhead = smem_overhead(a.e.epi_warps);
+  a.R = 2; a.S = 4;
+  a.halo_h = 16 * a.R + 2;
+  a.tiles_h = (p.ph + 16 * a.R - 1) / (16 * a.R); a.tiles_w = (p.pw + 7) / 8;
+  // segment length: whole waves of the persistent grid, few segments (each re-reads two boundary planes)
+  const long cols = (long)p.pn * a.tiles_h * a.tiles_w;
+  int bestL = p.pd;
+  double best = -1.0;
+  for (int L : {4, 6, 8, 12, 16, 24, 32, 48, 64, 128}) {
+    if (L > p.pd && L != 4) continue;
+    const int LL = L > p.pd ? p.pd : L;
+    const long items = cols * ((p.pd + LL - 1) / LL);
+    const long waves = (items + sm_count() - 1) / sm_count();
+    const double eff = (double)items / (double)(waves * sm_count()) * ((double)LL / (LL + 0.7));
+    if (eff > best) { best = eff; bestL = LL; }
+  }
+  a.segL = g_roll_seg > 0 ? (g_roll_seg < p.pd ? g_roll_seg : p.pd) : bestL;
+  a.nseg = (p.pd + a.segL - 1) / a.segL;
+  a.total = (int)(cols * a.nseg);
+  a.a_stage_bytes = (kHaloW * a.halo_h * 128 + 1023) / 1024 * 1024;
+  const int b_bytes = 3 * a.BN * 128;
+  // a filter slot (three depth slabs of one in-plane tap, 24 KB) lasts R x 4 MMAs = 768 cycles: at ~32 B/clk
+  // the weight stream needs >= 4 slots in flight to cover L2 latency, so the halo planes get two stages only
+  a.a_stages = 2;
+  int rem = kSmemBudget - kSmemOverhead - a.a_stages * a.a_stage_bytes;
+  a.b_resident = roll_filter_bytes(p) <= rem && a.kchunks * 9 <= 16;
+  if (a.b_resident) {
+    a.b_slots = a.kchunks * 9;
+    rem -= a.b_slots * b_bytes;
+    while (a.a_stages < 4 && rem >= a.a_stage_bytes) { ++a.a_stages; rem -= a.a_stage_bytes; }
+  } else {
+    a.b_slots = rem / b_bytes;
+    if (a.b_slots > 12) a.b_slots = 12;
+    if (a.b_slots < 2) return B200_ERR_UNSUPPORTED;
+  }
+
+  CUtensorMap tmA, tmB;
+  {
+    const ActView& v = p.a;
+    uint64_t dims[5] = {(uint64_t)v.c, (uint64_t)v.w, (uint64_t)v.h, (uint64_t)v.d, (uint64_t)v.n};
+    uint64_t str[5] = {1, (uint64_t)v.ctot, (uint64_t)v.w * v.ctot, (uint64_t)v.h * v.w * v.ctot,
+                       (uint64_t)v.d * v.h * v.w * v.ctot};
+    uint32_t box[5] = {64, (uint32_t)kHaloW, (uint32_t)a.halo_h, 1, 1};
+    int rc = make_tmap_bf16(&tmA, v.ptr + v.coff, 5, dims, str, box);
+    if (rc) return rc;
+  }
+  {
+    uint64_t dims[3] = {(uint64_t)p.kdim, (uint64_t)p.ncols, 27};
+    uint64_t str[3] = {1, (uint64_t)p.kdim, (uint64_t)p.kdim * p.ncols};
+    uint32_t box[3] = {64, (uint32_t)a.BN, 1};
+    int rc = make_tmap_bf16(&tmB, p.wp, 3, dims, str, box);
+    if (rc) return rc;
+  }
+  const int smem = a.a_stages * a.a_stage_bytes + a.b_slots * b_bytes + kSmemOverhead;
+  const int grid = a.total < sm_count() ? a.total : sm_count();
+  return launch_variant<RollArgs>(B200_PICK_VARIANT(tc_gemm_roll_kernel, RollArgs), p.mask != nullptr, kind, grid,
+                                  128 + 32 * a.e.epi_warps, smem, stream, tmA, tmB, a);
+}
+
 int tc_gemm_conv(const TcGemmProblem& p, cudaStream_t stream) {
   if (!tc_gemm_supported(p)) return B200_ERR_UNSUPPORTED;
+  if (roll_eligible(p)) return tc_gemm_roll(p, stream);
   if (halo_eligible(p)) return tc_gemm_halo(p, stream);
   GemmArgs a{};
   a.pn = p.pn; a.pd = p.pd; a.ph = p.ph; a.pw = p.pw;

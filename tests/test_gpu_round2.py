@@ -390,8 +390,10 @@ KNOBS = {                      # b200_set_tuning(key, value) lists; () = default
     "narrow_wgrad": ((6, 0), (8, 0)),
     "pair_wgrad": ((8, 0),),           # the tap-pair weight gradient instead of the 3-plane N = 192 kernel
     "per_tap": ((0, 0), (1, 0)),
+    "roll": ((10, 2),),                # the experimental depth-rolling N = 3 C_out kernel (C_out <= 64 layers)
+    "roll_seg5": ((10, 2), (11, 5)),   # ... with ragged depth segments (128 = 25 x 5 + 3)
 }
-DEFAULTS = {0: 1, 1: 1, 2: 4, 3: 1, 4: 0, 5: 0, 6: 1, 7: 0, 8: 1}
+DEFAULTS = {0: 1, 1: 1, 2: 4, 3: 1, 4: 0, 5: 0, 6: 1, 7: 0, 8: 1, 9: 80, 10: 0, 11: 0}
 
 LAYERS = [          # name, n, d, h, w, c_in, c_out  (SURVEY App. A headline shapes; batch cut to bound memory)
     ("3d_192_64_128", 1, 128, 128, 128, 192, 64),

@@ -17,6 +17,8 @@ LAYERS = {   # name: n, d, h, w, cin, cout
     "768_256": (2, 32, 32, 32, 768, 256),
     "256_256": (2, 32, 32, 32, 256, 256),
     "32_64": (2, 128, 128, 128, 32, 64),
+    "16_32": (2, 128, 128, 128, 16, 32),
+    "64_64_64": (2, 64, 64, 64, 64, 64),
     "64_128": (2, 64, 64, 64, 64, 128),
     "256_512": (2, 16, 16, 16, 256, 512),
     "2d_128_64": (16, 1, 512, 512, 128, 64),
@@ -24,7 +26,7 @@ LAYERS = {   # name: n, d, h, w, cin, cout
     "2d_512_256": (16, 1, 128, 128, 512, 256),
     "2d_1024_512": (16, 1, 64, 64, 1024, 512),
 }
-DEFAULTS = {0: 1, 1: 1, 2: 4, 3: 1, 4: 0, 5: 0, 6: 1, 7: 0, 8: 1}
+DEFAULTS = {0: 1, 1: 1, 2: 4, 3: 1, 4: 0, 5: 0, 6: 1, 7: 0, 8: 1, 9: 80, 10: 0, 11: 0}
 lib = _lib.lib()
 
 
