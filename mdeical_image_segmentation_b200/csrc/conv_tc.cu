@@ -2174,6 +2174,158 @@ __global__ void __launch_bounds__(256, 1)
   if (warp == 2) tmem_dealloc(tmem_base, 512);
 }
 
+// ===================================================================================== 2-D weight gradient, N = 192
+// The same widening for 3 x 3 layers without a depth axis: the three dy views are ROW shifts.  Tiles are 16 x 8
+// positions p of the x frame; A = x[p + (0, kw-1)] (tap pair (kw, kw+1) on the M side, as above), B = the dy box
+// of rows h0-1 .. h0+16 read at row offsets j = 0, 1, 2 — atom j = dy[p + (j-1, 0)], 1 KB after atom j-1, so the
+// three atoms overlap in shared memory and the leading-dimension byte offset is one tile row:
+//     D[(kw, ci)][(j, co)] = sum_p x[p + (0, kw-1)][ci] dy[p + (j-1, 0)][co] = dw[co][ci][kh = 2-j][kw].
+// x is zero outside the image, so summing p over the image covers every term; dy rows outside are zero-filled.
+// Two groups: kw pair (0,1) and kw = 2 (second half unused): 2 x 96 cycles per K step for nine taps, math-bound,
+// against 5 x 48 (tap-pair kernel, fetch-bound) or 4 x 64 + the separate centre-tap GEMM (wide variant).
+static const int kR2XBytes = 20480;                    // 16 x 10 positions x 128 B
+static const int kR2YBytes = 18432;                    // 18 x 8 positions x 128 B
+static const int kR2StageBytes = kR2XBytes + kR2YBytes;
+
+__global__ void __launch_bounds__(256, 1)
+    tc_wgrad_r2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmDY,
+                       const WgradD3Args p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t sraw = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (sraw & 1023u)) & 1023u);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem);
+  uint64_t* empty = full + 16;
+  uint64_t* tfull = empty + 16;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tfull + 2);
+  uint8_t* tiles = smem + 1024;
+
+  int w = blockIdx.x;
+  const int cib = w % p.ciblk; w /= p.ciblk;
+  const int cob = w % p.coblk; w /= p.coblk;
+  const int split = w;
+  const int mt_begin = split * p.tiles_per_split;
+  int mt_end = mt_begin + p.tiles_per_split;
+  if (mt_end > p.m_tiles) mt_end = p.m_tiles;
+  const bool do_bias = p.dbias != nullptr && cib == 0;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmX);
+    tma_prefetch_desc(&tmDY);
+    for (int s = 0; s < p.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], do_bias ? 5 : 1); }
+    mbar_init(&tfull[0], 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int mt = mt_begin; mt < mt_end; ++mt) {
+      const TileCoord tc = decode_tile(mt, p.pd, p.tiles_h, p.tiles_w, 0, 4, 3);
+      mbar_wait(&empty[stage], phase ^ 1);
+      if (elect_one()) {
+        uint8_t* sX = tiles + (size_t)stage * kR2StageBytes;
+        uint8_t* sY = sX + kR2XBytes;
+        mbar_arrive_expect_tx(&full[stage], (uint32_t)kR2StageBytes);
+        tma_load_5d(sX, &tmX, &full[stage], cib * 64, tc.w0 - 1, tc.h0, tc.d0, tc.n);       // 10 x 16 positions
+        tma_load_5d(sY, &tmDY, &full[stage], cob * 64, tc.w0, tc.h0 - 1, tc.d0, tc.n);      // 8 x 18 positions
+      }
+      __syncwarp();
+      if (++stage == p.stages) { stage = 0; phase ^= 1; }
+    }
+  } else if (warp == 1) {
+    const uint32_t idesc = make_idesc_bf16(128, 192, 1, 1);
+    int stage = 0;
+    uint32_t phase = 0;
+    bool first = true;
+    for (int mt = mt_begin; mt < mt_end; ++mt) {
+      mbar_wait(&full[stage], phase);
+      tc_fence_after();
+      const uint32_t xaddr = smem_u32(tiles + (size_t)stage * kR2StageBytes);
+      const uint32_t yaddr = xaddr + kR2XBytes;
+      if (elect_one()) {
+        const uint64_t db0 = make_smem_desc_sw128(yaddr, 1024, 1024);            // atoms = dy rows shifted by 0 / 1 / 2
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+          // M halves: kw = 0 | 1, then kw = 2 | 2 (second half dropped)
+          const uint64_t da0 = make_smem_desc_sw128(xaddr + (uint32_t)(g * 2 * 128), g == 0 ? 128u : 0u,
+                                                    kHaloW * 128);
+#pragma unroll
+          for (int j = 0; j < 8; ++j)   // 16 positions = 2 rows of the tile per MMA
+            umma_bf16(tmem_base + g * 192, da0 + (uint64_t)(j * ((2 * kHaloW * 128) >> 4)),
+                      db0 + (uint64_t)(j * (2048 >> 4)), idesc, !(first && j == 0));
+        }
+        umma_commit(&empty[stage]);
+        if (mt == mt_end - 1) umma_commit(&tfull[0]);
+      }
+      __syncwarp();
+      first = false;
+      if (++stage == p.stages) { stage = 0; phase ^= 1; }
+    }
+    if (mt_end <= mt_begin && elect_one()) umma_commit(&tfull[0]);
+  } else if (warp >= 4) {
+    const int q = warp - 4;
+    if (do_bias) {
+      // warp q sums positions [32 q, 32 q + 32) of the tile's own 16 rows (box rows 1..16): each position once
+      float bs0 = 0.f, bs1 = 0.f;
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int mt = mt_begin; mt < mt_end; ++mt) {
+        mbar_wait(&full[stage], phase);
+        const uint8_t* sY = tiles + (size_t)stage * kR2StageBytes + kR2XBytes + 1024;
+#pragma unroll 8
+        for (int r = 0; r < 32; ++r) {
+          const int row = q * 32 + r;
+          const uint32_t v = *reinterpret_cast<const uint32_t*>(
+              sY + row * 128 + ((((lane >> 2) ^ (row & 7))) << 4) + ((lane & 3) << 2));
+          const float2 f = unpack_bf16x2(v);
+          bs0 += f.x;
+          bs1 += f.y;
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[stage]);
+        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+      }
+      const int co = cob * 64 + 2 * lane;
+      if (co < p.cout) atomicAdd(p.dbias + co, bs0);
+      if (co + 1 < p.cout) atomicAdd(p.dbias + co + 1, bs1);
+    }
+    const int m = q * 32 + lane;           // 0..127: (tap half, ci)
+    const int half = m >> 6;
+    const int ci = cib * 64 + (m & 63);
+    mbar_wait(&tfull[0], 0);
+    tc_fence_after();
+    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+    for (int g = 0; g < 2; ++g) {
+      const int kwi = g == 0 ? half : 2;
+      const bool ok = !(g == 1 && half == 1) && ci < p.cin && mt_end > mt_begin;
+      for (int jb = 0; jb < 3; ++jb) {
+        const long base = (long)ci * p.s_ci + ((2 - jb) * 3 + kwi);     // dy row shift jb - 1  <->  kh = 2 - jb
+        for (int c0 = 0; c0 < 64; c0 += 16) {
+          uint32_t v[16];
+          tmem_ld16(taddr + g * 192 + jb * 64 + c0, v);
+          tmem_ld_wait();
+          if (ok) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const int co = cob * 64 + c0 + j;
+              if (co < p.cout) atomicAdd(p.dw + (long)co * p.s_co + base, __uint_as_float(v[j]));
+            }
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, 512);
+}
+
 thread_local int g_wgrad_d3 = 1;   // tuning knob: N = 192 three-plane weight gradient for 3-D layers
 thread_local int g_wgrad_d3_epi = 80;   // tuning knob: epilogue cost (65 k fp32 reductions per CTA) in tile times
 
@@ -2266,6 +2418,54 @@ static bool wgrad_d3_eligible(const TcWgradProblem& p) {
          p.kw == 3 && p.ph >= 12 && p.pw >= 8 && p.pd >= 2 && p.mop.c >= 48;
 }
 
+static bool wgrad_r2_eligible(const TcWgradProblem& p) {
+  return g_wgrad_d3 && g_wgrad_halo_mode && !p.table && p.tap_mode == TC_TAP_SHIFT && p.kd == 1 && p.kh == 3 &&
+         p.kw == 3 && p.ph >= 12 && p.pw >= 8 && p.mop.c >= 48;
+}
+
+static int tc_wgrad_r2(const TcWgradProblem& p, cudaStream_t stream) {
+  WgradD3Args a{};
+  a.pn = p.pn; a.pd = p.pd; a.ph = p.ph; a.pw = p.pw;
+  a.tiles_h = (p.ph + 15) / 16; a.tiles_w = (p.pw + 7) / 8;
+  a.m_tiles = p.pn * p.pd * a.tiles_h * a.tiles_w;
+  a.cin = p.nop.c; a.cout = p.mop.c;
+  a.ciblk = (a.cin + 63) / 64; a.coblk = (a.cout + 63) / 64;
+  a.stages = (kSmemBudget - 2048) / kR2StageBytes;
+  if (a.stages > 6) a.stages = 6;
+  const long base_ctas = (long)a.ciblk * a.coblk;
+  const long want = pick_splits(base_ctas, a.m_tiles, sm_count(), (double)g_wgrad_d3_epi * 0.75);
+  a.tiles_per_split = (int)((a.m_tiles + want - 1) / want);
+  a.splits = (a.m_tiles + a.tiles_per_split - 1) / a.tiles_per_split;
+  a.dw = p.dw; a.s_co = p.s_m; a.s_ci = p.s_n;
+  a.dbias = p.dbias;
+  CUtensorMap tmX, tmDY;
+  {
+    const ActView& v = p.nop;
+    uint64_t dims[5] = {(uint64_t)v.c, (uint64_t)v.w, (uint64_t)v.h, (uint64_t)v.d, (uint64_t)v.n};
+    uint64_t str[5] = {1, (uint64_t)v.ctot, (uint64_t)v.w * v.ctot, (uint64_t)v.h * v.w * v.ctot,
+                       (uint64_t)v.d * v.h * v.w * v.ctot};
+    uint32_t box[5] = {64, (uint32_t)kHaloW, 16, 1, 1};
+    int rc = make_tmap_bf16(&tmX, v.ptr + v.coff, 5, dims, str, box);
+    if (rc) return rc;
+  }
+  {
+    const ActView& v = p.mop;
+    uint64_t dims[5] = {(uint64_t)v.c, (uint64_t)v.w, (uint64_t)v.h, (uint64_t)v.d, (uint64_t)v.n};
+    uint64_t str[5] = {1, (uint64_t)v.ctot, (uint64_t)v.w * v.ctot, (uint64_t)v.h * v.w * v.ctot,
+                       (uint64_t)v.d * v.h * v.w * v.ctot};
+    uint32_t box[5] = {64, 8, 18, 1, 1};
+    int rc = make_tmap_bf16(&tmDY, v.ptr + v.coff, 5, dims, str, box);
+    if (rc) return rc;
+  }
+  const int smem = a.stages * kR2StageBytes + 2048;
+  cudaError_t e = ensure_dynamic_smem((const void*)tc_wgrad_r2_kernel, kSmemBudget);
+  if (e != cudaSuccess) return (int)e;
+  const long grid = base_ctas * a.splits;
+  tc_wgrad_r2_kernel<<<(unsigned)grid, 256, smem, stream>>>(tmX, tmDY, a);
+  B200_LAUNCH_CHECK();
+  return B200_OK;
+}
+
 static int tc_wgrad_d3(const TcWgradProblem& p, cudaStream_t stream) {
   // conv: mop = dy (c_out), nop = x (c_in); dw index = co * s_m + ci * s_n + tap
   WgradD3Args a{};
@@ -2326,6 +2526,7 @@ bool tc_wgrad_fuses_bias(const TcWgradProblem& p) {
 int tc_wgrad(const TcWgradProblem& p, cudaStream_t stream) {
   if (!tc_wgrad_supported(p)) return B200_ERR_UNSUPPORTED;
   if (wgrad_d3_eligible(p)) return tc_wgrad_d3(p, stream);
+  if (wgrad_r2_eligible(p)) return tc_wgrad_r2(p, stream);
   if (wgrad_halo_eligible(p)) return tc_wgrad_halo(p, stream);
   return tc_wgrad_generic(p, stream, false);
 }
