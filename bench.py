@@ -230,9 +230,10 @@ def conv_flops(name, args, real_cin=None):
 class KernelProfiler:
     """Per-call CUDA-event timing on the launching stream for one instrumented step."""
 
-    def __init__(self, real_cin=None):
+    def __init__(self, real_cin=None, steps=1):
         self.records = []
         self.real_cin = real_cin
+        self.steps = steps          # instrumented steps recorded: families are averaged over them
 
     @contextlib.contextmanager
     def hook(self, name, args):
@@ -263,9 +264,11 @@ class KernelProfiler:
             else:
                 key = name.replace("b200_", "")
             f = fam.setdefault(key, dict(ms=0.0, flops=0.0, launches=0))
-            f["ms"] += ms
-            f["flops"] += fl
-            f["launches"] += 1
+            f["ms"] += ms / self.steps
+            f["flops"] += fl / self.steps
+            f["launches"] += 1.0 / self.steps
+        for f in fam.values():
+            f["launches"] = int(round(f["launches"]))
         return fam
 
 
@@ -383,16 +386,17 @@ def measure(args, name, w, steps, warmup, device, world, rank, full):
         res["e2e"] = {"value": world * batch / (ems.item() / steps / 1e3), "unit": w["unit"],
                       "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4}
 
-    # ---- roofline: one instrumented step with per-call CUDA events on the launching stream.
+    # ---- roofline: three instrumented steps (averaged) with per-call CUDA events on the launching stream.
     # Every rank runs it (its backward contains the gradient all-reduce, so a rank-0-only step would wait
     # for peers forever); only rank 0 records and reports.  Per-kernel times must not include the contention
     # of the overlapped weight-gradient stream: the instrumented step runs single-stream.
-    prof = KernelProfiler(real_cin=w["cin"])
+    prof = KernelProfiler(real_cin=w["cin"], steps=3)
     if rank == 0:
         _lib.profile_hook = prof.hook
     side_was = _engine.WGRAD_STREAM
     _engine.WGRAD_STREAM = False
-    one_step(x, y)
+    for _ in range(prof.steps):
+        one_step(x, y)
     _engine.WGRAD_STREAM = side_was
     _lib.profile_hook = None
     barrier()
