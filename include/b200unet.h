@@ -184,6 +184,29 @@ int b200_bilinear2d_fwd(int32_t n, int32_t ih, int32_t iw, int32_t c, int32_t sc
                         b200_view y, b200_stream_t stream);
 int b200_bilinear2d_bwd(int32_t n, int32_t ih, int32_t iw, int32_t c, int32_t scale, b200_view dy,
                         b200_view add, b200_view dx, void* scratch, b200_stream_t stream);
+/* ---- GPU-side volume augmentation ------------------------------------
+ * replaces the numpy / scipy bodies of augment/unet3d_augment/transforms.py on dense fp32 (C, D, H, W)
+ * device tensors; the random decisions stay with the caller's np.random.RandomState.
+ * flip_rot90: np.flip along D / H / W (flip_bits 1 / 2 / 4; RandomFlip :25-50) followed by
+ *   np.rot90(m, rot_k, axes=(1, 2)) (RandomRotate90 :53-80); dst is (C, D, W, H) for odd rot_k. */
+int b200_aug_flip_rot90(int32_t c, int32_t d, int32_t h, int32_t w, int32_t flip_bits, int32_t rot_k,
+                        const float* src, float* dst, b200_stream_t stream);
+/* dst = clip(a[ch] * src + b[ch], lo, hi) (+-inf = no clip): RandomContrast :115-135, Standardize :495-523,
+ * Normalize :547-605 once their scalars are folded; in place allowed. */
+int b200_aug_affine_clip(int32_t c, int64_t per_channel, const float* src, const float* a, const float* b,
+                         float lo, float hi, float* dst, b200_stream_t stream);
+/* stats fp64 [c][4] accumulated into: sum, sum of squares, min, max (caller initialises 0, 0, +inf, -inf):
+ * np.mean / np.std / np.min / np.max of Standardize and Normalize. */
+int b200_aug_channel_stats(int32_t c, int64_t per_channel, const float* src, double* stats, b200_stream_t stream);
+/* one axis of scipy.ndimage.gaussian_filter(x, sigma, mode='reflect') (truncate 4.0) over an (n0, n1, n2) field:
+ * ElasticDeformation's displacement smoothing :165-175. */
+int b200_aug_gaussian_axis(int32_t n0, int32_t n1, int32_t n2, int32_t axis, float sigma, const float* src,
+                           float* dst, b200_stream_t stream);
+/* scipy.ndimage.map_coordinates(src[ch], (z + dz, y + dy, x + dx), order = 0 | 1, mode='reflect') for every
+ * channel (:178-190); dz may be NULL (apply_3d = False). */
+int b200_aug_map_coordinates(int32_t c, int32_t d, int32_t h, int32_t w, const float* src, const float* dz,
+                             const float* dy, const float* dx, int32_t order, float* dst, b200_stream_t stream);
+
 /* ---- layer_order letters 'l' / 'e' / 'd' / 'D' and avg-pool encoders ----------------------------
  * replaces nn.LeakyReLU / nn.ELU (buildingblocks.py:55-59; ResNetBlock's non_linearity :306-311, applied to
  * out + residual :319-323), nn.Dropout / nn.Dropout2d (:104-107) and nn.AvgPool2d/3d (:414-418).

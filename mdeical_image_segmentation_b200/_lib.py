@@ -83,6 +83,11 @@ SIGNATURES = {
     "b200_bilinear2d_fwd": [_I, _I, _I, _I, _I, View, View, _P],
     "b200_bilinear2d_bwd": [_I, _I, _I, _I, _I, View, View, View, _P, _P],
     "b200_add": [_L, _I, View, View, _P],
+    "b200_aug_flip_rot90": [_I, _I, _I, _I, _I, _I, _P, _P, _P],
+    "b200_aug_affine_clip": [_I, _L, _P, _P, _P, _F, _F, _P, _P],
+    "b200_aug_channel_stats": [_I, _L, _P, _P, _P],
+    "b200_aug_gaussian_axis": [_I, _I, _I, _I, _F, _P, _P, _P],
+    "b200_aug_map_coordinates": [_I, _I, _I, _I, _P, _P, _P, _P, _I, _P, _P],
     "b200_act_fwd": [_L, _I, _I, _F, View, View, View, _P],
     "b200_act_bwd": [_L, _I, _I, _F, View, View, View, _P],
     "b200_scale_mask": [_I, _L, _I, View, _P, _P, _F, View, _P],

@@ -597,3 +597,53 @@ def test_serving_handler_contract(B, tmp_path):
     assert pct["n"] == 2 and pct["p50_ms"] > 0
     app = create_app(svc)
     assert any(getattr(r, "path", None) == "/" for r in app.routes)
+
+
+# ===================================================================================== augmentation
+def test_gpu_augmentations_vs_reference_golden(B):
+    """The device transforms with the reference's class names against outputs of the reference's own classes for the
+    same RandomState seeds: flips / rotations bit-exact, the arithmetic ones to fp32 rounding, the elastic deformation
+    (host-noise mode = the reference's random stream; device Gaussian smoothing + tri-linear / nearest gather) to 1e-4."""
+    from mdeical_image_segmentation_b200 import augment as A
+    aug = load_golden("augment_r2")
+    m4 = torch.from_numpy(aug["m4"]).cuda()
+    m3 = torch.from_numpy(aug["m3"]).cuda()
+    lab = torch.from_numpy(aug["lab"]).cuda()
+    for seed in range(6):
+        assert np.array_equal(A.RandomFlip(np.random.RandomState(seed))(m4).cpu().numpy(), aug[f"flip/{seed}"])
+        assert np.array_equal(A.RandomRotate90(np.random.RandomState(seed))(m4).cpu().numpy(), aug[f"rot/{seed}"])
+        assert np.array_equal(A.RandomRotate90(np.random.RandomState(seed))(m3).cpu().numpy(), aug[f"rot3/{seed}"])
+        got = A.RandomContrast(np.random.RandomState(seed), execution_probability=0.7)(m4).cpu().numpy()
+        assert np.allclose(got, aug[f"contrast/{seed}"], atol=1e-6)
+    src = {"m4": m4, "m3": m3, "lab": lab}
+    for key in [k for k in aug if k.startswith("elastic/")]:
+        seed, order, name = key.split("/")[1].split("_")
+        e = A.ElasticDeformation(np.random.RandomState(int(seed)), spline_order=int(order), alpha=15, sigma=2,
+                                 execution_probability=1.0, noise="host")
+        got = e(src[name]).cpu().numpy()
+        if int(order) == 0:      # nearest: identical except where a coordinate sits on a rounding boundary
+            assert (got == aug[key]).mean() > 0.999, key
+        else:
+            assert np.abs(got - aug[key]).max() < 1e-4, (key, np.abs(got - aug[key]).max())
+    e2 = A.ElasticDeformation(np.random.RandomState(4), spline_order=1, alpha=15, sigma=2, execution_probability=1.0,
+                              apply_3d=False, noise="host")
+    assert np.abs(e2(m3).cpu().numpy() - aug["elastic2d/4_1_m3"]).max() < 1e-4
+    assert np.allclose(A.Standardize()(m4).cpu().numpy(), aug["standardize/global"], atol=2e-5)
+    assert np.allclose(A.Standardize(channelwise=True)(m4).cpu().numpy(), aug["standardize/channelwise"], atol=2e-5)
+    assert np.allclose(A.Standardize(mean=0.1, std=0.5)(m4).cpu().numpy(), aug["standardize/fixed"], atol=2e-6)
+    assert np.allclose(A.Normalize()(m4 * 3).cpu().numpy(), aug["normalize/default"], atol=2e-6)
+    assert np.allclose(A.Normalize(norm01=True)(m4 * 3).cpu().numpy(), aug["normalize/norm01"], atol=2e-6)
+    assert np.allclose(A.Normalize(min_value=-2.0, max_value=2.5)(m4 * 3).cpu().numpy(), aug["normalize/fixed"], atol=2e-6)
+    pipe = A.Compose([A.Standardize(), A.RandomFlip(np.random.RandomState(5)), A.RandomRotate90(np.random.RandomState(5)),
+                      A.RandomContrast(np.random.RandomState(5), execution_probability=1.0),
+                      A.ElasticDeformation(np.random.RandomState(5), spline_order=1, alpha=15, sigma=2,
+                                           execution_probability=1.0, noise="host")])
+    out = pipe(m4).cpu().numpy()
+    assert out.shape == aug["pipeline"].shape and np.abs(out - aug["pipeline"]).max() < 2e-4
+    # device-noise mode and the reference's default strength on a patch-sized volume: finite, same shape, deformed
+    big = torch.rand((1, 32, 96, 96), device="cuda")
+    ed = A.ElasticDeformation(np.random.RandomState(0), spline_order=1, alpha=2000, sigma=50, execution_probability=1.0)
+    y = ed(big)
+    assert y.shape == big.shape and torch.isfinite(y).all() and not torch.equal(y, big)
+    n = A.AdditiveGaussianNoise(np.random.RandomState(0), execution_probability=1.0)(big)
+    assert n.shape == big.shape and (n - big).std().item() > 0

@@ -147,3 +147,41 @@ def test_lazy_predictor_restatement_equals_standard():
         b = OP.lazy_predict(model_fn, raw, (6, 8, 6), (3, 5, 4), (1, 2, 1), out_channels=3, save_segmentation=seg,
                             batch_size=2)
         assert a.dtype == b.dtype and np.array_equal(a, b)
+
+
+# ----------------------------------------------------------------------------------- augmentation
+AUG = load_golden("augment_r2")
+
+
+def test_oracle_augmentations_vs_reference():
+    """oracle/augment.py against the outputs of the reference's own transforms (augment/unet3d_augment/transforms.py)
+    for the same np.random.RandomState seeds; its gaussian_filter / map_coordinates restatements against scipy."""
+    from scipy import ndimage
+    from oracle import augment as OA
+    m4, m3, lab = AUG["m4"], AUG["m3"], AUG["lab"]
+    for seed in range(6):
+        assert np.array_equal(OA.random_flip(m4, np.random.RandomState(seed)), AUG[f"flip/{seed}"])
+        assert np.array_equal(OA.random_rotate90(m4, np.random.RandomState(seed)), AUG[f"rot/{seed}"])
+        assert np.array_equal(OA.random_rotate90(m3, np.random.RandomState(seed)), AUG[f"rot3/{seed}"])
+        assert np.allclose(OA.random_contrast(m4, np.random.RandomState(seed), execution_probability=0.7),
+                           AUG[f"contrast/{seed}"], atol=1e-7)
+    src = {"m4": m4, "m3": m3, "lab": lab}
+    for key in [k for k in AUG if k.startswith("elastic/")]:
+        seed, order, name = key.split("/")[1].split("_")
+        got = OA.elastic_deformation(src[name], np.random.RandomState(int(seed)), int(order), alpha=15, sigma=2,
+                                     execution_probability=1.0)
+        assert np.allclose(got, AUG[key], atol=2e-6), key
+    got = OA.elastic_deformation(m3, np.random.RandomState(4), 1, alpha=15, sigma=2, execution_probability=1.0,
+                                 apply_3d=False)
+    assert np.allclose(got, AUG["elastic2d/4_1_m3"], atol=2e-6)
+    assert np.allclose(OA.standardize(m4), AUG["standardize/global"], atol=1e-6)
+    assert np.allclose(OA.standardize(m4, channelwise=True), AUG["standardize/channelwise"], atol=1e-6)
+    assert np.allclose(OA.normalize(m4 * 3), AUG["normalize/default"], atol=1e-6)
+    assert np.allclose(OA.normalize(m4 * 3, norm01=True), AUG["normalize/norm01"], atol=1e-6)
+    rs = np.random.RandomState(1)
+    field = rs.randn(6, 9, 10)
+    assert np.abs(OA.gaussian_filter(field, 2.0) - ndimage.gaussian_filter(field, 2.0, mode="reflect")).max() < 1e-12
+    coords = [rs.uniform(-12, 20, size=(6, 9, 10)) for _ in range(3)]
+    for order in (0, 1):
+        ref = ndimage.map_coordinates(m3[:6, :8, :10].copy(), coords, order=order, mode="reflect")
+        assert np.abs(OA.map_coordinates(m3[:6, :8, :10].copy(), coords, order) - ref).max() < 1e-6
