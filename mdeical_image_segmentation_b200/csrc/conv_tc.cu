@@ -1742,7 +1742,13 @@ __global__ void __launch_bounds__(256, 1)
       if (++stage == p.stages) { stage = 0; phase ^= 1; }
     }
   } else if (warp == 1) {
-    const uint32_t idesc = make_idesc_bf16(p.M, ncols, 1, 1);
+    // The T taps' boxes of the tap-addressed operand sit 16 KB apart, i.e. they ARE the atoms of one wider
+    // MN-major operand: when T * ncols <= 256 a single MMA per K step covers all taps (N = 256 for the four taps
+    // of a ConvTranspose 2x2, 192 for a three-tap group) instead of T fetch-bound N = 64 MMAs; the accumulator
+    // layout (tap t at column t * ncols) is unchanged.
+    const bool merged = p.T * ncols <= 256 && p.T > 1;
+    const uint32_t idesc = make_idesc_bf16(p.M, merged ? p.T * ncols : ncols, 1, 1);
+    const int tsteps = merged ? 1 : p.T;
     int stage = 0;
     uint32_t phase = 0;
     bool first = true;
@@ -1753,7 +1759,7 @@ __global__ void __launch_bounds__(256, 1)
       const uint32_t naddr = maddr + mboxes * kABytes;
       if (elect_one()) {
         const uint64_t da0 = make_smem_desc_sw128(maddr, kABytes, 1024);
-        for (int t = 0; t < p.T; ++t) {
+        for (int t = 0; t < tsteps; ++t) {
           const uint64_t db0 = make_smem_desc_sw128(naddr + t * NB * kABytes, kABytes, 1024);
 #pragma unroll
           for (int k = 0; k < 8; ++k)  // 16 positions (= 2 KB of rows) per MMA

@@ -27,20 +27,35 @@ def _bf(t: torch.Tensor) -> torch.Tensor:
     return t + (t.bfloat16().float() - t).detach()
 
 
-def conv_bn_relu(sd: SD, conv: str, bn: str, x: torch.Tensor, training: bool, emulate_bf16: bool = False):
+ALL_SITES = frozenset({"w", "x", "pre_bn", "act", "up", "head"})
+
+
+def _sites(emulate_bf16):
+    """``emulate_bf16``: False, True (every storage site) or a set of site names — "w" filter packs, "x" conv inputs,
+    "pre_bn" conv outputs in front of a BatchNorm, "act" normalised + ReLU outputs, "up" bilinear outputs, "head" the
+    output convs — for the per-site error budget (tools/u3p_error_budget.py)."""
+    if emulate_bf16 is True:
+        return ALL_SITES
+    return frozenset(emulate_bf16) if emulate_bf16 else frozenset()
+
+
+def conv_bn_relu(sd: SD, conv: str, bn: str, x: torch.Tensor, training: bool, emulate_bf16=False):
+    sites = _sites(emulate_bf16)
     w = sd[conv + ".weight"]
-    if emulate_bf16:
-        x, w = _bf(x), _bf(w)
+    if "x" in sites:
+        x = _bf(x)
+    if "w" in sites:
+        w = _bf(w)
     x = F.conv2d(x, w, sd[conv + ".bias"], padding=1)
-    if emulate_bf16:
+    if "pre_bn" in sites:
         x = _bf(x)
     x = F.batch_norm(x, sd[bn + ".running_mean"], sd[bn + ".running_var"], sd[bn + ".weight"], sd[bn + ".bias"],
                      training=training, momentum=0.1, eps=1e-5)
     x = F.relu(x)
-    return _bf(x) if emulate_bf16 else x
+    return _bf(x) if "act" in sites else x
 
 
-def unet3plus_forward(sd: SD, x: torch.Tensor, training: bool = True, emulate_bf16: bool = False,
+def unet3plus_forward(sd: SD, x: torch.Tensor, training: bool = True, emulate_bf16=False,
                       deep_sup: bool = False, cgm: bool = False):
     """unet.py:335-446: encoder (unetConv2 + MaxPool2d(2)) -> four full-scale decoder stages -> 3x3 output
     conv; returns logits (the sigmoid at :445 is commented out).  ``emulate_bf16`` rounds weights and every
@@ -49,13 +64,14 @@ def unet3plus_forward(sd: SD, x: torch.Tensor, training: bool = True, emulate_bf
     ``deep_sup``: UNet_3Plus_DeepSup (unet.py:454-787) — the tuple (d1..d5) of per-scale logits, each
     bilinearly up-sampled to the input size.  ``cgm`` (with deep_sup): UNet_3Plus_DeepSup_CGM (unet.py:795-1153)
     — the five maps gated per sample by the classification branch, as probabilities."""
+    sites = _sites(emulate_bf16)
     h = {}
     for lvl in range(1, 6):
         if lvl > 1:
             x = F.max_pool2d(x, 2)                                             # unet.py:343-353
-        if emulate_bf16:
+        if sites:
             for i in (1, 2):
-                x = conv_bn_relu(sd, f"conv{lvl}.conv{i}.0", f"conv{lvl}.conv{i}.1", x, training, True)
+                x = conv_bn_relu(sd, f"conv{lvl}.conv{i}.0", f"conv{lvl}.conv{i}.1", x, training, sites)
         else:
             x = unet_conv2(sd, f"conv{lvl}.", x, training=training)
         h[lvl] = x
@@ -71,22 +87,22 @@ def unet3plus_forward(sd: SD, x: torch.Tensor, training: bool = True, emulate_bf
                 src = h[level]
             else:                                                              # nn.Upsample(bilinear), :198
                 src = F.interpolate(hd[level], scale_factor=2 ** (level - stage), mode="bilinear")
-                if emulate_bf16:
+                if "up" in sites:
                     src = _bf(src)
-            parts.append(conv_bn_relu(sd, name + "_conv", name + "_bn", src, training, emulate_bf16))
-        hd[stage] = conv_bn_relu(sd, f"conv{stage}d_1", f"bn{stage}d_1", torch.cat(parts, 1), training,
-                                 emulate_bf16)
+            parts.append(conv_bn_relu(sd, name + "_conv", name + "_bn", src, training, sites))
+        hd[stage] = conv_bn_relu(sd, f"conv{stage}d_1", f"bn{stage}d_1", torch.cat(parts, 1), training, sites)
+
     def head(i):
         w = sd[f"outconv{i}.weight"]
-        y = F.conv2d(hd[i], _bf(w) if emulate_bf16 else w, sd[f"outconv{i}.bias"], padding=1)
-        return _bf(y) if emulate_bf16 else y
+        y = F.conv2d(hd[i], _bf(w) if "head" in sites else w, sd[f"outconv{i}.bias"], padding=1)
+        return _bf(y) if "head" in sites else y
 
     if not deep_sup:
         return head(1)
     outs = [head(1)]                                                           # unet.py:760-787
     for i in range(2, 6):
         y = F.interpolate(head(i), scale_factor=2 ** (i - 1), mode="bilinear")
-        outs.append(_bf(y) if emulate_bf16 else y)
+        outs.append(_bf(y) if "head" in sites else y)
     if not cgm:
         return tuple(outs)
     # class-guided module, unet.py:999-1004, 1035-1038, 1012-1017, 1147-1153 (dropout: identity, i.e. eval mode

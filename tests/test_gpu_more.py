@@ -388,54 +388,60 @@ def test_unet3plus_trained_parity(B):
         opt.zero_grad()
         bce(O3.unet3plus_forward(sd, x, True), m).backward()
         opt.step()
-    x, m = task(999, (2, 3, 96, 128))     # fully convolutional: compared on 24576 voxels (one flip = 1e-4 of IoU)
     trained = {k: v.detach().clone() for k, v in sd.items()}
+    # fully convolutional: compared on 24576 voxels (one flip = 1e-4 of IoU), and on a 256 x 256 batch, where the
+    # batch statistics average 5x more positions and the storage noise in the gradient halves
+    # (profiles/r02_u3p_error_budget.txt: per-site budget; torch.autocast(bf16) of the reference lands on the same
+    # 0.19 / 0.10 as this storage policy)
+    for eval_shape in ((2, 3, 96, 128), (2, 3, 256, 256)):
+        x, m = task(999, eval_shape)
+        net.zero_grad(set_to_none=True)
 
-    def grads_of(emulate):
-        s = {k: (v.clone().requires_grad_(True) if k in names else v.clone()) for k, v in trained.items()}
-        lo = O3.unet3plus_forward(s, x, True, emulate_bf16=emulate)
-        ls = bce(lo, m)
-        ls.backward()
-        return lo.detach(), ls.item(), torch.cat([s[k].grad.flatten() for k in names]), \
-            {k: s[k].grad.norm().item() for k in names}
+        def grads_of(emulate):
+            s = {k: (v.clone().requires_grad_(True) if k in names else v.clone()) for k, v in trained.items()}
+            lo = O3.unet3plus_forward(s, x, True, emulate_bf16=emulate)
+            ls = bce(lo, m)
+            ls.backward()
+            return lo.detach(), ls.item(), torch.cat([s[k].grad.flatten() for k in names]), \
+                {k: s[k].grad.norm().item() for k in names}
 
-    ref_logits, ref_loss, ref_g, ref_norms = grads_of(False)
-    _, _, emu_g, _ = grads_of(True)
-    with torch.no_grad():
-        ref_eval = O3.unet3plus_forward({k: v.clone() for k, v in trained.items()}, x, False)
+        ref_logits, ref_loss, ref_g, ref_norms = grads_of(False)
+        _, _, emu_g, _ = grads_of(True)
+        with torch.no_grad():
+            ref_eval = O3.unet3plus_forward({k: v.clone() for k, v in trained.items()}, x, False)
 
-    net.load_state_dict(trained)
-    net = net.cuda().train()
-    logits = net(x.cuda())
-    loss = B.BCEWithLogitsLoss()(logits, m.cuda())
-    loss.backward()
-    lg = logits.detach().cpu()
-    assert rel_l2(lg, ref_logits) < 2e-2, rel_l2(lg, ref_logits)
-    assert (lg - ref_logits).abs().max() / ref_logits.abs().max() < 2e-2
-    agree = _mask_agreement(lg, ref_logits)
-    assert abs(loss.item() - ref_loss) < 1e-3
-    mm = B.metrics.compute_metrics((lg.numpy(), m.numpy()))
-    rr = OM.compute_metrics(ref_logits.numpy(), m.numpy())
-    assert abs(mm["iou"] - rr["iou"]) < 1e-3 and abs(mm["dice"] - rr["dice"]) < 1e-3
-    named = dict(net.named_parameters())
-    g = torch.cat([named[k].grad.flatten().cpu() for k in names])
-    e_ref, e_emu, e_noise = rel_l2(g, ref_g), rel_l2(g, emu_g), rel_l2(emu_g, ref_g)
-    cos = (g @ ref_g / (g.norm() * ref_g.norm())).item()
-    print(f"UNet3+ trained: logits rel-L2 {rel_l2(lg, ref_logits):.3e}, masks {agree:.5f}, gradient vs fp32 "
-          f"{e_ref:.3f}, vs bf16-storage emulation {e_emu:.3f} (emulation vs fp32 {e_noise:.3f}), cosine {cos:.4f}")
-    assert e_ref < 1.5 * e_noise + 2e-2, (e_ref, e_noise)      # no further from fp32 than storage noise explains
-    assert e_emu < 1.5 * e_noise + 2e-2, (e_emu, e_noise)
-    assert cos > 0.97, cos
-    for k in names:                                             # a mis-wired branch shows up as an O(1) norm error
-        a, b = named[k].grad.norm().item(), ref_norms[k]
-        assert abs(a - b) < 0.3 * b + 2e-3 * ref_g.norm().item(), (k, a, b)
-    # eval mode: running statistics (updated by the oracle's training) instead of batch statistics
-    net.load_state_dict(trained)        # the training-mode forward above moved the running statistics
-    net.eval()
-    with torch.no_grad():
-        ev = net(x.cuda()).cpu()
-    assert rel_l2(ev, ref_eval) < 2e-2, rel_l2(ev, ref_eval)
-    _mask_agreement(ev, ref_eval, overall=0.99)   # 30 steps of running statistics: many logits near 0
+        net.load_state_dict(trained)
+        net = net.cuda().train()
+        logits = net(x.cuda())
+        loss = B.BCEWithLogitsLoss()(logits, m.cuda())
+        loss.backward()
+        lg = logits.detach().cpu()
+        assert rel_l2(lg, ref_logits) < 2e-2, rel_l2(lg, ref_logits)
+        assert (lg - ref_logits).abs().max() / ref_logits.abs().max() < 2e-2
+        agree = _mask_agreement(lg, ref_logits)
+        assert abs(loss.item() - ref_loss) < 1e-3
+        mm = B.metrics.compute_metrics((lg.numpy(), m.numpy()))
+        rr = OM.compute_metrics(ref_logits.numpy(), m.numpy())
+        assert abs(mm["iou"] - rr["iou"]) < 1e-3 and abs(mm["dice"] - rr["dice"]) < 1e-3
+        named = dict(net.named_parameters())
+        g = torch.cat([named[k].grad.flatten().cpu() for k in names])
+        e_ref, e_emu, e_noise = rel_l2(g, ref_g), rel_l2(g, emu_g), rel_l2(emu_g, ref_g)
+        cos = (g @ ref_g / (g.norm() * ref_g.norm())).item()
+        print(f"UNet3+ trained {eval_shape[2]}x{eval_shape[3]}: logits rel-L2 {rel_l2(lg, ref_logits):.3e}, masks {agree:.5f}, gradient vs fp32 "
+              f"{e_ref:.3f}, vs bf16-storage emulation {e_emu:.3f} (emulation vs fp32 {e_noise:.3f}), cosine {cos:.4f}")
+        assert e_ref < 1.5 * e_noise + 2e-2, (e_ref, e_noise)      # no further from fp32 than storage noise explains
+        assert e_emu < 1.5 * e_noise + 2e-2, (e_emu, e_noise)
+        assert cos > 0.97, cos
+        for k in names:                                             # a mis-wired branch shows up as an O(1) norm error
+            a, b = named[k].grad.norm().item(), ref_norms[k]
+            assert abs(a - b) < 0.3 * b + 2e-3 * ref_g.norm().item(), (k, a, b)
+        # eval mode: running statistics (updated by the oracle's training) instead of batch statistics
+        net.load_state_dict(trained)        # the training-mode forward above moved the running statistics
+        net.eval()
+        with torch.no_grad():
+            ev = net(x.cuda()).cpu()
+        assert rel_l2(ev, ref_eval) < 2e-2, rel_l2(ev, ref_eval)
+        _mask_agreement(ev, ref_eval, overall=0.99)   # 30 steps of running statistics: many logits near 0
 
 
 def test_unet3plus_deepsup_vs_reference_golden(B):
