@@ -292,12 +292,25 @@ int b200_gn_bwd(int32_t n, int64_t spatial, int32_t c, int32_t groups, b200_view
  * backward folded in: x / dy are the (n, ld*fd, lh*fh, lw*fw, cs + cx) concat tensors (f* = 1 or 2 per axis);
  * dskip receives the gradient of the skip half at full resolution, dlow (n, ld, lh, lw, cx) the gradient of the
  * up-sampled half summed over each source voxel's children — the full-resolution gradient of that half and the
- * separate F.interpolate backward pass do not exist.  colstats / scratch / dgamma / dbeta as b200_gn_bwd_fused. */
+ * separate F.interpolate backward pass do not exist.  colstats / scratch / dgamma / dbeta as b200_gn_bwd_fused.
+ * xlow: {NULL,0,0}, or the low-resolution (n, ld, lh, lw, cx) source of the up-sampled half when the forward ran
+ * b200_gn_apply_up and never wrote that half of x.
+ * beta_if_y (needs xlow): NULL, or the norm's bias when colstats holds (sum dy, sum dy * y) with y the norm's OUTPUT
+ * (a norm without fused activation: y = gamma * xhat + beta, so gamma * sum dy * xhat = sum dy * y - beta * sum dy);
+ * channels whose gamma is 0 or below |beta| / 8 get their dgamma from a direct reduction over (dy, x) instead. */
 int b200_gn_bwd_fused_up(int32_t n, int32_t ld, int32_t lh, int32_t lw, int32_t fd, int32_t fh, int32_t fw,
                          int32_t cs, int32_t cx, int32_t groups, b200_view x, const float* stats,
                          const float* gamma, b200_view dy, b200_view dskip, b200_view dlow, float* dgamma,
                          float* dbeta, const double* colstats, float* scratch, int32_t mask_relu,
-                         b200_stream_t stream);
+                         b200_view xlow, const float* beta_if_y, b200_stream_t stream);
+
+/* GroupNorm (+ ReLU) of a decoder concat (skip | nearest-upsampled) whose up-sampled half is NOT materialised
+ * (replaces F.interpolate(mode="nearest") + torch.cat + nn.GroupNorm, buildingblocks.py:539-547, 671-673, 73-103):
+ * xskip = the (n, ld*fd, lh*fh, lw*fw, cs) skip tensor, xlow = the (n, ld, lh, lw, cx) low-resolution tensor,
+ * f* = 1 or 2; stats [n][groups][2] over the cs + cx channels; y = the full (…, cs + cx) normalised tensor. */
+int b200_gn_apply_up(int32_t n, int32_t ld, int32_t lh, int32_t lw, int32_t fd, int32_t fh, int32_t fw,
+                     int32_t cs, int32_t cx, int32_t groups, b200_view xskip, b200_view xlow, const float* stats,
+                     const float* gamma, const float* beta, int32_t relu, b200_view y, b200_stream_t stream);
 /* (mean, rstd) per (sample, group) from per-channel sums: sums fp64 [n][2][c] = (sum x, sum x^2) as
  * produced by b200_conv_fwd_stats (or b200_gn_stats' scratch) */
 int b200_gn_stats_finalize(int32_t n, int64_t spatial, int32_t c, int32_t groups, float eps,

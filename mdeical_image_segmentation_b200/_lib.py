@@ -59,7 +59,8 @@ SIGNATURES = {
     "b200_gn_stats_finalize": [_I, _L, _I, _I, _F, _P, _P, _P],
     "b200_gn_bwd_fused": [_I, _L, _I, _I, View, _P, _P, View, View, _P, _P, _P, _P, _I, _P],
     "b200_gn_bwd_fused_up": [_I, _I, _I, _I, _I, _I, _I, _I, _I, _I, View, _P, _P, View, View, View, _P, _P, _P, _P,
-                             _I, _P],
+                             _I, View, _P, _P],
+    "b200_gn_apply_up": [_I, _I, _I, _I, _I, _I, _I, _I, _I, _I, View, View, _P, _P, _P, _I, View, _P],
     "b200_bn_bwd_red_from_sums": [_I, _I, _P, _P, _P, _P, _P],
     "b200_convt2x2_repack_weight": [_PT, _P, _P, _P, _P],
     "b200_convt2x2_fwd": [_PT, _P, _P, _P, _P, _P],
@@ -180,7 +181,7 @@ def check(rc: int, what: str = "") -> None:
 
 # kernels launched per successful C-ABI call (for bench.py's `gpu_launches` accounting)
 LAUNCHES_PER_CALL = {"b200_gn_stats": 2, "b200_gn_bwd": 3, "b200_gn_bwd_fused": 2, "b200_deconv3s2_fwd": 8,
-                     "b200_gn_bwd_fused_up": 3}
+                     "b200_gn_bwd_fused_up": 3, "b200_gn_apply_up": 2}
 launch_count = 0
 # optional profiler hook: fn(name, args) -> context manager, installed by bench.py for per-kernel timing
 profile_hook = None

@@ -1005,7 +1005,7 @@ struct ColMap {
 template <int V>
 __global__ void __launch_bounds__(256, 4)
     norm_apply_kernel(long spatial, int c, int groups, long chunk, int mode, View x, const float* p0,
-                      const float* p1, const float* gamma, const float* beta, int relu, View y) {
+                      const float* p1, const float* gamma, const float* beta, int relu, View y, int cpg = 0) {
   const ColMap m(c, V);
   if (!m.active()) return;
   const int b = blockIdx.z, ch = m.my_cv * V;
@@ -1014,7 +1014,7 @@ __global__ void __launch_bounds__(256, 4)
   for (int j = 0; j < V; ++j) {
     float mean, rstd;
     if (mode == 0) {
-      const int g = (ch + j) / (c / groups);
+      const int g = (ch + j) / (cpg ? cpg : c / groups);   // cpg given: x is a channel prefix of the normalised tensor
       mean = p0[(b * groups + g) * 2];
       rstd = p0[(b * groups + g) * 2 + 1];
     } else {
@@ -1180,7 +1180,7 @@ __global__ void __launch_bounds__(256, 4)
 __global__ void __launch_bounds__(256, 4)
     gn_bwd_up_kernel(int n, int ld, int lh, int lw, int fd, int fh, int fw, int cx, int coff_up, int cpg,
                      int groups, float inv_m, View xcat, View dy, const float* stats, const float* gamma,
-                     const float* gsum, View dlow, int mask_x) {
+                     const float* gsum, View dlow, int mask_x, View xlow) {
   const int cv = cx / 8;
   const long total = (long)n * ld * lh * lw * cv;
   const int od = ld * fd, oh = lh * fh, ow = lw * fw;
@@ -1200,7 +1200,10 @@ __global__ void __launch_bounds__(256, 4)
       if (a < fd && e < fh && g < fw) rg[q] = ldg_nc_v4(dy.at(p0 + ((long)a * oh + e) * ow + g, coff_up + ch));
       else rg[q] = make_uint4(0, 0, 0, 0);
     }
-    const uint4 rx = ldg_nc_v4(xcat.at(p0, coff_up + ch));
+    // x of the up-sampled half: its first child in the concat buffer, or (when the forward never materialised
+    // that half, b200_gn_apply_up) the low-resolution source itself
+    const uint4 rx = xlow.p ? ldg_nc_v4(xlow.at((((long)b * ld + xd) * lh + xh) * lw + xw, ch))
+                            : ldg_nc_v4(xcat.at(p0, coff_up + ch));
     float sg[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) sg[j] = 0.f;
@@ -1234,6 +1237,50 @@ __global__ void __launch_bounds__(256, 4)
       (&o.x)[w] = pack_bf16x2(res[0], res[1]);
     }
     *reinterpret_cast<uint4*>(dlow.at((((long)b * ld + xd) * lh + xh) * lw + xw, ch)) = o;
+  }
+}
+
+// GroupNorm apply over the up-sampled half of a decoder concat WITHOUT materialising it: one thread = one source
+// voxel x 8 channels of the low-resolution tensor, normalised once (+ ReLU) and written to its fd*fh*fw children in
+// channels [coff_up, coff_up + cx) of y.  Replaces upsample_exact_fwd (1 read + 8 writes) followed by the apply's
+// re-read of those 8 copies.
+__global__ void __launch_bounds__(256, 4)
+    gn_apply_up_kernel(int n, int ld, int lh, int lw, int fd, int fh, int fw, int cx, int coff_up, int cpg,
+                       int groups, View xlow, const float* stats, const float* gamma, const float* beta,
+                       int relu, View y) {
+  const int cv = cx / 8;
+  const long total = (long)n * ld * lh * lw * cv;
+  const int oh = lh * fh, ow = lw * fw, od = ld * fd;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    long r = i;
+    const int ch = (int)(r % cv) * 8; r /= cv;
+    const int xw = (int)(r % lw); r /= lw;
+    const int xh = (int)(r % lh); r /= lh;
+    const int xd = (int)(r % ld); r /= ld;
+    const int b = (int)r;
+    const uint4 rx = ldg_nc_v4(xlow.at((((long)b * ld + xd) * lh + xh) * lw + xw, ch));
+    uint4 o;
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+      float2 f = unpack_bf16x2((&rx.x)[w]);
+      float res[2] = {f.x, f.y};
+#pragma unroll
+      for (int h2 = 0; h2 < 2; ++h2) {
+        const int c_abs = coff_up + ch + 2 * w + h2;
+        const int gi = b * groups + c_abs / cpg;
+        const float sc = stats[gi * 2 + 1] * gamma[c_abs];
+        const float v = fmaf(res[h2], sc, beta[c_abs] - stats[gi * 2] * sc);
+        res[h2] = relu ? fmaxf(v, 0.f) : v;
+      }
+      (&o.x)[w] = pack_bf16x2(res[0], res[1]);
+    }
+    const long p0 = (((long)b * od + xd * fd) * oh + xh * fh) * ow + (long)xw * fw;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const int a = q >> 2, e = (q >> 1) & 1, g = q & 1;
+      if (a < fd && e < fh && g < fw)
+        *reinterpret_cast<uint4*>(y.at(p0 + ((long)a * oh + e) * ow + g, coff_up + ch)) = o;
+    }
   }
 }
 
@@ -1368,6 +1415,73 @@ __global__ void gn_bwd_finalize_raw_kernel(int n, int c, int groups, const float
     if (dbeta) atomicAdd(dbeta + i, (float)a);
     if (dgamma) atomicAdd(dgamma + i, (float)bb);
   }
+}
+// Variant for a GroupNorm WITHOUT activation whose input was never materialised (b200_gn_apply_up): the data-gradient
+// epilogue correlated dy with the norm's OUTPUT y = gamma * xhat + beta instead, raw[n][2][c] = (sum dy, sum dy * y):
+//   gamma * sum dy * xhat = sum dy * y - beta * sum dy        (group term: no division)
+//   dgamma = that / gamma                                     (channels with |gamma| * 8 < |beta|, where the bf16
+// rounding of y ~ beta would dominate — gamma == 0 included —, are left to gn_dgamma_direct_kernel)
+__device__ __forceinline__ bool gn_gamma_degenerate(float gamma, float beta) {
+  return gamma == 0.f || fabsf(gamma) * 8.f < fabsf(beta);
+}
+__global__ void gn_bwd_finalize_y_kernel(int n, int c, int groups, const float* gamma, const float* beta,
+                                         const double* raw, float* gsum, float* dgamma, float* dbeta) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int cpg = c / groups;
+  if (i < n * groups) {
+    const int b = i / groups, g = i % groups;
+    double a = 0, bb = 0;
+    for (int ch = g * cpg; ch < (g + 1) * cpg; ++ch) {
+      const double s1 = raw[((long)b * 2) * c + ch], sy = raw[((long)b * 2 + 1) * c + ch];
+      a += gamma[ch] * s1;
+      if (gamma[ch] != 0.f) bb += sy - (double)beta[ch] * s1;   // gamma == 0: y == beta, the true term is 0
+    }
+    gsum[2 * i] = (float)a;
+    gsum[2 * i + 1] = (float)bb;
+  }
+  if (i < c) {
+    double a = 0, bb = 0;
+    for (int b = 0; b < n; ++b) {
+      const double s1 = raw[((long)b * 2) * c + i], sy = raw[((long)b * 2 + 1) * c + i];
+      a += s1;
+      bb += sy - (double)beta[i] * s1;
+    }
+    if (dbeta) atomicAdd(dbeta + i, (float)a);
+    if (dgamma && !gn_gamma_degenerate(gamma[i], beta[i])) atomicAdd(dgamma + i, (float)(bb / (double)gamma[i]));
+  }
+}
+// dgamma_c = sum dy * xhat straight from the tensors, for the (rare) channels gn_bwd_finalize_y_kernel cannot serve:
+// one block per channel, which returns at once unless its gamma is degenerate.  x of channel ch >= cs comes from the
+// low-resolution tensor (nearest 1x/2x up-sampling).
+__global__ void gn_dgamma_direct_kernel(int n, int ld, int lh, int lw, int fd, int fh, int fw, int cs, int c,
+                                        int groups, View xskip, View xlow, View dy, const float* stats,
+                                        const float* gamma, const float* beta, float* dgamma) {
+  const int ch = blockIdx.x;
+  if (!gn_gamma_degenerate(gamma[ch], beta[ch])) return;
+  const int od = ld * fd, oh = lh * fh, ow = lw * fw, cpg = c / groups;
+  const long spatial = (long)od * oh * ow;
+  double acc = 0;
+  for (int b = 0; b < n; ++b) {
+    const float mean = stats[2 * (b * groups + ch / cpg)], rstd = stats[2 * (b * groups + ch / cpg) + 1];
+    float part = 0.f;
+    for (long p = threadIdx.x; p < spatial; p += blockDim.x) {
+      const int xw = (int)(p % ow), xh = (int)((p / ow) % oh), xd = (int)(p / ((long)ow * oh));
+      const long pos = (long)b * spatial + p;
+      const float xv = ch < cs ? __bfloat162float(*xskip.at(pos, ch))
+                               : __bfloat162float(*xlow.at((((long)b * ld + xd / fd) * lh + xh / fh) * lw + xw / fw,
+                                                           ch - cs));
+      part = fmaf(__bfloat162float(*dy.at(pos, ch)), (xv - mean) * rstd, part);
+    }
+    acc += (double)part;
+  }
+  __shared__ double red[256];
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  for (int s2 = blockDim.x / 2; s2 > 0; s2 >>= 1) {
+    if ((int)threadIdx.x < s2) red[threadIdx.x] += red[threadIdx.x + s2];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) atomicAdd(dgamma + ch, (float)red[0]);
 }
 __global__ void bn_red_from_sums_kernel(int n, int c, const double* raw, const float* mean,
                                         const float* rstd, float* red) {
@@ -1820,6 +1934,31 @@ int b200_gn_apply(int32_t n, int64_t spatial, int32_t c, int32_t groups, b200_vi
   B200_LAUNCH_CHECK();
   return B200_OK;
 }
+int b200_gn_apply_up(int32_t n, int32_t ld, int32_t lh, int32_t lw, int32_t fd, int32_t fh, int32_t fw,
+                     int32_t cs, int32_t cx, int32_t groups, b200_view xskip, b200_view xlow, const float* stats,
+                     const float* gamma, const float* beta, int32_t relu, b200_view y, b200_stream_t stream) {
+  const int c = cs + cx;
+  if (groups <= 0 || c % groups) return B200_ERR_BAD_ARG;
+  if (fd < 1 || fh < 1 || fw < 1 || fd > 2 || fh > 2 || fw > 2) return B200_ERR_UNSUPPORTED;
+  const b200_view up_y{y.ptr, y.ctot, y.coff + cs};
+  if (cs % 8 || cx % 8 || !vec8(cs, xskip) || !vec8(cs, y) || !vec8(cx, xlow) || !vec8(cx, up_y))
+    return B200_ERR_UNSUPPORTED;
+  const long spatial = (long)ld * fd * lh * fh * lw * fw;
+  if ((long)n * spatial <= 0) return B200_OK;
+  const int cpg = c / groups;
+  dim3 grid;
+  long chunk;
+  column_grid(spatial, cs, 8, grid, chunk);
+  grid.z = n;
+  norm_apply_kernel<8><<<grid, 256, 0, (cudaStream_t)stream>>>(spatial, cs, groups, chunk, 0, mk(xskip), stats, nullptr,
+                                                              gamma, beta, relu, mk(y), cpg);
+  B200_LAUNCH_CHECK();
+  const long total = (long)n * ld * lh * lw * (cx / 8);
+  gn_apply_up_kernel<<<GRID1D(total), 256, 0, (cudaStream_t)stream>>>(n, ld, lh, lw, fd, fh, fw, cx, cs, cpg, groups,
+                                                                      mk(xlow), stats, gamma, beta, relu, mk(y));
+  B200_LAUNCH_CHECK();
+  return B200_OK;
+}
 int b200_gn_bwd(int32_t n, int64_t spatial, int32_t c, int32_t groups, b200_view x,
                 const float* stats, const float* gamma, b200_view dy, b200_view dx, float* dgamma,
                 float* dbeta, float* scratch, int32_t mask_relu, b200_stream_t stream) {
@@ -1886,8 +2025,10 @@ int b200_gn_bwd_fused_up(int32_t n, int32_t ld, int32_t lh, int32_t lw, int32_t 
                          int32_t cs, int32_t cx, int32_t groups, b200_view x, const float* stats,
                          const float* gamma, b200_view dy, b200_view dskip, b200_view dlow, float* dgamma,
                          float* dbeta, const double* colstats, float* scratch, int32_t mask_relu,
-                         b200_stream_t stream) {
+                         b200_view xlow, const float* beta_if_y, b200_stream_t stream) {
   const int c = cs + cx;
+  if (xlow.ptr && !vec8(cx, xlow)) return B200_ERR_UNSUPPORTED;
+  if (beta_if_y && !xlow.ptr) return B200_ERR_BAD_ARG;
   if (groups <= 0 || c % groups || !colstats || !scratch) return B200_ERR_BAD_ARG;
   if (fd < 1 || fh < 1 || fw < 1 || fd > 2 || fh > 2 || fw > 2) return B200_ERR_UNSUPPORTED;
   const b200_view up_x{x.ptr, x.ctot, x.coff + cs}, up_dy{dy.ptr, dy.ctot, dy.coff + cs};
@@ -1898,9 +2039,20 @@ int b200_gn_bwd_fused_up(int32_t n, int32_t ld, int32_t lh, int32_t lw, int32_t 
   if ((long)n * spatial <= 0) return B200_OK;
   float* gsum = scratch;  // [n][groups][2]
   const int work = n * groups > c ? n * groups : c;
-  gn_bwd_finalize_raw_kernel<<<(work + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
-      n, c, groups, gamma, stats, colstats, gsum, dgamma, dbeta);
-  B200_LAUNCH_CHECK();
+  if (beta_if_y) {
+    gn_bwd_finalize_y_kernel<<<(work + 127) / 128, 128, 0, (cudaStream_t)stream>>>(n, c, groups, gamma, beta_if_y,
+                                                                                colstats, gsum, dgamma, dbeta);
+    B200_LAUNCH_CHECK();
+    if (dgamma) {
+      gn_dgamma_direct_kernel<<<c, 256, 0, (cudaStream_t)stream>>>(n, ld, lh, lw, fd, fh, fw, cs, c, groups, mk(x),
+                                                                  mk(xlow), mk(dy), stats, gamma, beta_if_y, dgamma);
+      B200_LAUNCH_CHECK();
+    }
+  } else {
+    gn_bwd_finalize_raw_kernel<<<(work + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
+        n, c, groups, gamma, stats, colstats, gsum, dgamma, dbeta);
+    B200_LAUNCH_CHECK();
+  }
   const float inv_m = 1.f / ((float)(c / groups) * (float)spatial);
   const int cpg = c / groups;
   // skip half: the plain apply pass on the channel prefix [0, cs)
@@ -1917,7 +2069,7 @@ int b200_gn_bwd_fused_up(int32_t n, int32_t ld, int32_t lh, int32_t lw, int32_t 
   const long total = (long)n * ld * lh * lw * (cx / 8);
   gn_bwd_up_kernel<<<GRID1D(total), 256, 0, (cudaStream_t)stream>>>(n, ld, lh, lw, fd, fh, fw, cx, cs, cpg, groups,
                                                                     inv_m, mk(x), mk(dy), stats, gamma, gsum,
-                                                                    mk(dlow), mask_relu);
+                                                                    mk(dlow), mask_relu, mk(xlow));
   B200_LAUNCH_CHECK();
   return B200_OK;
 }

@@ -245,9 +245,26 @@ def _plant_ones(dst: CL, tape, i: int, letters: str, nxt: int, fuse_relu: bool, 
     return dst.c
 
 
+class UpFold:
+    """A decoder concat (skip | nearest 1x/2x up-sampling of ``low``) whose up-sampled half [cs, c) has not been
+    written: the GroupNorm that reads it normalises from ``low`` directly (ops.gn_apply_up) and its backward reads
+    ``low`` again.  Any other reader calls materialise() first."""
+
+    def __init__(self, cat: CL, cs: int, low: CL):
+        self.cat, self.cs, self.low, self.done = cat, cs, low, False
+        self.dot_is_y = False      # backward: the data-gradient statistics were correlated with the norm's output
+
+    def materialise(self) -> None:
+        if not self.done:
+            ops.upsample_nearest_fwd(self.low, (self.cat.d, self.cat.h, self.cat.w),
+                                     out=self.cat.slice(self.cs, self.cat.c - self.cs))
+            self.done = True
+
+
 def single_conv_fwd(x: CL, spec: LayerSpec, training: bool, tape: Optional[list],
                     out: Optional[CL] = None, in_relu: bool = False,
-                    in_sums: Optional[torch.Tensor] = None, want_sums: bool = False):
+                    in_sums: Optional[torch.Tensor] = None, want_sums: bool = False,
+                    up_src: Optional[UpFold] = None):
     """Runs one layer; ``out`` (optional) is the destination slice of its final result.
     ``in_relu`` says the input is a ReLU output (>= 0, zero exactly where its producer was clipped):
     the first op's backward then folds that producer's ReLU backward into its own output.
@@ -257,6 +274,9 @@ def single_conv_fwd(x: CL, spec: LayerSpec, training: bool, tape: Optional[list]
     letters = spec.order
     cur = x
     cur_sums = in_sums if (in_sums is not None and in_sums.shape[2] == x.c) else None
+    if up_src is not None and not (letters[0] == "g" and cur_sums is not None):
+        up_src.materialise()          # only a GroupNorm with known statistics can skip the up-sampled half
+        up_src = None
     i = 0
     out_relu = False
     ones_ch = -1          # index of a constant-one channel planted in the padding of the conv's input
@@ -306,9 +326,13 @@ def single_conv_fwd(x: CL, spec: LayerSpec, training: bool, tape: Optional[list]
             if dst is None and cur.zpad:
                 dst = cur.new_like_padded()
                 ones_ch = _plant_ones(dst, tape, i, letters, nxt, fuse_relu, spec.conv)
-            y = ops.gn_apply(cur, gn.num_groups, stats, gamma, beta, fuse_relu, out=dst)
+            fold = up_src if i == 0 else None
+            if fold is not None:
+                y = ops.gn_apply_up(cur, fold.cs, fold.low, gn.num_groups, stats, gamma, beta, fuse_relu, out=dst)
+            else:
+                y = ops.gn_apply(cur, gn.num_groups, stats, gamma, beta, fuse_relu, out=dst)
             if tape is not None:
-                tape.append(("gn", cur, gn, stats, gamma, y if fuse_relu else None, in_relu and i == 0))
+                tape.append(("gn", cur, gn, stats, gamma, y if fuse_relu else None, in_relu and i == 0, fold))
             cur = y
         elif ch == "b":
             bn = spec.batchnorm
@@ -382,6 +406,7 @@ def _consumer_plan(consumer, fuse_mask: bool):
 
 
 FOLD_UPSAMPLE_BWD = os.environ.get("B200_FOLD_UPSAMPLE_BWD", "1") != "0"   # A/B knob
+FOLD_UPSAMPLE_FWD = os.environ.get("B200_FOLD_UPSAMPLE_FWD", "1") != "0"   # A/B knob
 
 
 class FoldedCatGrad:
@@ -475,6 +500,16 @@ def single_conv_bwd(dy: CL, recs: list, grads: Grads, need_dx: bool = True, prem
                 dot = dot.widened()
                 if dot.c != x_in.c or dot.dims != x_in.dims:
                     want, dot = False, None
+            fold = nxt_consumer[7] if (nxt_consumer is not None and nxt_consumer[0] == "gn") else None
+            if fold is not None and not fold.done:
+                # The norm's input was never written beyond its skip half (UpFold).  A norm without activation has
+                # y = gamma * xhat + beta, and y is this conv's own input: correlate the gradient with y instead of
+                # x and let the norm backward undo the affine map (ops.gn_bwd_fused_up, beta_if_y).
+                if (want and dot is not None and FOLD_UPSAMPLE_BWD and up_fold is not None and idx == 1
+                        and nxt_consumer[5] is None and not zpad and x_in.is_full() and nxt_consumer[1].is_full()):
+                    dot, fold.dot_is_y = x_in, True
+                else:
+                    fold.materialise()
             if want:   # only sums are consumed unless a norm's (sum g, sum g*x) is asked for
                 dy, sums = ops.conv_bwd_data(dy, wp_bwd, k, mask=x_in if fuse else None, impl=IMPL,
                                              stats="sum", dot=dot)
@@ -486,14 +521,23 @@ def single_conv_bwd(dy: CL, recs: list, grads: Grads, need_dx: bool = True, prem
                 if sums is not None:
                     sums = sums[:, :, :dy.c].contiguous()
         elif kind == "gn":
-            _, x_in, gn, stats, gamma, y_relu, mask_in = rec
+            _, x_in, gn, stats, gamma, y_relu, mask_in, fold = rec
             if y_relu is not None and not pm:
                 dy, _ = ops.relu_bwd(dy, y_relu, False, out=dy)
                 sums = None
-            if (sums is not None and up_fold is not None and idx == 0 and FOLD_UPSAMPLE_BWD
-                    and x_in.is_full() and up_fold[0] % 8 == 0 and (x_in.c - up_fold[0]) % 8 == 0):
-                dskip, dlow, dgamma, dbeta = ops.gn_bwd_fused_up(x_in, gn.num_groups, stats, gamma, dy, sums,
-                                                                 up_fold[0], up_fold[1], mask_relu=mask_in)
+            fused_up = (sums is not None and up_fold is not None and idx == 0 and FOLD_UPSAMPLE_BWD
+                        and x_in.is_full() and up_fold[0] % 8 == 0 and (x_in.c - up_fold[0]) % 8 == 0)
+            if fold is not None and not fold.done and not (fused_up and fold.dot_is_y):
+                if fold.dot_is_y:
+                    raise RuntimeError("statistics were taken against the norm's output but its folded backward "
+                                       "is not available")      # cannot happen: same conditions on both sides
+                fold.materialise()      # the passes below read the whole concat
+            if fused_up:
+                folded = fold is not None and not fold.done
+                dskip, dlow, dgamma, dbeta = ops.gn_bwd_fused_up(
+                    x_in, gn.num_groups, stats, gamma, dy, sums, up_fold[0], up_fold[1], mask_relu=mask_in,
+                    x_low=fold.low if folded else None,
+                    beta_if_y=gn.bias.detach().float().contiguous() if folded else None)
                 dx = FoldedCatGrad(dskip, dlow)
             elif sums is not None:
                 dx, dgamma, dbeta = ops.gn_bwd_fused(x_in, gn.num_groups, stats, gamma, dy, sums,
@@ -533,7 +577,8 @@ def single_conv_bwd(dy: CL, recs: list, grads: Grads, need_dx: bool = True, prem
 
 def block_fwd(x: CL, specs: List[LayerSpec], training: bool, tape: Optional[list],
               out: Optional[CL] = None, in_relu: bool = False,
-              in_sums: Optional[torch.Tensor] = None, want_sums: bool = False):
+              in_sums: Optional[torch.Tensor] = None, want_sums: bool = False,
+              up_src: Optional[UpFold] = None):
     """A DoubleConv / DoubleConvolution / unetConv2: consecutive layers, last one writes ``out``.
     Returns (y, y_is_relu_output, y_sums) — see single_conv_fwd for the sums."""
     flag, sums = in_relu, in_sums
@@ -542,7 +587,8 @@ def block_fwd(x: CL, specs: List[LayerSpec], training: bool, tape: Optional[list
         is_last = j == len(specs) - 1
         want = want_sums if is_last else specs[j + 1].order[0] in "gb"
         x, flag, sums = single_conv_fwd(x, spec, training, sub, out=out if is_last else None,
-                                        in_relu=flag, in_sums=sums, want_sums=want)
+                                        in_relu=flag, in_sums=sums, want_sums=want,
+                                        up_src=up_src if j == 0 else None)
         if tape is not None:
             tape.append(sub)
     return x, flag, sums
@@ -723,6 +769,7 @@ def unet3d_forward(net, x_in: torch.Tensor, training: bool, tape: Optional[list]
         up_dst = cat.slice(skip.c, cx)
         ct = getattr(getattr(dec.upsampling, "upsample", None), "conv_transposed", None)
         cat_sums: Optional[torch.Tensor] = None
+        up_src: Optional[UpFold] = None
         if ct is not None:
             wp_fwd, wp_bwd, kd = ops.deconv_repack_weight(ct.weight)
             planes = ops.deconv_fwd(x, wp_fwd, kd, impl=IMPL)
@@ -731,7 +778,6 @@ def unet3d_forward(net, x_in: torch.Tensor, training: bool, tape: Optional[list]
                 tape.append(("deconv", x, ct, wp_bwd, kd, skip.c, cx))
             cat_relu = False      # the transposed conv has no activation
         else:
-            ops.upsample_nearest_fwd(x, size, out=up_dst)
             if tape is not None:
                 tape.append(("nearest", (x.d, x.h, x.w), skip.c, cx))
             cat_relu = relu and skip_relu[n_enc - 2 - j]   # both halves are ReLU outputs
@@ -743,11 +789,19 @@ def unet3d_forward(net, x_in: torch.Tensor, training: bool, tape: Optional[list]
             if x_sums is not None and s_skip is not None and exact:
                 f = (size[0] // x.d) * (size[1] // x.h) * (size[2] // x.w)
                 cat_sums = torch.cat([s_skip, x_sums * float(f)], dim=2)
+            # with those statistics and 1x/2x factors the GroupNorm in front of the decoder's first conv reads
+            # the low-resolution tensor itself: the up-sampled half of the concat is never written
+            if (FOLD_UPSAMPLE_FWD and cat_sums is not None and order[0] == "g" and x.is_full()
+                    and skip.c % 8 == 0 and cx % 8 == 0
+                    and all(o == i or o == 2 * i for o, i in zip(size, (x.d, x.h, x.w)))):
+                up_src = UpFold(cat, skip.c, x)
+            else:
+                ops.upsample_nearest_fwd(x, size, out=up_dst)
         if ct is not None:
             cat_sums = None
         x, relu, x_sums = block_fwd(cat, double_conv_specs(dec.basic_module, order), training, tape,
                                     in_relu=cat_relu, in_sums=cat_sums,
-                                    want_sums=norm_first and j < len(net.decoders) - 1)
+                                    want_sums=norm_first and j < len(net.decoders) - 1, up_src=up_src)
     if tape is not None:
         tape.append(("skips", skips, relu))
     return x

@@ -270,9 +270,9 @@ def conv_bwd_data(dy: CL, wp_bwd: torch.Tensor, k, mask: Optional[CL] = None,
         call("b200_conv_bwd_data", C.byref(d), _p(dy.buf), _p(wp_bwd),
              _p(None if mask is None else mask.buf), _p(out.buf), _stream())
         return out
+    cs = colstats_buffer(dy.n, c_in, dy.device)
     if dot is not None:
         assert dot.c == c_in and dot.dims == out.dims
-    cs = colstats_buffer(dy.n, c_in, dy.device)
     call("b200_conv_bwd_data_stats", C.byref(d), _p(dy.buf), _p(wp_bwd),
          _p(None if mask is None else mask.buf), _p(out.buf), _stats_kind(stats, dot),
          _p(None if dot is None else dot.buf), 0 if dot is None else dot.ctot,
@@ -636,10 +636,22 @@ def gn_bwd_fused(x: CL, groups, stats, gamma, dy: CL, colstats: torch.Tensor,
     return out, dgamma, dbeta
 
 
+def gn_apply_up(cat: CL, cs: int, low: CL, groups, stats, gamma, beta, relu: bool, out: Optional[CL] = None) -> CL:
+    """GroupNorm (+ ReLU) of a decoder concat whose channels [cs, c) are the nearest 1x/2x up-sampling of ``low``:
+    only the skip half of ``cat`` is read, the up-sampled half is never written to memory."""
+    if out is None:
+        out = cat.new_like()
+    fd, fh, fw = cat.d // low.d, cat.h // low.h, cat.w // low.w
+    call("b200_gn_apply_up", low.n, low.d, low.h, low.w, fd, fh, fw, cs, low.c, groups, cat.slice(0, cs).view(),
+         low.view(), _p(stats), _p(gamma), _p(beta), int(relu), out.view(), _stream())
+    return out
+
+
 def gn_bwd_fused_up(x: CL, groups, stats, gamma, dy: CL, colstats: torch.Tensor, cs: int, low_dims,
-                    mask_relu: bool = False):
+                    mask_relu: bool = False, x_low: Optional[CL] = None, beta_if_y: Optional[torch.Tensor] = None):
     """GroupNorm backward over a decoder concat (skip | nearest-upsampled) with the up-sampling backward folded
-    in: returns (dskip full resolution (cs channels), dlow at the source resolution, dgamma, dbeta)."""
+    in: returns (dskip full resolution (cs channels), dlow at the source resolution, dgamma, dbeta).  ``x_low``:
+    the low-resolution source when the forward (gn_apply_up) left the up-sampled half of ``x`` unwritten."""
     n, ld, lh, lw = low_dims
     cx = x.c - cs
     fd, fh, fw = x.d // ld, x.h // lh, x.w // lw
@@ -650,7 +662,9 @@ def gn_bwd_fused_up(x: CL, groups, stats, gamma, dy: CL, colstats: torch.Tensor,
     scratch = torch.empty(x.n * groups * 2, dtype=torch.float32, device=x.device)
     call("b200_gn_bwd_fused_up", n, ld, lh, lw, fd, fh, fw, cs, cx, groups, x.view(), _p(stats), _p(gamma),
          dy.view(), dskip.view(), dlow.view(), _p(dgamma), _p(dbeta), _p(colstats), _p(scratch), int(mask_relu),
-         _stream())
+         _NULL_VIEW if x_low is None else x_low.view(), _p(beta_if_y), _stream())
+    if beta_if_y is not None:
+        _lib.launch_count += 1      # + the (normally idle) direct dgamma kernel
     return dskip, dlow, dgamma, dbeta
 
 

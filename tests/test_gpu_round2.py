@@ -647,3 +647,96 @@ def test_gpu_augmentations_vs_reference_golden(B):
     assert y.shape == big.shape and torch.isfinite(y).all() and not torch.equal(y, big)
     n = A.AdditiveGaussianNoise(np.random.RandomState(0), execution_probability=1.0)(big)
     assert n.shape == big.shape and (n - big).std().item() > 0
+
+
+# --------------------------------------------------------------- decoder concat whose up-sampled half is never written
+def test_gn_apply_up_and_its_backward_match_the_materialised_concat(B):
+    """b200_gn_apply_up == nearest up-sampling + b200_gn_apply on the written concat (bit-exact: same arithmetic);
+    b200_gn_bwd_fused_up fed with (sum dy, sum dy * y) and the low-resolution tensor == the same backward fed with
+    (sum dy, sum dy * x) and the written concat — including channels whose gamma is 0 or tiny against beta, whose
+    dgamma comes from the direct reduction."""
+    from mdeical_image_segmentation_b200 import ops
+    g = torch.Generator().manual_seed(31)
+    for dims, low_dims in (((2, 16, 24, 16), (8, 12, 8)), ((2, 1, 32, 24), (1, 16, 12)), ((1, 8, 16, 16), (8, 8, 16))):
+        n, d, h, w = dims
+        cs, cx, groups = 32, 64, 8
+        skip = torch.randn((n, cs, d, h, w), generator=g).cuda()
+        low = torch.randn((n, cx) + low_dims, generator=g).relu().cuda()
+        cat = ops.CL.empty(n, d, h, w, cs + cx, skip.device)
+        ops.from_nchw(skip, out=cat.slice(0, cs))
+        low_cl = ops.from_nchw(low)
+        full = ops.CL.empty(n, d, h, w, cs + cx, skip.device)
+        ops.copy_channels(cat.slice(0, cs), full.slice(0, cs))
+        ops.upsample_nearest_fwd(low_cl, (d, h, w), out=full.slice(cs, cx))
+        cat.buf.view(-1, cs + cx)[:, cs:] = float("nan")      # the up-sampled half of `cat` is never written: poison it
+        stats = ops.gn_stats(full, groups, 1e-5)
+        gamma = (1.0 + 0.3 * torch.randn(cs + cx, generator=g)).cuda()
+        beta = (0.2 * torch.randn(cs + cx, generator=g)).cuda()
+        gamma[3], gamma[40], beta[40] = 0.0, 1e-3, 0.5        # degenerate channels: skip half, up-sampled half
+        gamma[70], beta[70] = 0.0, 0.0
+        for relu in (False, True):
+            want = ops.gn_apply(full, groups, stats, gamma, beta, relu)
+            got = ops.gn_apply_up(cat, cs, low_cl, groups, stats, gamma, beta, relu)
+            assert torch.equal(want.dense(), got.dense()), (dims, relu)
+        y = ops.gn_apply_up(cat, cs, low_cl, groups, stats, gamma, beta, False)
+        # dgrad of a 3x3(x3) conv 96 <- 64 with (sum dx, sum dx * .) in its epilogue
+        k = (3 if d > 1 else 1, 3, 3)
+        wt = (0.05 * torch.randn((64, cs + cx) + k, generator=g)).cuda()
+        _, wp_bwd, kk = ops.conv_repack_weight(wt, need_bwd=True)
+        dy = ops.from_nchw(torch.randn((n, 64, d, h, w), generator=g).cuda())
+        dx0, s_x = ops.conv_bwd_data(dy, wp_bwd, kk, impl=1, stats="sum", dot=full)
+        dx1, s_y = ops.conv_bwd_data(dy, wp_bwd, kk, impl=1, stats="sum", dot=y)
+        assert torch.equal(dx0.dense(), dx1.dense())
+        for mask in (False, True):
+            a = ops.gn_bwd_fused_up(full, groups, stats, gamma, dx0, s_x, cs, (n,) + low_dims, mask_relu=mask)
+            b = ops.gn_bwd_fused_up(cat, groups, stats, gamma, dx1, s_y, cs, (n,) + low_dims, mask_relu=mask,
+                                    x_low=low_cl, beta_if_y=beta)
+            for name, u, v in zip(("dskip", "dlow", "dgamma", "dbeta"), a, b):
+                u, v = (u.dense().float(), v.dense().float()) if isinstance(u, ops.CL) else (u, v)
+                assert torch.isfinite(v).all(), (dims, name)
+                assert rel_l2(v.cpu(), u.cpu()) < 1e-2, (dims, mask, name, rel_l2(v.cpu(), u.cpu()))
+            dg_a, dg_b = a[2].cpu(), b[2].cpu()
+            for ch in (3, 40, 70):       # the direct reduction is as exact as the reference path
+                assert abs(dg_a[ch] - dg_b[ch]) <= 2e-3 * abs(dg_a[ch]) + 1e-3 * dg_a.abs().mean(), (dims, ch)
+
+
+@pytest.mark.parametrize("dims", [(2, 1, 32, 32, 32), (1, 1, 24, 40, 16)])
+def test_unet3d_with_and_without_the_unwritten_upsampled_half(B, dims):
+    """UNet3D gcr + nearest: the forward that never writes the up-sampled half of the decoder concats
+    (engine.FOLD_UPSAMPLE_FWD) against the one that does — same logits bit for bit, same gradients up to the
+    summation order of the fused statistics — and against the fp32 oracle."""
+    from mdeical_image_segmentation_b200 import engine
+    torch.manual_seed(41)
+    net = B.UNet3D(1, 2, f_maps=[16, 32, 64], num_groups=4, layer_order="gcr").cuda().train()
+    sd = {k: v.detach().cpu().clone() for k, v in net.state_dict().items()}
+    g = torch.Generator().manual_seed(42)
+    x = torch.randn(dims, generator=g)
+    t = (torch.rand((dims[0], 2) + dims[2:], generator=g) > 0.6).float()
+    runs = {}
+    old = engine.FOLD_UPSAMPLE_FWD
+    try:
+        for fold in (True, False):
+            engine.FOLD_UPSAMPLE_FWD = fold
+            net.zero_grad(set_to_none=True)
+            out = net(x.cuda())
+            loss = B.BCEDiceLoss(1.0, 1.0)(out, t.cuda())
+            loss.backward()
+            runs[fold] = (out.detach().clone(), torch.cat([p.grad.flatten() for p in net.parameters()]).clone())
+            with torch.no_grad():
+                net.eval()
+                assert torch.equal(net(x.cuda()), out.detach())     # inference path folds the same way
+                net.train()
+    finally:
+        engine.FOLD_UPSAMPLE_FWD = old
+    assert torch.equal(runs[True][0], runs[False][0])
+    # not bit-equal: the fused statistics are fp64 atomics of fp32 partials (order varies run to run), and a random-init
+    # gradient amplifies a flipped bf16 rounding — two runs of the SAME setting differ as much (measured 1e-7 .. 1.4e-3)
+    assert rel_l2(runs[True][1].cpu(), runs[False][1].cpu()) < 5e-3
+    for k, v in sd.items():
+        if v.is_floating_point() and "running" not in k:
+            v.requires_grad_(True)
+    ref = O.unet3d_forward(sd, x, training=True, num_levels=3, layer_order="gcr", num_groups=4, is3d=True)
+    O.bce_dice_loss(ref, t).backward()
+    gb = torch.cat([sd[k].grad.flatten() for k, _ in net.named_parameters()])
+    assert rel_l2(runs[True][0].cpu(), ref.detach()) < 5e-2
+    assert rel_l2(runs[True][1].cpu(), gb) < 0.3      # random init bound of test_gpu_more (strict one: trained tests)
