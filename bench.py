@@ -571,6 +571,7 @@ def run_sweep(args):
                          "h2d_bytes": xh.numel() * 4, "d2h_bytes": out.numel() * 4})
             del x, xh, out, oh
             torch.cuda.empty_cache()
+    serving = serving_rows(device, iters)
     head = next(r for r in rows if r["size"] == "128x128x128" and r["batch"] == 2)
     emit({
         "metric": "inference vols/s", "value": head["per_s"], "unit": "vols/s", "n_gpus": 1, "steps": iters,
@@ -582,7 +583,55 @@ def run_sweep(args):
         "e2e": {"value": head["e2e_per_s"], "unit": "vols/s", "h2d_bytes_per_step": head["h2d_bytes"],
                 "d2h_bytes_per_step": head["d2h_bytes"]},
         "gpu_launches": _lib.launch_count, "clocks": clocks.summary(), "roofline": None, "cpu_baseline": None,
-        "sweep": rows})
+        "sweep": rows, "serving": serving})
+
+
+def serving_rows(device, iters):
+    """Request latency of the serving core behind api/api.py's POST / (serving.SegmentationService): image file on
+    disk -> preprocessing (resize 256, centre-crop 224, normalise) -> bucketed CUDA-graph forward of UNet(3, 1) ->
+    mask on the device -> PNG written, path returned.  Wall-clock per handle() / handle_many() call, p50 / p99."""
+    import tempfile
+
+    import numpy as np
+    import mdeical_image_segmentation_b200 as B
+    try:
+        from PIL import Image
+    except ImportError:
+        return {"unavailable": "PIL is not installed"}
+    rows = []
+    with tempfile.TemporaryDirectory() as tmp:
+        rng = np.random.default_rng(0)
+        paths = []
+        for i in range(8):
+            path = os.path.join(tmp, f"img{i}.png")
+            Image.fromarray(rng.integers(0, 255, (300, 400, 3), dtype=np.uint8)).save(path)
+            paths.append(path)
+        net = B.UNet(3, 1).to(device).eval()
+        for graphs in (True, False):
+            svc = B.SegmentationService(net, os.path.join(tmp, "masks"), in_channels=3, max_batch=8, use_graphs=graphs)
+            for nreq in (1, 8):
+                reqs = [{"image_path": p} for p in paths[:nreq]]
+                for _ in range(3):
+                    ans = svc.handle_many(reqs)
+                assert all(a["status"] == 200 and os.path.exists(a["response"]) for a in ans)
+                svc.latencies_ms.clear()
+                for _ in range(max(iters, 20)):
+                    svc.handle_many(reqs)
+                lat = svc.latency_percentiles()
+                # the device part alone: preprocessed inputs -> masks on the host
+                inputs = [svc.build_input(p) for p in paths[:nreq]]
+                dev = []
+                for _ in range(max(iters, 20)):
+                    t0 = time.perf_counter()
+                    svc.predict_masks(inputs)
+                    dev.append((time.perf_counter() - t0) * 1e3)
+                dev.sort()
+                rows.append({"requests_per_call": nreq, "cuda_graphs": graphs, "n": lat["n"],
+                             "p50_ms": round(lat["p50_ms"], 3), "p99_ms": round(lat["p99_ms"], 3),
+                             "requests_per_s": round(nreq / (lat["p50_ms"] / 1e3), 1),
+                             "predict_p50_ms": round(dev[len(dev) // 2], 3),
+                             "predict_p99_ms": round(dev[min(len(dev) - 1, int(0.99 * len(dev)))], 3)})
+    return {"model": "UNet(3,1), 224x224 crop of a 300x400 PNG", "contract": "api/api.py:52-82", "rows": rows}
 
 
 # --------------------------------------------------------------------------------------- CPU arm
