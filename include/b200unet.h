@@ -311,6 +311,14 @@ int b200_gn_bwd_fused_up(int32_t n, int32_t ld, int32_t lh, int32_t lw, int32_t 
 int b200_gn_apply_up(int32_t n, int32_t ld, int32_t lh, int32_t lw, int32_t fd, int32_t fh, int32_t fw,
                      int32_t cs, int32_t cx, int32_t groups, b200_view xskip, b200_view xlow, const float* stats,
                      const float* gamma, const float* beta, int32_t relu, b200_view y, b200_stream_t stream);
+/* First layer of a 3-D U-Net on a ONE-channel volume, on the CUDA cores (replaces the forward of
+ * nn.Conv3d(1, 32, 3, padding=1), buildingblocks.py:116-162 with in_channels = 1; c_out = 32 only, every extent >= 2,
+ * B200_ERR_UNSUPPORTED otherwise — the caller then takes the zero-padded tensor-core path).
+ * x: channel 0 of a channels-last bf16 buffer (any ctot), wgt fp32 [32][27] (the module's own (32, 1, 3, 3, 3)),
+ * rounded to bf16 inside; y bf16 (n, d, h, w, 32) view; colstats fp64 [n][2][32] += (sum y, sum y^2) of the stored
+ * output, or NULL. */
+int b200_conv3d_c1_fwd(int32_t n, int32_t d, int32_t h, int32_t w, int32_t c_out, b200_view x, const float* wgt,
+                       const float* bias, int32_t relu, b200_view y, double* colstats, b200_stream_t stream);
 /* (mean, rstd) per (sample, group) from per-channel sums: sums fp64 [n][2][c] = (sum x, sum x^2) as
  * produced by b200_conv_fwd_stats (or b200_gn_stats' scratch) */
 int b200_gn_stats_finalize(int32_t n, int64_t spatial, int32_t c, int32_t groups, float eps,

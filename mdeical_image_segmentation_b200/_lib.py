@@ -60,6 +60,7 @@ SIGNATURES = {
     "b200_gn_bwd_fused": [_I, _L, _I, _I, View, _P, _P, View, View, _P, _P, _P, _P, _I, _P],
     "b200_gn_bwd_fused_up": [_I, _I, _I, _I, _I, _I, _I, _I, _I, _I, View, _P, _P, View, View, View, _P, _P, _P, _P,
                              _I, View, _P, _P],
+    "b200_conv3d_c1_fwd": [_I, _I, _I, _I, _I, View, _P, _P, _I, View, _P, _P],
     "b200_gn_apply_up": [_I, _I, _I, _I, _I, _I, _I, _I, _I, _I, View, View, _P, _P, _P, _I, View, _P],
     "b200_bn_bwd_red_from_sums": [_I, _I, _P, _P, _P, _P, _P],
     "b200_convt2x2_repack_weight": [_PT, _P, _P, _P, _P],

@@ -1,15 +1,16 @@
 // First layer of a 3-D U-Net on a ONE-channel volume (UNet3D(1, .): SingleConv1 of the first encoder,
-// model/unet3d/buildingblocks.py:116-162 with in_channels = 1): nn.Conv3d(1, 32, 3, padding=1) forward and its
-// weight gradient on the CUDA cores.
+// model/unet3d/buildingblocks.py:116-162 with in_channels = 1): nn.Conv3d(1, 32, 3, padding=1) forward on the CUDA
+// cores.
 //
 // On the tensor cores this layer runs with the input zero-padded to 16 channels — 15/16 of every MMA is padding and
-// an N = 32 MMA is operand-fetch bound on top (0.37 ms forward at 128^3 x 2, 317 TF/s of useful math), and its
-// weight gradient needs an im2col of the volume (0.34 ms) in front of a short-K GEMM (0.23 ms).  The real work is
-// 27 x 32 multiply-adds per voxel = 7.2 GFLOP per pass: 0.1 ms of fp32 FMA throughput.  Both kernels read the
-// volume from the channel-0 plane of the padded bf16 buffer the rest of the executor uses (2 of every 32 bytes:
-// 134 MB of sectors, 0.02 ms) and keep the numerics of the tensor-core path: bf16 operands (the filter is rounded
-// to bf16 as the packed filter is), fp32 accumulation, bf16 stored output, fp64 column statistics of the STORED
-// output for the norm that follows.
+// an N = 32 MMA is operand-fetch bound on top (0.37 ms at 128^3 x 2, 317 TF/s of useful math).  The real work is
+// 27 x 32 multiply-adds per voxel = 7.2 GFLOP: this kernel takes 0.30 ms with packed fp32x2 FMAs (ncu: 16 warps per
+// SM at 128 registers, issue-bound).  It reads the volume from the channel-0 plane of the padded bf16 buffer the rest
+// of the executor uses (2 of every 32 bytes: 134 MB of sectors, 0.02 ms) and keeps the numerics of the tensor-core
+// path: bf16 operands (the filter is rounded to bf16 as the packed filter is), fp32 accumulation, bf16 stored
+// output, fp64 column statistics of the STORED output for the norm that follows.
+// The matching CUDA-core WEIGHT GRADIENT (lane = output channel, the 3 x 3 x 3 window sliding through registers)
+// was written and measured at 0.59-0.62 ms against 0.48 ms for im2col + short-K tensor-core GEMM, and removed.
 #include "common.cuh"
 #include "../../include/b200unet.h"
 
@@ -61,7 +62,7 @@ __device__ __forceinline__ float warp_sum_by_channel(float (&v)[32], int lane) {
 // ------------------------------------------------------------------------------------------- forward
 // One thread = one (y, x) column of the tile: its 4 voxels along z, two at a time, 32 output channels each.
 // The filter sits in shared memory as [tap][32] fp32 (every lane reads the same float4: a broadcast).
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
     conv3d_c1_fwd_kernel(int n, int d, int h, int w, FView x, const float* __restrict__ wgt,
                          const float* __restrict__ bias, int relu, FView y, double* __restrict__ stats, int tiles_z,
                          int tiles_y, int tiles_x) {
@@ -85,10 +86,11 @@ __global__ void __launch_bounds__(256)
 #pragma unroll 1
   for (int pass = 0; pass < kTZ / 2; ++pass) {
     const int zo = pass * 2;
-    float acc[2][C];
+    // fp32x2 FMAs (FFMA2, sm_100): half the instructions of the scalar form for the same 27 x 32 x 2 products
+    float2 acc[2][C / 2];
 #pragma unroll
-    for (int c = 0; c < C; ++c) {
-      const float bv = bias ? bias[c] : 0.f;
+    for (int c = 0; c < C / 2; ++c) {
+      const float2 bv = bias ? make_float2(bias[2 * c], bias[2 * c + 1]) : make_float2(0.f, 0.f);
       acc[0][c] = bv;
       acc[1][c] = bv;
     }
@@ -96,23 +98,23 @@ __global__ void __launch_bounds__(256)
     for (int kh = 0; kh < 3; ++kh)
 #pragma unroll
       for (int kw = 0; kw < 3; ++kw) {
-        float in[4];
+        float2 in[4];
 #pragma unroll
-        for (int p = 0; p < 4; ++p) in[p] = s_in[zo + p][ly + kh][lx + kw];
+        for (int p = 0; p < 4; ++p) {
+          const float v = s_in[zo + p][ly + kh][lx + kw];
+          in[p] = make_float2(v, v);
+        }
 #pragma unroll
         for (int kd = 0; kd < 3; ++kd) {
           const float4* wrow = reinterpret_cast<const float4*>(s_w[(kd * 3 + kh) * 3 + kw]);
 #pragma unroll
           for (int q = 0; q < C / 4; ++q) {
             const float4 wv = wrow[q];
-            acc[0][4 * q] = fmaf(in[kd], wv.x, acc[0][4 * q]);
-            acc[0][4 * q + 1] = fmaf(in[kd], wv.y, acc[0][4 * q + 1]);
-            acc[0][4 * q + 2] = fmaf(in[kd], wv.z, acc[0][4 * q + 2]);
-            acc[0][4 * q + 3] = fmaf(in[kd], wv.w, acc[0][4 * q + 3]);
-            acc[1][4 * q] = fmaf(in[kd + 1], wv.x, acc[1][4 * q]);
-            acc[1][4 * q + 1] = fmaf(in[kd + 1], wv.y, acc[1][4 * q + 1]);
-            acc[1][4 * q + 2] = fmaf(in[kd + 1], wv.z, acc[1][4 * q + 2]);
-            acc[1][4 * q + 3] = fmaf(in[kd + 1], wv.w, acc[1][4 * q + 3]);
+            const float2 w01 = make_float2(wv.x, wv.y), w23 = make_float2(wv.z, wv.w);
+            acc[0][2 * q] = __ffma2_rn(in[kd], w01, acc[0][2 * q]);
+            acc[0][2 * q + 1] = __ffma2_rn(in[kd], w23, acc[0][2 * q + 1]);
+            acc[1][2 * q] = __ffma2_rn(in[kd + 1], w01, acc[1][2 * q]);
+            acc[1][2 * q + 1] = __ffma2_rn(in[kd + 1], w23, acc[1][2 * q + 1]);
           }
         }
       }
@@ -126,7 +128,7 @@ __global__ void __launch_bounds__(256)
       uint32_t pk[C / 2];
 #pragma unroll
       for (int c = 0; c < C; c += 2) {
-        float a0 = acc[v][c], a1 = acc[v][c + 1];
+        float a0 = acc[v][c / 2].x, a1 = acc[v][c / 2].y;
         if (relu) { a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f); }
         pk[c / 2] = pack_bf16x2(a0, a1);
         if (stats) {
@@ -158,82 +160,6 @@ __global__ void __launch_bounds__(256)
   }
 }
 
-// ------------------------------------------------------------------------------------------- weight gradient
-// dw[co][tap] += sum_pos dy[pos][co] * x[pos + tap],  region[r][co] += sum_{pos in region r} dy[pos][co]
-// where region r = (rz * 3 + ry) * 3 + rx and r? = 0 on the first plane / row / column, 2 on the last, 1 between:
-// the weight gradient of an all-ones input channel (what the first norm's parameter gradients are made of,
-// engine._plant_ones) and the bias gradient are sums of region totals, formed by the caller.
-// Lane = output channel.  A warp walks rows of 32 positions along x; the 3 x 3 x 3 window of the volume slides
-// through registers (9 broadcast shared-memory loads per position), the row's 32 dy values are fetched up front.
-__global__ void __launch_bounds__(256)
-    conv3d_c1_wgrad_kernel(int n, int d, int h, int w, FView x, FView dy, float* __restrict__ dw,
-                           float* __restrict__ region, int tiles_z, int tiles_y, int tiles_x, int total) {
-  constexpr int C = 32;
-  __shared__ float s_in[kHZ][kHY][kHX];
-  __shared__ float s_dw[27][C];
-  __shared__ float s_reg[27][C];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int i = threadIdx.x; i < 27 * C; i += blockDim.x) { s_dw[i / C][i % C] = 0.f; s_reg[i / C][i % C] = 0.f; }
-  float acc[27];
-#pragma unroll
-  for (int k = 0; k < 27; ++k) acc[k] = 0.f;
-  for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
-    int t = tile;
-    const int tx = t % tiles_x; t /= tiles_x;
-    const int ty = t % tiles_y; t /= tiles_y;
-    const int tz = t % tiles_z;
-    const int b = t / tiles_z;
-    const int z0 = tz * kTZ, y0 = ty * kTY, x0 = tx * kTX;
-    __syncthreads();                       // the previous tile's readers are done with s_in
-    load_halo(s_in, x, b, d, h, w, z0, y0, x0);
-    __syncthreads();
-#pragma unroll 1
-    for (int r = warp; r < kTZ * kTY; r += 8) {
-      const int zz = r / kTY, yy = r % kTY;
-      const int gz = z0 + zz, gy = y0 + yy;
-      if (gz >= d || gy >= h) continue;
-      const long rowpos = (((long)b * d + gz) * h + gy) * w + x0;
-      float g[kTX];
-#pragma unroll
-      for (int xx = 0; xx < kTX; ++xx)
-        g[xx] = (x0 + xx < w) ? __bfloat162float(*dy.at(rowpos + xx, lane)) : 0.f;
-      float c0[9], c1[9], c2[9];
-#pragma unroll
-      for (int k = 0; k < 9; ++k) { c1[k] = s_in[zz + k / 3][yy + k % 3][0]; c2[k] = s_in[zz + k / 3][yy + k % 3][1]; }
-      float r0 = 0.f, r1 = 0.f, r2 = 0.f;
-#pragma unroll
-      for (int xx = 0; xx < kTX; ++xx) {
-#pragma unroll
-        for (int k = 0; k < 9; ++k) { c0[k] = c1[k]; c1[k] = c2[k]; c2[k] = s_in[zz + k / 3][yy + k % 3][xx + 2]; }
-        const float gv = g[xx];
-#pragma unroll
-        for (int k = 0; k < 9; ++k) {
-          acc[k * 3] = fmaf(gv, c0[k], acc[k * 3]);
-          acc[k * 3 + 1] = fmaf(gv, c1[k], acc[k * 3 + 1]);
-          acc[k * 3 + 2] = fmaf(gv, c2[k], acc[k * 3 + 2]);
-        }
-        const int gx = x0 + xx;
-        if (gx == 0) r0 += gv;
-        else if (gx == w - 1) r2 += gv;
-        else r1 += gv;                      // (gx >= w contributes gv == 0)
-      }
-      const int rz = gz == 0 ? 0 : (gz == d - 1 ? 2 : 1), ry = gy == 0 ? 0 : (gy == h - 1 ? 2 : 1);
-      const int rbase = (rz * 3 + ry) * 3;
-      atomicAdd(&s_reg[rbase][lane], r0);
-      atomicAdd(&s_reg[rbase + 1][lane], r1);
-      atomicAdd(&s_reg[rbase + 2][lane], r2);
-    }
-  }
-#pragma unroll
-  for (int k = 0; k < 27; ++k) atomicAdd(&s_dw[k][lane], acc[k]);
-  __syncthreads();
-  for (int i = threadIdx.x; i < 27 * C; i += blockDim.x) {
-    const int k = i / C, co = i % C;
-    atomicAdd(dw + co * 27 + k, s_dw[k][co]);
-    if (region && s_reg[k][co] != 0.f) atomicAdd(region + k * C + co, s_reg[k][co]);
-  }
-}
-
 }  // namespace
 }  // namespace b200
 
@@ -252,22 +178,6 @@ int b200_conv3d_c1_fwd(int32_t n, int32_t d, int32_t h, int32_t w, int32_t c_out
   if (blocks > 0x7fffffffL) return B200_ERR_UNSUPPORTED;
   conv3d_c1_fwd_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(n, d, h, w, mk(x), wgt, bias, relu, mk(y),
                                                                           colstats, tz, ty, tx);
-  B200_LAUNCH_CHECK();
-  return B200_OK;
-}
-
-int b200_conv3d_c1_bwd_weight(int32_t n, int32_t d, int32_t h, int32_t w, int32_t c_out, b200_view x, b200_view dy,
-                              float* dw, float* region, b200_stream_t stream) {
-  if (c_out != 32 || !x.ptr || !dy.ptr || !dw) return B200_ERR_UNSUPPORTED;
-  if (d < 2 || h < 2 || w < 2) return B200_ERR_UNSUPPORTED;
-  if ((long)n * d * h * w <= 0) return B200_OK;
-  const int tz = (d + kTZ - 1) / kTZ, ty = (h + kTY - 1) / kTY, tx = (w + kTX - 1) / kTX;
-  const long total = (long)n * tz * ty * tx;
-  if (total > 0x7fffffffL) return B200_ERR_UNSUPPORTED;
-  const long cap = (long)sm_count() * 4;
-  const int grid = (int)(total < cap ? total : cap);
-  conv3d_c1_wgrad_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(n, d, h, w, mk(x), mk(dy), dw, region, tz, ty, tx,
-                                                                 (int)total);
   B200_LAUNCH_CHECK();
   return B200_OK;
 }

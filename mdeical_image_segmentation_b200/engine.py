@@ -225,6 +225,16 @@ def _im2col_weight_grad(dw2: torch.Tensor, w: torch.Tensor, c_col: Optional[int]
 
 
 FIRST_NORM_FROM_WGRAD = os.environ.get("B200_FIRST_NORM_FROM_WGRAD", "1") != "0"   # A/B knob
+FIRST_LAYER_DIRECT = os.environ.get("B200_FIRST_LAYER_DIRECT", "1") != "0"         # A/B knob
+
+
+def _first_layer_direct(conv: nn.Module, c_real: int, x: CL) -> bool:
+    """nn.Conv3d(1, 32, 3, padding=1) on a volume stored in channel 0 of a padded buffer: the CUDA-core forward of
+    csrc/first_layer.cu (0.37 -> 0.30 ms at 128^3 x 2) instead of the zero-padded tensor-core one.  The weight
+    gradient stays on the tensor cores (im2col + short-K GEMM)."""
+    w = conv.weight
+    return (FIRST_LAYER_DIRECT and c_real == 1 and x.coff == 0 and w.dim() == 5 and tuple(w.shape) == (32, 1, 3, 3, 3)
+            and min(x.d, x.h, x.w) >= 2)
 
 
 def _plant_ones(dst: CL, tape, i: int, letters: str, nxt: int, fuse_relu: bool, conv) -> int:
@@ -289,6 +299,18 @@ def single_conv_fwd(x: CL, spec: LayerSpec, training: bool, tape: Optional[list]
             conv = spec.conv
             w = conv.weight.detach()
             xin = cur
+            if cur.zpad and _first_layer_direct(conv, cur.c, cur):
+                bias = None if conv.bias is None else conv.bias.detach().float().contiguous()
+                need = (letters[nxt] in "gb") if nxt < len(letters) else want_sums
+                y, cur_sums = ops.conv3d_c1_fwd(cur, w, bias, fuse_relu, out=dst, stats=need)
+                if tape is not None:
+                    tape.append(("conv", cur.widened(), conv, None, (3, 3, 3), y if fuse_relu else None, cur.zpad,
+                                 in_relu and i == 0, ones_ch))
+                ones_ch = -1
+                cur = y
+                out_relu = fuse_relu
+                i = nxt
+                continue
             pk = _PACKS.get(id(conv)) if _PACKS is not None else None
             if pk is not None and pk[0] == w.shape[1] + cur.zpad and (pk[2] is not None or tape is None):
                 wp_fwd, wp_bwd, k = pk[1], pk[2], pk[3]      # pre-packed (and channel-padded) by the one launch
@@ -488,6 +510,9 @@ def single_conv_bwd(dy: CL, recs: list, grads: Grads, need_dx: bool = True, prem
                 return None, False, None
             if last and not need_dx:
                 return None, False, None
+            if wp_bwd is None:      # forward ran on the CUDA-core first-layer kernel: pack for the data gradient now
+                wpad = torch.nn.functional.pad(conv.weight.detach(), (0, 0) * (conv.weight.dim() - 2) + (0, zpad))
+                _, wp_bwd, k = ops.conv_repack_weight(wpad, need_bwd=True)
             # the fused mask must have the layout of the (dense) dx the kernel writes
             fuse = bool(mask_in and not zpad and x_in.is_full())
             want, dot = _consumer_plan(nxt_consumer, fuse)

@@ -293,6 +293,19 @@ def conv_bwd_weight(x: CL, dy: CL, k, w_shape, impl: int = 0, bias_grad: bool = 
     return dw
 
 
+def conv3d_c1_fwd(x: CL, w: torch.Tensor, bias: Optional[torch.Tensor], relu: bool, out: Optional[CL] = None,
+                  stats: bool = False):
+    """nn.Conv3d(1, 32, 3, padding=1) on the volume in channel 0 of ``x`` (CUDA cores, csrc/first_layer.cu);
+    returns (y, fp64 [n][2][32] column statistics of y or None)."""
+    c_out = w.shape[0]
+    if out is None:
+        out = CL.empty(x.n, x.d, x.h, x.w, c_out, x.device)
+    cs = colstats_buffer(x.n, c_out, x.device) if stats else None
+    call("b200_conv3d_c1_fwd", x.n, x.d, x.h, x.w, c_out, x.view(), _p(w.detach().float().contiguous()), _p(bias),
+         int(relu), out.view(), _p(cs), _stream())
+    return out, cs
+
+
 # ------------------------------------------------------------------------------------- convT 2x2 s2
 def convt_repack_weight(w: torch.Tensor):
     require_cuda(w)

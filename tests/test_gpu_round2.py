@@ -740,3 +740,59 @@ def test_unet3d_with_and_without_the_unwritten_upsampled_half(B, dims):
     gb = torch.cat([sd[k].grad.flatten() for k, _ in net.named_parameters()])
     assert rel_l2(runs[True][0].cpu(), ref.detach()) < 5e-2
     assert rel_l2(runs[True][1].cpu(), gb) < 0.3      # random init bound of test_gpu_more (strict one: trained tests)
+
+
+# --------------------------------------------------------------------------- first layer on the CUDA cores (C_in = 1)
+@pytest.mark.parametrize("dims", [(2, 8, 16, 32), (1, 5, 9, 37), (1, 2, 2, 2), (2, 12, 8, 70)])
+def test_first_layer_direct_kernel_vs_fp32_reference(B, dims):
+    """b200_conv3d_c1_fwd against F.conv3d on the same bf16-rounded operands: output within one bf16 rounding, and
+    its fp64 column statistics."""
+    from mdeical_image_segmentation_b200 import ops
+    n, d, h, w = dims
+    g = torch.Generator().manual_seed(sum(dims))
+    x = torch.randn((n, 1, d, h, w), generator=g).bfloat16().float()
+    wt = (0.3 * torch.randn((32, 1, 3, 3, 3), generator=g))
+    bias = torch.randn(32, generator=g)
+    xcl = ops.from_nchw(x.cuda(), pad=True)
+    assert xcl.c == 1 and xcl.zpad == 15
+    wr = wt.bfloat16().float()
+    for relu in (False, True):
+        ref = F.conv3d(x, wr, bias, padding=1)
+        ref = ref.relu() if relu else ref
+        y, cs = ops.conv3d_c1_fwd(xcl, wt.cuda(), bias.cuda(), relu, stats=True)
+        got = y.to_nchw().cpu()
+        assert (got - ref).abs().max() <= 2 ** -7 * ref.abs().max() + 1e-6, (dims, relu)
+        want_cs = torch.stack([got.double().sum(dim=(2, 3, 4)), got.double().square().sum(dim=(2, 3, 4))], 1)
+        assert torch.allclose(cs.cpu(), want_cs, rtol=1e-5, atol=1e-4)
+
+
+def test_first_layer_direct_path_matches_the_tensor_core_path(B):
+    """UNet3D(1, 2) f_maps 64: the network with engine.FIRST_LAYER_DIRECT on and off — logits within bf16 rounding of
+    each other, first-layer parameter gradients (conv weight, its norm's weight / bias) equal within tolerance."""
+    from mdeical_image_segmentation_b200 import engine
+    torch.manual_seed(51)
+    net = B.UNet3D(1, 2, f_maps=[64, 128], num_levels=2, num_groups=8, layer_order="gcr").cuda().train()
+    g = torch.Generator().manual_seed(52)
+    x = torch.randn((1, 1, 24, 32, 40), generator=g)
+    t = (torch.rand((1, 2, 24, 32, 40), generator=g) > 0.6).float()
+    runs = {}
+    old = engine.FIRST_LAYER_DIRECT
+    try:
+        for direct in (True, False):
+            engine.FIRST_LAYER_DIRECT = direct
+            net._b200_pack_plan = None           # the set of tensor-core filter packs differs between the two
+            net.zero_grad(set_to_none=True)
+            out = net(x.cuda())
+            B.BCEDiceLoss(1.0, 1.0)(out, t.cuda()).backward()
+            runs[direct] = (out.detach().clone(), {k: p.grad.clone() for k, p in net.named_parameters()})
+    finally:
+        engine.FIRST_LAYER_DIRECT = old
+    assert rel_l2(runs[True][0].cpu(), runs[False][0].cpu()) < 5e-3
+    # the two first convs differ in summation order only, but one flipped bf16 rounding of their output is amplified
+    # by the random-init network behind it: whole-gradient agreement, and a looser per-tensor bound
+    ga = torch.cat([v.flatten() for v in runs[True][1].values()]).cpu()
+    gb = torch.cat([v.flatten() for v in runs[False][1].values()]).cpu()
+    assert rel_l2(ga, gb) < 5e-2, rel_l2(ga, gb)
+    for k in runs[True][1]:
+        a, b = runs[True][1][k], runs[False][1][k]
+        assert (a - b).norm() <= 0.15 * b.norm() + 1e-3 * gb.norm(), (k, ((a - b).norm() / b.norm()).item())
