@@ -179,12 +179,13 @@ class ClockSampler:
 
 
 # --------------------------------------------------------------------------------------- B200 arm
-def build_model(w, device):
+def build_model(w, device, capturable=False):
+    """capturable: optimizer state on the device, so that optimizer.step() can sit inside a CUDA graph."""
     import mdeical_image_segmentation_b200 as B
     torch.manual_seed(0)
     if w["kind"] == "2d":
         model = B.UNetModel(B.UNetConfig(w["cin"], w["cout"], w.get("unet_type", "UNet"))).to(device).train()
-        opt = torch.optim.AdamW(model.parameters(), lr=1e-4, weight_decay=1e-3, fused=True)
+        opt = torch.optim.AdamW(model.parameters(), lr=1e-4, weight_decay=1e-3, fused=True, capturable=capturable)
 
         def step_fn(x, y):
             return model(images=x, labels=y).loss
@@ -196,7 +197,7 @@ def build_model(w, device):
             net = B.UNet3D(w["cin"], w["cout"], layer_order=w["order"], upsample=w["upsample"]).to(device).train()
         crit = B.DiceLoss(normalization="sigmoid") if w.get("loss") == "dice" else B.BCEDiceLoss(1.0, 1.0)
         model = net
-        opt = torch.optim.Adam(model.parameters(), lr=1e-4, fused=True)
+        opt = torch.optim.Adam(model.parameters(), lr=1e-4, fused=True, capturable=capturable)
 
         def step_fn(x, y):
             return crit(net(x), y)
@@ -300,17 +301,34 @@ def measure(args, name, w, steps, warmup, device, world, rank, full):
     from mdeical_image_segmentation_b200.parallel import DataParallelUNet
 
     batch = (args.batch if full else 0) or w["batch"]
-    model, opt, step_fn = build_model(w, device)
+    want_graph = args.graph and world == 1
+    model, opt, step_fn = build_model(w, device, capturable=want_graph)
     if world > 1:
         DataParallelUNet(model)
     x, y = make_batch(w, batch, 1234 + rank, device)
 
-    def one_step(xb, yb):
+    def eager_step(xb, yb):
         opt.zero_grad(set_to_none=True)
         loss = step_fn(xb, yb)
         loss.backward()
         opt.step()
         return loss
+
+    # One process, one GPU: the whole step (forward, loss, backward, optimizer) is captured once and replayed with a
+    # single launch per step — GraphedTrainStep, the package's public API for a fixed-shape training loop.  The eager
+    # loop needs ~20 ms of host enqueue work per 24 ms cfg3 step, so any slow host moment starves the GPU.
+    gstep = None
+    if want_graph:
+        import mdeical_image_segmentation_b200 as B
+        try:
+            gstep = B.GraphedTrainStep(step_fn, opt, (x, y), warmup=max(warmup, 3))
+            x, y = gstep.static_in
+        except Exception as e:   # noqa: BLE001 — a workload that cannot be captured is timed eagerly, and says so
+            print(f"[bench] {name}: CUDA-graph capture failed ({type(e).__name__}: {str(e)[:200]}); eager steps",
+                  file=sys.stderr)
+            gstep = None
+            torch.cuda.synchronize()
+    one_step = gstep if gstep is not None else eager_step
 
     def barrier():
         if world > 1:
@@ -329,7 +347,7 @@ def measure(args, name, w, steps, warmup, device, world, rank, full):
             loss = one_step(x, y)
         e1.record()
         barrier()
-    launches = _lib.launch_count
+    launches = _lib.launch_count if gstep is None else steps * gstep.launches_per_step
     ms = torch.tensor([e0.elapsed_time(e1)], device=device)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
@@ -337,6 +355,7 @@ def measure(args, name, w, steps, warmup, device, world, rank, full):
     pk = peaks()
     step_tf = w["train_tf"] * batch
     res = {"value": world * batch / (ms_step / 1e3), "ms_step": ms_step, "batch": batch, "launches": launches,
+           "step_launch": "one CUDA graph replay per step (GraphedTrainStep)" if gstep is not None else "eager",
            "clocks": clocks.summary(), "final_loss": float(loss.item()),
            "step": {"algorithmic_tflop_per_step": round(step_tf, 2),
                     "step_tflops": round(step_tf / (ms_step / 1e3), 1),
@@ -396,7 +415,7 @@ def measure(args, name, w, steps, warmup, device, world, rank, full):
     side_was = _engine.WGRAD_STREAM
     _engine.WGRAD_STREAM = False
     for _ in range(prof.steps):
-        one_step(x, y)
+        eager_step(x, y)
     _engine.WGRAD_STREAM = side_was
     _lib.profile_hook = None
     barrier()
@@ -463,8 +482,8 @@ def run_b200(args, w):
                             full=False)
                 extra[name] = {"workload": WORKLOADS[name]["desc"], "value": round(r["value"], 3),
                                "unit": WORKLOADS[name]["unit"], "ms_per_step": round(r["ms_step"], 3),
-                               "per_gpu_batch": r["batch"], "gpu_launches": r["launches"], **r["step"],
-                               "clocks": r["clocks"]}
+                               "per_gpu_batch": r["batch"], "gpu_launches": r["launches"],
+                               "step_launch": r["step_launch"], **r["step"], "clocks": r["clocks"]}
             except Exception as e:   # an extra must never take the headline line down with it
                 extra[name] = {"error": f"{type(e).__name__}: {e}"[:300]}
             release_device_memory()
@@ -481,8 +500,8 @@ def run_b200(args, w):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
             "data": "synthetic",
             "config": bench_config(args.workload, w, batch, world),
-            "e2e": head["e2e"], "gpu_launches": head["launches"], "clocks": head["clocks"],
-            "roofline": head["roofline"], "cpu_baseline": cpu, "breakdown": head["breakdown"],
+            "e2e": head["e2e"], "gpu_launches": head["launches"], "step_launch": head["step_launch"],
+            "clocks": head["clocks"], "roofline": head["roofline"], "cpu_baseline": cpu, "breakdown": head["breakdown"],
             "final_loss": head["final_loss"], "extra": extra,
         }
         emit(out)
@@ -496,7 +515,8 @@ def bench_config(name, w, batch, world):
             "global_batch": batch * world, "parallelism": f"dp{world}",
             "l2": "per-step inputs + activations far exceed the 126 MB L2 (no flush needed)",
             "streams": "weight gradients on a side stream in the timed steps; the roofline / "
-                       "breakdown step runs single-stream",
+                       "breakdown step runs single-stream and eager",
+            "launch": "N = 1: the whole step is one CUDA-graph replay (GraphedTrainStep); N > 1: eager steps",
             "reference_sample": REFERENCE_SAMPLE[w["kind"]]}
 
 
@@ -781,6 +801,8 @@ def main():
                     help="skip the short cfg2 / cfg3p measurements nested under 'extra'")
     ap.add_argument("--batch", type=int, default=0)
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-graph", dest="graph", action="store_false",
+                    help="time eager steps at N=1 too (default: one CUDA-graph replay per step at N=1)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup

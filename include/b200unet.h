@@ -163,6 +163,11 @@ typedef struct b200_view {
  * buildingblocks.py:409-413. pool_d = 1 keeps D (2D pooling). */
 int b200_maxpool2_fwd(int32_t n, int32_t d, int32_t h, int32_t w, int32_t c, int32_t pool_d,
                       b200_view x, b200_view y, b200_stream_t stream);
+/* the same pooling, which also accumulates the per-sample per-channel (sum y, sum y^2) of its output into
+ * sums fp64 [n][2][c] (zeroed by the caller) — the statistics of the GroupNorm that opens the next encoder level
+ * (buildingblocks.py:73-103, 409-425).  Even extents and 8-channel aligned views only (B200_ERR_UNSUPPORTED else). */
+int b200_maxpool2_fwd_sums(int32_t n, int32_t d, int32_t h, int32_t w, int32_t c, int32_t pool_d, b200_view x,
+                           b200_view y, double* sums, b200_stream_t stream);
 /* dx fully written; ties go to the first maximum in (d,h,w) scan order, as ATen does.
  * add (ptr may be NULL): a second gradient of x's shape summed in (the skip branch of the U).
  * mask_relu != 0: x is a ReLU output; dx is zeroed where x <= 0 (its producer's ReLU backward). */

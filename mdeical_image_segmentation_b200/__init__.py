@@ -3,7 +3,7 @@ a-green-hand-jack/mdeical_image_segmentation: drop-in ``nn.Module`` classes, los
 arithmetic runs in hand-written CUDA (tcgen05/TMEM/TMA implicit-GEMM convolutions + HBM-bound fused
 kernels) behind a C ABI (``include/b200unet.h``).  There is no CPU / PyTorch-eager fallback."""
 from . import _lib, augment, metrics  # noqa: F401
-from .graph import GraphedInference
+from .graph import GraphedInference, GraphedTrainStep
 from .unet3plus import UNet_3Plus, UNet_3Plus_DeepSup, UNet_3Plus_DeepSup_CGM
 from .losses import (BCEDiceLoss, BCEWithLogitsLoss, CrossEntropyLoss, DiceLoss, F1Loss, IoULoss, MSSSIMLoss,
                      SegmentationLoss, compute_per_channel_dice, flatten, get_loss_criterion)

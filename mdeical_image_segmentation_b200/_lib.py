@@ -74,6 +74,7 @@ SIGNATURES = {
     "b200_deconv3s2_bwd_data": [_PD, _P, _P, _P, _P],
     "b200_deconv3s2_bwd_weight": [_PD, _P, _P, _P, _P],
     "b200_maxpool2_fwd": [_I, _I, _I, _I, _I, _I, View, View, _P],
+    "b200_maxpool2_fwd_sums": [_I, _I, _I, _I, _I, _I, View, View, _P, _P],
     "b200_maxpool2_bwd": [_I, _I, _I, _I, _I, _I, View, View, View, View, _I, _P],
     "b200_upsample_nearest_fwd": [_I, _I, _I, _I, _I, _I, _I, _I, View, View, _P],
     "b200_upsample_nearest_bwd": [_I, _I, _I, _I, _I, _I, _I, _I, View, View, _P],

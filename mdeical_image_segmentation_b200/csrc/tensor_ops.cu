@@ -1299,6 +1299,41 @@ __global__ void __launch_bounds__(256, 4)
   };
   column_pass<V, 2, true, double>(spatial, c, chunk, f, outs);
 }
+// 2x max-pool forward that also leaves the per-sample per-channel (sum y, sum y^2) of its output in sums
+// fp64 [n][2][c]: the GroupNorm that opens the next encoder level (`gcr`) then needs no statistics pass over y.
+template <int PD>
+__global__ void __launch_bounds__(256, 4)
+    maxpool_fwd_sums_kernel(int d, int h, int w, int c, long chunk, View x, View y, double* sums) {
+  const int b = blockIdx.z;
+  const int od = d / PD, oh = h / 2, ow = w / 2;
+  const long ospatial = (long)od * oh * ow;
+  double* outs[2] = {sums + (long)b * c * 2, sums + (long)b * c * 2 + c};
+  auto f = [&](long pos, int ch, float(*acc)[8]) {
+    const int xw = (int)(pos % ow), xh = (int)((pos / ow) % oh), xd = (int)(pos / ((long)ow * oh));
+    uint4 r[PD * 4];
+#pragma unroll
+    for (int q = 0; q < PD * 4; ++q) {
+      const int a = q >> 2, e = (q >> 1) & 1, g = q & 1;
+      r[q] = ldg_nc_v4(x.at((((long)b * d + xd * PD + a) * h + xh * 2 + e) * w + xw * 2 + g, ch));
+    }
+    uint4 o;
+#pragma unroll
+    for (int w2 = 0; w2 < 4; ++w2) {
+      float2 m = unpack_bf16x2((&r[0].x)[w2]);
+#pragma unroll
+      for (int q = 1; q < PD * 4; ++q) {
+        const float2 v = unpack_bf16x2((&r[q].x)[w2]);
+        m.x = fmaxf(m.x, v.x);
+        m.y = fmaxf(m.y, v.y);
+      }
+      (&o.x)[w2] = pack_bf16x2(m.x, m.y);
+      acc[0][2 * w2] += m.x; acc[0][2 * w2 + 1] += m.y;
+      acc[1][2 * w2] = fmaf(m.x, m.x, acc[1][2 * w2]); acc[1][2 * w2 + 1] = fmaf(m.y, m.y, acc[1][2 * w2 + 1]);
+    }
+    *reinterpret_cast<uint4*>(y.at((long)b * ospatial + pos, ch)) = o;
+  };
+  column_pass<8, 2, true, double>(ospatial, c, chunk, f, outs);
+}
 __global__ void gn_finalize_kernel(int n, int c, int groups, double count, float eps,
                                    const double* sums, float* stats) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1627,6 +1662,22 @@ int b200_maxpool2_fwd(int32_t n, int32_t d, int32_t h, int32_t w, int32_t c, int
   if (total <= 0) return B200_OK;
   const bool v = vec8(c, x) && vec8(c, y);
   DISPATCH_V(v, maxpool_fwd_kernel, GRID1D(total / (v ? 8 : 1)), n, d, h, w, c, pool_d, mk(x), mk(y));
+  return B200_OK;
+}
+int b200_maxpool2_fwd_sums(int32_t n, int32_t d, int32_t h, int32_t w, int32_t c, int32_t pool_d, b200_view x,
+                           b200_view y, double* sums, b200_stream_t stream) {
+  if (pool_d != 1 && pool_d != 2) return B200_ERR_BAD_ARG;
+  if (!sums) return B200_ERR_BAD_ARG;
+  if (!vec8(c, x) || !vec8(c, y) || d % pool_d || h % 2 || w % 2) return B200_ERR_UNSUPPORTED;
+  const long ospatial = (long)(d / pool_d) * (h / 2) * (w / 2);
+  if ((long)n * ospatial * c <= 0) return B200_OK;
+  dim3 grid;
+  long chunk;
+  column_grid(ospatial, c, 8, grid, chunk);
+  grid.z = n;
+  if (pool_d == 2) maxpool_fwd_sums_kernel<2><<<grid, 256, 0, (cudaStream_t)stream>>>(d, h, w, c, chunk, mk(x), mk(y), sums);
+  else maxpool_fwd_sums_kernel<1><<<grid, 256, 0, (cudaStream_t)stream>>>(d, h, w, c, chunk, mk(x), mk(y), sums);
+  B200_LAUNCH_CHECK();
   return B200_OK;
 }
 int b200_maxpool2_bwd(int32_t n, int32_t d, int32_t h, int32_t w, int32_t c, int32_t pool_d,

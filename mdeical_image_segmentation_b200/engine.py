@@ -770,10 +770,14 @@ def unet3d_forward(net, x_in: torch.Tensor, training: bool, tape: Optional[list]
     for i, enc in enumerate(net.encoders):
         if enc.pooling is not None:
             avg = getattr(enc, "pool_type", "max") == "avg"
-            pooled = (ops.avgpool_fwd if avg else ops.maxpool_fwd)(x, 2 if is3d else 1)
+            if not avg and norm_first and order[0] == "g":
+                # the statistics of the GroupNorm that opens this level ride in the pooling pass
+                pooled, pooled_sums = ops.maxpool_fwd_sums(x, 2 if is3d else 1)
+            else:
+                pooled, pooled_sums = (ops.avgpool_fwd if avg else ops.maxpool_fwd)(x, 2 if is3d else 1), None
             if tape is not None:
                 tape.append(("pool", x, relu, avg))
-            x, x_sums = pooled, None
+            x, x_sums = pooled, pooled_sums
         cs = enc.basic_module.SingleConv2.conv.out_channels
         dst = None
         if i < n_enc - 1:

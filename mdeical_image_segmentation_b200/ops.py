@@ -427,6 +427,17 @@ def maxpool_fwd(x: CL, pool_d: int, out: Optional[CL] = None) -> CL:
     return out
 
 
+def maxpool_fwd_sums(x: CL, pool_d: int):
+    """(pooled, fp64 [n][2][c] per-sample per-channel (sum, sum of squares) of the pooled tensor) in one pass, or
+    (pooled, None) where the fused kernel does not apply (odd extents, unaligned channel counts)."""
+    if x.d % pool_d or x.h % 2 or x.w % 2 or x.c % 8 or x.ctot % 8 or x.coff % 8:
+        return maxpool_fwd(x, pool_d), None
+    out = CL.empty(x.n, x.d // pool_d, x.h // 2, x.w // 2, x.c, x.device)
+    sums = colstats_buffer(x.n, x.c, x.device)
+    call("b200_maxpool2_fwd_sums", x.n, x.d, x.h, x.w, x.c, pool_d, x.view(), out.view(), _p(sums), _stream())
+    return out, sums
+
+
 def maxpool_bwd(x: CL, dy: CL, pool_d: int, add: Optional[CL] = None,
                 out: Optional[CL] = None, mask_relu: bool = False) -> CL:
     if out is None:

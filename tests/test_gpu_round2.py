@@ -796,3 +796,61 @@ def test_first_layer_direct_path_matches_the_tensor_core_path(B):
     for k in runs[True][1]:
         a, b = runs[True][1][k], runs[False][1][k]
         assert (a - b).norm() <= 0.15 * b.norm() + 1e-3 * gb.norm(), (k, ((a - b).norm() / b.norm()).item())
+
+
+def test_maxpool_with_fused_statistics(B):
+    """b200_maxpool2_fwd_sums: the pooled tensor bit-equal to b200_maxpool2_fwd, its (sum, sum of squares) per sample
+    and channel equal to a direct reduction; odd extents fall back to the plain kernel (no statistics)."""
+    from mdeical_image_segmentation_b200 import ops
+    g = torch.Generator().manual_seed(61)
+    for shape, pd in (((2, 16, 8, 12, 20), 2), ((3, 64, 1, 16, 24), 1), ((1, 8, 4, 6, 2), 2)):
+        x = ops.from_nchw(torch.randn(shape, generator=g).cuda())
+        want = ops.maxpool_fwd(x, pd)
+        got, sums = ops.maxpool_fwd_sums(x, pd)
+        assert torch.equal(want.dense(), got.dense())
+        y = got.dense().double()                                   # (n, d, h, w, c)
+        ref = torch.stack([y.sum(dim=(1, 2, 3)), y.square().sum(dim=(1, 2, 3))], 1)
+        assert torch.allclose(sums, ref, rtol=1e-6, atol=1e-6), (shape, (sums - ref).abs().max())
+    x = ops.from_nchw(torch.randn((1, 8, 5, 6, 7), generator=g).cuda())
+    got, sums = ops.maxpool_fwd_sums(x, 2)
+    assert sums is None and torch.equal(got.dense(), ops.maxpool_fwd(x, 2).dense())
+
+
+def test_graphed_train_step_matches_eager_steps(B):
+    """GraphedTrainStep (forward + loss + backward + optimizer in one CUDA graph) against the same steps run eagerly
+    from the same initial state: losses of 4 steps and the final parameters agree (the kernels and their order are
+    the same; only atomics order differs), and new inputs are honoured.  SGD with momentum: linear in the gradient
+    (Adam's first steps move every weight by lr * sign(g), which turns gradient noise around 0 into +-lr)."""
+    def make():
+        torch.manual_seed(71)
+        net = B.UNet3D(1, 1, f_maps=[16, 32, 64], num_groups=4, layer_order="gcr").cuda().train()
+        opt = torch.optim.SGD(net.parameters(), lr=0.05, momentum=0.9)
+        crit = B.BCEDiceLoss(1.0, 1.0)
+        return net, opt, (lambda x, y: crit(net(x), y))
+    g = torch.Generator().manual_seed(72)
+    xs = [torch.randn((2, 1, 32, 32, 32), generator=g).cuda() for _ in range(4)]
+    ys = [(torch.rand((2, 1, 32, 32, 32), generator=g) > 0.5).float().cuda() for _ in range(4)]
+    net_e, opt_e, fn_e = make()
+    losses_e = []
+    for x, y in zip(xs, ys):
+        opt_e.zero_grad(set_to_none=True)
+        l = fn_e(x, y)
+        l.backward()
+        opt_e.step()
+        losses_e.append(l.item())
+    net_g, opt_g, fn_g = make()
+    state = {k: v.clone() for k, v in net_g.state_dict().items()}
+    step = B.GraphedTrainStep(fn_g, opt_g, (xs[0], ys[0]))        # its warm-up steps move the parameters ...
+    net_g.load_state_dict(state)                                  # ... so restore them and the optimizer state
+    for st in opt_g.state.values():
+        for v in st.values():
+            if torch.is_tensor(v):
+                v.zero_()                                         # momentum buffers back to their initial state
+    assert step.launches_per_step > 50
+    losses_g = [step(x, y).item() for x, y in zip(xs, ys)]
+    assert max(abs(a - b) for a, b in zip(losses_e, losses_g)) < 2e-3, (losses_e, losses_g)
+    pe = torch.cat([p.detach().flatten() for p in net_e.parameters()])
+    pg = torch.cat([p.detach().flatten() for p in net_g.parameters()])
+    assert rel_l2(pg.cpu(), pe.cpu()) < 2e-3
+    with pytest.raises(ValueError):
+        step(xs[0][:1], ys[0][:1])
