@@ -301,7 +301,7 @@ def measure(args, name, w, steps, warmup, device, world, rank, full):
     from mdeical_image_segmentation_b200.parallel import DataParallelUNet
 
     batch = (args.batch if full else 0) or w["batch"]
-    want_graph = args.graph and world == 1
+    want_graph = args.graph
     model, opt, step_fn = build_model(w, device, capturable=want_graph)
     if world > 1:
         DataParallelUNet(model)
@@ -314,9 +314,10 @@ def measure(args, name, w, steps, warmup, device, world, rank, full):
         opt.step()
         return loss
 
-    # One process, one GPU: the whole step (forward, loss, backward, optimizer) is captured once and replayed with a
-    # single launch per step — GraphedTrainStep, the package's public API for a fixed-shape training loop.  The eager
-    # loop needs ~20 ms of host enqueue work per 24 ms cfg3 step, so any slow host moment starves the GPU.
+    # The whole step (forward, loss, backward with its bucketed gradient all-reduces at N > 1, optimizer) is captured
+    # once and replayed with a single launch per step — GraphedTrainStep, the package's public API for a fixed-shape
+    # training loop.  The eager loop needs ~20 ms of host enqueue work per 24 ms cfg3 step, so any slow host moment
+    # starves the GPU (and, data-parallel, every other rank with it).
     gstep = None
     if want_graph:
         import mdeical_image_segmentation_b200 as B
@@ -516,7 +517,7 @@ def bench_config(name, w, batch, world):
             "l2": "per-step inputs + activations far exceed the 126 MB L2 (no flush needed)",
             "streams": "weight gradients on a side stream in the timed steps; the roofline / "
                        "breakdown step runs single-stream and eager",
-            "launch": "N = 1: the whole step is one CUDA-graph replay (GraphedTrainStep); N > 1: eager steps",
+            "launch": "the whole step is one CUDA-graph replay per rank (GraphedTrainStep), NCCL all-reduces inside",
             "reference_sample": REFERENCE_SAMPLE[w["kind"]]}
 
 
@@ -802,7 +803,7 @@ def main():
     ap.add_argument("--batch", type=int, default=0)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-graph", dest="graph", action="store_false",
-                    help="time eager steps at N=1 too (default: one CUDA-graph replay per step at N=1)")
+                    help="time eager steps (default: one CUDA-graph replay per step, at every N)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup

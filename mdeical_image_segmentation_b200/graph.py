@@ -57,8 +57,11 @@ class GraphedTrainStep:
     (SURVEY.md section 8b), the weight-gradient side stream forks and joins with events, accumulators come from
     in-graph memsets, and the filter packs are rebuilt from the fp32 masters inside the graph — so the whole step
     captures as is and replays honour the optimizer's updates.  Inputs must keep the example's shapes and dtypes;
-    the optimizer must be capturable (``capturable=True`` for Adam / AdamW).  Single-process use: the
-    data-parallel reducer's NCCL hand-over is not captured (``DataParallelUNet`` models run eagerly)."""
+    the optimizer must be capturable (``capturable=True`` for Adam / AdamW).  Under ``DataParallelUNet`` the
+    bucketed NCCL all-reduces of the gradient reducer are captured with the step (its communication stream joins
+    the capture through the events it already waits on); every rank must build and replay its graph in step, and
+    drop it (``del step``) before ``destroy_process_group()`` — a live graph that holds NCCL work keeps the
+    communicator from shutting down."""
 
     def __init__(self, loss_fn, optimizer: torch.optim.Optimizer, example_inputs, warmup: int = 3):
         example_inputs = tuple(example_inputs)

@@ -185,8 +185,33 @@ def _ddp_worker(rank, world, port, q):
     t = (torch.rand((1, 1, 16, 16, 16), generator=g) > 0.6).float().cuda()
     B.BCEDiceLoss(1.0, 1.0)(net(x), t).backward()
     torch.cuda.synchronize()
-    q.put((rank, {k: v.detach().cpu().numpy() for k, v in net.state_dict().items()},
-           {k: p.grad.cpu().numpy() for k, p in net.named_parameters()}, x.cpu().numpy(), t.cpu().numpy()))
+    first = (rank, {k: v.detach().cpu().numpy() for k, v in net.state_dict().items()},
+             {k: p.grad.cpu().numpy() for k, p in net.named_parameters()}, x.cpu().numpy(), t.cpu().numpy())
+    # the same data-parallel step captured as ONE CUDA graph (GraphedTrainStep): the bucketed all-reduces sit inside
+    # the graph; after three replays on rank-specific inputs every rank must hold bit-identical parameters, equal
+    # to three eager steps from the same state up to atomics order
+    crit = B.BCEDiceLoss(1.0, 1.0)
+    start = {k: v.clone() for k, v in net.state_dict().items()}
+    opt = torch.optim.SGD(net.parameters(), lr=0.05)
+    net.zero_grad(set_to_none=True)
+    for _ in range(3):
+        opt.zero_grad(set_to_none=True)
+        crit(net(x), t).backward()
+        opt.step()
+    eager = torch.cat([p.detach().flatten() for p in net.parameters()]).clone()
+    net.load_state_dict(start)
+    opt = torch.optim.SGD(net.parameters(), lr=0.05)
+    step = B.GraphedTrainStep(lambda a, b: crit(net(a), b), opt, (x, t))
+    net.load_state_dict(start)                    # the warm-up steps moved the parameters
+    for _ in range(3):
+        step(x, t)
+    torch.cuda.synchronize()
+    graphed = torch.cat([p.detach().flatten() for p in net.parameters()])
+    q.put(first + (graphed.cpu().numpy(), float(((graphed - eager).norm() / eager.norm()).item())))
+    del step                      # a live graph that holds NCCL work keeps destroy_process_group() from returning
+    import gc
+    gc.collect()
+    torch.cuda.synchronize()
     dist.barrier()
     dist.destroy_process_group()
 
@@ -203,8 +228,14 @@ def test_two_gpu_gradients_are_the_rank_mean(B):
     got = sorted([q.get(timeout=300) for _ in range(2)], key=lambda t: t[0])
     for p in procs:
         p.join(timeout=60)
-        assert p.exitcode == 0
-    (_, sd0, g0, x0, t0), (_, sd1, g1, x1, t1) = got
+    codes = [p.exitcode for p in procs]
+    for p in procs:
+        if p.exitcode is None:
+            p.kill()              # never leave a rank behind on the GPU box
+    assert codes == [0, 0], codes
+    (_, sd0, g0, x0, t0, gp0, ge0), (_, sd1, g1, x1, t1, gp1, ge1) = got
+    assert (gp0 == gp1).all()                                       # graphed data-parallel steps keep ranks in sync
+    assert ge0 < 1e-3 and ge1 < 1e-3, (ge0, ge1)                    # ... and equal the eager data-parallel steps
     for k in sd0:
         assert (sd0[k] == sd1[k]).all(), k                           # weights broadcast from rank 0
     for k in g0:
