@@ -407,6 +407,12 @@ def measure(args, name, w, steps, warmup, device, world, rank, full):
         res["e2e"] = {"value": world * batch / (ems.item() / steps / 1e3), "unit": w["unit"],
                       "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4}
 
+    # the graph's private pool holds one full set of activations: release it before the eager instrumented steps
+    # allocate theirs (UNet 3+ at 512^2 x 8 would not fit three sets in 180 GB)
+    if gstep is not None:
+        loss = gstep = one_step = None      # (the static loss tensor lives in the graph's pool too)
+        release_device_memory()
+
     # ---- roofline: five instrumented steps (averaged) with per-call CUDA events on the launching stream.
     # Every rank runs it (its backward contains the gradient all-reduce, so a rank-0-only step would wait
     # for peers forever); only rank 0 records and reports.  Per-kernel times must not include the contention

@@ -81,6 +81,9 @@ class GraphedTrainStep:
         torch.cuda.synchronize(device)
         from . import _lib
         optimizer.zero_grad(set_to_none=True)
+        # the warm-up activations were cached for the side stream; hand them back before the capture takes the same
+        # amount again for its private pool (UNet 3+ at 512^2 x 8: ~45 GB per copy)
+        torch.cuda.empty_cache()
         self.graph = torch.cuda.CUDAGraph()
         before = _lib.launch_count
         # capture on the warm-up stream: the parameters' AccumulateGrad nodes were created there (autograd warns when

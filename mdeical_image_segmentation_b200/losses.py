@@ -175,6 +175,19 @@ class F1Loss(nn.Module):
         return (1 - 2 * (precision * recall) / (precision + recall + self.epsilon)).float()
 
 
+_CONSTS: dict = {}
+
+
+def _device_const(key, device, dtype, make) -> torch.Tensor:
+    """Small constant tensors live on the device once per (key, device): a host -> device copy in every step costs a
+    blocking transfer and cannot sit inside a CUDA-graph capture (GraphedTrainStep)."""
+    k = (key, device, dtype)
+    t = _CONSTS.get(k)
+    if t is None:
+        t = _CONSTS[k] = torch.tensor(make(), dtype=dtype, device=device)
+    return t
+
+
 class _MSSSIMMeans(torch.autograd.Function):
     """(5, n) per-sample means of the MS-SSIM scale maps of (sigmoid(logits), targets)."""
 
@@ -185,8 +198,8 @@ class _MSSSIMMeans(torch.autograd.Function):
         sums, pyr_x, pyr_y = ops.msssim_fwd(logits, targets, data_range)
         ctx.save_for_backward(pyr_x, pyr_y)
         ctx.shape, ctx.data_range = tuple(logits.shape), data_range
-        counts = torch.tensor(ops.msssim_valid_counts(logits.shape[2], logits.shape[3]), dtype=torch.float64)
-        return (sums / counts.to(sums.device)[:, None]).float()
+        return (sums / _device_const(("counts", logits.shape[2], logits.shape[3]), sums.device, torch.float64,
+                                     lambda: ops.msssim_valid_counts(logits.shape[2], logits.shape[3]))[:, None]).float()
 
     @staticmethod
     def backward(ctx, gmeans):
@@ -211,7 +224,7 @@ class MSSSIMLoss(nn.Module):
         if inputs.shape != targets.shape:
             raise ValueError("Input images should have the same dimensions.")
         means = _MSSSIMMeans.apply(inputs, targets, self.data_range)          # (5, n)
-        weights = means.new_tensor(MS_SSIM_WEIGHTS).view(-1, 1)
+        weights = _device_const("weights", means.device, means.dtype, lambda: MS_SSIM_WEIGHTS).view(-1, 1)
         ms_ssim_val = torch.prod(torch.relu(means) ** weights, dim=0)
         return 1 - ms_ssim_val.mean()
 
