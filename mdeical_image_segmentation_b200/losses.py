@@ -225,7 +225,10 @@ class MSSSIMLoss(nn.Module):
             raise ValueError("Input images should have the same dimensions.")
         means = _MSSSIMMeans.apply(inputs, targets, self.data_range)          # (5, n)
         weights = _device_const("weights", means.device, means.dtype, lambda: MS_SSIM_WEIGHTS).view(-1, 1)
-        ms_ssim_val = torch.prod(torch.relu(means) ** weights, dim=0)
+        # product over the five scales written out: torch.prod's backward inspects its input for zeros on the host
+        # (a device -> host sync in every step, and it invalidates a CUDA-graph capture of the step)
+        v = torch.relu(means) ** weights
+        ms_ssim_val = v[0] * v[1] * v[2] * v[3] * v[4]
         return 1 - ms_ssim_val.mean()
 
 
