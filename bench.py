@@ -330,6 +330,14 @@ def measure(args, name, w, steps, warmup, device, world, rank, full):
                   file=sys.stderr)
             gstep = None
             torch.cuda.synchronize()
+    if want_graph and world > 1:
+        # every rank replays a graph or none does: the all-reduces of an eager rank would not pair with a peer's replay
+        ok = torch.tensor([1.0 if gstep is not None else 0.0], device=device)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if ok.item() < 1.0 and gstep is not None:
+            gstep = None
+            x, y = x.clone(), y.clone()
+            release_device_memory()
     one_step = gstep if gstep is not None else eager_step
 
     def barrier():
