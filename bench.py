@@ -449,19 +449,29 @@ def measure(args, name, w, steps, warmup, device, world, rank, full):
         if top[1]["flops"] > 0:
             traffic, tsrc = traffic_for(name, top[0])
             ach = top[1]["flops"] / top[1]["ms"] / 1e9
+            # Which measured peak the kernel is held against follows the clock it was timed at: the instrumented
+            # steps are eager with an event pair around every call, the GPU idles between kernels and — under the
+            # same 1 kW cap — runs them near the maximum SM clock, i.e. in the regime of the BURST cuBLAS figure
+            # (the sustained one was taken at a median 1.32 GHz, MEASURED_PEAKS.json).  Below 90 % of the maximum
+            # clock the sustained figure applies.
+            pc = prof_clocks.summary()
+            burst = bool(pc["sm_mhz"] and pc["sm_max_mhz"] and pc["sm_mhz"] >= 0.9 * pc["sm_max_mhz"])
+            peak = pk["tf_burst"] if burst else pk["tf_sustained"]
             res["roofline"] = {
                 "kernel": top[0], "bound": "tensor", "achieved": round(ach, 1),
-                "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": round(ach / pk["tf_sustained"], 4),
+                "peak": peak, "unit": "TFLOP/s", "frac": round(ach / peak, 4),
+                "frac_of_sustained": round(ach / pk["tf_sustained"], 4), "frac_of_burst": round(ach / pk["tf_burst"], 4),
                 "traffic": traffic,
                 "traffic_unit": "DRAM bytes per launch",
                 "traffic_source": None if tsrc is None else
                 f"STATIC: one ncu pass of this workload committed as {tsrc}; not measured in this run",
                 "algorithmic_flop_per_launch": round(top[1]["flops"] / top[1]["launches"]),
-                "peak_source": pk["source"] + " (sustained cuBLAS bf16)",
+                "peak_source": pk["source"] + (" (burst cuBLAS bf16: kernels timed at %s of %s MHz)" % (pc["sm_mhz"], pc["sm_max_mhz"])
+                                               if burst else " (sustained cuBLAS bf16)"),
                 "avg_launch_ms": round(top[1]["ms"] / top[1]["launches"], 4),
                 # the instrumented steps are eager, single-stream, with an event pair around every call: the GPU
                 # draws less power than in the timed steps and clocks higher under the same cap — compare
-                "sm_mhz_instrumented": prof_clocks.summary()["sm_mhz"], "sm_mhz_timed": clocks.summary()["sm_mhz"],
+                "sm_mhz_instrumented": pc["sm_mhz"], "sm_mhz_timed": clocks.summary()["sm_mhz"],
                 "instrumented_step_ms": round(total_ms, 3)}
         breakdown["_step"] = res["step"]
         res["breakdown"] = breakdown
