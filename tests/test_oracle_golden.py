@@ -237,6 +237,47 @@ def test_msssim_oracle_known_answers():
     assert M.msssim_loss(40 * (t - 0.5), t).item() < 1e-6
 
 
+def test_msssim_oracle_vs_independent_float64_numpy():
+    """A second, independent restatement (numpy / scipy, float64, dense loops over the five scales) of the published
+    multi-scale SSIM with pytorch-msssim's conventions — valid 11-tap Gaussian (sigma 1.5), K = (0.01, 0.03), 2 x 2
+    average pooling with zero padding of odd sizes counted in the divisor, cs of scales 0-3 and ssim of scale 4 raised
+    to the weights — must agree with oracle/msssim.py on odd and even image sizes."""
+    import numpy as np
+    from scipy.ndimage import correlate1d
+    from oracle import msssim as M
+
+    def blur(a):
+        k = np.exp(-((np.arange(11) - 5.0) ** 2) / (2 * 1.5 ** 2))
+        k /= k.sum()
+        a = correlate1d(a, k, axis=0, mode="constant")[5:-5]
+        return correlate1d(a, k, axis=1, mode="constant")[:, 5:-5]
+
+    def pool(a):
+        h, w = a.shape
+        a = np.pad(a, ((h % 2, h % 2), (w % 2, w % 2)))              # F.avg_pool2d(padding = size % 2), zeros counted
+        h2, w2 = a.shape[0] // 2, a.shape[1] // 2
+        return a[:2 * h2, :2 * w2].reshape(h2, 2, w2, 2).mean(axis=(1, 3))
+
+    def ms_ssim(x, y):
+        vals = []
+        for lvl in range(5):
+            mu1, mu2 = blur(x), blur(y)
+            s1, s2, s12 = blur(x * x) - mu1 ** 2, blur(y * y) - mu2 ** 2, blur(x * y) - mu1 * mu2
+            cs = (2 * s12 + 0.03 ** 2) / (s1 + s2 + 0.03 ** 2)
+            ssim = (2 * mu1 * mu2 + 0.01 ** 2) / (mu1 ** 2 + mu2 ** 2 + 0.01 ** 2) * cs
+            vals.append(max(cs.mean(), 0.0) if lvl < 4 else max(ssim.mean(), 0.0))
+            x, y = pool(x), pool(y)
+        return float(np.prod(np.array(vals) ** np.array(M.WEIGHTS)))
+
+    rng = np.random.default_rng(3)
+    for shape in ((176, 192), (177, 201), (256, 163)):
+        x = rng.random(shape)
+        y = np.clip(x + 0.3 * rng.standard_normal(shape), 0, 1)
+        want = ms_ssim(x, y)
+        got = M.ms_ssim(torch.from_numpy(x)[None, None], torch.from_numpy(y)[None, None], size_average=True).item()
+        assert abs(got - want) < 5e-6, (shape, got, want)      # the package (and the oracle) build the window in fp32
+
+
 def test_unet3plus_cgm_matches_reference():
     """UNet_3Plus_DeepSup_CGM (unet.py:795-1153, classification dropout off): gated probabilities of the five
     scales, BCE loss, gradient norms (the cls convolution receives none: arg-max) against the reference's run."""
