@@ -9,6 +9,8 @@ input shape and replayed with one launch.  Weights are re-packed from the fp32 m
 """
 from __future__ import annotations
 
+import os
+
 import torch
 
 
@@ -92,10 +94,16 @@ class GraphedTrainStep:
             torch.autograd.graph.set_warn_on_accumulate_grad_stream_mismatch(False)
         except AttributeError:
             pass
-        with torch.cuda.graph(self.graph, stream=side):
-            self.static_loss = loss_fn(*self.static_in)
-            self.static_loss.backward()
-            optimizer.step()
+        from . import ops
+        if os.environ.get("B200_GRAPH_ZERO_POOL", "1") != "0":      # A/B knob
+            ops._ZEROS.begin_capture()      # small accumulators: a few in-graph memsets instead of ~100
+        try:
+            with torch.cuda.graph(self.graph, stream=side):
+                self.static_loss = loss_fn(*self.static_in)
+                self.static_loss.backward()
+                optimizer.step()
+        finally:
+            ops._ZEROS.end_capture()
         self.launches_per_step = _lib.launch_count - before     # C-ABI kernel launches inside one replay
 
     def __call__(self, *inputs: torch.Tensor) -> torch.Tensor:

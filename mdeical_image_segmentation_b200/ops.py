@@ -57,24 +57,35 @@ class _ZeroPool:
 
     def __init__(self):
         self.cur = {}          # (device, stream, dtype) -> [chunk, offset]
+        self.capture = None    # chunks of the CUDA-graph capture in progress (graph.GraphedTrainStep), else None
+
+    def begin_capture(self) -> None:
+        """Inside a capture the chunks (and the memsets that zero them) belong to the graph: they are created
+        during the capture, re-zeroed by every replay, and never handed out again once the capture has ended."""
+        self.capture = {}
+
+    def end_capture(self) -> None:
+        self.capture = None
 
     def take(self, shape, dtype, device) -> torch.Tensor:
         numel = 1
         for v in shape:
             numel *= int(v)
         item = torch.empty((), dtype=dtype).element_size()
-        if numel * item > self.MAX_TAKE or torch.cuda.is_current_stream_capturing():
+        capturing = torch.cuda.is_current_stream_capturing()
+        if numel * item > self.MAX_TAKE or (capturing and self.capture is None):
             return torch.zeros(shape, dtype=dtype, device=device)
+        pool = self.capture if capturing else self.cur
         dev = torch.device(device)
         # one chunk per (device, STREAM, dtype): a region must be zero in the stream that accumulates into it, and
         # the chunk's fill was enqueued on the stream that allocated it
         key = (dev.index if dev.index is not None else torch.cuda.current_device(),
                torch.cuda.current_stream().cuda_stream, dtype)
         padded = (numel * item + 255) // 256 * 256 // item         # regions stay 256-byte aligned
-        ent = self.cur.get(key)
+        ent = pool.get(key)
         if ent is None or ent[1] + padded > ent[0].numel():
             ent = [torch.zeros(self.CHUNK_BYTES // item, dtype=dtype, device=device), 0]
-            self.cur[key] = ent
+            pool[key] = ent
         out = ent[0][ent[1]:ent[1] + numel].view(shape)
         ent[1] += padded
         return out
