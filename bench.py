@@ -11,6 +11,12 @@ gradient all-reduce overlaps backward (mdeical_image_segmentation_b200/parallel.
 Default workload = cfg3 (the north-star configuration: UNet3D(1,1) gcr + nearest, 128^3, batch 2 per GPU);
 the same line carries short device-resident measurements of cfg2 and cfg3p under "extra".
 
+The timed steps are replays of ONE CUDA graph per rank holding the whole step (GraphedTrainStep, the package's public
+API for a fixed-shape training loop; the NCCL all-reduces are inside the graph at N > 1) -- "step_launch" in the JSON
+line says so, --no-graph times the eager loop.  The roofline / breakdown steps are eager with CUDA events around every
+library call; "roofline" names the SM clock of both regimes and is held against the cuBLAS peak of the regime its
+kernels were timed in.
+
 `--impl reference` times the reference's own CPU implementation of the same path on all host threads: the
 UNMODIFIED reference modules from oracle/_ref (a copy of the path's files made by oracle/build_ref.py in the
 build container; git-ignored, travels with the snapshot) -- "kind": "reference" -- or, when oracle/_ref is
