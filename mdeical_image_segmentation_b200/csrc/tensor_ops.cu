@@ -983,6 +983,61 @@ __global__ void __launch_bounds__(256)
     for (int v = KV; v < kv; ++v) dst[v] = make_uint4(0, 0, 0, 0);
   }
 }
+// K' = 64 (the 3-D one-channel first layer with its ones column: 128 bytes per position).  Same values, but a warp's
+// 32 rows go through shared memory so that every store instruction writes one contiguous 512-byte run — a thread
+// storing its own row writes 32 scattered 16-byte pieces per instruction (2.1 TB/s).  16-byte slots are XOR-swizzled
+// by the row index: conflict-free both ways.
+template <int KD, int CREAL, int ONES>
+__global__ void __launch_bounds__(256)
+    im2col3_k64_kernel(int n, int d, int h, int w, View x, bf16* __restrict__ a) {
+  constexpr int CIN = CREAL + ONES;
+  constexpr int NT = KD * 9, KR = NT * CIN;
+  static_assert(KR <= 64, "one 128-byte row per position");
+  __shared__ uint4 stage[8][32 * 8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long total = (long)n * d * h * w;
+  const long nwarp_rows = (total + 31) / 32;
+  for (long wr = (long)blockIdx.x * 8 + warp; wr < nwarp_rows; wr += (long)gridDim.x * 8) {
+    const long pos = wr * 32 + lane;
+    unsigned short e[64];
+#pragma unroll
+    for (int k = 0; k < 64; ++k) e[k] = 0;
+    if (pos < total) {
+      long r = pos;
+      const int xw = (int)(r % w); r /= w;
+      const int xh = (int)(r % h); r /= h;
+      const int xd = (int)(r % d); r /= d;
+      const long b = r;
+#pragma unroll
+      for (int tap = 0; tap < NT; ++tap) {
+        const int kwi = tap % 3, khi = (tap / 3) % 3, kdi = tap / 9;
+        const int zd = xd + kdi - (KD >> 1), zh = xh + khi - 1, zw = xw + kwi - 1;
+        const bool ok = zd >= 0 && zd < d && zh >= 0 && zh < h && zw >= 0 && zw < w;
+        const unsigned short* src =
+            reinterpret_cast<const unsigned short*>(x.at(ok ? ((b * d + zd) * h + zh) * w + zw : pos, 0));
+#pragma unroll
+        for (int ci = 0; ci < CREAL; ++ci) e[tap * CIN + ci] = ok ? src[ci] : (unsigned short)0;
+        if (ONES) e[tap * CIN + CREAL] = ok ? (unsigned short)0x3F80 : (unsigned short)0;   // bf16 1.0
+      }
+    }
+#pragma unroll
+    for (int v = 0; v < 8; ++v) {
+      uint4 o;
+      o.x = e[8 * v] | ((uint32_t)e[8 * v + 1] << 16); o.y = e[8 * v + 2] | ((uint32_t)e[8 * v + 3] << 16);
+      o.z = e[8 * v + 4] | ((uint32_t)e[8 * v + 5] << 16); o.w = e[8 * v + 6] | ((uint32_t)e[8 * v + 7] << 16);
+      stage[warp][lane * 8 + (v ^ (lane & 7))] = o;
+    }
+    __syncwarp();
+    uint4* dst = reinterpret_cast<uint4*>(a) + wr * 32 * 8;
+    const long vec_left = (total - wr * 32) * 8;           // vectors of this warp's rows that exist
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int idx = j * 32 + lane, p = idx >> 3, v = idx & 7;
+      if (idx < vec_left) dst[idx] = stage[warp][p * 8 + (v ^ (p & 7))];
+    }
+    __syncwarp();
+  }
+}
 // ------------------------------------------------------------------------------------ affine streams
 // y = relu?(x * sc[ch] + sh[ch]) and dx = a[ch] * g + b[ch] * x + c0[ch] (g = dy, masked by y > 0):
 // every normalisation forward / backward "apply" pass of the path has this form once the per-channel
@@ -1930,7 +1985,11 @@ int b200_im2col3(int32_t n, int32_t d, int32_t h, int32_t w, int32_t c_in, int32
   if (c_in > 4 || kd * 9 * c_in > 64) return B200_ERR_UNSUPPORTED;
 #define IM2COL(KD, CIN) im2col3_kernel<KD, CIN><<<GRID1D(total), 256, 0, (cudaStream_t)stream>>>(n, d, h, w, kp, mk(x), (bf16*)a)
   if (ones) {
-    if (kd == 3 && c_in == 2) im2col3_kernel<3, 1, 1><<<GRID1D(total), 256, 0, (cudaStream_t)stream>>>(n, d, h, w, kp, mk(x), (bf16*)a);
+    if (kd == 3 && c_in == 2 && kp == 64) {
+      const long blocks = (total + 255) / 256;
+      im2col3_k64_kernel<3, 1, 1><<<(unsigned)(blocks < 148L * 16 ? blocks : 148L * 16), 256, 0, (cudaStream_t)stream>>>(
+          n, d, h, w, mk(x), (bf16*)a);
+    } else if (kd == 3 && c_in == 2) im2col3_kernel<3, 1, 1><<<GRID1D(total), 256, 0, (cudaStream_t)stream>>>(n, d, h, w, kp, mk(x), (bf16*)a);
     else if (kd == 1 && c_in == 2) im2col3_kernel<1, 1, 1><<<GRID1D(total), 256, 0, (cudaStream_t)stream>>>(n, d, h, w, kp, mk(x), (bf16*)a);
     else return B200_ERR_UNSUPPORTED;
     B200_LAUNCH_CHECK();

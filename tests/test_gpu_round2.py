@@ -854,3 +854,28 @@ def test_graphed_train_step_matches_eager_steps(B):
     assert rel_l2(pg.cpu(), pe.cpu()) < 2e-3
     with pytest.raises(ValueError):
         step(xs[0][:1], ys[0][:1])
+
+
+@pytest.mark.parametrize("shape,kd,ones", [((2, 1, 6, 9, 11), 3, True), ((1, 2, 5, 8, 8), 3, False),
+                                            ((2, 3, 1, 12, 10), 1, False), ((1, 1, 1, 9, 16), 1, True),
+                                            ((1, 4, 1, 8, 8), 1, False)])
+def test_im2col_of_the_narrow_input_vs_torch(B, shape, kd, ones):
+    """b200_im2col3: a[pos][tap * c + ci] = x[pos + tap][ci] (zero outside the volume), the optional synthesised
+    ones column = 1 where the tap is inside, zero padding up to K' — bit-exact against a torch construction."""
+    from mdeical_image_segmentation_b200 import ops
+    n, c, d, h, w = shape
+    g = torch.Generator().manual_seed(sum(shape))
+    x = torch.randn(shape, generator=g).bfloat16().float()
+    xcl = ops.from_nchw(x.cuda(), pad=True)
+    cin = c + (1 if ones else 0)
+    taps = kd * 9
+    kp = (taps * cin + 15) // 16 * 16
+    a = ops.im2col(ops.CL(xcl.buf, c, 0, xcl.buf.shape[4] - c), kd, kp, ones=ones).dense().float().cpu()
+    src = torch.cat([x, torch.ones((n, 1, d, h, w))], 1) if ones else x
+    pd = kd // 2
+    xp = F.pad(src, (1, 1, 1, 1, pd, pd))
+    want = torch.zeros((n, d, h, w, kp))
+    for t in range(taps):
+        kw_, kh_, kd_ = t % 3, (t // 3) % 3, t // 9
+        want[..., t * cin:(t + 1) * cin] = xp[:, :, kd_:kd_ + d, kh_:kh_ + h, kw_:kw_ + w].permute(0, 2, 3, 4, 1)
+    assert torch.equal(a, want), (shape, (a - want).abs().max())
