@@ -70,6 +70,7 @@ __global__ void __launch_bounds__(256, 2)
   __shared__ float s_in[kHZ][kHY][kHX];
   __shared__ __align__(16) float s_w[27][C];
   __shared__ float s_stat[2][C];
+  __shared__ uint4 s_out[8][32 * 4];
   int t = blockIdx.x;
   const int tx = t % tiles_x; t /= tiles_x;
   const int ty = t % tiles_y; t /= tiles_y;
@@ -139,11 +140,22 @@ __global__ void __launch_bounds__(256, 2)
           }
         }
       }
-      if (ok) {
-        uint4* o = reinterpret_cast<uint4*>(y.at((((long)b * d + gz) * h + gy) * w + gx, 0));
+      // a thread holds the 64 bytes of its voxel; through shared memory (16-byte slots XOR-swizzled by the row) the
+      // warp's 32 x-consecutive voxels leave as four contiguous 512-byte stores instead of 4 x 32 scattered pieces
+      uint4* st = s_out[threadIdx.x >> 5];
 #pragma unroll
-        for (int q = 0; q < C / 8; ++q) o[q] = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+      for (int q = 0; q < C / 8; ++q)
+        st[lane * 4 + (q ^ (lane & 3))] = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+      __syncwarp();
+      if (gy < h && gz < d) {
+        const long row0 = (((long)b * d + gz) * h + gy) * w + x0;
+#pragma unroll
+        for (int j = 0; j < C / 8; ++j) {
+          const int idx = j * 32 + lane, pp = idx >> 2, q = idx & 3;
+          if (x0 + pp < w) *reinterpret_cast<uint4*>(y.at(row0 + pp, q * 8)) = st[pp * 4 + (q ^ (pp & 3))];
+        }
       }
+      __syncwarp();
     }
     if (stats) {
       const float t1 = warp_sum_by_channel(s1, lane);
